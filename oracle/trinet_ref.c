@@ -1,0 +1,312 @@
+/*
+ * oracle/trinet_ref.c  --  TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * Scalar CPU restatement of the piecewise-trilinear network evaluation on the
+ * reference's mesh-extraction path.  Only tests/, __graft_entry__.smoke() and
+ * bench.py's cpu_baseline / --impl reference legs may load this library; the
+ * shipped path (tropical-nerf.pytorch_b200/) never does.
+ *
+ * What it follows in the reference (/root/reference):
+ *   - Net.forward(gather=True)        tropical/stanford/model.py:52-76
+ *   - Net.preprocess / sdf            tropical/stanford/model.py:78-88
+ *   - Net.region (sign vectors)       tropical/stanford/model.py:90-103
+ *   - TropicalHashGrid.region         tropical/tropical.py:227-236
+ *   - the x-gradient autograd takes in TropicalHashGrid.skeleton
+ *     (tropical/tropical.py:190-195) and Net.normal (model.py:105-123)
+ *   - TropicalHashGrid.forward -> tcnn.Encoding (tropical/tropical.py:32-47).
+ *     tiny-cuda-nn is a third-party dependency that is NOT in the reference
+ *     tree and NOT pinned by its requirements.txt; the multiresolution hash
+ *     encoding is restated here from its published algorithm (Mueller et al.
+ *     2022, Sec. 3 + App. A; tiny-cuda-nn GridEncoding: pos = x*scale+0.5,
+ *     dense index below the table size, prime-XOR hash above it).
+ *     => the encoding itself is "parity unpinned" against real tiny-cuda-nn;
+ *     everything downstream is pinned by running the reference's own Python
+ *     on top of the same encoding (tests/golden/make_golden.py).
+ *
+ * Floating point contract (what "bit-exact" means for the CUDA path): every
+ * operation below is a single IEEE-754 binary32 operation (+, -, *, /, sqrt,
+ * fma) in exactly the written order; fmaf() marks the fused ones and the file
+ * is compiled with -ffp-contract=off so nothing else fuses.  tanh is NOT taken
+ * from libm (glibc and CUDA differ in the last ulp): det_tanhf() below is the
+ * definition, built from the same primitive operations.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <string.h>
+
+#define TN_MAX_LEVELS 16
+#define TN_MAX_WIDTH 64
+#define TN_MAX_LINEAR 8
+
+typedef struct {
+    int32_t n_levels;   /* L */
+    int32_t n_feat;     /* F (features per level) */
+    int32_t n_linear;   /* number of nn.Linear layers (= Net.num_layers) */
+    int32_t n_hidden;   /* H */
+    float pre_scale;    /* Net.scale */
+    const float *lvl_scale;    /* [L] */
+    const uint32_t *lvl_res;   /* [L] */
+    const uint32_t *lvl_size;  /* [L] table entries of the level */
+    const uint32_t *lvl_off;   /* [L] first entry of the level */
+    const float *table;        /* [sum(size) * F] */
+    const float *mlp;          /* per layer: W[out][in] row-major, then b[out] */
+} trinet_t;
+
+static int layer_in(const trinet_t *n, int i) { return i == 0 ? n->n_levels * n->n_feat : n->n_hidden; }
+static int layer_out(const trinet_t *n, int i) { return i == n->n_linear - 1 ? 2 : n->n_hidden; }
+
+int trinet_n_outputs(const trinet_t *n) { return (n->n_linear - 1) * n->n_hidden + 1; }
+
+/* ---- deterministic transcendental ------------------------------------------------ */
+static float det_expf(float y)
+{
+    float n = rintf(y * 1.44269504088896341f);
+    float r = fmaf(n, -0.693359375f, y);
+    r = fmaf(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = fmaf(p, r, 1.3981999507e-3f);
+    p = fmaf(p, r, 8.3334519073e-3f);
+    p = fmaf(p, r, 4.1665795894e-2f);
+    p = fmaf(p, r, 1.6666665459e-1f);
+    p = fmaf(p, r, 5.0000001201e-1f);
+    float e = fmaf(p, r * r, r) + 1.0f;
+    union { float f; uint32_t u; } s;
+    s.u = (uint32_t)((int32_t)n + 127) << 23;
+    return e * s.f;
+}
+
+float det_tanhf(float x)
+{
+    float ax = fabsf(x);
+    float t;
+    if (ax < 0.25f) {
+        float x2 = ax * ax;
+        float p = 0.021869488536155203f;            /* 62/2835 */
+        p = fmaf(p, x2, -0.053968253968253971f);    /* -17/315 */
+        p = fmaf(p, x2, 0.13333333333333333f);      /* 2/15 */
+        p = fmaf(p, x2, -0.33333333333333331f);     /* -1/3 */
+        t = fmaf(ax * x2, p, ax);
+    } else if (ax > 9.0f) {
+        t = 1.0f;
+    } else {
+        float e = det_expf(2.0f * ax);
+        t = 1.0f - 2.0f / (e + 1.0f);
+    }
+    return copysignf(t, x);
+}
+
+/* ---- hash grid ------------------------------------------------------------------- */
+static uint32_t grid_index(uint32_t size, uint32_t res, const uint32_t c[3])
+{
+    uint32_t stride = 1, index = 0;
+    for (int d = 0; d < 3 && stride <= size; ++d) {
+        index += c[d] * stride;
+        stride *= res;
+    }
+    if (size < stride)
+        index = (c[0] * 1u) ^ (c[1] * 2654435761u) ^ (c[2] * 805459861u);
+    return index % size;
+}
+
+typedef struct {
+    uint32_t cell[TN_MAX_LEVELS][3];
+    float frac[TN_MAX_LEVELS][3];
+} enc_ctx_t;
+
+/* xp: preprocessed point in hash-grid coordinates */
+static void encode(const trinet_t *n, const float xp[3], float *enc, enc_ctx_t *ctx)
+{
+    const int F = n->n_feat;
+    for (int l = 0; l < n->n_levels; ++l) {
+        const float scale = n->lvl_scale[l];
+        uint32_t cell[3];
+        float frac[3];
+        for (int d = 0; d < 3; ++d) {
+            float pos = fmaf(scale, xp[d], 0.5f);
+            float fl = floorf(pos);
+            cell[d] = (uint32_t)(int32_t)fl;
+            frac[d] = pos - fl;
+            if (ctx) { ctx->cell[l][d] = cell[d]; ctx->frac[l][d] = frac[d]; }
+        }
+        const float *tab = n->table + (size_t)n->lvl_off[l] * F;
+        for (int f = 0; f < F; ++f) enc[l * F + f] = 0.0f;
+        for (int corner = 0; corner < 8; ++corner) {
+            float w = 1.0f;
+            uint32_t c[3];
+            for (int d = 0; d < 3; ++d) {
+                if (corner & (1 << d)) { w = w * frac[d]; c[d] = cell[d] + 1u; }
+                else                   { w = w * (1.0f - frac[d]); c[d] = cell[d]; }
+            }
+            uint32_t idx = grid_index(n->lvl_size[l], n->lvl_res[l], c);
+            for (int f = 0; f < F; ++f)
+                enc[l * F + f] = fmaf(w, tab[(size_t)idx * F + f], enc[l * F + f]);
+        }
+    }
+}
+
+/* d enc[l*F+f] / d xp[d]  (tiny-cuda-nn kernel_grid_backward_input, linear interpolation) */
+static void encode_dx(const trinet_t *n, const enc_ctx_t *ctx, int l, int d, float *dl)
+{
+    const int F = n->n_feat;
+    const float *tab = n->table + (size_t)n->lvl_off[l] * F;
+    for (int f = 0; f < F; ++f) dl[f] = 0.0f;
+    for (int idx = 0; idx < 4; ++idx) {
+        float w = n->lvl_scale[l];
+        uint32_t c[3];
+        for (int nd = 0; nd < 2; ++nd) {
+            int dim = nd >= d ? nd + 1 : nd;
+            if (idx & (1 << nd)) { w = w * ctx->frac[l][dim]; c[dim] = ctx->cell[l][dim] + 1u; }
+            else                 { w = w * (1.0f - ctx->frac[l][dim]); c[dim] = ctx->cell[l][dim]; }
+        }
+        c[d] = ctx->cell[l][d];
+        uint32_t il = grid_index(n->lvl_size[l], n->lvl_res[l], c);
+        c[d] = ctx->cell[l][d] + 1u;
+        uint32_t ir = grid_index(n->lvl_size[l], n->lvl_res[l], c);
+        for (int f = 0; f < F; ++f)
+            dl[f] = fmaf(w, tab[(size_t)ir * F + f] - tab[(size_t)il * F + f], dl[f]);
+    }
+}
+
+void trinet_encode(const trinet_t *n, const float *xp, int64_t count, float *enc)
+{
+    const int W = n->n_levels * n->n_feat;
+    for (int64_t i = 0; i < count; ++i) encode(n, xp + 3 * i, enc + (size_t)W * i, 0);
+}
+
+/* ---- MLP ------------------------------------------------------------------------- */
+/* pre[i][j] keeps the pre-activation of layer i; returns o[2] */
+static void mlp_forward(const trinet_t *n, const float *enc, float pre[TN_MAX_LINEAR][TN_MAX_WIDTH])
+{
+    float act[TN_MAX_WIDTH];
+    const float *p = n->mlp;
+    int nin = layer_in(n, 0);
+    for (int c = 0; c < nin; ++c) act[c] = enc[c];
+    for (int i = 0; i < n->n_linear; ++i) {
+        nin = layer_in(n, i);
+        const int nout = layer_out(n, i);
+        const float *W = p, *b = p + (size_t)nout * nin;
+        for (int j = 0; j < nout; ++j) {
+            float acc = b[j];
+            for (int c = 0; c < nin; ++c) acc = fmaf(act[c], W[j * nin + c], acc);
+            pre[i][j] = acc;
+        }
+        if (i != n->n_linear - 1)
+            for (int j = 0; j < nout; ++j) act[j] = pre[i][j] > 0.0f ? pre[i][j] : 0.0f;
+        p = b + nout;
+    }
+}
+
+static void preprocess(const trinet_t *n, const float *x, float xp[3])
+{
+    for (int d = 0; d < 3; ++d) xp[d] = (x[d] + n->pre_scale) / (n->pre_scale * 2.0f);
+}
+
+/* Net.forward(gather=True)[1] concatenated: hidden pre-activations, then o1 - o0 */
+void trinet_outputs(const trinet_t *n, const float *x, int64_t count, float *out)
+{
+    const int R = trinet_n_outputs(n), H = n->n_hidden;
+    for (int64_t i = 0; i < count; ++i) {
+        float xp[3], enc[TN_MAX_LEVELS * 8], pre[TN_MAX_LINEAR][TN_MAX_WIDTH];
+        preprocess(n, x + 3 * i, xp);
+        encode(n, xp, enc, 0);
+        mlp_forward(n, enc, pre);
+        float *o = out + (size_t)R * i;
+        for (int k = 0; k < n->n_linear - 1; ++k)
+            for (int j = 0; j < H; ++j) o[k * H + j] = pre[k][j];
+        o[R - 1] = pre[n->n_linear - 1][1] - pre[n->n_linear - 1][0];
+    }
+}
+
+/* Net.sdf(x)[:,0] = tanh(o1-o0) and its gradient w.r.t. the world-space input */
+void trinet_sdf_grad(const trinet_t *n, const float *x, int64_t count, float *sdf, float *grad)
+{
+    const int F = n->n_feat;
+    for (int64_t i = 0; i < count; ++i) {
+        float xp[3], enc[TN_MAX_LEVELS * 8], pre[TN_MAX_LINEAR][TN_MAX_WIDTH];
+        enc_ctx_t ctx;
+        preprocess(n, x + 3 * i, xp);
+        encode(n, xp, enc, &ctx);
+        mlp_forward(n, enc, pre);
+        const int last = n->n_linear - 1;
+        float t = det_tanhf(pre[last][1] - pre[last][0]);
+        sdf[i] = t;
+        if (!grad) continue;
+        float gs = 1.0f - t * t;
+        float g_out[TN_MAX_WIDTH], g_in[TN_MAX_WIDTH];
+        g_out[0] = -gs; g_out[1] = gs;
+        /* locate the packed weights of each layer */
+        const float *Wp[TN_MAX_LINEAR];
+        const float *p = n->mlp;
+        for (int k = 0; k < n->n_linear; ++k) {
+            Wp[k] = p;
+            p += (size_t)layer_out(n, k) * layer_in(n, k) + layer_out(n, k);
+        }
+        for (int k = last; k >= 0; --k) {
+            const int nin = layer_in(n, k), nout = layer_out(n, k);
+            for (int c = 0; c < nin; ++c) {
+                float acc = 0.0f;
+                for (int j = 0; j < nout; ++j) acc = fmaf(Wp[k][j * nin + c], g_out[j], acc);
+                g_in[c] = acc;
+            }
+            if (k > 0)
+                for (int c = 0; c < nin; ++c) g_out[c] = pre[k - 1][c] > 0.0f ? g_in[c] : 0.0f;
+        }
+        /* g_in now holds d sdf / d enc */
+        for (int d = 0; d < 3; ++d) {
+            float acc = 0.0f;
+            for (int l = 0; l < n->n_levels; ++l) {
+                float dl[8];
+                encode_dx(n, &ctx, l, d, dl);
+                for (int f = 0; f < F; ++f) acc = fmaf(g_in[l * F + f], dl[f], acc);
+            }
+            grad[3 * i + d] = acc / (n->pre_scale * 2.0f);
+        }
+    }
+}
+
+/* |grad| exactly as the skeleton sweep defines it (max_grad = max over a chunk of this) */
+void trinet_grad_norm(const float *grad, int64_t count, float *norm)
+{
+    for (int64_t i = 0; i < count; ++i) {
+        const float *g = grad + 3 * i;
+        float s = g[0] * g[0];
+        s = fmaf(g[1], g[1], s);
+        s = fmaf(g[2], g[2], s);
+        norm[i] = sqrtf(s);
+    }
+}
+
+/* ---- region indicators ------------------------------------------------------------ */
+/* torch.searchsorted(marks, v) with right=False: first i with marks[i] >= v */
+static int32_t lower_bound(const float *marks, int32_t m, float v)
+{
+    int32_t lo = 0, hi = m;
+    while (lo < hi) {
+        int32_t mid = (lo + hi) >> 1;
+        if (marks[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+/* signs: [count][3+R] int8 = (grid mask 0/1 per axis, then -1/0/+1 per neuron);
+ * offset: [count][3] int32 (can be -1, tropical.py:231) */
+void trinet_region(const trinet_t *n, const float *marks, int32_t n_marks, float eps,
+                   const float *x, const float *outputs, int64_t count,
+                   int8_t *signs, int32_t *offset)
+{
+    const int R = trinet_n_outputs(n);
+    for (int64_t i = 0; i < count; ++i) {
+        float xp[3];
+        preprocess(n, x + 3 * i, xp);
+        int8_t *s = signs + (size_t)(3 + R) * i;
+        for (int d = 0; d < 3; ++d) {
+            int32_t off = lower_bound(marks, n_marks, xp[d] + eps) - 1;
+            float mk = marks[off < 0 ? off + n_marks : off];
+            s[d] = fabsf(mk - xp[d]) > eps ? 1 : 0;
+            offset[3 * i + d] = off;
+        }
+        const float *o = outputs + (size_t)R * i;
+        for (int c = 0; c < R; ++c)
+            s[3 + c] = fabsf(o[c]) <= eps ? 0 : (o[c] > 0.0f ? 1 : -1);
+    }
+}
