@@ -1,0 +1,161 @@
+/*
+ * tropical_b200.h -- C ABI of the B200-native polyhedral-complex mesh extractor.
+ *
+ * Drop-in boundary for the reference's mesh-extraction path.  The reference is pure
+ * Python over torch + tiny-cuda-nn; each entry point below names the reference
+ * function (file:line under the reference tree) whose work it replaces.  Plain
+ * pointers and sizes only; no torch types.  Pointers prefixed d_ are CUDA device
+ * pointers, h_ are host pointers.  `stream` is a cudaStream_t passed as void*
+ * (NULL = the legacy default stream).  Every function returns TNB_OK (0) or a
+ * negative TNB_ERR_* code; tnb_last_error() gives the message of the last failure on
+ * the calling thread.
+ *
+ * There is no CPU implementation behind this interface: without a CUDA device every
+ * compute entry point returns TNB_ERR_CUDA.
+ */
+#ifndef TROPICAL_B200_H
+#define TROPICAL_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TNB_OK 0
+#define TNB_ERR_INVALID (-1)   /* bad argument / unsupported configuration */
+#define TNB_ERR_CUDA (-2)      /* CUDA runtime error (no device, launch failure, ...) */
+#define TNB_ERR_CAPACITY (-3)  /* device work buffers too small; raise capacity and retry */
+#define TNB_ERR_UNSUPPORTED (-4)
+
+#define TNB_MAX_LEVELS 16
+#define TNB_MAX_LINEAR 8
+#define TNB_MAX_HIDDEN 64
+
+/* Host-side description of one trilinear network = the state of the reference's
+ * `Net` (tropical/stanford/model.py:18-50) and its `TropicalHashGrid`
+ * (tropical/tropical.py:20-44).  All arrays are host pointers, copied at create. */
+typedef struct tnb_net_desc {
+    int32_t n_levels;         /* L  (tropical.py:21)                                   */
+    int32_t n_features;       /* F, must be 2 (model.py:32)                            */
+    int32_t log2_hashmap;     /* T                                                     */
+    int32_t base_resolution;  /* N_min                                                 */
+    double per_level_scale;   /* b  (tropical.py:31)                                   */
+    int32_t num_layers;       /* number of nn.Linear layers (model.py:39-50)           */
+    int32_t num_hidden;       /* H                                                     */
+    float scale;              /* Net.scale (model.py:34)                               */
+    float eps;                /* Net.eps                                               */
+    const float *table;       /* tcnn params, [sum(level sizes) * F]                   */
+    int64_t table_len;        /* number of floats in `table` (checked)                 */
+    const float *mlp;         /* per layer: weight [out][in] row-major, then bias      */
+    int64_t mlp_len;
+    const float *marks;       /* TropicalHashGrid.marks (tropical.py:49-79)            */
+    int32_t n_marks;
+} tnb_net_desc;
+
+typedef struct tnb_net tnb_net;          /* device-resident network                    */
+typedef struct tnb_complex tnb_complex;  /* device-resident vertices/edges/outputs     */
+typedef struct tnb_mesh tnb_mesh;        /* device-resident extracted surface mesh     */
+
+const char *tnb_last_error(void);
+int tnb_version(void);
+int tnb_device_count(void);
+
+/* ---- network ------------------------------------------------------------------ */
+int tnb_net_create(const tnb_net_desc *desc, tnb_net **out);
+void tnb_net_destroy(tnb_net *net);
+int tnb_net_num_outputs(const tnb_net *net); /* R = (num_layers-1)*H + 1 */
+/* per-level layout tiny-cuda-nn derives; arrays of n_levels entries (host) */
+int tnb_net_level_layout(const tnb_net *net, float *scale, uint32_t *res, uint32_t *size,
+                         uint32_t *offset);
+
+/* TropicalHashGrid.forward (tropical.py:46-47 -> tcnn.Encoding): d_xp [n,3] in grid
+ * coordinates -> d_enc [n, L*F] */
+int tnb_grid_encode(const tnb_net *net, const float *d_xp, int64_t n, float *d_enc, void *stream);
+
+/* torch.cat(Net.forward(x, gather=True)[1], -1) (model.py:52-76): d_x [n,3] world
+ * coordinates -> d_out [n,R] hidden pre-activations then (o1 - o0) */
+int tnb_net_outputs(const tnb_net *net, const float *d_x, int64_t n, float *d_out, void *stream);
+
+/* Net.sdf(x)[:,0] (model.py:84-88) and d sdf / d x as autograd returns it in
+ * TropicalHashGrid.skeleton (tropical.py:190-195) / Net.normal (model.py:105-123).
+ * d_grad may be NULL. */
+int tnb_net_sdf_grad(const tnb_net *net, const float *d_x, int64_t n, float *d_sdf,
+                     float *d_grad, void *stream);
+
+/* Net.region (model.py:90-103) + TropicalHashGrid.region (tropical.py:227-236).
+ * d_outputs may be NULL (then evaluated).  d_signs [n, 3+R] int8: grid masks 0/1 then
+ * neuron signs -1/0/+1.  d_offset [n,3] int32.  Either output may be NULL.
+ * d_packed (optional) [n,3] uint64: {positive-sign bits, negative-sign bits, grid word}
+ * -- the bit-packed form the subdivision kernels use. */
+int tnb_net_region(const tnb_net *net, const float *d_x, const float *d_outputs, int64_t n,
+                   float eps, int8_t *d_signs, int32_t *d_offset, uint64_t *d_packed,
+                   void *stream);
+
+/* Evaluation sweep over a dense lattice (BASELINE config "batched trilinear network
+ * eval + sign-vector sweep"): points lo + (hi-lo)*i/(n-1) per axis, z fastest;
+ * writes the packed sign vector of every lattice point, d_packed [nx*ny*nz, 2] uint64
+ * {positive bits, negative bits} (zero = neither). */
+int tnb_sweep_signs(const tnb_net *net, const float lo[3], const float hi[3], const int32_t n[3],
+                    float eps, uint64_t *d_packed, void *stream);
+
+/* ---- polyhedral complex -------------------------------------------------------- */
+/* TropicalHashGrid.skeleton(net, unit) (tropical.py:158-225, distance pruning).  When
+ * no grid edge survives, the hypercube of subpoly.py:51-52 / :731-750 with half-size
+ * `size` is returned instead (what subpoly() does next). */
+int tnb_skeleton(const tnb_net *net, int32_t unit, float size, tnb_complex **out, void *stream);
+/* Build a complex from caller arrays (device pointers): vertices [V,3] f32, edges
+ * [E,2] i64.  Outputs are evaluated. */
+int tnb_complex_from_arrays(const tnb_net *net, const float *d_vertices, int64_t V,
+                            const int64_t *d_edges, int64_t E, tnb_complex **out, void *stream);
+void tnb_complex_destroy(tnb_complex *c);
+int64_t tnb_complex_num_vertices(const tnb_complex *c);
+int64_t tnb_complex_num_edges(const tnb_complex *c);
+/* copy out to device buffers (any may be NULL): vertices [V,3] f32, edges [E,2] i64,
+ * outputs [V,R] f32 */
+int tnb_complex_read(const tnb_complex *c, float *d_vertices, int64_t *d_edges, float *d_outputs,
+                     void *stream);
+
+/* subpoly_(vertices, edges, net, l, h, eps, outputs, force=...) (subpoly.py:90-279):
+ * subdivide every edge the hyperplane of neuron (l,h) crosses, connect the new
+ * vertices, prune.  force != 0 is the planar path (reference default). */
+int tnb_subpoly_step(const tnb_net *net, tnb_complex *c, int32_t l, int32_t h, float eps,
+                     int32_t force, void *stream);
+
+/* extract_skeleton + extract_faces (subpoly.py:556-652). */
+int tnb_extract_mesh(const tnb_net *net, const tnb_complex *c, float eps, tnb_mesh **out,
+                     void *stream);
+void tnb_mesh_destroy(tnb_mesh *m);
+int64_t tnb_mesh_num_vertices(const tnb_mesh *m);
+int64_t tnb_mesh_num_edges(const tnb_mesh *m);
+int64_t tnb_mesh_num_triangles(const tnb_mesh *m);   /* rows of faces_with_indices */
+int64_t tnb_mesh_num_polygons(const tnb_mesh *m);
+int64_t tnb_mesh_polygon_width(const tnb_mesh *m);
+/* copy out (device buffers, any may be NULL): vertices [V,3] f32, edges [E,2] i64,
+ * triangles [T,3] i64 (faces_with_indices), faces [T,3,3] f32 (triangle corner
+ * positions, first return value of subpoly()), polygons [P,W] i64 (-1 padded, the
+ * angle-sorted face rows the triangles fan out of). */
+int tnb_mesh_read(const tnb_mesh *m, float *d_vertices, int64_t *d_edges, int64_t *d_triangles,
+                  float *d_faces, int64_t *d_polygons, void *stream);
+
+/* subpoly(net, d, size, eps, force) (subpoly.py:23-86): the whole path. */
+int tnb_subpoly(const tnb_net *net, float size, float eps, int32_t force, int32_t unit,
+                tnb_mesh **out, void *stream);
+/* same, end to end with HOST buffers: runs the path and copies the mesh to the host.
+ * Call once with all buffers NULL to get the sizes in n_out[4] = {V, T, P, W}, then
+ * tnb_mesh_read_host. */
+int tnb_mesh_read_host(const tnb_mesh *m, float *h_vertices, int64_t *h_triangles,
+                       float *h_faces, int64_t *h_polygons);
+
+/* ---- knobs / introspection ------------------------------------------------------ */
+/* work-buffer growth factor for the complex (default 4.0) */
+int tnb_set_capacity_factor(double f);
+/* number of CUDA kernels this library launched on the calling thread since the last
+ * reset (bench.py's gpu_launches) */
+int64_t tnb_launch_count(void);
+void tnb_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TROPICAL_B200_H */

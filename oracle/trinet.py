@@ -47,19 +47,34 @@ def lib():
     return _lib
 
 
+
+def _libm():
+    """glibc's log2f/exp2f: what tiny-cuda-nn's host code calls for the level scales
+    (numpy's float32 log2/exp2 differ from libm in the last ulp for some levels)."""
+    import ctypes
+    global _LIBM
+    try:
+        return _LIBM
+    except NameError:
+        _LIBM = ctypes.CDLL("libm.so.6")
+        for fn in (_LIBM.log2f, _LIBM.exp2f):
+            fn.restype = ctypes.c_float
+            fn.argtypes = [ctypes.c_float]
+        return _LIBM
+
+
 def grid_layout(n_levels, log2_hashmap_size, base_resolution, per_level_scale, n_dims=3):
     """Per-level (scale, resolution, table size, table offset) as tiny-cuda-nn's
     GridEncoding constructor derives them: float32 scale, uint32 sizes rounded up to a
     multiple of 8 and capped at 2^T."""
-    pls = np.float32(per_level_scale)
-    log2_pls = np.log2(pls, dtype=np.float32)
+    log2_pls = np.float32(_libm().log2f(np.float32(per_level_scale)))
     scale = np.zeros(n_levels, np.float32)
     res = np.zeros(n_levels, np.uint32)
     size = np.zeros(n_levels, np.uint32)
     off = np.zeros(n_levels, np.uint32)
     total = 0
     for l in range(n_levels):
-        s = np.float32(np.exp2(np.float32(l) * log2_pls, dtype=np.float32)
+        s = np.float32(np.float32(_libm().exp2f(np.float32(l) * log2_pls))
                        * np.float32(base_resolution) - np.float32(1.0))
         r = int(np.ceil(s)) + 1
         max_params = (2 ** 32 - 1) // 2

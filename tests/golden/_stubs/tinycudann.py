@@ -29,15 +29,30 @@ _PRIMES = (1, 2654435761, 805459861)
 _U32 = 0xFFFFFFFF
 
 
+
+def _libm():
+    """glibc's log2f/exp2f: what tiny-cuda-nn's host code calls for the level scales
+    (numpy's float32 log2/exp2 differ from libm in the last ulp for some levels)."""
+    import ctypes
+    global _LIBM
+    try:
+        return _LIBM
+    except NameError:
+        _LIBM = ctypes.CDLL("libm.so.6")
+        for fn in (_LIBM.log2f, _LIBM.exp2f):
+            fn.restype = ctypes.c_float
+            fn.argtypes = [ctypes.c_float]
+        return _LIBM
+
+
 def grid_layout(n_levels, log2_hashmap_size, base_resolution, per_level_scale, n_dims=3):
     """Level scales / resolutions / table sizes exactly as tiny-cuda-nn derives them
     (float32 arithmetic for the scale, uint32 for sizes)."""
-    pls = np.float32(per_level_scale)
-    log2_pls = np.log2(pls, dtype=np.float32)
+    log2_pls = np.float32(_libm().log2f(np.float32(per_level_scale)))
     scales, ress, sizes, offsets = [], [], [], []
     offset = 0
     for l in range(n_levels):
-        s = np.float32(np.exp2(np.float32(l) * log2_pls, dtype=np.float32)
+        s = np.float32(np.float32(_libm().exp2f(np.float32(l) * log2_pls))
                        * np.float32(base_resolution) - np.float32(1.0))
         res = int(np.ceil(s)) + 1
         max_params = (2 ** 32 - 1) // 2

@@ -1,0 +1,166 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle, bit-exact for
+every integer array and for every float the fixed operation order defines; against the
+reference's golden fixtures within the tolerances BASELINE.json states (positions 1e-5)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import CASES, canonical_polygons, load_golden, native_net, oracle_net, random_net
+
+pytestmark = pytest.mark.gpu
+
+
+def _pts(n, seed, lo=-1.0, hi=1.0):
+    rng = np.random.default_rng(seed)
+    return (rng.random((n, 3), dtype=np.float32) * np.float32(hi - lo) + np.float32(lo)).astype(np.float32)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_network_evaluation_bit_exact(case):
+    g = load_golden(case)
+    P = oracle_net(g)
+    N = native_net(P)
+    x = _pts(20000, 1, -1.2, 1.2)  # includes points outside the grid (uint32 wrap path)
+    xd = torch.from_numpy(x).cuda()
+    assert np.array_equal(N.encode(torch.from_numpy(P.preprocess(x)).cuda()).cpu().numpy(),
+                          P.encode(P.preprocess(x)))
+    assert np.array_equal(N.outputs(xd).cpu().numpy(), P.outputs(x))
+    sdf, grad = N.sdf_grad(xd)
+    so, go = P.sdf_grad(x)
+    assert np.array_equal(sdf.cpu().numpy(), so)
+    assert np.array_equal(grad.cpu().numpy(), go)
+    signs, off, _, packed = N.region(xd, packed=True)
+    m, o, _ = P.region(x)
+    assert np.array_equal(signs.cpu().numpy(), m)
+    assert np.array_equal(off.cpu().numpy(), o)
+
+
+def test_generic_shapes_bit_exact():
+    # shapes outside the compiled-in (4,16,3) configuration go through the runtime-sized kernels
+    for seed, kw in enumerate([dict(levels=2, num_hidden=8), dict(levels=6, num_hidden=12, num_layers=4),
+                               dict(levels=4, num_hidden=16, log2_T=10, n_max=64)]):
+        P = random_net(seed, **kw)
+        N = native_net(P)
+        x = _pts(5000, seed)
+        xd = torch.from_numpy(x).cuda()
+        assert np.array_equal(N.outputs(xd).cpu().numpy(), P.outputs(x)), kw
+        sdf, grad = N.sdf_grad(xd)
+        so, go = P.sdf_grad(x)
+        assert np.array_equal(sdf.cpu().numpy(), so) and np.array_equal(grad.cpu().numpy(), go), kw
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_skeleton_matches_oracle_and_reference(case):
+    from oracle import subpoly_ref as R
+    g = load_golden(case)
+    P = oracle_net(g)
+    N = native_net(P)
+    c = N.skeleton(128)
+    v, e, o = c.read()
+    vo, eo = R.skeleton(P)
+    assert np.array_equal(e.cpu().numpy(), eo)
+    assert np.array_equal(v.cpu().numpy(), vo)
+    assert np.array_equal(o.cpu().numpy(), P.outputs(vo))
+    # the reference's own skeleton
+    assert np.array_equal(e.cpu().numpy(), g["skeleton_edges"].astype(np.int64))
+    assert np.abs(v.cpu().numpy() - g["skeleton_vertices"]).max() <= 1e-6
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_every_hyperplane_step_bit_exact(case):
+    from oracle import subpoly_ref as R
+    g = load_golden(case)
+    P = oracle_net(g)
+    N = native_net(P)
+    c = N.skeleton(128)
+    vo, eo = R.skeleton(P)
+    oo = P.outputs(vo)
+    H = P.num_hidden
+    steps = [(l, h) for l in range(P.num_layers - 1) for h in range(H)] + [(P.num_layers - 2, H)]
+    for i, (l, h) in enumerate(steps):
+        c.step(l, h)
+        vo, eo, oo = R.subpoly_step(P, vo, eo, oo, l, h, 1e-4)
+        assert (c.num_vertices, c.num_edges) == (vo.shape[0], eo.shape[0]), (l, h)
+        assert (c.num_vertices, c.num_edges) == tuple(g["step_sizes"][i]), (l, h)
+        v, e, o = c.read()
+        assert np.array_equal(e.cpu().numpy(), eo), (l, h)
+        assert np.array_equal(v.cpu().numpy(), vo), (l, h)
+        assert np.array_equal(o.cpu().numpy(), oo), (l, h)
+    assert np.array_equal(eo, g["complex_edges"].astype(np.int64))
+    assert np.abs(vo - g["complex_vertices"]).max() <= 1e-5
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_whole_path_mesh(case):
+    from oracle import subpoly_ref as R
+    g = load_golden(case)
+    P = oracle_net(g)
+    N = native_net(P)
+    mesh = N.subpoly()
+    v, e, t, f, p = [a.cpu().numpy() for a in mesh.read()]
+    faces, vo, tri, inter = R.subpoly(P, return_intermediate=True)
+    # against the oracle: identical arrays
+    assert np.array_equal(v, vo)
+    assert np.array_equal(e, inter["surface_edges"])
+    assert np.array_equal(t, tri)
+    assert np.array_equal(f, faces)
+    # polygon rows: the oracle keeps torch's interleaved -1 padding, the device rows are
+    # left-packed; the vertex sequence of every row must be identical
+    op = inter["polygons"]
+    assert p.shape[0] == op.shape[0]
+    packed = np.full_like(p, -1)
+    for r, row in enumerate(op):
+        keep = row[row != -1]
+        packed[r, :keep.size] = keep
+    assert np.array_equal(p, packed)
+    # against the reference: same surface skeleton, same polygons, positions within 1e-5
+    assert np.array_equal(e, g["surface_edges"].astype(np.int64))
+    assert np.abs(v - g["surface_vertices"]).max() <= 1e-5
+    assert canonical_polygons(p) == canonical_polygons(g["polygons"])
+    assert t.shape[0] == g["triangles"].shape[0]
+    # host-buffer read (the e2e entry) agrees with the device read
+    hv, ht, hf, hp = mesh.read_host()
+    assert np.array_equal(hv, v) and np.array_equal(ht, t) and np.array_equal(hf, f) and np.array_equal(hp, p)
+
+
+def test_no_surface_falls_back_to_hypercube():
+    # a network whose SDF never crosses zero: the skeleton is empty and subpoly starts from
+    # the hypercube (subpoly.py:51-52)
+    from oracle import subpoly_ref as R
+    P = random_net(7, table_amp=1e-4)
+    P.biases[-1][:] = [0.0, 5.0]
+    P = type(P)(P.levels, 2, P.log2_T, P.n_min, P.per_level_scale, P.num_layers, P.num_hidden,
+                P.table, P.weights, P.biases, P.marks)
+    N = native_net(P)
+    vo, eo = R.skeleton(P)
+    assert eo.shape[0] == 0
+    c = N.skeleton(128, 1.2)
+    v, e, _ = c.read()
+    hv, he = R.get_hypercube(1.2)
+    assert np.array_equal(v.cpu().numpy(), hv) and np.array_equal(e.cpu().numpy(), he)
+    mesh = N.subpoly()
+    assert mesh.sizes()["T"] == R.subpoly(P)[2].shape[0]
+
+
+def test_sweep_signs_matches_region():
+    g = load_golden("small_sphere")
+    P = oracle_net(g)
+    N = native_net(P)
+    n = (17, 9, 33)
+    lo, hi = (-1.0, -0.5, -1.0), (1.0, 0.5, 1.0)
+    packed = N.sweep_signs(lo, hi, n).cpu().numpy().view(np.uint64)
+    ax = [np.float32(l) + np.arange(k, dtype=np.float32) * (np.float32(h - l) / np.float32(k - 1))
+          for l, h, k in zip(lo, hi, n)]
+    # lattice points as the kernel forms them: fma(i, step, lo)
+    pts = np.stack(np.meshgrid(*[np.arange(k) for k in n], indexing="ij"), -1).reshape(-1, 3)
+    step = [np.float32(h - l) / np.float32(k - 1) for l, h, k in zip(lo, hi, n)]
+    x = np.stack([(pts[:, d].astype(np.float64) * np.float64(step[d]) + np.float64(lo[d])).astype(np.float32)
+                  for d in range(3)], -1)
+    m, _, _ = P.region(x)
+    s = m[:, 3:]
+    pos = np.zeros(len(x), np.uint64)
+    neg = np.zeros(len(x), np.uint64)
+    for c in range(s.shape[1]):
+        pos |= (s[:, c] == 1).astype(np.uint64) << np.uint64(c)
+        neg |= (s[:, c] == -1).astype(np.uint64) << np.uint64(c)
+    assert np.array_equal(packed[:, 0], pos) and np.array_equal(packed[:, 1], neg)

@@ -1,0 +1,219 @@
+// common.cuh -- shared definitions of the B200 mesh-extraction kernels (sm_100a).
+//
+// Float contract: the whole library is compiled with -fmad=false, IEEE division and
+// square root, no flush-to-zero.  Every fused multiply-add is written explicitly as
+// __fmaf_rn; everything else is a single rounded operation in source order.  This is
+// the operation order oracle/trinet_ref.c documents, so results are bit-identical to
+// the CPU checker.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/tropical_b200.h"
+
+namespace tnb {
+
+constexpr int kMaxLevels = TNB_MAX_LEVELS;
+constexpr int kMaxLinear = TNB_MAX_LINEAR;
+constexpr int kMaxHidden = TNB_MAX_HIDDEN;
+constexpr int kMlpParamMax = 1024;  // floats kept in kernel-parameter (constant bank) space
+constexpr int kSMs = 148;           // B200
+
+struct LevelMeta {
+    float scale;
+    uint32_t res, size, off;
+};
+
+// Passed BY VALUE to kernels (__grid_constant__): lives in the constant bank, so the
+// MLP weights of the reference-sized networks are FFMA constant operands.
+struct NetMeta {
+    int L, H, NLIN, R;
+    float pre_scale, pre_2s, eps;
+    int n_marks;
+    int mlp_in_param;  // 1 when mlp_c holds the weights
+    LevelMeta lvl[kMaxLevels];
+    const float2 *table;  // [entries] (F = 2)
+    const float *mlp;     // global copy of the packed MLP
+    const float *marks;   // global copy of the marks
+    float mlp_c[kMlpParamMax];
+};
+
+// ---- error plumbing ---------------------------------------------------------------
+void set_error(const std::string &msg);
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
+void count_launch(int n = 1);
+
+#define TNB_CUDA(expr)                                                         \
+    do {                                                                       \
+        cudaError_t _e = (expr);                                               \
+        if (_e != cudaSuccess) return tnb::cuda_fail(_e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define TNB_LAUNCH_CHECK()                                                     \
+    do {                                                                       \
+        tnb::count_launch();                                                   \
+        cudaError_t _e = cudaGetLastError();                                   \
+        if (_e != cudaSuccess) return tnb::cuda_fail(_e, "kernel launch", __FILE__, __LINE__); \
+    } while (0)
+
+// ---- device helpers -----------------------------------------------------------------
+#ifdef __CUDACC__
+
+__device__ __forceinline__ float det_expf(float y)
+{
+    float n = rintf(y * 1.44269504088896341f);
+    float r = __fmaf_rn(n, -0.693359375f, y);
+    r = __fmaf_rn(n, 2.12194440e-4f, r);
+    float p = 1.9875691500e-4f;
+    p = __fmaf_rn(p, r, 1.3981999507e-3f);
+    p = __fmaf_rn(p, r, 8.3334519073e-3f);
+    p = __fmaf_rn(p, r, 4.1665795894e-2f);
+    p = __fmaf_rn(p, r, 1.6666665459e-1f);
+    p = __fmaf_rn(p, r, 5.0000001201e-1f);
+    float e = __fmaf_rn(p, r * r, r) + 1.0f;
+    float s = __uint_as_float((uint32_t)((int)n + 127) << 23);
+    return e * s;
+}
+
+// tanh as oracle/trinet_ref.c defines it (libm's and CUDA's differ in the last ulp)
+__device__ __forceinline__ float det_tanhf(float x)
+{
+    float ax = fabsf(x);
+    float t;
+    if (ax < 0.25f) {
+        float x2 = ax * ax;
+        float p = 0.021869488536155203f;
+        p = __fmaf_rn(p, x2, -0.053968253968253971f);
+        p = __fmaf_rn(p, x2, 0.13333333333333333f);
+        p = __fmaf_rn(p, x2, -0.33333333333333331f);
+        t = __fmaf_rn(ax * x2, p, ax);
+    } else if (ax > 9.0f) {
+        t = 1.0f;
+    } else {
+        float e = det_expf(2.0f * ax);
+        t = 1.0f - __fdiv_rn(2.0f, e + 1.0f);
+    }
+    return copysignf(t, x);
+}
+
+__device__ __forceinline__ uint32_t grid_index(uint32_t size, uint32_t res, uint32_t cx,
+                                               uint32_t cy, uint32_t cz)
+{
+    // tiny-cuda-nn grid_index(): dense while the running stride fits the table, prime
+    // XOR hash otherwise
+    uint32_t stride = 1, index = 0;
+    if (stride <= size) { index += cx * stride; stride *= res; }
+    else return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) % size;
+    if (stride <= size) { index += cy * stride; stride *= res; }
+    else return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) % size;
+    if (stride <= size) { index += cz * stride; stride *= res; }
+    else return (cx ^ (cy * 2654435761u) ^ (cz * 805459861u)) % size;
+    if (size < stride) index = cx ^ (cy * 2654435761u) ^ (cz * 805459861u);
+    return index % size;
+}
+
+__device__ __forceinline__ void preprocess(const NetMeta &n, const float x[3], float xp[3])
+{
+#pragma unroll
+    for (int d = 0; d < 3; ++d) xp[d] = __fdiv_rn(x[d] + n.pre_scale, n.pre_2s);
+}
+
+// Level l of the hash encoding at xp.  Returns the two features; optionally the cell
+// and the fractional position for the backward pass.
+__device__ __forceinline__ float2 encode_level(const NetMeta &n, int l, const float xp[3],
+                                               uint32_t cell[3], float frac[3])
+{
+    const LevelMeta lv = n.lvl[l];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float pos = __fmaf_rn(lv.scale, xp[d], 0.5f);
+        float fl = floorf(pos);
+        cell[d] = (uint32_t)(int)fl;
+        frac[d] = pos - fl;
+    }
+    const float2 *tab = n.table + lv.off;
+    float2 v[8];
+#pragma unroll
+    for (int corner = 0; corner < 8; ++corner) {
+        uint32_t idx = grid_index(lv.size, lv.res, cell[0] + (corner & 1), cell[1] + ((corner >> 1) & 1),
+                                  cell[2] + ((corner >> 2) & 1));
+        v[corner] = __ldg(tab + idx);
+    }
+    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int corner = 0; corner < 8; ++corner) {
+        float w = 1.0f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) w = w * ((corner >> d) & 1 ? frac[d] : 1.0f - frac[d]);
+        acc.x = __fmaf_rn(w, v[corner].x, acc.x);
+        acc.y = __fmaf_rn(w, v[corner].y, acc.y);
+    }
+    return acc;
+}
+
+// d(level features)/d xp[d]  (tiny-cuda-nn kernel_grid_backward_input, linear interp.)
+__device__ __forceinline__ float2 encode_level_dx(const NetMeta &n, int l, int d,
+                                                  const uint32_t cell[3], const float frac[3])
+{
+    const LevelMeta lv = n.lvl[l];
+    const float2 *tab = n.table + lv.off;
+    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int idx = 0; idx < 4; ++idx) {
+        float w = lv.scale;
+        uint32_t c[3];
+#pragma unroll
+        for (int nd = 0; nd < 2; ++nd) {
+            int dim = nd >= d ? nd + 1 : nd;
+            int bit = (idx >> nd) & 1;
+            w = w * (bit ? frac[dim] : 1.0f - frac[dim]);
+            c[dim] = cell[dim] + bit;
+        }
+        c[d] = cell[d];
+        float2 vl = __ldg(tab + grid_index(lv.size, lv.res, c[0], c[1], c[2]));
+        c[d] = cell[d] + 1u;
+        float2 vr = __ldg(tab + grid_index(lv.size, lv.res, c[0], c[1], c[2]));
+        acc.x = __fmaf_rn(w, vr.x - vl.x, acc.x);
+        acc.y = __fmaf_rn(w, vr.y - vl.y, acc.y);
+    }
+    return acc;
+}
+
+// torch.searchsorted(marks, v, right=False)
+__device__ __forceinline__ int lower_bound(const float *__restrict__ marks, int m, float v)
+{
+    int lo = 0, hi = m;
+    while (lo < hi) {
+        int mid = (lo + hi) >> 1;
+        if (marks[mid] < v) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+// ---- packed sign vectors -------------------------------------------------------------
+// Per vertex three 64-bit words:
+//   pos : bit c set  <=>  outputs[c] >  eps            (sign +1)
+//   neg : bit c set  <=>  outputs[c] < -eps            (sign -1)   (neither = sign 0)
+//   grd : bits [0,20) [20,40) [40,60) = offset+1 per axis (tropical.py:230-231),
+//         bits 60,61,62 = grid mask per axis (1 = strictly inside a cell, tropical.py:234)
+__device__ __forceinline__ uint64_t pack_grid(const NetMeta &n, const float *__restrict__ marks,
+                                              const float xp[3], float eps)
+{
+    uint64_t g = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        int off = lower_bound(marks, n.n_marks, xp[d] + eps) - 1;
+        float mk = marks[off < 0 ? off + n.n_marks : off];
+        uint64_t inside = fabsf(mk - xp[d]) > eps ? 1ull : 0ull;
+        g |= (uint64_t)(uint32_t)(off + 1) << (20 * d);
+        g |= inside << (60 + d);
+    }
+    return g;
+}
+__device__ __forceinline__ int grid_off(uint64_t g, int d) { return (int)((g >> (20 * d)) & 0xFFFFF) - 1; }
+__device__ __forceinline__ int grid_mask(uint64_t g, int d) { return (int)((g >> (60 + d)) & 1); }
+
+#endif  // __CUDACC__
+
+}  // namespace tnb

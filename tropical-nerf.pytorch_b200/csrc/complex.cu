@@ -1,0 +1,863 @@
+// complex.cu -- skeleton sweep and per-hyperplane edge subdivision on the device.
+//
+// Replaces TropicalHashGrid.skeleton (tropical.py:158-225) and subpoly_ (subpoly.py:90-279,
+// planar branch) including check_edges_with_new_vertices (subpoly_debug.py:33-51),
+// edge_vertices / regions_to_vertices (subpoly.py:281-340, :484-535) and the pruning block
+// (subpoly.py:252-277).  Every compaction is order preserving (scan.cuh), so vertex and
+// edge numbering equal the reference's.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+#include "complex.cuh"
+#include "net_eval.cuh"
+#include "scan.cuh"
+
+tnb_complex::~tnb_complex()
+{
+    if (h_counters) cudaFreeHost(h_counters);
+}
+
+namespace tnb {
+
+double g_capacity_factor = 4.0;
+constexpr int kThreads = 128;
+enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_EDGES, C_VERTS, C_OVERFLOW, C_TMP, C_NUM = 16 };
+
+// ---- allocation ---------------------------------------------------------------------------
+int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
+{
+    c->R = net->meta.R;
+    c->Vcap = Vcap;
+    c->Ecap = Ecap;
+    for (int k = 0; k < 2; ++k) {
+        TNB_CUDA(c->vert[k].reserve(Vcap * 3));
+        TNB_CUDA(c->out[k].reserve(Vcap * c->R));
+        TNB_CUDA(c->sig[k].reserve(Vcap * 3));
+        TNB_CUDA(c->edges[k].reserve(Ecap));
+    }
+    TNB_CUDA(c->split_list.reserve(Ecap));
+    TNB_CUDA(c->bmask.reserve(Ecap));
+    TNB_CUDA(c->cand.reserve(Vcap));
+    TNB_CUDA(c->pcount.reserve(Vcap));
+    TNB_CUDA(c->poff.reserve(Vcap));
+    TNB_CUDA(c->next.reserve(Vcap * 8));
+    TNB_CUDA(c->used.reserve(Vcap));
+    TNB_CUDA(c->remap.reserve(Vcap));
+    TNB_CUDA(c->block_sums.reserve(kScanMaxBlocks));
+    TNB_CUDA(c->counters.reserve(C_NUM));
+    TNB_CUDA(cudaMemset(c->counters.p, 0, C_NUM * sizeof(int)));
+    if (!c->h_counters) TNB_CUDA(cudaMallocHost((void **)&c->h_counters, C_NUM * sizeof(int)));
+    // cell buckets: offsets live in [-1, M-1], cells in [-2, M-1] -> M+2 per axis
+    c->cell_dim = net->meta.n_marks + 2;
+    c->n_cells = (int64_t)c->cell_dim * c->cell_dim * c->cell_dim;
+    if (c->n_cells > (int64_t)1 << 31) {
+        set_error("marks grid too fine for the dense cell buckets (n_marks " + std::to_string(net->meta.n_marks) + ")");
+        return TNB_ERR_UNSUPPORTED;
+    }
+    TNB_CUDA(c->head.reserve((size_t)c->n_cells));
+    TNB_CUDA(cudaMemset(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long)));
+    c->stamp = 0;
+    return TNB_OK;
+}
+
+template <class T>
+static int grow(DevBuf<T> &b, size_t new_elems, size_t keep_elems, cudaStream_t s)
+{
+    if (new_elems <= b.cap) return TNB_OK;
+    DevBuf<T> nb;
+    TNB_CUDA(nb.reserve(new_elems));
+    if (keep_elems) TNB_CUDA(cudaMemcpyAsync(nb.p, b.p, keep_elems * sizeof(T), cudaMemcpyDeviceToDevice, s));
+    TNB_CUDA(cudaStreamSynchronize(s));
+    b.swap(nb);
+    return TNB_OK;
+}
+
+// make room for Vneed vertices / Eneed edges, keeping the current contents
+int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
+{
+    if (Vneed > c->Vcap) {
+        size_t nc = std::max(Vneed, (size_t)(c->Vcap * 2));
+        int rc;
+        for (int k = 0; k < 2; ++k) {
+            size_t keep = (k == c->vcur) ? (size_t)c->V : 0;
+            if ((rc = grow(c->vert[k], nc * 3, keep * 3, s))) return rc;
+            if ((rc = grow(c->out[k], nc * c->R, keep * c->R, s))) return rc;
+            if ((rc = grow(c->sig[k], nc * 3, keep * 3, s))) return rc;
+        }
+        if ((rc = grow(c->cand, nc, 0, s)) || (rc = grow(c->pcount, nc, 0, s)) || (rc = grow(c->poff, nc, 0, s)) ||
+            (rc = grow(c->next, nc * 8, 0, s)) || (rc = grow(c->used, nc, 0, s)) || (rc = grow(c->remap, nc, 0, s)))
+            return rc;
+        c->Vcap = nc;
+    }
+    if (Eneed > c->Ecap) {
+        size_t nc = std::max(Eneed, (size_t)(c->Ecap * 2));
+        int rc;
+        for (int k = 0; k < 2; ++k)
+            if ((rc = grow(c->edges[k], nc, (k == c->ecur) ? (size_t)c->E : 0, s))) return rc;
+        if ((rc = grow(c->split_list, nc, 0, s)) || (rc = grow(c->bmask, nc, 0, s))) return rc;
+        c->Ecap = nc;
+    }
+    return TNB_OK;
+}
+
+static int read_counters(tnb_complex *c, cudaStream_t s)
+{
+    TNB_CUDA(cudaMemcpyAsync(c->h_counters, c->counters.p, C_NUM * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TNB_CUDA(cudaStreamSynchronize(s));
+    return TNB_OK;
+}
+
+// ================================================================================================
+// skeleton
+// ================================================================================================
+struct ChunkSeg {  // one (chunk, axis) block of candidate grid edges, in the reference's order
+    int64_t first;  // first slot number
+    int s[3], n[3]; // chunk start / size per axis
+    int axis, chunk;
+};
+constexpr int kMaxSegs = 3 * 512;
+
+// |tanh(sdf)| and |grad| of every marks-grid vertex of one chunk; per-chunk max |grad|
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_sweep_chunk(const __grid_constant__ NetMeta n, int M, int sx, int sy,
+                                                          int sz, int nx, int ny, int nz,
+                                                          float *__restrict__ dist, unsigned *__restrict__ max_grad)
+{
+    const int64_t count = (int64_t)nx * ny * nz;
+    float local = 0.0f;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        const int k = (int)(t % nz), j = (int)((t / nz) % ny), i = (int)(t / ((int64_t)nz * ny));
+        const int gi = sx + i, gj = sy + j, gk = sz + k;
+        // preprocess_inverse(marks[...]) (tropical.py:186, model.py:81-82)
+        float x[3] = {n.marks[gi] * n.pre_2s - n.pre_scale, n.marks[gj] * n.pre_2s - n.pre_scale,
+                      n.marks[gk] * n.pre_2s - n.pre_scale};
+        float g[3];
+        const float sdf = sdf_grad<C>(n, x, g, true);
+        dist[((int64_t)gi * M + gj) * M + gk] = fabsf(sdf);
+        local = fmaxf(local, grad_norm(g));
+    }
+    // block max (non-negative floats order like their bit patterns)
+    unsigned v = __float_as_uint(local);
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, d));
+    __shared__ unsigned s[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < kThreads / 32; ++w) v = max(v, s[w]);
+        atomicMax(max_grad, v);
+    }
+}
+
+struct SkelEdgeCount {
+    const ChunkSeg *segs;
+    int n_segs, M;
+    const float *dist;
+    const unsigned *max_grad;
+    float k_len;  // (sqrt(3)*2) * max mark spacing  (tropical.py:125-126)
+    __device__ __forceinline__ bool locate(int64_t t, int &hi, int &lo) const
+    {
+        int a = 0, b = n_segs - 1;
+        while (a < b) {  // last segment with first <= t
+            int mid = (a + b + 1) >> 1;
+            if (segs[mid].first <= t) a = mid; else b = mid - 1;
+        }
+        const ChunkSeg sg = segs[a];
+        int64_t r = t - sg.first;
+        int dims[3] = {sg.n[0], sg.n[1], sg.n[2]};
+        dims[sg.axis] -= 1;
+        const int k = (int)(r % dims[2]), j = (int)((r / dims[2]) % dims[1]), i = (int)(r / ((int64_t)dims[2] * dims[1]));
+        int p[3] = {sg.s[0] + i, sg.s[1] + j, sg.s[2] + k};
+        lo = (p[0] * M + p[1]) * M + p[2];
+        p[sg.axis] += 1;
+        hi = (p[0] * M + p[1]) * M + p[2];
+        return true;
+    }
+    __device__ __forceinline__ int chunk_of(int64_t t) const
+    {
+        int a = 0, b = n_segs - 1;
+        while (a < b) {
+            int mid = (a + b + 1) >> 1;
+            if (segs[mid].first <= t) a = mid; else b = mid - 1;
+        }
+        return segs[a].chunk;
+    }
+    __device__ __forceinline__ int operator()(int64_t t) const
+    {
+        int hi, lo;
+        locate(t, hi, lo);
+        const float eps = k_len * __uint_as_float(max_grad[chunk_of(t)]);
+        return (dist[hi] <= eps && dist[lo] <= eps) ? 1 : 0;
+    }
+};
+struct SkelEdgeEmit {
+    SkelEdgeCount q;
+    int2 *edges;
+    int *used;
+    __device__ __forceinline__ void operator()(int64_t t, int pos, int) const
+    {
+        int hi, lo;
+        q.locate(t, hi, lo);
+        edges[pos] = make_int2(hi, lo);  // (indices[1:], indices[:-1]) column order, tropical.py:130
+        used[hi] = 1;
+        used[lo] = 1;
+    }
+};
+
+struct FlagCount {
+    const int *flag;
+    __device__ __forceinline__ int operator()(int64_t i) const { return flag[i] ? 1 : 0; }
+};
+struct SkelVertEmit {
+    NetMeta const *unused;
+    const float *marks;
+    float pre_2s, pre_scale;
+    int M;
+    int *remap;
+    float *vert;
+    __device__ __forceinline__ void operator()(int64_t v, int pos, int) const
+    {
+        remap[v] = pos;
+        const int k = (int)(v % M), j = (int)((v / M) % M), i = (int)(v / ((int64_t)M * M));
+        vert[3 * pos] = marks[i] * pre_2s - pre_scale;
+        vert[3 * pos + 1] = marks[j] * pre_2s - pre_scale;
+        vert[3 * pos + 2] = marks[k] * pre_2s - pre_scale;
+    }
+};
+
+__global__ void k_remap_edges(int2 *__restrict__ edges, int64_t E, const int *__restrict__ remap)
+{
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        int2 ed = edges[e];
+        edges[e] = make_int2(remap[ed.x], remap[ed.y]);
+    }
+}
+
+// outputs row + packed signs of vertices [first, first+count)
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_vertex_outputs(const __grid_constant__ NetMeta n,
+                                                             const float *__restrict__ vert, int64_t first,
+                                                             int64_t count, float *__restrict__ out,
+                                                             uint64_t *__restrict__ sig)
+{
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t v = first + t;
+        float x[3] = {vert[3 * v], vert[3 * v + 1], vert[3 * v + 2]};
+        float *row = out + v * n.R;
+        outputs_row<C>(n, x, row);
+        float xp[3];
+        preprocess(n, x, xp);
+        uint64_t pos, neg;
+        pack_signs(row, n.R, n.eps, pos, neg);
+        sig[3 * v] = pos;
+        sig[3 * v + 1] = neg;
+        sig[3 * v + 2] = pack_grid(n, n.marks, xp, n.eps);
+    }
+}
+
+static int eval_vertices(const tnb_net *net, tnb_complex *c, int64_t first, int64_t count, cudaStream_t s)
+{
+    if (count <= 0) return TNB_OK;
+    unsigned g = grid_for(count, kThreads);
+    if (net->fixed_cfg) k_vertex_outputs<CfgRef><<<g, kThreads, 0, s>>>(net->meta, c->cvert(), first, count, c->cout_(), c->csig());
+    else k_vertex_outputs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, c->cvert(), first, count, c->cout_(), c->csig());
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+
+static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaStream_t s)
+{
+    const int M = net->meta.n_marks;
+    if (unit < 2) { set_error("tnb_skeleton: unit must be >= 2"); return TNB_ERR_INVALID; }
+    const int64_t M3 = (int64_t)M * M * M;
+    if (M3 > (int64_t)1 << 31) { set_error("tnb_skeleton: marks grid too large"); return TNB_ERR_UNSUPPORTED; }
+    // chunks exactly as range(0, L, unit - 1) enumerates them (tropical.py:176-181)
+    std::vector<int> starts;
+    for (int a = 0; a < M; a += unit - 1) starts.push_back(a);
+    const int nc = (int)starts.size();
+    if ((int64_t)nc * nc * nc * 3 > kMaxSegs) { set_error("tnb_skeleton: too many chunks"); return TNB_ERR_UNSUPPORTED; }
+    float len_max = 0.0f;
+    for (int i = 0; i + 1 < M; ++i) len_max = std::max(len_max, net->h_marks[i + 1] - net->h_marks[i]);
+    const float k_len = (std::sqrt(3.0f) * 2.0f) * len_max;
+
+    DevBuf<float> dist;
+    DevBuf<unsigned> max_grad;
+    DevBuf<ChunkSeg> d_segs;
+    DevBuf<int> used, remap, block_sums, total;
+    TNB_CUDA(dist.reserve((size_t)M3));
+    TNB_CUDA(max_grad.reserve((size_t)nc * nc * nc));
+    TNB_CUDA(cudaMemsetAsync(max_grad.p, 0, (size_t)nc * nc * nc * sizeof(unsigned), s));
+    std::vector<ChunkSeg> segs;
+    int64_t slots = 0;
+    int chunk = 0;
+    for (int a = 0; a < nc; ++a)
+        for (int b = 0; b < nc; ++b)
+            for (int cc = 0; cc < nc; ++cc, ++chunk) {
+                const int st[3] = {starts[a], starts[b], starts[cc]};
+                int nn[3];
+                for (int d = 0; d < 3; ++d) nn[d] = std::min(M, st[d] + unit) - st[d];
+                const int64_t count = (int64_t)nn[0] * nn[1] * nn[2];
+                unsigned g = grid_for(count, kThreads);
+                if (net->fixed_cfg)
+                    k_sweep_chunk<CfgRef><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist.p, max_grad.p + chunk);
+                else
+                    k_sweep_chunk<CfgAny><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist.p, max_grad.p + chunk);
+                TNB_LAUNCH_CHECK();
+                for (int axis = 0; axis < 3; ++axis) {
+                    int dims[3] = {nn[0], nn[1], nn[2]};
+                    dims[axis] -= 1;
+                    const int64_t cnt = (int64_t)dims[0] * dims[1] * dims[2];
+                    if (cnt <= 0) continue;
+                    ChunkSeg sg;
+                    sg.first = slots;
+                    for (int d = 0; d < 3; ++d) { sg.s[d] = st[d]; sg.n[d] = nn[d]; }
+                    sg.axis = axis;
+                    sg.chunk = chunk;
+                    segs.push_back(sg);
+                    slots += cnt;
+                }
+            }
+    tnb_complex *c = new tnb_complex();
+    *out = c;
+    if (segs.empty() || slots == 0) {  // degenerate grid: no edges at all
+        int rc = complex_alloc(c, net, 64, 64);
+        return rc;
+    }
+    TNB_CUDA(d_segs.reserve(segs.size()));
+    TNB_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(ChunkSeg), cudaMemcpyHostToDevice, s));
+    TNB_CUDA(used.reserve((size_t)M3));
+    TNB_CUDA(remap.reserve((size_t)M3));
+    TNB_CUDA(block_sums.reserve(kScanMaxBlocks));
+    TNB_CUDA(total.reserve(2));
+    TNB_CUDA(cudaMemsetAsync(used.p, 0, (size_t)M3 * sizeof(int), s));
+
+    // pass 1: count surviving edges so the complex can be sized
+    SkelEdgeCount q{d_segs.p, (int)segs.size(), M, dist.p, max_grad.p, k_len};
+    {
+        int64_t blocks = std::min<int64_t>((slots + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
+        k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, q, block_sums.p);
+        TNB_LAUNCH_CHECK();
+        std::vector<int> h(blocks);
+        TNB_CUDA(cudaMemcpyAsync(h.data(), block_sums.p, blocks * sizeof(int), cudaMemcpyDeviceToHost, s));
+        TNB_CUDA(cudaStreamSynchronize(s));
+        int64_t E = 0;
+        for (int v : h) E += v;
+        if (E == 0) return complex_alloc(c, net, 64, 64);
+        // vertices are bounded by 2E; real sizing happens after the vertex pass
+        DevBuf<int2> raw;
+        TNB_CUDA(raw.reserve((size_t)E));
+        SkelEdgeEmit emit{q, raw.p, used.p};
+        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, q, emit, block_sums.p, total.p);
+        TNB_LAUNCH_CHECK();
+        // vertex pass: count, size, then place
+        FlagCount fc{used.p};
+        int64_t vblocks = std::min<int64_t>((M3 + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
+        k_scan_count<<<(unsigned)vblocks, kScanThreads, 0, s>>>(M3, fc, block_sums.p);
+        TNB_LAUNCH_CHECK();
+        std::vector<int> hv(vblocks);
+        TNB_CUDA(cudaMemcpyAsync(hv.data(), block_sums.p, vblocks * sizeof(int), cudaMemcpyDeviceToHost, s));
+        TNB_CUDA(cudaStreamSynchronize(s));
+        int64_t V = 0;
+        for (int v : hv) V += v;
+        size_t Vcap = (size_t)(V * g_capacity_factor) + 4096, Ecap = (size_t)(E * g_capacity_factor) + 4096;
+        int rc = complex_alloc(c, net, Vcap, Ecap);
+        if (rc) return rc;
+        SkelVertEmit vemit{nullptr, net->meta.marks, net->meta.pre_2s, net->meta.pre_scale, M, remap.p, c->cvert()};
+        k_scan_write<<<(unsigned)vblocks, kScanThreads, 0, s>>>(M3, fc, vemit, block_sums.p, total.p + 1);
+        TNB_LAUNCH_CHECK();
+        TNB_CUDA(cudaMemcpyAsync(c->cedges(), raw.p, (size_t)E * sizeof(int2), cudaMemcpyDeviceToDevice, s));
+        k_remap_edges<<<grid_for(E, 256), 256, 0, s>>>(c->cedges(), E, remap.p);
+        TNB_LAUNCH_CHECK();
+        c->V = V;
+        c->E = E;
+        rc = eval_vertices(net, c, 0, V, s);
+        if (rc) return rc;
+        TNB_CUDA(cudaStreamSynchronize(s));  // locals are freed on return
+    }
+    return TNB_OK;
+}
+
+// ================================================================================================
+// one hyperplane (subpoly_)
+// ================================================================================================
+struct SplitCount {
+    const int2 *edges;
+    const float *out;
+    int R, idx;
+    float eps;
+    __device__ __forceinline__ int operator()(int64_t e) const
+    {
+        const int2 ed = edges[e];
+        const float d0 = out[(int64_t)ed.x * R + idx], d1 = out[(int64_t)ed.y * R + idx];
+        return ((d0 * d1) < 0.0f && fabsf(d0) > eps && fabsf(d1) > eps) ? 1 : 0;  // subpoly.py:104-105
+    }
+};
+struct ListEmit {
+    int *list;
+    __device__ __forceinline__ void operator()(int64_t i, int pos, int) const { list[pos] = (int)i; }
+};
+
+// new vertex of every split edge: position (subpoly.py:113-117, :180), network row, the
+// failover mask of subpoly_debug.py:37-43, edge rewiring (subpoly.py:210-215)
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant__ NetMeta n, int idx, float eps,
+                                                           int S, int V, int E, const int *__restrict__ split_list,
+                                                           int2 *__restrict__ edges, float *__restrict__ vert,
+                                                           float *__restrict__ out, const uint64_t *__restrict__ sig,
+                                                           uint64_t *__restrict__ bmask, int *__restrict__ counters)
+{
+    const int R = n.R;
+    int any = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
+        const int e = split_list[k];
+        const int2 ed = edges[e];
+        const float d0 = __fdiv_rn(out[(int64_t)ed.x * R + idx], eps), d1 = __fdiv_rn(out[(int64_t)ed.y * R + idx], eps);
+        const float w = __fdiv_rn(fabsf(d0), fabsf(d1 - d0));
+        const float omw = 1.0f - w;
+        float x[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[d] = vert[3 * (int64_t)ed.x + d] * omw + vert[3 * (int64_t)ed.y + d] * w;
+        const int64_t nv = (int64_t)V + k;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) vert[3 * nv + d] = x[d];
+        float *row = out + nv * R;
+        outputs_row<C>(n, x, row);
+        const uint64_t za = ~(sig[3 * (int64_t)ed.x] | sig[3 * (int64_t)ed.x + 1]);
+        const uint64_t zb = ~(sig[3 * (int64_t)ed.y] | sig[3 * (int64_t)ed.y + 1]);
+        const uint64_t bm = (za & zb & ((1ull << idx) - 1ull)) | (1ull << idx);
+        bmask[k] = bm;
+        for (uint64_t m = bm; m; m &= m - 1) {
+            const int col = __ffsll((long long)m) - 1;
+            if (fabsf(row[col]) > eps) any = 1;
+        }
+        edges[e].y = (int)nv;                    // left part keeps the first endpoint
+        edges[E + k] = make_int2(ed.y, (int)nv); // right part
+    }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(counters + C_FLAG, 1);
+}
+
+// apply the failover override when any new vertex violated it, then bit-pack the region
+// indicator of the new vertices
+__global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant__ NetMeta n, int S, int V,
+                                                           const float *__restrict__ vert, float *__restrict__ out,
+                                                           uint64_t *__restrict__ sig, const uint64_t *__restrict__ bmask,
+                                                           const int *__restrict__ counters)
+{
+    const int R = n.R;
+    const int flag = counters[C_FLAG];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
+        const int64_t v = (int64_t)V + k;
+        float *row = out + v * R;
+        if (flag)
+            for (uint64_t m = bmask[k]; m; m &= m - 1) row[__ffsll((long long)m) - 1] = 0.0f;
+        float x[3] = {vert[3 * v], vert[3 * v + 1], vert[3 * v + 2]}, xp[3];
+        preprocess(n, x, xp);
+        uint64_t pos, neg;
+        pack_signs(row, R, n.eps, pos, neg);
+        sig[3 * v] = pos;
+        sig[3 * v + 1] = neg;
+        sig[3 * v + 2] = pack_grid(n, n.marks, xp, n.eps);
+    }
+}
+
+struct HitCount {
+    const float *out;
+    int R, idx;
+    float eps;
+    __device__ __forceinline__ int operator()(int64_t v) const { return fabsf(out[v * R + idx]) < eps ? 1 : 0; }  // subpoly.py:233
+};
+
+__global__ void k_fill_new_cands(int *__restrict__ cand, int H, int S, int V)
+{
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) cand[H + k] = V + k;
+}
+
+// ---- cell buckets ------------------------------------------------------------------------------
+// A candidate lies in the cells [lo_d, hi_d] per axis: hi = offset, lo = offset - 1 when it
+// sits on the grid plane (mask 0) -- the (m-1)//2 + offset expansion of subpoly.py:332.
+struct CellBox {
+    int lo[3], hi[3];
+};
+__device__ __forceinline__ CellBox cell_box(uint64_t g)
+{
+    CellBox b;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        b.hi[d] = grid_off(g, d);
+        b.lo[d] = b.hi[d] - (grid_mask(g, d) ? 0 : 1);
+    }
+    return b;
+}
+__device__ __forceinline__ int64_t cell_id(int cx, int cy, int cz, int dim)
+{
+    return ((int64_t)(cx + 2) * dim + (cy + 2)) * dim + (cz + 2);
+}
+
+__global__ void k_bucket_insert(const int *__restrict__ cand, int n_cand, const uint64_t *__restrict__ sig,
+                                unsigned long long *__restrict__ head, int *__restrict__ next, int dim, uint32_t stamp)
+{
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += gridDim.x * blockDim.x) {
+        const CellBox b = cell_box(sig[3 * (int64_t)cand[c] + 2]);
+        int slot = 0;
+        for (int cx = b.lo[0]; cx <= b.hi[0]; ++cx)
+            for (int cy = b.lo[1]; cy <= b.hi[1]; ++cy)
+                for (int cz = b.lo[2]; cz <= b.hi[2]; ++cz, ++slot) {
+                    const int rec = c * 8 + slot;
+                    const unsigned long long mine = ((unsigned long long)stamp << 32) | (unsigned)rec;
+                    const unsigned long long old = atomicExch(head + cell_id(cx, cy, cz, dim), mine);
+                    next[rec] = ((uint32_t)(old >> 32) == stamp) ? (int)(uint32_t)old : -1;
+                }
+    }
+}
+
+constexpr int kMaxPartners = 256;
+
+// Partners of candidate a: candidates b with a larger vertex number that share an expanded
+// region with a and at least one plane (subpoly.py:484-535).  Each pair is found in exactly
+// one cell (the smallest common one).  Returns the count; partner vertex numbers go to
+// `list` (unsorted) when it is non-null.
+__device__ __forceinline__ int find_partners(int a, const int *__restrict__ cand, const uint64_t *__restrict__ sig,
+                                             const unsigned long long *__restrict__ head, const int *__restrict__ next,
+                                             int dim, uint32_t stamp, uint64_t colmask, int *list)
+{
+    const int va = cand[a];
+    const uint64_t pa = sig[3 * (int64_t)va], na = sig[3 * (int64_t)va + 1], ga = sig[3 * (int64_t)va + 2];
+    const uint64_t za = ~(pa | na);
+    const CellBox ba = cell_box(ga);
+    int count = 0;
+    for (int cx = ba.lo[0]; cx <= ba.hi[0]; ++cx)
+        for (int cy = ba.lo[1]; cy <= ba.hi[1]; ++cy)
+            for (int cz = ba.lo[2]; cz <= ba.hi[2]; ++cz) {
+                const unsigned long long h = head[cell_id(cx, cy, cz, dim)];
+                if ((uint32_t)(h >> 32) != stamp) continue;
+                const int cur[3] = {cx, cy, cz};
+                for (int rec = (int)(uint32_t)h; rec >= 0; rec = next[rec]) {
+                    const int vb = cand[rec >> 3];
+                    if (vb <= va) continue;
+                    const uint64_t pb = sig[3 * (int64_t)vb], nb = sig[3 * (int64_t)vb + 1], gb = sig[3 * (int64_t)vb + 2];
+                    if (((pa & nb) | (na & pb)) & colmask) continue;  // opposite signs: no common region
+                    const CellBox bb = cell_box(gb);
+                    bool ok = true;
+                    int shared = __popcll(za & ~(pb | nb) & colmask);
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) {
+                        const int lo = max(ba.lo[d], bb.lo[d]), hi = min(ba.hi[d], bb.hi[d]);
+                        if (lo > hi || cur[d] != lo) ok = false;  // not a common cell / not the canonical one
+                        if (!grid_mask(ga, d) && !grid_mask(gb, d) && ba.hi[d] == bb.hi[d]) ++shared;
+                    }
+                    if (!ok || shared < 1) continue;
+                    if (list && count < kMaxPartners) list[count] = vb;
+                    ++count;
+                }
+            }
+    return count;
+}
+
+__global__ void __launch_bounds__(kThreads) k_pair_count(const int *__restrict__ cand, int n_cand,
+                                                         const uint64_t *__restrict__ sig,
+                                                         const unsigned long long *__restrict__ head,
+                                                         const int *__restrict__ next, int dim, uint32_t stamp,
+                                                         uint64_t colmask, int *__restrict__ pcount,
+                                                         int *__restrict__ counters)
+{
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x) {
+        const int cnt = find_partners(a, cand, sig, head, next, dim, stamp, colmask, nullptr);
+        pcount[a] = cnt;
+        if (cnt > kMaxPartners) atomicOr(counters + C_OVERFLOW, 1);
+    }
+}
+
+struct ArrayCount {
+    const int *v;
+    __device__ __forceinline__ int operator()(int64_t i) const { return v[i]; }
+};
+struct OffsetEmit {
+    int *off;
+    __device__ __forceinline__ void operator()(int64_t i, int pos, int) const { off[i] = pos; }
+};
+
+__global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__ cand, int n_cand,
+                                                         const uint64_t *__restrict__ sig,
+                                                         const unsigned long long *__restrict__ head,
+                                                         const int *__restrict__ next, int dim, uint32_t stamp,
+                                                         uint64_t colmask, const int *__restrict__ pcount,
+                                                         const int *__restrict__ poff, int2 *__restrict__ edges_out)
+{
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x) {
+        const int cnt = pcount[a];
+        if (cnt == 0) continue;
+        int list[kMaxPartners];
+        find_partners(a, cand, sig, head, next, dim, stamp, colmask, list);
+        const int m = min(cnt, kMaxPartners);
+        for (int i = 1; i < m; ++i) {  // ascending partner number: unique(dim=0) order, subpoly.py:243-244
+            const int key = list[i];
+            int j = i - 1;
+            while (j >= 0 && list[j] > key) { list[j + 1] = list[j]; --j; }
+            list[j + 1] = key;
+        }
+        const int va = cand[a];
+        int2 *dst = edges_out + poff[a];
+        for (int i = 0; i < m; ++i) dst[i] = make_int2(va, list[i]);
+    }
+}
+
+// ---- pruning -------------------------------------------------------------------------------------
+struct KeepCount {  // subpoly.py:262-264: keep an edge iff its ends differ in a future indicator
+    const int2 *edges;
+    const uint64_t *sig;
+    uint64_t futmask;
+    __device__ __forceinline__ int operator()(int64_t e) const
+    {
+        const int2 ed = edges[e];
+        const uint64_t dp = sig[3 * (int64_t)ed.x] ^ sig[3 * (int64_t)ed.y];
+        const uint64_t dn = sig[3 * (int64_t)ed.x + 1] ^ sig[3 * (int64_t)ed.y + 1];
+        return ((dp | dn) & futmask) ? 1 : 0;
+    }
+};
+struct KeepEmit {
+    const int2 *edges;
+    int2 *dst;
+    int *used;
+    __device__ __forceinline__ void operator()(int64_t e, int pos, int) const
+    {
+        const int2 ed = edges[e];
+        dst[pos] = ed;
+        used[ed.x] = 1;
+        used[ed.y] = 1;
+    }
+};
+struct VertexMoveEmit {  // subpoly.py:268-277: compact vertices, positions, cached outputs
+    const float *vert, *out;
+    const uint64_t *sig;
+    float *nvert, *nout;
+    uint64_t *nsig;
+    int *remap;
+    int R;
+    __device__ __forceinline__ void operator()(int64_t v, int pos, int) const
+    {
+        remap[v] = pos;
+        for (int d = 0; d < 3; ++d) nvert[3 * (int64_t)pos + d] = vert[3 * v + d];
+        for (int d = 0; d < 3; ++d) nsig[3 * (int64_t)pos + d] = sig[3 * v + d];
+        for (int c = 0; c < R; ++c) nout[(int64_t)pos * R + c] = out[v * R + c];
+    }
+};
+
+static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps, cudaStream_t s)
+{
+    const NetMeta &m = net->meta;
+    const int H = m.H, R = m.R;
+    const int idx = l * H + h;
+    if (l < 0 || h < 0 || h > H || idx >= R) { set_error("tnb_subpoly_step: (l,h) out of range"); return TNB_ERR_INVALID; }
+    if (c->E == 0) return TNB_OK;
+    int *cnt = c->counters.p;
+    int rc;
+    TNB_CUDA(cudaMemsetAsync(cnt, 0, C_NUM * sizeof(int), s));
+
+    // 1. edges the hyperplane crosses
+    SplitCount sc{c->cedges(), c->cout_(), R, idx, eps};
+    if ((rc = compact(c->E, sc, ListEmit{c->split_list.p}, c->block_sums.p, cnt + C_SPLIT, s))) return rc;
+    if ((rc = read_counters(c, s))) return rc;
+    const int S = c->h_counters[C_SPLIT];
+    if (S == 0) return TNB_OK;  // subpoly.py:110-111
+    if ((rc = complex_reserve(c, c->V + S, c->E + S, s))) return rc;
+    const int V0 = (int)c->V, E0 = (int)c->E;
+
+    // 2. new vertices, their network rows, rewired edges
+    {
+        unsigned g = grid_for(S, kThreads);
+        if (net->fixed_cfg)
+            k_new_vertices<CfgRef><<<g, kThreads, 0, s>>>(m, idx, eps, S, V0, E0, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
+        else
+            k_new_vertices<CfgAny><<<g, kThreads, 0, s>>>(m, idx, eps, S, V0, E0, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
+        TNB_LAUNCH_CHECK();
+        k_finalize_new<<<g, kThreads, 0, s>>>(m, S, V0, c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
+        TNB_LAUNCH_CHECK();
+    }
+
+    // 3. candidates for connecting edges: old vertices on the plane, then the new ones
+    HitCount hc{c->cout_(), R, idx, eps};
+    if ((rc = compact(V0, hc, ListEmit{c->cand.p}, c->block_sums.p, cnt + C_HIT, s))) return rc;
+    if ((rc = read_counters(c, s))) return rc;
+    const int Hn = c->h_counters[C_HIT];
+    const int n_cand = Hn + S;
+    k_fill_new_cands<<<grid_for(S, 256), 256, 0, s>>>(c->cand.p, Hn, S, V0);
+    TNB_LAUNCH_CHECK();
+    c->stamp += 1;
+    if (c->stamp == 0) {  // generation wrapped: clear the heads once
+        TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
+        c->stamp = 1;
+    }
+    const uint64_t colmask = (1ull << idx) - 1ull;
+    {
+        unsigned g = grid_for(n_cand, kThreads);
+        k_bucket_insert<<<g, kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp);
+        TNB_LAUNCH_CHECK();
+        k_pair_count<<<g, kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, cnt);
+        TNB_LAUNCH_CHECK();
+    }
+    if ((rc = compact(n_cand, ArrayCount{c->pcount.p}, OffsetEmit{c->poff.p}, c->block_sums.p, cnt + C_PAIRS, s))) return rc;
+    if ((rc = read_counters(c, s))) return rc;
+    if (c->h_counters[C_OVERFLOW]) { set_error("a vertex has more than 256 connecting partners"); return TNB_ERR_CAPACITY; }
+    const int P = c->h_counters[C_PAIRS];
+    if ((rc = complex_reserve(c, c->V + S, (size_t)E0 + S + P, s))) return rc;
+    if (P > 0) {
+        k_pair_write<<<grid_for(n_cand, kThreads), kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S);
+        TNB_LAUNCH_CHECK();
+    }
+    c->V = V0 + S;
+    c->E = (int64_t)E0 + S + P;
+
+    // 4. pruning (not for the output neuron, subpoly.py:253)
+    if (h < H) {
+        const uint64_t futmask = ~colmask & (R >= 64 ? ~0ull : ((1ull << R) - 1ull));
+        TNB_CUDA(cudaMemsetAsync(c->used.p, 0, (size_t)c->V * sizeof(int), s));
+        KeepCount kc{c->cedges(), c->csig(), futmask};
+        int2 *dst = c->edges[c->ecur ^ 1].p;
+        if ((rc = compact(c->E, kc, KeepEmit{c->cedges(), dst, c->used.p}, c->block_sums.p, cnt + C_EDGES, s))) return rc;
+        const int o = c->vcur ^ 1;
+        VertexMoveEmit vm{c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->sig[o].p, c->remap.p, R};
+        if ((rc = compact(c->V, FlagCount{c->used.p}, vm, c->block_sums.p, cnt + C_VERTS, s))) return rc;
+        if ((rc = read_counters(c, s))) return rc;
+        c->E = c->h_counters[C_EDGES];
+        c->V = c->h_counters[C_VERTS];
+        c->ecur ^= 1;
+        c->vcur = o;
+        if (c->E > 0) {
+            k_remap_edges<<<grid_for(c->E, 256), 256, 0, s>>>(c->cedges(), c->E, c->remap.p);
+            TNB_LAUNCH_CHECK();
+        }
+    }
+    return TNB_OK;
+}
+
+// ---- hypercube fallback (subpoly.py:51-52, :731-750) -----------------------------------------------
+static void hypercube(float size, std::vector<float> &v, std::vector<int64_t> &e)
+{
+    const float c[2] = {-size, size};
+    for (int i = 0; i < 2; ++i)
+        for (int j = 0; j < 2; ++j)
+            for (int k = 0; k < 2; ++k) { v.push_back(c[i]); v.push_back(c[j]); v.push_back(c[k]); }
+    for (int a = 0; a < 8; ++a)
+        for (int b = a + 1; b < 8; ++b) {
+            int diff = 0;
+            for (int d = 0; d < 3; ++d) diff += (v[3 * a + d] * v[3 * b + d] < 0.0f) ? 1 : 0;
+            if (diff == 1) { e.push_back(a); e.push_back(b); }
+        }
+}
+
+__global__ void k_edges_from_i64(const int64_t *__restrict__ src, int64_t E, int2 *__restrict__ dst)
+{
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x)
+        dst[e] = make_int2((int)src[2 * e], (int)src[2 * e + 1]);
+}
+__global__ void k_edges_to_i64(const int2 *__restrict__ src, int64_t E, int64_t *__restrict__ dst)
+{
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        dst[2 * e] = src[e].x;
+        dst[2 * e + 1] = src[e].y;
+    }
+}
+
+static int from_arrays_impl(const tnb_net *net, const float *d_vertices, int64_t V, const int64_t *d_edges, int64_t E,
+                            tnb_complex **out, cudaStream_t s)
+{
+    tnb_complex *c = new tnb_complex();
+    *out = c;
+    int rc = complex_alloc(c, net, (size_t)(V * g_capacity_factor) + 4096, (size_t)(E * g_capacity_factor) + 4096);
+    if (rc) return rc;
+    if (V > 0) TNB_CUDA(cudaMemcpyAsync(c->cvert(), d_vertices, (size_t)V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (E > 0) {
+        k_edges_from_i64<<<grid_for(E, 256), 256, 0, s>>>(d_edges, E, c->cedges());
+        TNB_LAUNCH_CHECK();
+    }
+    c->V = V;
+    c->E = E;
+    return eval_vertices(net, c, 0, V, s);
+}
+
+}  // namespace tnb
+
+using namespace tnb;
+
+extern "C" {
+
+int tnb_set_capacity_factor(double f)
+{
+    if (!(f >= 1.0)) { set_error("capacity factor must be >= 1"); return TNB_ERR_INVALID; }
+    g_capacity_factor = f;
+    return TNB_OK;
+}
+
+int tnb_skeleton(const tnb_net *net, int32_t unit, float size, tnb_complex **out, void *stream)
+{
+    if (!net || !out) { set_error("tnb_skeleton: null argument"); return TNB_ERR_INVALID; }
+    *out = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    tnb_complex *c = nullptr;
+    int rc = skeleton_impl(net, unit, &c, s);
+    if (rc == TNB_OK && c->E == 0) {  // we start with a hypercube (subpoly.py:51-52)
+        delete c;
+        c = nullptr;
+        std::vector<float> v;
+        std::vector<int64_t> e;
+        hypercube(size, v, e);
+        DevBuf<float> dv;
+        DevBuf<int64_t> de;
+        TNB_CUDA(dv.reserve(v.size()));
+        TNB_CUDA(de.reserve(e.size()));
+        TNB_CUDA(cudaMemcpyAsync(dv.p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, s));
+        TNB_CUDA(cudaMemcpyAsync(de.p, e.data(), e.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
+        rc = from_arrays_impl(net, dv.p, 8, de.p, (int64_t)e.size() / 2, &c, s);
+        cudaStreamSynchronize(s);
+    }
+    if (rc != TNB_OK) { delete c; return rc; }
+    *out = c;
+    return TNB_OK;
+}
+
+int tnb_complex_from_arrays(const tnb_net *net, const float *d_vertices, int64_t V, const int64_t *d_edges, int64_t E,
+                            tnb_complex **out, void *stream)
+{
+    if (!net || !out || V < 0 || E < 0 || (V > 0 && !d_vertices) || (E > 0 && !d_edges)) {
+        set_error("tnb_complex_from_arrays: bad argument");
+        return TNB_ERR_INVALID;
+    }
+    *out = nullptr;
+    tnb_complex *c = nullptr;
+    int rc = from_arrays_impl(net, d_vertices, V, d_edges, E, &c, (cudaStream_t)stream);
+    if (rc != TNB_OK) { delete c; return rc; }
+    *out = c;
+    return TNB_OK;
+}
+
+void tnb_complex_destroy(tnb_complex *c) { delete c; }
+int64_t tnb_complex_num_vertices(const tnb_complex *c) { return c ? c->V : 0; }
+int64_t tnb_complex_num_edges(const tnb_complex *c) { return c ? c->E : 0; }
+
+int tnb_complex_read(const tnb_complex *c, float *d_vertices, int64_t *d_edges, float *d_outputs, void *stream)
+{
+    if (!c) { set_error("tnb_complex_read: null complex"); return TNB_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d_vertices && c->V) TNB_CUDA(cudaMemcpyAsync(d_vertices, c->cvert(), (size_t)c->V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (d_outputs && c->V) TNB_CUDA(cudaMemcpyAsync(d_outputs, c->cout_(), (size_t)c->V * c->R * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (d_edges && c->E) {
+        k_edges_to_i64<<<grid_for(c->E, 256), 256, 0, s>>>(c->cedges(), c->E, d_edges);
+        TNB_LAUNCH_CHECK();
+    }
+    return TNB_OK;
+}
+
+int tnb_subpoly_step(const tnb_net *net, tnb_complex *c, int32_t l, int32_t h, float eps, int32_t force, void *stream)
+{
+    if (!net || !c) { set_error("tnb_subpoly_step: null argument"); return TNB_ERR_INVALID; }
+    if (!force) {
+        set_error("the curve-approximation path (force=False, subpoly.py:120-177) is not built yet; "
+                  "only the planar path (the reference default) runs on the device");
+        return TNB_ERR_UNSUPPORTED;
+    }
+    return step_impl(net, c, l, h, eps, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,56 @@
+// complex.cuh -- the device-resident polyhedral complex behind tnb_complex.
+#pragma once
+#include "runtime.cuh"
+
+// Layout in HBM (structure of arrays, all rows indexed by vertex / edge number):
+//   vert  [V][3] f32   world-space position
+//   out   [V][R] f32   cached Net.forward(gather=True) row (subpoly.py:92-95, :275)
+//   sig   [V][3] u64   packed region indicator {pos bits, neg bits, grid word}
+//   edges [E]    int2  vertex pair (first, second) in the reference's column order
+// Vertex arrays and the edge array are double-buffered: pruning compacts from one set
+// into the other (order preserving) and flips.
+struct tnb_complex {
+    int R = 0;
+    int64_t V = 0, E = 0;
+    size_t Vcap = 0, Ecap = 0;
+    int vcur = 0, ecur = 0;
+    tnb::DevBuf<float> vert[2], out[2];
+    tnb::DevBuf<uint64_t> sig[2];
+    tnb::DevBuf<int2> edges[2];
+    // scratch
+    tnb::DevBuf<int> split_list;    // [Ecap]   edge numbers being split
+    tnb::DevBuf<uint64_t> bmask;    // [Ecap]   override mask of each new vertex
+    tnb::DevBuf<int> cand;          // [Vcap]   candidate vertex numbers (hits, then new)
+    tnb::DevBuf<int> pcount;        // [Vcap]   partners per candidate
+    tnb::DevBuf<int> poff;          // [Vcap]   exclusive scan of pcount
+    tnb::DevBuf<int> next;          // [8*Vcap] bucket chains
+    tnb::DevBuf<unsigned long long> head;  // [n_cells] (stamp << 32 | record)
+    tnb::DevBuf<int> used;          // [Vcap]   vertex referenced by a kept edge
+    tnb::DevBuf<int> remap;         // [Vcap]
+    tnb::DevBuf<int> block_sums;    // [kScanMaxBlocks]
+    tnb::DevBuf<int> counters;      // [16] device counters
+    int *h_counters = nullptr;      // pinned mirror
+    uint32_t stamp = 0;             // bucket generation
+    int64_t n_cells = 0;
+    int cell_dim = 0;
+
+    float *cvert() { return vert[vcur].p; }
+    float *cout_() { return out[vcur].p; }
+    uint64_t *csig() { return sig[vcur].p; }
+    int2 *cedges() { return edges[ecur].p; }
+    const float *cvert() const { return vert[vcur].p; }
+    const float *cout_() const { return out[vcur].p; }
+    const uint64_t *csig() const { return sig[vcur].p; }
+    const int2 *cedges() const { return edges[ecur].p; }
+    ~tnb_complex();
+};
+
+namespace tnb {
+int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap);
+int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s);
+int launch_outputs(const tnb_net *net, const float *d_x, int64_t n, float *d_out, cudaStream_t s);
+int launch_sdf_grad(const tnb_net *net, const float *d_x, int64_t n, float *d_sdf, float *d_grad, cudaStream_t s);
+int launch_region(const tnb_net *net, const float *d_x, const float *d_outputs, int64_t n, float eps,
+                  int8_t *d_signs, int32_t *d_offset, uint64_t *d_packed, cudaStream_t s);
+extern double g_capacity_factor;
+}  // namespace tnb

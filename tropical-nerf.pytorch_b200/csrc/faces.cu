@@ -1,0 +1,578 @@
+// faces.cu -- surface skeleton and face extraction on the device, and the whole-path entry.
+//
+// Replaces extract_skeleton (subpoly.py:556-581), extract_faces (subpoly.py:584-652) with
+// regions_to_vertices / r_idx_as_tensor (subpoly.py:281-370), mean_points_with_valid
+// (subpoly.py:669-678), sort_polygon_vertices_batch (geometry.py:483-525),
+// tensor_to_triangle_faces (subpoly.py:700-728) and the driver subpoly() (subpoly.py:23-86).
+//
+// The reference groups vertices by region with unique(dim=0) + argsort over an expanded
+// [sum 2^k, 36] int64 matrix.  Here every surface vertex owns a warp; lane q enumerates
+// the vertex's q-th adjacent region, collects the region's vertices from the cell buckets
+// and the vertex that is first in the row ("leader") emits it.  Rows of one leader are
+// ranked inside the warp, so the global row order (torch.unique(dim=0) = lexicographic, first
+// element = leader) falls out of one ordered scan over the vertices -- no global sort.
+#include <algorithm>
+#include <vector>
+
+#include "complex.cuh"
+#include "net_eval.cuh"
+#include "scan.cuh"
+
+struct tnb_mesh {
+    int64_t V = 0, E = 0, P = 0, W = 0, T = 0;
+    tnb::DevBuf<float> vert;   // [V][3]
+    tnb::DevBuf<float> out;    // [V][R]
+    tnb::DevBuf<int2> edges;   // [E]
+    tnb::DevBuf<int> poly;     // [P][W] angle-sorted rows, -1 padded
+    tnb::DevBuf<int> pcnt;     // [P]
+    tnb::DevBuf<int> tri;      // [T][3]
+};
+
+namespace tnb {
+
+constexpr int kThreads = 128;
+constexpr int kMaxRow = 32;   // vertices per face row
+constexpr int kMaxZeros = 5;  // 2^5 regions = one per lane
+enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_NUM = 16 };
+
+// ---- surface skeleton -----------------------------------------------------------------------------
+__global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
+                                const float *__restrict__ out, int64_t V, float eps, int *__restrict__ surf,
+                                int *__restrict__ counters)
+{
+    int local = 0;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+        float x[3] = {vert[3 * v], vert[3 * v + 1], vert[3 * v + 2]}, xp[3];
+        preprocess(n, x, xp);
+        bool on = fabsf(out[v * n.R + n.R - 1]) < eps;
+        for (int d = 0; d < 3; ++d)
+            if (xp[d] > 1.0f || xp[d] < 0.0f) on = false;
+        surf[v] = on ? 1 : 0;
+        local += on ? 1 : 0;
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(counters + F_SURF, local);
+}
+
+struct SurfEdgeCount {
+    const int2 *edges;
+    const int *surf;
+    __device__ __forceinline__ int operator()(int64_t e) const { return (surf[edges[e].x] && surf[edges[e].y]) ? 1 : 0; }
+};
+struct SurfEdgeEmit {
+    const int2 *edges;
+    int2 *dst;
+    int *used;
+    __device__ __forceinline__ void operator()(int64_t e, int pos, int) const
+    {
+        const int2 ed = edges[e];
+        dst[pos] = ed;
+        used[ed.x] = 1;
+        used[ed.y] = 1;
+    }
+};
+struct FlagCount {
+    const int *flag;
+    __device__ __forceinline__ int operator()(int64_t i) const { return flag[i] ? 1 : 0; }
+};
+struct SurfVertEmit {
+    const float *vert, *out;
+    float *nvert, *nout;
+    int *remap;
+    int R;
+    __device__ __forceinline__ void operator()(int64_t v, int pos, int) const
+    {
+        remap[v] = pos;
+        for (int d = 0; d < 3; ++d) nvert[3 * (int64_t)pos + d] = vert[3 * v + d];
+        for (int c = 0; c < R; ++c) nout[(int64_t)pos * R + c] = out[v * R + c];
+    }
+};
+__global__ void k_remap_edges2(int2 *__restrict__ edges, int64_t E, const int *__restrict__ remap)
+{
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        int2 ed = edges[e];
+        edges[e] = make_int2(remap[ed.x], remap[ed.y]);
+    }
+}
+
+// ---- region rows ------------------------------------------------------------------------------------
+__global__ void k_surface_sig(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
+                              const float *__restrict__ out, int64_t V, float eps, uint64_t *__restrict__ sig)
+{
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+        float x[3] = {vert[3 * v], vert[3 * v + 1], vert[3 * v + 2]}, xp[3];
+        preprocess(n, x, xp);
+        uint64_t pos, neg;
+        pack_signs(out + v * n.R, n.R, eps, pos, neg);
+        sig[3 * v] = pos;
+        sig[3 * v + 1] = neg;
+        sig[3 * v + 2] = pack_grid(n, n.marks, xp, eps);
+    }
+}
+
+struct Box {
+    int lo[3], hi[3];
+};
+__device__ __forceinline__ Box box_of(uint64_t g)
+{
+    Box b;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        b.hi[d] = grid_off(g, d);
+        b.lo[d] = b.hi[d] - (grid_mask(g, d) ? 0 : 1);
+    }
+    return b;
+}
+__device__ __forceinline__ int64_t cell_of(int cx, int cy, int cz, int dim)
+{
+    return ((int64_t)(cx + 2) * dim + (cy + 2)) * dim + (cz + 2);
+}
+__device__ __forceinline__ int zero_count(uint64_t pos, uint64_t neg, uint64_t g, uint64_t colmask)
+{
+    return __popcll(~(pos | neg) & colmask) + (3 - grid_mask(g, 0) - grid_mask(g, 1) - grid_mask(g, 2));
+}
+
+__global__ void k_face_bucket_insert(int64_t V, const uint64_t *__restrict__ sig, unsigned long long *__restrict__ head,
+                                     int *__restrict__ next, int dim, uint32_t stamp)
+{
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+        const Box b = box_of(sig[3 * v + 2]);
+        int slot = 0;
+        for (int cx = b.lo[0]; cx <= b.hi[0]; ++cx)
+            for (int cy = b.lo[1]; cy <= b.hi[1]; ++cy)
+                for (int cz = b.lo[2]; cz <= b.hi[2]; ++cz, ++slot) {
+                    const int rec = (int)v * 8 + slot;
+                    const unsigned long long mine = ((unsigned long long)stamp << 32) | (unsigned)rec;
+                    const unsigned long long old = atomicExch(head + cell_of(cx, cy, cz, dim), mine);
+                    next[rec] = ((uint32_t)(old >> 32) == stamp) ? (int)(uint32_t)old : -1;
+                }
+    }
+}
+
+// One warp per surface vertex a; lane q builds the row of a's q-th adjacent region.
+// mode 0: rows_per_vertex[a] = number of distinct rows a leads (>= 3 vertices), max width.
+// mode 1: write those rows, lexicographically ranked, at row_off[a].
+__global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint64_t *__restrict__ sig,
+                                                          const unsigned long long *__restrict__ head,
+                                                          const int *__restrict__ next, int dim, uint32_t stamp,
+                                                          uint64_t colmask, int mode, int *__restrict__ rows_per_vertex,
+                                                          const int *__restrict__ row_off, int *__restrict__ rows,
+                                                          int *__restrict__ row_cnt, int W, int *__restrict__ counters)
+{
+    __shared__ int s_rows[kThreads / 32][32][kMaxRow];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int(*my)[kMaxRow] = s_rows[warp];
+    for (int64_t a = (int64_t)blockIdx.x * (kThreads / 32) + warp; a < V; a += (int64_t)gridDim.x * (kThreads / 32)) {
+        const uint64_t pa = sig[3 * a], na = sig[3 * a + 1], ga = sig[3 * a + 2];
+        const uint64_t za = ~(pa | na) & colmask;
+        const int gz = 3 - grid_mask(ga, 0) - grid_mask(ga, 1) - grid_mask(ga, 2);
+        const int ka = __popcll(za) + gz;
+        int cnt = 0;
+        bool lead = false;
+        if (ka > kMaxZeros) {
+            if (lane == 0) atomicOr(counters + F_ERR_ZEROS, 1);
+        } else if (lane < (1 << ka)) {
+            // region q: bit t of q decides the side of a's t-th zero column (grid axes first)
+            int cell[3];
+            int t = 0;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) {
+                cell[d] = grid_off(ga, d);
+                if (!grid_mask(ga, d)) { if (!((lane >> t) & 1)) cell[d] -= 1; ++t; }
+            }
+            uint64_t pat = pa & colmask;
+            for (uint64_t m = za; m; m &= m - 1, ++t)
+                if ((lane >> t) & 1) pat |= m & (~m + 1);
+            // collect the region's vertices ordered by (zero count, vertex number): the row
+            // order r_idx_as_tensor builds from regions_to_vertices' group-by-zero-count output
+            unsigned long long keys[kMaxRow];
+            const unsigned long long h = head[cell_of(cell[0], cell[1], cell[2], dim)];
+            if ((uint32_t)(h >> 32) == stamp) {
+                for (int rec = (int)(uint32_t)h; rec >= 0; rec = next[rec]) {
+                    const int b = rec >> 3;
+                    const uint64_t pb = sig[3 * (int64_t)b], nb = sig[3 * (int64_t)b + 1], gb = sig[3 * (int64_t)b + 2];
+                    if ((pb & ~pat & colmask) || (nb & pat)) continue;  // a nonzero sign disagrees
+                    const Box bb = box_of(gb);
+                    bool in = true;
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) in = in && cell[d] >= bb.lo[d] && cell[d] <= bb.hi[d];
+                    if (!in) continue;
+                    const unsigned long long key = ((unsigned long long)zero_count(pb, nb, gb, colmask) << 32) | (unsigned)b;
+                    if (cnt < kMaxRow) {
+                        int j = cnt - 1;
+                        while (j >= 0 && keys[j] > key) { keys[j + 1] = keys[j]; --j; }
+                        keys[j + 1] = key;
+                    }
+                    ++cnt;
+                }
+            }
+            if (cnt > kMaxRow) { atomicOr(counters + F_ERR_ROW, 1); cnt = kMaxRow; }
+            lead = cnt >= 3 && (int)(uint32_t)keys[0] == (int)a;
+            for (int j = 0; j < kMaxRow; ++j) my[lane][j] = j < cnt ? (int)(uint32_t)keys[j] : -1;
+        }
+        __syncwarp();
+        const unsigned lead_mask = __ballot_sync(0xffffffffu, lead);
+        // rank among the rows this vertex leads: lexicographic, identical rows collapse
+        bool keep = lead;
+        int rank = 0;
+        if (lead) {
+            for (unsigned mset = lead_mask & ~(1u << lane); mset; mset &= mset - 1) {
+                const int o = __ffs(mset) - 1;
+                int cmp = 0;
+                for (int j = 0; j < kMaxRow && cmp == 0; ++j) cmp = (my[o][j] > my[lane][j]) - (my[o][j] < my[lane][j]);
+                if (cmp == 0) { if (o < lane) keep = false; }
+                else if (cmp < 0) ++rank;
+            }
+        }
+        // rows equal to an earlier kept row must not be counted in anybody's rank
+        const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
+        if (keep) {
+            rank = 0;
+            for (unsigned mset = keep_mask & ~(1u << lane); mset; mset &= mset - 1) {
+                const int o = __ffs(mset) - 1;
+                int cmp = 0;
+                for (int j = 0; j < kMaxRow && cmp == 0; ++j) cmp = (my[o][j] > my[lane][j]) - (my[o][j] < my[lane][j]);
+                if (cmp < 0) ++rank;
+            }
+        }
+        if (mode == 0) {
+            if (lane == 0) rows_per_vertex[a] = __popc(keep_mask);
+            int wmax = keep ? cnt : 0;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
+            if (lane == 0 && wmax) atomicMax(counters + F_WIDTH, wmax);
+        } else if (keep) {
+            const int64_t r = (int64_t)row_off[a] + rank;
+            for (int j = 0; j < W; ++j) rows[r * W + j] = my[lane][j];
+            row_cnt[r] = cnt;
+        }
+        __syncwarp();
+    }
+}
+
+struct ArrayCount {
+    const int *v;
+    __device__ __forceinline__ int operator()(int64_t i) const { return v[i]; }
+};
+struct OffsetEmit {
+    int *off;
+    __device__ __forceinline__ void operator()(int64_t i, int pos, int) const { off[i] = pos; }
+};
+
+// Angular sort of every face row (geometry.py:483-516) around the normal at the face
+// centre (subpoly.py:627-642); rewrites the row in sorted order.
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ NetMeta n, int64_t P, int W,
+                                                        const float *__restrict__ vert, int *__restrict__ rows,
+                                                        const int *__restrict__ row_cnt, int *__restrict__ counters)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
+        const int cnt = row_cnt[p];
+        int *row = rows + p * W;
+        int id[kMaxRow];
+        float px[kMaxRow], py[kMaxRow], pz[kMaxRow], sc[kMaxRow];
+        float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+        bool origin = false;
+        for (int j = 0; j < cnt; ++j) {
+            id[j] = row[j];
+            px[j] = vert[3 * (int64_t)id[j]];
+            py[j] = vert[3 * (int64_t)id[j] + 1];
+            pz[j] = vert[3 * (int64_t)id[j] + 2];
+            sx = sx + px[j];
+            sy = sy + py[j];
+            sz = sz + pz[j];
+            const float n2 = (px[j] * px[j] + py[j] * py[j]) + pz[j] * pz[j];
+            if (!(__fsqrt_rn(n2) > 0.0f)) origin = true;
+        }
+        if (origin) atomicOr(counters + F_ERR_ORIGIN, 1);  // geometry.py:496 would drop this vertex
+        const float k = (float)cnt;
+        float mean[3] = {__fdiv_rn(sx, k), __fdiv_rn(sy, k), __fdiv_rn(sz, k)};
+        float nrm[3];
+        sdf_grad<C>(n, mean, nrm, true);
+        const float a0 = px[0] - mean[0], a1 = py[0] - mean[1], a2 = pz[0] - mean[2];
+        const float an = fmaxf(__fsqrt_rn((a0 * a0 + a1 * a1) + a2 * a2), 1e-8f);
+        const float ua0 = __fdiv_rn(a0, an), ua1 = __fdiv_rn(a1, an), ua2 = __fdiv_rn(a2, an);
+        for (int j = 0; j < cnt; ++j) {
+            const float u0 = px[j] - mean[0], u1 = py[j] - mean[1], u2 = pz[j] - mean[2];
+            const float d0 = a1 * u2 - a2 * u1, d1 = a2 * u0 - a0 * u2, d2 = a0 * u1 - a1 * u0;
+            const float un = fmaxf(__fsqrt_rn((u0 * u0 + u1 * u1) + u2 * u2), 1e-8f);
+            const float c = (ua0 * __fdiv_rn(u0, un) + ua1 * __fdiv_rn(u1, un)) + ua2 * __fdiv_rn(u2, un);
+            const float dn = (d0 * nrm[0] + d1 * nrm[1]) + d2 * nrm[2];
+            sc[j] = c * (dn >= 0.0f ? 1.0f : -1.0f) + (dn < 0.0f ? 2.0f : 0.0f);
+        }
+        // stable descending insertion sort
+        for (int i = 1; i < cnt; ++i) {
+            const float ks = sc[i];
+            const int ki = id[i];
+            int j = i - 1;
+            while (j >= 0 && sc[j] < ks) { sc[j + 1] = sc[j]; id[j + 1] = id[j]; --j; }
+            sc[j + 1] = ks;
+            id[j + 1] = ki;
+        }
+        for (int j = 0; j < cnt; ++j) row[j] = id[j];
+    }
+}
+
+__global__ void k_row_hist(const int *__restrict__ row_cnt, int64_t P, int *__restrict__ hist)
+{
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(hist + row_cnt[p], 1);
+}
+
+struct FanCount {
+    const int *row_cnt;
+    int need;
+    __device__ __forceinline__ int operator()(int64_t p) const { return row_cnt[p] >= need ? 1 : 0; }
+};
+struct FanEmit {  // fan step i: (first, i+1-th, i+2-th), subpoly.py:718-726
+    const int *rows;
+    int W, i;
+    int *tri;
+    __device__ __forceinline__ void operator()(int64_t p, int pos, int) const
+    {
+        const int *row = rows + p * W;
+        tri[3 * (int64_t)pos] = row[0];
+        tri[3 * (int64_t)pos + 1] = row[i + 1];
+        tri[3 * (int64_t)pos + 2] = row[i + 2];
+    }
+};
+
+static int read_small(const int *d, int *h, int n, cudaStream_t s)
+{
+    TNB_CUDA(cudaMemcpyAsync(h, d, n * sizeof(int), cudaMemcpyDeviceToHost, s));
+    TNB_CUDA(cudaStreamSynchronize(s));
+    return TNB_OK;
+}
+
+static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb_mesh *m, cudaStream_t s)
+{
+    const NetMeta &nm = net->meta;
+    const int R = nm.R;
+    const int64_t V = c->V, E = c->E;
+    if (V == 0) return TNB_OK;
+    DevBuf<int> surf, used, remap, block_sums, counters;
+    int h[F_NUM];
+    int rc;
+    TNB_CUDA(surf.reserve((size_t)V));
+    TNB_CUDA(used.reserve((size_t)V));
+    TNB_CUDA(remap.reserve((size_t)V));
+    TNB_CUDA(block_sums.reserve(kScanMaxBlocks));
+    TNB_CUDA(counters.reserve(F_NUM + kMaxRow + 2));
+    TNB_CUDA(cudaMemsetAsync(counters.p, 0, (F_NUM + kMaxRow + 2) * sizeof(int), s));
+    TNB_CUDA(cudaMemsetAsync(used.p, 0, (size_t)V * sizeof(int), s));
+
+    // ---- extract_skeleton ----
+    k_surface_flags<<<grid_for(V, 256), 256, 0, s>>>(nm, c->cvert(), c->cout_(), V, eps, surf.p, counters.p);
+    TNB_LAUNCH_CHECK();
+    DevBuf<int2> tmp_edges;
+    TNB_CUDA(tmp_edges.reserve((size_t)std::max<int64_t>(E, 1)));
+    if ((rc = compact(E, SurfEdgeCount{c->cedges(), surf.p}, SurfEdgeEmit{c->cedges(), tmp_edges.p, used.p},
+                      block_sums.p, counters.p + F_EDGES, s)))
+        return rc;
+    if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
+    if (h[F_SURF] < 3) return TNB_OK;  // subpoly.py:568-569
+    const int64_t Es = h[F_EDGES];
+    // vertex compaction: count first to size the mesh
+    {
+        int64_t blocks = std::min<int64_t>((V + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
+        k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, FlagCount{used.p}, block_sums.p);
+        TNB_LAUNCH_CHECK();
+        std::vector<int> hb(blocks);
+        if ((rc = read_small(block_sums.p, hb.data(), (int)blocks, s))) return rc;
+        int64_t Vs = 0;
+        for (int v : hb) Vs += v;
+        m->V = Vs;
+        m->E = Es;
+        TNB_CUDA(m->vert.reserve((size_t)std::max<int64_t>(Vs, 1) * 3));
+        TNB_CUDA(m->out.reserve((size_t)std::max<int64_t>(Vs, 1) * R));
+        TNB_CUDA(m->edges.reserve((size_t)std::max<int64_t>(Es, 1)));
+        SurfVertEmit ve{c->cvert(), c->cout_(), m->vert.p, m->out.p, remap.p, R};
+        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, FlagCount{used.p}, ve, block_sums.p, counters.p + F_VERTS);
+        TNB_LAUNCH_CHECK();
+    }
+    if (Es > 0) {
+        TNB_CUDA(cudaMemcpyAsync(m->edges.p, tmp_edges.p, (size_t)Es * sizeof(int2), cudaMemcpyDeviceToDevice, s));
+        k_remap_edges2<<<grid_for(Es, 256), 256, 0, s>>>(m->edges.p, Es, remap.p);
+        TNB_LAUNCH_CHECK();
+    }
+    const int64_t Vs = m->V;
+    if (Vs == 0) { TNB_CUDA(cudaStreamSynchronize(s)); return TNB_OK; }
+
+    // ---- extract_faces ----
+    DevBuf<uint64_t> sig;
+    DevBuf<int> next, rows_per_vertex, row_off;
+    DevBuf<unsigned long long> head;
+    TNB_CUDA(sig.reserve((size_t)Vs * 3));
+    TNB_CUDA(next.reserve((size_t)Vs * 8));
+    TNB_CUDA(rows_per_vertex.reserve((size_t)Vs));
+    TNB_CUDA(row_off.reserve((size_t)Vs));
+    const int dim = nm.n_marks + 2;
+    const int64_t n_cells = (int64_t)dim * dim * dim;
+    TNB_CUDA(head.reserve((size_t)n_cells));
+    TNB_CUDA(cudaMemsetAsync(head.p, 0, (size_t)n_cells * sizeof(unsigned long long), s));
+    const uint32_t stamp = 1;
+    const uint64_t colmask = (1ull << (R - 1)) - 1ull;  // m_rgn[:, :-1], subpoly.py:611
+    k_surface_sig<<<grid_for(Vs, kThreads), kThreads, 0, s>>>(nm, m->vert.p, m->out.p, Vs, eps, sig.p);
+    TNB_LAUNCH_CHECK();
+    k_face_bucket_insert<<<grid_for(Vs, 256), 256, 0, s>>>(Vs, sig.p, head.p, next.p, dim, stamp);
+    TNB_LAUNCH_CHECK();
+    const unsigned gw = grid_for(Vs, kThreads / 32);
+    k_region_rows<<<gw, kThreads, 0, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 0, rows_per_vertex.p, nullptr,
+                                         nullptr, nullptr, 0, counters.p);
+    TNB_LAUNCH_CHECK();
+    if ((rc = compact(Vs, ArrayCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
+    if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
+    if (h[F_ERR_ZEROS]) { set_error("a surface vertex lies on more than 5 planes: more than 32 adjacent regions"); return TNB_ERR_UNSUPPORTED; }
+    if (h[F_ERR_ROW]) { set_error("a face has more than 32 vertices"); return TNB_ERR_UNSUPPORTED; }
+    const int64_t P = h[F_ROWS];
+    const int W = h[F_WIDTH];
+    m->P = P;
+    m->W = W;
+    if (P == 0) { TNB_CUDA(cudaStreamSynchronize(s)); return TNB_OK; }
+    TNB_CUDA(m->poly.reserve((size_t)P * W));
+    TNB_CUDA(m->pcnt.reserve((size_t)P));
+    k_region_rows<<<gw, kThreads, 0, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 1, rows_per_vertex.p, row_off.p,
+                                         m->poly.p, m->pcnt.p, W, counters.p);
+    TNB_LAUNCH_CHECK();
+    {
+        unsigned g = grid_for(P, kThreads);
+        if (net->fixed_cfg) k_sort_rows<CfgRef><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, counters.p);
+        else k_sort_rows<CfgAny><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, counters.p);
+        TNB_LAUNCH_CHECK();
+    }
+    // fan triangles, ordered by fan step then by row
+    int *hist = counters.p + F_NUM;
+    k_row_hist<<<grid_for(P, 256), 256, 0, s>>>(m->pcnt.p, P, hist);
+    TNB_LAUNCH_CHECK();
+    int hh[F_NUM + kMaxRow + 2];
+    if ((rc = read_small(counters.p, hh, F_NUM + kMaxRow + 2, s))) return rc;
+    if (hh[F_ERR_ORIGIN]) {
+        set_error("a face vertex sits exactly at the origin (geometry.py:496 treats it as padding): unsupported");
+        return TNB_ERR_UNSUPPORTED;
+    }
+    std::vector<int64_t> base(W, 0);
+    int64_t T = 0;
+    for (int i = 0; i + 3 <= W; ++i) {
+        int64_t ni = 0;
+        for (int cc = i + 3; cc <= W; ++cc) ni += hh[F_NUM + cc];
+        base[i] = T;
+        T += ni;
+    }
+    m->T = T;
+    TNB_CUDA(m->tri.reserve((size_t)std::max<int64_t>(T, 1) * 3));
+    for (int i = 0; i + 3 <= W; ++i) {
+        if ((rc = compact(P, FanCount{m->pcnt.p, i + 3}, FanEmit{m->poly.p, W, i, m->tri.p + 3 * base[i]}, block_sums.p,
+                          counters.p + F_VERTS, s)))
+            return rc;
+    }
+    TNB_CUDA(cudaStreamSynchronize(s));  // locals are freed on return
+    return TNB_OK;
+}
+
+// ---- read back -------------------------------------------------------------------------------------
+__global__ void k_i32_to_i64(const int *__restrict__ src, int64_t n, int64_t *__restrict__ dst)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+__global__ void k_tri_positions(const int *__restrict__ tri, int64_t T, const float *__restrict__ vert, float *__restrict__ faces)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < T * 3; i += (int64_t)gridDim.x * blockDim.x) {
+        const int v = tri[i];
+        faces[3 * i] = vert[3 * (int64_t)v];
+        faces[3 * i + 1] = vert[3 * (int64_t)v + 1];
+        faces[3 * i + 2] = vert[3 * (int64_t)v + 2];
+    }
+}
+
+}  // namespace tnb
+
+using namespace tnb;
+
+extern "C" {
+
+int tnb_extract_mesh(const tnb_net *net, const tnb_complex *c, float eps, tnb_mesh **out, void *stream)
+{
+    if (!net || !c || !out) { set_error("tnb_extract_mesh: null argument"); return TNB_ERR_INVALID; }
+    tnb_mesh *m = new tnb_mesh();
+    int rc = extract_impl(net, c, eps, m, (cudaStream_t)stream);
+    if (rc != TNB_OK) { delete m; *out = nullptr; return rc; }
+    *out = m;
+    return TNB_OK;
+}
+
+void tnb_mesh_destroy(tnb_mesh *m) { delete m; }
+int64_t tnb_mesh_num_vertices(const tnb_mesh *m) { return m ? m->V : 0; }
+int64_t tnb_mesh_num_edges(const tnb_mesh *m) { return m ? m->E : 0; }
+int64_t tnb_mesh_num_triangles(const tnb_mesh *m) { return m ? m->T : 0; }
+int64_t tnb_mesh_num_polygons(const tnb_mesh *m) { return m ? m->P : 0; }
+int64_t tnb_mesh_polygon_width(const tnb_mesh *m) { return m ? m->W : 0; }
+
+int tnb_mesh_read(const tnb_mesh *m, float *d_vertices, int64_t *d_edges, int64_t *d_triangles, float *d_faces,
+                  int64_t *d_polygons, void *stream)
+{
+    if (!m) { set_error("tnb_mesh_read: null mesh"); return TNB_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (d_vertices && m->V) TNB_CUDA(cudaMemcpyAsync(d_vertices, m->vert.p, (size_t)m->V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    if (d_edges && m->E) {
+        k_i32_to_i64<<<grid_for(m->E * 2, 256), 256, 0, s>>>((const int *)m->edges.p, m->E * 2, d_edges);
+        TNB_LAUNCH_CHECK();
+    }
+    if (d_triangles && m->T) {
+        k_i32_to_i64<<<grid_for(m->T * 3, 256), 256, 0, s>>>(m->tri.p, m->T * 3, d_triangles);
+        TNB_LAUNCH_CHECK();
+    }
+    if (d_faces && m->T) {
+        k_tri_positions<<<grid_for(m->T * 3, 256), 256, 0, s>>>(m->tri.p, m->T, m->vert.p, d_faces);
+        TNB_LAUNCH_CHECK();
+    }
+    if (d_polygons && m->P) {
+        k_i32_to_i64<<<grid_for(m->P * m->W, 256), 256, 0, s>>>(m->poly.p, m->P * m->W, d_polygons);
+        TNB_LAUNCH_CHECK();
+    }
+    return TNB_OK;
+}
+
+int tnb_mesh_read_host(const tnb_mesh *m, float *h_vertices, int64_t *h_triangles, float *h_faces, int64_t *h_polygons)
+{
+    if (!m) { set_error("tnb_mesh_read_host: null mesh"); return TNB_ERR_INVALID; }
+    DevBuf<int64_t> t64, p64;
+    DevBuf<float> f;
+    if (h_vertices && m->V) TNB_CUDA(cudaMemcpy(h_vertices, m->vert.p, (size_t)m->V * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (h_triangles && m->T) {
+        TNB_CUDA(t64.reserve((size_t)m->T * 3));
+        k_i32_to_i64<<<grid_for(m->T * 3, 256), 256>>>(m->tri.p, m->T * 3, t64.p);
+        TNB_LAUNCH_CHECK();
+        TNB_CUDA(cudaMemcpy(h_triangles, t64.p, (size_t)m->T * 3 * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    }
+    if (h_faces && m->T) {
+        TNB_CUDA(f.reserve((size_t)m->T * 9));
+        k_tri_positions<<<grid_for(m->T * 3, 256), 256>>>(m->tri.p, m->T, m->vert.p, f.p);
+        TNB_LAUNCH_CHECK();
+        TNB_CUDA(cudaMemcpy(h_faces, f.p, (size_t)m->T * 9 * sizeof(float), cudaMemcpyDeviceToHost));
+    }
+    if (h_polygons && m->P) {
+        TNB_CUDA(p64.reserve((size_t)m->P * m->W));
+        k_i32_to_i64<<<grid_for(m->P * m->W, 256), 256>>>(m->poly.p, m->P * m->W, p64.p);
+        TNB_LAUNCH_CHECK();
+        TNB_CUDA(cudaMemcpy(h_polygons, p64.p, (size_t)m->P * m->W * sizeof(int64_t), cudaMemcpyDeviceToHost));
+    }
+    return TNB_OK;
+}
+
+int tnb_subpoly(const tnb_net *net, float size, float eps, int32_t force, int32_t unit, tnb_mesh **out, void *stream)
+{
+    if (!net || !out) { set_error("tnb_subpoly: null argument"); return TNB_ERR_INVALID; }
+    *out = nullptr;
+    tnb_complex *c = nullptr;
+    int rc = tnb_skeleton(net, unit, size, &c, stream);
+    if (rc != TNB_OK) return rc;
+    const int H = net->meta.H, NL = net->meta.NLIN;
+    for (int l = 0; l < NL - 1 && rc == TNB_OK; ++l)
+        for (int h = 0; h < H && rc == TNB_OK; ++h) rc = tnb_subpoly_step(net, c, l, h, eps, force, stream);
+    if (rc == TNB_OK) rc = tnb_subpoly_step(net, c, NL - 2, H, eps, force, stream);  // the output neuron
+    if (rc == TNB_OK) rc = tnb_extract_mesh(net, c, eps, out, stream);
+    tnb_complex_destroy(c);
+    return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,202 @@
+// net_eval.cuh -- per-point evaluation of the trilinear network (hash grid fused with
+// the ReLU MLP), forward and input-gradient.  Replaces, for the mesh-extraction path,
+// TropicalHashGrid.forward (tropical.py:46) + Net.forward(gather=True) (model.py:52-76)
+// + the autograd x-gradient of Net.sdf (tropical.py:190-195, model.py:105-123).
+//
+// Cfg<L,H,NLIN> fixes the sizes at compile time (all loops unroll, the MLP weights are
+// read as constant-bank FFMA operands out of the kernel parameter block); Cfg<0,0,0> is
+// the runtime-sized fallback for other Net(...) shapes.
+#pragma once
+#include "common.cuh"
+
+namespace tnb {
+
+template <int kL, int kH, int kNLIN>
+struct Cfg {
+    static constexpr bool kFixed = kL > 0;
+    static constexpr int kMaxL = kFixed ? kL : kMaxLevels;
+    static constexpr int kMaxH = kFixed ? kH : kMaxHidden;
+    static constexpr int kMaxLin = kFixed ? kNLIN : kMaxLinear;
+    static constexpr int kMaxW = (2 * kMaxL > kMaxH) ? 2 * kMaxL : kMaxH;  // widest activation
+    static constexpr int kUnroll = kFixed ? 64 : 1;  // full unroll only for compile-time sizes
+    __device__ __forceinline__ static int L(const NetMeta &n) { return kFixed ? kL : n.L; }
+    __device__ __forceinline__ static int H(const NetMeta &n) { return kFixed ? kH : n.H; }
+    __device__ __forceinline__ static int NLIN(const NetMeta &n) { return kFixed ? kNLIN : n.NLIN; }
+    __device__ __forceinline__ static float w(const NetMeta &n, int i)
+    {
+        if (kFixed) return n.mlp_c[i];
+        return __ldg(n.mlp + i);
+    }
+    __device__ __forceinline__ static int nin(const NetMeta &n, int i) { return i == 0 ? 2 * L(n) : H(n); }
+    __device__ __forceinline__ static int nout(const NetMeta &n, int i) { return i == NLIN(n) - 1 ? 2 : H(n); }
+};
+
+using CfgRef = Cfg<4, 16, 3>;  // every network the reference builds (train.py:82)
+using CfgAny = Cfg<0, 0, 0>;
+
+// Forward pass from grid coordinates.  pre[(i*maxH)+j] = pre-activation j of hidden
+// layer i; o[2] = last layer.
+template <class C>
+__device__ __forceinline__ void forward(const NetMeta &n, const float xp[3],
+                                        float *__restrict__ pre, float o[2])
+{
+    float act[C::kMaxW];
+#pragma unroll(C::kUnroll)
+    for (int l = 0; l < C::kMaxL; ++l) {
+        if (l < C::L(n)) {
+            uint32_t cell[3];
+            float frac[3];
+            float2 f = encode_level(n, l, xp, cell, frac);
+            act[2 * l] = f.x;
+            act[2 * l + 1] = f.y;
+        }
+    }
+    int base = 0;
+#pragma unroll(C::kUnroll)
+    for (int i = 0; i < C::kMaxLin; ++i) {
+        if (i < C::NLIN(n)) {
+            const int ni = C::nin(n, i), no = C::nout(n, i);
+            const bool last = i == C::NLIN(n) - 1;
+            float nxt[C::kMaxH];
+#pragma unroll(C::kUnroll)
+            for (int j = 0; j < C::kMaxH; ++j) {
+                if (j < no) {
+                    float acc = C::w(n, base + no * ni + j);
+#pragma unroll(C::kUnroll)
+                    for (int c = 0; c < C::kMaxW; ++c)
+                        if (c < ni) acc = __fmaf_rn(act[c], C::w(n, base + j * ni + c), acc);
+                    nxt[j] = acc;
+                }
+            }
+            if (last) {
+                o[0] = nxt[0];
+                o[1] = nxt[1];
+            } else {
+#pragma unroll(C::kUnroll)
+                for (int j = 0; j < C::kMaxH; ++j)
+                    if (j < no) {
+                        pre[i * C::kMaxH + j] = nxt[j];
+                        act[j] = nxt[j] > 0.0f ? nxt[j] : 0.0f;
+                    }
+            }
+            base += no * ni + no;
+        }
+    }
+}
+
+// tanh(o1-o0) and its gradient w.r.t. the world-space input.
+template <class C>
+__device__ __forceinline__ float sdf_grad(const NetMeta &n, const float x[3], float grad[3],
+                                          bool want_grad)
+{
+    float xp[3];
+    preprocess(n, x, xp);
+    float pre[(C::kMaxLin - 1) * C::kMaxH];
+    float o[2];
+    forward<C>(n, xp, pre, o);
+    const float t = det_tanhf(o[1] - o[0]);
+    if (!want_grad) return t;
+    const float gs = 1.0f - t * t;
+    float g_out[C::kMaxW], g_in[C::kMaxW];
+    g_out[0] = -gs;
+    g_out[1] = gs;
+    // offsets of the packed layers
+    int base[C::kMaxLin];
+    {
+        int b = 0;
+#pragma unroll(C::kUnroll)
+        for (int i = 0; i < C::kMaxLin; ++i)
+            if (i < C::NLIN(n)) { base[i] = b; b += C::nout(n, i) * C::nin(n, i) + C::nout(n, i); }
+    }
+#pragma unroll(C::kUnroll)
+    for (int k = C::kMaxLin - 1; k >= 0; --k) {
+        if (k < C::NLIN(n)) {
+            const int ni = C::nin(n, k), no = C::nout(n, k);
+#pragma unroll(C::kUnroll)
+            for (int c = 0; c < C::kMaxW; ++c) {
+                if (c < ni) {
+                    float acc = 0.0f;
+#pragma unroll(C::kUnroll)
+                    for (int j = 0; j < C::kMaxH; ++j)
+                        if (j < no) acc = __fmaf_rn(C::w(n, base[k] + j * ni + c), g_out[j], acc);
+                    g_in[c] = acc;
+                }
+            }
+            if (k > 0) {
+#pragma unroll(C::kUnroll)
+                for (int c = 0; c < C::kMaxH; ++c)
+                    if (c < ni) g_out[c] = pre[(k - 1) * C::kMaxH + c] > 0.0f ? g_in[c] : 0.0f;
+            }
+        }
+    }
+    float acc[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll(C::kUnroll)
+    for (int l = 0; l < C::kMaxL; ++l) {
+        if (l < C::L(n)) {
+            uint32_t cell[3];
+            float frac[3];
+            const LevelMeta lv = n.lvl[l];
+#pragma unroll(C::kUnroll)
+            for (int d = 0; d < 3; ++d) {
+                float pos = __fmaf_rn(lv.scale, xp[d], 0.5f);
+                float fl = floorf(pos);
+                cell[d] = (uint32_t)(int)fl;
+                frac[d] = pos - fl;
+            }
+#pragma unroll(C::kUnroll)
+            for (int d = 0; d < 3; ++d) {
+                float2 dl = encode_level_dx(n, l, d, cell, frac);
+                acc[d] = __fmaf_rn(g_in[2 * l], dl.x, acc[d]);
+                acc[d] = __fmaf_rn(g_in[2 * l + 1], dl.y, acc[d]);
+            }
+        }
+    }
+#pragma unroll(C::kUnroll)
+    for (int d = 0; d < 3; ++d) grad[d] = __fdiv_rn(acc[d], n.pre_2s);
+    return t;
+}
+
+__device__ __forceinline__ float grad_norm(const float g[3])
+{
+    float s = g[0] * g[0];
+    s = __fmaf_rn(g[1], g[1], s);
+    s = __fmaf_rn(g[2], g[2], s);
+    return __fsqrt_rn(s);
+}
+
+// One row of torch.cat(Net.forward(x, gather=True)[1], -1): R floats to `row`
+// (stride 1), from world coordinates.
+template <class C>
+__device__ __forceinline__ void outputs_row(const NetMeta &n, const float x[3], float *__restrict__ row)
+{
+    float xp[3];
+    preprocess(n, x, xp);
+    float pre[(C::kMaxLin - 1) * C::kMaxH];
+    float o[2];
+    forward<C>(n, xp, pre, o);
+    const int H = C::H(n), NL = C::NLIN(n);
+#pragma unroll(C::kUnroll)
+    for (int i = 0; i < C::kMaxLin - 1; ++i)
+        if (i < NL - 1) {
+#pragma unroll(C::kUnroll)
+            for (int j = 0; j < C::kMaxH; ++j)
+                if (j < H) row[i * H + j] = pre[i * C::kMaxH + j];
+        }
+    row[(NL - 1) * H] = o[1] - o[0];
+}
+
+// sign bits of a row of outputs (model.py:97-98)
+__device__ __forceinline__ void pack_signs(const float *__restrict__ row, int R, float eps,
+                                           uint64_t &pos, uint64_t &neg)
+{
+    pos = 0;
+    neg = 0;
+    for (int c = 0; c < R; ++c) {
+        float v = row[c];
+        if (!(fabsf(v) <= eps)) {
+            if (v > 0.0f) pos |= 1ull << c; else neg |= 1ull << c;
+        }
+    }
+}
+
+}  // namespace tnb

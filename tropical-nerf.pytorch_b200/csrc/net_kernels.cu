@@ -1,0 +1,355 @@
+// net_kernels.cu -- network-level entry points of the C ABI: hash-grid encoding, fused
+// trilinear evaluation, SDF + input gradient, region indicators, dense sign sweep.
+#include <cmath>
+#include <cstring>
+#include <mutex>
+
+#include "net_eval.cuh"
+#include "runtime.cuh"
+
+namespace tnb {
+
+// ---- error state ---------------------------------------------------------------------
+static thread_local std::string g_error;
+static thread_local int64_t g_launches = 0;
+void set_error(const std::string &msg) { g_error = msg; }
+int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
+{
+    g_error = std::string("CUDA error: ") + cudaGetErrorString(e) + " in " + what + " (" + file + ":" +
+              std::to_string(line) + ")";
+    return TNB_ERR_CUDA;
+}
+void count_launch(int n) { g_launches += n; }
+
+constexpr int kThreads = 128;
+
+// ---- kernels ---------------------------------------------------------------------------
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_encode(const __grid_constant__ NetMeta n,
+                                                     const float *__restrict__ xp, int64_t count,
+                                                     float *__restrict__ enc)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float p[3] = {xp[3 * i], xp[3 * i + 1], xp[3 * i + 2]};
+        const int L = C::L(n);
+#pragma unroll(C::kUnroll)
+        for (int l = 0; l < C::kMaxL; ++l)
+            if (l < L) {
+                uint32_t cell[3];
+                float frac[3];
+                float2 f = encode_level(n, l, p, cell, frac);
+                enc[i * (2 * L) + 2 * l] = f.x;
+                enc[i * (2 * L) + 2 * l + 1] = f.y;
+            }
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_outputs(const __grid_constant__ NetMeta n,
+                                                      const float *__restrict__ x, int64_t count,
+                                                      float *__restrict__ out)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float p[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]};
+        outputs_row<C>(n, p, out + i * n.R);
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_sdf_grad(const __grid_constant__ NetMeta n,
+                                                       const float *__restrict__ x, int64_t count,
+                                                       float *__restrict__ sdf, float *__restrict__ grad)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float p[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]};
+        float g[3];
+        float t = sdf_grad<C>(n, p, g, grad != nullptr);
+        sdf[i] = t;
+        if (grad) {
+            grad[3 * i] = g[0];
+            grad[3 * i + 1] = g[1];
+            grad[3 * i + 2] = g[2];
+        }
+    }
+}
+
+// outputs must be given (evaluated by k_outputs beforehand when the caller has none)
+__global__ void __launch_bounds__(kThreads) k_region(const __grid_constant__ NetMeta n,
+                                                     const float *__restrict__ x,
+                                                     const float *__restrict__ outputs, int64_t count,
+                                                     float eps, int8_t *__restrict__ signs,
+                                                     int32_t *__restrict__ offset,
+                                                     uint64_t *__restrict__ packed)
+{
+    const int R = n.R;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        float p[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]};
+        float xp[3];
+        preprocess(n, p, xp);
+        uint64_t g = pack_grid(n, n.marks, xp, eps);
+        uint64_t pos, neg;
+        pack_signs(outputs + i * R, R, eps, pos, neg);
+        if (packed) {
+            packed[3 * i] = pos;
+            packed[3 * i + 1] = neg;
+            packed[3 * i + 2] = g;
+        }
+        if (offset)
+            for (int d = 0; d < 3; ++d) offset[3 * i + d] = grid_off(g, d);
+        if (signs) {
+            int8_t *s = signs + i * (3 + R);
+            for (int d = 0; d < 3; ++d) s[d] = (int8_t)grid_mask(g, d);
+            for (int c = 0; c < R; ++c)
+                s[3 + c] = (int8_t)(((pos >> c) & 1) ? 1 : (((neg >> c) & 1) ? -1 : 0));
+        }
+    }
+}
+
+// Dense lattice sweep: evaluate + bit-pack, nothing but 16 B per point leaves the SM.
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_sweep_signs(const __grid_constant__ NetMeta n, float3 lo,
+                                                          float3 step, int nx, int ny, int nz,
+                                                          float eps, ulonglong2 *__restrict__ packed)
+{
+    const int64_t count = (int64_t)nx * ny * nz;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        int iz = (int)(i % nz);
+        int iy = (int)((i / nz) % ny);
+        int ix = (int)(i / ((int64_t)nz * ny));
+        float p[3] = {__fmaf_rn((float)ix, step.x, lo.x), __fmaf_rn((float)iy, step.y, lo.y),
+                      __fmaf_rn((float)iz, step.z, lo.z)};
+        float xp[3];
+        preprocess(n, p, xp);
+        float pre[(C::kMaxLin - 1) * C::kMaxH];
+        float o[2];
+        forward<C>(n, xp, pre, o);
+        uint64_t pos = 0, neg = 0;
+        const int H = C::H(n), NL = C::NLIN(n);
+#pragma unroll(C::kUnroll)
+        for (int l = 0; l < C::kMaxLin - 1; ++l)
+            if (l < NL - 1) {
+#pragma unroll(C::kUnroll)
+                for (int j = 0; j < C::kMaxH; ++j)
+                    if (j < H) {
+                        float v = pre[l * C::kMaxH + j];
+                        if (!(fabsf(v) <= eps)) {
+                            if (v > 0.0f) pos |= 1ull << (l * H + j); else neg |= 1ull << (l * H + j);
+                        }
+                    }
+            }
+        float v = o[1] - o[0];
+        if (!(fabsf(v) <= eps)) {
+            if (v > 0.0f) pos |= 1ull << ((NL - 1) * H); else neg |= 1ull << ((NL - 1) * H);
+        }
+        packed[i] = make_ulonglong2(pos, neg);
+    }
+}
+
+// ---- launchers shared with the complex code ----------------------------------------------
+int launch_outputs(const tnb_net *net, const float *d_x, int64_t n, float *d_out, cudaStream_t s)
+{
+    if (n <= 0) return TNB_OK;
+    unsigned g = grid_for(n, kThreads);
+    if (net->fixed_cfg) k_outputs<CfgRef><<<g, kThreads, 0, s>>>(net->meta, d_x, n, d_out);
+    else k_outputs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, d_x, n, d_out);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+
+int launch_sdf_grad(const tnb_net *net, const float *d_x, int64_t n, float *d_sdf, float *d_grad,
+                    cudaStream_t s)
+{
+    if (n <= 0) return TNB_OK;
+    unsigned g = grid_for(n, kThreads);
+    if (net->fixed_cfg) k_sdf_grad<CfgRef><<<g, kThreads, 0, s>>>(net->meta, d_x, n, d_sdf, d_grad);
+    else k_sdf_grad<CfgAny><<<g, kThreads, 0, s>>>(net->meta, d_x, n, d_sdf, d_grad);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+
+int launch_region(const tnb_net *net, const float *d_x, const float *d_outputs, int64_t n, float eps,
+                  int8_t *d_signs, int32_t *d_offset, uint64_t *d_packed, cudaStream_t s)
+{
+    if (n <= 0) return TNB_OK;
+    k_region<<<grid_for(n, kThreads), kThreads, 0, s>>>(net->meta, d_x, d_outputs, n, eps, d_signs,
+                                                       d_offset, d_packed);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+
+}  // namespace tnb
+
+using namespace tnb;
+
+// ---- C ABI ------------------------------------------------------------------------------------
+extern "C" {
+
+const char *tnb_last_error(void) { return g_error.c_str(); }
+int tnb_version(void) { return 100; }
+int tnb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+int64_t tnb_launch_count(void) { return g_launches; }
+void tnb_launch_count_reset(void) { g_launches = 0; }
+
+int tnb_net_create(const tnb_net_desc *d, tnb_net **out)
+{
+    if (!d || !out) { set_error("tnb_net_create: null argument"); return TNB_ERR_INVALID; }
+    *out = nullptr;
+    if (d->n_features != 2) { set_error("only n_features_per_level == 2 is supported (model.py:32)"); return TNB_ERR_UNSUPPORTED; }
+    if (d->n_levels < 1 || d->n_levels > kMaxLevels || d->num_layers < 2 || d->num_layers > kMaxLinear ||
+        d->num_hidden < 1 || d->num_hidden > kMaxHidden) {
+        set_error("tnb_net_create: network shape out of range");
+        return TNB_ERR_INVALID;
+    }
+    const int R = (d->num_layers - 1) * d->num_hidden + 1;
+    if (R > 64) { set_error("more than 64 neurons: sign vectors do not fit the packed words"); return TNB_ERR_UNSUPPORTED; }
+    if (d->n_marks < 2 || d->n_marks >= (1 << 20) - 2) { set_error("tnb_net_create: bad n_marks"); return TNB_ERR_INVALID; }
+    if (tnb_device_count() == 0) { set_error("no CUDA device: this library has no CPU path"); return TNB_ERR_CUDA; }
+
+    tnb_net *net = new tnb_net();
+    NetMeta &m = net->meta;
+    memset(&m, 0, sizeof(m));
+    m.L = d->n_levels; m.H = d->num_hidden; m.NLIN = d->num_layers; m.R = R;
+    m.pre_scale = d->scale; m.pre_2s = d->scale * 2.0f; m.eps = d->eps; m.n_marks = d->n_marks;
+    // level layout exactly as tiny-cuda-nn's GridEncoding constructor derives it
+    const float log2_pls = std::log2((float)d->per_level_scale);
+    uint64_t total = 0;
+    for (int l = 0; l < m.L; ++l) {
+        float scale = std::exp2((float)l * log2_pls) * (float)d->base_resolution - 1.0f;
+        uint32_t res = (uint32_t)std::ceil(scale) + 1u;
+        const uint32_t max_params = 0xFFFFFFFFu / 2;
+        uint32_t n = std::pow((float)res, 3.0f) > (float)max_params ? max_params : res * res * res;
+        n = (n + 7u) / 8u * 8u;
+        uint32_t cap = 1u << d->log2_hashmap;
+        if (n > cap) n = cap;
+        m.lvl[l] = LevelMeta{scale, res, n, (uint32_t)total};
+        net->h_scale.push_back(scale); net->h_res.push_back(res); net->h_size.push_back(n);
+        net->h_off.push_back((uint32_t)total);
+        total += n;
+    }
+    if ((int64_t)total * 2 != d->table_len) {
+        set_error("tnb_net_create: table_len " + std::to_string(d->table_len) + " != 2 * " + std::to_string(total));
+        delete net;
+        return TNB_ERR_INVALID;
+    }
+    int64_t mlp_len = 0;
+    for (int i = 0; i < m.NLIN; ++i) {
+        int ni = i == 0 ? 2 * m.L : m.H, no = i == m.NLIN - 1 ? 2 : m.H;
+        mlp_len += (int64_t)no * ni + no;
+    }
+    if (mlp_len != d->mlp_len) { set_error("tnb_net_create: mlp_len mismatch"); delete net; return TNB_ERR_INVALID; }
+
+    cudaError_t e;
+    if ((e = net->table.reserve(total)) != cudaSuccess || (e = net->mlp.reserve(mlp_len)) != cudaSuccess ||
+        (e = net->marks.reserve(d->n_marks)) != cudaSuccess) {
+        delete net;
+        return cuda_fail(e, "cudaMalloc(net)", __FILE__, __LINE__);
+    }
+    if ((e = cudaMemcpy(net->table.p, d->table, total * sizeof(float2), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(net->mlp.p, d->mlp, mlp_len * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess ||
+        (e = cudaMemcpy(net->marks.p, d->marks, d->n_marks * sizeof(float), cudaMemcpyHostToDevice)) != cudaSuccess) {
+        delete net;
+        return cuda_fail(e, "cudaMemcpy(net)", __FILE__, __LINE__);
+    }
+    m.table = net->table.p; m.mlp = net->mlp.p; m.marks = net->marks.p;
+    net->h_marks.assign(d->marks, d->marks + d->n_marks);
+    if (mlp_len <= kMlpParamMax) {
+        memcpy(m.mlp_c, d->mlp, mlp_len * sizeof(float));
+        m.mlp_in_param = 1;
+    }
+    net->fixed_cfg = m.mlp_in_param && m.L == 4 && m.H == 16 && m.NLIN == 3;
+    *out = net;
+    return TNB_OK;
+}
+
+void tnb_net_destroy(tnb_net *net) { delete net; }
+int tnb_net_num_outputs(const tnb_net *net) { return net ? net->meta.R : 0; }
+
+int tnb_net_level_layout(const tnb_net *net, float *scale, uint32_t *res, uint32_t *size, uint32_t *offset)
+{
+    if (!net) { set_error("null net"); return TNB_ERR_INVALID; }
+    for (int l = 0; l < net->meta.L; ++l) {
+        if (scale) scale[l] = net->h_scale[l];
+        if (res) res[l] = net->h_res[l];
+        if (size) size[l] = net->h_size[l];
+        if (offset) offset[l] = net->h_off[l];
+    }
+    return TNB_OK;
+}
+
+int tnb_grid_encode(const tnb_net *net, const float *d_xp, int64_t n, float *d_enc, void *stream)
+{
+    if (!net || (n > 0 && (!d_xp || !d_enc))) { set_error("tnb_grid_encode: null argument"); return TNB_ERR_INVALID; }
+    if (n <= 0) return TNB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned g = grid_for(n, kThreads);
+    if (net->fixed_cfg) k_encode<CfgRef><<<g, kThreads, 0, s>>>(net->meta, d_xp, n, d_enc);
+    else k_encode<CfgAny><<<g, kThreads, 0, s>>>(net->meta, d_xp, n, d_enc);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+
+int tnb_net_outputs(const tnb_net *net, const float *d_x, int64_t n, float *d_out, void *stream)
+{
+    if (!net || (n > 0 && (!d_x || !d_out))) { set_error("tnb_net_outputs: null argument"); return TNB_ERR_INVALID; }
+    return launch_outputs(net, d_x, n, d_out, (cudaStream_t)stream);
+}
+
+int tnb_net_sdf_grad(const tnb_net *net, const float *d_x, int64_t n, float *d_sdf, float *d_grad, void *stream)
+{
+    if (!net || (n > 0 && (!d_x || !d_sdf))) { set_error("tnb_net_sdf_grad: null argument"); return TNB_ERR_INVALID; }
+    return launch_sdf_grad(net, d_x, n, d_sdf, d_grad, (cudaStream_t)stream);
+}
+
+int tnb_net_region(const tnb_net *net, const float *d_x, const float *d_outputs, int64_t n, float eps,
+                   int8_t *d_signs, int32_t *d_offset, uint64_t *d_packed, void *stream)
+{
+    if (!net || (n > 0 && !d_x)) { set_error("tnb_net_region: null argument"); return TNB_ERR_INVALID; }
+    if (n <= 0) return TNB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    DevBuf<float> tmp;
+    if (!d_outputs) {
+        TNB_CUDA(tmp.reserve((size_t)n * net->meta.R));
+        int rc = launch_outputs(net, d_x, n, tmp.p, s);
+        if (rc) return rc;
+        d_outputs = tmp.p;
+    }
+    int rc = launch_region(net, d_x, d_outputs, n, eps, d_signs, d_offset, d_packed, s);
+    if (rc) return rc;
+    if (tmp.p) TNB_CUDA(cudaStreamSynchronize(s));  // tmp is freed on return
+    return TNB_OK;
+}
+
+int tnb_sweep_signs(const tnb_net *net, const float lo[3], const float hi[3], const int32_t nn[3], float eps,
+                    uint64_t *d_packed, void *stream)
+{
+    if (!net || !lo || !hi || !nn || !d_packed) { set_error("tnb_sweep_signs: null argument"); return TNB_ERR_INVALID; }
+    if (nn[0] < 1 || nn[1] < 1 || nn[2] < 1) { set_error("tnb_sweep_signs: empty lattice"); return TNB_ERR_INVALID; }
+    float3 l = make_float3(lo[0], lo[1], lo[2]);
+    float3 st = make_float3(nn[0] > 1 ? (hi[0] - lo[0]) / (float)(nn[0] - 1) : 0.0f,
+                            nn[1] > 1 ? (hi[1] - lo[1]) / (float)(nn[1] - 1) : 0.0f,
+                            nn[2] > 1 ? (hi[2] - lo[2]) / (float)(nn[2] - 1) : 0.0f);
+    int64_t count = (int64_t)nn[0] * nn[1] * nn[2];
+    cudaStream_t s = (cudaStream_t)stream;
+    unsigned g = grid_for(count, kThreads, kSMs * 32);
+    if (net->fixed_cfg)
+        k_sweep_signs<CfgRef><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], eps, (ulonglong2 *)d_packed);
+    else
+        k_sweep_signs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], eps, (ulonglong2 *)d_packed);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+
+}  // extern "C"

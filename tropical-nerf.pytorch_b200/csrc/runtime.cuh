@@ -1,0 +1,59 @@
+// runtime.cuh -- host-side objects behind the C ABI handles.
+#pragma once
+#include <vector>
+
+#include "common.cuh"
+
+namespace tnb {
+
+// RAII device array
+template <class T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    DevBuf() = default;
+    DevBuf(const DevBuf &) = delete;
+    DevBuf &operator=(const DevBuf &) = delete;
+    ~DevBuf() { release(); }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+    // (re)allocate without preserving contents
+    cudaError_t reserve(size_t n)
+    {
+        if (n <= cap) return cudaSuccess;
+        release();
+        cudaError_t e = cudaMalloc((void **)&p, (n ? n : 1) * sizeof(T));
+        if (e == cudaSuccess) cap = n; else p = nullptr;
+        return e;
+    }
+    void swap(DevBuf &o)
+    {
+        T *tp = p; p = o.p; o.p = tp;
+        size_t tc = cap; cap = o.cap; o.cap = tc;
+    }
+};
+
+inline unsigned grid_for(int64_t n, int threads, int max_blocks = kSMs * 16)
+{
+    int64_t b = (n + threads - 1) / threads;
+    if (b < 1) b = 1;
+    if (b > max_blocks) b = max_blocks;
+    return (unsigned)b;
+}
+
+}  // namespace tnb
+
+struct tnb_net {
+    tnb::NetMeta meta;
+    bool fixed_cfg = false;  // CfgRef applies
+    tnb::DevBuf<float2> table;
+    tnb::DevBuf<float> mlp;
+    tnb::DevBuf<float> marks;
+    std::vector<float> h_marks;
+    std::vector<float> h_scale;
+    std::vector<uint32_t> h_res, h_size, h_off;
+};

@@ -1,0 +1,135 @@
+// scan.cuh -- order-preserving stream compaction / exclusive scan built on warp-level
+// prefix scans.  This replaces the torch boolean indexing (`x[mask]`), `nonzero`,
+// `masked_scatter_` and `unique(return_inverse=True)` calls the reference uses to
+// compact vertices and edges (e.g. subpoly.py:113-114, :210-218, :265-272;
+// tropical.py:93-102, :211-220): the output order is exactly the input order, which is
+// what keeps vertex and edge numbering identical to the reference.
+//
+// Two launches per compaction over a fixed grid:
+//   count:  every block owns one contiguous slice of the index space and adds up
+//           count(i) of its slice (warp shuffle reduction) -> block_sums[b]
+//   write:  every block sums block_sums[0..b) for its base offset, then walks its
+//           slice tile by tile; inside a tile an inclusive warp scan (shfl_up) plus a
+//           scan over the warp totals gives each item its exclusive position, and
+//           emit(i, position, count) places it.
+#pragma once
+#include "common.cuh"
+
+namespace tnb {
+
+constexpr int kScanThreads = 256;
+constexpr int kScanWarps = kScanThreads / 32;
+constexpr int kScanMaxBlocks = kSMs * 4;
+
+__device__ __forceinline__ int warp_inclusive_scan(int v)
+{
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, d);
+        if (lane >= d) v += t;
+    }
+    return v;
+}
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// slice of block b: [begin, end)
+__device__ __forceinline__ void scan_slice(int64_t n, int64_t &begin, int64_t &end)
+{
+    int64_t per = (n + gridDim.x - 1) / gridDim.x;
+    per = (per + kScanThreads - 1) / kScanThreads * kScanThreads;
+    begin = per * blockIdx.x;
+    end = begin + per;
+    if (begin > n) begin = n;
+    if (end > n) end = n;
+}
+
+template <class Count>
+__global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, Count count, int *__restrict__ block_sums)
+{
+    int64_t begin, end;
+    scan_slice(n, begin, end);
+    int acc = 0;
+    for (int64_t i = begin + threadIdx.x; i < end; i += kScanThreads) acc += count(i);
+    acc = warp_sum(acc);
+    __shared__ int s[kScanWarps];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kScanWarps; ++w) t += s[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+template <class Count, class Emit>
+__global__ void __launch_bounds__(kScanThreads) k_scan_write(int64_t n, Count count, Emit emit,
+                                                             const int *__restrict__ block_sums,
+                                                             int *__restrict__ total)
+{
+    __shared__ int s_warp[kScanWarps];
+    __shared__ int s_base;
+    // base offset of this block = sum of the sums before it; block 0 also publishes the total
+    {
+        int acc = 0;
+        const int upto = (blockIdx.x == 0) ? (int)gridDim.x : (int)blockIdx.x;
+        for (int b = threadIdx.x; b < upto; b += kScanThreads) acc += block_sums[b];
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int t = 0;
+            for (int w = 0; w < kScanWarps; ++w) t += s_warp[w];
+            if (blockIdx.x == 0) { if (total) *total = t; s_base = 0; }
+            else s_base = t;
+        }
+        __syncthreads();
+    }
+    int64_t begin, end;
+    scan_slice(n, begin, end);
+    int running = s_base;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t tile = begin; tile < end; tile += kScanThreads) {
+        const int64_t i = tile + threadIdx.x;
+        const int c = (i < end) ? count(i) : 0;
+        const int incl = warp_inclusive_scan(c);
+        __syncthreads();  // s_warp reuse
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        int warp_off = 0, tile_total = 0;
+#pragma unroll
+        for (int w = 0; w < kScanWarps; ++w) {
+            const int t = s_warp[w];
+            if (w < warp) warp_off += t;
+            tile_total += t;
+        }
+        if (c) emit(i, running + warp_off + incl - c, c);
+        running += tile_total;
+    }
+}
+
+// Host helper: runs both phases.  `block_sums` must hold kScanMaxBlocks ints; the total
+// lands in *d_total (device).
+template <class Count, class Emit>
+inline int compact(int64_t n, Count count, Emit emit, int *block_sums, int *d_total, cudaStream_t s)
+{
+    if (n <= 0) {
+        TNB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int), s));
+        return TNB_OK;
+    }
+    int64_t blocks = (n + kScanThreads - 1) / kScanThreads;
+    if (blocks > kScanMaxBlocks) blocks = kScanMaxBlocks;
+    k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, count, block_sums);
+    TNB_LAUNCH_CHECK();
+    k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, count, emit, block_sums, d_total);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+
+}  // namespace tnb

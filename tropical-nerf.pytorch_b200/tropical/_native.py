@@ -1,0 +1,303 @@
+"""ctypes binding of libtropical_b200.so (include/tropical_b200.h).
+
+PyTorch is used for device memory and streams only: every function here takes torch
+CUDA tensors, hands their raw pointers to the C ABI, and returns torch CUDA tensors.
+There is no CPU implementation: importing works without a GPU (so the ABI can be
+checked), every compute call raises `NativeError` when the library or a CUDA device is
+missing.
+"""
+import ctypes
+import os
+
+import numpy as np
+import torch
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_ROOT, "lib", "libtropical_b200.so")
+
+TNB_OK = 0
+ERRORS = {-1: "TNB_ERR_INVALID", -2: "TNB_ERR_CUDA", -3: "TNB_ERR_CAPACITY", -4: "TNB_ERR_UNSUPPORTED"}
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+class NetDesc(ctypes.Structure):
+    _fields_ = [("n_levels", ctypes.c_int32), ("n_features", ctypes.c_int32),
+                ("log2_hashmap", ctypes.c_int32), ("base_resolution", ctypes.c_int32),
+                ("per_level_scale", ctypes.c_double),
+                ("num_layers", ctypes.c_int32), ("num_hidden", ctypes.c_int32),
+                ("scale", ctypes.c_float), ("eps", ctypes.c_float),
+                ("table", ctypes.c_void_p), ("table_len", ctypes.c_int64),
+                ("mlp", ctypes.c_void_p), ("mlp_len", ctypes.c_int64),
+                ("marks", ctypes.c_void_p), ("n_marks", ctypes.c_int32)]
+
+
+_lib = None
+
+_P = ctypes.c_void_p
+_I64 = ctypes.c_int64
+_I32 = ctypes.c_int32
+_F = ctypes.c_float
+# name -> (restype, argtypes); every symbol include/tropical_b200.h declares
+SIGNATURES = {
+    "tnb_last_error": (ctypes.c_char_p, []),
+    "tnb_version": (ctypes.c_int, []),
+    "tnb_device_count": (ctypes.c_int, []),
+    "tnb_net_create": (ctypes.c_int, [ctypes.POINTER(NetDesc), ctypes.POINTER(_P)]),
+    "tnb_net_destroy": (None, [_P]),
+    "tnb_net_num_outputs": (ctypes.c_int, [_P]),
+    "tnb_net_level_layout": (ctypes.c_int, [_P, _P, _P, _P, _P]),
+    "tnb_grid_encode": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
+    "tnb_net_outputs": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
+    "tnb_net_sdf_grad": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "tnb_net_region": (ctypes.c_int, [_P, _P, _P, _I64, _F, _P, _P, _P, _P]),
+    "tnb_sweep_signs": (ctypes.c_int, [_P, _P, _P, _P, _F, _P, _P]),
+    "tnb_skeleton": (ctypes.c_int, [_P, _I32, _F, ctypes.POINTER(_P), _P]),
+    "tnb_complex_from_arrays": (ctypes.c_int, [_P, _P, _I64, _P, _I64, ctypes.POINTER(_P), _P]),
+    "tnb_complex_destroy": (None, [_P]),
+    "tnb_complex_num_vertices": (_I64, [_P]),
+    "tnb_complex_num_edges": (_I64, [_P]),
+    "tnb_complex_read": (ctypes.c_int, [_P, _P, _P, _P, _P]),
+    "tnb_subpoly_step": (ctypes.c_int, [_P, _P, _I32, _I32, _F, _I32, _P]),
+    "tnb_extract_mesh": (ctypes.c_int, [_P, _P, _F, ctypes.POINTER(_P), _P]),
+    "tnb_mesh_destroy": (None, [_P]),
+    "tnb_mesh_num_vertices": (_I64, [_P]),
+    "tnb_mesh_num_edges": (_I64, [_P]),
+    "tnb_mesh_num_triangles": (_I64, [_P]),
+    "tnb_mesh_num_polygons": (_I64, [_P]),
+    "tnb_mesh_polygon_width": (_I64, [_P]),
+    "tnb_mesh_read": (ctypes.c_int, [_P, _P, _P, _P, _P, _P, _P]),
+    "tnb_subpoly": (ctypes.c_int, [_P, _F, _F, _I32, _I32, ctypes.POINTER(_P), _P]),
+    "tnb_mesh_read_host": (ctypes.c_int, [_P, _P, _P, _P, _P]),
+    "tnb_set_capacity_factor": (ctypes.c_int, [ctypes.c_double]),
+    "tnb_launch_count": (_I64, []),
+    "tnb_launch_count_reset": (None, []),
+}
+
+
+def lib():
+    """Load the CUDA library; fail loudly when it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(
+                f"{LIB_PATH} is missing: build it with `python __graft_entry__.py` "
+                "(nvcc, sm_100a). There is no CPU fallback for the mesh-extraction path.")
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+def check(rc):
+    if rc != TNB_OK:
+        msg = lib().tnb_last_error().decode("utf-8", "replace")
+        raise NativeError(f"{ERRORS.get(rc, rc)}: {msg}")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda():
+    if not torch.cuda.is_available() or lib().tnb_device_count() == 0:
+        raise NativeError("no CUDA device: the mesh-extraction path has no CPU fallback")
+
+
+class NativeNet:
+    """Device-resident copy of one trilinear network (tnb_net)."""
+
+    def __init__(self, levels, n_feat, log2_T, n_min, per_level_scale, num_layers, num_hidden,
+                 table, mlp, marks, eps=1e-4, scale=1.0):
+        require_cuda()
+        table = np.ascontiguousarray(table, np.float32).reshape(-1)
+        mlp = np.ascontiguousarray(mlp, np.float32).reshape(-1)
+        marks = np.ascontiguousarray(marks, np.float32).reshape(-1)
+        d = NetDesc(int(levels), int(n_feat), int(log2_T), int(n_min), float(per_level_scale),
+                    int(num_layers), int(num_hidden), float(scale), float(eps),
+                    table.ctypes.data, table.size, mlp.ctypes.data, mlp.size,
+                    marks.ctypes.data, marks.size)
+        h = ctypes.c_void_p()
+        check(lib().tnb_net_create(ctypes.byref(d), ctypes.byref(h)))
+        self.handle = h
+        self.levels, self.n_feat = int(levels), int(n_feat)
+        self.num_layers, self.num_hidden = int(num_layers), int(num_hidden)
+        self.n_outputs = lib().tnb_net_num_outputs(h)
+        self.eps, self.scale = float(eps), float(scale)
+        self.n_marks = marks.size
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None:
+            _lib.tnb_net_destroy(h)
+
+    def level_layout(self):
+        L = self.levels
+        scale = np.zeros(L, np.float32)
+        res, size, off = (np.zeros(L, np.uint32) for _ in range(3))
+        check(lib().tnb_net_level_layout(self.handle, scale.ctypes.data, res.ctypes.data,
+                                         size.ctypes.data, off.ctypes.data))
+        return scale, res, size, off
+
+    # ---- network evaluation ---------------------------------------------------------
+    def encode(self, xp):
+        xp = xp.contiguous().float()
+        n = xp.shape[0]
+        enc = torch.empty((n, self.levels * self.n_feat), dtype=torch.float32, device=xp.device)
+        check(lib().tnb_grid_encode(self.handle, _ptr(xp), n, _ptr(enc), _stream()))
+        return enc
+
+    def outputs(self, x):
+        x = x.contiguous().float()
+        n = x.shape[0]
+        out = torch.empty((n, self.n_outputs), dtype=torch.float32, device=x.device)
+        check(lib().tnb_net_outputs(self.handle, _ptr(x), n, _ptr(out), _stream()))
+        return out
+
+    def sdf_grad(self, x, want_grad=True):
+        x = x.contiguous().float()
+        n = x.shape[0]
+        sdf = torch.empty(n, dtype=torch.float32, device=x.device)
+        grad = torch.empty((n, 3), dtype=torch.float32, device=x.device) if want_grad else None
+        check(lib().tnb_net_sdf_grad(self.handle, _ptr(x), n, _ptr(sdf), _ptr(grad), _stream()))
+        return sdf, grad
+
+    def region(self, x, outputs=None, eps=None, packed=False):
+        x = x.contiguous().float()
+        n = x.shape[0]
+        eps = self.eps if eps is None else float(eps)
+        if outputs is None:
+            outputs = self.outputs(x)
+        outputs = outputs.contiguous().float()
+        signs = torch.empty((n, 3 + self.n_outputs), dtype=torch.int8, device=x.device)
+        offset = torch.empty((n, 3), dtype=torch.int32, device=x.device)
+        pk = torch.empty((n, 3), dtype=torch.int64, device=x.device) if packed else None
+        check(lib().tnb_net_region(self.handle, _ptr(x), _ptr(outputs), n, eps, _ptr(signs),
+                                   _ptr(offset), _ptr(pk), _stream()))
+        if packed:
+            return signs, offset, outputs, pk
+        return signs, offset, outputs
+
+    def sweep_signs(self, lo, hi, n, eps=None, out=None):
+        lo = (ctypes.c_float * 3)(*lo)
+        hi = (ctypes.c_float * 3)(*hi)
+        nn = (ctypes.c_int32 * 3)(*n)
+        count = int(n[0]) * int(n[1]) * int(n[2])
+        if out is None:
+            out = torch.empty((count, 2), dtype=torch.int64, device="cuda")
+        eps = self.eps if eps is None else float(eps)
+        check(lib().tnb_sweep_signs(self.handle, lo, hi, nn, eps, _ptr(out), _stream()))
+        return out
+
+    # ---- polyhedral complex -----------------------------------------------------------
+    def skeleton(self, unit=128, size=1.2):
+        h = ctypes.c_void_p()
+        check(lib().tnb_skeleton(self.handle, int(unit), float(size), ctypes.byref(h), _stream()))
+        return NativeComplex(self, h)
+
+    def complex_from_arrays(self, vertices, edges):
+        vertices = vertices.contiguous().float()
+        edges = edges.contiguous().long()
+        h = ctypes.c_void_p()
+        check(lib().tnb_complex_from_arrays(self.handle, _ptr(vertices), vertices.shape[0], _ptr(edges),
+                                            edges.shape[0], ctypes.byref(h), _stream()))
+        return NativeComplex(self, h)
+
+    def subpoly(self, size=1.2, eps=1e-4, force=True, unit=128):
+        """The whole path (tnb_subpoly); returns a NativeMesh."""
+        h = ctypes.c_void_p()
+        check(lib().tnb_subpoly(self.handle, float(size), float(eps), int(bool(force)), int(unit),
+                                ctypes.byref(h), _stream()))
+        return NativeMesh(self, h)
+
+
+class NativeComplex:
+    """Device-resident vertices / edges / cached outputs (tnb_complex)."""
+
+    def __init__(self, net, handle):
+        self.net, self.handle = net, handle
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None:
+            _lib.tnb_complex_destroy(h)
+
+    @property
+    def num_vertices(self):
+        return int(lib().tnb_complex_num_vertices(self.handle))
+
+    @property
+    def num_edges(self):
+        return int(lib().tnb_complex_num_edges(self.handle))
+
+    def read(self, vertices=True, edges=True, outputs=True):
+        V, E, R = self.num_vertices, self.num_edges, self.net.n_outputs
+        v = torch.empty((V, 3), dtype=torch.float32, device="cuda") if vertices else None
+        e = torch.empty((E, 2), dtype=torch.int64, device="cuda") if edges else None
+        o = torch.empty((V, R), dtype=torch.float32, device="cuda") if outputs else None
+        check(lib().tnb_complex_read(self.handle, _ptr(v), _ptr(e), _ptr(o), _stream()))
+        return v, e, o
+
+    def step(self, l, h, eps=1e-4, force=True):
+        check(lib().tnb_subpoly_step(self.net.handle, self.handle, int(l), int(h), float(eps),
+                                     int(bool(force)), _stream()))
+        return self
+
+    def extract_mesh(self, eps=1e-4):
+        h = ctypes.c_void_p()
+        check(lib().tnb_extract_mesh(self.net.handle, self.handle, float(eps), ctypes.byref(h), _stream()))
+        return NativeMesh(self.net, h)
+
+
+class NativeMesh:
+    """Extracted surface mesh (tnb_mesh)."""
+
+    def __init__(self, net, handle):
+        self.net, self.handle = net, handle
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None:
+            _lib.tnb_mesh_destroy(h)
+
+    def sizes(self):
+        L = lib()
+        return dict(V=int(L.tnb_mesh_num_vertices(self.handle)), E=int(L.tnb_mesh_num_edges(self.handle)),
+                    T=int(L.tnb_mesh_num_triangles(self.handle)), P=int(L.tnb_mesh_num_polygons(self.handle)),
+                    W=int(L.tnb_mesh_polygon_width(self.handle)))
+
+    def read(self):
+        """Device tensors: vertices [V,3], edges [E,2], triangles [T,3], faces [T,3,3],
+        polygons [P,W]."""
+        s = self.sizes()
+        dev = "cuda"
+        v = torch.empty((s["V"], 3), dtype=torch.float32, device=dev)
+        e = torch.empty((s["E"], 2), dtype=torch.int64, device=dev)
+        t = torch.empty((s["T"], 3), dtype=torch.int64, device=dev)
+        f = torch.empty((s["T"], 3, 3), dtype=torch.float32, device=dev)
+        p = torch.empty((s["P"], s["W"]), dtype=torch.int64, device=dev)
+        check(lib().tnb_mesh_read(self.handle, _ptr(v), _ptr(e), _ptr(t), _ptr(f), _ptr(p), _stream()))
+        return v, e, t, f, p
+
+    def read_host(self):
+        """numpy arrays through tnb_mesh_read_host (host buffers): vertices, triangles,
+        faces, polygons."""
+        s = self.sizes()
+        v = np.empty((s["V"], 3), np.float32)
+        t = np.empty((s["T"], 3), np.int64)
+        f = np.empty((s["T"], 3, 3), np.float32)
+        p = np.empty((s["P"], s["W"]), np.int64)
+        check(lib().tnb_mesh_read_host(self.handle, v.ctypes.data, t.ctypes.data, f.ctypes.data, p.ctypes.data))
+        return v, t, f, p
