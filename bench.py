@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py -- mesh-extraction benchmark (BASELINE.json metric: mesh-extraction s and
+vertices/s vs host CPU; % HBM roofline).
+
+A "step" is one full polyhedral-complex mesh extraction (skeleton -> 33 hyperplane
+subdivisions -> faces) of one trilinear SDF network, planar (-f) path.  At N ranks every
+rank extracts its own copy of the object (independent objects, no data-path collective):
+weak scaling; `value` = mesh vertices extracted by all ranks / second.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload small_sphere|small_torus|large_random]
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "tropical-nerf.pytorch_b200")
+for _p in (ROOT, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+METRIC = "mesh_extraction_vertices_per_s"
+UNIT = "vertices/s"
+
+
+# ---------------------------------------------------------------------------------------
+# workloads (synthetic: fitted-analytic-SDF fixtures or seeded random weights)
+# ---------------------------------------------------------------------------------------
+def load_workload(name):
+    """Plain arrays of one network: dict(levels, n_feat, log2_T, n_min, per_level_scale,
+    num_layers, num_hidden, table, mlp, marks, eps, scale, describe)."""
+    if name in ("small_sphere", "small_torus"):
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"{name}.npz"))
+        nl = int(g["net_num_layers"])
+        mlp = np.concatenate([np.concatenate([g[f"net_w{i}"].reshape(-1), g[f"net_b{i}"].reshape(-1)])
+                              for i in range(nl)]).astype(np.float32)
+        shape = "sphere" if "sphere" in name else "torus"
+        return dict(levels=int(g["net_levels"]), n_feat=int(g["net_n_feat"]), log2_T=int(g["net_log2_T"]),
+                    n_min=int(g["net_n_min"]), per_level_scale=float(g["net_per_level_scale"]),
+                    num_layers=nl, num_hidden=int(g["net_num_hidden"]), table=g["net_table"], mlp=mlp,
+                    marks=g["net_marks"], eps=float(g["net_eps"]), scale=float(g["net_scale"]),
+                    describe=f"small HashGrid+MLP (L=4 F=2 T=19 r=2..32, MLP 8-16-16-2) briefly fitted to an "
+                             f"analytic {shape} SDF, planar (-f) extraction, marks grid {len(g['net_marks'])}^3")
+    if name.endswith("_random"):
+        from tropical.stanford.model import Net
+        import torch
+        size = name.split("_")[0]
+        r_min, r_max = {"small": (2, 32), "medium": (4, 64), "large": (8, 128)}[size]
+        torch.manual_seed(0)
+        net = Net(num_layers=3, num_hidden=16, levels=4, r_min=r_min, r_max=r_max, T=19)
+        with torch.no_grad():  # random-init weights with an amplitude that gives a surface
+            net.enc.module.params.uniform_(-1.0, 1.0)
+        mlp = np.concatenate([np.concatenate([fc.weight.detach().numpy().reshape(-1),
+                                              fc.bias.detach().numpy().reshape(-1)]) for fc in net.fc])
+        return dict(levels=4, n_feat=2, log2_T=19, n_min=r_min, per_level_scale=float(net.enc.b),
+                    num_layers=3, num_hidden=16, table=net.enc.module.params.detach().numpy(),
+                    mlp=mlp.astype(np.float32), marks=net.enc.marks.numpy(), eps=1e-4, scale=1.0,
+                    describe=f"{size} HashGrid+MLP (r={r_min}..{r_max}), random-init weights (table U(-1,1)), "
+                             f"planar (-f) extraction, marks grid {len(net.enc.marks)}^3")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def make_native(w, pinned=None):
+    from tropical._native import NativeNet
+    src = pinned if pinned is not None else w
+    return NativeNet(w["levels"], w["n_feat"], w["log2_T"], w["n_min"], w["per_level_scale"],
+                     w["num_layers"], w["num_hidden"], src["table"], src["mlp"], src["marks"],
+                     w["eps"], w["scale"])
+
+
+def oracle_params(w):
+    """CPU checker network -- only the cpu_baseline / --impl reference legs call this."""
+    from oracle.trinet import NetParams
+    nodes = [w["levels"] * w["n_feat"]] + [w["num_hidden"]] * (w["num_layers"] - 1) + [2]
+    ws, bs, o = [], [], 0
+    for i in range(w["num_layers"]):
+        n = nodes[i] * nodes[i + 1]
+        ws.append(w["mlp"][o:o + n].reshape(nodes[i + 1], nodes[i])); o += n
+        bs.append(w["mlp"][o:o + nodes[i + 1]]); o += nodes[i + 1]
+    return NetParams(w["levels"], w["n_feat"], w["log2_T"], w["n_min"], w["per_level_scale"],
+                     w["num_layers"], w["num_hidden"], w["table"], ws, bs, w["marks"], w["eps"], w["scale"])
+
+
+# ---------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.idx), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._pump, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) > 8 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) > 8 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) > 8:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------
+# the CPU arm (oracle port of the reference's algorithm)
+# ---------------------------------------------------------------------------------------
+def cpu_extract_seconds(P):
+    from oracle import subpoly_ref as R
+    t = time.perf_counter()
+    faces, vertices, tri = R.subpoly(P)
+    return time.perf_counter() - t, vertices.shape[0], tri.shape[0]
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    w = load_workload(args.workload)
+    P = oracle_params(w)
+    for _ in range(min(args.warmup, 1)):
+        cpu_extract_seconds(P)
+    total, nv = 0.0, 0
+    for _ in range(args.steps):
+        dt, nv, _ = cpu_extract_seconds(P)
+        total += dt
+    value = nv * args.steps / total
+    cpu = {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
+           "sample": f"{args.steps} full extraction(s) of the same network with the numpy+C oracle port "
+                     f"(the reference is Python over tiny-cuda-nn and cannot run on the GPU box)"}
+    print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+                      "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                      "data": "synthetic", "config": {"workload": w["describe"], "mesh_vertices": nv},
+                      "cpu_baseline": cpu,
+                      "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+
+
+# ---------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------
+ALGO_BYTES = {
+    # algorithmic HBM bytes per unit of each timed kernel class (DESIGN.md "Kernels")
+    "sweep": lambda R: 4,                       # |sdf| written per marks-grid vertex (inputs are generated)
+    "vertex_rows": lambda R: 12 + 4 * R + 24,   # position in, R outputs + 3 packed words out
+    "new_vertices": lambda R: 8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * R + 8 + 16,
+    "pairs": lambda R: 4 + 24 + 4,
+    "face_rows": lambda R: 24 + 4,
+    "sign_sweep": lambda R: 16,
+}
+
+
+def run_ours(args):
+    import torch
+    from tropical import _native
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    w = load_workload(args.workload)
+    net = make_native(w)
+    R = net.n_outputs
+    flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")  # > 126 MB L2
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return net.subpoly(size=1.2, eps=w["eps"], force=True)
+
+    for _ in range(max(args.warmup, 3)):
+        mesh = step()
+    sizes = mesh.sizes()
+    del mesh
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    _native.profile_enable(True)
+    _native.profile_reset()
+    _native.lib().tnb_launch_count_reset()
+    barrier()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for a, b in ev:
+        flush.fill_(1)          # L2 flush between timed iterations (outside the event pair)
+        a.record()
+        mesh = step()
+        b.record()
+        del mesh
+    barrier()
+    launches = int(_native.lib().tnb_launch_count())
+    ms_total = sum(a.elapsed_time(b) for a, b in ev)
+    prof = _native.profile_read()
+    _native.profile_enable(False)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    value = sizes["V"] * world * args.steps / (ms_total * 1e-3)
+
+    # ---- end to end through the C ABI with host buffers --------------------------------
+    pinned = {k: torch.from_numpy(np.ascontiguousarray(w[k], np.float32)).pin_memory() for k in ("table", "mlp", "marks")}
+    pinned_np = {k: v.numpy() for k, v in pinned.items()}
+    h2d = sum(v.numel() * 4 for v in pinned.values())
+    d2h = 0
+
+    def e2e_step():
+        n2 = make_native(w, pinned_np)            # host -> device copy of the step's inputs
+        m2 = n2.subpoly(size=1.2, eps=w["eps"], force=True)
+        v, tr, f, p = m2.read_host()              # device -> host read of the result
+        return v.nbytes + tr.nbytes + f.nbytes + p.nbytes
+
+    for _ in range(2):
+        d2h = e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = sizes["V"] * world * args.steps / float(t.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel class -------------------------------------------
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    top = max(prof, key=lambda k: prof[k][0])
+    ms, n_launch, units = prof[top]
+    table_bytes = w["table"].size * 4
+    algo = ALGO_BYTES[top](R) * units + (table_bytes * n_launch if top in ("sweep", "vertex_rows", "new_vertices", "sign_sweep") else 0)
+    achieved = algo / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        tj = json.load(open(tpath)).get(args.workload, {}).get(top)
+        if tj:
+            traffic = tj["dram_bytes_per_launch"]
+    roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": algo / max(n_launch, 1), "launches": n_launch,
+                "avg_launch_ms": ms / max(n_launch, 1), "kernel_share_of_step": ms / ms_total,
+                "note": "the fused trilinear kernels are fp32-issue bound, not HBM bound: see DESIGN.md",
+                "by_kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+
+    # ---- CPU baseline (bounded sample on the box's host cores) ----------------------------
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        dt, nv, _ = cpu_extract_seconds(oracle_params(w))
+        cpu = {"value": nv / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
+               "sample": "1 full extraction of the same network with the numpy+C oracle port"}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+           "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": w["describe"], "mesh_vertices": sizes["V"], "mesh_triangles": sizes["T"],
+                      "polygons": sizes["P"], "objects_per_step": world, "l2": "flushed (512 MiB write) between timed steps",
+                      "extraction_s": ms_total / args.steps * 1e-3},
+           "clocks": clocks, "gpu_launches": launches,
+           "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                   "ms_per_step": 1e3 * float(t.item()) / args.steps},
+           "roofline": roofline, "cpu_baseline": cpu}
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="small_sphere")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -102,7 +102,8 @@ int tnb_sweep_signs(const tnb_net *net, const float lo[3], const float hi[3], co
 /* ---- polyhedral complex -------------------------------------------------------- */
 /* TropicalHashGrid.skeleton(net, unit) (tropical.py:158-225, distance pruning).  When
  * no grid edge survives, the hypercube of subpoly.py:51-52 / :731-750 with half-size
- * `size` is returned instead (what subpoly() does next). */
+ * `size` is returned instead (what subpoly() does next); size <= 0 disables the fallback
+ * and returns the empty complex (what skeleton() itself returns, tropical.py:208-209). */
 int tnb_skeleton(const tnb_net *net, int32_t unit, float size, tnb_complex **out, void *stream);
 /* Build a complex from caller arrays (device pointers): vertices [V,3] f32, edges
  * [E,2] i64.  Outputs are evaluated. */
@@ -154,6 +155,22 @@ int tnb_set_capacity_factor(double f);
  * reset (bench.py's gpu_launches) */
 int64_t tnb_launch_count(void);
 void tnb_launch_count_reset(void);
+/* Per-kernel timers: when enabled, the library brackets its heavy kernels with CUDA
+ * events on the launching stream.  Classes: 0 = marks-grid sweep (sdf + gradient),
+ * 1 = vertex network rows (outputs + packed signs), 2 = new-vertex subdivision kernel,
+ * 3 = connecting-edge search, 4 = face rows, 5 = dense sign sweep.
+ * tnb_profile_read synchronises the recorded events and returns the summed milliseconds,
+ * the launch count and the number of units (vertices / points / edges) processed. */
+#define TNB_PROF_SWEEP 0
+#define TNB_PROF_VERTEX_ROWS 1
+#define TNB_PROF_NEW_VERTICES 2
+#define TNB_PROF_PAIRS 3
+#define TNB_PROF_FACE_ROWS 4
+#define TNB_PROF_SIGN_SWEEP 5
+#define TNB_PROF_CLASSES 6
+int tnb_profile_enable(int on);
+int tnb_profile_read(int cls, double *ms, int64_t *launches, int64_t *units);
+void tnb_profile_reset(void);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,9 @@ struct NetMeta {
 void set_error(const std::string &msg);
 int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 void count_launch(int n = 1);
+// optional CUDA-event timers around the heavy kernels (tnb_profile_*)
+void prof_begin(int cls, cudaStream_t s);
+void prof_end(int cls, cudaStream_t s, int64_t units);
 
 #define TNB_CUDA(expr)                                                         \
     do {                                                                       \

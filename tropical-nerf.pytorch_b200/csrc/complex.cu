@@ -14,16 +14,14 @@
 #include "net_eval.cuh"
 #include "scan.cuh"
 
-tnb_complex::~tnb_complex()
-{
-    if (h_counters) cudaFreeHost(h_counters);
-}
+tnb_complex::~tnb_complex() {}
 
 namespace tnb {
 
 double g_capacity_factor = 4.0;
 constexpr int kThreads = 128;
-enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_EDGES, C_VERTS, C_OVERFLOW, C_TMP, C_NUM = 16 };
+// device counters: [0, C_V) are cleared at the start of every step, C_V / C_E hold the complex size
+enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_PARTNER_OVERFLOW, C_TMP, C_V = 8, C_E = 9, C_NUM = 16 };
 
 // ---- allocation ---------------------------------------------------------------------------
 int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
@@ -47,8 +45,12 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
     TNB_CUDA(c->remap.reserve(Vcap));
     TNB_CUDA(c->block_sums.reserve(kScanMaxBlocks));
     TNB_CUDA(c->counters.reserve(C_NUM));
-    TNB_CUDA(cudaMemset(c->counters.p, 0, C_NUM * sizeof(int)));
-    if (!c->h_counters) TNB_CUDA(cudaMallocHost((void **)&c->h_counters, C_NUM * sizeof(int)));
+    TNB_CUDA(cudaMemsetAsync(c->counters.p, 0, C_NUM * sizeof(int), current_stream()));
+    {   // one pinned mirror per thread, reused by every complex
+        static thread_local int *pinned = nullptr;
+        if (!pinned) TNB_CUDA(cudaMallocHost((void **)&pinned, C_NUM * sizeof(int)));
+        c->h_counters = pinned;
+    }
     // cell buckets: offsets live in [-1, M-1], cells in [-2, M-1] -> M+2 per axis
     c->cell_dim = net->meta.n_marks + 2;
     c->n_cells = (int64_t)c->cell_dim * c->cell_dim * c->cell_dim;
@@ -57,7 +59,7 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
         return TNB_ERR_UNSUPPORTED;
     }
     TNB_CUDA(c->head.reserve((size_t)c->n_cells));
-    TNB_CUDA(cudaMemset(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long)));
+    TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), current_stream()));
     c->stamp = 0;
     return TNB_OK;
 }
@@ -101,6 +103,8 @@ int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
     }
     return TNB_OK;
 }
+
+__global__ void k_set_counts(int *__restrict__ cnt, int V, int E);
 
 static int read_counters(tnb_complex *c, cudaStream_t s)
 {
@@ -261,9 +265,11 @@ static int eval_vertices(const tnb_net *net, tnb_complex *c, int64_t first, int6
 {
     if (count <= 0) return TNB_OK;
     unsigned g = grid_for(count, kThreads);
+    prof_begin(TNB_PROF_VERTEX_ROWS, s);
     if (net->fixed_cfg) k_vertex_outputs<CfgRef><<<g, kThreads, 0, s>>>(net->meta, c->cvert(), first, count, c->cout_(), c->csig());
     else k_vertex_outputs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, c->cvert(), first, count, c->cout_(), c->csig());
     TNB_LAUNCH_CHECK();
+    prof_end(TNB_PROF_VERTEX_ROWS, s, count);
     return TNB_OK;
 }
 
@@ -300,11 +306,13 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
                 for (int d = 0; d < 3; ++d) nn[d] = std::min(M, st[d] + unit) - st[d];
                 const int64_t count = (int64_t)nn[0] * nn[1] * nn[2];
                 unsigned g = grid_for(count, kThreads);
+                prof_begin(TNB_PROF_SWEEP, s);
                 if (net->fixed_cfg)
                     k_sweep_chunk<CfgRef><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist.p, max_grad.p + chunk);
                 else
                     k_sweep_chunk<CfgAny><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist.p, max_grad.p + chunk);
                 TNB_LAUNCH_CHECK();
+                prof_end(TNB_PROF_SWEEP, s, count);
                 for (int axis = 0; axis < 3; ++axis) {
                     int dims[3] = {nn[0], nn[1], nn[2]};
                     dims[axis] -= 1;
@@ -337,7 +345,7 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
     SkelEdgeCount q{d_segs.p, (int)segs.size(), M, dist.p, max_grad.p, k_len};
     {
         int64_t blocks = std::min<int64_t>((slots + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
-        k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, q, block_sums.p);
+        k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, nullptr, q, block_sums.p);
         TNB_LAUNCH_CHECK();
         std::vector<int> h(blocks);
         TNB_CUDA(cudaMemcpyAsync(h.data(), block_sums.p, blocks * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -349,12 +357,12 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
         DevBuf<int2> raw;
         TNB_CUDA(raw.reserve((size_t)E));
         SkelEdgeEmit emit{q, raw.p, used.p};
-        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, q, emit, block_sums.p, total.p);
+        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, nullptr, q, emit, block_sums.p, total.p);
         TNB_LAUNCH_CHECK();
         // vertex pass: count, size, then place
         FlagCount fc{used.p};
         int64_t vblocks = std::min<int64_t>((M3 + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
-        k_scan_count<<<(unsigned)vblocks, kScanThreads, 0, s>>>(M3, fc, block_sums.p);
+        k_scan_count<<<(unsigned)vblocks, kScanThreads, 0, s>>>(M3, nullptr, fc, block_sums.p);
         TNB_LAUNCH_CHECK();
         std::vector<int> hv(vblocks);
         TNB_CUDA(cudaMemcpyAsync(hv.data(), block_sums.p, vblocks * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -365,16 +373,17 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
         int rc = complex_alloc(c, net, Vcap, Ecap);
         if (rc) return rc;
         SkelVertEmit vemit{nullptr, net->meta.marks, net->meta.pre_2s, net->meta.pre_scale, M, remap.p, c->cvert()};
-        k_scan_write<<<(unsigned)vblocks, kScanThreads, 0, s>>>(M3, fc, vemit, block_sums.p, total.p + 1);
+        k_scan_write<<<(unsigned)vblocks, kScanThreads, 0, s>>>(M3, nullptr, fc, vemit, block_sums.p, total.p + 1);
         TNB_LAUNCH_CHECK();
         TNB_CUDA(cudaMemcpyAsync(c->cedges(), raw.p, (size_t)E * sizeof(int2), cudaMemcpyDeviceToDevice, s));
         k_remap_edges<<<grid_for(E, 256), 256, 0, s>>>(c->cedges(), E, remap.p);
         TNB_LAUNCH_CHECK();
         c->V = V;
         c->E = E;
+        k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E);
+        TNB_LAUNCH_CHECK();
         rc = eval_vertices(net, c, 0, V, s);
         if (rc) return rc;
-        TNB_CUDA(cudaStreamSynchronize(s));  // locals are freed on return
     }
     return TNB_OK;
 }
@@ -382,6 +391,10 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
 // ================================================================================================
 // one hyperplane (subpoly_)
 // ================================================================================================
+// All sizes a step produces (splits, hits, pairs, post-prune V/E) stay in device memory:
+//   cnt[C_SPLIT..]  transient per step,  cnt[C_V], cnt[C_E] the current complex size.
+// Kernels read them there; the host only supplies upper bounds to size grids, and syncs
+// ONCE per step (after the connecting-edge count, where it must size the edge array).
 struct SplitCount {
     const int2 *edges;
     const float *out;
@@ -403,12 +416,17 @@ struct ListEmit {
 // failover mask of subpoly_debug.py:37-43, edge rewiring (subpoly.py:210-215)
 template <class C>
 __global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant__ NetMeta n, int idx, float eps,
-                                                           int S, int V, int E, const int *__restrict__ split_list,
+                                                           int Vcap, int Ecap, const int *__restrict__ split_list,
                                                            int2 *__restrict__ edges, float *__restrict__ vert,
                                                            float *__restrict__ out, const uint64_t *__restrict__ sig,
-                                                           uint64_t *__restrict__ bmask, int *__restrict__ counters)
+                                                           uint64_t *__restrict__ bmask, int *__restrict__ cnt)
 {
     const int R = n.R;
+    const int S = cnt[C_SPLIT], V = cnt[C_V], E = cnt[C_E];
+    if ((int64_t)V + S > Vcap || (int64_t)E + S > Ecap) {  // host grows the arrays and re-runs
+        if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_OVERFLOW] = 1;
+        return;
+    }
     int any = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
         const int e = split_list[k];
@@ -435,18 +453,19 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant
         edges[e].y = (int)nv;                    // left part keeps the first endpoint
         edges[E + k] = make_int2(ed.y, (int)nv); // right part
     }
-    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(counters + C_FLAG, 1);
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
 }
 
 // apply the failover override when any new vertex violated it, then bit-pack the region
 // indicator of the new vertices
-__global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant__ NetMeta n, int S, int V,
+__global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant__ NetMeta n,
                                                            const float *__restrict__ vert, float *__restrict__ out,
                                                            uint64_t *__restrict__ sig, const uint64_t *__restrict__ bmask,
-                                                           const int *__restrict__ counters)
+                                                           const int *__restrict__ cnt)
 {
     const int R = n.R;
-    const int flag = counters[C_FLAG];
+    if (cnt[C_OVERFLOW]) return;
+    const int flag = cnt[C_FLAG], S = cnt[C_SPLIT], V = cnt[C_V];
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
         const int64_t v = (int64_t)V + k;
         float *row = out + v * R;
@@ -469,9 +488,14 @@ struct HitCount {
     __device__ __forceinline__ int operator()(int64_t v) const { return fabsf(out[v * R + idx]) < eps ? 1 : 0; }  // subpoly.py:233
 };
 
-__global__ void k_fill_new_cands(int *__restrict__ cand, int H, int S, int V)
+// candidates = hit old vertices (already in cand[0..H)), then the new ones; publishes the
+// candidate count
+__global__ void k_fill_new_cands(int *__restrict__ cand, int *__restrict__ cnt)
 {
+    const int H = cnt[C_HIT], S = cnt[C_SPLIT], V = cnt[C_V];
+    if (cnt[C_OVERFLOW]) return;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) cand[H + k] = V + k;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_CAND] = S ? H + S : 0;
 }
 
 // ---- cell buckets ------------------------------------------------------------------------------
@@ -495,9 +519,11 @@ __device__ __forceinline__ int64_t cell_id(int cx, int cy, int cz, int dim)
     return ((int64_t)(cx + 2) * dim + (cy + 2)) * dim + (cz + 2);
 }
 
-__global__ void k_bucket_insert(const int *__restrict__ cand, int n_cand, const uint64_t *__restrict__ sig,
-                                unsigned long long *__restrict__ head, int *__restrict__ next, int dim, uint32_t stamp)
+__global__ void k_bucket_insert(const int *__restrict__ cand, const int *__restrict__ cnt,
+                                const uint64_t *__restrict__ sig, unsigned long long *__restrict__ head,
+                                int *__restrict__ next, int dim, uint32_t stamp)
 {
+    const int n_cand = cnt[C_CAND];
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += gridDim.x * blockDim.x) {
         const CellBox b = cell_box(sig[3 * (int64_t)cand[c] + 2]);
         int slot = 0;
@@ -555,17 +581,17 @@ __device__ __forceinline__ int find_partners(int a, const int *__restrict__ cand
     return count;
 }
 
-__global__ void __launch_bounds__(kThreads) k_pair_count(const int *__restrict__ cand, int n_cand,
+__global__ void __launch_bounds__(kThreads) k_pair_count(const int *__restrict__ cand, int *__restrict__ cnt,
                                                          const uint64_t *__restrict__ sig,
                                                          const unsigned long long *__restrict__ head,
                                                          const int *__restrict__ next, int dim, uint32_t stamp,
-                                                         uint64_t colmask, int *__restrict__ pcount,
-                                                         int *__restrict__ counters)
+                                                         uint64_t colmask, int *__restrict__ pcount)
 {
+    const int n_cand = cnt[C_CAND];
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x) {
-        const int cnt = find_partners(a, cand, sig, head, next, dim, stamp, colmask, nullptr);
-        pcount[a] = cnt;
-        if (cnt > kMaxPartners) atomicOr(counters + C_OVERFLOW, 1);
+        const int c = find_partners(a, cand, sig, head, next, dim, stamp, colmask, nullptr);
+        pcount[a] = c;
+        if (c > kMaxPartners) atomicOr(cnt + C_PARTNER_OVERFLOW, 1);
     }
 }
 
@@ -586,11 +612,11 @@ __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__
                                                          const int *__restrict__ poff, int2 *__restrict__ edges_out)
 {
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x) {
-        const int cnt = pcount[a];
-        if (cnt == 0) continue;
+        const int c = pcount[a];
+        if (c == 0) continue;
         int list[kMaxPartners];
         find_partners(a, cand, sig, head, next, dim, stamp, colmask, list);
-        const int m = min(cnt, kMaxPartners);
+        const int m = min(c, kMaxPartners);
         for (int i = 1; i < m; ++i) {  // ascending partner number: unique(dim=0) order, subpoly.py:243-244
             const int key = list[i];
             int j = i - 1;
@@ -644,90 +670,133 @@ struct VertexMoveEmit {  // subpoly.py:268-277: compact vertices, positions, cac
     }
 };
 
+__global__ void k_remap_edges_dev(int2 *__restrict__ edges, const int *__restrict__ n_dev, const int *__restrict__ remap)
+{
+    const int64_t E = *n_dev;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        int2 ed = edges[e];
+        edges[e] = make_int2(remap[ed.x], remap[ed.y]);
+    }
+}
+__global__ void k_set_counts(int *__restrict__ cnt, int V, int E)
+{
+    cnt[C_V] = V;
+    cnt[C_E] = E;
+}
+__global__ void k_clear_step_counters(int *__restrict__ cnt)
+{
+    if (threadIdx.x < C_V) cnt[threadIdx.x] = 0;
+}
+
+// Refresh the host's view of the complex size (one small D2H + sync).
+int complex_sync_counts(tnb_complex *c, cudaStream_t s)
+{
+    if (!c->counts_stale) return TNB_OK;
+    int rc = read_counters(c, s);
+    if (rc) return rc;
+    c->V = c->h_counters[C_V];
+    c->E = c->h_counters[C_E];
+    c->counts_stale = false;
+    return TNB_OK;
+}
+
 static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps, cudaStream_t s)
 {
     const NetMeta &m = net->meta;
     const int H = m.H, R = m.R;
     const int idx = l * H + h;
     if (l < 0 || h < 0 || h > H || idx >= R) { set_error("tnb_subpoly_step: (l,h) out of range"); return TNB_ERR_INVALID; }
-    if (c->E == 0) return TNB_OK;
     int *cnt = c->counters.p;
     int rc;
-    TNB_CUDA(cudaMemsetAsync(cnt, 0, C_NUM * sizeof(int), s));
+    // c->V / c->E are upper bounds here when counts_stale (the exact values are in cnt[C_V], cnt[C_E])
+    if (c->E == 0) return TNB_OK;
+    const uint64_t colmask = (1ull << idx) - 1ull;
 
-    // 1. edges the hyperplane crosses
-    SplitCount sc{c->cedges(), c->cout_(), R, idx, eps};
-    if ((rc = compact(c->E, sc, ListEmit{c->split_list.p}, c->block_sums.p, cnt + C_SPLIT, s))) return rc;
-    if ((rc = read_counters(c, s))) return rc;
+    for (int attempt = 0;; ++attempt) {
+        k_clear_step_counters<<<1, 32, 0, s>>>(cnt);
+        TNB_LAUNCH_CHECK();
+        // 1. edges the hyperplane crosses
+        SplitCount sc{c->cedges(), c->cout_(), R, idx, eps};
+        if ((rc = compact(c->E, sc, ListEmit{c->split_list.p}, c->block_sums.p, cnt + C_SPLIT, s, cnt + C_E))) return rc;
+        // 2. new vertices, their network rows, rewired edges (all sized on the device)
+        {
+            unsigned g = grid_for(c->E, kThreads);
+            prof_begin(TNB_PROF_NEW_VERTICES, s);
+            if (net->fixed_cfg)
+                k_new_vertices<CfgRef><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
+            else
+                k_new_vertices<CfgAny><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
+            TNB_LAUNCH_CHECK();
+            prof_end(TNB_PROF_NEW_VERTICES, s, 0);
+            k_finalize_new<<<g, kThreads, 0, s>>>(m, c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
+            TNB_LAUNCH_CHECK();
+        }
+        // 3. candidates for connecting edges: old vertices on the plane, then the new ones
+        HitCount hc{c->cout_(), R, idx, eps};
+        if ((rc = compact(c->V, hc, ListEmit{c->cand.p}, c->block_sums.p, cnt + C_HIT, s, cnt + C_V))) return rc;
+        const int64_t cand_ub = std::min<int64_t>(c->V + c->E, (int64_t)c->Vcap);
+        k_fill_new_cands<<<grid_for(c->E, 256), 256, 0, s>>>(c->cand.p, cnt);
+        TNB_LAUNCH_CHECK();
+        c->stamp += 1;
+        if (c->stamp == 0) {  // generation wrapped: clear the heads once
+            TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
+            c->stamp = 1;
+        }
+        {
+            unsigned g = grid_for(cand_ub, kThreads);
+            k_bucket_insert<<<g, kThreads, 0, s>>>(c->cand.p, cnt, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp);
+            TNB_LAUNCH_CHECK();
+            prof_begin(TNB_PROF_PAIRS, s);
+            k_pair_count<<<g, kThreads, 0, s>>>(c->cand.p, cnt, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p);
+            TNB_LAUNCH_CHECK();
+            prof_end(TNB_PROF_PAIRS, s, 0);
+        }
+        if ((rc = compact(cand_ub, ArrayCount{c->pcount.p}, OffsetEmit{c->poff.p}, c->block_sums.p, cnt + C_PAIRS, s, cnt + C_CAND))) return rc;
+        // ---- the one host sync of the step ----
+        if ((rc = read_counters(c, s))) return rc;
+        c->V = c->h_counters[C_V];
+        c->E = c->h_counters[C_E];
+        c->counts_stale = false;
+        if (!c->h_counters[C_OVERFLOW]) break;
+        if (attempt > 0) { set_error("work buffers did not grow"); return TNB_ERR_CAPACITY; }
+        const int S_need = c->h_counters[C_SPLIT];
+        if ((rc = complex_reserve(c, c->V + S_need, c->E + S_need, s))) return rc;
+    }
     const int S = c->h_counters[C_SPLIT];
     if (S == 0) return TNB_OK;  // subpoly.py:110-111
-    if ((rc = complex_reserve(c, c->V + S, c->E + S, s))) return rc;
+    if (c->h_counters[C_PARTNER_OVERFLOW]) { set_error("a vertex has more than 256 connecting partners"); return TNB_ERR_CAPACITY; }
     const int V0 = (int)c->V, E0 = (int)c->E;
-
-    // 2. new vertices, their network rows, rewired edges
-    {
-        unsigned g = grid_for(S, kThreads);
-        if (net->fixed_cfg)
-            k_new_vertices<CfgRef><<<g, kThreads, 0, s>>>(m, idx, eps, S, V0, E0, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
-        else
-            k_new_vertices<CfgAny><<<g, kThreads, 0, s>>>(m, idx, eps, S, V0, E0, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
-        TNB_LAUNCH_CHECK();
-        k_finalize_new<<<g, kThreads, 0, s>>>(m, S, V0, c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
-        TNB_LAUNCH_CHECK();
-    }
-
-    // 3. candidates for connecting edges: old vertices on the plane, then the new ones
-    HitCount hc{c->cout_(), R, idx, eps};
-    if ((rc = compact(V0, hc, ListEmit{c->cand.p}, c->block_sums.p, cnt + C_HIT, s))) return rc;
-    if ((rc = read_counters(c, s))) return rc;
-    const int Hn = c->h_counters[C_HIT];
+    const int Hn = c->h_counters[C_HIT], P = c->h_counters[C_PAIRS];
     const int n_cand = Hn + S;
-    k_fill_new_cands<<<grid_for(S, 256), 256, 0, s>>>(c->cand.p, Hn, S, V0);
-    TNB_LAUNCH_CHECK();
-    c->stamp += 1;
-    if (c->stamp == 0) {  // generation wrapped: clear the heads once
-        TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
-        c->stamp = 1;
-    }
-    const uint64_t colmask = (1ull << idx) - 1ull;
-    {
-        unsigned g = grid_for(n_cand, kThreads);
-        k_bucket_insert<<<g, kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp);
-        TNB_LAUNCH_CHECK();
-        k_pair_count<<<g, kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, cnt);
-        TNB_LAUNCH_CHECK();
-    }
-    if ((rc = compact(n_cand, ArrayCount{c->pcount.p}, OffsetEmit{c->poff.p}, c->block_sums.p, cnt + C_PAIRS, s))) return rc;
-    if ((rc = read_counters(c, s))) return rc;
-    if (c->h_counters[C_OVERFLOW]) { set_error("a vertex has more than 256 connecting partners"); return TNB_ERR_CAPACITY; }
-    const int P = c->h_counters[C_PAIRS];
-    if ((rc = complex_reserve(c, c->V + S, (size_t)E0 + S + P, s))) return rc;
+    if ((rc = complex_reserve(c, (size_t)V0 + S, (size_t)E0 + S + P, s))) return rc;
+    cnt = c->counters.p;
     if (P > 0) {
+        prof_begin(TNB_PROF_PAIRS, s);
         k_pair_write<<<grid_for(n_cand, kThreads), kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S);
         TNB_LAUNCH_CHECK();
+        prof_end(TNB_PROF_PAIRS, s, n_cand);
     }
     c->V = V0 + S;
     c->E = (int64_t)E0 + S + P;
 
-    // 4. pruning (not for the output neuron, subpoly.py:253)
+    // 4. pruning (not for the output neuron, subpoly.py:253); its sizes stay on the device
     if (h < H) {
         const uint64_t futmask = ~colmask & (R >= 64 ? ~0ull : ((1ull << R) - 1ull));
         TNB_CUDA(cudaMemsetAsync(c->used.p, 0, (size_t)c->V * sizeof(int), s));
         KeepCount kc{c->cedges(), c->csig(), futmask};
         int2 *dst = c->edges[c->ecur ^ 1].p;
-        if ((rc = compact(c->E, kc, KeepEmit{c->cedges(), dst, c->used.p}, c->block_sums.p, cnt + C_EDGES, s))) return rc;
+        if ((rc = compact(c->E, kc, KeepEmit{c->cedges(), dst, c->used.p}, c->block_sums.p, cnt + C_E, s))) return rc;
         const int o = c->vcur ^ 1;
         VertexMoveEmit vm{c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->sig[o].p, c->remap.p, R};
-        if ((rc = compact(c->V, FlagCount{c->used.p}, vm, c->block_sums.p, cnt + C_VERTS, s))) return rc;
-        if ((rc = read_counters(c, s))) return rc;
-        c->E = c->h_counters[C_EDGES];
-        c->V = c->h_counters[C_VERTS];
+        if ((rc = compact(c->V, FlagCount{c->used.p}, vm, c->block_sums.p, cnt + C_V, s))) return rc;
         c->ecur ^= 1;
         c->vcur = o;
-        if (c->E > 0) {
-            k_remap_edges<<<grid_for(c->E, 256), 256, 0, s>>>(c->cedges(), c->E, c->remap.p);
-            TNB_LAUNCH_CHECK();
-        }
+        k_remap_edges_dev<<<grid_for(c->E, 256), 256, 0, s>>>(c->cedges(), cnt + C_E, c->remap.p);
+        TNB_LAUNCH_CHECK();
+        c->counts_stale = true;  // c->V, c->E are upper bounds until the next sync
+    } else {
+        k_set_counts<<<1, 1, 0, s>>>(cnt, (int)c->V, (int)c->E);
+        TNB_LAUNCH_CHECK();
     }
     return TNB_OK;
 }
@@ -774,6 +843,8 @@ static int from_arrays_impl(const tnb_net *net, const float *d_vertices, int64_t
     }
     c->V = V;
     c->E = E;
+    k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E);
+    TNB_LAUNCH_CHECK();
     return eval_vertices(net, c, 0, V, s);
 }
 
@@ -795,9 +866,10 @@ int tnb_skeleton(const tnb_net *net, int32_t unit, float size, tnb_complex **out
     if (!net || !out) { set_error("tnb_skeleton: null argument"); return TNB_ERR_INVALID; }
     *out = nullptr;
     cudaStream_t s = (cudaStream_t)stream;
+    current_stream() = s;
     tnb_complex *c = nullptr;
     int rc = skeleton_impl(net, unit, &c, s);
-    if (rc == TNB_OK && c->E == 0) {  // we start with a hypercube (subpoly.py:51-52)
+    if (rc == TNB_OK && c->E == 0 && size > 0.0f) {  // we start with a hypercube (subpoly.py:51-52)
         delete c;
         c = nullptr;
         std::vector<float> v;
@@ -810,9 +882,10 @@ int tnb_skeleton(const tnb_net *net, int32_t unit, float size, tnb_complex **out
         TNB_CUDA(cudaMemcpyAsync(dv.p, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice, s));
         TNB_CUDA(cudaMemcpyAsync(de.p, e.data(), e.size() * sizeof(int64_t), cudaMemcpyHostToDevice, s));
         rc = from_arrays_impl(net, dv.p, 8, de.p, (int64_t)e.size() / 2, &c, s);
-        cudaStreamSynchronize(s);
+        cudaStreamSynchronize(s);  // v, e (host vectors) are read by the async copies
     }
     if (rc != TNB_OK) { delete c; return rc; }
+    c->stream = s;
     *out = c;
     return TNB_OK;
 }
@@ -825,21 +898,36 @@ int tnb_complex_from_arrays(const tnb_net *net, const float *d_vertices, int64_t
         return TNB_ERR_INVALID;
     }
     *out = nullptr;
+    current_stream() = (cudaStream_t)stream;
     tnb_complex *c = nullptr;
     int rc = from_arrays_impl(net, d_vertices, V, d_edges, E, &c, (cudaStream_t)stream);
     if (rc != TNB_OK) { delete c; return rc; }
+    c->stream = (cudaStream_t)stream;
     *out = c;
     return TNB_OK;
 }
 
 void tnb_complex_destroy(tnb_complex *c) { delete c; }
-int64_t tnb_complex_num_vertices(const tnb_complex *c) { return c ? c->V : 0; }
-int64_t tnb_complex_num_edges(const tnb_complex *c) { return c ? c->E : 0; }
+int64_t tnb_complex_num_vertices(const tnb_complex *c)
+{
+    if (!c) return 0;
+    complex_sync_counts(const_cast<tnb_complex *>(c), c->stream);
+    return c->V;
+}
+int64_t tnb_complex_num_edges(const tnb_complex *c)
+{
+    if (!c) return 0;
+    complex_sync_counts(const_cast<tnb_complex *>(c), c->stream);
+    return c->E;
+}
 
 int tnb_complex_read(const tnb_complex *c, float *d_vertices, int64_t *d_edges, float *d_outputs, void *stream)
 {
     if (!c) { set_error("tnb_complex_read: null complex"); return TNB_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
+    current_stream() = s;
+    int rcs = complex_sync_counts(const_cast<tnb_complex *>(c), s);
+    if (rcs) return rcs;
     if (d_vertices && c->V) TNB_CUDA(cudaMemcpyAsync(d_vertices, c->cvert(), (size_t)c->V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (d_outputs && c->V) TNB_CUDA(cudaMemcpyAsync(d_outputs, c->cout_(), (size_t)c->V * c->R * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (d_edges && c->E) {
@@ -857,6 +945,8 @@ int tnb_subpoly_step(const tnb_net *net, tnb_complex *c, int32_t l, int32_t h, f
                   "only the planar path (the reference default) runs on the device");
         return TNB_ERR_UNSUPPORTED;
     }
+    current_stream() = (cudaStream_t)stream;
+    c->stream = (cudaStream_t)stream;
     return step_impl(net, c, l, h, eps, (cudaStream_t)stream);
 }
 

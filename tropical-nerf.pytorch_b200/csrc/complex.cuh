@@ -29,7 +29,9 @@ struct tnb_complex {
     tnb::DevBuf<int> remap;         // [Vcap]
     tnb::DevBuf<int> block_sums;    // [kScanMaxBlocks]
     tnb::DevBuf<int> counters;      // [16] device counters
-    int *h_counters = nullptr;      // pinned mirror
+    int *h_counters = nullptr;      // pinned mirror (per thread, not owned)
+    bool counts_stale = false;      // V/E are upper bounds; exact sizes are in counters[C_V], [C_E]
+    cudaStream_t stream = nullptr;  // stream of the last call
     uint32_t stamp = 0;             // bucket generation
     int64_t n_cells = 0;
     int cell_dim = 0;
@@ -48,6 +50,7 @@ struct tnb_complex {
 namespace tnb {
 int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap);
 int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s);
+int complex_sync_counts(tnb_complex *c, cudaStream_t s);
 int launch_outputs(const tnb_net *net, const float *d_x, int64_t n, float *d_out, cudaStream_t s);
 int launch_sdf_grad(const tnb_net *net, const float *d_x, int64_t n, float *d_sdf, float *d_grad, cudaStream_t s);
 int launch_region(const tnb_net *net, const float *d_x, const float *d_outputs, int64_t n, float eps,

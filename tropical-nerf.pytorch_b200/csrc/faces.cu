@@ -348,6 +348,10 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
 {
     const NetMeta &nm = net->meta;
     const int R = nm.R;
+    {
+        int rcs = complex_sync_counts(const_cast<tnb_complex *>(c), s);
+        if (rcs) return rcs;
+    }
     const int64_t V = c->V, E = c->E;
     if (V == 0) return TNB_OK;
     DevBuf<int> surf, used, remap, block_sums, counters;
@@ -375,7 +379,7 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
     // vertex compaction: count first to size the mesh
     {
         int64_t blocks = std::min<int64_t>((V + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
-        k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, FlagCount{used.p}, block_sums.p);
+        k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, nullptr, FlagCount{used.p}, block_sums.p);
         TNB_LAUNCH_CHECK();
         std::vector<int> hb(blocks);
         if ((rc = read_small(block_sums.p, hb.data(), (int)blocks, s))) return rc;
@@ -387,7 +391,7 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
         TNB_CUDA(m->out.reserve((size_t)std::max<int64_t>(Vs, 1) * R));
         TNB_CUDA(m->edges.reserve((size_t)std::max<int64_t>(Es, 1)));
         SurfVertEmit ve{c->cvert(), c->cout_(), m->vert.p, m->out.p, remap.p, R};
-        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, FlagCount{used.p}, ve, block_sums.p, counters.p + F_VERTS);
+        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, nullptr, FlagCount{used.p}, ve, block_sums.p, counters.p + F_VERTS);
         TNB_LAUNCH_CHECK();
     }
     if (Es > 0) {
@@ -396,7 +400,7 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
         TNB_LAUNCH_CHECK();
     }
     const int64_t Vs = m->V;
-    if (Vs == 0) { TNB_CUDA(cudaStreamSynchronize(s)); return TNB_OK; }
+    if (Vs == 0) return TNB_OK;
 
     // ---- extract_faces ----
     DevBuf<uint64_t> sig;
@@ -417,9 +421,11 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
     k_face_bucket_insert<<<grid_for(Vs, 256), 256, 0, s>>>(Vs, sig.p, head.p, next.p, dim, stamp);
     TNB_LAUNCH_CHECK();
     const unsigned gw = grid_for(Vs, kThreads / 32);
+    prof_begin(TNB_PROF_FACE_ROWS, s);
     k_region_rows<<<gw, kThreads, 0, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 0, rows_per_vertex.p, nullptr,
                                          nullptr, nullptr, 0, counters.p);
     TNB_LAUNCH_CHECK();
+    prof_end(TNB_PROF_FACE_ROWS, s, Vs);
     if ((rc = compact(Vs, ArrayCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
     if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
     if (h[F_ERR_ZEROS]) { set_error("a surface vertex lies on more than 5 planes: more than 32 adjacent regions"); return TNB_ERR_UNSUPPORTED; }
@@ -428,7 +434,7 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
     const int W = h[F_WIDTH];
     m->P = P;
     m->W = W;
-    if (P == 0) { TNB_CUDA(cudaStreamSynchronize(s)); return TNB_OK; }
+    if (P == 0) return TNB_OK;
     TNB_CUDA(m->poly.reserve((size_t)P * W));
     TNB_CUDA(m->pcnt.reserve((size_t)P));
     k_region_rows<<<gw, kThreads, 0, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 1, rows_per_vertex.p, row_off.p,
@@ -465,8 +471,7 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
                           counters.p + F_VERTS, s)))
             return rc;
     }
-    TNB_CUDA(cudaStreamSynchronize(s));  // locals are freed on return
-    return TNB_OK;
+    return TNB_OK;  // locals are released in stream order
 }
 
 // ---- read back -------------------------------------------------------------------------------------
@@ -493,6 +498,7 @@ extern "C" {
 int tnb_extract_mesh(const tnb_net *net, const tnb_complex *c, float eps, tnb_mesh **out, void *stream)
 {
     if (!net || !c || !out) { set_error("tnb_extract_mesh: null argument"); return TNB_ERR_INVALID; }
+    current_stream() = (cudaStream_t)stream;
     tnb_mesh *m = new tnb_mesh();
     int rc = extract_impl(net, c, eps, m, (cudaStream_t)stream);
     if (rc != TNB_OK) { delete m; *out = nullptr; return rc; }
@@ -512,6 +518,7 @@ int tnb_mesh_read(const tnb_mesh *m, float *d_vertices, int64_t *d_edges, int64_
 {
     if (!m) { set_error("tnb_mesh_read: null mesh"); return TNB_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
+    current_stream() = s;
     if (d_vertices && m->V) TNB_CUDA(cudaMemcpyAsync(d_vertices, m->vert.p, (size_t)m->V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (d_edges && m->E) {
         k_i32_to_i64<<<grid_for(m->E * 2, 256), 256, 0, s>>>((const int *)m->edges.p, m->E * 2, d_edges);
@@ -535,6 +542,8 @@ int tnb_mesh_read(const tnb_mesh *m, float *d_vertices, int64_t *d_edges, int64_
 int tnb_mesh_read_host(const tnb_mesh *m, float *h_vertices, int64_t *h_triangles, float *h_faces, int64_t *h_polygons)
 {
     if (!m) { set_error("tnb_mesh_read_host: null mesh"); return TNB_ERR_INVALID; }
+    TNB_CUDA(cudaDeviceSynchronize());
+    current_stream() = nullptr;
     DevBuf<int64_t> t64, p64;
     DevBuf<float> f;
     if (h_vertices && m->V) TNB_CUDA(cudaMemcpy(h_vertices, m->vert.p, (size_t)m->V * 3 * sizeof(float), cudaMemcpyDeviceToHost));

@@ -3,6 +3,8 @@
 #include <cmath>
 #include <cstring>
 #include <mutex>
+#include <utility>
+#include <vector>
 
 #include "net_eval.cuh"
 #include "runtime.cuh"
@@ -20,6 +22,65 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line)
     return TNB_ERR_CUDA;
 }
 void count_launch(int n) { g_launches += n; }
+
+cudaStream_t &current_stream()
+{
+    static thread_local cudaStream_t s = nullptr;
+    return s;
+}
+void init_pool_once()
+{
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = ~0ull;  // never trim: the work buffers are reused by the next extraction
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    });
+}
+
+struct ProfClass {
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
+    cudaEvent_t open = nullptr;
+    int64_t units = 0;
+    double ms = 0.0;
+    int64_t launches = 0;
+};
+static bool g_prof_on = false;
+static ProfClass g_prof[TNB_PROF_CLASSES];
+void prof_begin(int cls, cudaStream_t s)
+{
+    if (!g_prof_on) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    g_prof[cls].open = e;
+}
+void prof_end(int cls, cudaStream_t s, int64_t units)
+{
+    if (!g_prof_on || !g_prof[cls].open) return;
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    cudaEventRecord(e, s);
+    g_prof[cls].ev.emplace_back(g_prof[cls].open, e);
+    g_prof[cls].open = nullptr;
+    g_prof[cls].units += units;
+}
+static void prof_collect(int cls)
+{
+    for (auto &pr : g_prof[cls].ev) {
+        cudaEventSynchronize(pr.second);
+        float ms = 0.0f;
+        cudaEventElapsedTime(&ms, pr.first, pr.second);
+        g_prof[cls].ms += ms;
+        g_prof[cls].launches += 1;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    g_prof[cls].ev.clear();
+}
 
 constexpr int kThreads = 128;
 
@@ -202,6 +263,25 @@ int tnb_device_count(void)
 }
 int64_t tnb_launch_count(void) { return g_launches; }
 void tnb_launch_count_reset(void) { g_launches = 0; }
+int tnb_profile_enable(int on) { g_prof_on = on != 0; return TNB_OK; }
+void tnb_profile_reset(void)
+{
+    for (int c = 0; c < TNB_PROF_CLASSES; ++c) {
+        prof_collect(c);
+        g_prof[c].ms = 0.0;
+        g_prof[c].launches = 0;
+        g_prof[c].units = 0;
+    }
+}
+int tnb_profile_read(int cls, double *ms, int64_t *launches, int64_t *units)
+{
+    if (cls < 0 || cls >= TNB_PROF_CLASSES) { set_error("tnb_profile_read: bad class"); return TNB_ERR_INVALID; }
+    prof_collect(cls);
+    if (ms) *ms = g_prof[cls].ms;
+    if (launches) *launches = g_prof[cls].launches;
+    if (units) *units = g_prof[cls].units;
+    return TNB_OK;
+}
 
 int tnb_net_create(const tnb_net_desc *d, tnb_net **out)
 {
@@ -218,6 +298,7 @@ int tnb_net_create(const tnb_net_desc *d, tnb_net **out)
     if (d->n_marks < 2 || d->n_marks >= (1 << 20) - 2) { set_error("tnb_net_create: bad n_marks"); return TNB_ERR_INVALID; }
     if (tnb_device_count() == 0) { set_error("no CUDA device: this library has no CPU path"); return TNB_ERR_CUDA; }
 
+    current_stream() = nullptr;  // created with blocking copies on the default stream
     tnb_net *net = new tnb_net();
     NetMeta &m = net->meta;
     memset(&m, 0, sizeof(m));
@@ -319,6 +400,7 @@ int tnb_net_region(const tnb_net *net, const float *d_x, const float *d_outputs,
     if (!net || (n > 0 && !d_x)) { set_error("tnb_net_region: null argument"); return TNB_ERR_INVALID; }
     if (n <= 0) return TNB_OK;
     cudaStream_t s = (cudaStream_t)stream;
+    current_stream() = s;
     DevBuf<float> tmp;
     if (!d_outputs) {
         TNB_CUDA(tmp.reserve((size_t)n * net->meta.R));
@@ -328,7 +410,6 @@ int tnb_net_region(const tnb_net *net, const float *d_x, const float *d_outputs,
     }
     int rc = launch_region(net, d_x, d_outputs, n, eps, d_signs, d_offset, d_packed, s);
     if (rc) return rc;
-    if (tmp.p) TNB_CUDA(cudaStreamSynchronize(s));  // tmp is freed on return
     return TNB_OK;
 }
 
@@ -344,11 +425,13 @@ int tnb_sweep_signs(const tnb_net *net, const float lo[3], const float hi[3], co
     int64_t count = (int64_t)nn[0] * nn[1] * nn[2];
     cudaStream_t s = (cudaStream_t)stream;
     unsigned g = grid_for(count, kThreads, kSMs * 32);
+    prof_begin(TNB_PROF_SIGN_SWEEP, s);
     if (net->fixed_cfg)
         k_sweep_signs<CfgRef><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], eps, (ulonglong2 *)d_packed);
     else
         k_sweep_signs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], eps, (ulonglong2 *)d_packed);
     TNB_LAUNCH_CHECK();
+    prof_end(TNB_PROF_SIGN_SWEEP, s, count);
     return TNB_OK;
 }
 

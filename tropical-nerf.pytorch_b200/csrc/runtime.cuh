@@ -6,18 +6,25 @@
 
 namespace tnb {
 
-// RAII device array
+// Stream the library is currently working on (set at every C ABI entry).  Device arrays
+// are carved from the CUDA stream-ordered memory pool of the device, whose release
+// threshold is raised once so that repeated extractions never go back to cudaMalloc.
+cudaStream_t &current_stream();
+void init_pool_once();
+
+// RAII device array (stream-ordered allocation)
 template <class T>
 struct DevBuf {
     T *p = nullptr;
     size_t cap = 0;  // elements
+    cudaStream_t stream = nullptr;
     DevBuf() = default;
     DevBuf(const DevBuf &) = delete;
     DevBuf &operator=(const DevBuf &) = delete;
     ~DevBuf() { release(); }
     void release()
     {
-        if (p) cudaFree(p);
+        if (p) cudaFreeAsync(p, stream);
         p = nullptr;
         cap = 0;
     }
@@ -26,7 +33,9 @@ struct DevBuf {
     {
         if (n <= cap) return cudaSuccess;
         release();
-        cudaError_t e = cudaMalloc((void **)&p, (n ? n : 1) * sizeof(T));
+        init_pool_once();
+        stream = current_stream();
+        cudaError_t e = cudaMallocAsync((void **)&p, (n ? n : 1) * sizeof(T), stream);
         if (e == cudaSuccess) cap = n; else p = nullptr;
         return e;
     }
@@ -34,6 +43,7 @@ struct DevBuf {
     {
         T *tp = p; p = o.p; o.p = tp;
         size_t tc = cap; cap = o.cap; o.cap = tc;
+        cudaStream_t ts = stream; stream = o.stream; o.stream = ts;
     }
 };
 

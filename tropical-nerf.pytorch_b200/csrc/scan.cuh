@@ -50,9 +50,13 @@ __device__ __forceinline__ void scan_slice(int64_t n, int64_t &begin, int64_t &e
     if (end > n) end = n;
 }
 
+// n_dev (optional): the item count lives in device memory (a previous kernel produced it);
+// n is then only the host's upper bound used to size the grid.
 template <class Count>
-__global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, Count count, int *__restrict__ block_sums)
+__global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, const int *__restrict__ n_dev, Count count,
+                                                             int *__restrict__ block_sums)
 {
+    if (n_dev) n = *n_dev;
     int64_t begin, end;
     scan_slice(n, begin, end);
     int acc = 0;
@@ -69,10 +73,11 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, Count co
 }
 
 template <class Count, class Emit>
-__global__ void __launch_bounds__(kScanThreads) k_scan_write(int64_t n, Count count, Emit emit,
-                                                             const int *__restrict__ block_sums,
+__global__ void __launch_bounds__(kScanThreads) k_scan_write(int64_t n, const int *__restrict__ n_dev, Count count,
+                                                             Emit emit, const int *__restrict__ block_sums,
                                                              int *__restrict__ total)
 {
+    if (n_dev) n = *n_dev;
     __shared__ int s_warp[kScanWarps];
     __shared__ int s_base;
     // base offset of this block = sum of the sums before it; block 0 also publishes the total
@@ -117,7 +122,8 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_write(int64_t n, Count co
 // Host helper: runs both phases.  `block_sums` must hold kScanMaxBlocks ints; the total
 // lands in *d_total (device).
 template <class Count, class Emit>
-inline int compact(int64_t n, Count count, Emit emit, int *block_sums, int *d_total, cudaStream_t s)
+inline int compact(int64_t n, Count count, Emit emit, int *block_sums, int *d_total, cudaStream_t s,
+                   const int *n_dev = nullptr)
 {
     if (n <= 0) {
         TNB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int), s));
@@ -125,9 +131,9 @@ inline int compact(int64_t n, Count count, Emit emit, int *block_sums, int *d_to
     }
     int64_t blocks = (n + kScanThreads - 1) / kScanThreads;
     if (blocks > kScanMaxBlocks) blocks = kScanMaxBlocks;
-    k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, count, block_sums);
+    k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, n_dev, count, block_sums);
     TNB_LAUNCH_CHECK();
-    k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, count, emit, block_sums, d_total);
+    k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, n_dev, count, emit, block_sums, d_total);
     TNB_LAUNCH_CHECK();
     return TNB_OK;
 }

@@ -1,0 +1,91 @@
+"""Net (reference: tropical/stanford/model.py), CUDA-backed for the extraction path."""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+from torch import Tensor
+
+from tropical import TropicalHashGrid
+from tropical import _native
+
+
+class Net(nn.Module):
+    """HashGrid + ReLU MLP SDF network (model.py:18-50).  Same constructor, parameter names
+    and methods as the reference; forward/sdf/region/normal run in the fused sm_100a
+    kernels (no autograd through them: the extraction path is @torch.no_grad in the
+    reference too, and its input gradients are computed analytically on the device)."""
+
+    def __init__(self, num_layers: int = 3, num_hidden: int = 16, levels: int = 4,
+                 r_min: int = 2, r_max: int = 32, T: int = 19, eps: float = 1e-4):
+        super().__init__()
+        DIM = 3
+        self.num_layers, self.num_hidden, self.eps = num_layers, num_hidden, eps
+        L, Fe = levels, 2
+        self.scale = 1
+        self.enc = TropicalHashGrid(1.0, DIM, L, Fe, T, r_min, r_max, eps)
+        num_nodes = [L * Fe] + [num_hidden] * (num_layers - 1) + [2]
+        self.num_nodes = num_nodes
+        self.fc = nn.ModuleList([nn.Linear(num_nodes[i], num_nodes[i + 1])
+                                 for i in range(len(num_nodes) - 1)])
+        self._native_cache = None
+
+    # ---- device copy of the network ------------------------------------------------------
+    def native(self) -> "_native.NativeNet":
+        """The tnb_net for the current parameters (rebuilt when any parameter changed)."""
+        key = tuple((p._version, p.data_ptr()) for p in self.parameters())
+        if self._native_cache is None or self._native_cache[0] != key:
+            mlp = np.concatenate([np.concatenate([fc.weight.detach().cpu().numpy().reshape(-1),
+                                                  fc.bias.detach().cpu().numpy().reshape(-1)])
+                                  for fc in self.fc]).astype(np.float32)
+            nat = _native.NativeNet(self.enc.L, self.enc.F, self.enc.T, self.enc.N_min, self.enc.b,
+                                    self.num_layers, self.num_hidden,
+                                    self.enc.module.params.detach().cpu().numpy(), mlp,
+                                    self.enc.marks.cpu().numpy(), self.eps, self.scale)
+            self._native_cache = (key, nat)
+        return self._native_cache[1]
+
+    def forward(self, x, gather: bool = False, group: int = 1):
+        """model.py:52-76.  gather=True returns (output, [hidden pre-activations..., o1-o0])."""
+        if group != 1:
+            raise _native.NativeError("group != 1 belongs to the curve-approximation path "
+                                      "(force=False), which is not built on the device yet")
+        nat = self.native()
+        rows = nat.outputs(x)
+        H = self.num_hidden
+        inputs = [rows[:, i * H:(i + 1) * H] for i in range(self.num_layers - 1)] + [rows[:, -1:]]
+        # the last linear layer on the last hidden activation gives the 2-vector output
+        h = F.relu(inputs[-2])
+        out = F.linear(h, self.fc[-1].weight, self.fc[-1].bias)
+        if gather:
+            return out, inputs
+        return out
+
+    def preprocess(self, x):
+        return (x + self.scale) / (self.scale * 2)
+
+    def preprocess_inverse(self, x):
+        return x * (self.scale * 2) - self.scale
+
+    def sdf(self, x):
+        """tanh(o1 - o0) (model.py:84-88), [n,1]."""
+        sdf, _ = self.native().sdf_grad(x, want_grad=False)
+        return sdf.unsqueeze(-1)
+
+    def region(self, vertices: Tensor, output: Tensor = None, eps=None):
+        """Sign vectors + grid offsets (model.py:90-103): (m [n,3+R] int64, offset [n,3]
+        int64, output [n,R])."""
+        signs, offset, output = self.native().region(vertices, output, eps)
+        return signs.long(), offset.long(), output
+
+    def normal(self, vertices: Tensor, l: int = None, h: int = None, create_graph=False,
+               return_y=False) -> Tensor:
+        """d sdf / d x (model.py:105-123), analytic on the device."""
+        if not (l is None or h is None or h == self.num_hidden) or create_graph:
+            raise _native.NativeError("only the SDF normal (l=h=None) is available on the device")
+        y, J = self.native().sdf_grad(vertices.detach())
+        if return_y:
+            return J, y.unsqueeze(-1)
+        return J
+
+    def device(self):
+        return next(self.parameters()).device

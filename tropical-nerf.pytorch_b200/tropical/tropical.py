@@ -1,0 +1,178 @@
+"""TropicalHashGrid / Tropical (reference: tropical/tropical.py), CUDA-backed.
+
+`TropicalHashGrid.module` is a `HashEncoding` -- the tiny-cuda-nn `Encoding` stand-in whose
+forward runs the fused sm_100a gather kernel (`tnb_grid_encode`).  Parameter names match
+the reference (`enc.module.params`), so its released state_dicts load unchanged.
+"""
+from typing import Any, Tuple
+
+import numpy as np
+import torch
+from torch import LongTensor, Tensor
+from torch.nn import Module
+
+from . import _native
+
+__all__ = ["HashEncoding", "TropicalHashGrid", "Tropical", "low_precision"]
+
+
+class HashEncoding(Module):
+    """Multiresolution hash encoding with tiny-cuda-nn's parameter layout
+    (`tcnn.Encoding(D, {"otype": "Grid", "type": "Hash", ...}, dtype=torch.float)`,
+    tropical.py:32-40).  Inference only: the extraction path never differentiates through
+    it (gradients w.r.t. the input come from `tnb_net_sdf_grad`)."""
+
+    def __init__(self, n_input_dims, n_levels, n_features_per_level, log2_hashmap_size,
+                 base_resolution, per_level_scale, seed=1337):
+        super().__init__()
+        assert n_input_dims == 3 and n_features_per_level == 2
+        self.n_levels, self.n_features = n_levels, n_features_per_level
+        self.log2_hashmap_size, self.base_resolution = log2_hashmap_size, base_resolution
+        self.per_level_scale = float(per_level_scale)
+        self.n_output_dims = n_levels * n_features_per_level
+        self.level_sizes = self._layout()
+        g = torch.Generator().manual_seed(seed)
+        init = (torch.rand(int(sum(self.level_sizes)) * self.n_features, generator=g) * 2 - 1) * 1e-4
+        self.params = torch.nn.Parameter(init)  # U(-1e-4, 1e-4) like tiny-cuda-nn
+        # set by TropicalHashGrid (kept out of nn.Module's registry: no module cycle)
+        self.__dict__["_owner"] = None
+
+    def _layout(self):
+        import ctypes
+        libm = ctypes.CDLL("libm.so.6")
+        for fn in (libm.log2f, libm.exp2f):
+            fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float]
+        log2_pls = np.float32(libm.log2f(np.float32(self.per_level_scale)))
+        sizes = []
+        for l in range(self.n_levels):
+            s = np.float32(np.float32(libm.exp2f(np.float32(l) * log2_pls))
+                           * np.float32(self.base_resolution) - np.float32(1.0))
+            res = int(np.ceil(s)) + 1
+            n = min((res ** 3 + 7) // 8 * 8, 1 << self.log2_hashmap_size)
+            sizes.append(n)
+        return sizes
+
+    def forward(self, x: Tensor) -> Tensor:
+        if torch.is_grad_enabled() and (x.requires_grad or self.params.requires_grad):
+            raise _native.NativeError(
+                "HashEncoding.forward is inference-only on the device path; wrap the call in "
+                "torch.no_grad() (input gradients: Net.normal / tnb_net_sdf_grad)")
+        return self._owner._native_for_encoding().encode(x)
+
+
+class TropicalHashGrid(Module):
+    """tropical.py:20-239."""
+
+    def __init__(self, scale: float = 1.0, D: int = 3, L: int = 16, F: int = 2,
+                 T: int = 19, N_min: int = 16, N_max: int = 2048, eps: float = 1e-4):
+        super().__init__()
+        self.scale, self.D, self.L, self.F, self.T = scale, D, L, F, T
+        self.N_min, self.N_max = N_min, N_max
+        self.b = np.exp2(np.log2(N_max * scale / N_min) / (L - 1))
+        self.module = HashEncoding(D, L, F, T, N_min, self.b)
+        self.module.__dict__["_owner"] = self
+        self.eps = eps
+        self.marks = self._marks()
+        self._enc_native = None
+
+    def forward(self, x):
+        return self.module(x)
+
+    def _marks(self):
+        """Aggregated, sorted, eps-merged grid marks of all levels (tropical.py:49-79).
+        Same torch operations as the reference, evaluated on the host."""
+        vertices = []
+        for l in range(self.L):
+            grid_scale = np.exp2(l * np.log2(self.b)) * self.N_min - 1.0
+            unit = 1 / grid_scale
+            vertices += [torch.arange(0, 1.5, unit) - 0.5 * unit]
+        vertices += [torch.Tensor([0, self.scale])]
+        marks, _ = torch.cat(vertices).unique().sort()
+        m = marks.new_zeros(len(marks)).bool().fill_(True)
+        for i in range(len(marks) - 1):
+            if self.eps > (marks[i] - marks[i + 1]).abs():
+                marks[i + 1] = (marks[i] + marks[i + 1]) / 2
+                m[i] = False
+        marks = marks[m]
+        marks = marks[marks >= 0]
+        marks = marks[marks <= self.scale]
+        return marks
+
+    # encoding-only native net (no MLP owner): a 2-layer dummy MLP keeps the ABI uniform
+    def _native_for_encoding(self):
+        key = (self.module.params._version, self.module.params.data_ptr())
+        if self._enc_native is None or self._enc_native[0] != key:
+            mlp = np.zeros(2 * self.L * self.F + 2 + 2 * 2 + 2, np.float32)  # [L*F -> 2 -> 2]
+            nn_ = _native.NativeNet(self.L, self.F, self.T, self.N_min, self.b, 2, 2,
+                                    self.module.params.detach().cpu().numpy(), mlp,
+                                    self.marks.cpu().numpy(), self.eps, self.scale)
+            self._enc_native = (key, nn_)
+        return self._enc_native[1]
+
+    def p2v(self, indices: LongTensor) -> LongTensor:
+        """Serialized vertex index from marks-grid indices (tropical.py:141-146)."""
+        L = len(self.marks)
+        weights = indices.new_tensor([L ** (self.D - 1 - i) for i in range(self.D)])
+        return (indices * weights).sum(dim=-1).long()
+
+    def v2p(self, v_idx: LongTensor) -> LongTensor:
+        """tropical.py:149-156."""
+        L = len(self.marks)
+        p, rest = [], v_idx.clone()
+        for i in range(self.D - 1, -1, -1):
+            q = torch.div(rest, L ** i, rounding_mode="floor")
+            p.append(q.long())
+            rest = rest - q * L ** i
+        return torch.stack(p, dim=-1)
+
+    def skeleton(self, net: Module, unit: int = 128) -> Tuple[Tensor, Tensor]:
+        """Starting skeleton: the marks-grid edges near the surface (tropical.py:158-225,
+        distance pruning).  Runs `tnb_skeleton`; returns (vertices [V,3], edges [V,2]) on the
+        device, or two empty tensors when nothing survives (tropical.py:208-209)."""
+        cx = net.native().skeleton(unit, 0.0)  # size 0: no hypercube fallback here
+        if cx.num_edges == 0:
+            e = torch.empty(0, dtype=torch.int64, device="cuda")
+            return e, e
+        v, e, _ = cx.read(outputs=False)
+        return v, e
+
+    def region(self, x: Tensor, eps: float = None) -> Tuple[Tensor, Tensor]:
+        """Epsilon-tolerant grid offsets and on-plane masks (tropical.py:227-236)."""
+        eps = eps if eps is not None else self.eps
+        marks = self.marks.to(x.device)
+        offset = torch.searchsorted(marks, x + eps) - 1
+        mask = ((marks[offset] - x).abs() > eps).long()
+        return mask, offset
+
+    def device(self):
+        return next(self.parameters()).device
+
+
+class Tropical(Module):
+    """tropical.py:242-281."""
+
+    def __init__(self, module: Module, dim: int = 3, scale: float = 1.0):
+        super().__init__()
+        self.module, self.dim, self.scale = module, dim, scale
+
+    def region(self, x: Tensor) -> Any:
+        return NotImplementedError
+
+    def grid(self) -> Tuple[Tensor, Tensor]:
+        for m in self.module.modules():
+            if isinstance(m, TropicalHashGrid):
+                return m.skeleton(self.module)
+        vertices, edges, _ = self.get_hypercube(self.dim, self.scale / 2)
+        return vertices, edges
+
+    def get_hypercube(self, d, size):
+        from .subpoly import get_hypercube
+        return get_hypercube(d, size)
+
+
+def low_precision(x):
+    """tropical.py:284-288."""
+    x *= 100000
+    x = x.floor()
+    x /= 100000
+    return x
