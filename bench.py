@@ -51,6 +51,8 @@ def load_workload(name):
                     marks=g["net_marks"], eps=float(g["net_eps"]), scale=float(g["net_scale"]),
                     describe=f"small HashGrid+MLP (L=4 F=2 T=19 r=2..32, MLP 8-16-16-2) briefly fitted to an "
                              f"analytic {shape} SDF, planar (-f) extraction, marks grid {len(g['net_marks'])}^3")
+    if name.split("_")[0] in ("medium", "large") and name.split("_")[1] in ("sphere", "torus"):
+        return fitted_workload(*name.split("_")[:2])
     if name.endswith("_random"):
         from tropical.stanford.model import Net
         import torch
@@ -68,6 +70,104 @@ def load_workload(name):
                     describe=f"{size} HashGrid+MLP (r={r_min}..{r_max}), random-init weights (table U(-1,1)), "
                              f"planar (-f) extraction, marks grid {len(net.enc.marks)}^3")
     raise SystemExit(f"unknown workload {name}")
+
+
+def fitted_workload(size, shape, steps=800, batch=1 << 16):
+    """medium / large HashGrid+MLP briefly fitted to an analytic SDF (BASELINE.json: datasets
+    and checkpoints are unavailable offline).  Workload GENERATION only: a plain torch
+    autograd fit (pure-torch hash-grid gather), run once per box and cached so that both
+    bench arms and every rank see identical weights."""
+    import tempfile
+    import torch
+    from tropical.stanford.model import Net
+    r_min, r_max = {"medium": (4, 64), "large": (8, 128)}[size]
+    cache = os.path.join(tempfile.gettempdir(), f"tnb_workload_{size}_{shape}_{steps}.npz")
+    torch.manual_seed(0)
+    net = Net(num_layers=3, num_hidden=16, levels=4, r_min=r_min, r_max=r_max, T=19)
+    describe = (f"{size} HashGrid+MLP (L=4 F=2 T=19 r={r_min}..{r_max}, MLP 8-16-16-2) briefly fitted "
+                f"({steps} Adam steps) to an analytic {shape} SDF, planar (-f) extraction, marks grid "
+                f"{len(net.enc.marks)}^3")
+    base = dict(levels=4, n_feat=2, log2_T=19, n_min=r_min, per_level_scale=float(net.enc.b), num_layers=3,
+                num_hidden=16, marks=net.enc.marks.numpy(), eps=1e-4, scale=1.0, describe=describe)
+    rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not os.path.exists(cache) and rank != 0:
+        for _ in range(3000):
+            if os.path.exists(cache):
+                break
+            time.sleep(0.1)
+    if os.path.exists(cache):
+        g = np.load(cache)
+        return dict(base, table=g["table"], mlp=g["mlp"])
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    sizes = net.enc.module.level_sizes
+    scales, ress = [], []
+    import ctypes
+    libm = ctypes.CDLL("libm.so.6")
+    for fn in (libm.log2f, libm.exp2f):
+        fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float]
+    lp = np.float32(libm.log2f(np.float32(net.enc.b)))
+    for l in range(4):
+        sc = np.float32(np.float32(libm.exp2f(np.float32(l) * lp)) * np.float32(r_min) - np.float32(1))
+        scales.append(float(sc)); ress.append(int(np.ceil(sc)) + 1)
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    table = torch.nn.Parameter(net.enc.module.params.detach().clone().to(dev))
+    fcs = [torch.nn.Linear(a, b).to(dev) for a, b in zip(net.num_nodes[:-1], net.num_nodes[1:])]
+    for fc, ref in zip(fcs, net.fc):
+        fc.load_state_dict(ref.state_dict())
+    U32 = 0xFFFFFFFF
+
+    def encode(x):
+        tab = table.view(-1, 2)
+        outs = []
+        for l in range(4):
+            pos = x * scales[l] + 0.5
+            cf = torch.floor(pos)
+            fr = pos - cf
+            c = cf.long() & U32
+            acc = 0
+            for corner in range(8):
+                w = 1
+                cc = []
+                for d in range(3):
+                    bit = (corner >> d) & 1
+                    w = w * (fr[:, d] if bit else 1 - fr[:, d])
+                    cc.append((c[:, d] + bit) & U32)
+                if ress[l] ** 3 <= sizes[l]:
+                    idx = (cc[0] + cc[1] * ress[l] + cc[2] * ress[l] * ress[l]) & U32
+                else:
+                    idx = cc[0] ^ ((cc[1] * 2654435761) & U32) ^ ((cc[2] * 805459861) & U32)
+                acc = acc + w.unsqueeze(-1) * tab[int(offs[l]) + idx % sizes[l]]
+            outs.append(acc)
+        return torch.cat(outs, -1)
+
+    def sdf_fn(x):
+        if shape == "sphere":
+            return 0.6 - x.norm(dim=-1)
+        q = (x[:, 0] ** 2 + x[:, 1] ** 2).sqrt() - 0.55
+        return 0.22 - (q ** 2 + x[:, 2] ** 2).sqrt()
+
+    opt = torch.optim.Adam([table] + [p for fc in fcs for p in fc.parameters()], lr=1e-2)
+    sched = torch.optim.lr_scheduler.CosineAnnealingLR(opt, steps)
+    gen = torch.Generator(device=dev).manual_seed(0)
+    for _ in range(steps):
+        x = torch.rand(batch, 3, device=dev, generator=gen) * 2 - 1
+        h = encode((x + 1) / 2)
+        for i, fc in enumerate(fcs):
+            h = fc(h)
+            if i != len(fcs) - 1:
+                h = torch.relu(h)
+        loss = (torch.tanh(h[:, 1] - h[:, 0]) - sdf_fn(x).clamp(-0.3, 0.3)).abs().mean()
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        sched.step()
+    mlp = np.concatenate([np.concatenate([fc.weight.detach().cpu().numpy().reshape(-1),
+                                          fc.bias.detach().cpu().numpy().reshape(-1)]) for fc in fcs]).astype(np.float32)
+    tab = table.detach().cpu().numpy().astype(np.float32)
+    tmp = cache + f".{os.getpid()}.tmp.npz"
+    np.savez(tmp, table=tab, mlp=mlp, loss=float(loss.detach()))
+    os.replace(tmp, cache)
+    return dict(base, table=tab, mlp=mlp)
 
 
 def make_native(w, pinned=None):

@@ -538,15 +538,15 @@ __global__ void k_bucket_insert(const int *__restrict__ cand, const int *__restr
     }
 }
 
-constexpr int kMaxPartners = 256;
+constexpr int kLocalPartners = 128;  // partner lists up to this size are sorted in registers/local memory
 
 // Partners of candidate a: candidates b with a larger vertex number that share an expanded
 // region with a and at least one plane (subpoly.py:484-535).  Each pair is found in exactly
-// one cell (the smallest common one).  Returns the count; partner vertex numbers go to
-// `list` (unsorted) when it is non-null.
+// one cell (the smallest common one).  Returns the count; when `list` is non-null the first
+// `cap` partner vertex numbers are stored there (unsorted).
 __device__ __forceinline__ int find_partners(int a, const int *__restrict__ cand, const uint64_t *__restrict__ sig,
                                              const unsigned long long *__restrict__ head, const int *__restrict__ next,
-                                             int dim, uint32_t stamp, uint64_t colmask, int *list)
+                                             int dim, uint32_t stamp, uint64_t colmask, int *list, int cap, int stride)
 {
     const int va = cand[a];
     const uint64_t pa = sig[3 * (int64_t)va], na = sig[3 * (int64_t)va + 1], ga = sig[3 * (int64_t)va + 2];
@@ -574,7 +574,7 @@ __device__ __forceinline__ int find_partners(int a, const int *__restrict__ cand
                         if (!grid_mask(ga, d) && !grid_mask(gb, d) && ba.hi[d] == bb.hi[d]) ++shared;
                     }
                     if (!ok || shared < 1) continue;
-                    if (list && count < kMaxPartners) list[count] = vb;
+                    if (list && count < cap) list[(int64_t)count * stride] = vb;
                     ++count;
                 }
             }
@@ -588,11 +588,8 @@ __global__ void __launch_bounds__(kThreads) k_pair_count(const int *__restrict__
                                                          uint64_t colmask, int *__restrict__ pcount)
 {
     const int n_cand = cnt[C_CAND];
-    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x) {
-        const int c = find_partners(a, cand, sig, head, next, dim, stamp, colmask, nullptr);
-        pcount[a] = c;
-        if (c > kMaxPartners) atomicOr(cnt + C_PARTNER_OVERFLOW, 1);
-    }
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x)
+        pcount[a] = find_partners(a, cand, sig, head, next, dim, stamp, colmask, nullptr, 0, 1);
 }
 
 struct ArrayCount {
@@ -614,18 +611,48 @@ __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x) {
         const int c = pcount[a];
         if (c == 0) continue;
-        int list[kMaxPartners];
-        find_partners(a, cand, sig, head, next, dim, stamp, colmask, list);
-        const int m = min(c, kMaxPartners);
-        for (int i = 1; i < m; ++i) {  // ascending partner number: unique(dim=0) order, subpoly.py:243-244
-            const int key = list[i];
-            int j = i - 1;
-            while (j >= 0 && list[j] > key) { list[j + 1] = list[j]; --j; }
-            list[j + 1] = key;
-        }
         const int va = cand[a];
         int2 *dst = edges_out + poff[a];
-        for (int i = 0; i < m; ++i) dst[i] = make_int2(va, list[i]);
+        // ascending partner number = the order unique(dim=0) leaves (subpoly.py:243-244)
+        if (c <= kLocalPartners) {
+            int list[kLocalPartners];
+            find_partners(a, cand, sig, head, next, dim, stamp, colmask, list, kLocalPartners, 1);
+            for (int i = 1; i < c; ++i) {
+                const int key = list[i];
+                int j = i - 1;
+                while (j >= 0 && list[j] > key) { list[j + 1] = list[j]; --j; }
+                list[j + 1] = key;
+            }
+            for (int i = 0; i < c; ++i) dst[i] = make_int2(va, list[i]);
+        } else {  // long list (degenerate, very large region): gather and sort in place in HBM
+            int *keys = &dst[0].y;  // stride 2 ints
+            find_partners(a, cand, sig, head, next, dim, stamp, colmask, keys, c, 2);
+            // heap sort on the strided keys
+            for (int start = c / 2 - 1; start >= 0; --start) {
+                int root = start;
+                for (;;) {
+                    int child = 2 * root + 1;
+                    if (child >= c) break;
+                    if (child + 1 < c && keys[2 * child] < keys[2 * (child + 1)]) ++child;
+                    if (keys[2 * root] >= keys[2 * child]) break;
+                    const int t = keys[2 * root]; keys[2 * root] = keys[2 * child]; keys[2 * child] = t;
+                    root = child;
+                }
+            }
+            for (int end = c - 1; end > 0; --end) {
+                const int t0 = keys[0]; keys[0] = keys[2 * end]; keys[2 * end] = t0;
+                int root = 0;
+                for (;;) {
+                    int child = 2 * root + 1;
+                    if (child >= end) break;
+                    if (child + 1 < end && keys[2 * child] < keys[2 * (child + 1)]) ++child;
+                    if (keys[2 * root] >= keys[2 * child]) break;
+                    const int t = keys[2 * root]; keys[2 * root] = keys[2 * child]; keys[2 * child] = t;
+                    root = child;
+                }
+            }
+            for (int i = 0; i < c; ++i) dst[i].x = va;
+        }
     }
 }
 
@@ -764,7 +791,6 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     }
     const int S = c->h_counters[C_SPLIT];
     if (S == 0) return TNB_OK;  // subpoly.py:110-111
-    if (c->h_counters[C_PARTNER_OVERFLOW]) { set_error("a vertex has more than 256 connecting partners"); return TNB_ERR_CAPACITY; }
     const int V0 = (int)c->V, E0 = (int)c->E;
     const int Hn = c->h_counters[C_HIT], P = c->h_counters[C_PAIRS];
     const int n_cand = Hn + S;

@@ -31,9 +31,10 @@ struct tnb_mesh {
 namespace tnb {
 
 constexpr int kThreads = 128;
-constexpr int kMaxRow = 32;   // vertices per face row
+constexpr int kMaxRow = 8192;      // hard limit of vertices per face row (sizes the HBM row scratch)
+constexpr int kSmemRowStride = 64;  // rows up to this length are built in shared memory (64 KB per CTA)
 constexpr int kMaxZeros = 5;  // 2^5 regions = one per lane
-enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_NUM = 16 };
+enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NUM = 16 };
 
 // ---- surface skeleton -----------------------------------------------------------------------------
 __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
@@ -152,16 +153,35 @@ __global__ void k_face_bucket_insert(int64_t V, const uint64_t *__restrict__ sig
 // One warp per surface vertex a; lane q builds the row of a's q-th adjacent region.
 // mode 0: rows_per_vertex[a] = number of distinct rows a leads (>= 3 vertices), max width.
 // mode 1: write those rows, lexicographically ranked, at row_off[a].
+// Row storage: `stride` 64-bit keys ((zero count << 32) | vertex) per lane, in dynamic shared
+// memory when `scratch` is null, else in HBM (one slice per thread).  A row longer than
+// `stride` raises F_ERR_ROW and the host retries with an HBM scratch of the measured width.
+__device__ __forceinline__ int row_compare(const unsigned long long *x, int nx, const unsigned long long *y, int ny)
+{
+    const int n = min(nx, ny);
+    for (int j = 0; j < n; ++j) {
+        const unsigned a = (unsigned)x[j], b = (unsigned)y[j];
+        if (a != b) return a < b ? -1 : 1;
+    }
+    return nx == ny ? 0 : (nx < ny ? -1 : 1);  // torch pads with -1, which sorts first
+}
+
 __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint64_t *__restrict__ sig,
                                                           const unsigned long long *__restrict__ head,
                                                           const int *__restrict__ next, int dim, uint32_t stamp,
-                                                          uint64_t colmask, int mode, int *__restrict__ rows_per_vertex,
+                                                          uint64_t colmask, int mode, int stride,
+                                                          unsigned long long *__restrict__ scratch,
+                                                          int *__restrict__ rows_per_vertex,
                                                           const int *__restrict__ row_off, int *__restrict__ rows,
                                                           int *__restrict__ row_cnt, int W, int *__restrict__ counters)
 {
-    __shared__ int s_rows[kThreads / 32][32][kMaxRow];
+    extern __shared__ unsigned long long s_rows[];  // [kThreads][stride] unless scratch is used
+    __shared__ int s_cnt[kThreads];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int(*my)[kMaxRow] = s_rows[warp];
+    unsigned long long *base = scratch ? scratch + ((size_t)blockIdx.x * kThreads + warp * 32) * stride
+                                       : s_rows + (size_t)warp * 32 * stride;
+    unsigned long long *mine = base + (size_t)lane * stride;
+    int *wcnt = s_cnt + warp * 32;
     for (int64_t a = (int64_t)blockIdx.x * (kThreads / 32) + warp; a < V; a += (int64_t)gridDim.x * (kThreads / 32)) {
         const uint64_t pa = sig[3 * a], na = sig[3 * a + 1], ga = sig[3 * a + 2];
         const uint64_t za = ~(pa | na) & colmask;
@@ -185,7 +205,6 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                 if ((lane >> t) & 1) pat |= m & (~m + 1);
             // collect the region's vertices ordered by (zero count, vertex number): the row
             // order r_idx_as_tensor builds from regions_to_vertices' group-by-zero-count output
-            unsigned long long keys[kMaxRow];
             const unsigned long long h = head[cell_of(cell[0], cell[1], cell[2], dim)];
             if ((uint32_t)(h >> 32) == stamp) {
                 for (int rec = (int)(uint32_t)h; rec >= 0; rec = next[rec]) {
@@ -198,43 +217,32 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                     for (int d = 0; d < 3; ++d) in = in && cell[d] >= bb.lo[d] && cell[d] <= bb.hi[d];
                     if (!in) continue;
                     const unsigned long long key = ((unsigned long long)zero_count(pb, nb, gb, colmask) << 32) | (unsigned)b;
-                    if (cnt < kMaxRow) {
+                    if (cnt < stride) {
                         int j = cnt - 1;
-                        while (j >= 0 && keys[j] > key) { keys[j + 1] = keys[j]; --j; }
-                        keys[j + 1] = key;
+                        while (j >= 0 && mine[j] > key) { mine[j + 1] = mine[j]; --j; }
+                        mine[j + 1] = key;
                     }
                     ++cnt;
                 }
             }
-            if (cnt > kMaxRow) { atomicOr(counters + F_ERR_ROW, 1); cnt = kMaxRow; }
-            lead = cnt >= 3 && (int)(uint32_t)keys[0] == (int)a;
-            for (int j = 0; j < kMaxRow; ++j) my[lane][j] = j < cnt ? (int)(uint32_t)keys[j] : -1;
+            if (cnt > stride) {
+                atomicOr(counters + F_ERR_ROW, 1);
+                atomicMax(counters + F_MAXCNT, cnt);
+                cnt = 0;
+            }
+            lead = cnt >= 3 && (int)(uint32_t)mine[0] == (int)a;
         }
+        wcnt[lane] = cnt;
         __syncwarp();
         const unsigned lead_mask = __ballot_sync(0xffffffffu, lead);
-        // rank among the rows this vertex leads: lexicographic, identical rows collapse
+        // identical rows collapse onto the lowest lane (torch.unique(dim=0), subpoly.py:620)
         bool keep = lead;
-        int rank = 0;
-        if (lead) {
-            for (unsigned mset = lead_mask & ~(1u << lane); mset; mset &= mset - 1) {
+        if (lead)
+            for (unsigned mset = lead_mask & ((1u << lane) - 1u); mset && keep; mset &= mset - 1) {
                 const int o = __ffs(mset) - 1;
-                int cmp = 0;
-                for (int j = 0; j < kMaxRow && cmp == 0; ++j) cmp = (my[o][j] > my[lane][j]) - (my[o][j] < my[lane][j]);
-                if (cmp == 0) { if (o < lane) keep = false; }
-                else if (cmp < 0) ++rank;
+                if (row_compare(base + (size_t)o * stride, wcnt[o], mine, cnt) == 0) keep = false;
             }
-        }
-        // rows equal to an earlier kept row must not be counted in anybody's rank
         const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
-        if (keep) {
-            rank = 0;
-            for (unsigned mset = keep_mask & ~(1u << lane); mset; mset &= mset - 1) {
-                const int o = __ffs(mset) - 1;
-                int cmp = 0;
-                for (int j = 0; j < kMaxRow && cmp == 0; ++j) cmp = (my[o][j] > my[lane][j]) - (my[o][j] < my[lane][j]);
-                if (cmp < 0) ++rank;
-            }
-        }
         if (mode == 0) {
             if (lane == 0) rows_per_vertex[a] = __popc(keep_mask);
             int wmax = keep ? cnt : 0;
@@ -242,8 +250,13 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
             for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
             if (lane == 0 && wmax) atomicMax(counters + F_WIDTH, wmax);
         } else if (keep) {
+            int rank = 0;  // lexicographic rank among the rows this vertex leads
+            for (unsigned mset = keep_mask & ~(1u << lane); mset; mset &= mset - 1) {
+                const int o = __ffs(mset) - 1;
+                if (row_compare(base + (size_t)o * stride, wcnt[o], mine, cnt) < 0) ++rank;
+            }
             const int64_t r = (int64_t)row_off[a] + rank;
-            for (int j = 0; j < W; ++j) rows[r * W + j] = my[lane][j];
+            for (int j = 0; j < W; ++j) rows[r * W + j] = j < cnt ? (int)(uint32_t)mine[j] : -1;
             row_cnt[r] = cnt;
         }
         __syncwarp();
@@ -260,28 +273,37 @@ struct OffsetEmit {
 };
 
 // Angular sort of every face row (geometry.py:483-516) around the normal at the face
-// centre (subpoly.py:627-642); rewrites the row in sorted order.
+// centre (subpoly.py:627-642); rewrites the row in sorted order.  Rows up to kSortLocal
+// vertices are sorted in registers/local memory; longer ones (duplicated chunk-boundary
+// geometry) in place in HBM with their scores in `score_scratch` [P][W].
+constexpr int kSortLocal = 32;
+
+__device__ __forceinline__ float angle_score(const float a[3], const float ua[3], const float u[3], const float nrm[3])
+{
+    const float d0 = a[1] * u[2] - a[2] * u[1], d1 = a[2] * u[0] - a[0] * u[2], d2 = a[0] * u[1] - a[1] * u[0];
+    const float un = fmaxf(__fsqrt_rn((u[0] * u[0] + u[1] * u[1]) + u[2] * u[2]), 1e-8f);
+    const float c = (ua[0] * __fdiv_rn(u[0], un) + ua[1] * __fdiv_rn(u[1], un)) + ua[2] * __fdiv_rn(u[2], un);
+    const float dn = (d0 * nrm[0] + d1 * nrm[1]) + d2 * nrm[2];
+    return c * (dn >= 0.0f ? 1.0f : -1.0f) + (dn < 0.0f ? 2.0f : 0.0f);
+}
+
 template <class C>
 __global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ NetMeta n, int64_t P, int W,
                                                         const float *__restrict__ vert, int *__restrict__ rows,
-                                                        const int *__restrict__ row_cnt, int *__restrict__ counters)
+                                                        const int *__restrict__ row_cnt, float *__restrict__ score_scratch,
+                                                        int *__restrict__ counters)
 {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
         const int cnt = row_cnt[p];
         int *row = rows + p * W;
-        int id[kMaxRow];
-        float px[kMaxRow], py[kMaxRow], pz[kMaxRow], sc[kMaxRow];
         float sx = 0.0f, sy = 0.0f, sz = 0.0f;
         bool origin = false;
         for (int j = 0; j < cnt; ++j) {
-            id[j] = row[j];
-            px[j] = vert[3 * (int64_t)id[j]];
-            py[j] = vert[3 * (int64_t)id[j] + 1];
-            pz[j] = vert[3 * (int64_t)id[j] + 2];
-            sx = sx + px[j];
-            sy = sy + py[j];
-            sz = sz + pz[j];
-            const float n2 = (px[j] * px[j] + py[j] * py[j]) + pz[j] * pz[j];
+            const float *q = vert + 3 * (int64_t)row[j];
+            sx = sx + q[0];
+            sy = sy + q[1];
+            sz = sz + q[2];
+            const float n2 = (q[0] * q[0] + q[1] * q[1]) + q[2] * q[2];
             if (!(__fsqrt_rn(n2) > 0.0f)) origin = true;
         }
         if (origin) atomicOr(counters + F_ERR_ORIGIN, 1);  // geometry.py:496 would drop this vertex
@@ -289,53 +311,158 @@ __global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ 
         float mean[3] = {__fdiv_rn(sx, k), __fdiv_rn(sy, k), __fdiv_rn(sz, k)};
         float nrm[3];
         sdf_grad<C>(n, mean, nrm, true);
-        const float a0 = px[0] - mean[0], a1 = py[0] - mean[1], a2 = pz[0] - mean[2];
-        const float an = fmaxf(__fsqrt_rn((a0 * a0 + a1 * a1) + a2 * a2), 1e-8f);
-        const float ua0 = __fdiv_rn(a0, an), ua1 = __fdiv_rn(a1, an), ua2 = __fdiv_rn(a2, an);
-        for (int j = 0; j < cnt; ++j) {
-            const float u0 = px[j] - mean[0], u1 = py[j] - mean[1], u2 = pz[j] - mean[2];
-            const float d0 = a1 * u2 - a2 * u1, d1 = a2 * u0 - a0 * u2, d2 = a0 * u1 - a1 * u0;
-            const float un = fmaxf(__fsqrt_rn((u0 * u0 + u1 * u1) + u2 * u2), 1e-8f);
-            const float c = (ua0 * __fdiv_rn(u0, un) + ua1 * __fdiv_rn(u1, un)) + ua2 * __fdiv_rn(u2, un);
-            const float dn = (d0 * nrm[0] + d1 * nrm[1]) + d2 * nrm[2];
-            sc[j] = c * (dn >= 0.0f ? 1.0f : -1.0f) + (dn < 0.0f ? 2.0f : 0.0f);
+        const float *q0 = vert + 3 * (int64_t)row[0];
+        const float a[3] = {q0[0] - mean[0], q0[1] - mean[1], q0[2] - mean[2]};
+        const float an = fmaxf(__fsqrt_rn((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]), 1e-8f);
+        const float ua[3] = {__fdiv_rn(a[0], an), __fdiv_rn(a[1], an), __fdiv_rn(a[2], an)};
+        if (cnt <= kSortLocal) {
+            int id[kSortLocal];
+            float sc[kSortLocal];
+            for (int j = 0; j < cnt; ++j) {
+                id[j] = row[j];
+                const float *q = vert + 3 * (int64_t)id[j];
+                const float u[3] = {q[0] - mean[0], q[1] - mean[1], q[2] - mean[2]};
+                sc[j] = angle_score(a, ua, u, nrm);
+            }
+            for (int i = 1; i < cnt; ++i) {  // stable, descending
+                const float ks = sc[i];
+                const int ki = id[i];
+                int j = i - 1;
+                while (j >= 0 && sc[j] < ks) { sc[j + 1] = sc[j]; id[j + 1] = id[j]; --j; }
+                sc[j + 1] = ks;
+                id[j + 1] = ki;
+            }
+            for (int j = 0; j < cnt; ++j) row[j] = id[j];
+        } else {
+            float *sc = score_scratch + p * W;
+            for (int j = 0; j < cnt; ++j) {
+                const float *q = vert + 3 * (int64_t)row[j];
+                const float u[3] = {q[0] - mean[0], q[1] - mean[1], q[2] - mean[2]};
+                sc[j] = angle_score(a, ua, u, nrm);
+            }
+            for (int i = 1; i < cnt; ++i) {
+                const float ks = sc[i];
+                const int ki = row[i];
+                int j = i - 1;
+                while (j >= 0 && sc[j] < ks) { sc[j + 1] = sc[j]; row[j + 1] = row[j]; --j; }
+                sc[j + 1] = ks;
+                row[j + 1] = ki;
+            }
         }
-        // stable descending insertion sort
-        for (int i = 1; i < cnt; ++i) {
-            const float ks = sc[i];
-            const int ki = id[i];
-            int j = i - 1;
-            while (j >= 0 && sc[j] < ks) { sc[j + 1] = sc[j]; id[j + 1] = id[j]; --j; }
-            sc[j + 1] = ks;
-            id[j + 1] = ki;
-        }
-        for (int j = 0; j < cnt; ++j) row[j] = id[j];
     }
 }
 
-__global__ void k_row_hist(const int *__restrict__ row_cnt, int64_t P, int *__restrict__ hist)
+// ---- fan triangulation ---------------------------------------------------------------------------
+// tensor_to_triangle_faces (subpoly.py:700-728) emits, for fan step i = 0,1,..., one triangle
+// (first, i+1-th, i+2-th) per row that has at least i+3 vertices: ordered by step, then by row.
+// Position of (row p, step i) = base[i] + #{rows before p with >= i+3 vertices}.  Three kernels
+// over a fixed grid give all steps at once (the reference loops over steps with boolean
+// masks):  per-block counts per step -> column scan -> warp-ballot ranks inside each block.
+constexpr int kFanThreads = 256;
+
+__device__ __forceinline__ void fan_slice(int64_t P, int64_t &begin, int64_t &end)
 {
-    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x)
-        atomicAdd(hist + row_cnt[p], 1);
+    int64_t per = (P + gridDim.x - 1) / gridDim.x;
+    per = (per + kFanThreads - 1) / kFanThreads * kFanThreads;
+    begin = min(per * blockIdx.x, P);
+    end = min(begin + per, P);
 }
 
-struct FanCount {
-    const int *row_cnt;
-    int need;
-    __device__ __forceinline__ int operator()(int64_t p) const { return row_cnt[p] >= need ? 1 : 0; }
-};
-struct FanEmit {  // fan step i: (first, i+1-th, i+2-th), subpoly.py:718-726
-    const int *rows;
-    int W, i;
-    int *tri;
-    __device__ __forceinline__ void operator()(int64_t p, int pos, int) const
-    {
-        const int *row = rows + p * W;
-        tri[3 * (int64_t)pos] = row[0];
-        tri[3 * (int64_t)pos + 1] = row[i + 1];
-        tri[3 * (int64_t)pos + 2] = row[i + 2];
+// G[b][i] = rows of block b with at least i+3 vertices (i < W-2)
+__global__ void __launch_bounds__(kFanThreads) k_fan_hist(const int *__restrict__ row_cnt, int64_t P, int W,
+                                                          int *__restrict__ G)
+{
+    extern __shared__ int s_hist[];  // [W+1]
+    for (int c = threadIdx.x; c <= W; c += kFanThreads) s_hist[c] = 0;
+    __syncthreads();
+    int64_t begin, end;
+    fan_slice(P, begin, end);
+    for (int64_t p = begin + threadIdx.x; p < end; p += kFanThreads) atomicAdd(s_hist + row_cnt[p], 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {  // suffix sums (W is small)
+        int run = 0;
+        for (int c = W; c >= 3; --c) {
+            run += s_hist[c];
+            G[(int64_t)blockIdx.x * W + (c - 3)] = run;
+        }
     }
-};
+}
+
+// off[b][i] = base[i] + sum_{b' < b} G[b'][i];  total triangle count -> *total
+__global__ void __launch_bounds__(1024) k_fan_scan(const int *__restrict__ G, int blocks, int W, int *__restrict__ off,
+                                                   int *__restrict__ total)
+{
+    __shared__ int s_col[kMaxRow + 1];
+    for (int i = threadIdx.x; i < W - 2; i += blockDim.x) {
+        int col = 0;
+        for (int b = 0; b < blocks; ++b) col += G[(int64_t)b * W + i];
+        s_col[i] = col;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int run = 0;
+        for (int j = 0; j < W - 2; ++j) { const int t = s_col[j]; s_col[j] = run; run += t; }
+        *total = run;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < W - 2; i += blockDim.x) {
+        int run = s_col[i];
+        for (int b = 0; b < blocks; ++b) {
+            off[(int64_t)b * W + i] = run;
+            run += G[(int64_t)b * W + i];
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kFanThreads) k_fan_write(const int *__restrict__ rows, const int *__restrict__ row_cnt,
+                                                           int64_t P, int W, const int *__restrict__ off,
+                                                           int *__restrict__ tri)
+{
+    extern __shared__ int s_run[];  // [W] triangles already emitted by this block per step
+    __shared__ int s_w[kFanThreads / 32];
+    __shared__ int s_max;
+    for (int c = threadIdx.x; c < W; c += kFanThreads) s_run[c] = 0;
+    __syncthreads();
+    int64_t begin, end;
+    fan_slice(P, begin, end);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int *boff = off + (int64_t)blockIdx.x * W;
+    for (int64_t tile = begin; tile < end; tile += kFanThreads) {
+        const int64_t p = tile + threadIdx.x;
+        const int c = p < end ? row_cnt[p] : 0;
+        int mx = c;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, d));
+        if (threadIdx.x == 0) s_max = 0;
+        __syncthreads();
+        if (lane == 0) atomicMax(&s_max, mx);
+        __syncthreads();
+        const int tile_max = s_max;
+        const int *row = rows + p * W;
+        for (int i = 0; i + 3 <= tile_max; ++i) {
+            const bool pred = c >= i + 3;
+            const unsigned ball = __ballot_sync(0xffffffffu, pred);
+            if (lane == 0) s_w[warp] = __popc(ball);
+            __syncthreads();
+            int woff = 0, ttot = 0;
+#pragma unroll
+            for (int w = 0; w < kFanThreads / 32; ++w) {
+                const int t = s_w[w];
+                if (w < warp) woff += t;
+                ttot += t;
+            }
+            if (pred) {
+                const int64_t pos = (int64_t)boff[i] + s_run[i] + woff + __popc(ball & ((1u << lane) - 1u));
+                tri[3 * pos] = row[0];
+                tri[3 * pos + 1] = row[i + 1];
+                tri[3 * pos + 2] = row[i + 2];
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_run[i] += ttot;
+        }
+        __syncthreads();
+    }
+}
 
 static int read_small(const int *d, int *h, int n, cudaStream_t s)
 {
@@ -361,8 +488,8 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
     TNB_CUDA(used.reserve((size_t)V));
     TNB_CUDA(remap.reserve((size_t)V));
     TNB_CUDA(block_sums.reserve(kScanMaxBlocks));
-    TNB_CUDA(counters.reserve(F_NUM + kMaxRow + 2));
-    TNB_CUDA(cudaMemsetAsync(counters.p, 0, (F_NUM + kMaxRow + 2) * sizeof(int), s));
+    TNB_CUDA(counters.reserve(F_NUM));
+    TNB_CUDA(cudaMemsetAsync(counters.p, 0, F_NUM * sizeof(int), s));
     TNB_CUDA(cudaMemsetAsync(used.p, 0, (size_t)V * sizeof(int), s));
 
     // ---- extract_skeleton ----
@@ -420,16 +547,38 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
     TNB_LAUNCH_CHECK();
     k_face_bucket_insert<<<grid_for(Vs, 256), 256, 0, s>>>(Vs, sig.p, head.p, next.p, dim, stamp);
     TNB_LAUNCH_CHECK();
-    const unsigned gw = grid_for(Vs, kThreads / 32);
-    prof_begin(TNB_PROF_FACE_ROWS, s);
-    k_region_rows<<<gw, kThreads, 0, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 0, rows_per_vertex.p, nullptr,
-                                         nullptr, nullptr, 0, counters.p);
-    TNB_LAUNCH_CHECK();
-    prof_end(TNB_PROF_FACE_ROWS, s, Vs);
-    if ((rc = compact(Vs, ArrayCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
-    if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
-    if (h[F_ERR_ZEROS]) { set_error("a surface vertex lies on more than 5 planes: more than 32 adjacent regions"); return TNB_ERR_UNSUPPORTED; }
-    if (h[F_ERR_ROW]) { set_error("a face has more than 32 vertices"); return TNB_ERR_UNSUPPORTED; }
+    unsigned gw = grid_for(Vs, kThreads / 32);
+    int stride = kSmemRowStride;
+    DevBuf<unsigned long long> scratch;
+    size_t rows_smem = (size_t)kThreads * stride * sizeof(unsigned long long);
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            TNB_CUDA(cudaFuncSetAttribute(k_region_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
+            attr_set = true;
+        }
+    }
+    for (int attempt = 0;; ++attempt) {
+        prof_begin(TNB_PROF_FACE_ROWS, s);
+        k_region_rows<<<gw, kThreads, scratch.p ? 0 : rows_smem, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 0, stride,
+                                                                       scratch.p, rows_per_vertex.p, nullptr, nullptr, nullptr, 0,
+                                                                       counters.p);
+        TNB_LAUNCH_CHECK();
+        prof_end(TNB_PROF_FACE_ROWS, s, Vs);
+        if ((rc = compact(Vs, ArrayCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
+        if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
+        if (h[F_ERR_ZEROS]) { set_error("a surface vertex lies on more than 5 planes: more than 32 adjacent regions"); return TNB_ERR_UNSUPPORTED; }
+        if (!h[F_ERR_ROW]) break;
+        // a face row did not fit: retry with rows in HBM, sized to the longest row seen
+        if (attempt > 0 || h[F_MAXCNT] > kMaxRow) {
+            set_error("a face has more than " + std::to_string(kMaxRow) + " vertices (" + std::to_string(h[F_MAXCNT]) + ")");
+            return TNB_ERR_UNSUPPORTED;
+        }
+        stride = kMaxRow;
+        gw = std::min<unsigned>(gw, kSMs * 2);
+        TNB_CUDA(scratch.reserve((size_t)gw * kThreads * stride));
+        TNB_CUDA(cudaMemsetAsync(counters.p + F_ROWS, 0, (F_NUM - F_ROWS) * sizeof(int), s));
+    }
     const int64_t P = h[F_ROWS];
     const int W = h[F_WIDTH];
     m->P = P;
@@ -437,39 +586,40 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
     if (P == 0) return TNB_OK;
     TNB_CUDA(m->poly.reserve((size_t)P * W));
     TNB_CUDA(m->pcnt.reserve((size_t)P));
-    k_region_rows<<<gw, kThreads, 0, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 1, rows_per_vertex.p, row_off.p,
-                                         m->poly.p, m->pcnt.p, W, counters.p);
+    k_region_rows<<<gw, kThreads, scratch.p ? 0 : rows_smem, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 1, stride, scratch.p,
+                                                                   rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p);
     TNB_LAUNCH_CHECK();
     {
         unsigned g = grid_for(P, kThreads);
-        if (net->fixed_cfg) k_sort_rows<CfgRef><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, counters.p);
-        else k_sort_rows<CfgAny><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, counters.p);
+        DevBuf<float> score_scratch;
+        if (W > kSortLocal) TNB_CUDA(score_scratch.reserve((size_t)P * W));
+        if (net->fixed_cfg) k_sort_rows<CfgRef><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p);
+        else k_sort_rows<CfgAny><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p);
         TNB_LAUNCH_CHECK();
     }
     // fan triangles, ordered by fan step then by row
-    int *hist = counters.p + F_NUM;
-    k_row_hist<<<grid_for(P, 256), 256, 0, s>>>(m->pcnt.p, P, hist);
-    TNB_LAUNCH_CHECK();
-    int hh[F_NUM + kMaxRow + 2];
-    if ((rc = read_small(counters.p, hh, F_NUM + kMaxRow + 2, s))) return rc;
-    if (hh[F_ERR_ORIGIN]) {
+    if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
+    if (h[F_ERR_ORIGIN]) {
         set_error("a face vertex sits exactly at the origin (geometry.py:496 treats it as padding): unsupported");
         return TNB_ERR_UNSUPPORTED;
     }
-    std::vector<int64_t> base(W, 0);
-    int64_t T = 0;
-    for (int i = 0; i + 3 <= W; ++i) {
-        int64_t ni = 0;
-        for (int cc = i + 3; cc <= W; ++cc) ni += hh[F_NUM + cc];
-        base[i] = T;
-        T += ni;
-    }
-    m->T = T;
-    TNB_CUDA(m->tri.reserve((size_t)std::max<int64_t>(T, 1) * 3));
-    for (int i = 0; i + 3 <= W; ++i) {
-        if ((rc = compact(P, FanCount{m->pcnt.p, i + 3}, FanEmit{m->poly.p, W, i, m->tri.p + 3 * base[i]}, block_sums.p,
-                          counters.p + F_VERTS, s)))
-            return rc;
+    if (W >= 3) {
+        const int fblocks = (int)std::min<int64_t>((P + kFanThreads - 1) / kFanThreads, kSMs * 4);
+        DevBuf<int> G, off;
+        TNB_CUDA(G.reserve((size_t)fblocks * W));
+        TNB_CUDA(off.reserve((size_t)fblocks * W));
+        k_fan_hist<<<fblocks, kFanThreads, (W + 1) * sizeof(int), s>>>(m->pcnt.p, P, W, G.p);
+        TNB_LAUNCH_CHECK();
+        k_fan_scan<<<1, 1024, 0, s>>>(G.p, fblocks, W, off.p, counters.p + F_VERTS);
+        TNB_LAUNCH_CHECK();
+        if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
+        const int64_t T = h[F_VERTS];
+        m->T = T;
+        TNB_CUDA(m->tri.reserve((size_t)std::max<int64_t>(T, 1) * 3));
+        if (T > 0) {
+            k_fan_write<<<fblocks, kFanThreads, W * sizeof(int), s>>>(m->poly.p, m->pcnt.p, P, W, off.p, m->tri.p);
+            TNB_LAUNCH_CHECK();
+        }
     }
     return TNB_OK;  // locals are released in stream order
 }
