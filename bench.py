@@ -389,6 +389,30 @@ def run_ours(args):
                 "note": "the fused trilinear kernels are fp32-issue bound, not HBM bound: see DESIGN.md",
                 "by_kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
 
+    # ---- evaluation-sweep throughput (BASELINE configs[4]), outside the timed region -----
+    sweep = None
+    if not args.no_sweep:
+        n3 = args.sweep_n
+        buf = torch.empty((n3 ** 3, 2), dtype=torch.int64, device="cuda")
+        for _ in range(2):
+            net.sweep_signs((-1, -1, -1), (1, 1, 1), (n3, n3, n3), out=buf)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        torch.cuda.synchronize()
+        a.record()
+        for _ in range(reps):
+            net.sweep_signs((-1, -1, -1), (1, 1, 1), (n3, n3, n3), out=buf)
+        b.record()
+        torch.cuda.synchronize()
+        ms_sw = a.elapsed_time(b) / reps
+        pts = n3 ** 3
+        sweep = {"lattice": f"{n3}^3", "points_per_s": pts / (ms_sw * 1e-3), "ms": ms_sw,
+                 "algorithmic_bytes_per_point": 16, "achieved_gbs": pts * 16 / (ms_sw * 1e-3) / 1e9,
+                 "hbm_frac": pts * 16 / (ms_sw * 1e-3) / 1e9 / peak,
+                 "approx_fp32_tflops": pts * 2 * (4 * 8 * 5 + 8 * 16 + 16 * 16 + 16 * 2) / (ms_sw * 1e-3) / 1e12,
+                 "note": "output larger than L2 (16 B/point); the kernel is fp32-issue bound"}
+        del buf
+
     # ---- CPU baseline (bounded sample on the box's host cores) ----------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -405,7 +429,7 @@ def run_ours(args):
            "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": 1e3 * float(t.item()) / args.steps},
-           "roofline": roofline, "cpu_baseline": cpu}
+           "roofline": roofline, "cpu_baseline": cpu, "eval_sweep": sweep}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -419,6 +443,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="small_sphere")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the evaluation-sweep throughput leg")
+    ap.add_argument("--sweep-n", type=int, default=512, help="lattice size per axis of the evaluation sweep")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -125,14 +125,16 @@ constexpr int kMaxSegs = 3 * 512;
 
 // |tanh(sdf)| and |grad| of every marks-grid vertex of one chunk; per-chunk max |grad|
 template <class C>
-__global__ void __launch_bounds__(kThreads) k_sweep_chunk(const __grid_constant__ NetMeta n, int M, int sx, int sy,
+__global__ void __launch_bounds__(kThreads, 4) k_sweep_chunk(const __grid_constant__ NetMeta n, int M, int sx, int sy,
                                                           int sz, int nx, int ny, int nz,
                                                           float *__restrict__ dist, unsigned *__restrict__ max_grad)
 {
     const int64_t count = (int64_t)nx * ny * nz;
     float local = 0.0f;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
-        const int k = (int)(t % nz), j = (int)((t / nz) % ny), i = (int)(t / ((int64_t)nz * ny));
+        // x is the lane axis: the hash table is x-fastest, so a warp's gathers touch
+        // consecutive entries (the |sdf| store is the only strided access)
+        const int i = (int)(t % nx), j = (int)((t / nx) % ny), k = (int)(t / ((int64_t)nx * ny));
         const int gi = sx + i, gj = sy + j, gk = sz + k;
         // preprocess_inverse(marks[...]) (tropical.py:186, model.py:81-82)
         float x[3] = {n.marks[gi] * n.pre_2s - n.pre_scale, n.marks[gj] * n.pre_2s - n.pre_scale,

@@ -84,6 +84,105 @@ __device__ __forceinline__ void forward(const NetMeta &n, const float xp[3],
     }
 }
 
+// Forward pass that keeps only what the backward pass needs: the ReLU masks as bits
+// (mask[i] bit j = pre-activation j of hidden layer i is > 0) instead of the rows.
+template <class C>
+__device__ __forceinline__ void forward_masks(const NetMeta &n, const float xp[3], uint64_t mask[C::kMaxLin],
+                                              float o[2])
+{
+    float act[C::kMaxW];
+#pragma unroll(C::kUnroll)
+    for (int l = 0; l < C::kMaxL; ++l) {
+        if (l < C::L(n)) {
+            uint32_t cell[3];
+            float frac[3];
+            float2 f = encode_level(n, l, xp, cell, frac);
+            act[2 * l] = f.x;
+            act[2 * l + 1] = f.y;
+        }
+    }
+    int base = 0;
+#pragma unroll(C::kUnroll)
+    for (int i = 0; i < C::kMaxLin; ++i) {
+        if (i < C::NLIN(n)) {
+            const int ni = C::nin(n, i), no = C::nout(n, i);
+            const bool last = i == C::NLIN(n) - 1;
+            float nxt[C::kMaxH];
+#pragma unroll(C::kUnroll)
+            for (int j = 0; j < C::kMaxH; ++j) {
+                if (j < no) {
+                    float acc = C::w(n, base + no * ni + j);
+#pragma unroll(C::kUnroll)
+                    for (int c = 0; c < C::kMaxW; ++c)
+                        if (c < ni) acc = __fmaf_rn(act[c], C::w(n, base + j * ni + c), acc);
+                    nxt[j] = acc;
+                }
+            }
+            if (last) {
+                o[0] = nxt[0];
+                o[1] = nxt[1];
+            } else {
+                uint64_t mk = 0;
+#pragma unroll(C::kUnroll)
+                for (int j = 0; j < C::kMaxH; ++j)
+                    if (j < no) {
+                        const bool on = nxt[j] > 0.0f;
+                        mk |= (uint64_t)on << j;
+                        act[j] = on ? nxt[j] : 0.0f;
+                    }
+                mask[i] = mk;
+            }
+            base += no * ni + no;
+        }
+    }
+}
+
+// d(level features)/d xp for all three axes from ONE fetch of the cell's 8 corners
+// (tiny-cuda-nn kernel_grid_backward_input: for axis d, sum over the 4 corner pairs that
+// differ in d of scale * prod(other weights) * (right - left)).  Accumulates
+// g0 * d f0 + g1 * d f1 into acc[d] in the oracle's order.
+__device__ __forceinline__ void encode_level_grad(const NetMeta &n, int l, const float xp[3], float g0, float g1,
+                                                  float acc[3])
+{
+    const LevelMeta lv = n.lvl[l];
+    uint32_t cell[3];
+    float frac[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float pos = __fmaf_rn(lv.scale, xp[d], 0.5f);
+        float fl = floorf(pos);
+        cell[d] = (uint32_t)(int)fl;
+        frac[d] = pos - fl;
+    }
+    const float2 *tab = n.table + lv.off;
+    float2 v[8];
+#pragma unroll
+    for (int corner = 0; corner < 8; ++corner)
+        v[corner] = __ldg(tab + grid_index(lv.size, lv.res, cell[0] + (corner & 1), cell[1] + ((corner >> 1) & 1),
+                                           cell[2] + ((corner >> 2) & 1)));
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        float2 dl = make_float2(0.0f, 0.0f);
+#pragma unroll
+        for (int idx = 0; idx < 4; ++idx) {
+            float w = lv.scale;
+            int corner = 0;
+#pragma unroll
+            for (int nd = 0; nd < 2; ++nd) {
+                const int dim = nd >= d ? nd + 1 : nd;
+                const int bit = (idx >> nd) & 1;
+                w = w * (bit ? frac[dim] : 1.0f - frac[dim]);
+                corner |= bit << dim;
+            }
+            const float2 vl = v[corner], vr = v[corner | (1 << d)];
+            dl.x = __fmaf_rn(w, vr.x - vl.x, dl.x);
+            dl.y = __fmaf_rn(w, vr.y - vl.y, dl.y);
+        }
+        acc[d] = __fmaf_rn(g0, dl.x, acc[d]);
+        acc[d] = __fmaf_rn(g1, dl.y, acc[d]);
+    }
+}
+
 // tanh(o1-o0) and its gradient w.r.t. the world-space input.
 template <class C>
 __device__ __forceinline__ float sdf_grad(const NetMeta &n, const float x[3], float grad[3],
@@ -91,9 +190,9 @@ __device__ __forceinline__ float sdf_grad(const NetMeta &n, const float x[3], fl
 {
     float xp[3];
     preprocess(n, x, xp);
-    float pre[(C::kMaxLin - 1) * C::kMaxH];
+    uint64_t mask[C::kMaxLin];
     float o[2];
-    forward<C>(n, xp, pre, o);
+    forward_masks<C>(n, xp, mask, o);
     const float t = det_tanhf(o[1] - o[0]);
     if (!want_grad) return t;
     const float gs = 1.0f - t * t;
@@ -125,32 +224,14 @@ __device__ __forceinline__ float sdf_grad(const NetMeta &n, const float x[3], fl
             if (k > 0) {
 #pragma unroll(C::kUnroll)
                 for (int c = 0; c < C::kMaxH; ++c)
-                    if (c < ni) g_out[c] = pre[(k - 1) * C::kMaxH + c] > 0.0f ? g_in[c] : 0.0f;
+                    if (c < ni) g_out[c] = ((mask[k - 1] >> c) & 1) ? g_in[c] : 0.0f;
             }
         }
     }
     float acc[3] = {0.0f, 0.0f, 0.0f};
 #pragma unroll(C::kUnroll)
-    for (int l = 0; l < C::kMaxL; ++l) {
-        if (l < C::L(n)) {
-            uint32_t cell[3];
-            float frac[3];
-            const LevelMeta lv = n.lvl[l];
-#pragma unroll(C::kUnroll)
-            for (int d = 0; d < 3; ++d) {
-                float pos = __fmaf_rn(lv.scale, xp[d], 0.5f);
-                float fl = floorf(pos);
-                cell[d] = (uint32_t)(int)fl;
-                frac[d] = pos - fl;
-            }
-#pragma unroll(C::kUnroll)
-            for (int d = 0; d < 3; ++d) {
-                float2 dl = encode_level_dx(n, l, d, cell, frac);
-                acc[d] = __fmaf_rn(g_in[2 * l], dl.x, acc[d]);
-                acc[d] = __fmaf_rn(g_in[2 * l + 1], dl.y, acc[d]);
-            }
-        }
-    }
+    for (int l = 0; l < C::kMaxL; ++l)
+        if (l < C::L(n)) encode_level_grad(n, l, xp, g_in[2 * l], g_in[2 * l + 1], acc);
 #pragma unroll(C::kUnroll)
     for (int d = 0; d < 3; ++d) grad[d] = __fdiv_rn(acc[d], n.pre_2s);
     return t;

@@ -172,16 +172,17 @@ __global__ void __launch_bounds__(kThreads) k_region(const __grid_constant__ Net
 
 // Dense lattice sweep: evaluate + bit-pack, nothing but 16 B per point leaves the SM.
 template <class C>
-__global__ void __launch_bounds__(kThreads) k_sweep_signs(const __grid_constant__ NetMeta n, float3 lo,
+__global__ void __launch_bounds__(kThreads, 4) k_sweep_signs(const __grid_constant__ NetMeta n, float3 lo,
                                                           float3 step, int nx, int ny, int nz,
                                                           float eps, ulonglong2 *__restrict__ packed)
 {
     const int64_t count = (int64_t)nx * ny * nz;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
          i += (int64_t)gridDim.x * blockDim.x) {
-        int iz = (int)(i % nz);
-        int iy = (int)((i / nz) % ny);
-        int ix = (int)(i / ((int64_t)nz * ny));
+        // x is the lane axis (table is x-fastest); the output index stays z-fastest
+        int ix = (int)(i % nx);
+        int iy = (int)((i / nx) % ny);
+        int iz = (int)(i / ((int64_t)nx * ny));
         float p[3] = {__fmaf_rn((float)ix, step.x, lo.x), __fmaf_rn((float)iy, step.y, lo.y),
                       __fmaf_rn((float)iz, step.z, lo.z)};
         float xp[3];
@@ -207,7 +208,7 @@ __global__ void __launch_bounds__(kThreads) k_sweep_signs(const __grid_constant_
         if (!(fabsf(v) <= eps)) {
             if (v > 0.0f) pos |= 1ull << ((NL - 1) * H); else neg |= 1ull << ((NL - 1) * H);
         }
-        packed[i] = make_ulonglong2(pos, neg);
+        packed[((int64_t)ix * ny + iy) * nz + iz] = make_ulonglong2(pos, neg);
     }
 }
 
