@@ -206,6 +206,8 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
             // collect the region's vertices ordered by (zero count, vertex number): the row
             // order r_idx_as_tensor builds from regions_to_vertices' group-by-zero-count output
             const unsigned long long h = head[cell_of(cell[0], cell[1], cell[2], dim)];
+            const unsigned long long my_key = ((unsigned long long)ka << 32) | (unsigned)a;
+            bool led_by_other = false;
             if ((uint32_t)(h >> 32) == stamp) {
                 for (int rec = (int)(uint32_t)h; rec >= 0; rec = next[rec]) {
                     const int b = rec >> 3;
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                     for (int d = 0; d < 3; ++d) in = in && cell[d] >= bb.lo[d] && cell[d] <= bb.hi[d];
                     if (!in) continue;
                     const unsigned long long key = ((unsigned long long)zero_count(pb, nb, gb, colmask) << 32) | (unsigned)b;
+                    if (key < my_key) { led_by_other = true; break; }  // that vertex emits this row, not a
                     if (cnt < stride) {
                         int j = cnt - 1;
                         while (j >= 0 && mine[j] > key) { mine[j + 1] = mine[j]; --j; }
@@ -225,12 +228,13 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                     ++cnt;
                 }
             }
+            if (led_by_other) cnt = 0;
             if (cnt > stride) {
                 atomicOr(counters + F_ERR_ROW, 1);
                 atomicMax(counters + F_MAXCNT, cnt);
                 cnt = 0;
             }
-            lead = cnt >= 3 && (int)(uint32_t)mine[0] == (int)a;
+            lead = cnt >= 3;  // every surviving row starts with a itself
         }
         wcnt[lane] = cnt;
         __syncwarp();
@@ -574,8 +578,8 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
             set_error("a face has more than " + std::to_string(kMaxRow) + " vertices (" + std::to_string(h[F_MAXCNT]) + ")");
             return TNB_ERR_UNSUPPORTED;
         }
-        stride = kMaxRow;
-        gw = std::min<unsigned>(gw, kSMs * 2);
+        stride = (h[F_MAXCNT] + 7) / 8 * 8;  // exactly the longest row: the retry cannot overflow
+        gw = std::min<unsigned>(gw, kSMs * 4);
         TNB_CUDA(scratch.reserve((size_t)gw * kThreads * stride));
         TNB_CUDA(cudaMemsetAsync(counters.p + F_ROWS, 0, (F_NUM - F_ROWS) * sizeof(int), s));
     }
