@@ -93,9 +93,9 @@ int tnb_net_region(const tnb_net *net, const float *d_x, const float *d_outputs,
                    void *stream);
 
 /* Evaluation sweep over a dense lattice (BASELINE config "batched trilinear network
- * eval + sign-vector sweep"): points lo + (hi-lo)*i/(n-1) per axis, z fastest;
- * writes the packed sign vector of every lattice point, d_packed [nx*ny*nz, 2] uint64
- * {positive bits, negative bits} (zero = neither). */
+ * eval + sign-vector sweep"): points lo + (hi-lo)*i/(n-1) per axis; writes the packed
+ * sign vector of every lattice point, d_packed [nz][ny][nx][2] uint64 {positive bits,
+ * negative bits} (zero = neither) -- x is the fastest index, like the hash table. */
 int tnb_sweep_signs(const tnb_net *net, const float lo[3], const float hi[3], const int32_t n[3],
                     float eps, uint64_t *d_packed, void *stream);
 

@@ -158,7 +158,9 @@ def test_sweep_signs_matches_region():
     ax = [np.float32(l) + np.arange(k, dtype=np.float32) * (np.float32(h - l) / np.float32(k - 1))
           for l, h, k in zip(lo, hi, n)]
     # lattice points as the kernel forms them: fma(i, step, lo)
-    pts = np.stack(np.meshgrid(*[np.arange(k) for k in n], indexing="ij"), -1).reshape(-1, 3)
+    # output order: x fastest, then y, then z
+    zyx = np.stack(np.meshgrid(*[np.arange(k) for k in n[::-1]], indexing="ij"), -1).reshape(-1, 3)
+    pts = zyx[:, ::-1]
     step = [np.float32(h - l) / np.float32(k - 1) for l, h, k in zip(lo, hi, n)]
     x = np.stack([(pts[:, d].astype(np.float64) * np.float64(step[d]) + np.float64(lo[d])).astype(np.float32)
                   for d in range(3)], -1)

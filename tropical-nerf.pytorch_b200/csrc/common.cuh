@@ -20,9 +20,17 @@ constexpr int kMaxHidden = TNB_MAX_HIDDEN;
 constexpr int kMlpParamMax = 1024;  // floats kept in kernel-parameter (constant bank) space
 constexpr int kSMs = 148;           // B200
 
+// mode: how the 8 corner indices of a cell are formed (all three give exactly
+// tiny-cuda-nn's grid_index() result; the first two avoid its per-corner multiplies and
+// the runtime modulo):
+//   0  dense level   index = cx + cy*res + cz*res^2  (wraps only for out-of-grid points)
+//   1  hashed level with a power-of-two table: (cx ^ cy*P1 ^ cz*P2) & (size-1)
+//   2  anything else: the generic routine
+enum { kLevelDense = 0, kLevelHashPow2 = 1, kLevelGeneric = 2 };
 struct LevelMeta {
     float scale;
     uint32_t res, size, off;
+    uint32_t mode, res2;
 };
 
 // Passed BY VALUE to kernels (__grid_constant__): lives in the constant bank, so the
@@ -30,6 +38,8 @@ struct LevelMeta {
 struct NetMeta {
     int L, H, NLIN, R;
     float pre_scale, pre_2s, eps;
+    float pre_inv;   // 1 / pre_2s
+    int pre_pow2;    // pre_2s is a power of two: multiplying by pre_inv IS the IEEE division
     int n_marks;
     int mlp_in_param;  // 1 when mlp_c holds the weights
     LevelMeta lvl[kMaxLevels];
@@ -116,10 +126,42 @@ __device__ __forceinline__ uint32_t grid_index(uint32_t size, uint32_t res, uint
     return index % size;
 }
 
+// x / pre_2s, bit-identical to the IEEE division (exact scaling when pre_2s is a power of two)
+__device__ __forceinline__ float div_2s(const NetMeta &n, float v)
+{
+    return n.pre_pow2 ? v * n.pre_inv : __fdiv_rn(v, n.pre_2s);
+}
+
 __device__ __forceinline__ void preprocess(const NetMeta &n, const float x[3], float xp[3])
 {
 #pragma unroll
-    for (int d = 0; d < 3; ++d) xp[d] = __fdiv_rn(x[d] + n.pre_scale, n.pre_2s);
+    for (int d = 0; d < 3; ++d) xp[d] = div_2s(n, x[d] + n.pre_scale);
+}
+
+// the 8 corner indices of cell (cx,cy,cz): corner bit d set = +1 along axis d
+__device__ __forceinline__ void corner_indices(const LevelMeta &lv, uint32_t cx, uint32_t cy, uint32_t cz,
+                                               uint32_t idx[8])
+{
+    if (lv.mode == kLevelDense) {
+        const uint32_t base = cx + cy * lv.res + cz * lv.res2;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            uint32_t i = base + (c & 1) + ((c >> 1) & 1) * lv.res + ((c >> 2) & 1) * lv.res2;
+            if (i >= lv.size) i %= lv.size;  // only for points outside the grid
+            idx[c] = i;
+        }
+    } else if (lv.mode == kLevelHashPow2) {
+        const uint32_t hx[2] = {cx, cx + 1u};
+        const uint32_t hy[2] = {cy * 2654435761u, (cy + 1u) * 2654435761u};
+        const uint32_t hz[2] = {cz * 805459861u, (cz + 1u) * 805459861u};
+        const uint32_t mask = lv.size - 1u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) idx[c] = (hx[c & 1] ^ hy[(c >> 1) & 1] ^ hz[(c >> 2) & 1]) & mask;
+    } else {
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            idx[c] = grid_index(lv.size, lv.res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1));
+    }
 }
 
 // Level l of the hash encoding at xp.  Returns the two features; optionally the cell
@@ -137,12 +179,10 @@ __device__ __forceinline__ float2 encode_level(const NetMeta &n, int l, const fl
     }
     const float2 *tab = n.table + lv.off;
     float2 v[8];
+    uint32_t idx[8];
+    corner_indices(lv, cell[0], cell[1], cell[2], idx);
 #pragma unroll
-    for (int corner = 0; corner < 8; ++corner) {
-        uint32_t idx = grid_index(lv.size, lv.res, cell[0] + (corner & 1), cell[1] + ((corner >> 1) & 1),
-                                  cell[2] + ((corner >> 2) & 1));
-        v[corner] = __ldg(tab + idx);
-    }
+    for (int corner = 0; corner < 8; ++corner) v[corner] = __ldg(tab + idx[corner]);
     float2 acc = make_float2(0.0f, 0.0f);
 #pragma unroll
     for (int corner = 0; corner < 8; ++corner) {

@@ -156,10 +156,10 @@ __device__ __forceinline__ void encode_level_grad(const NetMeta &n, int l, const
     }
     const float2 *tab = n.table + lv.off;
     float2 v[8];
+    uint32_t cidx[8];
+    corner_indices(lv, cell[0], cell[1], cell[2], cidx);
 #pragma unroll
-    for (int corner = 0; corner < 8; ++corner)
-        v[corner] = __ldg(tab + grid_index(lv.size, lv.res, cell[0] + (corner & 1), cell[1] + ((corner >> 1) & 1),
-                                           cell[2] + ((corner >> 2) & 1)));
+    for (int corner = 0; corner < 8; ++corner) v[corner] = __ldg(tab + cidx[corner]);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
         float2 dl = make_float2(0.0f, 0.0f);
@@ -233,7 +233,7 @@ __device__ __forceinline__ float sdf_grad(const NetMeta &n, const float x[3], fl
     for (int l = 0; l < C::kMaxL; ++l)
         if (l < C::L(n)) encode_level_grad(n, l, xp, g_in[2 * l], g_in[2 * l + 1], acc);
 #pragma unroll(C::kUnroll)
-    for (int d = 0; d < 3; ++d) grad[d] = __fdiv_rn(acc[d], n.pre_2s);
+    for (int d = 0; d < 3; ++d) grad[d] = div_2s(n, acc[d]);
     return t;
 }
 

@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_signs(const __grid_consta
         if (!(fabsf(v) <= eps)) {
             if (v > 0.0f) pos |= 1ull << ((NL - 1) * H); else neg |= 1ull << ((NL - 1) * H);
         }
-        packed[((int64_t)ix * ny + iy) * nz + iz] = make_ulonglong2(pos, neg);
+        packed[i] = make_ulonglong2(pos, neg);  // x fastest: coalesced 16 B stores
     }
 }
 
@@ -305,6 +305,12 @@ int tnb_net_create(const tnb_net_desc *d, tnb_net **out)
     memset(&m, 0, sizeof(m));
     m.L = d->n_levels; m.H = d->num_hidden; m.NLIN = d->num_layers; m.R = R;
     m.pre_scale = d->scale; m.pre_2s = d->scale * 2.0f; m.eps = d->eps; m.n_marks = d->n_marks;
+    {
+        int ex = 0;
+        const float mant = std::frexp(m.pre_2s, &ex);
+        m.pre_pow2 = (mant == 0.5f && ex > -100 && ex < 100) ? 1 : 0;
+        m.pre_inv = 1.0f / m.pre_2s;
+    }
     // level layout exactly as tiny-cuda-nn's GridEncoding constructor derives it
     const float log2_pls = std::log2((float)d->per_level_scale);
     uint64_t total = 0;
@@ -316,7 +322,12 @@ int tnb_net_create(const tnb_net_desc *d, tnb_net **out)
         n = (n + 7u) / 8u * 8u;
         uint32_t cap = 1u << d->log2_hashmap;
         if (n > cap) n = cap;
-        m.lvl[l] = LevelMeta{scale, res, n, (uint32_t)total};
+        // which index path reproduces grid_index() for this level (common.cuh)
+        const uint64_t r1 = res, r2 = r1 * r1, r3 = r2 * r1;
+        uint32_t mode = kLevelGeneric;
+        if (r1 <= n && r2 <= n && r3 <= n && r3 < (1ull << 32)) mode = kLevelDense;
+        else if ((n & (n - 1u)) == 0u) mode = kLevelHashPow2;
+        m.lvl[l] = LevelMeta{scale, res, n, (uint32_t)total, mode, (uint32_t)(r2 & 0xFFFFFFFFull)};
         net->h_scale.push_back(scale); net->h_res.push_back(res); net->h_size.push_back(n);
         net->h_off.push_back((uint32_t)total);
         total += n;
