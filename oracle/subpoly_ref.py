@@ -1,14 +1,18 @@
 """oracle/subpoly_ref.py -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
 
-numpy restatement of the reference's polyhedral-complex mesh extraction for the
-planar (`force=True`, the reference default) path, on top of the C network
-evaluation in `trinet_ref.c`.  Only tests/, `__graft_entry__.smoke()` and
+numpy restatement of the reference's polyhedral-complex mesh extraction -- the planar
+(`force=True`, the reference default) path and the curve-approximation (`force=False`) path --
+on top of the C network evaluation in `trinet_ref.c`.  Only tests/, `__graft_entry__.smoke()` and
 bench.py's cpu_baseline / `--impl reference` legs may import this module.
 
 Reference functions restated (file:line under /root/reference/tropical):
   skeleton()            tropical.py:158-225  (distance pruning mode, :188-197, :113-138)
   subpoly()             subpoly.py:23-86
-  subpoly_()            subpoly.py:90-279    (force=True branch)
+  subpoly_()            subpoly.py:90-279    (both branches; the gradient-descent repair of
+                        subpoly_debug.py:121-165 is NOT restated: it raises if it would be needed,
+                        which the reference's own runs never do)
+  strict_check          subpoly_debug.py:234-271
+  corner_points / intersection_of_two_planes   geometry.py:350-372, :24-138 (C: curve_intersection)
   check_edges_with_new_vertices (failover)   subpoly_debug.py:33-51
   regions_to_vertices   subpoly.py:281-340
   r_idx_as_tensor       subpoly.py:342-370
@@ -160,8 +164,21 @@ def edge_vertices(m, offset):
 # --------------------------------------------------------------------------------------
 # one hyperplane
 # --------------------------------------------------------------------------------------
-def subpoly_step(P, vertices, edges, outputs, l, h, eps, pruning=True):
-    """subpoly.py:90-279 with force=True.  Returns (vertices, edges, outputs)."""
+def corner_points(e):
+    """geometry.py:350-372: the 8 corners of the box an edge spans, index 4*iz + 2*iy + ix
+    (coordinate taken from endpoint 0 or 1 per axis).  e: [E,2,3] -> [E,8,3]."""
+    out = np.empty((e.shape[0], 8, 3), F32)
+    for i in range(2):
+        for j in range(2):
+            for k in range(2):
+                out[:, 4 * i + 2 * j + k, 0] = e[:, k, 0]
+                out[:, 4 * i + 2 * j + k, 1] = e[:, j, 1]
+                out[:, 4 * i + 2 * j + k, 2] = e[:, i, 2]
+    return out
+
+
+def subpoly_step(P, vertices, edges, outputs, l, h, eps, pruning=True, force=True):
+    """subpoly.py:90-279.  Returns (vertices, edges, outputs)."""
     eps32 = F32(eps)
     H = P.num_hidden
     idx = l * H + h
@@ -176,6 +193,30 @@ def subpoly_step(P, vertices, edges, outputs, l, h, eps, pruning=True):
     w = np.abs(d[:, :1]) / np.abs(d[:, 1:] - d[:, :1])
     regions, offs, _ = P.region(vertices, outputs)
     v_new = e[:, 0] * (F32(1) - w) + e[:, 1] * w
+    have_c = False
+    if not force:
+        # bi-/tri-linear corrections for edges that are not axis aligned (subpoly.py:120-183)
+        from .trinet import curve_intersections
+        c = ((np.abs(e[:, 1, :] - e[:, 0, :]) > eps32).sum(-1)) > 1
+        ec = e[c]
+        have_c = ec.shape[0] > 0
+        if have_c:
+            dd = P.outputs_group8(corner_points(ec))           # [Ec,8,R]
+            rg = regions[edges][m][c][:, :, 3:]
+            r_edges = (rg[:, 0] == 0) & (rg[:, 1] == 0)
+            sub = r_edges[:, :idx]
+            if not sub.any(1).all():
+                raise RuntimeError("an edge lies on no earlier plane (the reference exits here, subpoly.py:140-148)")
+            plane = idx - 1 - np.argmax(sub[:, ::-1], 1)       # nonzero_last
+            rows = np.arange(ec.shape[0])
+            ints = curve_intersections(dd[rows, :, plane], dd[:, :, idx])
+            xg = ec[:, 0] * (F32(1) - ints) + ec[:, 1] * ints
+            og = P.outputs(xg)
+            d_new = np.stack([og[rows, plane], og[:, idx]], -1)
+            gg = ((ints < 0) | (ints > 1)).sum(-1) > 0
+            if (~gg & ((np.abs(d_new) > eps32).sum(-1) > 0)).any():
+                raise NotImplementedError("gradient-descent repair (subpoly_debug.py:121-165) is not restated")
+            v_new[c] = ec[:, 0] + ints * (ec[:, 1] - ec[:, 0])
     m_rgn_all, offset, outputs_new = P.region(v_new)
     m_idx = 3 + idx
 
@@ -190,6 +231,17 @@ def subpoly_step(P, vertices, edges, outputs, l, h, eps, pruning=True):
         outputs_new = outputs_new.copy()
         outputs_new[b] = 0
         m_rgn_all, offset, outputs_new = P.region(v_new, outputs_new)
+    if not force:
+        # strict_check (subpoly_debug.py:234-271): drop new vertices that are not on the plane,
+        # and every non-axis-aligned edge without an admissible intersection stays unsplit
+        chk = outputs_new[:, idx]
+        if have_c or np.abs(chk).max() >= eps32:
+            g = np.abs(chk) < eps32
+            if have_c:
+                g[c] = (np.abs(chk[c]) < eps32) & ~gg
+            m = m.copy()
+            m[m] = g
+            v_new, m_rgn_all, offset, outputs_new = v_new[g], m_rgn_all[g], offset[g], outputs_new[g]
     m_rgn, m_rgn_f = m_rgn_all[:, :m_idx], m_rgn_all[:, m_idx:]
 
     V0 = vertices.shape[0]
@@ -351,8 +403,8 @@ def canonical_polygons(polygons):
 # --------------------------------------------------------------------------------------
 # driver
 # --------------------------------------------------------------------------------------
-def subpoly(P, size=1.2, eps=1e-4, unit=128, return_intermediate=False):
-    """subpoly.py:23-86 (force=True).  Returns (faces, vertices, faces_with_indices);
+def subpoly(P, size=1.2, eps=1e-4, unit=128, return_intermediate=False, force=True):
+    """subpoly.py:23-86.  Returns (faces, vertices, faces_with_indices);
     with return_intermediate also a dict of the pre-extraction complex."""
     vertices, edges = skeleton(P, unit)
     if edges.shape[0] == 0:
@@ -361,9 +413,9 @@ def subpoly(P, size=1.2, eps=1e-4, unit=128, return_intermediate=False):
     H = P.num_hidden
     for l in range(P.num_layers - 1):
         for h in range(H):
-            vertices, edges, outputs = subpoly_step(P, vertices, edges, outputs, l, h, eps)
+            vertices, edges, outputs = subpoly_step(P, vertices, edges, outputs, l, h, eps, force=force)
     vertices, edges, outputs = subpoly_step(P, vertices, edges, outputs,
-                                            P.num_layers - 2, H, eps)
+                                            P.num_layers - 2, H, eps, force=force)
     inter = dict(vertices=vertices, edges=edges, outputs=outputs)
     s_vertices, s_edges, v_idx = extract_skeleton(P, vertices, edges, outputs, eps)
     if v_idx is None:

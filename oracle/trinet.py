@@ -196,3 +196,24 @@ class NetParams:
                             ctypes.c_int64(x.shape[0]), ctypes.c_void_p(m.ctypes.data),
                             ctypes.c_void_p(off.ctypes.data))
         return m, off, outputs
+
+    # ---- curve-approximation path ------------------------------------------------------
+    def outputs_group8(self, corners, eps=None):
+        """Net.forward(gather=True, group=8) rows for [G,8,3] corner points -> [G,8,R]."""
+        x = np.ascontiguousarray(corners, np.float32).reshape(-1, 8, 3)
+        out = np.empty((x.shape[0], 8, self.n_outputs), np.float32)
+        lib().trinet_outputs_group8(ctypes.byref(self._c), ctypes.c_void_p(x.ctypes.data),
+                                    ctypes.c_int64(x.shape[0]),
+                                    ctypes.c_float(np.float32(self.eps if eps is None else eps)),
+                                    ctypes.c_void_p(out.ctypes.data))
+        return out
+
+
+def curve_intersections(p, q):
+    """geometry.intersection_of_two_planes for [E,8] corner values -> [E,3]."""
+    p = np.ascontiguousarray(p, np.float32).reshape(-1, 8)
+    q = np.ascontiguousarray(q, np.float32).reshape(-1, 8)
+    out = np.empty((p.shape[0], 3), np.float32)
+    lib().curve_intersections(ctypes.c_void_p(p.ctypes.data), ctypes.c_void_p(q.ctypes.data),
+                              ctypes.c_int64(p.shape[0]), ctypes.c_void_p(out.ctypes.data))
+    return out

@@ -13,6 +13,9 @@
  *   - TropicalHashGrid.region         tropical/tropical.py:227-236
  *   - the x-gradient autograd takes in TropicalHashGrid.skeleton
  *     (tropical/tropical.py:190-195) and Net.normal (model.py:105-123)
+ *   - Net.forward(gather=True, group=8) (model.py:65-70) and
+ *     geometry.intersection_of_two_planes / batched_polynomial_roots
+ *     (geometry.py:24-138, :259-299) for the curve-approximation path
  *   - TropicalHashGrid.forward -> tcnn.Encoding (tropical/tropical.py:32-47).
  *     tiny-cuda-nn is a third-party dependency that is NOT in the reference
  *     tree and NOT pinned by its requirements.txt; the multiresolution hash
@@ -309,4 +312,146 @@ void trinet_region(const trinet_t *n, const float *marks, int32_t n_marks, float
         for (int c = 0; c < R; ++c)
             s[3 + c] = fabsf(o[c]) <= eps ? 0 : (o[c] > 0.0f ? 1 : -1);
     }
+}
+
+/* ---- curve-approximation path (force=False) ---------------------------------------- */
+/* Net.forward(x, gather=True, group=8) (model.py:65-70): x holds groups of 8 corner points;
+ * inside a group every hidden neuron is kept (linear) iff it is > eps at the first OR the last
+ * corner, else multiplied by 0 -- "infer within a common linear space".  out: [groups*8][R]. */
+void trinet_outputs_group8(const trinet_t *n, const float *x, int64_t groups, float eps, float *out)
+{
+    const int R = trinet_n_outputs(n), H = n->n_hidden;
+    for (int64_t g = 0; g < groups; ++g) {
+        float act[8][TN_MAX_WIDTH], pre[8][TN_MAX_WIDTH];
+        for (int k = 0; k < 8; ++k) {
+            float xp[3];
+            preprocess(n, x + 3 * (8 * g + k), xp);
+            encode(n, xp, act[k], 0);
+        }
+        const float *p = n->mlp;
+        for (int i = 0; i < n->n_linear; ++i) {
+            const int nin = layer_in(n, i), nout = layer_out(n, i);
+            const float *W = p, *b = p + (size_t)nout * nin;
+            for (int k = 0; k < 8; ++k)
+                for (int j = 0; j < nout; ++j) {
+                    float acc = b[j];
+                    for (int c = 0; c < nin; ++c) acc = fmaf(act[k][c], W[j * nin + c], acc);
+                    pre[k][j] = acc;
+                }
+            if (i != n->n_linear - 1) {
+                for (int k = 0; k < 8; ++k)
+                    for (int j = 0; j < H; ++j) out[(size_t)R * (8 * g + k) + i * H + j] = pre[k][j];
+                for (int j = 0; j < nout; ++j) {
+                    const float m = (pre[0][j] > eps || pre[7][j] > eps) ? 1.0f : 0.0f;
+                    for (int k = 0; k < 8; ++k) act[k][j] = pre[k][j] * m;
+                }
+            } else {
+                for (int k = 0; k < 8; ++k) out[(size_t)R * (8 * g + k) + R - 1] = pre[k][1] - pre[k][0];
+            }
+            p = b + nout;
+        }
+    }
+}
+
+/* Smallest real root in [0,1] of c[0] t^deg + ... + c[deg] (deg <= 4), or -1.
+ * The reference takes the eigenvalues of the companion matrix (geometry.py:271-299) and keeps
+ * the LAST admissible one in LAPACK's order, which for these matrices is the smallest root
+ * (checked empirically, tests/test_oracle_vs_reference.py).  Defined here as: scan 1024 equal
+ * sub-intervals of [0,1] left to right in double precision, take the first sign change (or
+ * exact zero) and bisect it 60 times. */
+static double poly_eval(const double *c, int deg, double t)
+{
+    double v = c[0];
+    for (int i = 1; i <= deg; ++i) v = v * t + c[i];
+    return v;
+}
+static double smallest_root01(const double *c, int deg)
+{
+    const int N = 1024;
+    double t0 = 0.0, f0 = poly_eval(c, deg, 0.0);
+    if (f0 == 0.0) return 0.0;
+    for (int k = 1; k <= N; ++k) {
+        const double t1 = (double)k / (double)N, f1 = poly_eval(c, deg, t1);
+        if (f1 == 0.0) return t1;
+        if ((f0 < 0.0) != (f1 < 0.0)) {
+            double lo = t0, hi = t1, flo = f0;
+            for (int it = 0; it < 60; ++it) {
+                const double mid = 0.5 * (lo + hi), fm = poly_eval(c, deg, mid);
+                if (fm == 0.0) return mid;
+                if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else hi = mid;
+            }
+            return 0.5 * (lo + hi);
+        }
+        t0 = t1;
+        f0 = f1;
+    }
+    return -1.0;
+}
+
+/* geometry.intersection_of_two_planes for ONE edge: p, q = the two planes' values at the 8
+ * corners (index 4*iz + 2*iy + ix).  out = (x, y, z) trilinear coordinates, -1 where the
+ * reference leaves "no root".  Planar (bilinear) configurations return (-1,-1,-1) exactly as
+ * the reference does with its failover switched off (geometry.py:90-108). */
+void curve_intersection(const float *p, const float *q, float *out)
+{
+    static const int T_[3][4] = {{0, 1, 4, 5}, {0, 1, 2, 3}, {0, 4, 2, 6}};
+    static const int U_[3][4] = {{2, 3, 6, 7}, {4, 5, 6, 7}, {1, 5, 3, 7}};
+    for (int pl = 0; pl < 3; ++pl) {
+        int same = 1;
+        for (int k = 0; k < 4; ++k)
+            same = same && p[T_[pl][k]] == p[U_[pl][k]] && q[T_[pl][k]] == q[U_[pl][k]];
+        if (same) { out[0] = out[1] = out[2] = -1.0f; return; }
+    }
+    static const int r[4] = {0, 1, 4, 5}, s[4] = {2, 3, 6, 7};
+    /* z(v) = [v0, v1+v2, v3] in float32 like the reference, then everything in double */
+    double a[3], b[3], c[3], d[3];
+    a[0] = q[r[0]]; a[1] = (float)(q[r[1]] + q[r[2]]); a[2] = q[r[3]];   /* z(q[:, r]) */
+    b[0] = p[s[0]]; b[1] = (float)(p[s[1]] + p[s[2]]); b[2] = p[s[3]];   /* z(p[:, s]) */
+    c[0] = q[s[0]]; c[1] = (float)(q[s[1]] + q[s[2]]); c[2] = q[s[3]];   /* z(q[:, s]) */
+    d[0] = p[r[0]]; d[1] = (float)(p[r[1]] + p[r[2]]); d[2] = p[r[3]];   /* z(p[:, r]) */
+    double A[3][3], B[3][3], TA[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) A[i][j] = a[i] * b[j] - c[i] * d[j];
+    static const double T[3][3] = {{1, -2, 1}, {-1, 1, 0}, {1, 0, 0}};
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double v = 0.0;
+            for (int k = 0; k < 3; ++k) v += T[k][i] * A[k][j];   /* T^T A */
+            TA[i][j] = v;
+        }
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) {
+            double v = 0.0;
+            for (int k = 0; k < 3; ++k) v += TA[i][k] * T[k][j];  /* (T^T A) T */
+            B[i][j] = v;
+        }
+    double co[5] = {B[0][0], B[1][0] + B[0][1], B[2][0] + B[1][1] + B[0][2], B[1][2] + B[2][1], B[2][2]};
+    float x = -1.0f;
+    {
+        float cf[5];
+        for (int i = 0; i < 5; ++i) { cf[i] = (float)co[i]; if (fabsf(cf[i]) < 1e-9f) { cf[i] = 0.0f; co[i] = 0.0; } }
+        int lead = 0;
+        while (lead < 4 && !(fabsf(cf[lead]) > 1e-9f)) ++lead;   /* first coefficient that counts */
+        if (lead < 4) {
+            float mean = 0.0f;
+            for (int i = lead; i < 5; ++i) mean += fabsf(cf[i]);
+            mean /= (float)(5 - lead);
+            if (mean > 1e-9f) {
+                const double rt = smallest_root01(co + lead, 4 - lead);
+                if (rt >= 0.0) x = (float)rt;
+            }
+        }
+    }
+    /* quad_y (geometry.py:61-67), float32, left-to-right sums */
+    const float w0 = (1.0f - x) * (1.0f - x), w1 = x * (1.0f - x), w3 = x * x;
+    const float AX = ((q[r[0]] * w0 + q[r[1]] * w1) + q[r[2]] * w1) + q[r[3]] * w3;
+    const float BX = ((q[s[0]] * w0 + q[s[1]] * w1) + q[s[2]] * w1) + q[s[3]] * w3;
+    out[0] = x;
+    out[1] = AX / (AX - BX);
+    out[2] = x;
+}
+
+void curve_intersections(const float *p, const float *q, int64_t count, float *out)
+{
+    for (int64_t i = 0; i < count; ++i) curve_intersection(p + 8 * i, q + 8 * i, out + 3 * i);
 }

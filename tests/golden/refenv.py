@@ -39,6 +39,19 @@ def import_reference():
     return tropical, sp, Net
 
 
+def release_reference():
+    """Undo import_reference(): the product mirror is also called `tropical`."""
+    for name in [k for k in sys.modules if k == "tropical" or k.startswith("tropical.")]:
+        del sys.modules[name]
+    for p in (_STUBS, REFERENCE_ROOT):
+        while p in sys.path:
+            sys.path.remove(p)
+    for name in ("tinycudann", "matplotlib", "matplotlib.pyplot", "deprecation", "trimesh", "cubvh", "mcubes"):
+        mod = sys.modules.get(name)
+        if mod is not None and _STUBS in (getattr(mod, "__file__", "") or ""):
+            del sys.modules[name]
+
+
 def sphere_sdf(x, r=0.6):
     """Analytic SDF, inside positive (the reference's convention, dataset.py:94)."""
     return r - x.norm(dim=-1)

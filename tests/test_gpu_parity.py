@@ -172,3 +172,49 @@ def test_sweep_signs_matches_region():
         pos |= (s[:, c] == 1).astype(np.uint64) << np.uint64(c)
         neg |= (s[:, c] == -1).astype(np.uint64) << np.uint64(c)
     assert np.array_equal(packed[:, 0], pos) and np.array_equal(packed[:, 1], neg)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_curve_path_every_step_bit_exact(case):
+    """force=False (curve approximation): device == oracle at every hyperplane."""
+    from oracle import subpoly_ref as R
+    g = load_golden(case)
+    P = oracle_net(g)
+    N = native_net(P)
+    c = N.skeleton(128)
+    vo, eo = R.skeleton(P)
+    oo = P.outputs(vo)
+    H = P.num_hidden
+    for (l, h) in [(l, h) for l in range(P.num_layers - 1) for h in range(H)] + [(P.num_layers - 2, H)]:
+        c.step(l, h, force=False)
+        vo, eo, oo = R.subpoly_step(P, vo, eo, oo, l, h, 1e-4, force=False)
+        assert (c.num_vertices, c.num_edges) == (vo.shape[0], eo.shape[0]), (l, h)
+        v, e, o = c.read()
+        assert np.array_equal(e.cpu().numpy(), eo), (l, h)
+        assert np.array_equal(v.cpu().numpy(), vo), (l, h)
+        assert np.array_equal(o.cpu().numpy(), oo), (l, h)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_curve_path_mesh_matches_reference(case):
+    """force=False whole path: identical to the oracle; against the reference's mesh the
+    tolerances of BASELINE.json (max nearest-vertex error 1e-5, Chamfer 1e-6).  The float32
+    eigenvalue root finder of the reference decides near-degenerate in-plane edges by rounding
+    noise, so the complex away from the surface may differ in a handful of vertices."""
+    from scipy.spatial import cKDTree
+    from oracle import subpoly_ref as R
+    g = load_golden(case)
+    gc = dict(np.load(__import__("os").path.join(__import__("helpers").GOLDEN, f"{case}_curve.npz")))
+    P = oracle_net(g)
+    N = native_net(P)
+    mesh = N.subpoly(force=False)
+    v, e, t, f, p = [a.cpu().numpy() for a in mesh.read()]
+    faces, vo, tri = R.subpoly(P, force=False)
+    assert np.array_equal(v, vo) and np.array_equal(t, tri) and np.array_equal(f, faces)
+    ref_v = gc["surface_vertices"]
+    d1, _ = cKDTree(ref_v).query(v)
+    d2, _ = cKDTree(v).query(ref_v)
+    assert d1.max() <= 1e-5 and d2.max() <= 1e-5
+    assert (d1.mean() + d2.mean()) / 2 <= 1e-6
+    assert v.shape[0] == ref_v.shape[0]
+    assert 0 <= gc["triangles"].shape[0] - t.shape[0] <= 4  # duplicated reference faces, see test_whole_path_mesh

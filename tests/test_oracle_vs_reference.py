@@ -13,6 +13,12 @@ import refenv  # noqa: E402
 pytestmark = pytest.mark.skipif(not refenv.available(), reason="reference tree not present")
 
 
+@pytest.fixture(scope="module", autouse=True)
+def _leave_no_reference_modules_behind():
+    yield
+    refenv.release_reference()
+
+
 @pytest.fixture(scope="module")
 def ref():
     import torch

@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "complex.cuh"
+#include "curve.cuh"
 #include "net_eval.cuh"
 #include "scan.cuh"
 
@@ -21,7 +22,10 @@ namespace tnb {
 double g_capacity_factor = 4.0;
 constexpr int kThreads = 128;
 // device counters: [0, C_V) are cleared at the start of every step, C_V / C_E hold the complex size
-enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_PARTNER_OVERFLOW, C_TMP, C_V = 8, C_E = 9, C_NUM = 16 };
+//   C_RAW = edges the plane crosses, C_SPLIT = edges actually split (== C_RAW on the planar path,
+//   fewer after strict_check on the curve path)
+enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_NUM = 16 };
+enum { kErrNoPlane = 1, kErrGradientDescent = 2 };
 
 // ---- allocation ---------------------------------------------------------------------------
 int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
@@ -424,11 +428,12 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant
                                                            uint64_t *__restrict__ bmask, int *__restrict__ cnt)
 {
     const int R = n.R;
-    const int S = cnt[C_SPLIT], V = cnt[C_V], E = cnt[C_E];
+    const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
     if ((int64_t)V + S > Vcap || (int64_t)E + S > Ecap) {  // host grows the arrays and re-runs
         if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_OVERFLOW] = 1;
         return;
     }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_SPLIT] = S;  // planar path: every crossed edge is split
     int any = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
         const int e = split_list[k];
@@ -483,6 +488,159 @@ __global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant
     }
 }
 
+
+// ---- curve-approximation path (force=False, subpoly.py:120-183 + strict_check) ----------------------
+// Pass 1: candidate new vertex of every crossed edge into TEMP slots (the idle half of the
+// ping-pong vertex arrays), no rewiring yet.  sflag bit0 = edge is not axis aligned (c),
+// bit1 = no admissible intersection (gg).
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_new_vertices_curve(const __grid_constant__ NetMeta n, int idx, float eps,
+                                                                 int Vcap, int Ecap, const int *__restrict__ split_list,
+                                                                 const int2 *__restrict__ edges,
+                                                                 const float *__restrict__ vert, const float *__restrict__ out,
+                                                                 const uint64_t *__restrict__ sig, float *__restrict__ tvert,
+                                                                 float *__restrict__ tout, uint64_t *__restrict__ bmask,
+                                                                 int *__restrict__ sflag, int *__restrict__ cnt)
+{
+    const int R = n.R;
+    const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
+    if ((int64_t)V + S > Vcap || (int64_t)E + S > Ecap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_OVERFLOW] = 1;
+        return;
+    }
+    int any = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
+        const int e = split_list[k];
+        const int2 ed = edges[e];
+        float e0[3], e1[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { e0[d] = vert[3 * (int64_t)ed.x + d]; e1[d] = vert[3 * (int64_t)ed.y + d]; }
+        const float d0 = __fdiv_rn(out[(int64_t)ed.x * R + idx], eps), d1 = __fdiv_rn(out[(int64_t)ed.y * R + idx], eps);
+        const float w = __fdiv_rn(fabsf(d0), fabsf(d1 - d0));
+        const float omw = 1.0f - w;
+        float x[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) x[d] = e0[d] * omw + e1[d] * w;
+        const uint64_t za = ~(sig[3 * (int64_t)ed.x] | sig[3 * (int64_t)ed.x + 1]);
+        const uint64_t zb = ~(sig[3 * (int64_t)ed.y] | sig[3 * (int64_t)ed.y + 1]);
+        const uint64_t common = za & zb & ((1ull << idx) - 1ull);
+        int flags = 0;
+        int moved = 0;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) moved += fabsf(e1[d] - e0[d]) > eps ? 1 : 0;
+        if (moved > 1) {  // bi-/tri-linear edge (subpoly.py:122)
+            flags = 1;
+            if (!common) {
+                atomicOr(cnt + C_ERR, kErrNoPlane);  // the reference exits here (subpoly.py:140-148)
+            } else {
+                const int plane = 63 - __clzll((long long)common);  // nonzero_last
+                float p8[8], q8[8], ints[3];
+                group8_columns<C>(n, e0, e1, n.eps, plane, idx, p8, q8);
+                curve_intersection(p8, q8, ints);
+                bool gg = false;
+#pragma unroll
+                for (int d = 0; d < 3; ++d) gg = gg || ints[d] < 0.0f || ints[d] > 1.0f;
+                if (gg) {
+                    flags |= 2;
+                } else {
+                    float xg[3];
+#pragma unroll
+                    for (int d = 0; d < 3; ++d) xg[d] = e0[d] * (1.0f - ints[d]) + e1[d] * ints[d];
+                    float *row = tout + (int64_t)k * R;
+                    outputs_row<C>(n, xg, row);
+                    if (fabsf(row[plane]) > eps || fabsf(row[idx]) > eps)
+                        atomicOr(cnt + C_ERR, kErrGradientDescent);  // subpoly_debug.py:121-165 not built
+                }
+#pragma unroll
+                for (int d = 0; d < 3; ++d) x[d] = e0[d] + ints[d] * (e1[d] - e0[d]);  // subpoly.py:183
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 3; ++d) tvert[3 * (int64_t)k + d] = x[d];
+        float *row = tout + (int64_t)k * R;
+        outputs_row<C>(n, x, row);
+        const uint64_t bm = common | (1ull << idx);
+        bmask[k] = bm;
+        sflag[k] = flags;
+        for (uint64_t m = bm; m; m &= m - 1) {
+            const int col = __ffsll((long long)m) - 1;
+            if (fabsf(row[col]) > eps) any = 1;
+        }
+    }
+    if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
+}
+
+// Pass 2: failover override on the temp rows, then strict_check's keep decision
+// (subpoly_debug.py:234-271): on the plane within eps, and not a curved edge without a root.
+__global__ void __launch_bounds__(kThreads) k_strict_keep(int R, int idx, float eps, float *__restrict__ tout,
+                                                          const uint64_t *__restrict__ bmask, int *__restrict__ sflag,
+                                                          const int *__restrict__ cnt)
+{
+    if (cnt[C_OVERFLOW]) return;
+    const int flag = cnt[C_FLAG], S = cnt[C_RAW];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
+        float *row = tout + (int64_t)k * R;
+        if (flag)
+            for (uint64_t m = bmask[k]; m; m &= m - 1) row[__ffsll((long long)m) - 1] = 0.0f;
+        const int f = sflag[k];
+        const bool keep = fabsf(row[idx]) < eps && !((f & 1) && (f & 2));
+        sflag[k] = keep ? 1 : 0;
+    }
+}
+
+struct KeepFlagCount {
+    const int *flag;
+    const int *overflow;
+    __device__ __forceinline__ int operator()(int64_t k) const { return (*overflow == 0 && flag[k]) ? 1 : 0; }
+};
+// Pass 3: surviving new vertices move to their final slots, edges are rewired (subpoly.py:210-215)
+struct CurveCommitEmit {
+    NetMeta const *meta;  // device copy not needed: fields below
+    const int *split_list;
+    int2 *edges;
+    const float *tvert, *tout;
+    float *vert, *out;
+    uint64_t *sig;
+    const float *marks;
+    const int *cnt;
+    int R, n_marks;
+    float eps, pre_scale, pre_2s, pre_inv;
+    int pre_pow2;
+    __device__ __forceinline__ void operator()(int64_t k, int rank, int) const
+    {
+        const int V = cnt[C_V], E = cnt[C_E];
+        const int64_t nv = (int64_t)V + rank;
+        float x[3], xp[3];
+        for (int d = 0; d < 3; ++d) {
+            x[d] = tvert[3 * k + d];
+            vert[3 * nv + d] = x[d];
+            const float t = x[d] + pre_scale;
+            xp[d] = pre_pow2 ? t * pre_inv : __fdiv_rn(t, pre_2s);
+        }
+        float *row = out + nv * R;
+        uint64_t pos = 0, neg = 0;
+        for (int c = 0; c < R; ++c) {
+            const float v = tout[k * R + c];
+            row[c] = v;
+            if (!(fabsf(v) <= eps)) { if (v > 0.0f) pos |= 1ull << c; else neg |= 1ull << c; }
+        }
+        uint64_t g = 0;
+        for (int d = 0; d < 3; ++d) {
+            int off = lower_bound(marks, n_marks, xp[d] + eps) - 1;
+            const float mk = marks[off < 0 ? off + n_marks : off];
+            g |= (uint64_t)(uint32_t)(off + 1) << (20 * d);
+            g |= (fabsf(mk - xp[d]) > eps ? 1ull : 0ull) << (60 + d);
+        }
+        sig[3 * nv] = pos;
+        sig[3 * nv + 1] = neg;
+        sig[3 * nv + 2] = g;
+        const int e = split_list[k];
+        const int old = edges[e].y;
+        edges[e].y = (int)nv;
+        edges[E + rank] = make_int2(old, (int)nv);
+    }
+};
+
 struct HitCount {
     const float *out;
     int R, idx;
@@ -497,7 +655,7 @@ __global__ void k_fill_new_cands(int *__restrict__ cand, int *__restrict__ cnt)
     const int H = cnt[C_HIT], S = cnt[C_SPLIT], V = cnt[C_V];
     if (cnt[C_OVERFLOW]) return;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) cand[H + k] = V + k;
-    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_CAND] = S ? H + S : 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_CAND] = cnt[C_RAW] ? H + S : 0;  // subpoly.py:110 tests the crossed edges
 }
 
 // ---- cell buckets ------------------------------------------------------------------------------
@@ -729,7 +887,7 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
     return TNB_OK;
 }
 
-static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps, cudaStream_t s)
+static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps, bool planar, cudaStream_t s)
 {
     const NetMeta &m = net->meta;
     const int H = m.H, R = m.R;
@@ -746,9 +904,24 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         TNB_LAUNCH_CHECK();
         // 1. edges the hyperplane crosses
         SplitCount sc{c->cedges(), c->cout_(), R, idx, eps};
-        if ((rc = compact(c->E, sc, ListEmit{c->split_list.p}, c->block_sums.p, cnt + C_SPLIT, s, cnt + C_E))) return rc;
+        if ((rc = compact(c->E, sc, ListEmit{c->split_list.p}, c->block_sums.p, cnt + C_RAW, s, cnt + C_E))) return rc;
         // 2. new vertices, their network rows, rewired edges (all sized on the device)
-        {
+        if (!planar) {
+            const int o = c->vcur ^ 1;  // idle half of the ping-pong arrays = temp slots
+            unsigned g = grid_for(c->E, kThreads);
+            prof_begin(TNB_PROF_NEW_VERTICES, s);
+            if (net->fixed_cfg)
+                k_new_vertices_curve<CfgRef><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->bmask.p, c->pcount.p, cnt);
+            else
+                k_new_vertices_curve<CfgAny><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->bmask.p, c->pcount.p, cnt);
+            TNB_LAUNCH_CHECK();
+            prof_end(TNB_PROF_NEW_VERTICES, s, 0);
+            k_strict_keep<<<g, kThreads, 0, s>>>(R, idx, eps, c->out[o].p, c->bmask.p, c->pcount.p, cnt);
+            TNB_LAUNCH_CHECK();
+            CurveCommitEmit ce{nullptr, c->split_list.p, c->cedges(), c->vert[o].p, c->out[o].p, c->cvert(), c->cout_(), c->csig(),
+                               m.marks, cnt, R, m.n_marks, m.eps, m.pre_scale, m.pre_2s, m.pre_inv, m.pre_pow2};
+            if ((rc = compact(c->E, KeepFlagCount{c->pcount.p, cnt + C_OVERFLOW}, ce, c->block_sums.p, cnt + C_SPLIT, s, cnt + C_RAW))) return rc;
+        } else {
             unsigned g = grid_for(c->E, kThreads);
             prof_begin(TNB_PROF_NEW_VERTICES, s);
             if (net->fixed_cfg)
@@ -788,11 +961,19 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         c->counts_stale = false;
         if (!c->h_counters[C_OVERFLOW]) break;
         if (attempt > 0) { set_error("work buffers did not grow"); return TNB_ERR_CAPACITY; }
-        const int S_need = c->h_counters[C_SPLIT];
+        const int S_need = c->h_counters[C_RAW];
         if ((rc = complex_reserve(c, c->V + S_need, c->E + S_need, s))) return rc;
     }
+    if (c->h_counters[C_ERR] & kErrNoPlane) {
+        set_error("curve path: a non-axis-aligned edge lies on no earlier plane (the reference exits here, subpoly.py:140-148)");
+        return TNB_ERR_INVALID;
+    }
+    if (c->h_counters[C_ERR] & kErrGradientDescent) {
+        set_error("curve path: an intersection needs the gradient-descent repair of subpoly_debug.py:121-165, which is not built");
+        return TNB_ERR_UNSUPPORTED;
+    }
+    if (c->h_counters[C_RAW] == 0) return TNB_OK;  // subpoly.py:110-111
     const int S = c->h_counters[C_SPLIT];
-    if (S == 0) return TNB_OK;  // subpoly.py:110-111
     const int V0 = (int)c->V, E0 = (int)c->E;
     const int Hn = c->h_counters[C_HIT], P = c->h_counters[C_PAIRS];
     const int n_cand = Hn + S;
@@ -968,14 +1149,9 @@ int tnb_complex_read(const tnb_complex *c, float *d_vertices, int64_t *d_edges, 
 int tnb_subpoly_step(const tnb_net *net, tnb_complex *c, int32_t l, int32_t h, float eps, int32_t force, void *stream)
 {
     if (!net || !c) { set_error("tnb_subpoly_step: null argument"); return TNB_ERR_INVALID; }
-    if (!force) {
-        set_error("the curve-approximation path (force=False, subpoly.py:120-177) is not built yet; "
-                  "only the planar path (the reference default) runs on the device");
-        return TNB_ERR_UNSUPPORTED;
-    }
     current_stream() = (cudaStream_t)stream;
     c->stream = (cudaStream_t)stream;
-    return step_impl(net, c, l, h, eps, (cudaStream_t)stream);
+    return step_impl(net, c, l, h, eps, force != 0, (cudaStream_t)stream);
 }
 
 }  // extern "C"

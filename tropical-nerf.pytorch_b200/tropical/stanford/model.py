@@ -47,8 +47,8 @@ class Net(nn.Module):
     def forward(self, x, gather: bool = False, group: int = 1):
         """model.py:52-76.  gather=True returns (output, [hidden pre-activations..., o1-o0])."""
         if group != 1:
-            raise _native.NativeError("group != 1 belongs to the curve-approximation path "
-                                      "(force=False), which is not built on the device yet")
+            raise _native.NativeError("group != 1 (model.py:65-70) is evaluated inside the device "
+                                      "kernels of the curve-approximation path; it has no host entry")
         nat = self.native()
         rows = nat.outputs(x)
         H = self.num_hidden

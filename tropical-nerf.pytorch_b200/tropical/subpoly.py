@@ -15,13 +15,6 @@ from torch.nn import Module
 from tropical import TropicalHashGrid, _native
 
 
-def _require_planar(force):
-    if not force:
-        raise _native.NativeError(
-            "force=False (curve approximation, subpoly.py:120-177) is not built on the device "
-            "yet; the planar path (the reference default) is")
-
-
 @torch.no_grad()
 def subpoly(net: Module, d: int, size: float, eps: float = 1e-4, force: bool = False,
             return_mesh: bool = False):
@@ -29,10 +22,10 @@ def subpoly(net: Module, d: int, size: float, eps: float = 1e-4, force: bool = F
 
     Returns (faces, vertices, faces_with_indices): faces [T,3,3] numpy triangle positions,
     vertices [V,3] device tensor, faces_with_indices [T,3] numpy vertex indices.
-    NOTE the reference's default is force=False but its entry point passes force=True
-    (train.py:50-51,127); only force=True runs here."""
-    _require_planar(force)
-    mesh = net.native().subpoly(size=size, eps=eps, force=True)
+    force=True is the planar path the reference's entry point uses (train.py:50-51,127);
+    force=False is the curve-approximation path (subpoly.py:120-183 + strict_check); its
+    gradient-descent repair (subpoly_debug.py:121-165) is not built and raises if needed."""
+    mesh = net.native().subpoly(size=size, eps=eps, force=force)
     s = mesh.sizes()
     print()
     print(f"# of vertices and edges => {s['V']}/{s['E']}, {s['P']} faces", end=", ")
@@ -54,14 +47,13 @@ def subpoly_(vertices, edges, net, l, h, eps, outputs_=None, pruning=True, stric
     """One hyperplane (subpoly.py:90-279).  `outputs_` is either None (first call: the
     complex is built from `vertices`/`edges`) or the state object returned by the previous
     call.  Returns (vertices, edges, state)."""
-    _require_planar(force)
     if not pruning:
         raise _native.NativeError("pruning=False is not supported on the device path")
     if isinstance(outputs_, _ComplexState):
         state = outputs_
     else:
         state = _ComplexState(net.native().complex_from_arrays(vertices, edges))
-    state.cx.step(l, h, eps, True)
+    state.cx.step(l, h, eps, force)
     v, e, _ = state.cx.read(outputs=False)
     return v, e, state
 
