@@ -257,10 +257,10 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------
 # the CPU arm (oracle port of the reference's algorithm)
 # ---------------------------------------------------------------------------------------
-def cpu_extract_seconds(P):
+def cpu_extract_seconds(P, planar=True):
     from oracle import subpoly_ref as R
     t = time.perf_counter()
-    faces, vertices, tri = R.subpoly(P)
+    faces, vertices, tri = R.subpoly(P, force=planar)
     return time.perf_counter() - t, vertices.shape[0], tri.shape[0]
 
 
@@ -270,11 +270,12 @@ def run_reference(args):
         return
     w = load_workload(args.workload)
     P = oracle_params(w)
+    planar = args.path == "planar"
     for _ in range(min(args.warmup, 1)):
-        cpu_extract_seconds(P)
+        cpu_extract_seconds(P, planar)
     total, nv = 0.0, 0
     for _ in range(args.steps):
-        dt, nv, _ = cpu_extract_seconds(P)
+        dt, nv, _ = cpu_extract_seconds(P, planar)
         total += dt
     value = nv * args.steps / total
     cpu = {"value": value, "unit": UNIT, "cores": 1, "kind": "port",
@@ -283,7 +284,7 @@ def run_reference(args):
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                      "data": "synthetic", "config": {"workload": w["describe"], "mesh_vertices": nv},
+                      "data": "synthetic", "config": {"workload": w["describe"] + ("" if planar else " [curve-approximation path]"), "mesh_vertices": nv},
                       "cpu_baseline": cpu,
                       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -324,8 +325,10 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    planar = args.path == "planar"
+
     def step():
-        return net.subpoly(size=1.2, eps=w["eps"], force=True)
+        return net.subpoly(size=1.2, eps=w["eps"], force=planar)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -367,9 +370,9 @@ def run_ours(args):
 
     def e2e_step():
         n2 = make_native(w, pinned_np)            # host -> device copy of the step's inputs
-        m2 = n2.subpoly(size=1.2, eps=w["eps"], force=True)
-        v, tr, f, p = m2.read_host()              # device -> host read of the result
-        return v.nbytes + tr.nbytes + f.nbytes + p.nbytes
+        m2 = n2.subpoly(size=1.2, eps=w["eps"], force=planar)
+        v, tr, f, _ = m2.read_host(polygons=False)   # device -> host read of subpoly()'s return values
+        return v.nbytes + tr.nbytes + f.nbytes
 
     for _ in range(2):
         d2h = e2e_step()
@@ -441,14 +444,14 @@ def run_ours(args):
     # ---- CPU baseline (bounded sample on the box's host cores) ----------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
-        dt, nv, _ = cpu_extract_seconds(oracle_params(w))
+        dt, nv, _ = cpu_extract_seconds(oracle_params(w), planar)
         cpu = {"value": nv / dt, "unit": UNIT, "cores": 1, "kind": "port", "seconds": dt,
                "sample": "1 full extraction of the same network with the numpy+C oracle port"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": w["describe"], "mesh_vertices": sizes["V"], "mesh_triangles": sizes["T"],
+           "config": {"workload": w["describe"] + ("" if planar else " [curve-approximation path]"), "mesh_vertices": sizes["V"], "mesh_triangles": sizes["T"],
                       "polygons": sizes["P"], "objects_per_step": world, "l2": "flushed (512 MiB write) between timed steps",
                       "extraction_s": ms_total / args.steps * 1e-3},
            "clocks": clocks, "gpu_launches": launches,
@@ -467,6 +470,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="small_sphere")
+    ap.add_argument("--path", default="planar", choices=["planar", "curve"],
+                    help="planar = the reference's -f default (force=True); curve = curve approximation")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the evaluation-sweep throughput leg")
     ap.add_argument("--sweep-n", type=int, default=512, help="lattice size per axis of the evaluation sweep")

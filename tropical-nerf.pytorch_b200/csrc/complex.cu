@@ -7,8 +7,11 @@
 // edge numbering equal the reference's.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
+
+#include <cooperative_groups.h>
 
 #include "complex.cuh"
 #include "curve.cuh"
@@ -421,11 +424,11 @@ struct ListEmit {
 // new vertex of every split edge: position (subpoly.py:113-117, :180), network row, the
 // failover mask of subpoly_debug.py:37-43, edge rewiring (subpoly.py:210-215)
 template <class C>
-__global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant__ NetMeta n, int idx, float eps,
-                                                           int Vcap, int Ecap, const int *__restrict__ split_list,
-                                                           int2 *__restrict__ edges, float *__restrict__ vert,
-                                                           float *__restrict__ out, const uint64_t *__restrict__ sig,
-                                                           uint64_t *__restrict__ bmask, int *__restrict__ cnt)
+__device__ __forceinline__ void body_new_vertices(const NetMeta &n, int idx, float eps,
+                                                           int Vcap, int Ecap, const int *split_list,
+                                                           int2 *edges, float *vert,
+                                                           float *out, const uint64_t *sig,
+                                                           uint64_t *bmask, int *cnt)
 {
     const int R = n.R;
     const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
@@ -463,12 +466,22 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant
     if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
 }
 
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant__ NetMeta n, int idx, float eps,
+                                                           int Vcap, int Ecap, const int *__restrict__ split_list,
+                                                           int2 *__restrict__ edges, float *__restrict__ vert,
+                                                           float *__restrict__ out, const uint64_t *__restrict__ sig,
+                                                           uint64_t *__restrict__ bmask, int *__restrict__ cnt)
+{
+    body_new_vertices<C>(n, idx, eps, Vcap, Ecap, split_list, edges, vert, out, sig, bmask, cnt);
+}
+
 // apply the failover override when any new vertex violated it, then bit-pack the region
 // indicator of the new vertices
-__global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant__ NetMeta n,
-                                                           const float *__restrict__ vert, float *__restrict__ out,
-                                                           uint64_t *__restrict__ sig, const uint64_t *__restrict__ bmask,
-                                                           const int *__restrict__ cnt)
+__device__ __forceinline__ void body_finalize_new(const NetMeta &n,
+                                                           const float *vert, float *out,
+                                                           uint64_t *sig, const uint64_t *bmask,
+                                                           const int *cnt)
 {
     const int R = n.R;
     if (cnt[C_OVERFLOW]) return;
@@ -486,6 +499,14 @@ __global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant
         sig[3 * v + 1] = neg;
         sig[3 * v + 2] = pack_grid(n, n.marks, xp, n.eps);
     }
+}
+
+__global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant__ NetMeta n,
+                                                           const float *__restrict__ vert, float *__restrict__ out,
+                                                           uint64_t *__restrict__ sig, const uint64_t *__restrict__ bmask,
+                                                           const int *__restrict__ cnt)
+{
+    body_finalize_new(n, vert, out, sig, bmask, cnt);
 }
 
 
@@ -650,12 +671,17 @@ struct HitCount {
 
 // candidates = hit old vertices (already in cand[0..H)), then the new ones; publishes the
 // candidate count
-__global__ void k_fill_new_cands(int *__restrict__ cand, int *__restrict__ cnt)
+__device__ __forceinline__ void body_fill_new_cands(int *cand, int *cnt)
 {
     const int H = cnt[C_HIT], S = cnt[C_SPLIT], V = cnt[C_V];
     if (cnt[C_OVERFLOW]) return;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) cand[H + k] = V + k;
     if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_CAND] = cnt[C_RAW] ? H + S : 0;  // subpoly.py:110 tests the crossed edges
+}
+
+__global__ void k_fill_new_cands(int *__restrict__ cand, int *__restrict__ cnt)
+{
+    body_fill_new_cands(cand, cnt);
 }
 
 // ---- cell buckets ------------------------------------------------------------------------------
@@ -679,9 +705,9 @@ __device__ __forceinline__ int64_t cell_id(int cx, int cy, int cz, int dim)
     return ((int64_t)(cx + 2) * dim + (cy + 2)) * dim + (cz + 2);
 }
 
-__global__ void k_bucket_insert(const int *__restrict__ cand, const int *__restrict__ cnt,
-                                const uint64_t *__restrict__ sig, unsigned long long *__restrict__ head,
-                                int *__restrict__ next, int dim, uint32_t stamp)
+__device__ __forceinline__ void body_bucket_insert(const int *cand, const int *cnt,
+                                const uint64_t *sig, unsigned long long *head,
+                                int *next, int dim, uint32_t stamp)
 {
     const int n_cand = cnt[C_CAND];
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += gridDim.x * blockDim.x) {
@@ -698,14 +724,21 @@ __global__ void k_bucket_insert(const int *__restrict__ cand, const int *__restr
     }
 }
 
+__global__ void __launch_bounds__(kThreads) k_bucket_insert(const int *__restrict__ cand, const int *__restrict__ cnt,
+                                const uint64_t *__restrict__ sig, unsigned long long *__restrict__ head,
+                                int *__restrict__ next, int dim, uint32_t stamp)
+{
+    body_bucket_insert(cand, cnt, sig, head, next, dim, stamp);
+}
+
 constexpr int kLocalPartners = 128;  // partner lists up to this size are sorted in registers/local memory
 
 // Partners of candidate a: candidates b with a larger vertex number that share an expanded
 // region with a and at least one plane (subpoly.py:484-535).  Each pair is found in exactly
 // one cell (the smallest common one).  Returns the count; when `list` is non-null the first
 // `cap` partner vertex numbers are stored there (unsorted).
-__device__ __forceinline__ int find_partners(int a, const int *__restrict__ cand, const uint64_t *__restrict__ sig,
-                                             const unsigned long long *__restrict__ head, const int *__restrict__ next,
+__device__ __forceinline__ int find_partners(int a, const int *cand, const uint64_t *sig,
+                                             const unsigned long long *head, const int *next,
                                              int dim, uint32_t stamp, uint64_t colmask, int *list, int cap, int stride)
 {
     const int va = cand[a];
@@ -741,17 +774,42 @@ __device__ __forceinline__ int find_partners(int a, const int *__restrict__ cand
     return count;
 }
 
-__global__ void __launch_bounds__(kThreads) k_pair_count(const int *__restrict__ cand, int *__restrict__ cnt,
-                                                         const uint64_t *__restrict__ sig,
-                                                         const unsigned long long *__restrict__ head,
-                                                         const int *__restrict__ next, int dim, uint32_t stamp,
-                                                         uint64_t colmask, int *__restrict__ pcount)
+__device__ __forceinline__ void body_pair_count(const int *cand, int *cnt,
+                                                         const uint64_t *sig,
+                                                         const unsigned long long *head,
+                                                         const int *next, int dim, uint32_t stamp,
+                                                         uint64_t colmask, int *pcount)
 {
     const int n_cand = cnt[C_CAND];
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x)
         pcount[a] = find_partners(a, cand, sig, head, next, dim, stamp, colmask, nullptr, 0, 1);
 }
 
+__global__ void __launch_bounds__(kThreads) k_pair_count(const int *__restrict__ cand, int *__restrict__ cnt,
+                                                         const uint64_t *__restrict__ sig,
+                                                         const unsigned long long *__restrict__ head,
+                                                         const int *__restrict__ next, int dim, uint32_t stamp,
+                                                         uint64_t colmask, int *__restrict__ pcount)
+{
+    body_pair_count(cand, cnt, sig, head, next, dim, stamp, colmask, pcount);
+}
+
+struct PairCountFn {  // count phase of the partner-offset scan: search, remember, return the count
+    const int *cand;
+    const uint64_t *sig;
+    const unsigned long long *head;
+    const int *next;
+    int dim;
+    uint32_t stamp;
+    uint64_t colmask;
+    int *pcount;
+    __device__ __forceinline__ int operator()(int64_t a) const
+    {
+        const int c = find_partners((int)a, cand, sig, head, next, dim, stamp, colmask, nullptr, 0, 1);
+        pcount[a] = c;
+        return c;
+    }
+};
 struct ArrayCount {
     const int *v;
     __device__ __forceinline__ int operator()(int64_t i) const { return v[i]; }
@@ -761,12 +819,12 @@ struct OffsetEmit {
     __device__ __forceinline__ void operator()(int64_t i, int pos, int) const { off[i] = pos; }
 };
 
-__global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__ cand, int n_cand,
-                                                         const uint64_t *__restrict__ sig,
-                                                         const unsigned long long *__restrict__ head,
-                                                         const int *__restrict__ next, int dim, uint32_t stamp,
-                                                         uint64_t colmask, const int *__restrict__ pcount,
-                                                         const int *__restrict__ poff, int2 *__restrict__ edges_out)
+__device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
+                                                         const uint64_t *sig,
+                                                         const unsigned long long *head,
+                                                         const int *next, int dim, uint32_t stamp,
+                                                         uint64_t colmask, const int *pcount,
+                                                         const int *poff, int2 *edges_out)
 {
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x) {
         const int c = pcount[a];
@@ -816,6 +874,16 @@ __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__
     }
 }
 
+__global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__ cand, int n_cand,
+                                                         const uint64_t *__restrict__ sig,
+                                                         const unsigned long long *__restrict__ head,
+                                                         const int *__restrict__ next, int dim, uint32_t stamp,
+                                                         uint64_t colmask, const int *__restrict__ pcount,
+                                                         const int *__restrict__ poff, int2 *__restrict__ edges_out)
+{
+    body_pair_write(cand, n_cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out);
+}
+
 // ---- pruning -------------------------------------------------------------------------------------
 struct KeepCount {  // subpoly.py:262-264: keep an edge iff its ends differ in a future indicator
     const int2 *edges;
@@ -857,13 +925,18 @@ struct VertexMoveEmit {  // subpoly.py:268-277: compact vertices, positions, cac
     }
 };
 
-__global__ void k_remap_edges_dev(int2 *__restrict__ edges, const int *__restrict__ n_dev, const int *__restrict__ remap)
+__device__ __forceinline__ void body_remap_edges_dev(int2 *edges, const int *n_dev, const int *remap)
 {
     const int64_t E = *n_dev;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
         int2 ed = edges[e];
         edges[e] = make_int2(remap[ed.x], remap[ed.y]);
     }
+}
+
+__global__ void k_remap_edges_dev(int2 *__restrict__ edges, const int *__restrict__ n_dev, const int *__restrict__ remap)
+{
+    body_remap_edges_dev(edges, n_dev, remap);
 }
 __global__ void k_set_counts(int *__restrict__ cnt, int V, int E)
 {
@@ -874,6 +947,110 @@ __global__ void k_clear_step_counters(int *__restrict__ cnt)
 {
     if (threadIdx.x < C_V) cnt[threadIdx.x] = 0;
 }
+
+
+// ---- fused hyperplane step (planar path) ------------------------------------------------------------
+// The front half of a step is eleven dependent phases over a few thousand items each; as
+// separate launches their cost is launch latency.  Both halves are therefore also available as
+// ONE cooperative kernel each: a persistent grid (a multiple of the 148 SMs, all CTAs
+// co-resident) walks the phases separated by grid.sync().  Same device functions, same results.
+namespace cg = cooperative_groups;
+
+struct StepArgs {
+    int idx;
+    float eps;
+    int Vcap, Ecap, dim;
+    uint32_t stamp;
+    uint64_t colmask, futmask;
+    int2 *edges, *edges_dst;
+    float *vert, *out, *nvert, *nout;
+    uint64_t *sig, *nsig, *bmask;
+    int *split_list, *cand, *pcount, *poff, *next, *used, *remap, *block_sums, *cnt;
+    unsigned long long *head;
+    int n_cand, V, E, S, P;  // back half: exact sizes the host read at the sync
+};
+
+template <class C>
+__global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_constant__ NetMeta n, const StepArgs a)
+{
+    cg::grid_group grid = cg::this_grid();
+    int *cnt = a.cnt;
+    if (blockIdx.x == 0 && threadIdx.x < C_V) cnt[threadIdx.x] = 0;
+    const int E = cnt[C_E], V = cnt[C_V];
+    const SplitCount sc{a.edges, a.out, n.R, a.idx, a.eps};
+    scan_count_body(E, sc, a.block_sums);
+    grid.sync();
+    scan_write_body(E, sc, ListEmit{a.split_list}, a.block_sums, cnt + C_RAW);
+    grid.sync();
+    body_new_vertices<C>(n, a.idx, a.eps, a.Vcap, a.Ecap, a.split_list, a.edges, a.vert, a.out, a.sig, a.bmask, cnt);
+    const HitCount hc{a.out, n.R, a.idx, a.eps};  // old vertices only: independent of the new rows
+    scan_count_body(V, hc, a.block_sums);
+    grid.sync();
+    body_finalize_new(n, a.vert, a.out, a.sig, a.bmask, cnt);
+    {   // every CTA knows the hit count from the block sums: the new vertices' candidate slots
+        // [H, H+S) can be filled in the same phase as the hit list [0, H)
+        __shared__ int s_h[kScanWarps];
+        int acc = 0;
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += kScanThreads) acc += a.block_sums[b];
+        acc = warp_sum(acc);
+        if ((threadIdx.x & 31) == 0) s_h[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        int Hn = 0;
+        for (int w = 0; w < kScanWarps; ++w) Hn += s_h[w];
+        __syncthreads();
+        if (!cnt[C_OVERFLOW]) {
+            const int S = cnt[C_SPLIT];
+            for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) a.cand[Hn + k] = V + k;
+            if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_CAND] = cnt[C_RAW] ? Hn + S : 0;
+        }
+    }
+    scan_write_body(V, hc, ListEmit{a.cand}, a.block_sums, cnt + C_HIT);
+    grid.sync();
+    body_bucket_insert(a.cand, cnt, a.sig, a.head, a.next, a.dim, a.stamp);
+    grid.sync();
+    const int n_cand = cnt[C_CAND];
+    scan_count_body(n_cand, PairCountFn{a.cand, a.sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount}, a.block_sums);
+    grid.sync();
+    scan_write_body(n_cand, ArrayCount{a.pcount}, OffsetEmit{a.poff}, a.block_sums, cnt + C_PAIRS);
+}
+
+__global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a, int R)
+{
+    cg::grid_group grid = cg::this_grid();
+    int *cnt = a.cnt;
+    const int Vn = a.V + a.S;
+    const int64_t En = (int64_t)a.E + a.S + a.P;
+    if (a.P > 0)
+        body_pair_write(a.cand, a.n_cand, a.sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount, a.poff,
+                        a.edges + a.E + a.S);
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += gridDim.x * blockDim.x) a.used[v] = 0;
+    grid.sync();
+    const KeepCount kc{a.edges, a.sig, a.futmask};
+    scan_count_body(En, kc, a.block_sums);
+    grid.sync();
+    scan_write_body(En, kc, KeepEmit{a.edges, a.edges_dst, a.used}, a.block_sums, cnt + C_E);
+    grid.sync();
+    const FlagCount fc{a.used};
+    scan_count_body(Vn, fc, a.block_sums);
+    grid.sync();
+    scan_write_body(Vn, fc, VertexMoveEmit{a.vert, a.out, a.sig, a.nvert, a.nout, a.nsig, a.remap, R}, a.block_sums,
+                    cnt + C_V);
+    grid.sync();
+    body_remap_edges_dev(a.edges_dst, cnt + C_E, a.remap);
+}
+
+// co-resident grid size of a cooperative kernel: blocks/SM x SMs, capped by the scan tables
+template <class K>
+static int coop_blocks(K kernel)
+{
+    int dev = 0, sms = kSMs, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kScanThreads, 0) != cudaSuccess || per_sm < 1) return 0;
+    return std::min(per_sm * sms, kScanMaxBlocks);
+}
+constexpr int64_t kFusedMaxItems = 400000;
+static bool g_fused_steps = std::getenv("TNB_NO_FUSED_STEPS") == nullptr;  // A/B switch for profiling
 
 // Refresh the host's view of the complex size (one small D2H + sync).
 int complex_sync_counts(tnb_complex *c, cudaStream_t s)
@@ -899,7 +1076,46 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     if (c->E == 0) return TNB_OK;
     const uint64_t colmask = (1ull << idx) - 1ull;
 
+    // planar path: both halves as one cooperative kernel each (grid = co-resident CTAs)
+    static int front_blocks_ref = -1, front_blocks_any = -1, back_blocks = -1;
+    if (front_blocks_ref < 0) {
+        front_blocks_ref = coop_blocks(k_step_front<CfgRef>);
+        front_blocks_any = coop_blocks(k_step_front<CfgAny>);
+        back_blocks = coop_blocks(k_step_back);
+    }
+    // Cooperative grids are for SMALL complexes (where launch latency dominates): one CTA per SM
+    // keeps grid.sync() cheap.  Large complexes keep the multi-launch path with full-size grids.
+    const int sm_blocks = std::min(kSMs, std::min(front_blocks_ref, back_blocks));
+    const int front_blocks = std::min(net->fixed_cfg ? front_blocks_ref : front_blocks_any, sm_blocks);
+    const bool fused = planar && g_fused_steps && front_blocks > 0 && back_blocks > 0 && c->E + c->V <= kFusedMaxItems;
+    StepArgs sa;
+    auto fill_args = [&]() {
+        memset(&sa, 0, sizeof(sa));
+        sa.idx = idx; sa.eps = eps; sa.Vcap = (int)c->Vcap; sa.Ecap = (int)c->Ecap; sa.dim = c->cell_dim;
+        sa.stamp = c->stamp; sa.colmask = colmask;
+        sa.edges = c->cedges(); sa.vert = c->cvert(); sa.out = c->cout_(); sa.sig = c->csig();
+        sa.bmask = c->bmask.p; sa.split_list = c->split_list.p; sa.cand = c->cand.p; sa.pcount = c->pcount.p;
+        sa.poff = c->poff.p; sa.next = c->next.p; sa.used = c->used.p; sa.remap = c->remap.p;
+        sa.block_sums = c->block_sums.p; sa.cnt = c->counters.p; sa.head = c->head.p;
+    };
+
     for (int attempt = 0;; ++attempt) {
+      if (fused) {
+        c->stamp += 1;
+        if (c->stamp == 0) {
+            TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
+            c->stamp = 1;
+        }
+        fill_args();
+        void *params[] = {(void *)&m, (void *)&sa};
+        prof_begin(TNB_PROF_NEW_VERTICES, s);
+        if (net->fixed_cfg)
+            TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_front<CfgRef>, dim3(front_blocks), dim3(kScanThreads), params, 0, s));
+        else
+            TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_front<CfgAny>, dim3(front_blocks), dim3(kScanThreads), params, 0, s));
+        count_launch();
+        prof_end(TNB_PROF_NEW_VERTICES, s, 0);
+      } else {
         k_clear_step_counters<<<1, 32, 0, s>>>(cnt);
         TNB_LAUNCH_CHECK();
         // 1. edges the hyperplane crosses
@@ -954,6 +1170,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             prof_end(TNB_PROF_PAIRS, s, 0);
         }
         if ((rc = compact(cand_ub, ArrayCount{c->pcount.p}, OffsetEmit{c->poff.p}, c->block_sums.p, cnt + C_PAIRS, s, cnt + C_CAND))) return rc;
+      }
         // ---- the one host sync of the step ----
         if ((rc = read_counters(c, s))) return rc;
         c->V = c->h_counters[C_V];
@@ -979,6 +1196,26 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     const int n_cand = Hn + S;
     if ((rc = complex_reserve(c, (size_t)V0 + S, (size_t)E0 + S + P, s))) return rc;
     cnt = c->counters.p;
+    if (fused && h < H) {
+        const uint64_t futmask = ~colmask & (R >= 64 ? ~0ull : ((1ull << R) - 1ull));
+        fill_args();
+        const int o = c->vcur ^ 1;
+        sa.futmask = futmask; sa.edges_dst = c->edges[c->ecur ^ 1].p;
+        sa.nvert = c->vert[o].p; sa.nout = c->out[o].p; sa.nsig = c->sig[o].p;
+        sa.n_cand = n_cand; sa.V = V0; sa.E = E0; sa.S = S; sa.P = P;
+        int Rv = R;
+        void *params[] = {(void *)&sa, (void *)&Rv};
+        prof_begin(TNB_PROF_PAIRS, s);
+        TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_back, dim3(std::min(back_blocks, sm_blocks)), dim3(kScanThreads), params, 0, s));
+        count_launch();
+        prof_end(TNB_PROF_PAIRS, s, n_cand);
+        c->V = V0 + S;
+        c->E = (int64_t)E0 + S + P;
+        c->ecur ^= 1;
+        c->vcur = o;
+        c->counts_stale = true;
+        return TNB_OK;
+    }
     if (P > 0) {
         prof_begin(TNB_PROF_PAIRS, s);
         k_pair_write<<<grid_for(n_cand, kThreads), kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S);

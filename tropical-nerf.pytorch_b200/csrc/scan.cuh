@@ -50,13 +50,11 @@ __device__ __forceinline__ void scan_slice(int64_t n, int64_t &begin, int64_t &e
     if (end > n) end = n;
 }
 
-// n_dev (optional): the item count lives in device memory (a previous kernel produced it);
-// n is then only the host's upper bound used to size the grid.
+// The two phases as device functions (blockDim.x == kScanThreads), so that fused cooperative
+// kernels can run them between grid syncs; the __global__ wrappers follow.
 template <class Count>
-__global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, const int *__restrict__ n_dev, Count count,
-                                                             int *__restrict__ block_sums)
+__device__ __forceinline__ void scan_count_body(int64_t n, Count count, int *block_sums)
 {
-    if (n_dev) n = *n_dev;
     int64_t begin, end;
     scan_slice(n, begin, end);
     int acc = 0;
@@ -70,14 +68,12 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, const in
         for (int w = 0; w < kScanWarps; ++w) t += s[w];
         block_sums[blockIdx.x] = t;
     }
+    __syncthreads();  // s[] may be reused by the caller's next phase
 }
 
 template <class Count, class Emit>
-__global__ void __launch_bounds__(kScanThreads) k_scan_write(int64_t n, const int *__restrict__ n_dev, Count count,
-                                                             Emit emit, const int *__restrict__ block_sums,
-                                                             int *__restrict__ total)
+__device__ __forceinline__ void scan_write_body(int64_t n, Count count, Emit emit, const int *block_sums, int *total)
 {
-    if (n_dev) n = *n_dev;
     __shared__ int s_warp[kScanWarps];
     __shared__ int s_base;
     // base offset of this block = sum of the sums before it; block 0 also publishes the total
@@ -117,6 +113,26 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_write(int64_t n, const in
         if (c) emit(i, running + warp_off + incl - c, c);
         running += tile_total;
     }
+    __syncthreads();
+}
+
+// n_dev (optional): the item count lives in device memory (a previous kernel produced it);
+// n is then only the host's upper bound used to size the grid.
+template <class Count>
+__global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, const int *__restrict__ n_dev, Count count,
+                                                             int *__restrict__ block_sums)
+{
+    if (n_dev) n = *n_dev;
+    scan_count_body(n, count, block_sums);
+}
+
+template <class Count, class Emit>
+__global__ void __launch_bounds__(kScanThreads) k_scan_write(int64_t n, const int *__restrict__ n_dev, Count count,
+                                                             Emit emit, const int *__restrict__ block_sums,
+                                                             int *__restrict__ total)
+{
+    if (n_dev) n = *n_dev;
+    scan_write_body(n, count, emit, block_sums, total);
 }
 
 // Host helper: runs both phases.  `block_sums` must hold kScanMaxBlocks ints; the total

@@ -315,13 +315,14 @@ class NativeMesh:
         check(lib().tnb_mesh_read(self.handle, _ptr(v), _ptr(e), _ptr(t), _ptr(f), _ptr(p), _stream()))
         return v, e, t, f, p
 
-    def read_host(self):
+    def read_host(self, polygons=True):
         """numpy arrays through tnb_mesh_read_host (host buffers): vertices, triangles,
-        faces, polygons."""
+        faces (what the reference's subpoly() returns) and, optionally, the polygon rows."""
         s = self.sizes()
         v = np.empty((s["V"], 3), np.float32)
         t = np.empty((s["T"], 3), np.int64)
         f = np.empty((s["T"], 3, 3), np.float32)
-        p = np.empty((s["P"], s["W"]), np.int64)
-        check(lib().tnb_mesh_read_host(self.handle, v.ctypes.data, t.ctypes.data, f.ctypes.data, p.ctypes.data))
+        p = np.empty((s["P"], s["W"]), np.int64) if polygons else None
+        check(lib().tnb_mesh_read_host(self.handle, v.ctypes.data, t.ctypes.data, f.ctypes.data,
+                                       p.ctypes.data if polygons else None))
         return v, t, f, p
