@@ -292,17 +292,6 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------
-ALGO_BYTES = {
-    # algorithmic HBM bytes per unit of each timed kernel class (DESIGN.md "Kernels")
-    "sweep": lambda R: 4,                       # |sdf| written per marks-grid vertex (inputs are generated)
-    "vertex_rows": lambda R: 12 + 4 * R + 24,   # position in, R outputs + 3 packed words out
-    "new_vertices": lambda R: 8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * R + 8 + 16,
-    "pairs": lambda R: 4 + 24 + 4,
-    "face_rows": lambda R: 24 + 4,
-    "sign_sweep": lambda R: 16,
-}
-
-
 def run_ours(args):
     import torch
     from tropical import _native
@@ -400,9 +389,7 @@ def run_ours(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     top = max(prof, key=lambda k: prof[k][0])
-    ms, n_launch, units = prof[top]
-    table_bytes = w["table"].size * 4
-    algo = ALGO_BYTES[top](R) * units + (table_bytes * n_launch if top in ("sweep", "vertex_rows", "new_vertices", "sign_sweep") else 0)
+    ms, n_launch, units, algo = prof[top]   # algorithmic bytes are accounted by the library
     achieved = algo / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -414,8 +401,10 @@ def run_ours(args):
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": algo / max(n_launch, 1), "launches": n_launch,
                 "avg_launch_ms": ms / max(n_launch, 1), "kernel_share_of_step": ms / ms_total,
-                "note": "the fused trilinear kernels are fp32-issue bound, not HBM bound: see DESIGN.md",
-                "by_kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()}}
+                "units": units,
+                "note": "small complexes are latency bound (grid syncs / dependent phases), the trilinear kernels fp32-issue bound: see DESIGN.md section 5",
+                "by_kernel_ms_per_step": {k: v[0] / args.steps for k, v in prof.items()},
+                "by_kernel_gbs": {k: (v[3] / (v[0] * 1e-3) / 1e9 if v[0] > 0 else 0.0) for k, v in prof.items()}}
 
     # ---- evaluation-sweep throughput (BASELINE configs[4]), outside the timed region -----
     sweep = None

@@ -159,8 +159,12 @@ void tnb_launch_count_reset(void);
  * events on the launching stream.  Classes: 0 = marks-grid sweep (sdf + gradient),
  * 1 = vertex network rows (outputs + packed signs), 2 = new-vertex subdivision kernel,
  * 3 = connecting-edge search, 4 = face rows, 5 = dense sign sweep.
+ * On small complexes the planar step runs as two fused cooperative kernels: class 2 then
+ * times the front half (split scan + new vertices + hit scan + buckets + partner count) and
+ * class 3 the back half (connecting-edge write + pruning compactions).
  * tnb_profile_read synchronises the recorded events and returns the summed milliseconds,
- * the launch count and the number of units (vertices / points / edges) processed. */
+ * the launch count, the units (vertices / points / edges / candidates) processed and the
+ * ALGORITHMIC bytes of those launches (compulsory HBM traffic). */
 #define TNB_PROF_SWEEP 0
 #define TNB_PROF_VERTEX_ROWS 1
 #define TNB_PROF_NEW_VERTICES 2
@@ -169,7 +173,7 @@ void tnb_launch_count_reset(void);
 #define TNB_PROF_SIGN_SWEEP 5
 #define TNB_PROF_CLASSES 6
 int tnb_profile_enable(int on);
-int tnb_profile_read(int cls, double *ms, int64_t *launches, int64_t *units);
+int tnb_profile_read(int cls, double *ms, int64_t *launches, int64_t *units, int64_t *bytes);
 void tnb_profile_reset(void);
 
 #ifdef __cplusplus

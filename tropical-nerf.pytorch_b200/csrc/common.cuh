@@ -55,7 +55,8 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line);
 void count_launch(int n = 1);
 // optional CUDA-event timers around the heavy kernels (tnb_profile_*)
 void prof_begin(int cls, cudaStream_t s);
-void prof_end(int cls, cudaStream_t s, int64_t units);
+void prof_end(int cls, cudaStream_t s, int64_t units, int64_t bytes = 0);
+void prof_add(int cls, int64_t units, int64_t bytes);  // sizes that are only known after a later sync
 
 #define TNB_CUDA(expr)                                                         \
     do {                                                                       \

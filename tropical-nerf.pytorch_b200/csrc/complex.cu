@@ -278,7 +278,7 @@ static int eval_vertices(const tnb_net *net, tnb_complex *c, int64_t first, int6
     if (net->fixed_cfg) k_vertex_outputs<CfgRef><<<g, kThreads, 0, s>>>(net->meta, c->cvert(), first, count, c->cout_(), c->csig());
     else k_vertex_outputs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, c->cvert(), first, count, c->cout_(), c->csig());
     TNB_LAUNCH_CHECK();
-    prof_end(TNB_PROF_VERTEX_ROWS, s, count);
+    prof_end(TNB_PROF_VERTEX_ROWS, s, count, count * (12 + 4 * net->meta.R + 24) + (int64_t)net->table.cap * 8);
     return TNB_OK;
 }
 
@@ -321,7 +321,7 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
                 else
                     k_sweep_chunk<CfgAny><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist.p, max_grad.p + chunk);
                 TNB_LAUNCH_CHECK();
-                prof_end(TNB_PROF_SWEEP, s, count);
+                prof_end(TNB_PROF_SWEEP, s, count, count * 4 + (int64_t)net->table.cap * 8);
                 for (int axis = 0; axis < 3; ++axis) {
                     int dims[3] = {nn[0], nn[1], nn[2]};
                     dims[axis] -= 1;
@@ -1192,6 +1192,15 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     if (c->h_counters[C_RAW] == 0) return TNB_OK;  // subpoly.py:110-111
     const int S = c->h_counters[C_SPLIT];
     const int V0 = (int)c->V, E0 = (int)c->E;
+    {   // algorithmic bytes of what ran before the sync (sizes are known only now)
+        const int64_t Hc = c->h_counters[C_HIT], newv = (int64_t)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * R + 8 + 16);
+        if (fused)  // split scan (edge + two cached outputs, two passes), hit scan, new vertices, buckets + partner count
+            prof_add(TNB_PROF_NEW_VERTICES, (int64_t)E0 + V0, 2 * 16 * (int64_t)E0 + 2 * 4 * (int64_t)V0 + newv + (Hc + S) * (24 + 8 + 4 + 24));
+        else {
+            prof_add(TNB_PROF_NEW_VERTICES, S, newv + (int64_t)net->table.cap * 8);
+            prof_add(TNB_PROF_PAIRS, Hc + S, (Hc + S) * (24 + 4));
+        }
+    }
     const int Hn = c->h_counters[C_HIT], P = c->h_counters[C_PAIRS];
     const int n_cand = Hn + S;
     if ((rc = complex_reserve(c, (size_t)V0 + S, (size_t)E0 + S + P, s))) return rc;
@@ -1208,7 +1217,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         prof_begin(TNB_PROF_PAIRS, s);
         TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_back, dim3(std::min(back_blocks, sm_blocks)), dim3(kScanThreads), params, 0, s));
         count_launch();
-        prof_end(TNB_PROF_PAIRS, s, n_cand);
+        prof_end(TNB_PROF_PAIRS, s, n_cand, (int64_t)n_cand * 28 + (int64_t)P * 8 + ((int64_t)E0 + S + P) * (8 + 2 * 48) + ((int64_t)V0 + S) * (4 + 2 * (36 + 4 * R)));
         c->V = V0 + S;
         c->E = (int64_t)E0 + S + P;
         c->ecur ^= 1;
@@ -1220,7 +1229,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         prof_begin(TNB_PROF_PAIRS, s);
         k_pair_write<<<grid_for(n_cand, kThreads), kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S);
         TNB_LAUNCH_CHECK();
-        prof_end(TNB_PROF_PAIRS, s, n_cand);
+        prof_end(TNB_PROF_PAIRS, s, n_cand, (int64_t)n_cand * 28 + (int64_t)P * 8);
     }
     c->V = V0 + S;
     c->E = (int64_t)E0 + S + P;

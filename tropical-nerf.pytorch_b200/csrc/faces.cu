@@ -568,7 +568,7 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
                                                                        scratch.p, rows_per_vertex.p, nullptr, nullptr, nullptr, 0,
                                                                        counters.p);
         TNB_LAUNCH_CHECK();
-        prof_end(TNB_PROF_FACE_ROWS, s, Vs);
+        prof_end(TNB_PROF_FACE_ROWS, s, Vs, Vs * 28);
         if ((rc = compact(Vs, ArrayCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
         if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
         if (h[F_ERR_ZEROS]) { set_error("a surface vertex lies on more than 5 planes: more than 32 adjacent regions"); return TNB_ERR_UNSUPPORTED; }

@@ -44,7 +44,7 @@ void init_pool_once()
 struct ProfClass {
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev;
     cudaEvent_t open = nullptr;
-    int64_t units = 0;
+    int64_t units = 0, bytes = 0;
     double ms = 0.0;
     int64_t launches = 0;
 };
@@ -58,7 +58,13 @@ void prof_begin(int cls, cudaStream_t s)
     cudaEventRecord(e, s);
     g_prof[cls].open = e;
 }
-void prof_end(int cls, cudaStream_t s, int64_t units)
+void prof_add(int cls, int64_t units, int64_t bytes)
+{
+    if (!g_prof_on) return;
+    g_prof[cls].units += units;
+    g_prof[cls].bytes += bytes;
+}
+void prof_end(int cls, cudaStream_t s, int64_t units, int64_t bytes)
 {
     if (!g_prof_on || !g_prof[cls].open) return;
     cudaEvent_t e;
@@ -67,6 +73,7 @@ void prof_end(int cls, cudaStream_t s, int64_t units)
     g_prof[cls].ev.emplace_back(g_prof[cls].open, e);
     g_prof[cls].open = nullptr;
     g_prof[cls].units += units;
+    g_prof[cls].bytes += bytes;
 }
 static void prof_collect(int cls)
 {
@@ -272,15 +279,17 @@ void tnb_profile_reset(void)
         g_prof[c].ms = 0.0;
         g_prof[c].launches = 0;
         g_prof[c].units = 0;
+        g_prof[c].bytes = 0;
     }
 }
-int tnb_profile_read(int cls, double *ms, int64_t *launches, int64_t *units)
+int tnb_profile_read(int cls, double *ms, int64_t *launches, int64_t *units, int64_t *bytes)
 {
     if (cls < 0 || cls >= TNB_PROF_CLASSES) { set_error("tnb_profile_read: bad class"); return TNB_ERR_INVALID; }
     prof_collect(cls);
     if (ms) *ms = g_prof[cls].ms;
     if (launches) *launches = g_prof[cls].launches;
     if (units) *units = g_prof[cls].units;
+    if (bytes) *bytes = g_prof[cls].bytes;
     return TNB_OK;
 }
 
@@ -443,7 +452,7 @@ int tnb_sweep_signs(const tnb_net *net, const float lo[3], const float hi[3], co
     else
         k_sweep_signs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], eps, (ulonglong2 *)d_packed);
     TNB_LAUNCH_CHECK();
-    prof_end(TNB_PROF_SIGN_SWEEP, s, count);
+    prof_end(TNB_PROF_SIGN_SWEEP, s, count, count * 16);
     return TNB_OK;
 }
 

@@ -76,7 +76,7 @@ SIGNATURES = {
     "tnb_launch_count": (_I64, []),
     "tnb_launch_count_reset": (None, []),
     "tnb_profile_enable": (ctypes.c_int, [ctypes.c_int]),
-    "tnb_profile_read": (ctypes.c_int, [ctypes.c_int, _P, _P, _P]),
+    "tnb_profile_read": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, _P]),
     "tnb_profile_reset": (None, []),
 }
 
@@ -114,7 +114,7 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-PROFILE_CLASSES = ["sweep", "vertex_rows", "new_vertices", "pairs", "face_rows", "sign_sweep"]
+PROFILE_CLASSES = ["sweep", "vertex_rows", "step_front", "step_back", "face_rows", "sign_sweep"]
 
 
 def profile_enable(on=True):
@@ -126,12 +126,13 @@ def profile_reset():
 
 
 def profile_read():
-    """{class: (milliseconds, launches, units)} of the library's per-kernel event timers."""
+    """{class: (milliseconds, launches, units, algorithmic bytes)} of the library's per-kernel
+    event timers."""
     out = {}
     for i, name in enumerate(PROFILE_CLASSES):
-        ms, n, u = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64()
-        check(lib().tnb_profile_read(i, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(u)))
-        out[name] = (ms.value, n.value, u.value)
+        ms, n, u, b = ctypes.c_double(), ctypes.c_int64(), ctypes.c_int64(), ctypes.c_int64()
+        check(lib().tnb_profile_read(i, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(u), ctypes.byref(b)))
+        out[name] = (ms.value, n.value, u.value, b.value)
     return out
 
 
