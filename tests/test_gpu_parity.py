@@ -218,3 +218,43 @@ def test_curve_path_mesh_matches_reference(case):
     assert (d1.mean() + d2.mean()) / 2 <= 1e-6
     assert v.shape[0] == ref_v.shape[0]
     assert 0 <= gc["triangles"].shape[0] - t.shape[0] <= 4  # duplicated reference faces, see test_whole_path_mesh
+
+
+def test_train_entry_point_runs_end_to_end(tmp_path, monkeypatch):
+    """python -m tropical.stanford.train -d sphere -e : fit, extract on the device, write the mesh."""
+    from tropical.stanford import train
+    monkeypatch.chdir(tmp_path)
+    train.main(["-d", "sphere", "-s", "1", "-c", "-e"])   # the reference's 10 epochs x 50 batches
+    ply = tmp_path / "meshes" / "sphere" / "our_mesh_small_1.ply"
+    assert ply.exists()
+    head = ply.read_text().splitlines()[:4]
+    assert head[0] == "ply" and int(head[2].split()[-1]) > 1000   # a real surface came out
+
+
+def test_mirror_api_matches_native():
+    """tropical.subpoly.subpoly / Net methods (the reference-facing API) on the device."""
+    import tropical.subpoly as sp
+    from tropical.stanford.model import Net
+    g = load_golden("small_sphere")
+    P = oracle_net(g)
+    net = Net(num_layers=3, num_hidden=16, levels=4, r_min=2, r_max=32, T=19)
+    sd = {"enc.module.params": torch.from_numpy(g["net_table"])}
+    for i in range(3):
+        sd[f"fc.{i}.weight"], sd[f"fc.{i}.bias"] = torch.from_numpy(g[f"net_w{i}"]), torch.from_numpy(g[f"net_b{i}"])
+    net.load_state_dict(sd)
+    net = net.cuda()
+    with torch.no_grad():
+        x = torch.rand(1000, 3, device="cuda") * 2 - 1
+        out, inputs = net(x, gather=True)
+        assert np.array_equal(torch.cat(inputs, -1).cpu().numpy(), P.outputs(x.cpu().numpy()))
+        m, off, _ = net.region(x)
+        mo, oo, _ = P.region(x.cpu().numpy())
+        assert np.array_equal(m.cpu().numpy(), mo) and np.array_equal(off.cpu().numpy(), oo)
+        assert np.array_equal(net.sdf(x)[:, 0].cpu().numpy(), P.sdf_grad(x.cpu().numpy(), False)[0])
+        assert np.array_equal(net.normal(x).cpu().numpy(), P.sdf_grad(x.cpu().numpy())[1])
+        v, e = net.enc.skeleton(net)
+        assert np.array_equal(e.cpu().numpy(), g["skeleton_edges"].astype(np.int64))
+        faces, vertices, tri = sp.subpoly(net, 3, 1.2, force=True)
+    from oracle import subpoly_ref as R
+    fo, vo, to = R.subpoly(P)
+    assert np.array_equal(vertices.cpu().numpy(), vo) and np.array_equal(tri, to) and np.array_equal(faces, fo)

@@ -54,3 +54,31 @@ def test_hypercube():
     from oracle import subpoly_ref as R
     vo, eo = R.get_hypercube(1.2)
     assert np.array_equal(v.numpy(), vo) and np.array_equal(e.numpy(), eo)
+
+
+def test_training_route_is_differentiable_and_matches_the_oracle_encoding():
+    """With autograd enabled Net/HashEncoding evaluate in differentiable torch (the training loop
+    of stanford/train.py incl. its double-backward eikonal term); same interpolation as the
+    oracle's encoding."""
+    from helpers import load_golden, oracle_net
+    from tropical.stanford.model import Net
+    g = load_golden("small_sphere")
+    P = oracle_net(g)
+    net = Net()
+    net.enc.module.params.data = torch.from_numpy(g["net_table"])
+    xp = torch.rand(500, 3)
+    enc = net.enc.module.forward_autograd(xp.clone().requires_grad_(True))
+    assert np.abs(enc.detach().numpy() - P.encode(xp.numpy())).max() <= 1e-6
+    x = (torch.rand(64, 3) * 2 - 1).requires_grad_(True)
+    s = net.sdf(x)
+    J = torch.autograd.grad(s.sum(), x, create_graph=True)[0]
+    ((J.norm() - 1) ** 2 + s.abs().mean()).backward()
+    assert float(net.enc.module.params.grad.abs().sum()) > 0 and float(net.fc[0].weight.grad.abs().sum()) > 0
+
+
+def test_train_entry_point_cli_matches_the_reference():
+    from tropical.stanford import train
+    a = train.parse(["-d", "bunny", "-s", "1", "-m", "large", "-e"])
+    assert (a.dataset, a.seed, a.model_size, a.eval, a.force, a.cache) == ("bunny", 1, "large", True, True, True)
+    a = train.parse(["-f", "-c"])   # both switches are store_false in the reference (train.py:44-51)
+    assert a.force is False and a.cache is False and a.dataset == "dragon" and a.seed == 45

@@ -11,9 +11,10 @@ from tropical import _native
 
 class Net(nn.Module):
     """HashGrid + ReLU MLP SDF network (model.py:18-50).  Same constructor, parameter names
-    and methods as the reference; forward/sdf/region/normal run in the fused sm_100a
-    kernels (no autograd through them: the extraction path is @torch.no_grad in the
-    reference too, and its input gradients are computed analytically on the device)."""
+    and methods as the reference.  Under torch.no_grad() (the extraction path, which is
+    @torch.no_grad in the reference too) forward/sdf/region/normal run in the fused sm_100a
+    kernels and input gradients are computed analytically on the device; with autograd enabled
+    (the training loop) forward/sdf are ordinary differentiable torch."""
 
     def __init__(self, num_layers: int = 3, num_hidden: int = 16, levels: int = 4,
                  r_min: int = 2, r_max: int = 32, T: int = 19, eps: float = 1e-4):
@@ -46,6 +47,8 @@ class Net(nn.Module):
 
     def forward(self, x, gather: bool = False, group: int = 1):
         """model.py:52-76.  gather=True returns (output, [hidden pre-activations..., o1-o0])."""
+        if torch.is_grad_enabled() and (x.requires_grad or self.fc[0].weight.requires_grad):
+            return self._forward_autograd(x, gather)
         if group != 1:
             raise _native.NativeError("group != 1 (model.py:65-70) is evaluated inside the device "
                                       "kernels of the curve-approximation path; it has no host entry")
@@ -60,6 +63,20 @@ class Net(nn.Module):
             return out, inputs
         return out
 
+    def _forward_autograd(self, x, gather=False):
+        """model.py:52-76 in differentiable torch ops (training)."""
+        inputs = []
+        h = self.enc.module.forward_autograd(self.preprocess(x)).float()
+        last = len(self.fc) - 1
+        for i, fc in enumerate(self.fc):
+            h = fc(h)
+            if i != last:
+                inputs.append(h)
+                h = F.relu(h)
+            else:
+                inputs.append(h[:, 1:] - h[:, :1])
+        return (h, inputs) if gather else h
+
     def preprocess(self, x):
         return (x + self.scale) / (self.scale * 2)
 
@@ -68,6 +85,9 @@ class Net(nn.Module):
 
     def sdf(self, x):
         """tanh(o1 - o0) (model.py:84-88), [n,1]."""
+        if torch.is_grad_enabled() and (x.requires_grad or self.fc[0].weight.requires_grad):
+            out = self._forward_autograd(x)
+            return torch.tanh(out[:, 1:] - out[:, :1])
         sdf, _ = self.native().sdf_grad(x, want_grad=False)
         return sdf.unsqueeze(-1)
 

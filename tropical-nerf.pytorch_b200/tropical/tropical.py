@@ -19,8 +19,13 @@ __all__ = ["HashEncoding", "TropicalHashGrid", "Tropical", "low_precision"]
 class HashEncoding(Module):
     """Multiresolution hash encoding with tiny-cuda-nn's parameter layout
     (`tcnn.Encoding(D, {"otype": "Grid", "type": "Hash", ...}, dtype=torch.float)`,
-    tropical.py:32-40).  Inference only: the extraction path never differentiates through
-    it (gradients w.r.t. the input come from `tnb_net_sdf_grad`)."""
+    tropical.py:32-40).
+
+    Two evaluation routes.  Under `torch.no_grad()` (the whole extraction path) the fused
+    sm_100a kernel runs (`tnb_grid_encode`).  When autograd needs the result (the training loop
+    of stanford/train.py, including its double-backward eikonal term) the same interpolation is
+    expressed in differentiable torch ops on whatever device the parameters live on; training
+    is not on the extraction hot path."""
 
     def __init__(self, n_input_dims, n_levels, n_features_per_level, log2_hashmap_size,
                  base_resolution, per_level_scale, seed=1337):
@@ -30,7 +35,7 @@ class HashEncoding(Module):
         self.log2_hashmap_size, self.base_resolution = log2_hashmap_size, base_resolution
         self.per_level_scale = float(per_level_scale)
         self.n_output_dims = n_levels * n_features_per_level
-        self.level_sizes = self._layout()
+        self.level_sizes, self.level_scales, self.level_res = self._layout()
         g = torch.Generator().manual_seed(seed)
         init = (torch.rand(int(sum(self.level_sizes)) * self.n_features, generator=g) * 2 - 1) * 1e-4
         self.params = torch.nn.Parameter(init)  # U(-1e-4, 1e-4) like tiny-cuda-nn
@@ -43,20 +48,47 @@ class HashEncoding(Module):
         for fn in (libm.log2f, libm.exp2f):
             fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float]
         log2_pls = np.float32(libm.log2f(np.float32(self.per_level_scale)))
-        sizes = []
+        sizes, scales, ress = [], [], []
         for l in range(self.n_levels):
             s = np.float32(np.float32(libm.exp2f(np.float32(l) * log2_pls))
                            * np.float32(self.base_resolution) - np.float32(1.0))
             res = int(np.ceil(s)) + 1
             n = min((res ** 3 + 7) // 8 * 8, 1 << self.log2_hashmap_size)
             sizes.append(n)
-        return sizes
+            scales.append(float(s))
+            ress.append(res)
+        return sizes, scales, ress
+
+    def forward_autograd(self, x: Tensor) -> Tensor:
+        """Differentiable (any order) torch expression of the encoding, for training."""
+        U32 = 0xFFFFFFFF
+        table = self.params.view(-1, self.n_features)
+        outs, off = [], 0
+        for l in range(self.n_levels):
+            res, size = self.level_res[l], self.level_sizes[l]
+            pos = x * self.level_scales[l] + 0.5
+            cell_f = torch.floor(pos)
+            frac = pos - cell_f
+            cell = cell_f.detach().long() & U32
+            acc = 0
+            for corner in range(8):
+                w, cc = 1, []
+                for d in range(3):
+                    bit = (corner >> d) & 1
+                    w = w * (frac[:, d] if bit else 1 - frac[:, d])
+                    cc.append((cell[:, d] + bit) & U32)
+                if res ** 3 <= size:
+                    idx = (cc[0] + cc[1] * res + cc[2] * res * res) & U32
+                else:
+                    idx = cc[0] ^ ((cc[1] * 2654435761) & U32) ^ ((cc[2] * 805459861) & U32)
+                acc = acc + w.unsqueeze(-1) * table[off + idx % size]
+            outs.append(acc)
+            off += size
+        return torch.cat(outs, dim=-1)
 
     def forward(self, x: Tensor) -> Tensor:
         if torch.is_grad_enabled() and (x.requires_grad or self.params.requires_grad):
-            raise _native.NativeError(
-                "HashEncoding.forward is inference-only on the device path; wrap the call in "
-                "torch.no_grad() (input gradients: Net.normal / tnb_net_sdf_grad)")
+            return self.forward_autograd(x)
         return self._owner._native_for_encoding().encode(x)
 
 
