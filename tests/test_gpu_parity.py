@@ -258,3 +258,67 @@ def test_mirror_api_matches_native():
     from oracle import subpoly_ref as R
     fo, vo, to = R.subpoly(P)
     assert np.array_equal(vertices.cpu().numpy(), vo) and np.array_equal(tri, to) and np.array_equal(faces, fo)
+
+
+@pytest.mark.parametrize("unit", [17, 25])
+def test_chunked_skeleton_reproduces_the_overlap_duplicates(unit):
+    """TropicalHashGrid.skeleton walks the marks grid in chunks of `unit` vertices that overlap by
+    one plane (tropical.py:176-181): per-chunk thresholds, and grid edges on a chunk-boundary plane
+    come out twice.  Small chunks exercise that path (the large model hits it with unit=128)."""
+    from oracle import subpoly_ref as R
+    g = load_golden("small_sphere")
+    P = oracle_net(g)
+    N = native_net(P)
+    c = N.skeleton(unit, 1.2)
+    v, e, o = c.read()
+    vo, eo = R.skeleton(P, unit)
+    assert np.array_equal(e.cpu().numpy(), eo) and np.array_equal(v.cpu().numpy(), vo)
+    e_np = e.cpu().numpy()
+    assert len(np.unique(e_np, axis=0)) < len(e_np)   # the duplicated boundary edges are really there
+    mesh = N.subpoly(unit=unit)
+    vv, _, t, f, _ = [a.cpu().numpy() for a in mesh.read()]
+    fo, vo2, to = R.subpoly(P, unit=unit)
+    assert np.array_equal(vv, vo2) and np.array_equal(t, to) and np.array_equal(f, fo)
+
+
+def test_work_buffers_grow_on_demand():
+    """capacity factor 1.0: no head-room at all, every growing step takes the re-allocation path."""
+    from oracle import subpoly_ref as R
+    from tropical import _native
+    g = load_golden("small_torus")
+    P = oracle_net(g)
+    N = native_net(P)
+    _native.check(_native.lib().tnb_set_capacity_factor(1.0))
+    try:
+        mesh = N.subpoly()
+        v, _, t, _, _ = [a.cpu().numpy() for a in mesh.read()]
+    finally:
+        _native.check(_native.lib().tnb_set_capacity_factor(4.0))
+    _, vo, to = R.subpoly(P)
+    assert np.array_equal(v, vo) and np.array_equal(t, to)
+
+
+def test_empty_and_caller_supplied_inputs():
+    from oracle import subpoly_ref as R
+    g = load_golden("tiny_sphere_h8")
+    P = oracle_net(g)
+    N = native_net(P)
+    empty = torch.empty((0, 3), device="cuda")
+    assert N.outputs(empty).shape == (0, P.n_outputs)
+    assert N.sdf_grad(empty)[0].shape == (0,)
+    s, off, _ = N.region(empty)
+    assert s.shape == (0, 3 + P.n_outputs) and off.shape == (0, 3)
+    # a complex built from caller arrays (the reference passes its own vertices/edges to subpoly_)
+    vo, eo = R.skeleton(P)
+    c = N.complex_from_arrays(torch.from_numpy(vo).cuda(), torch.from_numpy(eo).cuda())
+    oo = P.outputs(vo)
+    for (l, h) in [(0, 0), (0, 1), (1, 3)]:
+        c.step(l, h)
+        vo, eo, oo = R.subpoly_step(P, vo, eo, oo, l, h, 1e-4)
+        v, e, o = c.read()
+        assert np.array_equal(e.cpu().numpy(), eo) and np.array_equal(v.cpu().numpy(), vo)
+    # a complex without edges stays empty
+    c0 = N.complex_from_arrays(torch.from_numpy(vo[:4]).cuda(), torch.empty((0, 2), dtype=torch.int64, device="cuda"))
+    c0.step(0, 0)
+    assert c0.num_edges == 0
+    assert c0.extract_mesh().sizes()["T"] == 0
