@@ -27,8 +27,11 @@ constexpr int kThreads = 128;
 // device counters: [0, C_V) are cleared at the start of every step, C_V / C_E hold the complex size
 //   C_RAW = edges the plane crosses, C_SPLIT = edges actually split (== C_RAW on the planar path,
 //   fewer after strict_check on the curve path)
-enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_NUM = 16 };
+//   C_VPAR / C_EPAR = which half of the ping-pong vertex / edge arrays is current,
+//   C_STICKY = error bits that survive steps (sync-free fused path)
+enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_NUM = 16 };
 enum { kErrNoPlane = 1, kErrGradientDescent = 2 };
+enum { kStickyCapacity = 1 };
 
 // ---- allocation ---------------------------------------------------------------------------
 int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
@@ -52,6 +55,8 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
     TNB_CUDA(c->remap.reserve(Vcap));
     TNB_CUDA(c->block_sums.reserve(kScanMaxBlocks));
     TNB_CUDA(c->counters.reserve(C_NUM));
+    TNB_CUDA(c->bytes.reserve(2));
+    TNB_CUDA(cudaMemsetAsync(c->bytes.p, 0, 2 * sizeof(unsigned long long), current_stream()));
     TNB_CUDA(cudaMemsetAsync(c->counters.p, 0, C_NUM * sizeof(int), current_stream()));
     {   // one pinned mirror per thread, reused by every complex
         static thread_local int *pinned = nullptr;
@@ -111,7 +116,7 @@ int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
     return TNB_OK;
 }
 
-__global__ void k_set_counts(int *__restrict__ cnt, int V, int E);
+__global__ void k_set_counts(int *__restrict__ cnt, int V, int E, int vpar, int epar);
 
 static int read_counters(tnb_complex *c, cudaStream_t s)
 {
@@ -389,7 +394,7 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
         TNB_LAUNCH_CHECK();
         c->V = V;
         c->E = E;
-        k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E);
+        k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E, c->vcur, c->ecur);
         TNB_LAUNCH_CHECK();
         rc = eval_vertices(net, c, 0, V, s);
         if (rc) return rc;
@@ -938,10 +943,17 @@ __global__ void k_remap_edges_dev(int2 *__restrict__ edges, const int *__restric
 {
     body_remap_edges_dev(edges, n_dev, remap);
 }
-__global__ void k_set_counts(int *__restrict__ cnt, int V, int E)
+__global__ void k_set_counts(int *__restrict__ cnt, int V, int E, int vpar, int epar)
 {
     cnt[C_V] = V;
     cnt[C_E] = E;
+    cnt[C_VPAR] = vpar;
+    cnt[C_EPAR] = epar;
+}
+__global__ void k_set_parity(int *__restrict__ cnt, int vpar, int epar)
+{
+    cnt[C_VPAR] = vpar;
+    cnt[C_EPAR] = epar;
 }
 __global__ void k_clear_step_counters(int *__restrict__ cnt)
 {
@@ -956,18 +968,20 @@ __global__ void k_clear_step_counters(int *__restrict__ cnt)
 // co-resident) walks the phases separated by grid.sync().  Same device functions, same results.
 namespace cg = cooperative_groups;
 
+// Everything a step needs lives on the device: sizes, which half of the ping-pong arrays is
+// current (C_VPAR / C_EPAR), capacity checks and sticky error bits (C_STICKY).  The host can
+// therefore enqueue all 33 steps back to back and sync ONCE at the end.
 struct StepArgs {
-    int idx;
+    int idx, R, do_prune;
     float eps;
     int Vcap, Ecap, dim;
     uint32_t stamp;
     uint64_t colmask, futmask;
-    int2 *edges, *edges_dst;
-    float *vert, *out, *nvert, *nout;
-    uint64_t *sig, *nsig, *bmask;
+    int2 *edges[2];
+    float *vert[2], *out[2];
+    uint64_t *sig[2], *bmask;
     int *split_list, *cand, *pcount, *poff, *next, *used, *remap, *block_sums, *cnt;
-    unsigned long long *head;
-    int n_cand, V, E, S, P;  // back half: exact sizes the host read at the sync
+    unsigned long long *head, *bytes;  // bytes[0/1]: algorithmic bytes of the front / back halves
 };
 
 template <class C>
@@ -975,18 +989,23 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
 {
     cg::grid_group grid = cg::this_grid();
     int *cnt = a.cnt;
+    if (cnt[C_STICKY]) return;  // an earlier step failed: uniform exit, nobody reaches a grid sync
+    const int E = cnt[C_E], V = cnt[C_V], pv = cnt[C_VPAR], pe = cnt[C_EPAR];
+    int2 *edges = a.edges[pe];
+    float *vert = a.vert[pv], *out = a.out[pv];
+    uint64_t *sig = a.sig[pv];
+    // the words read above (>= C_V) are not among the transient counters block 0 clears now
     if (blockIdx.x == 0 && threadIdx.x < C_V) cnt[threadIdx.x] = 0;
-    const int E = cnt[C_E], V = cnt[C_V];
-    const SplitCount sc{a.edges, a.out, n.R, a.idx, a.eps};
+    const SplitCount sc{edges, out, n.R, a.idx, a.eps};
     scan_count_body(E, sc, a.block_sums);
     grid.sync();
     scan_write_body(E, sc, ListEmit{a.split_list}, a.block_sums, cnt + C_RAW);
     grid.sync();
-    body_new_vertices<C>(n, a.idx, a.eps, a.Vcap, a.Ecap, a.split_list, a.edges, a.vert, a.out, a.sig, a.bmask, cnt);
-    const HitCount hc{a.out, n.R, a.idx, a.eps};  // old vertices only: independent of the new rows
+    body_new_vertices<C>(n, a.idx, a.eps, a.Vcap, a.Ecap, a.split_list, edges, vert, out, sig, a.bmask, cnt);
+    const HitCount hc{out, n.R, a.idx, a.eps};  // old vertices only: independent of the new rows
     scan_count_body(V, hc, a.block_sums);
     grid.sync();
-    body_finalize_new(n, a.vert, a.out, a.sig, a.bmask, cnt);
+    body_finalize_new(n, vert, out, sig, a.bmask, cnt);
     {   // every CTA knows the hit count from the block sums: the new vertices' candidate slots
         // [H, H+S) can be filled in the same phase as the hit list [0, H)
         __shared__ int s_h[kScanWarps];
@@ -1001,42 +1020,73 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
         if (!cnt[C_OVERFLOW]) {
             const int S = cnt[C_SPLIT];
             for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) a.cand[Hn + k] = V + k;
-            if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_CAND] = cnt[C_RAW] ? Hn + S : 0;
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                cnt[C_CAND] = cnt[C_RAW] ? Hn + S : 0;
+                // split scan (edge + two cached outputs, two passes), hit scan, new vertices, buckets + partner count
+                a.bytes[0] += 2ull * 16 * E + 2ull * 4 * V + (unsigned long long)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * n.R + 8 + 16) +
+                              (unsigned long long)(Hn + S) * (24 + 8 + 4 + 24);
+            }
         }
     }
     scan_write_body(V, hc, ListEmit{a.cand}, a.block_sums, cnt + C_HIT);
     grid.sync();
-    body_bucket_insert(a.cand, cnt, a.sig, a.head, a.next, a.dim, a.stamp);
+    body_bucket_insert(a.cand, cnt, sig, a.head, a.next, a.dim, a.stamp);
     grid.sync();
     const int n_cand = cnt[C_CAND];
-    scan_count_body(n_cand, PairCountFn{a.cand, a.sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount}, a.block_sums);
+    scan_count_body(n_cand, PairCountFn{a.cand, sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount}, a.block_sums);
     grid.sync();
     scan_write_body(n_cand, ArrayCount{a.pcount}, OffsetEmit{a.poff}, a.block_sums, cnt + C_PAIRS);
 }
 
-__global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a, int R)
+__global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
 {
     cg::grid_group grid = cg::this_grid();
     int *cnt = a.cnt;
-    const int Vn = a.V + a.S;
-    const int64_t En = (int64_t)a.E + a.S + a.P;
-    if (a.P > 0)
-        body_pair_write(a.cand, a.n_cand, a.sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount, a.poff,
-                        a.edges + a.E + a.S);
+    // all decisions are uniform over the grid (same device words read by everybody before any write)
+    const int sticky = cnt[C_STICKY], raw = cnt[C_RAW], overflow = cnt[C_OVERFLOW];
+    const int S = cnt[C_SPLIT], P = cnt[C_PAIRS], V0 = cnt[C_V], E0 = cnt[C_E], n_cand = cnt[C_CAND];
+    const int pv = cnt[C_VPAR], pe = cnt[C_EPAR];
+    if (sticky || raw == 0) return;  // subpoly.py:110-111: nothing crossed, nothing changes
+    const int64_t En = (int64_t)E0 + S + P;
+    const int Vn = V0 + S;
+    if (overflow || En > a.Ecap) {  // the host re-runs the extraction with larger arrays
+        if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_STICKY] = kStickyCapacity;
+        return;
+    }
+    int2 *edges = a.edges[pe], *edges_dst = a.edges[pe ^ 1];
+    float *vert = a.vert[pv], *out = a.out[pv];
+    uint64_t *sig = a.sig[pv];
+    if (P > 0)
+        body_pair_write(a.cand, n_cand, sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount, a.poff, edges + E0 + S);
+    if (!a.do_prune) {  // the output neuron (subpoly.py:253): sizes only
+        grid.sync();
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            cnt[C_V] = Vn;
+            cnt[C_E] = (int)En;
+            a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8;
+        }
+        return;
+    }
     for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += gridDim.x * blockDim.x) a.used[v] = 0;
     grid.sync();
-    const KeepCount kc{a.edges, a.sig, a.futmask};
+    const KeepCount kc{edges, sig, a.futmask};
     scan_count_body(En, kc, a.block_sums);
     grid.sync();
-    scan_write_body(En, kc, KeepEmit{a.edges, a.edges_dst, a.used}, a.block_sums, cnt + C_E);
+    scan_write_body(En, kc, KeepEmit{edges, edges_dst, a.used}, a.block_sums, cnt + C_E);
     grid.sync();
     const FlagCount fc{a.used};
     scan_count_body(Vn, fc, a.block_sums);
     grid.sync();
-    scan_write_body(Vn, fc, VertexMoveEmit{a.vert, a.out, a.sig, a.nvert, a.nout, a.nsig, a.remap, R}, a.block_sums,
-                    cnt + C_V);
+    scan_write_body(Vn, fc, VertexMoveEmit{vert, out, sig, a.vert[pv ^ 1], a.out[pv ^ 1], a.sig[pv ^ 1], a.remap, a.R},
+                    a.block_sums, cnt + C_V);
     grid.sync();
-    body_remap_edges_dev(a.edges_dst, cnt + C_E, a.remap);
+    body_remap_edges_dev(edges_dst, cnt + C_E, a.remap);
+    if (blockIdx.x == 0 && threadIdx.x == 0) {  // flip the ping-pong halves
+        cnt[C_VPAR] = pv ^ 1;
+        cnt[C_EPAR] = pe ^ 1;
+        a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8 + (unsigned long long)En * (8 + 2 * 48) +
+                      (unsigned long long)Vn * (4 + 2 * (36 + 4 * a.R));
+    }
 }
 
 // co-resident grid size of a cooperative kernel: blocks/SM x SMs, capped by the scan tables
@@ -1060,7 +1110,21 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
     if (rc) return rc;
     c->V = c->h_counters[C_V];
     c->E = c->h_counters[C_E];
+    c->vcur = c->h_counters[C_VPAR];
+    c->ecur = c->h_counters[C_EPAR];
     c->counts_stale = false;
+    if (c->bytes.p) {  // algorithmic bytes the fused kernels accumulated on the device
+        unsigned long long hb[2] = {0, 0};
+        TNB_CUDA(cudaMemcpyAsync(hb, c->bytes.p, sizeof(hb), cudaMemcpyDeviceToHost, s));
+        TNB_CUDA(cudaMemsetAsync(c->bytes.p, 0, sizeof(hb), s));
+        TNB_CUDA(cudaStreamSynchronize(s));
+        prof_add(TNB_PROF_NEW_VERTICES, 0, (int64_t)hb[0]);
+        prof_add(TNB_PROF_PAIRS, 0, (int64_t)hb[1]);
+    }
+    if (c->h_counters[C_STICKY] & kStickyCapacity) {
+        set_error("work buffers too small for this complex (capacity factor " + std::to_string(g_capacity_factor) + ")");
+        return TNB_ERR_CAPACITY;
+    }
     return TNB_OK;
 }
 
@@ -1076,46 +1140,61 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     if (c->E == 0) return TNB_OK;
     const uint64_t colmask = (1ull << idx) - 1ull;
 
-    // planar path: both halves as one cooperative kernel each (grid = co-resident CTAs)
+    // planar path on small complexes: both halves as one cooperative kernel each, fully
+    // device-driven (sizes, buffer parity, capacity and error flags live in the counter block):
+    // nothing to wait for here, the host syncs when somebody asks for the sizes or the data.
     static int front_blocks_ref = -1, front_blocks_any = -1, back_blocks = -1;
     if (front_blocks_ref < 0) {
         front_blocks_ref = coop_blocks(k_step_front<CfgRef>);
         front_blocks_any = coop_blocks(k_step_front<CfgAny>);
         back_blocks = coop_blocks(k_step_back);
     }
-    // Cooperative grids are for SMALL complexes (where launch latency dominates): one CTA per SM
-    // keeps grid.sync() cheap.  Large complexes keep the multi-launch path with full-size grids.
+    // One CTA per SM keeps grid.sync() cheap.  Large complexes keep the multi-launch path with
+    // full-size grids (c->V / c->E may be stale upper bounds here: good enough for this choice).
     const int sm_blocks = std::min(kSMs, std::min(front_blocks_ref, back_blocks));
     const int front_blocks = std::min(net->fixed_cfg ? front_blocks_ref : front_blocks_any, sm_blocks);
     const bool fused = planar && g_fused_steps && front_blocks > 0 && back_blocks > 0 && c->E + c->V <= kFusedMaxItems;
-    StepArgs sa;
-    auto fill_args = [&]() {
-        memset(&sa, 0, sizeof(sa));
-        sa.idx = idx; sa.eps = eps; sa.Vcap = (int)c->Vcap; sa.Ecap = (int)c->Ecap; sa.dim = c->cell_dim;
-        sa.stamp = c->stamp; sa.colmask = colmask;
-        sa.edges = c->cedges(); sa.vert = c->cvert(); sa.out = c->cout_(); sa.sig = c->csig();
-        sa.bmask = c->bmask.p; sa.split_list = c->split_list.p; sa.cand = c->cand.p; sa.pcount = c->pcount.p;
-        sa.poff = c->poff.p; sa.next = c->next.p; sa.used = c->used.p; sa.remap = c->remap.p;
-        sa.block_sums = c->block_sums.p; sa.cnt = c->counters.p; sa.head = c->head.p;
-    };
-
-    for (int attempt = 0;; ++attempt) {
-      if (fused) {
+    if (fused) {
         c->stamp += 1;
         if (c->stamp == 0) {
             TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
             c->stamp = 1;
         }
-        fill_args();
-        void *params[] = {(void *)&m, (void *)&sa};
+        StepArgs sa;
+        memset(&sa, 0, sizeof(sa));
+        sa.idx = idx; sa.R = R; sa.do_prune = h < H ? 1 : 0; sa.eps = eps;
+        sa.Vcap = (int)c->Vcap; sa.Ecap = (int)c->Ecap; sa.dim = c->cell_dim; sa.stamp = c->stamp;
+        sa.colmask = colmask;
+        sa.futmask = ~colmask & (R >= 64 ? ~0ull : ((1ull << R) - 1ull));
+        for (int k = 0; k < 2; ++k) {
+            sa.edges[k] = c->edges[k].p; sa.vert[k] = c->vert[k].p; sa.out[k] = c->out[k].p; sa.sig[k] = c->sig[k].p;
+        }
+        sa.bmask = c->bmask.p; sa.split_list = c->split_list.p; sa.cand = c->cand.p; sa.pcount = c->pcount.p;
+        sa.poff = c->poff.p; sa.next = c->next.p; sa.used = c->used.p; sa.remap = c->remap.p;
+        sa.block_sums = c->block_sums.p; sa.cnt = c->counters.p; sa.head = c->head.p; sa.bytes = c->bytes.p;
+        void *fparams[] = {(void *)&m, (void *)&sa};
         prof_begin(TNB_PROF_NEW_VERTICES, s);
         if (net->fixed_cfg)
-            TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_front<CfgRef>, dim3(front_blocks), dim3(kScanThreads), params, 0, s));
+            TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_front<CfgRef>, dim3(front_blocks), dim3(kScanThreads), fparams, 0, s));
         else
-            TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_front<CfgAny>, dim3(front_blocks), dim3(kScanThreads), params, 0, s));
+            TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_front<CfgAny>, dim3(front_blocks), dim3(kScanThreads), fparams, 0, s));
         count_launch();
         prof_end(TNB_PROF_NEW_VERTICES, s, 0);
-      } else {
+        void *bparams[] = {(void *)&sa};
+        prof_begin(TNB_PROF_PAIRS, s);
+        TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_back, dim3(std::min(back_blocks, sm_blocks)), dim3(kScanThreads), bparams, 0, s));
+        count_launch();
+        prof_end(TNB_PROF_PAIRS, s, 0);
+        c->counts_stale = true;  // sizes and buffer parity are on the device until the next sync
+        return TNB_OK;
+    }
+    // multi-launch path: needs the host's view of sizes and buffer parity to be current
+    if ((rc = complex_sync_counts(c, s))) return rc;
+    if (c->E == 0) return TNB_OK;
+    cnt = c->counters.p;
+
+    for (int attempt = 0;; ++attempt) {
+      {
         k_clear_step_counters<<<1, 32, 0, s>>>(cnt);
         TNB_LAUNCH_CHECK();
         // 1. edges the hyperplane crosses
@@ -1194,37 +1273,13 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     const int V0 = (int)c->V, E0 = (int)c->E;
     {   // algorithmic bytes of what ran before the sync (sizes are known only now)
         const int64_t Hc = c->h_counters[C_HIT], newv = (int64_t)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * R + 8 + 16);
-        if (fused)  // split scan (edge + two cached outputs, two passes), hit scan, new vertices, buckets + partner count
-            prof_add(TNB_PROF_NEW_VERTICES, (int64_t)E0 + V0, 2 * 16 * (int64_t)E0 + 2 * 4 * (int64_t)V0 + newv + (Hc + S) * (24 + 8 + 4 + 24));
-        else {
-            prof_add(TNB_PROF_NEW_VERTICES, S, newv + (int64_t)net->table.cap * 8);
-            prof_add(TNB_PROF_PAIRS, Hc + S, (Hc + S) * (24 + 4));
-        }
+        prof_add(TNB_PROF_NEW_VERTICES, S, newv + (int64_t)net->table.cap * 8);
+        prof_add(TNB_PROF_PAIRS, Hc + S, (Hc + S) * (24 + 4));
     }
     const int Hn = c->h_counters[C_HIT], P = c->h_counters[C_PAIRS];
     const int n_cand = Hn + S;
     if ((rc = complex_reserve(c, (size_t)V0 + S, (size_t)E0 + S + P, s))) return rc;
     cnt = c->counters.p;
-    if (fused && h < H) {
-        const uint64_t futmask = ~colmask & (R >= 64 ? ~0ull : ((1ull << R) - 1ull));
-        fill_args();
-        const int o = c->vcur ^ 1;
-        sa.futmask = futmask; sa.edges_dst = c->edges[c->ecur ^ 1].p;
-        sa.nvert = c->vert[o].p; sa.nout = c->out[o].p; sa.nsig = c->sig[o].p;
-        sa.n_cand = n_cand; sa.V = V0; sa.E = E0; sa.S = S; sa.P = P;
-        int Rv = R;
-        void *params[] = {(void *)&sa, (void *)&Rv};
-        prof_begin(TNB_PROF_PAIRS, s);
-        TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_back, dim3(std::min(back_blocks, sm_blocks)), dim3(kScanThreads), params, 0, s));
-        count_launch();
-        prof_end(TNB_PROF_PAIRS, s, n_cand, (int64_t)n_cand * 28 + (int64_t)P * 8 + ((int64_t)E0 + S + P) * (8 + 2 * 48) + ((int64_t)V0 + S) * (4 + 2 * (36 + 4 * R)));
-        c->V = V0 + S;
-        c->E = (int64_t)E0 + S + P;
-        c->ecur ^= 1;
-        c->vcur = o;
-        c->counts_stale = true;
-        return TNB_OK;
-    }
     if (P > 0) {
         prof_begin(TNB_PROF_PAIRS, s);
         k_pair_write<<<grid_for(n_cand, kThreads), kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S);
@@ -1248,9 +1303,11 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         c->vcur = o;
         k_remap_edges_dev<<<grid_for(c->E, 256), 256, 0, s>>>(c->cedges(), cnt + C_E, c->remap.p);
         TNB_LAUNCH_CHECK();
+        k_set_parity<<<1, 1, 0, s>>>(cnt, c->vcur, c->ecur);  // the fused kernels read the parity on the device
+        TNB_LAUNCH_CHECK();
         c->counts_stale = true;  // c->V, c->E are upper bounds until the next sync
     } else {
-        k_set_counts<<<1, 1, 0, s>>>(cnt, (int)c->V, (int)c->E);
+        k_set_counts<<<1, 1, 0, s>>>(cnt, (int)c->V, (int)c->E, c->vcur, c->ecur);
         TNB_LAUNCH_CHECK();
     }
     return TNB_OK;
@@ -1298,7 +1355,7 @@ static int from_arrays_impl(const tnb_net *net, const float *d_vertices, int64_t
     }
     c->V = V;
     c->E = E;
-    k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E);
+    k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E, c->vcur, c->ecur);
     TNB_LAUNCH_CHECK();
     return eval_vertices(net, c, 0, V, s);
 }

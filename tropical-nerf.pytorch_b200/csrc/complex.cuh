@@ -29,6 +29,7 @@ struct tnb_complex {
     tnb::DevBuf<int> remap;         // [Vcap]
     tnb::DevBuf<int> block_sums;    // [kScanMaxBlocks]
     tnb::DevBuf<int> counters;      // [16] device counters
+    tnb::DevBuf<unsigned long long> bytes;  // [2] algorithmic bytes accumulated by the fused kernels
     int *h_counters = nullptr;      // pinned mirror (per thread, not owned)
     bool counts_stale = false;      // V/E are upper bounds; exact sizes are in counters[C_V], [C_E]
     cudaStream_t stream = nullptr;  // stream of the last call

@@ -726,15 +726,24 @@ int tnb_subpoly(const tnb_net *net, float size, float eps, int32_t force, int32_
 {
     if (!net || !out) { set_error("tnb_subpoly: null argument"); return TNB_ERR_INVALID; }
     *out = nullptr;
-    tnb_complex *c = nullptr;
-    int rc = tnb_skeleton(net, unit, size, &c, stream);
-    if (rc != TNB_OK) return rc;
-    const int H = net->meta.H, NL = net->meta.NLIN;
-    for (int l = 0; l < NL - 1 && rc == TNB_OK; ++l)
-        for (int h = 0; h < H && rc == TNB_OK; ++h) rc = tnb_subpoly_step(net, c, l, h, eps, force, stream);
-    if (rc == TNB_OK) rc = tnb_subpoly_step(net, c, NL - 2, H, eps, force, stream);  // the output neuron
-    if (rc == TNB_OK) rc = tnb_extract_mesh(net, c, eps, out, stream);
-    tnb_complex_destroy(c);
+    const double factor0 = g_capacity_factor;
+    int rc = TNB_OK;
+    // The steps run without host syncs; if the device reports that the work arrays were too
+    // small (sticky capacity bit), the extraction is simply repeated with twice the head-room.
+    for (int attempt = 0; attempt < 4; ++attempt) {
+        tnb_complex *c = nullptr;
+        rc = tnb_skeleton(net, unit, size, &c, stream);
+        if (rc != TNB_OK) break;
+        const int H = net->meta.H, NL = net->meta.NLIN;
+        for (int l = 0; l < NL - 1 && rc == TNB_OK; ++l)
+            for (int h = 0; h < H && rc == TNB_OK; ++h) rc = tnb_subpoly_step(net, c, l, h, eps, force, stream);
+        if (rc == TNB_OK) rc = tnb_subpoly_step(net, c, NL - 2, H, eps, force, stream);  // the output neuron
+        if (rc == TNB_OK) rc = tnb_extract_mesh(net, c, eps, out, stream);
+        tnb_complex_destroy(c);
+        if (rc != TNB_ERR_CAPACITY) break;
+        g_capacity_factor *= 2.0;
+    }
+    g_capacity_factor = factor0;
     return rc;
 }
 
