@@ -56,6 +56,7 @@ typedef struct tnb_net_desc {
 typedef struct tnb_net tnb_net;          /* device-resident network                    */
 typedef struct tnb_complex tnb_complex;  /* device-resident vertices/edges/outputs     */
 typedef struct tnb_mesh tnb_mesh;        /* device-resident extracted surface mesh     */
+typedef struct tnb_sweep tnb_sweep;      /* |sdf| / max |grad| of a marks-grid slab    */
 
 const char *tnb_last_error(void);
 int tnb_version(void);
@@ -147,6 +148,56 @@ int tnb_subpoly(const tnb_net *net, float size, float eps, int32_t force, int32_
  * tnb_mesh_read_host. */
 int tnb_mesh_read_host(const tnb_mesh *m, float *h_vertices, int64_t *h_triangles,
                        float *h_faces, int64_t *h_polygons);
+
+/* ---- slab sharding: ONE object split over several GPUs along the first grid axis ----
+ * Rank r holds the marks-grid planes [x_lo, x_hi] (cells x_lo .. x_hi-1); neighbouring
+ * slabs share one plane.  The reference's path is cell-local except for three decisions
+ * that look at all edges / vertices at once: "nothing crossed -> skip the step"
+ * (subpoly.py:110-111), the failover override (subpoly_debug.py:41-49), and vertex
+ * survival after pruning (subpoly.py:268-272: a vertex on a shared plane has edges on
+ * both sides).  Every hyperplane step and the surface-skeleton extraction therefore end in
+ * one exchange, written by the step's own kernels straight into the peers' mailboxes
+ * (device memory mapped with CUDA IPC over NVLink; plain pointers when the slabs of one
+ * object run on one device).  Planar path only.
+ *
+ * Skeleton of one slab, in two halves: the reference's distance threshold is per chunk
+ * (tropical.py:189-197), so the caller reduces max_grad (MAX over ranks) in between. */
+int tnb_skeleton_sweep(const tnb_net *net, int32_t unit, int32_t x_lo, int32_t x_hi,
+                       int32_t shared_lower, int32_t shared_upper, tnb_sweep **out, void *stream);
+void tnb_sweep_destroy(tnb_sweep *sw);
+int32_t tnb_sweep_num_chunks(const tnb_sweep *sw);
+int tnb_sweep_read_max_grad(const tnb_sweep *sw, float *d_out, void *stream);   /* [n_chunks] */
+int tnb_sweep_write_max_grad(tnb_sweep *sw, const float *d_in, void *stream);
+int tnb_skeleton_finish(const tnb_net *net, tnb_sweep *sw, tnb_complex **out, void *stream);
+/* Mailboxes: `payload` = capacity in shared-plane vertices of one neighbour message. */
+int64_t tnb_mailbox_bytes(int64_t payload);
+int tnb_mailbox_create(int64_t payload, void **out);
+int tnb_mailbox_destroy(void *box);
+int tnb_mailbox_export(void *box, void *handle64);           /* cudaIpcMemHandle_t, 64 bytes */
+int tnb_mailbox_import(const void *handle64, void **out);    /* in another process           */
+int tnb_mailbox_release(void *imported);
+/* boxes[world]: the mailbox of every rank as seen from this process (own one included).
+ * timeout_ms bounds the device-side wait for a peer (<= 0: keep the default, 2 s).  seq0:
+ * exchange numbers of this complex start above seq0; all ranks pass the same value and a
+ * larger one for every new extraction that reuses the mailboxes. */
+int tnb_complex_set_halo(tnb_complex *c, int32_t rank, int32_t world, void *const *boxes,
+                         int64_t payload, int32_t timeout_ms, uint32_t seq0);
+/* tnb_subpoly_step in two halves around the exchange: part 1 = up to and including the send,
+ * part 2 = from the receive on, part 0 = both (one slab per device).  Several slabs on ONE
+ * device: part 1 for every slab, then part 2 for every slab, on one stream. */
+int tnb_subpoly_step_part(const tnb_net *net, tnb_complex *c, int32_t l, int32_t h, float eps,
+                          int32_t force, int32_t part, void *stream);
+/* tnb_extract_mesh in two halves around the exchange of surface-vertex liveness. */
+int tnb_extract_mesh_begin(const tnb_net *net, tnb_complex *c, float eps, tnb_mesh **out, void *stream);
+int tnb_extract_mesh_finish(const tnb_net *net, tnb_complex *c, tnb_mesh *m, void *stream);
+/* per mesh vertex: bit0 / bit1 = lies on the plane shared with the lower / upper neighbour
+ * (what the merge de-duplicates) */
+int tnb_mesh_read_tags(const tnb_mesh *m, uint8_t *d_tags, void *stream);
+/* Exactness indicator of a slab run: vertices of the final complex that lie within eps of a
+ * shared plane (so the reference sees them from both sides) but exist on one slab only.
+ * 0 = the slab mesh equals the single-GPU mesh; otherwise the faces touching those vertices
+ * from the other side can differ. */
+int64_t tnb_mesh_near_plane(const tnb_mesh *m);
 
 /* ---- knobs / introspection ------------------------------------------------------ */
 /* work-buffer growth factor for the complex (default 4.0) */

@@ -44,3 +44,24 @@ def random_net(seed, levels=4, n_min=2, n_max=32, log2_T=19, num_layers=3, num_h
 def canonical_polygons(rows):
     from oracle.subpoly_ref import canonical_polygons as cp
     return cp(rows)
+
+
+def canonical_triangles(vertices, triangles):
+    """Mesh as a sorted multiset of triangles given by their corner POSITION bits (cyclic order
+    kept, rotation normalised): independent of vertex numbering, exact on positions."""
+    v = np.ascontiguousarray(np.asarray(vertices, np.float32)).view(np.int32).astype(np.int64)
+    t = np.asarray(triangles, np.int64)
+    if t.shape[0] == 0:
+        return np.zeros((0, 9), np.int64)
+    p = v[t]                                   # [T,3,3]
+    key = (p[..., 0] << 42) ^ (p[..., 1] << 21) ^ p[..., 2]
+    first = np.argmin(key, axis=1)
+    idx = (first[:, None] + np.arange(3)[None, :]) % 3
+    p = np.take_along_axis(p, idx[:, :, None], axis=1).reshape(-1, 9)
+    order = np.lexsort(p.T[::-1])
+    return p[order]
+
+
+def canonical_vertices(vertices):
+    v = np.ascontiguousarray(np.asarray(vertices, np.float32)).view(np.int32).reshape(-1, 3)
+    return v[np.lexsort(v.T[::-1])]

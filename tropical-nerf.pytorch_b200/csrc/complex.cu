@@ -15,6 +15,7 @@
 
 #include "complex.cuh"
 #include "curve.cuh"
+#include "halo.cuh"
 #include "net_eval.cuh"
 #include "scan.cuh"
 
@@ -29,7 +30,8 @@ constexpr int kThreads = 128;
 //   fewer after strict_check on the curve path)
 //   C_VPAR / C_EPAR = which half of the ping-pong vertex / edge arrays is current,
 //   C_STICKY = error bits that survive steps (sync-free fused path)
-enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_NUM = 16 };
+//   C_KEPT = edges kept by pruning, parked until the slab exchange decides whether the step counts
+enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_NUM = 16 };
 enum { kErrNoPlane = 1, kErrGradientDescent = 2 };
 enum { kStickyCapacity = 1 };
 
@@ -44,6 +46,8 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
         TNB_CUDA(c->out[k].reserve(Vcap * c->R));
         TNB_CUDA(c->sig[k].reserve(Vcap * 3));
         TNB_CUDA(c->edges[k].reserve(Ecap));
+        TNB_CUDA(c->tag[k].reserve(Vcap));
+        TNB_CUDA(cudaMemsetAsync(c->tag[k].p, 0, Vcap, current_stream()));
     }
     TNB_CUDA(c->split_list.reserve(Ecap));
     TNB_CUDA(c->bmask.reserve(Ecap));
@@ -99,6 +103,7 @@ int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
             if ((rc = grow(c->vert[k], nc * 3, keep * 3, s))) return rc;
             if ((rc = grow(c->out[k], nc * c->R, keep * c->R, s))) return rc;
             if ((rc = grow(c->sig[k], nc * 3, keep * 3, s))) return rc;
+            if ((rc = grow(c->tag[k], nc, keep, s))) return rc;
         }
         if ((rc = grow(c->cand, nc, 0, s)) || (rc = grow(c->pcount, nc, 0, s)) || (rc = grow(c->poff, nc, 0, s)) ||
             (rc = grow(c->next, nc * 8, 0, s)) || (rc = grow(c->used, nc, 0, s)) || (rc = grow(c->remap, nc, 0, s)))
@@ -235,13 +240,17 @@ struct SkelVertEmit {
     int M;
     int *remap;
     float *vert;
+    unsigned char *tag;
+    int x0;              // first plane of the slab: item v is grid vertex v + x0*M*M
+    int plane_lo, plane_hi;  // planes shared with a neighbour rank (-1: none)
     __device__ __forceinline__ void operator()(int64_t v, int pos, int) const
     {
         remap[v] = pos;
-        const int k = (int)(v % M), j = (int)((v / M) % M), i = (int)(v / ((int64_t)M * M));
+        const int k = (int)(v % M), j = (int)((v / M) % M), i = (int)(v / ((int64_t)M * M)) + x0;
         vert[3 * pos] = marks[i] * pre_2s - pre_scale;
         vert[3 * pos + 1] = marks[j] * pre_2s - pre_scale;
         vert[3 * pos + 2] = marks[k] * pre_2s - pre_scale;
+        tag[pos] = (unsigned char)((i == plane_lo ? 1 : 0) | (i == plane_hi ? 2 : 0));
     }
 };
 
@@ -287,10 +296,30 @@ static int eval_vertices(const tnb_net *net, tnb_complex *c, int64_t first, int6
     return TNB_OK;
 }
 
-static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaStream_t s)
+}  // namespace tnb
+
+// State between the two halves of the skeleton: the sweep (|sdf|, per-chunk max |grad|) and the
+// edge selection.  A slab-sharded run reduces max_grad over the ranks in between, because the
+// reference's threshold is per CHUNK (tropical.py:189-197), not per slab.
+struct tnb_sweep {
+    int M = 0, unit = 0, n_chunks = 0;
+    int x_lo = 0, x_hi = 0;  // planes of the slab along the first axis (the whole grid: 0, M-1)
+    bool tag_lower = false, tag_upper = false;
+    float k_len = 0.0f;
+    int64_t slots = 0;
+    std::vector<tnb::ChunkSeg> segs;
+    tnb::DevBuf<float> dist;         // [(x_hi-x_lo+1) * M * M], plane x_lo first
+    tnb::DevBuf<unsigned> max_grad;  // [n_chunks] bit patterns of non-negative floats
+};
+
+namespace tnb {
+
+static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag_lower, bool tag_upper, tnb_sweep *sw,
+                      cudaStream_t s)
 {
     const int M = net->meta.n_marks;
     if (unit < 2) { set_error("tnb_skeleton: unit must be >= 2"); return TNB_ERR_INVALID; }
+    if (x_lo < 0 || x_hi >= M || x_lo > x_hi) { set_error("tnb_skeleton_sweep: slab out of range"); return TNB_ERR_INVALID; }
     const int64_t M3 = (int64_t)M * M * M;
     if (M3 > (int64_t)1 << 31) { set_error("tnb_skeleton: marks grid too large"); return TNB_ERR_UNSUPPORTED; }
     // chunks exactly as range(0, L, unit - 1) enumerates them (tropical.py:176-181)
@@ -300,31 +329,35 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
     if ((int64_t)nc * nc * nc * 3 > kMaxSegs) { set_error("tnb_skeleton: too many chunks"); return TNB_ERR_UNSUPPORTED; }
     float len_max = 0.0f;
     for (int i = 0; i + 1 < M; ++i) len_max = std::max(len_max, net->h_marks[i + 1] - net->h_marks[i]);
-    const float k_len = (std::sqrt(3.0f) * 2.0f) * len_max;
-
-    DevBuf<float> dist;
-    DevBuf<unsigned> max_grad;
-    DevBuf<ChunkSeg> d_segs;
-    DevBuf<int> used, remap, block_sums, total;
-    TNB_CUDA(dist.reserve((size_t)M3));
-    TNB_CUDA(max_grad.reserve((size_t)nc * nc * nc));
-    TNB_CUDA(cudaMemsetAsync(max_grad.p, 0, (size_t)nc * nc * nc * sizeof(unsigned), s));
-    std::vector<ChunkSeg> segs;
+    sw->M = M; sw->unit = unit; sw->n_chunks = nc * nc * nc;
+    sw->x_lo = x_lo; sw->x_hi = x_hi; sw->tag_lower = tag_lower; sw->tag_upper = tag_upper;
+    sw->k_len = (std::sqrt(3.0f) * 2.0f) * len_max;
+    const int64_t planes = x_hi - x_lo + 1;
+    TNB_CUDA(sw->dist.reserve((size_t)(planes * M * M)));
+    TNB_CUDA(sw->max_grad.reserve((size_t)sw->n_chunks));
+    TNB_CUDA(cudaMemsetAsync(sw->max_grad.p, 0, (size_t)sw->n_chunks * sizeof(unsigned), s));
+    float *dist0 = sw->dist.p - (int64_t)x_lo * M * M;  // indexed by the global vertex number
     int64_t slots = 0;
     int chunk = 0;
     for (int a = 0; a < nc; ++a)
         for (int b = 0; b < nc; ++b)
             for (int cc = 0; cc < nc; ++cc, ++chunk) {
-                const int st[3] = {starts[a], starts[b], starts[cc]};
+                int st[3] = {starts[a], starts[b], starts[cc]};
                 int nn[3];
                 for (int d = 0; d < 3; ++d) nn[d] = std::min(M, st[d] + unit) - st[d];
+                // the part of the chunk inside the slab (a chunk piece emits every edge whose
+                // two ends lie in the slab, in the chunk's own order)
+                const int lo = std::max(st[0], x_lo), hi = std::min(st[0] + nn[0] - 1, x_hi);
+                if (lo > hi) continue;
+                st[0] = lo;
+                nn[0] = hi - lo + 1;
                 const int64_t count = (int64_t)nn[0] * nn[1] * nn[2];
                 unsigned g = grid_for(count, kThreads);
                 prof_begin(TNB_PROF_SWEEP, s);
                 if (net->fixed_cfg)
-                    k_sweep_chunk<CfgRef><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist.p, max_grad.p + chunk);
+                    k_sweep_chunk<CfgRef><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist0, sw->max_grad.p + chunk);
                 else
-                    k_sweep_chunk<CfgAny><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist.p, max_grad.p + chunk);
+                    k_sweep_chunk<CfgAny><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist0, sw->max_grad.p + chunk);
                 TNB_LAUNCH_CHECK();
                 prof_end(TNB_PROF_SWEEP, s, count, count * 4 + (int64_t)net->table.cap * 8);
                 for (int axis = 0; axis < 3; ++axis) {
@@ -337,26 +370,42 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
                     for (int d = 0; d < 3; ++d) { sg.s[d] = st[d]; sg.n[d] = nn[d]; }
                     sg.axis = axis;
                     sg.chunk = chunk;
-                    segs.push_back(sg);
+                    sw->segs.push_back(sg);
                     slots += cnt;
                 }
             }
+    sw->slots = slots;
+    return TNB_OK;
+}
+
+static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex **out, cudaStream_t s)
+{
+    const int M = sw->M;
+    const std::vector<ChunkSeg> &segs = sw->segs;
+    const int64_t slots = sw->slots;
     tnb_complex *c = new tnb_complex();
     *out = c;
+    c->halo.x_lo = sw->x_lo; c->halo.x_hi = sw->x_hi;
+    c->halo.tag_lower = sw->tag_lower; c->halo.tag_upper = sw->tag_upper;
     if (segs.empty() || slots == 0) {  // degenerate grid: no edges at all
         int rc = complex_alloc(c, net, 64, 64);
         return rc;
     }
+    DevBuf<ChunkSeg> d_segs;
+    DevBuf<int> used, remap, block_sums, total;
+    const int64_t base = (int64_t)sw->x_lo * M * M;              // first global vertex number of the slab
+    const int64_t MS = (int64_t)(sw->x_hi - sw->x_lo + 1) * M * M;  // grid vertices of the slab
+    float *dist0 = sw->dist.p - base;
     TNB_CUDA(d_segs.reserve(segs.size()));
     TNB_CUDA(cudaMemcpyAsync(d_segs.p, segs.data(), segs.size() * sizeof(ChunkSeg), cudaMemcpyHostToDevice, s));
-    TNB_CUDA(used.reserve((size_t)M3));
-    TNB_CUDA(remap.reserve((size_t)M3));
+    TNB_CUDA(used.reserve((size_t)MS));
+    TNB_CUDA(remap.reserve((size_t)MS));
     TNB_CUDA(block_sums.reserve(kScanMaxBlocks));
     TNB_CUDA(total.reserve(2));
-    TNB_CUDA(cudaMemsetAsync(used.p, 0, (size_t)M3 * sizeof(int), s));
+    TNB_CUDA(cudaMemsetAsync(used.p, 0, (size_t)MS * sizeof(int), s));
 
     // pass 1: count surviving edges so the complex can be sized
-    SkelEdgeCount q{d_segs.p, (int)segs.size(), M, dist.p, max_grad.p, k_len};
+    SkelEdgeCount q{d_segs.p, (int)segs.size(), M, dist0, sw->max_grad.p, sw->k_len};
     {
         int64_t blocks = std::min<int64_t>((slots + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
         k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, nullptr, q, block_sums.p);
@@ -370,13 +419,13 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
         // vertices are bounded by 2E; real sizing happens after the vertex pass
         DevBuf<int2> raw;
         TNB_CUDA(raw.reserve((size_t)E));
-        SkelEdgeEmit emit{q, raw.p, used.p};
+        SkelEdgeEmit emit{q, raw.p, used.p - base};
         k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, nullptr, q, emit, block_sums.p, total.p);
         TNB_LAUNCH_CHECK();
         // vertex pass: count, size, then place
         FlagCount fc{used.p};
-        int64_t vblocks = std::min<int64_t>((M3 + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
-        k_scan_count<<<(unsigned)vblocks, kScanThreads, 0, s>>>(M3, nullptr, fc, block_sums.p);
+        int64_t vblocks = std::min<int64_t>((MS + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
+        k_scan_count<<<(unsigned)vblocks, kScanThreads, 0, s>>>(MS, nullptr, fc, block_sums.p);
         TNB_LAUNCH_CHECK();
         std::vector<int> hv(vblocks);
         TNB_CUDA(cudaMemcpyAsync(hv.data(), block_sums.p, vblocks * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -386,11 +435,12 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
         size_t Vcap = (size_t)(V * g_capacity_factor) + 4096, Ecap = (size_t)(E * g_capacity_factor) + 4096;
         int rc = complex_alloc(c, net, Vcap, Ecap);
         if (rc) return rc;
-        SkelVertEmit vemit{nullptr, net->meta.marks, net->meta.pre_2s, net->meta.pre_scale, M, remap.p, c->cvert()};
-        k_scan_write<<<(unsigned)vblocks, kScanThreads, 0, s>>>(M3, nullptr, fc, vemit, block_sums.p, total.p + 1);
+        SkelVertEmit vemit{nullptr, net->meta.marks, net->meta.pre_2s, net->meta.pre_scale, M, remap.p, c->cvert(),
+                           c->tag[c->vcur].p, sw->x_lo, sw->tag_lower ? sw->x_lo : -1, sw->tag_upper ? sw->x_hi : -1};
+        k_scan_write<<<(unsigned)vblocks, kScanThreads, 0, s>>>(MS, nullptr, fc, vemit, block_sums.p, total.p + 1);
         TNB_LAUNCH_CHECK();
         TNB_CUDA(cudaMemcpyAsync(c->cedges(), raw.p, (size_t)E * sizeof(int2), cudaMemcpyDeviceToDevice, s));
-        k_remap_edges<<<grid_for(E, 256), 256, 0, s>>>(c->cedges(), E, remap.p);
+        k_remap_edges<<<grid_for(E, 256), 256, 0, s>>>(c->cedges(), E, remap.p - base);
         TNB_LAUNCH_CHECK();
         c->V = V;
         c->E = E;
@@ -400,6 +450,14 @@ static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaSt
         if (rc) return rc;
     }
     return TNB_OK;
+}
+
+static int skeleton_impl(const tnb_net *net, int unit, tnb_complex **out, cudaStream_t s)
+{
+    tnb_sweep sw;
+    int rc = sweep_impl(net, unit, 0, net->meta.n_marks - 1, false, false, &sw, s);
+    if (rc) return rc;
+    return skeleton_finish_impl(net, &sw, out, s);
 }
 
 // ================================================================================================
@@ -433,7 +491,7 @@ __device__ __forceinline__ void body_new_vertices(const NetMeta &n, int idx, flo
                                                            int Vcap, int Ecap, const int *split_list,
                                                            int2 *edges, float *vert,
                                                            float *out, const uint64_t *sig,
-                                                           uint64_t *bmask, int *cnt)
+                                                           uint64_t *bmask, int *cnt, unsigned char *tag)
 {
     const int R = n.R;
     const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
@@ -465,6 +523,7 @@ __device__ __forceinline__ void body_new_vertices(const NetMeta &n, int idx, flo
             const int col = __ffsll((long long)m) - 1;
             if (fabsf(row[col]) > eps) any = 1;
         }
+        tag[nv] = tag[ed.x] & tag[ed.y];         // on a shared slab plane iff both parents are
         edges[e].y = (int)nv;                    // left part keeps the first endpoint
         edges[E + k] = make_int2(ed.y, (int)nv); // right part
     }
@@ -476,9 +535,10 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant
                                                            int Vcap, int Ecap, const int *__restrict__ split_list,
                                                            int2 *__restrict__ edges, float *__restrict__ vert,
                                                            float *__restrict__ out, const uint64_t *__restrict__ sig,
-                                                           uint64_t *__restrict__ bmask, int *__restrict__ cnt)
+                                                           uint64_t *__restrict__ bmask, int *__restrict__ cnt,
+                                                           unsigned char *__restrict__ tag)
 {
-    body_new_vertices<C>(n, idx, eps, Vcap, Ecap, split_list, edges, vert, out, sig, bmask, cnt);
+    body_new_vertices<C>(n, idx, eps, Vcap, Ecap, split_list, edges, vert, out, sig, bmask, cnt, tag);
 }
 
 // apply the failover override when any new vertex violated it, then bit-pack the region
@@ -632,6 +692,7 @@ struct CurveCommitEmit {
     int R, n_marks;
     float eps, pre_scale, pre_2s, pre_inv;
     int pre_pow2;
+    unsigned char *tag;
     __device__ __forceinline__ void operator()(int64_t k, int rank, int) const
     {
         const int V = cnt[C_V], E = cnt[C_E];
@@ -662,6 +723,7 @@ struct CurveCommitEmit {
         sig[3 * nv + 2] = g;
         const int e = split_list[k];
         const int old = edges[e].y;
+        tag[nv] = tag[edges[e].x] & tag[old];
         edges[e].y = (int)nv;
         edges[E + rank] = make_int2(old, (int)nv);
     }
@@ -921,9 +983,12 @@ struct VertexMoveEmit {  // subpoly.py:268-277: compact vertices, positions, cac
     uint64_t *nsig;
     int *remap;
     int R;
+    const unsigned char *tag;
+    unsigned char *ntag;
     __device__ __forceinline__ void operator()(int64_t v, int pos, int) const
     {
         remap[v] = pos;
+        ntag[pos] = tag[v];
         for (int d = 0; d < 3; ++d) nvert[3 * (int64_t)pos + d] = vert[3 * v + d];
         for (int d = 0; d < 3; ++d) nsig[3 * (int64_t)pos + d] = sig[3 * v + d];
         for (int c = 0; c < R; ++c) nout[(int64_t)pos * R + c] = out[v * R + c];
@@ -982,6 +1047,30 @@ struct StepArgs {
     uint64_t *sig[2], *bmask;
     int *split_list, *cand, *pcount, *poff, *next, *used, *remap, *block_sums, *cnt;
     unsigned long long *head, *bytes;  // bytes[0/1]: algorithmic bytes of the front / back halves
+    unsigned char *tag[2];
+    // slab sharding (halo.cuh): the back half runs in two launches around the exchange
+    int halo, part;                 // part 0: whole back half, 1: up to the exchange, 2: after it
+    int has_lower, has_upper;
+    int *hslot, *stage_count, stage_cap;
+    unsigned char *stage[2];
+    const unsigned char *in[2];     // liveness bytes received from the lower / upper neighbour
+};
+
+struct TagCount {  // vertices on one shared slab plane
+    const unsigned char *tag;
+    int bit;
+    __device__ __forceinline__ int operator()(int64_t v) const { return (tag[v] & bit) ? 1 : 0; }
+};
+struct StageEmit {  // k-th vertex of the plane: remember k, publish its liveness
+    int *slot;
+    unsigned char *stage;
+    const int *used;
+    int cap;  // a longer plane list is reported by the count (k_halo_send poisons the message)
+    __device__ __forceinline__ void operator()(int64_t v, int pos, int) const
+    {
+        slot[v] = pos;
+        if (pos < cap) stage[pos] = used[v] ? 1 : 0;
+    }
 };
 
 template <class C>
@@ -1001,7 +1090,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
     grid.sync();
     scan_write_body(E, sc, ListEmit{a.split_list}, a.block_sums, cnt + C_RAW);
     grid.sync();
-    body_new_vertices<C>(n, a.idx, a.eps, a.Vcap, a.Ecap, a.split_list, edges, vert, out, sig, a.bmask, cnt);
+    body_new_vertices<C>(n, a.idx, a.eps, a.Vcap, a.Ecap, a.split_list, edges, vert, out, sig, a.bmask, cnt, a.tag[pv]);
     const HitCount hc{out, n.R, a.idx, a.eps};  // old vertices only: independent of the new rows
     scan_count_body(V, hc, a.block_sums);
     grid.sync();
@@ -1021,7 +1110,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
             const int S = cnt[C_SPLIT];
             for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) a.cand[Hn + k] = V + k;
             if (blockIdx.x == 0 && threadIdx.x == 0) {
-                cnt[C_CAND] = cnt[C_RAW] ? Hn + S : 0;
+                // a slab cannot know yet whether another slab crossed the plane: it prepares the
+                // hit vertices' connecting edges anyway and the exchange decides (halo.cuh)
+                cnt[C_CAND] = (cnt[C_RAW] || a.halo) ? Hn + S : 0;
                 // split scan (edge + two cached outputs, two passes), hit scan, new vertices, buckets + partner count
                 a.bytes[0] += 2ull * 16 * E + 2ull * 4 * V + (unsigned long long)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * n.R + 8 + 16) +
                               (unsigned long long)(Hn + S) * (24 + 8 + 4 + 24);
@@ -1046,42 +1137,89 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
     const int sticky = cnt[C_STICKY], raw = cnt[C_RAW], overflow = cnt[C_OVERFLOW];
     const int S = cnt[C_SPLIT], P = cnt[C_PAIRS], V0 = cnt[C_V], E0 = cnt[C_E], n_cand = cnt[C_CAND];
     const int pv = cnt[C_VPAR], pe = cnt[C_EPAR];
-    if (sticky || raw == 0) return;  // subpoly.py:110-111: nothing crossed, nothing changes
+    const int local_flag = cnt[C_FLAG];
+    const int word = a.part == 2 ? a.stage_count[2] : 0;  // OR of every slab's status word
+    if (sticky) return;
+    if (!a.halo && raw == 0) return;  // subpoly.py:110-111: nothing crossed, nothing changes
     const int64_t En = (int64_t)E0 + S + P;
     const int Vn = V0 + S;
-    if (overflow || En > a.Ecap) {  // the host re-runs the extraction with larger arrays
-        if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_STICKY] = kStickyCapacity;
-        return;
-    }
     int2 *edges = a.edges[pe], *edges_dst = a.edges[pe ^ 1];
     float *vert = a.vert[pv], *out = a.out[pv];
     uint64_t *sig = a.sig[pv];
-    if (P > 0)
-        body_pair_write(a.cand, n_cand, sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount, a.poff, edges + E0 + S);
-    if (!a.do_prune) {  // the output neuron (subpoly.py:253): sizes only
-        grid.sync();
-        if (blockIdx.x == 0 && threadIdx.x == 0) {
-            cnt[C_V] = Vn;
-            cnt[C_E] = (int)En;
-            a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8;
+    int *kept = a.halo ? cnt + C_KEPT : cnt + C_E;
+    if (a.part != 2) {
+        if (overflow || En > a.Ecap) {  // the host re-runs the extraction with larger arrays
+            if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_STICKY] = kStickyCapacity;
+            return;
         }
-        return;
+        if (P > 0)
+            body_pair_write(a.cand, n_cand, sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount, a.poff, edges + E0 + S);
+        if (!a.do_prune) {  // the output neuron (subpoly.py:253): sizes only
+            if (a.halo) {   // no liveness to exchange, only the status word
+                if (blockIdx.x == 0 && threadIdx.x == 0) a.stage_count[0] = a.stage_count[1] = 0;
+                return;
+            }
+            grid.sync();
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                cnt[C_V] = Vn;
+                cnt[C_E] = (int)En;
+                a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8;
+            }
+            return;
+        }
+        for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += gridDim.x * blockDim.x) a.used[v] = 0;
+        grid.sync();
+        const KeepCount kc{edges, sig, a.futmask};
+        scan_count_body(En, kc, a.block_sums);
+        grid.sync();
+        scan_write_body(En, kc, KeepEmit{edges, edges_dst, a.used}, a.block_sums, kept);
+        grid.sync();
+        if (a.halo) {  // ordered lists of the two shared planes' vertices and their liveness
+            for (int side = 0; side < 2; ++side) {
+                const TagCount tc{a.tag[pv], 1 << side};
+                scan_count_body(Vn, tc, a.block_sums);
+                grid.sync();
+                scan_write_body(Vn, tc, StageEmit{a.hslot, a.stage[side], a.used, a.stage_cap}, a.block_sums, a.stage_count + side);
+                grid.sync();
+            }
+            return;  // k_halo_send / k_halo_recv run between the two launches
+        }
+    } else {
+        if (!(word & kWordRaw)) return;  // no slab crossed the plane: the step changes nothing
+        if ((word & kWordFlag) && !local_flag) {
+            // another slab raised the failover override (subpoly_debug.py:41-49): it applies to the
+            // new vertices here too.  Their masked entries are within eps (else the flag would be
+            // up here as well), so the packed signs stay as they are.
+            for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x)
+                for (uint64_t m = a.bmask[k]; m; m &= m - 1) out[((int64_t)V0 + k) * a.R + __ffsll((long long)m) - 1] = 0.0f;
+        }
+        if (!a.do_prune) {
+            if (blockIdx.x == 0 && threadIdx.x == 0) {
+                cnt[C_V] = Vn;
+                cnt[C_E] = (int)En;
+            }
+            return;
+        }
+        // a vertex on a shared plane lives if an edge on EITHER side of the plane keeps it
+        const unsigned char *tag = a.tag[pv];
+        for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += gridDim.x * blockDim.x) {
+            const int t = tag[v];
+            if ((t & 1) && a.has_lower && a.hslot[v] < a.stage_cap && a.in[0][a.hslot[v]]) a.used[v] = 1;
+            if ((t & 2) && a.has_upper && a.hslot[v] < a.stage_cap && a.in[1][a.hslot[v]]) a.used[v] = 1;
+        }
+        grid.sync();
     }
-    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += gridDim.x * blockDim.x) a.used[v] = 0;
-    grid.sync();
-    const KeepCount kc{edges, sig, a.futmask};
-    scan_count_body(En, kc, a.block_sums);
-    grid.sync();
-    scan_write_body(En, kc, KeepEmit{edges, edges_dst, a.used}, a.block_sums, cnt + C_E);
-    grid.sync();
     const FlagCount fc{a.used};
     scan_count_body(Vn, fc, a.block_sums);
     grid.sync();
-    scan_write_body(Vn, fc, VertexMoveEmit{vert, out, sig, a.vert[pv ^ 1], a.out[pv ^ 1], a.sig[pv ^ 1], a.remap, a.R},
+    scan_write_body(Vn, fc, VertexMoveEmit{vert, out, sig, a.vert[pv ^ 1], a.out[pv ^ 1], a.sig[pv ^ 1], a.remap, a.R,
+                                           a.tag[pv], a.tag[pv ^ 1]},
                     a.block_sums, cnt + C_V);
     grid.sync();
-    body_remap_edges_dev(edges_dst, cnt + C_E, a.remap);
+    body_remap_edges_dev(edges_dst, kept, a.remap);
+    if (a.halo) grid.sync();  // every CTA has read the parked count before it is published
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // flip the ping-pong halves
+        if (a.halo) cnt[C_E] = cnt[C_KEPT];
         cnt[C_VPAR] = pv ^ 1;
         cnt[C_EPAR] = pe ^ 1;
         a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8 + (unsigned long long)En * (8 + 2 * 48) +
@@ -1125,10 +1263,106 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
         set_error("work buffers too small for this complex (capacity factor " + std::to_string(g_capacity_factor) + ")");
         return TNB_ERR_CAPACITY;
     }
+    if (c->h_counters[C_STICKY] & kStickyHaloPayload) {
+        set_error("slab exchange: a shared plane holds more vertices than the mailbox payload");
+        return TNB_ERR_CAPACITY;
+    }
+    if (c->h_counters[C_STICKY] & kStickyHaloTimeout) {
+        set_error("slab exchange: a peer did not answer within the timeout");
+        return TNB_ERR_CUDA;
+    }
+    if (c->h_counters[C_STICKY] & kStickyHaloMismatch) {
+        set_error("slab exchange: the two sides of a shared plane disagree on its vertex count");
+        return TNB_ERR_INVALID;
+    }
+    if (c->h_counters[C_STICKY] & kStickyHaloPeer) {
+        set_error("slab exchange: another slab reported an error");
+        return TNB_ERR_CAPACITY;
+    }
     return TNB_OK;
 }
 
-static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps, bool planar, cudaStream_t s)
+// ---- slab exchange (halo.cuh) ------------------------------------------------------------------
+static long long g_halo_timeout_ns = 2000000000ll;
+
+static HaloArgs halo_args(tnb_complex *c, int word_raw_index, int word_flag_index)
+{
+    tnb_halo &h = c->halo;
+    HaloArgs a;
+    memset(&a, 0, sizeof(a));
+    a.rank = h.rank; a.world = h.world; a.seq = h.seq; a.parity = (int)(h.seq & 1u);
+    a.payload = h.payload;
+    for (int r = 0; r < h.world; ++r) a.boxes[r] = h.boxes[r];
+    a.stage[0] = h.stage[0].p; a.stage[1] = h.stage[1].p;
+    a.stage_count = h.stage_count.p;
+    a.cnt = c->counters.p;
+    a.has[0] = h.tag_lower ? 1 : 0; a.has[1] = h.tag_upper ? 1 : 0;
+    a.word_raw_index = word_raw_index; a.word_flag_index = word_flag_index; a.sticky_index = C_STICKY;
+    a.timeout_ns = g_halo_timeout_ns;
+    return a;
+}
+
+// liveness bytes + status word to the peers (starts a new exchange)
+int halo_send(tnb_complex *c, int word_raw_index, int word_flag_index, cudaStream_t s)
+{
+    c->halo.seq += 1;
+    const HaloArgs a = halo_args(c, word_raw_index, word_flag_index);
+    k_halo_send<<<3, 256, 0, s>>>(a);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+// waits (on the device) for the peers' messages of the current exchange
+int halo_recv(tnb_complex *c, cudaStream_t s)
+{
+    const HaloArgs a = halo_args(c, C_RAW, C_FLAG);
+    k_halo_recv<<<1, 256, 0, s>>>(a);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+const unsigned char *halo_in(const tnb_complex *c, int side)
+{
+    const tnb_halo &h = c->halo;
+    return halo_inbox(h.boxes[h.rank], h.payload, side, (int)(h.seq & 1u)) + kHaloHeader;
+}
+
+__global__ void k_halo_apply(const unsigned char *__restrict__ tag, const int *__restrict__ slot, int V, int cap, int has_lower,
+                             int has_upper, const unsigned char *__restrict__ in0, const unsigned char *__restrict__ in1,
+                             int *__restrict__ used)
+{
+    for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < V; v += gridDim.x * blockDim.x) {
+        const int t = tag[v];
+        if ((t & 1) && has_lower && slot[v] < cap && in0[slot[v]]) used[v] = 1;
+        if ((t & 2) && has_upper && slot[v] < cap && in1[slot[v]]) used[v] = 1;
+    }
+}
+
+// The same exchange for the surface skeleton (faces.cu): liveness of the current complex's
+// shared-plane vertices out, then (halo_merge_used) the neighbours' flags in.
+int halo_publish_used(tnb_complex *c, int64_t V, const int *used, cudaStream_t s)
+{
+    tnb_halo &h = c->halo;
+    int rc;
+    for (int side = 0; side < 2; ++side) {
+        const TagCount tc{c->tag[c->vcur].p, 1 << side};
+        if ((rc = compact(V, tc, StageEmit{h.slot.p, h.stage[side].p, used, (int)h.payload}, c->block_sums.p, h.stage_count.p + side, s)))
+            return rc;
+    }
+    return halo_send(c, C_RAW, C_FLAG, s);
+}
+int halo_merge_used(tnb_complex *c, int64_t V, int *used, cudaStream_t s)
+{
+    int rc = halo_recv(c, s);
+    if (rc) return rc;
+    if (V > 0) {
+        k_halo_apply<<<grid_for(V, 256), 256, 0, s>>>(c->tag[c->vcur].p, c->halo.slot.p, (int)V, (int)c->halo.payload, c->halo.tag_lower,
+                                                      c->halo.tag_upper, halo_in(c, 0), halo_in(c, 1), used);
+        TNB_LAUNCH_CHECK();
+    }
+    return TNB_OK;
+}
+
+// part 0: the whole step; 1: up to and including the send of the slab exchange; 2: from its receive on
+static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps, bool planar, cudaStream_t s, int part = 0)
 {
     const NetMeta &m = net->meta;
     const int H = m.H, R = m.R;
@@ -1137,7 +1371,10 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     int *cnt = c->counters.p;
     int rc;
     // c->V / c->E are upper bounds here when counts_stale (the exact values are in cnt[C_V], cnt[C_E])
-    if (c->E == 0) return TNB_OK;
+    const bool halo = c->halo.enabled;
+    if (c->E == 0 && !halo) return TNB_OK;
+    if (halo && !planar) { set_error("slab-sharded extraction supports the planar path only"); return TNB_ERR_UNSUPPORTED; }
+    if (!halo && part != 0) { set_error("tnb_subpoly_step_part: the complex has no slab exchange configured"); return TNB_ERR_INVALID; }
     const uint64_t colmask = (1ull << idx) - 1ull;
 
     // planar path on small complexes: both halves as one cooperative kernel each, fully
@@ -1153,12 +1390,15 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     // full-size grids (c->V / c->E may be stale upper bounds here: good enough for this choice).
     const int sm_blocks = std::min(kSMs, std::min(front_blocks_ref, back_blocks));
     const int front_blocks = std::min(net->fixed_cfg ? front_blocks_ref : front_blocks_any, sm_blocks);
-    const bool fused = planar && g_fused_steps && front_blocks > 0 && back_blocks > 0 && c->E + c->V <= kFusedMaxItems;
+    const bool fused = planar && front_blocks > 0 && back_blocks > 0 && (halo || (g_fused_steps && c->E + c->V <= kFusedMaxItems));
+    if (halo && !fused) { set_error("slab-sharded extraction needs the cooperative step kernels"); return TNB_ERR_UNSUPPORTED; }
     if (fused) {
-        c->stamp += 1;
-        if (c->stamp == 0) {
-            TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
-            c->stamp = 1;
+        if (part != 2) {
+            c->stamp += 1;
+            if (c->stamp == 0) {
+                TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
+                c->stamp = 1;
+            }
         }
         StepArgs sa;
         memset(&sa, 0, sizeof(sa));
@@ -1172,19 +1412,41 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         sa.bmask = c->bmask.p; sa.split_list = c->split_list.p; sa.cand = c->cand.p; sa.pcount = c->pcount.p;
         sa.poff = c->poff.p; sa.next = c->next.p; sa.used = c->used.p; sa.remap = c->remap.p;
         sa.block_sums = c->block_sums.p; sa.cnt = c->counters.p; sa.head = c->head.p; sa.bytes = c->bytes.p;
+        sa.tag[0] = c->tag[0].p; sa.tag[1] = c->tag[1].p;
+        sa.halo = halo ? 1 : 0;
         void *fparams[] = {(void *)&m, (void *)&sa};
-        prof_begin(TNB_PROF_NEW_VERTICES, s);
-        if (net->fixed_cfg)
-            TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_front<CfgRef>, dim3(front_blocks), dim3(kScanThreads), fparams, 0, s));
-        else
-            TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_front<CfgAny>, dim3(front_blocks), dim3(kScanThreads), fparams, 0, s));
-        count_launch();
-        prof_end(TNB_PROF_NEW_VERTICES, s, 0);
         void *bparams[] = {(void *)&sa};
-        prof_begin(TNB_PROF_PAIRS, s);
-        TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_back, dim3(std::min(back_blocks, sm_blocks)), dim3(kScanThreads), bparams, 0, s));
-        count_launch();
-        prof_end(TNB_PROF_PAIRS, s, 0);
+        const dim3 bgrid(std::min(back_blocks, sm_blocks));
+        if (halo) {
+            sa.has_lower = c->halo.tag_lower; sa.has_upper = c->halo.tag_upper;
+            sa.hslot = c->halo.slot.p; sa.stage_count = c->halo.stage_count.p;
+            sa.stage[0] = c->halo.stage[0].p; sa.stage[1] = c->halo.stage[1].p;
+            sa.stage_cap = (int)c->halo.payload;
+        }
+        if (part != 2) {
+            prof_begin(TNB_PROF_NEW_VERTICES, s);
+            if (net->fixed_cfg)
+                TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_front<CfgRef>, dim3(front_blocks), dim3(kScanThreads), fparams, 0, s));
+            else
+                TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_front<CfgAny>, dim3(front_blocks), dim3(kScanThreads), fparams, 0, s));
+            count_launch();
+            prof_end(TNB_PROF_NEW_VERTICES, s, 0);
+            sa.part = halo ? 1 : 0;
+            prof_begin(TNB_PROF_PAIRS, s);
+            TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_back, bgrid, dim3(kScanThreads), bparams, 0, s));
+            count_launch();
+            prof_end(TNB_PROF_PAIRS, s, 0);
+            if (halo && (rc = halo_send(c, C_RAW, C_FLAG, s))) return rc;
+        }
+        if (halo && part != 1) {
+            if ((rc = halo_recv(c, s))) return rc;
+            sa.part = 2;
+            sa.in[0] = halo_in(c, 0); sa.in[1] = halo_in(c, 1);
+            prof_begin(TNB_PROF_PAIRS, s);
+            TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_step_back, bgrid, dim3(kScanThreads), bparams, 0, s));
+            count_launch();
+            prof_end(TNB_PROF_PAIRS, s, 0);
+        }
         c->counts_stale = true;  // sizes and buffer parity are on the device until the next sync
         return TNB_OK;
     }
@@ -1214,15 +1476,15 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             k_strict_keep<<<g, kThreads, 0, s>>>(R, idx, eps, c->out[o].p, c->bmask.p, c->pcount.p, cnt);
             TNB_LAUNCH_CHECK();
             CurveCommitEmit ce{nullptr, c->split_list.p, c->cedges(), c->vert[o].p, c->out[o].p, c->cvert(), c->cout_(), c->csig(),
-                               m.marks, cnt, R, m.n_marks, m.eps, m.pre_scale, m.pre_2s, m.pre_inv, m.pre_pow2};
+                               m.marks, cnt, R, m.n_marks, m.eps, m.pre_scale, m.pre_2s, m.pre_inv, m.pre_pow2, c->tag[c->vcur].p};
             if ((rc = compact(c->E, KeepFlagCount{c->pcount.p, cnt + C_OVERFLOW}, ce, c->block_sums.p, cnt + C_SPLIT, s, cnt + C_RAW))) return rc;
         } else {
             unsigned g = grid_for(c->E, kThreads);
             prof_begin(TNB_PROF_NEW_VERTICES, s);
             if (net->fixed_cfg)
-                k_new_vertices<CfgRef><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
+                k_new_vertices<CfgRef><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt, c->tag[c->vcur].p);
             else
-                k_new_vertices<CfgAny><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
+                k_new_vertices<CfgAny><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt, c->tag[c->vcur].p);
             TNB_LAUNCH_CHECK();
             prof_end(TNB_PROF_NEW_VERTICES, s, 0);
             k_finalize_new<<<g, kThreads, 0, s>>>(m, c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
@@ -1297,7 +1559,8 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         int2 *dst = c->edges[c->ecur ^ 1].p;
         if ((rc = compact(c->E, kc, KeepEmit{c->cedges(), dst, c->used.p}, c->block_sums.p, cnt + C_E, s))) return rc;
         const int o = c->vcur ^ 1;
-        VertexMoveEmit vm{c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->sig[o].p, c->remap.p, R};
+        VertexMoveEmit vm{c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->sig[o].p, c->remap.p, R,
+                          c->tag[c->vcur].p, c->tag[o].p};
         if ((rc = compact(c->V, FlagCount{c->used.p}, vm, c->block_sums.p, cnt + C_V, s))) return rc;
         c->ecur ^= 1;
         c->vcur = o;
@@ -1400,6 +1663,115 @@ int tnb_skeleton(const tnb_net *net, int32_t unit, float size, tnb_complex **out
     c->stream = s;
     *out = c;
     return TNB_OK;
+}
+
+// ---- slab-sharded skeleton: sweep | (max_grad reduced over the ranks by the caller) | edges ----------
+int tnb_skeleton_sweep(const tnb_net *net, int32_t unit, int32_t x_lo, int32_t x_hi, int32_t shared_lower,
+                       int32_t shared_upper, tnb_sweep **out, void *stream)
+{
+    if (!net || !out) { set_error("tnb_skeleton_sweep: null argument"); return TNB_ERR_INVALID; }
+    *out = nullptr;
+    if ((shared_lower || shared_upper) && x_hi <= x_lo) { set_error("tnb_skeleton_sweep: a shared slab needs at least one cell"); return TNB_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    current_stream() = s;
+    tnb_sweep *sw = new tnb_sweep();
+    int rc = sweep_impl(net, unit, x_lo, x_hi, shared_lower != 0, shared_upper != 0, sw, s);
+    if (rc != TNB_OK) { delete sw; return rc; }
+    *out = sw;
+    return TNB_OK;
+}
+void tnb_sweep_destroy(tnb_sweep *sw) { delete sw; }
+int32_t tnb_sweep_num_chunks(const tnb_sweep *sw) { return sw ? sw->n_chunks : 0; }
+int tnb_sweep_read_max_grad(const tnb_sweep *sw, float *d_out, void *stream)
+{
+    if (!sw || !d_out) { set_error("tnb_sweep_read_max_grad: null argument"); return TNB_ERR_INVALID; }
+    TNB_CUDA(cudaMemcpyAsync(d_out, sw->max_grad.p, (size_t)sw->n_chunks * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TNB_OK;
+}
+int tnb_sweep_write_max_grad(tnb_sweep *sw, const float *d_in, void *stream)
+{
+    if (!sw || !d_in) { set_error("tnb_sweep_write_max_grad: null argument"); return TNB_ERR_INVALID; }
+    TNB_CUDA(cudaMemcpyAsync(sw->max_grad.p, d_in, (size_t)sw->n_chunks * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TNB_OK;
+}
+int tnb_skeleton_finish(const tnb_net *net, tnb_sweep *sw, tnb_complex **out, void *stream)
+{
+    if (!net || !sw || !out) { set_error("tnb_skeleton_finish: null argument"); return TNB_ERR_INVALID; }
+    *out = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    current_stream() = s;
+    tnb_complex *c = nullptr;
+    int rc = skeleton_finish_impl(net, sw, &c, s);
+    if (rc != TNB_OK) { delete c; return rc; }
+    c->stream = s;
+    *out = c;
+    return TNB_OK;
+}
+
+// ---- mailboxes of the slab exchange (plain cudaMalloc: exportable over CUDA IPC) ------------------------
+int64_t tnb_mailbox_bytes(int64_t payload) { return (int64_t)halo_box_bytes((size_t)payload); }
+int tnb_mailbox_create(int64_t payload, void **out)
+{
+    if (!out || payload < 16) { set_error("tnb_mailbox_create: bad argument"); return TNB_ERR_INVALID; }
+    void *p = nullptr;
+    TNB_CUDA(cudaMalloc(&p, halo_box_bytes((size_t)payload)));
+    TNB_CUDA(cudaMemset(p, 0, halo_box_bytes((size_t)payload)));
+    *out = p;
+    return TNB_OK;
+}
+int tnb_mailbox_destroy(void *box) { TNB_CUDA(cudaFree(box)); return TNB_OK; }
+int tnb_mailbox_export(void *box, void *handle64)
+{
+    if (!box || !handle64) { set_error("tnb_mailbox_export: null argument"); return TNB_ERR_INVALID; }
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    cudaIpcMemHandle_t h;
+    TNB_CUDA(cudaIpcGetMemHandle(&h, box));
+    memcpy(handle64, &h, 64);
+    return TNB_OK;
+}
+int tnb_mailbox_import(const void *handle64, void **out)
+{
+    if (!handle64 || !out) { set_error("tnb_mailbox_import: null argument"); return TNB_ERR_INVALID; }
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, 64);
+    TNB_CUDA(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return TNB_OK;
+}
+int tnb_mailbox_release(void *imported) { TNB_CUDA(cudaIpcCloseMemHandle(imported)); return TNB_OK; }
+
+int tnb_complex_set_halo(tnb_complex *c, int32_t rank, int32_t world, void *const *boxes, int64_t payload, int32_t timeout_ms,
+                         uint32_t seq0)
+{
+    if (!c || !boxes || world < 1 || world > kHaloMaxWorld || rank < 0 || rank >= world || payload < 16) {
+        set_error("tnb_complex_set_halo: bad argument");
+        return TNB_ERR_INVALID;
+    }
+    tnb_halo &h = c->halo;
+    if (h.tag_lower && rank == 0) { set_error("tnb_complex_set_halo: rank 0 has no lower neighbour"); return TNB_ERR_INVALID; }
+    if (h.tag_upper && rank == world - 1) { set_error("tnb_complex_set_halo: the last rank has no upper neighbour"); return TNB_ERR_INVALID; }
+    current_stream() = c->stream;
+    h.rank = rank; h.world = world; h.payload = (size_t)payload; h.seq = seq0;
+    for (int r = 0; r < world; ++r) {
+        if (!boxes[r]) { set_error("tnb_complex_set_halo: null mailbox"); return TNB_ERR_INVALID; }
+        h.boxes[r] = (unsigned char *)boxes[r];
+    }
+    TNB_CUDA(h.slot.reserve(c->Vcap));
+    TNB_CUDA(h.stage[0].reserve((size_t)payload));
+    TNB_CUDA(h.stage[1].reserve((size_t)payload));
+    TNB_CUDA(h.stage_count.reserve(4));
+    TNB_CUDA(cudaMemsetAsync(h.stage_count.p, 0, 4 * sizeof(int), c->stream));
+    if (timeout_ms > 0) g_halo_timeout_ns = (long long)timeout_ms * 1000000ll;
+    h.enabled = true;
+    return TNB_OK;
+}
+
+int tnb_subpoly_step_part(const tnb_net *net, tnb_complex *c, int32_t l, int32_t h, float eps, int32_t force, int32_t part,
+                          void *stream)
+{
+    if (!net || !c || part < 0 || part > 2) { set_error("tnb_subpoly_step_part: bad argument"); return TNB_ERR_INVALID; }
+    current_stream() = (cudaStream_t)stream;
+    c->stream = (cudaStream_t)stream;
+    return step_impl(net, c, l, h, eps, force != 0, (cudaStream_t)stream, part);
 }
 
 int tnb_complex_from_arrays(const tnb_net *net, const float *d_vertices, int64_t V, const int64_t *d_edges, int64_t E,

@@ -9,6 +9,24 @@
 //   edges [E]    int2  vertex pair (first, second) in the reference's column order
 // Vertex arrays and the edge array are double-buffered: pruning compacts from one set
 // into the other (order preserving) and flips.
+// Slab sharding (one object split over several GPUs along the first grid axis): the complex of
+// one rank holds the cells [x_lo, x_hi-1]; the planes x_lo / x_hi are shared with the neighbours.
+// What crosses a shared plane is exchanged once per hyperplane step through peer-mapped
+// mailboxes (see halo.cuh): the liveness of the plane's vertices (neighbours) and one status
+// word (all ranks).
+struct tnb_halo {
+    bool enabled = false;
+    int rank = 0, world = 1;
+    int x_lo = -1, x_hi = -1;        // marks-grid plane numbers bounding the slab (inclusive)
+    bool tag_lower = false, tag_upper = false;  // a neighbour exists below / above
+    unsigned char *boxes[64] = {};   // mailbox base pointer of every rank (own one included)
+    size_t payload = 0;              // bytes of one neighbour message
+    uint32_t seq = 0;                // exchange number (both parities of the mailboxes alternate)
+    tnb::DevBuf<int> slot;           // [Vcap] position of a tagged vertex in its plane list
+    tnb::DevBuf<unsigned char> stage[2];  // [payload] outgoing liveness bytes (lower, upper)
+    tnb::DevBuf<int> stage_count;    // [4] plane vertices (lower, upper), exchange status word, spare
+};
+
 struct tnb_complex {
     int R = 0;
     int64_t V = 0, E = 0;
@@ -17,6 +35,8 @@ struct tnb_complex {
     tnb::DevBuf<float> vert[2], out[2];
     tnb::DevBuf<uint64_t> sig[2];
     tnb::DevBuf<int2> edges[2];
+    tnb::DevBuf<unsigned char> tag[2];  // [Vcap] lineage on a shared slab plane: bit0 lower, bit1 upper
+    tnb_halo halo;
     // scratch
     tnb::DevBuf<int> split_list;    // [Ecap]   edge numbers being split
     tnb::DevBuf<uint64_t> bmask;    // [Ecap]   override mask of each new vertex
@@ -56,5 +76,8 @@ int launch_outputs(const tnb_net *net, const float *d_x, int64_t n, float *d_out
 int launch_sdf_grad(const tnb_net *net, const float *d_x, int64_t n, float *d_sdf, float *d_grad, cudaStream_t s);
 int launch_region(const tnb_net *net, const float *d_x, const float *d_outputs, int64_t n, float eps,
                   int8_t *d_signs, int32_t *d_offset, uint64_t *d_packed, cudaStream_t s);
+// slab exchange of vertex liveness (complex.cu, halo.cuh)
+int halo_publish_used(tnb_complex *c, int64_t V, const int *used, cudaStream_t s);
+int halo_merge_used(tnb_complex *c, int64_t V, int *used, cudaStream_t s);
 extern double g_capacity_factor;
 }  // namespace tnb

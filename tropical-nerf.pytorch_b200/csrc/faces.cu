@@ -26,6 +26,13 @@ struct tnb_mesh {
     tnb::DevBuf<int> poly;     // [P][W] angle-sorted rows, -1 padded
     tnb::DevBuf<int> pcnt;     // [P]
     tnb::DevBuf<int> tri;      // [T][3]
+    tnb::DevBuf<unsigned char> tag;  // [V] slab sharding: bit0 / bit1 = on the plane shared with the lower / upper neighbour
+    // between tnb_extract_mesh_begin and _finish (the slab exchange of vertex liveness sits in between)
+    tnb::DevBuf<int> surf, used, counters;
+    tnb::DevBuf<int2> tmp_edges;
+    float eps = 0.0f;
+    bool begun = false;
+    int64_t near_plane = 0;  // slab sharding: vertices within eps of a shared plane that only one slab holds
 };
 
 namespace tnb {
@@ -34,7 +41,7 @@ constexpr int kThreads = 128;
 constexpr int kMaxRow = 8192;      // hard limit of vertices per face row (sizes the HBM row scratch)
 constexpr int kSmemRowStride = 64;  // rows up to this length are built in shared memory (64 KB per CTA)
 constexpr int kMaxZeros = 5;  // 2^5 regions = one per lane
-enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NUM = 16 };
+enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_NUM = 16 };
 
 // ---- surface skeleton -----------------------------------------------------------------------------
 __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
@@ -53,6 +60,25 @@ __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *
     }
     local = warp_sum(local);
     if ((threadIdx.x & 31) == 0 && local) atomicAdd(counters + F_SURF, local);
+}
+
+// Slab sharding is exact as long as every vertex the reference treats as lying ON a shared plane
+// (|x - mark| <= eps, tropical.py:227-236) really was created in that plane, because only those
+// exist on both slabs.  A vertex strictly inside one slab but within eps of the plane is seen by
+// the reference from the cells on both sides; the neighbour slab does not have it.  They are
+// counted here so that a run can say whether it was exact.
+__global__ void k_count_near_plane(const uint64_t *__restrict__ sig, const unsigned char *__restrict__ tag, int64_t V,
+                                   int plane_lo, int plane_hi, int *__restrict__ counters)
+{
+    int local = 0;
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+        const uint64_t g = sig[3 * v + 2];
+        if (grid_mask(g, 0)) continue;
+        const int off = grid_off(g, 0), t = tag[v];
+        if ((off == plane_lo && !(t & 1)) || (off == plane_hi && !(t & 2))) ++local;
+    }
+    local = warp_sum(local);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(counters + F_NEAR, local);
 }
 
 struct SurfEdgeCount {
@@ -81,9 +107,12 @@ struct SurfVertEmit {
     float *nvert, *nout;
     int *remap;
     int R;
+    const unsigned char *tag;
+    unsigned char *ntag;
     __device__ __forceinline__ void operator()(int64_t v, int pos, int) const
     {
         remap[v] = pos;
+        ntag[pos] = tag[v];
         for (int d = 0; d < 3; ++d) nvert[3 * (int64_t)pos + d] = vert[3 * v + d];
         for (int c = 0; c < R; ++c) nout[(int64_t)pos * R + c] = out[v * R + c];
     }
@@ -173,7 +202,8 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                                                           unsigned long long *__restrict__ scratch,
                                                           int *__restrict__ rows_per_vertex,
                                                           const int *__restrict__ row_off, int *__restrict__ rows,
-                                                          int *__restrict__ row_cnt, int W, int *__restrict__ counters)
+                                                          int *__restrict__ row_cnt, int W, int *__restrict__ counters,
+                                                          int cell_lo, int cell_hi)
 {
     extern __shared__ unsigned long long s_rows[];  // [kThreads][stride] unless scratch is used
     __shared__ int s_cnt[kThreads];
@@ -203,12 +233,14 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
             uint64_t pat = pa & colmask;
             for (uint64_t m = za; m; m &= m - 1, ++t)
                 if ((lane >> t) & 1) pat |= m & (~m + 1);
+            // slab sharding: regions of cells that belong to a neighbour slab are emitted there
+            const bool mine_cell = cell[0] >= cell_lo && cell[0] <= cell_hi;
             // collect the region's vertices ordered by (zero count, vertex number): the row
             // order r_idx_as_tensor builds from regions_to_vertices' group-by-zero-count output
             const unsigned long long h = head[cell_of(cell[0], cell[1], cell[2], dim)];
             const unsigned long long my_key = ((unsigned long long)ka << 32) | (unsigned)a;
             bool led_by_other = false;
-            if ((uint32_t)(h >> 32) == stamp) {
+            if (mine_cell && (uint32_t)(h >> 32) == stamp) {
                 for (int rec = (int)(uint32_t)h; rec >= 0; rec = next[rec]) {
                     const int b = rec >> 3;
                     const uint64_t pb = sig[3 * (int64_t)b], nb = sig[3 * (int64_t)b + 1], gb = sig[3 * (int64_t)b + 2];
@@ -475,37 +507,67 @@ static int read_small(const int *d, int *h, int n, cudaStream_t s)
     return TNB_OK;
 }
 
-static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb_mesh *m, cudaStream_t s)
+// extract_skeleton up to the liveness flags of the surface vertices (subpoly.py:556-572); a
+// slab-sharded run publishes the flags of its shared-plane vertices here
+static int extract_begin_impl(const tnb_net *net, tnb_complex *c, float eps, tnb_mesh *m, cudaStream_t s)
 {
     const NetMeta &nm = net->meta;
-    const int R = nm.R;
     {
-        int rcs = complex_sync_counts(const_cast<tnb_complex *>(c), s);
+        int rcs = complex_sync_counts(c, s);
         if (rcs) return rcs;
     }
     const int64_t V = c->V, E = c->E;
-    if (V == 0) return TNB_OK;
-    DevBuf<int> surf, used, remap, block_sums, counters;
+    m->eps = eps;
+    m->begun = true;
+    int rc;
+    TNB_CUDA(m->surf.reserve((size_t)std::max<int64_t>(V, 1)));
+    TNB_CUDA(m->used.reserve((size_t)std::max<int64_t>(V, 1)));
+    TNB_CUDA(m->counters.reserve(F_NUM));
+    TNB_CUDA(cudaMemsetAsync(m->counters.p, 0, F_NUM * sizeof(int), s));
+    TNB_CUDA(cudaMemsetAsync(m->used.p, 0, (size_t)std::max<int64_t>(V, 1) * sizeof(int), s));
+    TNB_CUDA(m->tmp_edges.reserve((size_t)std::max<int64_t>(E, 1)));
+    if (V > 0) {
+        k_surface_flags<<<grid_for(V, 256), 256, 0, s>>>(nm, c->cvert(), c->cout_(), V, eps, m->surf.p, m->counters.p);
+        TNB_LAUNCH_CHECK();
+        DevBuf<int> block_sums;
+        TNB_CUDA(block_sums.reserve(kScanMaxBlocks));
+        if ((rc = compact(E, SurfEdgeCount{c->cedges(), m->surf.p}, SurfEdgeEmit{c->cedges(), m->tmp_edges.p, m->used.p},
+                          block_sums.p, m->counters.p + F_EDGES, s)))
+            return rc;
+    }
+    if (c->halo.enabled && V > 0) {
+        k_count_near_plane<<<grid_for(V, 256), 256, 0, s>>>(c->csig(), c->tag[c->vcur].p, V, c->halo.tag_lower ? c->halo.x_lo : -7,
+                                                            c->halo.tag_upper ? c->halo.x_hi : -7, m->counters.p);
+        TNB_LAUNCH_CHECK();
+    }
+    if (c->halo.enabled && (rc = halo_publish_used(c, V, m->used.p, s))) return rc;
+    return TNB_OK;
+}
+
+static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, cudaStream_t s)
+{
+    const NetMeta &nm = net->meta;
+    const int R = nm.R;
+    const float eps = m->eps;
+    const int64_t V = c->V, E = c->E;
+    (void)E;
     int h[F_NUM];
     int rc;
-    TNB_CUDA(surf.reserve((size_t)V));
-    TNB_CUDA(used.reserve((size_t)V));
+    const bool halo = c->halo.enabled;
+    if (halo) {
+        if ((rc = halo_merge_used(c, V, m->used.p, s))) return rc;
+        c->counts_stale = true;  // re-read the sticky bits the exchange may have raised
+        if ((rc = complex_sync_counts(c, s))) return rc;
+    }
+    if (V == 0) return TNB_OK;
+    DevBuf<int> remap, block_sums;
+    DevBuf<int> &used = m->used, &counters = m->counters;
+    DevBuf<int2> &tmp_edges = m->tmp_edges;
     TNB_CUDA(remap.reserve((size_t)V));
     TNB_CUDA(block_sums.reserve(kScanMaxBlocks));
-    TNB_CUDA(counters.reserve(F_NUM));
-    TNB_CUDA(cudaMemsetAsync(counters.p, 0, F_NUM * sizeof(int), s));
-    TNB_CUDA(cudaMemsetAsync(used.p, 0, (size_t)V * sizeof(int), s));
-
-    // ---- extract_skeleton ----
-    k_surface_flags<<<grid_for(V, 256), 256, 0, s>>>(nm, c->cvert(), c->cout_(), V, eps, surf.p, counters.p);
-    TNB_LAUNCH_CHECK();
-    DevBuf<int2> tmp_edges;
-    TNB_CUDA(tmp_edges.reserve((size_t)std::max<int64_t>(E, 1)));
-    if ((rc = compact(E, SurfEdgeCount{c->cedges(), surf.p}, SurfEdgeEmit{c->cedges(), tmp_edges.p, used.p},
-                      block_sums.p, counters.p + F_EDGES, s)))
-        return rc;
     if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
-    if (h[F_SURF] < 3) return TNB_OK;  // subpoly.py:568-569
+    m->near_plane = h[F_NEAR];
+    if (h[F_SURF] < 3 && !halo) return TNB_OK;  // subpoly.py:568-569
     const int64_t Es = h[F_EDGES];
     // vertex compaction: count first to size the mesh
     {
@@ -520,8 +582,9 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
         m->E = Es;
         TNB_CUDA(m->vert.reserve((size_t)std::max<int64_t>(Vs, 1) * 3));
         TNB_CUDA(m->out.reserve((size_t)std::max<int64_t>(Vs, 1) * R));
+        TNB_CUDA(m->tag.reserve((size_t)std::max<int64_t>(Vs, 1)));
         TNB_CUDA(m->edges.reserve((size_t)std::max<int64_t>(Es, 1)));
-        SurfVertEmit ve{c->cvert(), c->cout_(), m->vert.p, m->out.p, remap.p, R};
+        SurfVertEmit ve{c->cvert(), c->cout_(), m->vert.p, m->out.p, remap.p, R, c->tag[c->vcur].p, m->tag.p};
         k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, nullptr, FlagCount{used.p}, ve, block_sums.p, counters.p + F_VERTS);
         TNB_LAUNCH_CHECK();
     }
@@ -530,6 +593,9 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
         k_remap_edges2<<<grid_for(Es, 256), 256, 0, s>>>(m->edges.p, Es, remap.p);
         TNB_LAUNCH_CHECK();
     }
+    // cells of this slab along the first axis (all of them without slab sharding)
+    const int cell_lo = c->halo.tag_lower ? c->halo.x_lo : -(1 << 30);
+    const int cell_hi = c->halo.tag_upper ? c->halo.x_hi - 1 : (1 << 30);
     const int64_t Vs = m->V;
     if (Vs == 0) return TNB_OK;
 
@@ -566,7 +632,7 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
         prof_begin(TNB_PROF_FACE_ROWS, s);
         k_region_rows<<<gw, kThreads, scratch.p ? 0 : rows_smem, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 0, stride,
                                                                        scratch.p, rows_per_vertex.p, nullptr, nullptr, nullptr, 0,
-                                                                       counters.p);
+                                                                       counters.p, cell_lo, cell_hi);
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_FACE_ROWS, s, Vs, Vs * 28);
         if ((rc = compact(Vs, ArrayCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
@@ -591,7 +657,7 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
     TNB_CUDA(m->poly.reserve((size_t)P * W));
     TNB_CUDA(m->pcnt.reserve((size_t)P));
     k_region_rows<<<gw, kThreads, scratch.p ? 0 : rows_smem, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 1, stride, scratch.p,
-                                                                   rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p);
+                                                                   rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi);
     TNB_LAUNCH_CHECK();
     {
         unsigned g = grid_for(P, kThreads);
@@ -628,6 +694,12 @@ static int extract_impl(const tnb_net *net, const tnb_complex *c, float eps, tnb
     return TNB_OK;  // locals are released in stream order
 }
 
+static void extract_release_scratch(tnb_mesh *m)
+{
+    m->surf.release(); m->used.release(); m->counters.release(); m->tmp_edges.release();
+    m->begun = false;
+}
+
 // ---- read back -------------------------------------------------------------------------------------
 __global__ void k_i32_to_i64(const int *__restrict__ src, int64_t n, int64_t *__restrict__ dst)
 {
@@ -654,9 +726,39 @@ int tnb_extract_mesh(const tnb_net *net, const tnb_complex *c, float eps, tnb_me
     if (!net || !c || !out) { set_error("tnb_extract_mesh: null argument"); return TNB_ERR_INVALID; }
     current_stream() = (cudaStream_t)stream;
     tnb_mesh *m = new tnb_mesh();
-    int rc = extract_impl(net, c, eps, m, (cudaStream_t)stream);
+    tnb_complex *cc = const_cast<tnb_complex *>(c);
+    int rc = extract_begin_impl(net, cc, eps, m, (cudaStream_t)stream);
+    if (rc == TNB_OK) rc = extract_finish_impl(net, cc, m, (cudaStream_t)stream);
+    extract_release_scratch(m);
     if (rc != TNB_OK) { delete m; *out = nullptr; return rc; }
     *out = m;
+    return TNB_OK;
+}
+
+// The two halves separately: a driver that runs several slabs of one object on ONE device
+// calls _begin for every slab before _finish for any (the exchange sits in between).
+int tnb_extract_mesh_begin(const tnb_net *net, tnb_complex *c, float eps, tnb_mesh **out, void *stream)
+{
+    if (!net || !c || !out) { set_error("tnb_extract_mesh_begin: null argument"); return TNB_ERR_INVALID; }
+    current_stream() = (cudaStream_t)stream;
+    tnb_mesh *m = new tnb_mesh();
+    int rc = extract_begin_impl(net, c, eps, m, (cudaStream_t)stream);
+    if (rc != TNB_OK) { delete m; *out = nullptr; return rc; }
+    *out = m;
+    return TNB_OK;
+}
+int tnb_extract_mesh_finish(const tnb_net *net, tnb_complex *c, tnb_mesh *m, void *stream)
+{
+    if (!net || !c || !m || !m->begun) { set_error("tnb_extract_mesh_finish: bad argument"); return TNB_ERR_INVALID; }
+    current_stream() = (cudaStream_t)stream;
+    int rc = extract_finish_impl(net, c, m, (cudaStream_t)stream);
+    extract_release_scratch(m);
+    return rc;
+}
+int tnb_mesh_read_tags(const tnb_mesh *m, uint8_t *d_tags, void *stream)
+{
+    if (!m || !d_tags) { set_error("tnb_mesh_read_tags: null argument"); return TNB_ERR_INVALID; }
+    if (m->V) TNB_CUDA(cudaMemcpyAsync(d_tags, m->tag.p, (size_t)m->V, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return TNB_OK;
 }
 
@@ -666,6 +768,7 @@ int64_t tnb_mesh_num_edges(const tnb_mesh *m) { return m ? m->E : 0; }
 int64_t tnb_mesh_num_triangles(const tnb_mesh *m) { return m ? m->T : 0; }
 int64_t tnb_mesh_num_polygons(const tnb_mesh *m) { return m ? m->P : 0; }
 int64_t tnb_mesh_polygon_width(const tnb_mesh *m) { return m ? m->W : 0; }
+int64_t tnb_mesh_near_plane(const tnb_mesh *m) { return m ? m->near_plane : 0; }
 
 int tnb_mesh_read(const tnb_mesh *m, float *d_vertices, int64_t *d_edges, int64_t *d_triangles, float *d_faces,
                   int64_t *d_polygons, void *stream)

@@ -73,6 +73,24 @@ SIGNATURES = {
     "tnb_subpoly": (ctypes.c_int, [_P, _F, _F, _I32, _I32, ctypes.POINTER(_P), _P]),
     "tnb_mesh_read_host": (ctypes.c_int, [_P, _P, _P, _P, _P]),
     "tnb_set_capacity_factor": (ctypes.c_int, [ctypes.c_double]),
+    "tnb_skeleton_sweep": (ctypes.c_int, [_P, _I32, _I32, _I32, _I32, _I32, ctypes.POINTER(_P), _P]),
+    "tnb_sweep_destroy": (None, [_P]),
+    "tnb_sweep_num_chunks": (_I32, [_P]),
+    "tnb_sweep_read_max_grad": (ctypes.c_int, [_P, _P, _P]),
+    "tnb_sweep_write_max_grad": (ctypes.c_int, [_P, _P, _P]),
+    "tnb_skeleton_finish": (ctypes.c_int, [_P, _P, ctypes.POINTER(_P), _P]),
+    "tnb_mailbox_bytes": (_I64, [_I64]),
+    "tnb_mailbox_create": (ctypes.c_int, [_I64, ctypes.POINTER(_P)]),
+    "tnb_mailbox_destroy": (ctypes.c_int, [_P]),
+    "tnb_mailbox_export": (ctypes.c_int, [_P, _P]),
+    "tnb_mailbox_import": (ctypes.c_int, [_P, ctypes.POINTER(_P)]),
+    "tnb_mailbox_release": (ctypes.c_int, [_P]),
+    "tnb_complex_set_halo": (ctypes.c_int, [_P, _I32, _I32, ctypes.POINTER(_P), _I64, _I32, ctypes.c_uint32]),
+    "tnb_subpoly_step_part": (ctypes.c_int, [_P, _P, _I32, _I32, _F, _I32, _I32, _P]),
+    "tnb_extract_mesh_begin": (ctypes.c_int, [_P, _P, _F, ctypes.POINTER(_P), _P]),
+    "tnb_extract_mesh_finish": (ctypes.c_int, [_P, _P, _P, _P]),
+    "tnb_mesh_read_tags": (ctypes.c_int, [_P, _P, _P]),
+    "tnb_mesh_near_plane": (_I64, [_P]),
     "tnb_launch_count": (_I64, []),
     "tnb_launch_count_reset": (None, []),
     "tnb_profile_enable": (ctypes.c_int, [ctypes.c_int]),
@@ -240,12 +258,75 @@ class NativeNet:
                                             edges.shape[0], ctypes.byref(h), _stream()))
         return NativeComplex(self, h)
 
+    def skeleton_sweep(self, x_lo, x_hi, shared_lower, shared_upper, unit=128):
+        """First half of the skeleton of the slab of marks-grid planes [x_lo, x_hi]."""
+        h = ctypes.c_void_p()
+        check(lib().tnb_skeleton_sweep(self.handle, int(unit), int(x_lo), int(x_hi), int(bool(shared_lower)),
+                                       int(bool(shared_upper)), ctypes.byref(h), _stream()))
+        return NativeSweep(self, h)
+
     def subpoly(self, size=1.2, eps=1e-4, force=True, unit=128):
         """The whole path (tnb_subpoly); returns a NativeMesh."""
         h = ctypes.c_void_p()
         check(lib().tnb_subpoly(self.handle, float(size), float(eps), int(bool(force)), int(unit),
                                 ctypes.byref(h), _stream()))
         return NativeMesh(self, h)
+
+
+class NativeSweep:
+    """|sdf| and per-chunk max |grad| of one marks-grid slab (tnb_sweep)."""
+
+    def __init__(self, net, handle):
+        self.net, self.handle = net, handle
+        self.n_chunks = int(lib().tnb_sweep_num_chunks(handle))
+
+    def __del__(self):
+        h, self.handle = getattr(self, "handle", None), None
+        if h and _lib is not None:
+            _lib.tnb_sweep_destroy(h)
+
+    def max_grad(self):
+        out = torch.empty(self.n_chunks, dtype=torch.float32, device="cuda")
+        check(lib().tnb_sweep_read_max_grad(self.handle, _ptr(out), _stream()))
+        return out
+
+    def set_max_grad(self, t):
+        t = t.contiguous().float()
+        assert t.numel() == self.n_chunks
+        check(lib().tnb_sweep_write_max_grad(self.handle, _ptr(t), _stream()))
+
+    def finish(self):
+        h = ctypes.c_void_p()
+        check(lib().tnb_skeleton_finish(self.net.handle, self.handle, ctypes.byref(h), _stream()))
+        return NativeComplex(self.net, h)
+
+
+class Mailbox:
+    """Device memory the slab exchange writes into (tnb_mailbox_*): created here, or mapped
+    from another process through its 64-byte CUDA IPC handle."""
+
+    def __init__(self, payload=None, handle=None):
+        self.owned = handle is None
+        p = ctypes.c_void_p()
+        if self.owned:
+            check(lib().tnb_mailbox_create(int(payload), ctypes.byref(p)))
+        else:
+            buf = ctypes.create_string_buffer(bytes(handle), 64)
+            check(lib().tnb_mailbox_import(buf, ctypes.byref(p)))
+        self.ptr = p
+
+    def export(self):
+        buf = ctypes.create_string_buffer(64)
+        check(lib().tnb_mailbox_export(self.ptr, buf))
+        return bytes(buf.raw)
+
+    def close(self):
+        p, self.ptr = getattr(self, "ptr", None), None
+        if p and _lib is not None:
+            (_lib.tnb_mailbox_destroy if self.owned else _lib.tnb_mailbox_release)(p)
+
+    def __del__(self):
+        self.close()
 
 
 class NativeComplex:
@@ -285,6 +366,25 @@ class NativeComplex:
         check(lib().tnb_extract_mesh(self.net.handle, self.handle, float(eps), ctypes.byref(h), _stream()))
         return NativeMesh(self.net, h)
 
+    # ---- slab sharding ----------------------------------------------------------------
+    def set_halo(self, rank, world, boxes, payload, timeout_ms=0, seq0=0):
+        arr = (ctypes.c_void_p * world)(*[b.ptr for b in boxes])
+        self._boxes = list(boxes)  # keep the mailboxes alive as long as the complex
+        check(lib().tnb_complex_set_halo(self.handle, int(rank), int(world), arr, int(payload), int(timeout_ms), int(seq0)))
+
+    def step_part(self, l, h, part, eps=1e-4, force=True):
+        check(lib().tnb_subpoly_step_part(self.net.handle, self.handle, int(l), int(h), float(eps),
+                                          int(bool(force)), int(part), _stream()))
+
+    def extract_mesh_begin(self, eps=1e-4):
+        h = ctypes.c_void_p()
+        check(lib().tnb_extract_mesh_begin(self.net.handle, self.handle, float(eps), ctypes.byref(h), _stream()))
+        return NativeMesh(self.net, h)
+
+    def extract_mesh_finish(self, mesh):
+        check(lib().tnb_extract_mesh_finish(self.net.handle, self.handle, mesh.handle, _stream()))
+        return mesh
+
 
 class NativeMesh:
     """Extracted surface mesh (tnb_mesh)."""
@@ -315,6 +415,17 @@ class NativeMesh:
         p = torch.empty((s["P"], s["W"]), dtype=torch.int64, device=dev)
         check(lib().tnb_mesh_read(self.handle, _ptr(v), _ptr(e), _ptr(t), _ptr(f), _ptr(p), _stream()))
         return v, e, t, f, p
+
+    @property
+    def near_plane(self):
+        return int(lib().tnb_mesh_near_plane(self.handle))
+
+    def read_tags(self):
+        """uint8 per vertex: bit0 / bit1 = on the slab plane shared with the lower / upper neighbour."""
+        t = torch.empty(self.sizes()["V"], dtype=torch.uint8, device="cuda")
+        if t.numel():
+            check(lib().tnb_mesh_read_tags(self.handle, _ptr(t), _stream()))
+        return t
 
     def read_host(self, polygons=True):
         """numpy arrays through tnb_mesh_read_host (host buffers): vertices, triangles,
