@@ -315,9 +315,28 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     planar = args.path == "planar"
+    slab = args.shard == "slab" and world > 1
+    if slab and not planar:
+        raise SystemExit("--shard slab supports the planar path only")
 
-    def step():
-        return net.subpoly(size=1.2, eps=w["eps"], force=planar)
+    class SlabMesh:
+        """One object sharded over the ranks by marks-grid slabs and merged (tropical/parallel.py)."""
+
+        def __init__(self, n):
+            from tropical import parallel
+            self.v, self.t, self.stats = parallel.subpoly_sharded(n, size=1.2, eps=w["eps"])
+
+        def sizes(self):
+            return {"V": int(self.v.shape[0]), "T": int(self.t.shape[0]), "P": None}
+
+        def read_host(self, polygons=False):
+            v, t = self.v.cpu().numpy(), self.t.cpu().numpy()
+            return v, t, v[t], None
+
+    def step(n=None):
+        if slab:
+            return SlabMesh(n or net)
+        return (n or net).subpoly(size=1.2, eps=w["eps"], force=planar)
 
     sampler = ClockSampler(local)
     if rank == 0:
@@ -325,6 +344,7 @@ def run_ours(args):
     for _ in range(max(args.warmup, 3)):
         mesh = step()
     sizes = mesh.sizes()
+    slab_stats = dict(mesh.stats) if slab else None
     del mesh
 
     _native.profile_enable(True)
@@ -349,7 +369,8 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    value = sizes["V"] * world * args.steps / (ms_total * 1e-3)
+    objects = 1 if slab else world   # slab mode: ONE object over all ranks (strong scaling)
+    value = sizes["V"] * objects * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the C ABI with host buffers --------------------------------
     pinned = {k: torch.from_numpy(np.ascontiguousarray(w[k], np.float32)).pin_memory() for k in ("table", "mlp", "marks")}
@@ -359,7 +380,7 @@ def run_ours(args):
 
     def e2e_step():
         n2 = make_native(w, pinned_np)            # host -> device copy of the step's inputs
-        m2 = n2.subpoly(size=1.2, eps=w["eps"], force=planar)
+        m2 = step(n2)
         v, tr, f, _ = m2.read_host(polygons=False)   # device -> host read of subpoly()'s return values
         return v.nbytes + tr.nbytes + f.nbytes
 
@@ -375,7 +396,7 @@ def run_ours(args):
     t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = sizes["V"] * world * args.steps / float(t.item())
+    e2e_value = sizes["V"] * objects * args.steps / float(t.item())
 
     if rank != 0:
         if dist is not None:
@@ -439,10 +460,13 @@ def run_ours(args):
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-           "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "scaling": "strong" if slab else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": {"workload": w["describe"] + ("" if planar else " [curve-approximation path]"), "mesh_vertices": sizes["V"], "mesh_triangles": sizes["T"],
-                      "polygons": sizes["P"], "objects_per_step": world, "l2": "flushed (512 MiB write) between timed steps",
-                      "extraction_s": ms_total / args.steps * 1e-3},
+                      "polygons": sizes["P"], "objects_per_step": objects, "l2": "flushed (512 MiB write) between timed steps",
+                      "extraction_s": ms_total / args.steps * 1e-3,
+                      "sharding": ("one object cut into %d marks-grid slabs, one per GPU; per-step exchange through peer mailboxes, "
+                                   "all-gather + merge inside the timed region" % world) if slab else "one object per GPU",
+                      "slab_stats": slab_stats},
            "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": 1e3 * float(t.item()) / args.steps},
@@ -461,6 +485,9 @@ def main():
     ap.add_argument("--workload", default="small_sphere")
     ap.add_argument("--path", default="planar", choices=["planar", "curve"],
                     help="planar = the reference's -f default (force=True); curve = curve approximation")
+    ap.add_argument("--shard", default="object", choices=["object", "slab"],
+                    help="N>1: object = every rank extracts its own object (weak scaling, default); "
+                         "slab = ONE object cut into marks-grid slabs, one per GPU (strong scaling)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the evaluation-sweep throughput leg")
     ap.add_argument("--sweep-n", type=int, default=512, help="lattice size per axis of the evaluation sweep")

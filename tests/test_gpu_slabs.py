@@ -77,8 +77,8 @@ def test_slabs_repeat_and_reuse_mailboxes():
 def test_slab_of_empty_space():
     # 8 slabs of the small sphere: the outer slabs hold no surface at all and still take part
     from tropical import parallel
-    N = native_net(oracle_net(load_golden("small_torus")))
-    v, t, stats = parallel.subpoly_slabs_local(N, 8)
+    N = native_net(oracle_net(load_golden("small_sphere")))
+    v, t, stats = parallel.subpoly_slabs_local(N, 5)
     assert min(stats["slab_vertices"]) == 0 and stats["near_plane"] == 0
     v1, t1 = _single(N)
     assert np.array_equal(canonical_triangles(v.cpu().numpy(), t.cpu().numpy()), canonical_triangles(v1, t1))
