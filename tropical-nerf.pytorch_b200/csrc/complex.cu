@@ -18,6 +18,7 @@
 #include "halo.cuh"
 #include "net_eval.cuh"
 #include "scan.cuh"
+#include "sort.cuh"
 
 tnb_complex::~tnb_complex() {}
 
@@ -902,40 +903,12 @@ __device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
         if (c <= kLocalPartners) {
             int list[kLocalPartners];
             find_partners(a, cand, sig, head, next, dim, stamp, colmask, list, kLocalPartners, 1);
-            for (int i = 1; i < c; ++i) {
-                const int key = list[i];
-                int j = i - 1;
-                while (j >= 0 && list[j] > key) { list[j + 1] = list[j]; --j; }
-                list[j + 1] = key;
-            }
+            thread_sort(list, c);
             for (int i = 0; i < c; ++i) dst[i] = make_int2(va, list[i]);
         } else {  // long list (degenerate, very large region): gather and sort in place in HBM
             int *keys = &dst[0].y;  // stride 2 ints
             find_partners(a, cand, sig, head, next, dim, stamp, colmask, keys, c, 2);
-            // heap sort on the strided keys
-            for (int start = c / 2 - 1; start >= 0; --start) {
-                int root = start;
-                for (;;) {
-                    int child = 2 * root + 1;
-                    if (child >= c) break;
-                    if (child + 1 < c && keys[2 * child] < keys[2 * (child + 1)]) ++child;
-                    if (keys[2 * root] >= keys[2 * child]) break;
-                    const int t = keys[2 * root]; keys[2 * root] = keys[2 * child]; keys[2 * child] = t;
-                    root = child;
-                }
-            }
-            for (int end = c - 1; end > 0; --end) {
-                const int t0 = keys[0]; keys[0] = keys[2 * end]; keys[2 * end] = t0;
-                int root = 0;
-                for (;;) {
-                    int child = 2 * root + 1;
-                    if (child >= end) break;
-                    if (child + 1 < end && keys[2 * child] < keys[2 * (child + 1)]) ++child;
-                    if (keys[2 * root] >= keys[2 * child]) break;
-                    const int t = keys[2 * root]; keys[2 * root] = keys[2 * child]; keys[2 * child] = t;
-                    root = child;
-                }
-            }
+            thread_sort(keys, c, 2);
             for (int i = 0; i < c; ++i) dst[i].x = va;
         }
     }
@@ -1090,6 +1063,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
     grid.sync();
     scan_write_body(E, sc, ListEmit{a.split_list}, a.block_sums, cnt + C_RAW);
     grid.sync();
+    // subpoly.py:110-111: the plane crosses no edge -> the step changes nothing (uniform exit; a
+    // slab must go on, another slab may have crossed: halo.cuh)
+    if (cnt[C_RAW] == 0 && !a.halo) return;
     body_new_vertices<C>(n, a.idx, a.eps, a.Vcap, a.Ecap, a.split_list, edges, vert, out, sig, a.bmask, cnt, a.tag[pv]);
     const HitCount hc{out, n.R, a.idx, a.eps};  // old vertices only: independent of the new rows
     scan_count_body(V, hc, a.block_sums);
@@ -1462,6 +1438,10 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         // 1. edges the hyperplane crosses
         SplitCount sc{c->cedges(), c->cout_(), R, idx, eps};
         if ((rc = compact(c->E, sc, ListEmit{c->split_list.p}, c->block_sums.p, cnt + C_RAW, s, cnt + C_E))) return rc;
+        if (attempt == 0) {  // most hyperplanes of a fitted network cross nothing: learn it now (subpoly.py:110-111)
+            if ((rc = read_counters(c, s))) return rc;
+            if (c->h_counters[C_RAW] == 0) return TNB_OK;
+        }
         // 2. new vertices, their network rows, rewired edges (all sized on the device)
         if (!planar) {
             const int o = c->vcur ^ 1;  // idle half of the ping-pong arrays = temp slots

@@ -17,6 +17,7 @@
 #include "complex.cuh"
 #include "net_eval.cuh"
 #include "scan.cuh"
+#include "sort.cuh"
 
 struct tnb_mesh {
     int64_t V = 0, E = 0, P = 0, W = 0, T = 0;
@@ -41,7 +42,8 @@ constexpr int kThreads = 128;
 constexpr int kMaxRow = 8192;      // hard limit of vertices per face row (sizes the HBM row scratch)
 constexpr int kSmemRowStride = 64;  // rows up to this length are built in shared memory (64 KB per CTA)
 constexpr int kMaxZeros = 5;  // 2^5 regions = one per lane
-enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_NUM = 16 };
+constexpr int kSortLocal = 32;  // face rows up to this length are angle-sorted in registers / local memory
+enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_NUM = 16 };
 
 // ---- surface skeleton -----------------------------------------------------------------------------
 __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
@@ -252,15 +254,12 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                     if (!in) continue;
                     const unsigned long long key = ((unsigned long long)zero_count(pb, nb, gb, colmask) << 32) | (unsigned)b;
                     if (key < my_key) { led_by_other = true; break; }  // that vertex emits this row, not a
-                    if (cnt < stride) {
-                        int j = cnt - 1;
-                        while (j >= 0 && mine[j] > key) { mine[j + 1] = mine[j]; --j; }
-                        mine[j + 1] = key;
-                    }
+                    if (cnt < stride) mine[cnt] = key;
                     ++cnt;
                 }
             }
             if (led_by_other) cnt = 0;
+            if (cnt <= stride) thread_sort(mine, cnt);
             if (cnt > stride) {
                 atomicOr(counters + F_ERR_ROW, 1);
                 atomicMax(counters + F_MAXCNT, cnt);
@@ -285,6 +284,7 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
             if (lane == 0 && wmax) atomicMax(counters + F_WIDTH, wmax);
+            if (keep && cnt > kSortLocal) atomicAdd(counters + F_LONG_TOTAL, cnt);  // sizes k_sort_rows' key scratch
         } else if (keep) {
             int rank = 0;  // lexicographic rank among the rows this vertex leads
             for (unsigned mset = keep_mask & ~(1u << lane); mset; mset &= mset - 1) {
@@ -312,8 +312,6 @@ struct OffsetEmit {
 // centre (subpoly.py:627-642); rewrites the row in sorted order.  Rows up to kSortLocal
 // vertices are sorted in registers/local memory; longer ones (duplicated chunk-boundary
 // geometry) in place in HBM with their scores in `score_scratch` [P][W].
-constexpr int kSortLocal = 32;
-
 __device__ __forceinline__ float angle_score(const float a[3], const float ua[3], const float u[3], const float nrm[3])
 {
     const float d0 = a[1] * u[2] - a[2] * u[1], d1 = a[2] * u[0] - a[0] * u[2], d2 = a[0] * u[1] - a[1] * u[0];
@@ -326,7 +324,8 @@ __device__ __forceinline__ float angle_score(const float a[3], const float ua[3]
 template <class C>
 __global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ NetMeta n, int64_t P, int W,
                                                         const float *__restrict__ vert, int *__restrict__ rows,
-                                                        const int *__restrict__ row_cnt, float *__restrict__ score_scratch,
+                                                        const int *__restrict__ row_cnt,
+                                                        unsigned long long *__restrict__ key_scratch,
                                                         int *__restrict__ counters)
 {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
@@ -370,20 +369,19 @@ __global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ 
             }
             for (int j = 0; j < cnt; ++j) row[j] = id[j];
         } else {
-            float *sc = score_scratch + p * W;
+            // long row: 64-bit keys (descending score, then original position = stable) in a
+            // scratch segment, heap sort, gather
+            unsigned long long *keys = key_scratch + atomicAdd(counters + F_LONG_CURSOR, cnt);
             for (int j = 0; j < cnt; ++j) {
                 const float *q = vert + 3 * (int64_t)row[j];
                 const float u[3] = {q[0] - mean[0], q[1] - mean[1], q[2] - mean[2]};
-                sc[j] = angle_score(a, ua, u, nrm);
+                const uint32_t b = __float_as_uint(angle_score(a, ua, u, nrm));
+                const uint32_t asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // orders like the float
+                keys[j] = ((unsigned long long)(0xFFFFFFFFu - asc) << 32) | (unsigned)j;
             }
-            for (int i = 1; i < cnt; ++i) {
-                const float ks = sc[i];
-                const int ki = row[i];
-                int j = i - 1;
-                while (j >= 0 && sc[j] < ks) { sc[j + 1] = sc[j]; row[j + 1] = row[j]; --j; }
-                sc[j + 1] = ks;
-                row[j + 1] = ki;
-            }
+            thread_sort(keys, cnt);
+            for (int j = 0; j < cnt; ++j) keys[j] = (unsigned)row[(uint32_t)keys[j]];
+            for (int j = 0; j < cnt; ++j) row[j] = (int)(uint32_t)keys[j];
         }
     }
 }
@@ -621,6 +619,12 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     int stride = kSmemRowStride;
     DevBuf<unsigned long long> scratch;
     size_t rows_smem = (size_t)kThreads * stride * sizeof(unsigned long long);
+    if (net->face_row_hint > kSmemRowStride) {
+        // the previous extraction of this network needed rows in HBM: start there (saves the failed pass)
+        stride = net->face_row_hint;
+        gw = std::min<unsigned>(gw, kSMs * 4);
+        TNB_CUDA(scratch.reserve((size_t)gw * kThreads * stride));
+    }
     {
         static bool attr_set = false;
         if (!attr_set) {
@@ -640,11 +644,12 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         if (h[F_ERR_ZEROS]) { set_error("a surface vertex lies on more than 5 planes: more than 32 adjacent regions"); return TNB_ERR_UNSUPPORTED; }
         if (!h[F_ERR_ROW]) break;
         // a face row did not fit: retry with rows in HBM, sized to the longest row seen
-        if (attempt > 0 || h[F_MAXCNT] > kMaxRow) {
+        if (attempt > 1 || h[F_MAXCNT] > kMaxRow) {
             set_error("a face has more than " + std::to_string(kMaxRow) + " vertices (" + std::to_string(h[F_MAXCNT]) + ")");
             return TNB_ERR_UNSUPPORTED;
         }
         stride = (h[F_MAXCNT] + 7) / 8 * 8;  // exactly the longest row: the retry cannot overflow
+        net->face_row_hint = stride;
         gw = std::min<unsigned>(gw, kSMs * 4);
         TNB_CUDA(scratch.reserve((size_t)gw * kThreads * stride));
         TNB_CUDA(cudaMemsetAsync(counters.p + F_ROWS, 0, (F_NUM - F_ROWS) * sizeof(int), s));
@@ -661,8 +666,8 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     TNB_LAUNCH_CHECK();
     {
         unsigned g = grid_for(P, kThreads);
-        DevBuf<float> score_scratch;
-        if (W > kSortLocal) TNB_CUDA(score_scratch.reserve((size_t)P * W));
+        DevBuf<unsigned long long> score_scratch;  // one segment per long row (their total was counted with the rows)
+        if (W > kSortLocal) TNB_CUDA(score_scratch.reserve((size_t)std::max(h[F_LONG_TOTAL], 1)));
         if (net->fixed_cfg) k_sort_rows<CfgRef><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p);
         else k_sort_rows<CfgAny><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p);
         TNB_LAUNCH_CHECK();

@@ -66,4 +66,5 @@ struct tnb_net {
     std::vector<float> h_marks;
     std::vector<float> h_scale;
     std::vector<uint32_t> h_res, h_size, h_off;
+    mutable int face_row_hint = 0;  // longest face row of the previous extraction (faces.cu)
 };
