@@ -775,11 +775,17 @@ __device__ __forceinline__ int64_t cell_id(int cx, int cy, int cz, int dim)
 
 __device__ __forceinline__ void body_bucket_insert(const int *cand, const int *cnt,
                                 const uint64_t *sig, unsigned long long *head,
-                                int *next, int dim, uint32_t stamp)
+                                tnb_bucket_rec *next, int dim, uint32_t stamp)
 {
     const int n_cand = cnt[C_CAND];
     for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += gridDim.x * blockDim.x) {
-        const CellBox b = cell_box(sig[3 * (int64_t)cand[c] + 2]);
+        const int v = cand[c];
+        tnb_bucket_rec r;
+        r.v = v;
+        r.pos = sig[3 * (int64_t)v];
+        r.neg = sig[3 * (int64_t)v + 1];
+        r.grd = sig[3 * (int64_t)v + 2];
+        const CellBox b = cell_box(r.grd);
         int slot = 0;
         for (int cx = b.lo[0]; cx <= b.hi[0]; ++cx)
             for (int cy = b.lo[1]; cy <= b.hi[1]; ++cy)
@@ -787,14 +793,15 @@ __device__ __forceinline__ void body_bucket_insert(const int *cand, const int *c
                     const int rec = c * 8 + slot;
                     const unsigned long long mine = ((unsigned long long)stamp << 32) | (unsigned)rec;
                     const unsigned long long old = atomicExch(head + cell_id(cx, cy, cz, dim), mine);
-                    next[rec] = ((uint32_t)(old >> 32) == stamp) ? (int)(uint32_t)old : -1;
+                    r.next = ((uint32_t)(old >> 32) == stamp) ? (int)(uint32_t)old : -1;
+                    next[rec] = r;
                 }
     }
 }
 
 __global__ void __launch_bounds__(kThreads) k_bucket_insert(const int *__restrict__ cand, const int *__restrict__ cnt,
                                 const uint64_t *__restrict__ sig, unsigned long long *__restrict__ head,
-                                int *__restrict__ next, int dim, uint32_t stamp)
+                                tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp)
 {
     body_bucket_insert(cand, cnt, sig, head, next, dim, stamp);
 }
@@ -806,7 +813,7 @@ constexpr int kLocalPartners = 128;  // partner lists up to this size are sorted
 // one cell (the smallest common one).  Returns the count; when `list` is non-null the first
 // `cap` partner vertex numbers are stored there (unsorted).
 __device__ __forceinline__ int find_partners(int a, const int *cand, const uint64_t *sig,
-                                             const unsigned long long *head, const int *next,
+                                             const unsigned long long *head, const tnb_bucket_rec *next,
                                              int dim, uint32_t stamp, uint64_t colmask, int *list, int cap, int stride)
 {
     const int va = cand[a];
@@ -820,10 +827,12 @@ __device__ __forceinline__ int find_partners(int a, const int *cand, const uint6
                 const unsigned long long h = head[cell_id(cx, cy, cz, dim)];
                 if ((uint32_t)(h >> 32) != stamp) continue;
                 const int cur[3] = {cx, cy, cz};
-                for (int rec = (int)(uint32_t)h; rec >= 0; rec = next[rec]) {
-                    const int vb = cand[rec >> 3];
+                for (int rec = (int)(uint32_t)h; rec >= 0;) {
+                    const tnb_bucket_rec r = next[rec];
+                    rec = r.next;
+                    const int vb = r.v;
                     if (vb <= va) continue;
-                    const uint64_t pb = sig[3 * (int64_t)vb], nb = sig[3 * (int64_t)vb + 1], gb = sig[3 * (int64_t)vb + 2];
+                    const uint64_t pb = r.pos, nb = r.neg, gb = r.grd;
                     if (((pa & nb) | (na & pb)) & colmask) continue;  // opposite signs: no common region
                     const CellBox bb = cell_box(gb);
                     bool ok = true;
@@ -845,7 +854,7 @@ __device__ __forceinline__ int find_partners(int a, const int *cand, const uint6
 __device__ __forceinline__ void body_pair_count(const int *cand, int *cnt,
                                                          const uint64_t *sig,
                                                          const unsigned long long *head,
-                                                         const int *next, int dim, uint32_t stamp,
+                                                         const tnb_bucket_rec *next, int dim, uint32_t stamp,
                                                          uint64_t colmask, int *pcount)
 {
     const int n_cand = cnt[C_CAND];
@@ -856,7 +865,7 @@ __device__ __forceinline__ void body_pair_count(const int *cand, int *cnt,
 __global__ void __launch_bounds__(kThreads) k_pair_count(const int *__restrict__ cand, int *__restrict__ cnt,
                                                          const uint64_t *__restrict__ sig,
                                                          const unsigned long long *__restrict__ head,
-                                                         const int *__restrict__ next, int dim, uint32_t stamp,
+                                                         const tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp,
                                                          uint64_t colmask, int *__restrict__ pcount)
 {
     body_pair_count(cand, cnt, sig, head, next, dim, stamp, colmask, pcount);
@@ -866,7 +875,7 @@ struct PairCountFn {  // count phase of the partner-offset scan: search, remembe
     const int *cand;
     const uint64_t *sig;
     const unsigned long long *head;
-    const int *next;
+    const tnb_bucket_rec *next;
     int dim;
     uint32_t stamp;
     uint64_t colmask;
@@ -890,7 +899,7 @@ struct OffsetEmit {
 __device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
                                                          const uint64_t *sig,
                                                          const unsigned long long *head,
-                                                         const int *next, int dim, uint32_t stamp,
+                                                         const tnb_bucket_rec *next, int dim, uint32_t stamp,
                                                          uint64_t colmask, const int *pcount,
                                                          const int *poff, int2 *edges_out)
 {
@@ -917,7 +926,7 @@ __device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
 __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__ cand, int n_cand,
                                                          const uint64_t *__restrict__ sig,
                                                          const unsigned long long *__restrict__ head,
-                                                         const int *__restrict__ next, int dim, uint32_t stamp,
+                                                         const tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp,
                                                          uint64_t colmask, const int *__restrict__ pcount,
                                                          const int *__restrict__ poff, int2 *__restrict__ edges_out)
 {
@@ -949,24 +958,43 @@ struct KeepEmit {
         used[ed.y] = 1;
     }
 };
-struct VertexMoveEmit {  // subpoly.py:268-277: compact vertices, positions, cached outputs
+struct VertexMoveEmit {  // subpoly.py:268-277: new number of every surviving vertex
+    int *remap;
+    __device__ __forceinline__ void operator()(int64_t v, int pos, int) const { remap[v] = pos; }
+};
+// ... and the move itself, flattened over (vertex, column) so that a warp reads and writes
+// consecutive floats of the 33-float rows (one thread per row costs 32 sectors per store)
+struct VertexArrays {
     const float *vert, *out;
     const uint64_t *sig;
+    const unsigned char *tag;
     float *nvert, *nout;
     uint64_t *nsig;
-    int *remap;
-    int R;
-    const unsigned char *tag;
     unsigned char *ntag;
-    __device__ __forceinline__ void operator()(int64_t v, int pos, int) const
-    {
-        remap[v] = pos;
-        ntag[pos] = tag[v];
-        for (int d = 0; d < 3; ++d) nvert[3 * (int64_t)pos + d] = vert[3 * v + d];
-        for (int d = 0; d < 3; ++d) nsig[3 * (int64_t)pos + d] = sig[3 * v + d];
-        for (int c = 0; c < R; ++c) nout[(int64_t)pos * R + c] = out[v * R + c];
-    }
 };
+__device__ __forceinline__ void body_move_rows(int V, int R, const int *used, const int *remap, const VertexArrays a)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    for (int64_t i = t0; i < (int64_t)V * R; i += stride) {
+        const int v = (int)(i / R);
+        if (used[v]) a.nout[(int64_t)remap[v] * R + (i - (int64_t)v * R)] = a.out[i];
+    }
+    for (int64_t i = t0; i < (int64_t)V * 3; i += stride) {
+        const int v = (int)(i / 3);
+        if (used[v]) {
+            const int64_t j = (int64_t)remap[v] * 3 + (i - (int64_t)v * 3);
+            a.nvert[j] = a.vert[i];
+            a.nsig[j] = a.sig[i];
+        }
+    }
+    for (int64_t v = t0; v < V; v += stride)
+        if (used[v]) a.ntag[remap[v]] = a.tag[v];
+}
+__global__ void __launch_bounds__(256) k_move_rows(const int *__restrict__ n_dev, int R, const int *__restrict__ used,
+                                                   const int *__restrict__ remap, const VertexArrays a)
+{
+    body_move_rows(*n_dev, R, used, remap, a);
+}
 
 __device__ __forceinline__ void body_remap_edges_dev(int2 *edges, const int *n_dev, const int *remap)
 {
@@ -988,6 +1016,7 @@ __global__ void k_set_counts(int *__restrict__ cnt, int V, int E, int vpar, int 
     cnt[C_VPAR] = vpar;
     cnt[C_EPAR] = epar;
 }
+__global__ void k_set_scratch_count(int *__restrict__ p, int v) { *p = v; }
 __global__ void k_set_parity(int *__restrict__ cnt, int vpar, int epar)
 {
     cnt[C_VPAR] = vpar;
@@ -1018,7 +1047,8 @@ struct StepArgs {
     int2 *edges[2];
     float *vert[2], *out[2];
     uint64_t *sig[2], *bmask;
-    int *split_list, *cand, *pcount, *poff, *next, *used, *remap, *block_sums, *cnt;
+    int *split_list, *cand, *pcount, *poff, *used, *remap, *block_sums, *cnt;
+    tnb_bucket_rec *next;
     unsigned long long *head, *bytes;  // bytes[0/1]: algorithmic bytes of the front / back halves
     unsigned char *tag[2];
     // slab sharding (halo.cuh): the back half runs in two launches around the exchange
@@ -1188,10 +1218,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
     const FlagCount fc{a.used};
     scan_count_body(Vn, fc, a.block_sums);
     grid.sync();
-    scan_write_body(Vn, fc, VertexMoveEmit{vert, out, sig, a.vert[pv ^ 1], a.out[pv ^ 1], a.sig[pv ^ 1], a.remap, a.R,
-                                           a.tag[pv], a.tag[pv ^ 1]},
-                    a.block_sums, cnt + C_V);
+    scan_write_body(Vn, fc, VertexMoveEmit{a.remap}, a.block_sums, cnt + C_V);
     grid.sync();
+    body_move_rows(Vn, a.R, a.used, a.remap,
+                   VertexArrays{vert, out, sig, a.tag[pv], a.vert[pv ^ 1], a.out[pv ^ 1], a.sig[pv ^ 1], a.tag[pv ^ 1]});
     body_remap_edges_dev(edges_dst, kept, a.remap);
     if (a.halo) grid.sync();  // every CTA has read the parked count before it is published
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // flip the ping-pong halves
@@ -1539,9 +1569,12 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         int2 *dst = c->edges[c->ecur ^ 1].p;
         if ((rc = compact(c->E, kc, KeepEmit{c->cedges(), dst, c->used.p}, c->block_sums.p, cnt + C_E, s))) return rc;
         const int o = c->vcur ^ 1;
-        VertexMoveEmit vm{c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->sig[o].p, c->remap.p, R,
-                          c->tag[c->vcur].p, c->tag[o].p};
-        if ((rc = compact(c->V, FlagCount{c->used.p}, vm, c->block_sums.p, cnt + C_V, s))) return rc;
+        k_set_scratch_count<<<1, 1, 0, s>>>(cnt + C_KEPT, (int)c->V);  // vertices before the compaction, for k_move_rows
+        TNB_LAUNCH_CHECK();
+        if ((rc = compact(c->V, FlagCount{c->used.p}, VertexMoveEmit{c->remap.p}, c->block_sums.p, cnt + C_V, s))) return rc;
+        k_move_rows<<<grid_for(c->V * R, 256, kSMs * 8), 256, 0, s>>>(cnt + C_KEPT, R, c->used.p, c->remap.p,
+            VertexArrays{c->cvert(), c->cout_(), c->csig(), c->tag[c->vcur].p, c->vert[o].p, c->out[o].p, c->sig[o].p, c->tag[o].p});
+        TNB_LAUNCH_CHECK();
         c->ecur ^= 1;
         c->vcur = o;
         k_remap_edges_dev<<<grid_for(c->E, 256), 256, 0, s>>>(c->cedges(), cnt + C_E, c->remap.p);

@@ -9,6 +9,15 @@
 //   edges [E]    int2  vertex pair (first, second) in the reference's column order
 // Vertex arrays and the edge array are double-buffered: pruning compacts from one set
 // into the other (order preserving) and flips.
+// One entry of a cell bucket (generation-stamped linked lists over the marks-grid cells).  The
+// candidate's packed sign vector travels with the link, so walking a list costs ONE dependent
+// 32-byte load per hop instead of link -> candidate -> signature.
+struct alignas(32) tnb_bucket_rec {
+    int next;  // next record of the same cell, -1 = end
+    int v;     // vertex number
+    uint64_t pos, neg, grd;
+};
+
 // Slab sharding (one object split over several GPUs along the first grid axis): the complex of
 // one rank holds the cells [x_lo, x_hi-1]; the planes x_lo / x_hi are shared with the neighbours.
 // What crosses a shared plane is exchanged once per hyperplane step through peer-mapped
@@ -43,7 +52,7 @@ struct tnb_complex {
     tnb::DevBuf<int> cand;          // [Vcap]   candidate vertex numbers (hits, then new)
     tnb::DevBuf<int> pcount;        // [Vcap]   partners per candidate
     tnb::DevBuf<int> poff;          // [Vcap]   exclusive scan of pcount
-    tnb::DevBuf<int> next;          // [8*Vcap] bucket chains
+    tnb::DevBuf<tnb_bucket_rec> next;  // [8*Vcap] bucket chains
     tnb::DevBuf<unsigned long long> head;  // [n_cells] (stamp << 32 | record)
     tnb::DevBuf<int> used;          // [Vcap]   vertex referenced by a kept edge
     tnb::DevBuf<int> remap;         // [Vcap]

@@ -165,10 +165,15 @@ __device__ __forceinline__ int zero_count(uint64_t pos, uint64_t neg, uint64_t g
 }
 
 __global__ void k_face_bucket_insert(int64_t V, const uint64_t *__restrict__ sig, unsigned long long *__restrict__ head,
-                                     int *__restrict__ next, int dim, uint32_t stamp)
+                                     tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp)
 {
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
-        const Box b = box_of(sig[3 * v + 2]);
+        tnb_bucket_rec r;
+        r.v = (int)v;
+        r.pos = sig[3 * v];
+        r.neg = sig[3 * v + 1];
+        r.grd = sig[3 * v + 2];
+        const Box b = box_of(r.grd);
         int slot = 0;
         for (int cx = b.lo[0]; cx <= b.hi[0]; ++cx)
             for (int cy = b.lo[1]; cy <= b.hi[1]; ++cy)
@@ -176,7 +181,8 @@ __global__ void k_face_bucket_insert(int64_t V, const uint64_t *__restrict__ sig
                     const int rec = (int)v * 8 + slot;
                     const unsigned long long mine = ((unsigned long long)stamp << 32) | (unsigned)rec;
                     const unsigned long long old = atomicExch(head + cell_of(cx, cy, cz, dim), mine);
-                    next[rec] = ((uint32_t)(old >> 32) == stamp) ? (int)(uint32_t)old : -1;
+                    r.next = ((uint32_t)(old >> 32) == stamp) ? (int)(uint32_t)old : -1;
+                    next[rec] = r;
                 }
     }
 }
@@ -199,7 +205,7 @@ __device__ __forceinline__ int row_compare(const unsigned long long *x, int nx, 
 
 __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint64_t *__restrict__ sig,
                                                           const unsigned long long *__restrict__ head,
-                                                          const int *__restrict__ next, int dim, uint32_t stamp,
+                                                          const tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp,
                                                           uint64_t colmask, int mode, int stride,
                                                           unsigned long long *__restrict__ scratch,
                                                           int *__restrict__ rows_per_vertex,
@@ -243,9 +249,11 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
             const unsigned long long my_key = ((unsigned long long)ka << 32) | (unsigned)a;
             bool led_by_other = false;
             if (mine_cell && (uint32_t)(h >> 32) == stamp) {
-                for (int rec = (int)(uint32_t)h; rec >= 0; rec = next[rec]) {
-                    const int b = rec >> 3;
-                    const uint64_t pb = sig[3 * (int64_t)b], nb = sig[3 * (int64_t)b + 1], gb = sig[3 * (int64_t)b + 2];
+                for (int rec = (int)(uint32_t)h; rec >= 0;) {
+                    const tnb_bucket_rec r = next[rec];
+                    rec = r.next;
+                    const int b = r.v;
+                    const uint64_t pb = r.pos, nb = r.neg, gb = r.grd;
                     if ((pb & ~pat & colmask) || (nb & pat)) continue;  // a nonzero sign disagrees
                     const Box bb = box_of(gb);
                     bool in = true;
@@ -599,7 +607,8 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
 
     // ---- extract_faces ----
     DevBuf<uint64_t> sig;
-    DevBuf<int> next, rows_per_vertex, row_off;
+    DevBuf<tnb_bucket_rec> next;
+    DevBuf<int> rows_per_vertex, row_off;
     DevBuf<unsigned long long> head;
     TNB_CUDA(sig.reserve((size_t)Vs * 3));
     TNB_CUDA(next.reserve((size_t)Vs * 8));
@@ -619,9 +628,12 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     int stride = kSmemRowStride;
     DevBuf<unsigned long long> scratch;
     size_t rows_smem = (size_t)kThreads * stride * sizeof(unsigned long long);
-    if (net->face_row_hint > kSmemRowStride) {
-        // the previous extraction of this network needed rows in HBM: start there (saves the failed pass)
-        stride = net->face_row_hint;
+    // the previous extraction of this network (or of one on the same marks grid) needed rows in
+    // HBM: start there (saves the failed pass)
+    static int hint_marks = 0, hint_stride = 0;
+    const int hint = std::max(net->face_row_hint, hint_marks == nm.n_marks ? hint_stride : 0);
+    if (hint > kSmemRowStride) {
+        stride = hint;
         gw = std::min<unsigned>(gw, kSMs * 4);
         TNB_CUDA(scratch.reserve((size_t)gw * kThreads * stride));
     }
@@ -650,6 +662,8 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         }
         stride = (h[F_MAXCNT] + 7) / 8 * 8;  // exactly the longest row: the retry cannot overflow
         net->face_row_hint = stride;
+        hint_marks = nm.n_marks;
+        hint_stride = stride;
         gw = std::min<unsigned>(gw, kSMs * 4);
         TNB_CUDA(scratch.reserve((size_t)gw * kThreads * stride));
         TNB_CUDA(cudaMemsetAsync(counters.p + F_ROWS, 0, (F_NUM - F_ROWS) * sizeof(int), s));
