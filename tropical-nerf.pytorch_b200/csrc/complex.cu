@@ -8,6 +8,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -26,6 +27,8 @@ namespace tnb {
 
 double g_capacity_factor = 4.0;
 constexpr int kThreads = 128;
+constexpr int kCachedPartners = 12;  // the partner-count pass keeps this many partners per candidate: the write
+                                    // pass of a short list (nearly all of them) does not walk the buckets again
 // device counters: [0, C_V) are cleared at the start of every step, C_V / C_E hold the complex size
 //   C_RAW = edges the plane crosses, C_SPLIT = edges actually split (== C_RAW on the planar path,
 //   fewer after strict_check on the curve path)
@@ -55,6 +58,7 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
     TNB_CUDA(c->cand.reserve(Vcap));
     TNB_CUDA(c->pcount.reserve(Vcap));
     TNB_CUDA(c->poff.reserve(Vcap));
+    TNB_CUDA(c->pcache.reserve(Vcap * kCachedPartners));
     TNB_CUDA(c->next.reserve(Vcap * 8));
     TNB_CUDA(c->used.reserve(Vcap));
     TNB_CUDA(c->remap.reserve(Vcap));
@@ -106,7 +110,7 @@ int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
             if ((rc = grow(c->sig[k], nc * 3, keep * 3, s))) return rc;
             if ((rc = grow(c->tag[k], nc, keep, s))) return rc;
         }
-        if ((rc = grow(c->cand, nc, 0, s)) || (rc = grow(c->pcount, nc, 0, s)) || (rc = grow(c->poff, nc, 0, s)) ||
+        if ((rc = grow(c->cand, nc, 0, s)) || (rc = grow(c->pcount, nc, 0, s)) || (rc = grow(c->poff, nc, 0, s)) || (rc = grow(c->pcache, nc * kCachedPartners, 0, s)) ||
             (rc = grow(c->next, nc * 8, 0, s)) || (rc = grow(c->used, nc, 0, s)) || (rc = grow(c->remap, nc, 0, s)))
             return rc;
         c->Vcap = nc;
@@ -810,83 +814,120 @@ constexpr int kLocalPartners = 128;  // partner lists up to this size are sorted
 
 // Partners of candidate a: candidates b with a larger vertex number that share an expanded
 // region with a and at least one plane (subpoly.py:484-535).  Each pair is found in exactly
-// one cell (the smallest common one).  Returns the count; when `list` is non-null the first
-// `cap` partner vertex numbers are stored there (unsorted).
+// one cell (the smallest common one).
+struct PartnerQuery {
+    int va;
+    uint64_t pa, na, ga, za;
+    CellBox ba;
+};
+__device__ __forceinline__ PartnerQuery partner_query(int va, const uint64_t *sig)
+{
+    PartnerQuery q;
+    q.va = va;
+    q.pa = sig[3 * (int64_t)va];
+    q.na = sig[3 * (int64_t)va + 1];
+    q.ga = sig[3 * (int64_t)va + 2];
+    q.za = ~(q.pa | q.na);
+    q.ba = cell_box(q.ga);
+    return q;
+}
+// walks the bucket of ONE cell; hit(vb) is called for every partner found there
+template <class Hit>
+__device__ __forceinline__ void walk_cell(const PartnerQuery &q, int cx, int cy, int cz, const unsigned long long *head,
+                                          const tnb_bucket_rec *next, int dim, uint32_t stamp, uint64_t colmask, Hit hit)
+{
+    const unsigned long long h = head[cell_id(cx, cy, cz, dim)];
+    if ((uint32_t)(h >> 32) != stamp) return;
+    const int cur[3] = {cx, cy, cz};
+    for (int rec = (int)(uint32_t)h; rec >= 0;) {
+        const tnb_bucket_rec r = next[rec];
+        rec = r.next;
+        const int vb = r.v;
+        if (vb <= q.va) continue;
+        const uint64_t pb = r.pos, nb = r.neg, gb = r.grd;
+        if (((q.pa & nb) | (q.na & pb)) & colmask) continue;  // opposite signs: no common region
+        const CellBox bb = cell_box(gb);
+        bool ok = true;
+        int shared = __popcll(q.za & ~(pb | nb) & colmask);
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const int lo = max(q.ba.lo[d], bb.lo[d]), hi = min(q.ba.hi[d], bb.hi[d]);
+            if (lo > hi || cur[d] != lo) ok = false;  // not a common cell / not the canonical one
+            if (!grid_mask(q.ga, d) && !grid_mask(gb, d) && q.ba.hi[d] == bb.hi[d]) ++shared;
+        }
+        if (!ok || shared < 1) continue;
+        hit(vb);
+    }
+}
+// One thread, all cells of the candidate's box.  Returns the count; when `list` is non-null the
+// first `cap` partner vertex numbers are stored there (unsorted).
 __device__ __forceinline__ int find_partners(int a, const int *cand, const uint64_t *sig,
                                              const unsigned long long *head, const tnb_bucket_rec *next,
                                              int dim, uint32_t stamp, uint64_t colmask, int *list, int cap, int stride)
 {
-    const int va = cand[a];
-    const uint64_t pa = sig[3 * (int64_t)va], na = sig[3 * (int64_t)va + 1], ga = sig[3 * (int64_t)va + 2];
-    const uint64_t za = ~(pa | na);
-    const CellBox ba = cell_box(ga);
+    const PartnerQuery q = partner_query(cand[a], sig);
     int count = 0;
-    for (int cx = ba.lo[0]; cx <= ba.hi[0]; ++cx)
-        for (int cy = ba.lo[1]; cy <= ba.hi[1]; ++cy)
-            for (int cz = ba.lo[2]; cz <= ba.hi[2]; ++cz) {
-                const unsigned long long h = head[cell_id(cx, cy, cz, dim)];
-                if ((uint32_t)(h >> 32) != stamp) continue;
-                const int cur[3] = {cx, cy, cz};
-                for (int rec = (int)(uint32_t)h; rec >= 0;) {
-                    const tnb_bucket_rec r = next[rec];
-                    rec = r.next;
-                    const int vb = r.v;
-                    if (vb <= va) continue;
-                    const uint64_t pb = r.pos, nb = r.neg, gb = r.grd;
-                    if (((pa & nb) | (na & pb)) & colmask) continue;  // opposite signs: no common region
-                    const CellBox bb = cell_box(gb);
-                    bool ok = true;
-                    int shared = __popcll(za & ~(pb | nb) & colmask);
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) {
-                        const int lo = max(ba.lo[d], bb.lo[d]), hi = min(ba.hi[d], bb.hi[d]);
-                        if (lo > hi || cur[d] != lo) ok = false;  // not a common cell / not the canonical one
-                        if (!grid_mask(ga, d) && !grid_mask(gb, d) && ba.hi[d] == bb.hi[d]) ++shared;
-                    }
-                    if (!ok || shared < 1) continue;
+    for (int cx = q.ba.lo[0]; cx <= q.ba.hi[0]; ++cx)
+        for (int cy = q.ba.lo[1]; cy <= q.ba.hi[1]; ++cy)
+            for (int cz = q.ba.lo[2]; cz <= q.ba.hi[2]; ++cz)
+                walk_cell(q, cx, cy, cz, head, next, dim, stamp, colmask, [&](int vb) {
                     if (list && count < cap) list[(int64_t)count * stride] = vb;
                     ++count;
-                }
-            }
+                });
     return count;
+}
+
+// Eight lanes per candidate, one cell of its box each (a vertex on a grid plane / line / point
+// lies in 2 / 4 / 8 cells): the dependent-load chains of the cells run side by side.  Handles the
+// candidates [begin, end) with the calling CTA (blockDim.x threads, a multiple of 32); leaves the
+// count in pcount[a] and the first kCachedPartners partners (unsorted) in pcache.
+__device__ __forceinline__ void pair_count_groups(int begin, int end, const int *cand, const uint64_t *sig,
+                                                  const unsigned long long *head, const tnb_bucket_rec *next, int dim,
+                                                  uint32_t stamp, uint64_t colmask, int *pcount, int *pcache, int *s_cnt)
+{
+    const int g = threadIdx.x & 7, grp = threadIdx.x >> 3, per_pass = blockDim.x >> 3;
+    for (int base = begin; base < end; base += per_pass) {
+        const int a = base + grp;
+        if (g == 0) s_cnt[grp] = 0;
+        __syncwarp();
+        if (a < end) {
+            const PartnerQuery q = partner_query(cand[a], sig);
+            const int nx = q.ba.hi[0] - q.ba.lo[0] + 1, ny = q.ba.hi[1] - q.ba.lo[1] + 1, nz = q.ba.hi[2] - q.ba.lo[2] + 1;
+            if (g < nx * ny * nz) {
+                const int cz = q.ba.lo[2] + g % nz, cy = q.ba.lo[1] + (g / nz) % ny, cx = q.ba.lo[0] + g / (nz * ny);
+                walk_cell(q, cx, cy, cz, head, next, dim, stamp, colmask, [&](int vb) {
+                    const int pos = atomicAdd(s_cnt + grp, 1);
+                    if (pos < kCachedPartners) pcache[(int64_t)a * kCachedPartners + pos] = vb;
+                });
+            }
+        }
+        __syncwarp();
+        if (g == 0 && a < end) pcount[a] = s_cnt[grp];
+        __syncwarp();
+    }
 }
 
 __device__ __forceinline__ void body_pair_count(const int *cand, int *cnt,
                                                          const uint64_t *sig,
                                                          const unsigned long long *head,
                                                          const tnb_bucket_rec *next, int dim, uint32_t stamp,
-                                                         uint64_t colmask, int *pcount)
+                                                         uint64_t colmask, int *pcount, int *pcache)
 {
-    const int n_cand = cnt[C_CAND];
-    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x)
-        pcount[a] = find_partners(a, cand, sig, head, next, dim, stamp, colmask, nullptr, 0, 1);
+    __shared__ int s_cnt[kThreads / 8];
+    const int n_cand = cnt[C_CAND], per_block = blockDim.x >> 3;
+    for (int base = blockIdx.x * per_block; base < n_cand; base += gridDim.x * per_block)
+        pair_count_groups(base, min(base + per_block, n_cand), cand, sig, head, next, dim, stamp, colmask, pcount, pcache, s_cnt);
 }
 
 __global__ void __launch_bounds__(kThreads) k_pair_count(const int *__restrict__ cand, int *__restrict__ cnt,
                                                          const uint64_t *__restrict__ sig,
                                                          const unsigned long long *__restrict__ head,
                                                          const tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp,
-                                                         uint64_t colmask, int *__restrict__ pcount)
+                                                         uint64_t colmask, int *__restrict__ pcount, int *__restrict__ pcache)
 {
-    body_pair_count(cand, cnt, sig, head, next, dim, stamp, colmask, pcount);
+    body_pair_count(cand, cnt, sig, head, next, dim, stamp, colmask, pcount, pcache);
 }
 
-struct PairCountFn {  // count phase of the partner-offset scan: search, remember, return the count
-    const int *cand;
-    const uint64_t *sig;
-    const unsigned long long *head;
-    const tnb_bucket_rec *next;
-    int dim;
-    uint32_t stamp;
-    uint64_t colmask;
-    int *pcount;
-    __device__ __forceinline__ int operator()(int64_t a) const
-    {
-        const int c = find_partners((int)a, cand, sig, head, next, dim, stamp, colmask, nullptr, 0, 1);
-        pcount[a] = c;
-        return c;
-    }
-};
 struct ArrayCount {
     const int *v;
     __device__ __forceinline__ int operator()(int64_t i) const { return v[i]; }
@@ -901,7 +942,7 @@ __device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
                                                          const unsigned long long *head,
                                                          const tnb_bucket_rec *next, int dim, uint32_t stamp,
                                                          uint64_t colmask, const int *pcount,
-                                                         const int *poff, int2 *edges_out)
+                                                         const int *poff, int2 *edges_out, const int *pcache)
 {
     for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x) {
         const int c = pcount[a];
@@ -909,7 +950,19 @@ __device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
         const int va = cand[a];
         int2 *dst = edges_out + poff[a];
         // ascending partner number = the order unique(dim=0) leaves (subpoly.py:243-244)
-        if (c <= kLocalPartners) {
+        if (c <= kCachedPartners) {  // the count pass left the whole list behind
+            int list[kCachedPartners];
+#pragma unroll
+            for (int i = 0; i < kCachedPartners; ++i) list[i] = i < c ? pcache[(int64_t)a * kCachedPartners + i] : 0x7fffffff;
+#pragma unroll
+            for (int i = 1; i < kCachedPartners; ++i)
+#pragma unroll
+                for (int j = kCachedPartners - 1; j >= i; --j)
+                    if (list[j - 1] > list[j]) { const int t = list[j]; list[j] = list[j - 1]; list[j - 1] = t; }
+#pragma unroll
+            for (int i = 0; i < kCachedPartners; ++i)
+                if (i < c) dst[i] = make_int2(va, list[i]);
+        } else if (c <= kLocalPartners) {
             int list[kLocalPartners];
             find_partners(a, cand, sig, head, next, dim, stamp, colmask, list, kLocalPartners, 1);
             thread_sort(list, c);
@@ -928,9 +981,10 @@ __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__
                                                          const unsigned long long *__restrict__ head,
                                                          const tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp,
                                                          uint64_t colmask, const int *__restrict__ pcount,
-                                                         const int *__restrict__ poff, int2 *__restrict__ edges_out)
+                                                         const int *__restrict__ poff, int2 *__restrict__ edges_out,
+                                                         const int *__restrict__ pcache)
 {
-    body_pair_write(cand, n_cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out);
+    body_pair_write(cand, n_cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache);
 }
 
 // ---- pruning -------------------------------------------------------------------------------------
@@ -975,9 +1029,29 @@ struct VertexArrays {
 __device__ __forceinline__ void body_move_rows(int V, int R, const int *used, const int *remap, const VertexArrays a)
 {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-    for (int64_t i = t0; i < (int64_t)V * R; i += stride) {
-        const int v = (int)(i / R);
-        if (used[v]) a.nout[(int64_t)remap[v] * R + (i - (int64_t)v * R)] = a.out[i];
+    {   // four independent elements in flight per thread: on small complexes this loop is latency bound
+        const float *__restrict__ src = a.out;
+        float *__restrict__ dst = a.nout;
+        const int64_t total = (int64_t)V * R;
+        for (int64_t i = t0; i < total; i += 4 * stride) {
+            float val[4];
+            int64_t to[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int64_t ii = i + k * stride;
+                to[k] = -1;
+                if (ii < total) {
+                    const int v = (int)(ii / R);
+                    if (used[v]) {
+                        to[k] = (int64_t)remap[v] * R + (ii - (int64_t)v * R);
+                        val[k] = src[ii];
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (to[k] >= 0) dst[to[k]] = val[k];
+        }
     }
     for (int64_t i = t0; i < (int64_t)V * 3; i += stride) {
         const int v = (int)(i / 3);
@@ -1047,7 +1121,7 @@ struct StepArgs {
     int2 *edges[2];
     float *vert[2], *out[2];
     uint64_t *sig[2], *bmask;
-    int *split_list, *cand, *pcount, *poff, *used, *remap, *block_sums, *cnt;
+    int *split_list, *cand, *pcount, *poff, *used, *remap, *block_sums, *cnt, *pcache;
     tnb_bucket_rec *next;
     unsigned long long *head, *bytes;  // bytes[0/1]: algorithmic bytes of the front / back halves
     unsigned char *tag[2];
@@ -1057,7 +1131,9 @@ struct StepArgs {
     int *hslot, *stage_count, stage_cap;
     unsigned char *stage[2];
     const unsigned char *in[2];     // liveness bytes received from the lower / upper neighbour
+    long long *dbg;                 // TNB_PHASE_TRACE: globaltimer stamps after every phase
 };
+#define TNB_PHASE_MARK(k) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[k] = global_ns(); } while (0)
 
 struct TagCount {  // vertices on one shared slab plane
     const unsigned char *tag;
@@ -1080,6 +1156,7 @@ template <class C>
 __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_constant__ NetMeta n, const StepArgs a)
 {
     cg::grid_group grid = cg::this_grid();
+    TNB_PHASE_MARK(0);
     int *cnt = a.cnt;
     if (cnt[C_STICKY]) return;  // an earlier step failed: uniform exit, nobody reaches a grid sync
     const int E = cnt[C_E], V = cnt[C_V], pv = cnt[C_VPAR], pe = cnt[C_EPAR];
@@ -1091,8 +1168,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
     const SplitCount sc{edges, out, n.R, a.idx, a.eps};
     scan_count_body(E, sc, a.block_sums);
     grid.sync();
+    TNB_PHASE_MARK(1);
     scan_write_body(E, sc, ListEmit{a.split_list}, a.block_sums, cnt + C_RAW);
     grid.sync();
+    TNB_PHASE_MARK(2);
     // subpoly.py:110-111: the plane crosses no edge -> the step changes nothing (uniform exit; a
     // slab must go on, another slab may have crossed: halo.cuh)
     if (cnt[C_RAW] == 0 && !a.halo) return;
@@ -1100,6 +1179,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
     const HitCount hc{out, n.R, a.idx, a.eps};  // old vertices only: independent of the new rows
     scan_count_body(V, hc, a.block_sums);
     grid.sync();
+    TNB_PHASE_MARK(3);
     body_finalize_new(n, vert, out, sig, a.bmask, cnt);
     {   // every CTA knows the hit count from the block sums: the new vertices' candidate slots
         // [H, H+S) can be filled in the same phase as the hit list [0, H)
@@ -1127,17 +1207,29 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
     }
     scan_write_body(V, hc, ListEmit{a.cand}, a.block_sums, cnt + C_HIT);
     grid.sync();
+    TNB_PHASE_MARK(4);
     body_bucket_insert(a.cand, cnt, sig, a.head, a.next, a.dim, a.stamp);
     grid.sync();
+    TNB_PHASE_MARK(5);
     const int n_cand = cnt[C_CAND];
-    scan_count_body(n_cand, PairCountFn{a.cand, sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount}, a.block_sums);
+    {   // partner search on this CTA's slice of the candidates (8 lanes each), then the slice's sum
+        __shared__ int s_grp[kScanThreads / 8];
+        int64_t begin, end;
+        scan_slice(n_cand, begin, end);
+        pair_count_groups((int)begin, (int)end, a.cand, sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount, a.pcache, s_grp);
+        __syncthreads();
+    }
+    scan_count_body(n_cand, ArrayCount{a.pcount}, a.block_sums);
     grid.sync();
+    TNB_PHASE_MARK(6);
     scan_write_body(n_cand, ArrayCount{a.pcount}, OffsetEmit{a.poff}, a.block_sums, cnt + C_PAIRS);
+    TNB_PHASE_MARK(7);
 }
 
 __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
 {
     cg::grid_group grid = cg::this_grid();
+    TNB_PHASE_MARK(16);
     int *cnt = a.cnt;
     // all decisions are uniform over the grid (same device words read by everybody before any write)
     const int sticky = cnt[C_STICKY], raw = cnt[C_RAW], overflow = cnt[C_OVERFLOW];
@@ -1159,13 +1251,14 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
             return;
         }
         if (P > 0)
-            body_pair_write(a.cand, n_cand, sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount, a.poff, edges + E0 + S);
+            body_pair_write(a.cand, n_cand, sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount, a.poff, edges + E0 + S, a.pcache);
         if (!a.do_prune) {  // the output neuron (subpoly.py:253): sizes only
             if (a.halo) {   // no liveness to exchange, only the status word
                 if (blockIdx.x == 0 && threadIdx.x == 0) a.stage_count[0] = a.stage_count[1] = 0;
                 return;
             }
             grid.sync();
+        TNB_PHASE_MARK(17);
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 cnt[C_V] = Vn;
                 cnt[C_E] = (int)En;
@@ -1175,18 +1268,23 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
         }
         for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += gridDim.x * blockDim.x) a.used[v] = 0;
         grid.sync();
+        TNB_PHASE_MARK(18);
         const KeepCount kc{edges, sig, a.futmask};
         scan_count_body(En, kc, a.block_sums);
         grid.sync();
+        TNB_PHASE_MARK(19);
         scan_write_body(En, kc, KeepEmit{edges, edges_dst, a.used}, a.block_sums, kept);
         grid.sync();
+        TNB_PHASE_MARK(20);
         if (a.halo) {  // ordered lists of the two shared planes' vertices and their liveness
             for (int side = 0; side < 2; ++side) {
                 const TagCount tc{a.tag[pv], 1 << side};
                 scan_count_body(Vn, tc, a.block_sums);
                 grid.sync();
+        TNB_PHASE_MARK(21);
                 scan_write_body(Vn, tc, StageEmit{a.hslot, a.stage[side], a.used, a.stage_cap}, a.block_sums, a.stage_count + side);
                 grid.sync();
+        TNB_PHASE_MARK(22);
             }
             return;  // k_halo_send / k_halo_recv run between the two launches
         }
@@ -1214,16 +1312,20 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
             if ((t & 2) && a.has_upper && a.hslot[v] < a.stage_cap && a.in[1][a.hslot[v]]) a.used[v] = 1;
         }
         grid.sync();
+        TNB_PHASE_MARK(23);
     }
     const FlagCount fc{a.used};
     scan_count_body(Vn, fc, a.block_sums);
     grid.sync();
+        TNB_PHASE_MARK(24);
     scan_write_body(Vn, fc, VertexMoveEmit{a.remap}, a.block_sums, cnt + C_V);
     grid.sync();
+        TNB_PHASE_MARK(25);
     body_move_rows(Vn, a.R, a.used, a.remap,
                    VertexArrays{vert, out, sig, a.tag[pv], a.vert[pv ^ 1], a.out[pv ^ 1], a.sig[pv ^ 1], a.tag[pv ^ 1]});
     body_remap_edges_dev(edges_dst, kept, a.remap);
     if (a.halo) grid.sync();  // every CTA has read the parked count before it is published
+    TNB_PHASE_MARK(31);
     if (blockIdx.x == 0 && threadIdx.x == 0) {  // flip the ping-pong halves
         if (a.halo) cnt[C_E] = cnt[C_KEPT];
         cnt[C_VPAR] = pv ^ 1;
@@ -1394,7 +1496,8 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     }
     // One CTA per SM keeps grid.sync() cheap.  Large complexes keep the multi-launch path with
     // full-size grids (c->V / c->E may be stale upper bounds here: good enough for this choice).
-    const int sm_blocks = std::min(kSMs, std::min(front_blocks_ref, back_blocks));
+    static const int env_blocks = std::getenv("TNB_STEP_BLOCKS") ? std::atoi(std::getenv("TNB_STEP_BLOCKS")) : 0;  // tuning knob
+    const int sm_blocks = std::min(env_blocks > 0 ? env_blocks : kSMs, std::min(front_blocks_ref, back_blocks));
     const int front_blocks = std::min(net->fixed_cfg ? front_blocks_ref : front_blocks_any, sm_blocks);
     const bool fused = planar && front_blocks > 0 && back_blocks > 0 && (halo || (g_fused_steps && c->E + c->V <= kFusedMaxItems));
     if (halo && !fused) { set_error("slab-sharded extraction needs the cooperative step kernels"); return TNB_ERR_UNSUPPORTED; }
@@ -1416,9 +1519,16 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             sa.edges[k] = c->edges[k].p; sa.vert[k] = c->vert[k].p; sa.out[k] = c->out[k].p; sa.sig[k] = c->sig[k].p;
         }
         sa.bmask = c->bmask.p; sa.split_list = c->split_list.p; sa.cand = c->cand.p; sa.pcount = c->pcount.p;
-        sa.poff = c->poff.p; sa.next = c->next.p; sa.used = c->used.p; sa.remap = c->remap.p;
+        sa.poff = c->poff.p; sa.pcache = c->pcache.p; sa.next = c->next.p; sa.used = c->used.p; sa.remap = c->remap.p;
         sa.block_sums = c->block_sums.p; sa.cnt = c->counters.p; sa.head = c->head.p; sa.bytes = c->bytes.p;
         sa.tag[0] = c->tag[0].p; sa.tag[1] = c->tag[1].p;
+        static const bool trace = std::getenv("TNB_PHASE_TRACE") != nullptr;
+        static DevBuf<long long> dbg;
+        if (trace) {
+            TNB_CUDA(dbg.reserve(64));
+            TNB_CUDA(cudaMemsetAsync(dbg.p, 0, 64 * sizeof(long long), s));
+            sa.dbg = dbg.p;
+        }
         sa.halo = halo ? 1 : 0;
         void *fparams[] = {(void *)&m, (void *)&sa};
         void *bparams[] = {(void *)&sa};
@@ -1454,6 +1564,17 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             prof_end(TNB_PROF_PAIRS, s, 0);
         }
         c->counts_stale = true;  // sizes and buffer parity are on the device until the next sync
+        if (trace) {
+            long long h[64];
+            TNB_CUDA(cudaMemcpyAsync(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+            TNB_CUDA(cudaStreamSynchronize(s));
+            fprintf(stderr, "phase-trace idx %d front:", idx);
+            for (int k = 1; k < 16 && h[k]; ++k) fprintf(stderr, " %.1f", (h[k] - h[k - 1]) * 1e-3);
+            fprintf(stderr, " | gap %.1f | back:", h[16] && h[0] ? (h[16] - h[0]) * 1e-3 : 0.0);
+            long long prev = h[16];
+            for (int k = 17; k < 32; ++k) if (h[k]) { fprintf(stderr, " %.1f", (h[k] - prev) * 1e-3); prev = h[k]; }
+            fprintf(stderr, "\n");
+        }
         return TNB_OK;
     }
     // multi-launch path: needs the host's view of sizes and buffer parity to be current
@@ -1516,7 +1637,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             k_bucket_insert<<<g, kThreads, 0, s>>>(c->cand.p, cnt, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp);
             TNB_LAUNCH_CHECK();
             prof_begin(TNB_PROF_PAIRS, s);
-            k_pair_count<<<g, kThreads, 0, s>>>(c->cand.p, cnt, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p);
+            k_pair_count<<<grid_for(cand_ub * 8, kThreads), kThreads, 0, s>>>(c->cand.p, cnt, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->pcache.p);
             TNB_LAUNCH_CHECK();
             prof_end(TNB_PROF_PAIRS, s, 0);
         }
@@ -1554,7 +1675,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     cnt = c->counters.p;
     if (P > 0) {
         prof_begin(TNB_PROF_PAIRS, s);
-        k_pair_write<<<grid_for(n_cand, kThreads), kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S);
+        k_pair_write<<<grid_for(n_cand, kThreads), kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S, c->pcache.p);
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_PAIRS, s, n_cand, (int64_t)n_cand * 28 + (int64_t)P * 8);
     }

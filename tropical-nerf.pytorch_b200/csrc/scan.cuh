@@ -43,7 +43,7 @@ __device__ __forceinline__ int warp_sum(int v)
 __device__ __forceinline__ void scan_slice(int64_t n, int64_t &begin, int64_t &end)
 {
     int64_t per = (n + gridDim.x - 1) / gridDim.x;
-    per = (per + kScanThreads - 1) / kScanThreads * kScanThreads;
+    per = (per + 31) / 32 * 32;  // warp-aligned slices: a short list still spreads over all CTAs
     begin = per * blockIdx.x;
     end = begin + per;
     if (begin > n) begin = n;
