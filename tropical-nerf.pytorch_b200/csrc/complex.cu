@@ -35,7 +35,8 @@ constexpr int kCachedPartners = 12;  // the partner-count pass keeps this many p
 //   C_VPAR / C_EPAR = which half of the ping-pong vertex / edge arrays is current,
 //   C_STICKY = error bits that survive steps (sync-free fused path)
 //   C_KEPT = edges kept by pruning, parked until the slab exchange decides whether the step counts
-enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_NUM = 16 };
+//   C_APAR = which half of the liveness array is current.  C_V counts vertex SLOTS (dead rows included)
+enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_NUM = 16 };
 enum { kErrNoPlane = 1, kErrGradientDescent = 2 };
 enum { kStickyCapacity = 1 };
 
@@ -52,6 +53,8 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
         TNB_CUDA(c->edges[k].reserve(Ecap));
         TNB_CUDA(c->tag[k].reserve(Vcap));
         TNB_CUDA(cudaMemsetAsync(c->tag[k].p, 0, Vcap, current_stream()));
+        TNB_CUDA(c->used[k].reserve(Vcap));
+        TNB_CUDA(cudaMemsetAsync(c->used[k].p, 1, Vcap * sizeof(int), current_stream()));  // nonzero = alive
     }
     TNB_CUDA(c->split_list.reserve(Ecap));
     TNB_CUDA(c->bmask.reserve(Ecap));
@@ -60,7 +63,6 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
     TNB_CUDA(c->poff.reserve(Vcap));
     TNB_CUDA(c->pcache.reserve(Vcap * kCachedPartners));
     TNB_CUDA(c->next.reserve(Vcap * 8));
-    TNB_CUDA(c->used.reserve(Vcap));
     TNB_CUDA(c->remap.reserve(Vcap));
     TNB_CUDA(c->block_sums.reserve(kScanMaxBlocks));
     TNB_CUDA(c->counters.reserve(C_NUM));
@@ -109,9 +111,10 @@ int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
             if ((rc = grow(c->out[k], nc * c->R, keep * c->R, s))) return rc;
             if ((rc = grow(c->sig[k], nc * 3, keep * 3, s))) return rc;
             if ((rc = grow(c->tag[k], nc, keep, s))) return rc;
+            if ((rc = grow(c->used[k], nc, (k == c->acur) ? (size_t)c->V : 0, s))) return rc;
         }
         if ((rc = grow(c->cand, nc, 0, s)) || (rc = grow(c->pcount, nc, 0, s)) || (rc = grow(c->poff, nc, 0, s)) || (rc = grow(c->pcache, nc * kCachedPartners, 0, s)) ||
-            (rc = grow(c->next, nc * 8, 0, s)) || (rc = grow(c->used, nc, 0, s)) || (rc = grow(c->remap, nc, 0, s)))
+            (rc = grow(c->next, nc * 8, 0, s)) || (rc = grow(c->remap, nc, 0, s)))
             return rc;
         c->Vcap = nc;
     }
@@ -126,7 +129,7 @@ int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
     return TNB_OK;
 }
 
-__global__ void k_set_counts(int *__restrict__ cnt, int V, int E, int vpar, int epar);
+__global__ void k_set_counts(int *__restrict__ cnt, int V, int E, int vpar, int epar, int apar);
 
 static int read_counters(tnb_complex *c, cudaStream_t s)
 {
@@ -449,7 +452,7 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
         TNB_LAUNCH_CHECK();
         c->V = V;
         c->E = E;
-        k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E, c->vcur, c->ecur);
+        k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E, c->vcur, c->ecur, c->acur);
         TNB_LAUNCH_CHECK();
         rc = eval_vertices(net, c, 0, V, s);
         if (rc) return rc;
@@ -736,9 +739,10 @@ struct CurveCommitEmit {
 
 struct HitCount {
     const float *out;
+    const int *alive;  // rows of pruned vertices stay in place (complex.cuh): they are not part of the complex
     int R, idx;
     float eps;
-    __device__ __forceinline__ int operator()(int64_t v) const { return fabsf(out[v * R + idx]) < eps ? 1 : 0; }  // subpoly.py:233
+    __device__ __forceinline__ int operator()(int64_t v) const { return (alive[v] && fabsf(out[v * R + idx]) < eps) ? 1 : 0; }  // subpoly.py:233
 };
 
 // candidates = hit old vertices (already in cand[0..H)), then the new ones; publishes the
@@ -1083,18 +1087,20 @@ __global__ void k_remap_edges_dev(int2 *__restrict__ edges, const int *__restric
 {
     body_remap_edges_dev(edges, n_dev, remap);
 }
-__global__ void k_set_counts(int *__restrict__ cnt, int V, int E, int vpar, int epar)
+__global__ void k_set_counts(int *__restrict__ cnt, int V, int E, int vpar, int epar, int apar)
 {
     cnt[C_V] = V;
-    cnt[C_E] = E;
+    if (E >= 0) cnt[C_E] = E;  // E < 0: a compaction just left the edge count there
     cnt[C_VPAR] = vpar;
     cnt[C_EPAR] = epar;
+    cnt[C_APAR] = apar;
 }
 __global__ void k_set_scratch_count(int *__restrict__ p, int v) { *p = v; }
-__global__ void k_set_parity(int *__restrict__ cnt, int vpar, int epar)
+__global__ void k_set_parity(int *__restrict__ cnt, int vpar, int epar, int apar)
 {
     cnt[C_VPAR] = vpar;
     cnt[C_EPAR] = epar;
+    cnt[C_APAR] = apar;
 }
 __global__ void k_clear_step_counters(int *__restrict__ cnt)
 {
@@ -1121,7 +1127,7 @@ struct StepArgs {
     int2 *edges[2];
     float *vert[2], *out[2];
     uint64_t *sig[2], *bmask;
-    int *split_list, *cand, *pcount, *poff, *used, *remap, *block_sums, *cnt, *pcache;
+    int *split_list, *cand, *pcount, *poff, *used[2], *remap, *block_sums, *cnt, *pcache;
     tnb_bucket_rec *next;
     unsigned long long *head, *bytes;  // bytes[0/1]: algorithmic bytes of the front / back halves
     unsigned char *tag[2];
@@ -1176,7 +1182,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
     // slab must go on, another slab may have crossed: halo.cuh)
     if (cnt[C_RAW] == 0 && !a.halo) return;
     body_new_vertices<C>(n, a.idx, a.eps, a.Vcap, a.Ecap, a.split_list, edges, vert, out, sig, a.bmask, cnt, a.tag[pv]);
-    const HitCount hc{out, n.R, a.idx, a.eps};  // old vertices only: independent of the new rows
+    const HitCount hc{out, a.used[cnt[C_APAR]], n.R, a.idx, a.eps};  // old vertices only: independent of the new rows
     scan_count_body(V, hc, a.block_sums);
     grid.sync();
     TNB_PHASE_MARK(3);
@@ -1208,6 +1214,11 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
     scan_write_body(V, hc, ListEmit{a.cand}, a.block_sums, cnt + C_HIT);
     grid.sync();
     TNB_PHASE_MARK(4);
+    if (a.do_prune && !cnt[C_OVERFLOW]) {  // the back half marks the vertices that keep an edge in the idle half of the liveness array
+        int *used = a.used[cnt[C_APAR] ^ 1];
+        const int Vn = V + cnt[C_SPLIT];
+        for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += gridDim.x * blockDim.x) used[v] = 0;
+    }
     body_bucket_insert(a.cand, cnt, sig, a.head, a.next, a.dim, a.stamp);
     grid.sync();
     TNB_PHASE_MARK(5);
@@ -1234,7 +1245,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
     // all decisions are uniform over the grid (same device words read by everybody before any write)
     const int sticky = cnt[C_STICKY], raw = cnt[C_RAW], overflow = cnt[C_OVERFLOW];
     const int S = cnt[C_SPLIT], P = cnt[C_PAIRS], V0 = cnt[C_V], E0 = cnt[C_E], n_cand = cnt[C_CAND];
-    const int pv = cnt[C_VPAR], pe = cnt[C_EPAR];
+    const int pv = cnt[C_VPAR], pe = cnt[C_EPAR], pa = cnt[C_APAR];
     const int local_flag = cnt[C_FLAG];
     const int word = a.part == 2 ? a.stage_count[2] : 0;  // OR of every slab's status word
     if (sticky) return;
@@ -1242,8 +1253,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
     const int64_t En = (int64_t)E0 + S + P;
     const int Vn = V0 + S;
     int2 *edges = a.edges[pe], *edges_dst = a.edges[pe ^ 1];
-    float *vert = a.vert[pv], *out = a.out[pv];
+    float *out = a.out[pv];
     uint64_t *sig = a.sig[pv];
+    int *alive = a.used[pa], *used = a.used[pa ^ 1];  // `used` was cleared by the front half
     int *kept = a.halo ? cnt + C_KEPT : cnt + C_E;
     if (a.part != 2) {
         if (overflow || En > a.Ecap) {  // the host re-runs the extraction with larger arrays
@@ -1257,8 +1269,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
                 if (blockIdx.x == 0 && threadIdx.x == 0) a.stage_count[0] = a.stage_count[1] = 0;
                 return;
             }
+            for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) alive[V0 + k] = 1;
             grid.sync();
-        TNB_PHASE_MARK(17);
+            TNB_PHASE_MARK(17);
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 cnt[C_V] = Vn;
                 cnt[C_E] = (int)En;
@@ -1266,14 +1279,13 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
             }
             return;
         }
-        for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += gridDim.x * blockDim.x) a.used[v] = 0;
         grid.sync();
         TNB_PHASE_MARK(18);
         const KeepCount kc{edges, sig, a.futmask};
         scan_count_body(En, kc, a.block_sums);
         grid.sync();
         TNB_PHASE_MARK(19);
-        scan_write_body(En, kc, KeepEmit{edges, edges_dst, a.used}, a.block_sums, kept);
+        scan_write_body(En, kc, KeepEmit{edges, edges_dst, used}, a.block_sums, kept);
         grid.sync();
         TNB_PHASE_MARK(20);
         if (a.halo) {  // ordered lists of the two shared planes' vertices and their liveness
@@ -1281,10 +1293,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
                 const TagCount tc{a.tag[pv], 1 << side};
                 scan_count_body(Vn, tc, a.block_sums);
                 grid.sync();
-        TNB_PHASE_MARK(21);
-                scan_write_body(Vn, tc, StageEmit{a.hslot, a.stage[side], a.used, a.stage_cap}, a.block_sums, a.stage_count + side);
+                TNB_PHASE_MARK(21);
+                scan_write_body(Vn, tc, StageEmit{a.hslot, a.stage[side], used, a.stage_cap}, a.block_sums, a.stage_count + side);
                 grid.sync();
-        TNB_PHASE_MARK(22);
+                TNB_PHASE_MARK(22);
             }
             return;  // k_halo_send / k_halo_recv run between the two launches
         }
@@ -1298,40 +1310,38 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
                 for (uint64_t m = a.bmask[k]; m; m &= m - 1) out[((int64_t)V0 + k) * a.R + __ffsll((long long)m) - 1] = 0.0f;
         }
         if (!a.do_prune) {
+            for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) alive[V0 + k] = 1;
+            grid.sync();  // everybody has read the counter block
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 cnt[C_V] = Vn;
                 cnt[C_E] = (int)En;
             }
             return;
         }
-        // a vertex on a shared plane lives if an edge on EITHER side of the plane keeps it
-        const unsigned char *tag = a.tag[pv];
+        // a vertex on a shared plane lives if an edge on EITHER side of the plane keeps it; a dead
+        // vertex leaves the plane lists for good (both sides agree on who died)
+        unsigned char *tag = a.tag[pv];
         for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += gridDim.x * blockDim.x) {
             const int t = tag[v];
-            if ((t & 1) && a.has_lower && a.hslot[v] < a.stage_cap && a.in[0][a.hslot[v]]) a.used[v] = 1;
-            if ((t & 2) && a.has_upper && a.hslot[v] < a.stage_cap && a.in[1][a.hslot[v]]) a.used[v] = 1;
+            int u = used[v];
+            if ((t & 1) && a.has_lower && a.hslot[v] < a.stage_cap && a.in[0][a.hslot[v]]) u = 1;
+            if ((t & 2) && a.has_upper && a.hslot[v] < a.stage_cap && a.in[1][a.hslot[v]]) u = 1;
+            used[v] = u;
+            if (!u && t) tag[v] = 0;
         }
-        grid.sync();
+        grid.sync();  // everybody has read the counter block (the parked edge count among it)
         TNB_PHASE_MARK(23);
     }
-    const FlagCount fc{a.used};
-    scan_count_body(Vn, fc, a.block_sums);
-    grid.sync();
-        TNB_PHASE_MARK(24);
-    scan_write_body(Vn, fc, VertexMoveEmit{a.remap}, a.block_sums, cnt + C_V);
-    grid.sync();
-        TNB_PHASE_MARK(25);
-    body_move_rows(Vn, a.R, a.used, a.remap,
-                   VertexArrays{vert, out, sig, a.tag[pv], a.vert[pv ^ 1], a.out[pv ^ 1], a.sig[pv ^ 1], a.tag[pv ^ 1]});
-    body_remap_edges_dev(edges_dst, kept, a.remap);
-    if (a.halo) grid.sync();  // every CTA has read the parked count before it is published
+    // Commit: the freshly marked half of the liveness array and the compacted half of the edge
+    // array become current.  The rows of dead vertices stay where they are (complex.cuh).
     TNB_PHASE_MARK(31);
-    if (blockIdx.x == 0 && threadIdx.x == 0) {  // flip the ping-pong halves
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
         if (a.halo) cnt[C_E] = cnt[C_KEPT];
-        cnt[C_VPAR] = pv ^ 1;
+        cnt[C_V] = Vn;
         cnt[C_EPAR] = pe ^ 1;
+        cnt[C_APAR] = pa ^ 1;
         a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8 + (unsigned long long)En * (8 + 2 * 48) +
-                      (unsigned long long)Vn * (4 + 2 * (36 + 4 * a.R));
+                      (unsigned long long)Vn * 8;
     }
 }
 
@@ -1358,6 +1368,7 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
     c->E = c->h_counters[C_E];
     c->vcur = c->h_counters[C_VPAR];
     c->ecur = c->h_counters[C_EPAR];
+    c->acur = c->h_counters[C_APAR];
     c->counts_stale = false;
     if (c->bytes.p) {  // algorithmic bytes the fused kernels accumulated on the device
         unsigned long long hb[2] = {0, 0};
@@ -1519,7 +1530,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             sa.edges[k] = c->edges[k].p; sa.vert[k] = c->vert[k].p; sa.out[k] = c->out[k].p; sa.sig[k] = c->sig[k].p;
         }
         sa.bmask = c->bmask.p; sa.split_list = c->split_list.p; sa.cand = c->cand.p; sa.pcount = c->pcount.p;
-        sa.poff = c->poff.p; sa.pcache = c->pcache.p; sa.next = c->next.p; sa.used = c->used.p; sa.remap = c->remap.p;
+        sa.poff = c->poff.p; sa.pcache = c->pcache.p; sa.next = c->next.p; sa.used[0] = c->used[0].p; sa.used[1] = c->used[1].p; sa.remap = c->remap.p;
         sa.block_sums = c->block_sums.p; sa.cnt = c->counters.p; sa.head = c->head.p; sa.bytes = c->bytes.p;
         sa.tag[0] = c->tag[0].p; sa.tag[1] = c->tag[1].p;
         static const bool trace = std::getenv("TNB_PHASE_TRACE") != nullptr;
@@ -1564,6 +1575,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             prof_end(TNB_PROF_PAIRS, s, 0);
         }
         c->counts_stale = true;  // sizes and buffer parity are on the device until the next sync
+        if (sa.do_prune) c->maybe_dead = true;
         if (trace) {
             long long h[64];
             TNB_CUDA(cudaMemcpyAsync(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost, s));
@@ -1580,6 +1592,8 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     // multi-launch path: needs the host's view of sizes and buffer parity to be current
     if ((rc = complex_sync_counts(c, s))) return rc;
     if (c->E == 0) return TNB_OK;
+    // dead rows cost a little in every per-vertex pass: squeeze them out once they fill half the arrays
+    if (c->maybe_dead && (size_t)c->V * 2 > c->Vcap && (rc = complex_compact(c, s))) return rc;
     cnt = c->counters.p;
 
     for (int attempt = 0;; ++attempt) {
@@ -1622,7 +1636,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             TNB_LAUNCH_CHECK();
         }
         // 3. candidates for connecting edges: old vertices on the plane, then the new ones
-        HitCount hc{c->cout_(), R, idx, eps};
+        HitCount hc{c->cout_(), c->calive(), R, idx, eps};
         if ((rc = compact(c->V, hc, ListEmit{c->cand.p}, c->block_sums.p, cnt + C_HIT, s, cnt + C_V))) return rc;
         const int64_t cand_ub = std::min<int64_t>(c->V + c->E, (int64_t)c->Vcap);
         k_fill_new_cands<<<grid_for(c->E, 256), 256, 0, s>>>(c->cand.p, cnt);
@@ -1682,32 +1696,56 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     c->V = V0 + S;
     c->E = (int64_t)E0 + S + P;
 
-    // 4. pruning (not for the output neuron, subpoly.py:253); its sizes stay on the device
+    // 4. pruning (not for the output neuron, subpoly.py:253): edges are compacted, vertices only
+    //    marked (complex.cuh); the edge count stays on the device
     if (h < H) {
         const uint64_t futmask = ~colmask & (R >= 64 ? ~0ull : ((1ull << R) - 1ull));
-        TNB_CUDA(cudaMemsetAsync(c->used.p, 0, (size_t)c->V * sizeof(int), s));
+        int *used = c->used[c->acur ^ 1].p;
+        TNB_CUDA(cudaMemsetAsync(used, 0, (size_t)c->V * sizeof(int), s));
         KeepCount kc{c->cedges(), c->csig(), futmask};
         int2 *dst = c->edges[c->ecur ^ 1].p;
-        if ((rc = compact(c->E, kc, KeepEmit{c->cedges(), dst, c->used.p}, c->block_sums.p, cnt + C_E, s))) return rc;
-        const int o = c->vcur ^ 1;
-        k_set_scratch_count<<<1, 1, 0, s>>>(cnt + C_KEPT, (int)c->V);  // vertices before the compaction, for k_move_rows
-        TNB_LAUNCH_CHECK();
-        if ((rc = compact(c->V, FlagCount{c->used.p}, VertexMoveEmit{c->remap.p}, c->block_sums.p, cnt + C_V, s))) return rc;
-        k_move_rows<<<grid_for(c->V * R, 256, kSMs * 8), 256, 0, s>>>(cnt + C_KEPT, R, c->used.p, c->remap.p,
-            VertexArrays{c->cvert(), c->cout_(), c->csig(), c->tag[c->vcur].p, c->vert[o].p, c->out[o].p, c->sig[o].p, c->tag[o].p});
-        TNB_LAUNCH_CHECK();
+        if ((rc = compact(c->E, kc, KeepEmit{c->cedges(), dst, used}, c->block_sums.p, cnt + C_E, s))) return rc;
         c->ecur ^= 1;
-        c->vcur = o;
-        k_remap_edges_dev<<<grid_for(c->E, 256), 256, 0, s>>>(c->cedges(), cnt + C_E, c->remap.p);
+        c->acur ^= 1;
+        k_set_counts<<<1, 1, 0, s>>>(cnt, (int)c->V, -1, c->vcur, c->ecur, c->acur);  // the fused kernels read sizes and parity on the device
         TNB_LAUNCH_CHECK();
-        k_set_parity<<<1, 1, 0, s>>>(cnt, c->vcur, c->ecur);  // the fused kernels read the parity on the device
-        TNB_LAUNCH_CHECK();
-        c->counts_stale = true;  // c->V, c->E are upper bounds until the next sync
+        c->maybe_dead = true;
+        c->counts_stale = true;  // c->E is an upper bound until the next sync
     } else {
-        k_set_counts<<<1, 1, 0, s>>>(cnt, (int)c->V, (int)c->E, c->vcur, c->ecur);
+        TNB_CUDA(cudaMemsetAsync(c->calive() + V0, 1, (size_t)S * sizeof(int), s));  // the new vertices are alive
+        k_set_counts<<<1, 1, 0, s>>>(cnt, (int)c->V, (int)c->E, c->vcur, c->ecur, c->acur);
         TNB_LAUNCH_CHECK();
     }
     return TNB_OK;
+}
+
+// Drop the rows of dead vertices (order preserving) and renumber the edges: what the reference
+// does after every hyperplane (subpoly.py:268-277), done here once, when the complex is read.
+int complex_compact(tnb_complex *c, cudaStream_t s)
+{
+    int rc;
+    if ((rc = complex_sync_counts(c, s))) return rc;
+    if (!c->maybe_dead) return TNB_OK;
+    c->maybe_dead = false;
+    if (c->V == 0) return TNB_OK;
+    int *cnt = c->counters.p;
+    const int o = c->vcur ^ 1, R = c->R;
+    k_set_scratch_count<<<1, 1, 0, s>>>(cnt + C_KEPT, (int)c->V);  // slots before the compaction, for k_move_rows
+    TNB_LAUNCH_CHECK();
+    if ((rc = compact(c->V, FlagCount{c->calive()}, VertexMoveEmit{c->remap.p}, c->block_sums.p, cnt + C_V, s))) return rc;
+    k_move_rows<<<grid_for(c->V * R, 256, kSMs * 8), 256, 0, s>>>(cnt + C_KEPT, R, c->calive(), c->remap.p,
+        VertexArrays{c->cvert(), c->cout_(), c->csig(), c->tag[c->vcur].p, c->vert[o].p, c->out[o].p, c->sig[o].p, c->tag[o].p});
+    TNB_LAUNCH_CHECK();
+    c->vcur = o;
+    if (c->E > 0) {
+        k_remap_edges_dev<<<grid_for(c->E, 256), 256, 0, s>>>(c->cedges(), cnt + C_E, c->remap.p);
+        TNB_LAUNCH_CHECK();
+    }
+    TNB_CUDA(cudaMemsetAsync(c->calive(), 1, (size_t)c->V * sizeof(int), s));  // what is left is alive
+    k_set_parity<<<1, 1, 0, s>>>(cnt, c->vcur, c->ecur, c->acur);
+    TNB_LAUNCH_CHECK();
+    c->counts_stale = true;
+    return complex_sync_counts(c, s);
 }
 
 // ---- hypercube fallback (subpoly.py:51-52, :731-750) -----------------------------------------------
@@ -1752,7 +1790,7 @@ static int from_arrays_impl(const tnb_net *net, const float *d_vertices, int64_t
     }
     c->V = V;
     c->E = E;
-    k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E, c->vcur, c->ecur);
+    k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E, c->vcur, c->ecur, c->acur);
     TNB_LAUNCH_CHECK();
     return eval_vertices(net, c, 0, V, s);
 }
@@ -1929,7 +1967,8 @@ void tnb_complex_destroy(tnb_complex *c) { delete c; }
 int64_t tnb_complex_num_vertices(const tnb_complex *c)
 {
     if (!c) return 0;
-    complex_sync_counts(const_cast<tnb_complex *>(c), c->stream);
+    current_stream() = c->stream;
+    complex_compact(const_cast<tnb_complex *>(c), c->stream);
     return c->V;
 }
 int64_t tnb_complex_num_edges(const tnb_complex *c)
@@ -1944,7 +1983,7 @@ int tnb_complex_read(const tnb_complex *c, float *d_vertices, int64_t *d_edges, 
     if (!c) { set_error("tnb_complex_read: null complex"); return TNB_ERR_INVALID; }
     cudaStream_t s = (cudaStream_t)stream;
     current_stream() = s;
-    int rcs = complex_sync_counts(const_cast<tnb_complex *>(c), s);
+    int rcs = complex_compact(const_cast<tnb_complex *>(c), s);
     if (rcs) return rcs;
     if (d_vertices && c->V) TNB_CUDA(cudaMemcpyAsync(d_vertices, c->cvert(), (size_t)c->V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (d_outputs && c->V) TNB_CUDA(cudaMemcpyAsync(d_outputs, c->cout_(), (size_t)c->V * c->R * sizeof(float), cudaMemcpyDeviceToDevice, s));

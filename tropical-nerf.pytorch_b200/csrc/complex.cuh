@@ -7,8 +7,16 @@
 //   out   [V][R] f32   cached Net.forward(gather=True) row (subpoly.py:92-95, :275)
 //   sig   [V][3] u64   packed region indicator {pos bits, neg bits, grid word}
 //   edges [E]    int2  vertex pair (first, second) in the reference's column order
-// Vertex arrays and the edge array are double-buffered: pruning compacts from one set
-// into the other (order preserving) and flips.
+//   used  [V]    int   liveness: pruning (subpoly.py:268-272) only MARKS a vertex dead; its row stays
+//                      where it is and no edge refers to it any more.  Every order the reference
+//                      derives from vertex numbers (ascending partner lists, face-row leaders, the
+//                      final numbering) depends on relative order only, which lazy deletion keeps, so
+//                      the rows are compacted once, when somebody reads the complex
+//                      (complex_compact), not after each of the 33 hyperplanes.
+// The edge array is double-buffered: pruning compacts it from one half into the other (order
+// preserving) and flips.  The vertex arrays are double-buffered for complex_compact and for the
+// curve path's temporary rows; the liveness array is double-buffered so that a step that is
+// abandoned half-way (slab exchange: no slab crossed the plane) leaves it intact.
 // One entry of a cell bucket (generation-stamped linked lists over the marks-grid cells).  The
 // candidate's packed sign vector travels with the link, so walking a list costs ONE dependent
 // 32-byte load per hop instead of link -> candidate -> signature.
@@ -40,7 +48,8 @@ struct tnb_complex {
     int R = 0;
     int64_t V = 0, E = 0;
     size_t Vcap = 0, Ecap = 0;
-    int vcur = 0, ecur = 0;
+    int vcur = 0, ecur = 0, acur = 0;
+    bool maybe_dead = false;        // a prune ran since the last compaction: rows of dead vertices may exist
     tnb::DevBuf<float> vert[2], out[2];
     tnb::DevBuf<uint64_t> sig[2];
     tnb::DevBuf<int2> edges[2];
@@ -55,7 +64,7 @@ struct tnb_complex {
     tnb::DevBuf<int> pcache;        // [6*Vcap] first partners of each candidate, left by the count pass
     tnb::DevBuf<tnb_bucket_rec> next;  // [8*Vcap] bucket chains
     tnb::DevBuf<unsigned long long> head;  // [n_cells] (stamp << 32 | record)
-    tnb::DevBuf<int> used;          // [Vcap]   vertex referenced by a kept edge
+    tnb::DevBuf<int> used[2];       // [Vcap]   vertex referenced by a kept edge; used[acur] = liveness of the current complex
     tnb::DevBuf<int> remap;         // [Vcap]
     tnb::DevBuf<int> block_sums;    // [kScanMaxBlocks]
     tnb::DevBuf<int> counters;      // [16] device counters
@@ -75,6 +84,8 @@ struct tnb_complex {
     const float *cout_() const { return out[vcur].p; }
     const uint64_t *csig() const { return sig[vcur].p; }
     const int2 *cedges() const { return edges[ecur].p; }
+    int *calive() { return used[acur].p; }
+    const int *calive() const { return used[acur].p; }
     ~tnb_complex();
 };
 
@@ -82,6 +93,7 @@ namespace tnb {
 int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap);
 int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s);
 int complex_sync_counts(tnb_complex *c, cudaStream_t s);
+int complex_compact(tnb_complex *c, cudaStream_t s);  // drop the rows of dead vertices (order preserving), renumber the edges
 int launch_outputs(const tnb_net *net, const float *d_x, int64_t n, float *d_out, cudaStream_t s);
 int launch_sdf_grad(const tnb_net *net, const float *d_x, int64_t n, float *d_sdf, float *d_grad, cudaStream_t s);
 int launch_region(const tnb_net *net, const float *d_x, const float *d_outputs, int64_t n, float eps,

@@ -47,14 +47,15 @@ enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_
 
 // ---- surface skeleton -----------------------------------------------------------------------------
 __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
-                                const float *__restrict__ out, int64_t V, float eps, int *__restrict__ surf,
-                                int *__restrict__ counters)
+                                const float *__restrict__ out, const int *__restrict__ alive, int64_t V, float eps,
+                                int *__restrict__ surf, int *__restrict__ counters)
 {
     int local = 0;
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
         float x[3] = {vert[3 * v], vert[3 * v + 1], vert[3 * v + 2]}, xp[3];
         preprocess(n, x, xp);
-        bool on = fabsf(out[v * n.R + n.R - 1]) < eps;
+        // rows of pruned vertices are still in place (complex.cuh): they are not part of the complex
+        bool on = alive[v] && fabsf(out[v * n.R + n.R - 1]) < eps;
         for (int d = 0; d < 3; ++d)
             if (xp[d] > 1.0f || xp[d] < 0.0f) on = false;
         surf[v] = on ? 1 : 0;
@@ -69,11 +70,13 @@ __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *
 // exist on both slabs.  A vertex strictly inside one slab but within eps of the plane is seen by
 // the reference from the cells on both sides; the neighbour slab does not have it.  They are
 // counted here so that a run can say whether it was exact.
-__global__ void k_count_near_plane(const uint64_t *__restrict__ sig, const unsigned char *__restrict__ tag, int64_t V,
-                                   int plane_lo, int plane_hi, int *__restrict__ counters)
+__global__ void k_count_near_plane(const uint64_t *__restrict__ sig, const unsigned char *__restrict__ tag,
+                                   const int *__restrict__ alive, int64_t V, int plane_lo, int plane_hi,
+                                   int *__restrict__ counters)
 {
     int local = 0;
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+        if (!alive[v]) continue;
         const uint64_t g = sig[3 * v + 2];
         if (grid_mask(g, 0)) continue;
         const int off = grid_off(g, 0), t = tag[v];
@@ -533,7 +536,7 @@ static int extract_begin_impl(const tnb_net *net, tnb_complex *c, float eps, tnb
     TNB_CUDA(cudaMemsetAsync(m->used.p, 0, (size_t)std::max<int64_t>(V, 1) * sizeof(int), s));
     TNB_CUDA(m->tmp_edges.reserve((size_t)std::max<int64_t>(E, 1)));
     if (V > 0) {
-        k_surface_flags<<<grid_for(V, 256), 256, 0, s>>>(nm, c->cvert(), c->cout_(), V, eps, m->surf.p, m->counters.p);
+        k_surface_flags<<<grid_for(V, 256), 256, 0, s>>>(nm, c->cvert(), c->cout_(), c->calive(), V, eps, m->surf.p, m->counters.p);
         TNB_LAUNCH_CHECK();
         DevBuf<int> block_sums;
         TNB_CUDA(block_sums.reserve(kScanMaxBlocks));
@@ -542,7 +545,7 @@ static int extract_begin_impl(const tnb_net *net, tnb_complex *c, float eps, tnb
             return rc;
     }
     if (c->halo.enabled && V > 0) {
-        k_count_near_plane<<<grid_for(V, 256), 256, 0, s>>>(c->csig(), c->tag[c->vcur].p, V, c->halo.tag_lower ? c->halo.x_lo : -7,
+        k_count_near_plane<<<grid_for(V, 256), 256, 0, s>>>(c->csig(), c->tag[c->vcur].p, c->calive(), V, c->halo.tag_lower ? c->halo.x_lo : -7,
                                                             c->halo.tag_upper ? c->halo.x_hi : -7, m->counters.p);
         TNB_LAUNCH_CHECK();
     }
