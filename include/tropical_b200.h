@@ -124,6 +124,13 @@ int tnb_complex_read(const tnb_complex *c, float *d_vertices, int64_t *d_edges, 
 int tnb_subpoly_step(const tnb_net *net, tnb_complex *c, int32_t l, int32_t h, float eps,
                      int32_t force, void *stream);
 
+/* The loop over hyperplanes of subpoly() (subpoly.py:58-72) in one call: lh[2*i], lh[2*i+1] =
+ * (l, h) of step i.  Same result as n_steps calls of tnb_subpoly_step; a small complex on the
+ * planar path runs all of them in ONE launch of one thread-block cluster (no host round trip
+ * and no grid-wide barrier between steps). */
+int tnb_subpoly_steps(const tnb_net *net, tnb_complex *c, const int32_t *lh, int32_t n_steps, float eps,
+                      int32_t force, void *stream);
+
 /* extract_skeleton + extract_faces (subpoly.py:556-652). */
 int tnb_extract_mesh(const tnb_net *net, const tnb_complex *c, float eps, tnb_mesh **out,
                      void *stream);
@@ -202,6 +209,10 @@ int64_t tnb_mesh_near_plane(const tnb_mesh *m);
 /* ---- knobs / introspection ------------------------------------------------------ */
 /* work-buffer growth factor for the complex (default 4.0) */
 int tnb_set_capacity_factor(double f);
+/* tnb_subpoly_steps / tnb_subpoly run the hyperplanes of a complex with at most `items`
+ * vertices + edges as one thread-block-cluster launch (default 200000, env
+ * TNB_CLUSTER_MAX_ITEMS; 0 = never).  Returns the previous value; items < 0 only queries. */
+int64_t tnb_set_cluster_max_items(int64_t items);
 /* number of CUDA kernels this library launched on the calling thread since the last
  * reset (bench.py's gpu_launches) */
 int64_t tnb_launch_count(void);

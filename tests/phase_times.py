@@ -13,11 +13,8 @@ for rep in range(4):
     e = [ev() for _ in range(4)]
     t0 = time.perf_counter()
     e[0].record(); c = net.skeleton(128); e[1].record()
-    sizes = []
-    for l in range(net.num_layers - 1):
-        for h in range(net.num_hidden):
-            c.step(l, h)
-    c.step(net.num_layers - 2, net.num_hidden); e[2].record()
+    lh = [(l, h) for l in range(net.num_layers - 1) for h in range(net.num_hidden)] + [(net.num_layers - 2, net.num_hidden)]
+    c.steps(lh); e[2].record()
     m = c.extract_mesh(); e[3].record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()

@@ -322,3 +322,58 @@ def test_empty_and_caller_supplied_inputs():
     c0.step(0, 0)
     assert c0.num_edges == 0
     assert c0.extract_mesh().sizes()["T"] == 0
+
+
+def _all_steps(P):
+    H = P.num_hidden
+    return [(l, h) for l in range(P.num_layers - 1) for h in range(H)] + [(P.num_layers - 2, H)]
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_cluster_steps_equal_single_steps(case):
+    """All hyperplanes in ONE persistent launch (tnb_subpoly_steps; here by a single thread-block
+    cluster) leave exactly the complex that 33 separate tnb_subpoly_step calls (cooperative grid)
+    leave, and the oracle's; prefixes of the step list too (the device-side step loop has no host
+    in between)."""
+    from oracle import subpoly_ref as R
+    from tropical._native import lib
+    g = load_golden(case)
+    P = oracle_net(g)
+    N = native_net(P)
+    steps = _all_steps(P)
+    before = lib().tnb_set_cluster_max_items(-1)
+    try:
+        for upto in (len(steps), 7):
+            lib().tnb_set_cluster_max_items(0)          # one persistent cooperative-grid launch per step
+            a = N.skeleton(128)
+            for l, h in steps[:upto]:
+                a.step(l, h)
+            va, ea, oa = [t.cpu().numpy() for t in a.read()]
+            lib().tnb_set_cluster_max_items(1 << 40)    # one cluster launch for the whole list
+            b = N.skeleton(128)
+            b.steps(steps[:upto])
+            vb, eb, ob = [t.cpu().numpy() for t in b.read()]
+            assert np.array_equal(ea, eb) and np.array_equal(va, vb) and np.array_equal(oa, ob), upto
+    finally:
+        lib().tnb_set_cluster_max_items(before)
+    vo, eo = R.skeleton(P)
+    oo = P.outputs(vo)
+    for l, h in steps[:7]:
+        vo, eo, oo = R.subpoly_step(P, vo, eo, oo, l, h, 1e-4)
+    assert np.array_equal(eb, eo) and np.array_equal(vb, vo) and np.array_equal(ob, oo)
+
+
+def test_whole_path_same_mesh_with_and_without_cluster_launch():
+    from tropical._native import lib
+    g = load_golden("small_sphere")
+    N = native_net(oracle_net(g))
+    before = lib().tnb_set_cluster_max_items(-1)
+    try:
+        lib().tnb_set_cluster_max_items(0)
+        m0 = [a.cpu().numpy() for a in N.subpoly().read()]
+        lib().tnb_set_cluster_max_items(1 << 40)
+        m1 = [a.cpu().numpy() for a in N.subpoly().read()]
+    finally:
+        lib().tnb_set_cluster_max_items(before)
+    for x, y in zip(m0, m1):
+        assert np.array_equal(x, y)

@@ -494,22 +494,15 @@ struct ListEmit {
 
 // new vertex of every split edge: position (subpoly.py:113-117, :180), network row, the
 // failover mask of subpoly_debug.py:37-43, edge rewiring (subpoly.py:210-215)
+// k-th split edge of the step -> vertex V + k; returns whether the failover override fires
 template <class C>
-__device__ __forceinline__ void body_new_vertices(const NetMeta &n, int idx, float eps,
-                                                           int Vcap, int Ecap, const int *split_list,
-                                                           int2 *edges, float *vert,
-                                                           float *out, const uint64_t *sig,
-                                                           uint64_t *bmask, int *cnt, unsigned char *tag)
+__device__ __forceinline__ int new_vertex_item(const NetMeta &n, int idx, float eps, int k, int V, int E, const int *split_list,
+                                               int2 *edges, float *vert, float *out, const uint64_t *sig, uint64_t *bmask,
+                                               unsigned char *tag)
 {
     const int R = n.R;
-    const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
-    if ((int64_t)V + S > Vcap || (int64_t)E + S > Ecap) {  // host grows the arrays and re-runs
-        if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_OVERFLOW] = 1;
-        return;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_SPLIT] = S;  // planar path: every crossed edge is split
     int any = 0;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
+    {
         const int e = split_list[k];
         const int2 ed = edges[e];
         const float d0 = __fdiv_rn(out[(int64_t)ed.x * R + idx], eps), d1 = __fdiv_rn(out[(int64_t)ed.y * R + idx], eps);
@@ -535,6 +528,25 @@ __device__ __forceinline__ void body_new_vertices(const NetMeta &n, int idx, flo
         edges[e].y = (int)nv;                    // left part keeps the first endpoint
         edges[E + k] = make_int2(ed.y, (int)nv); // right part
     }
+    return any;
+}
+
+template <class C>
+__device__ __forceinline__ void body_new_vertices(const NetMeta &n, int idx, float eps,
+                                                           int Vcap, int Ecap, const int *split_list,
+                                                           int2 *edges, float *vert,
+                                                           float *out, const uint64_t *sig,
+                                                           uint64_t *bmask, int *cnt, unsigned char *tag)
+{
+    const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
+    if ((int64_t)V + S > Vcap || (int64_t)E + S > Ecap) {  // host grows the arrays and re-runs
+        if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_OVERFLOW] = 1;
+        return;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_SPLIT] = S;  // planar path: every crossed edge is split
+    int any = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x)
+        any |= new_vertex_item<C>(n, idx, eps, k, V, E, split_list, edges, vert, out, sig, bmask, tag);
     if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
 }
 
@@ -551,15 +563,11 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant
 
 // apply the failover override when any new vertex violated it, then bit-pack the region
 // indicator of the new vertices
-__device__ __forceinline__ void body_finalize_new(const NetMeta &n,
-                                                           const float *vert, float *out,
-                                                           uint64_t *sig, const uint64_t *bmask,
-                                                           const int *cnt)
+__device__ __forceinline__ void finalize_item(const NetMeta &n, const float *vert, float *out, uint64_t *sig,
+                                              const uint64_t *bmask, int flag, int V, int k)
 {
     const int R = n.R;
-    if (cnt[C_OVERFLOW]) return;
-    const int flag = cnt[C_FLAG], S = cnt[C_SPLIT], V = cnt[C_V];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
+    {
         const int64_t v = (int64_t)V + k;
         float *row = out + v * R;
         if (flag)
@@ -572,6 +580,15 @@ __device__ __forceinline__ void body_finalize_new(const NetMeta &n,
         sig[3 * v + 1] = neg;
         sig[3 * v + 2] = pack_grid(n, n.marks, xp, n.eps);
     }
+}
+__device__ __forceinline__ void body_finalize_new(const NetMeta &n,
+                                                           const float *vert, float *out,
+                                                           uint64_t *sig, const uint64_t *bmask,
+                                                           const int *cnt)
+{
+    if (cnt[C_OVERFLOW]) return;
+    const int flag = cnt[C_FLAG], S = cnt[C_SPLIT], V = cnt[C_V];
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) finalize_item(n, vert, out, sig, bmask, flag, V, k);
 }
 
 __global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant__ NetMeta n,
@@ -781,13 +798,10 @@ __device__ __forceinline__ int64_t cell_id(int cx, int cy, int cz, int dim)
     return ((int64_t)(cx + 2) * dim + (cy + 2)) * dim + (cz + 2);
 }
 
-__device__ __forceinline__ void body_bucket_insert(const int *cand, const int *cnt,
-                                const uint64_t *sig, unsigned long long *head,
-                                tnb_bucket_rec *next, int dim, uint32_t stamp)
+__device__ __forceinline__ void bucket_insert_item(int c, int v, const uint64_t *sig, unsigned long long *head,
+                                                   tnb_bucket_rec *next, int dim, uint32_t stamp)
 {
-    const int n_cand = cnt[C_CAND];
-    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += gridDim.x * blockDim.x) {
-        const int v = cand[c];
+    {
         tnb_bucket_rec r;
         r.v = v;
         r.pos = sig[3 * (int64_t)v];
@@ -805,6 +819,14 @@ __device__ __forceinline__ void body_bucket_insert(const int *cand, const int *c
                     next[rec] = r;
                 }
     }
+}
+__device__ __forceinline__ void body_bucket_insert(const int *cand, const int *cnt,
+                                const uint64_t *sig, unsigned long long *head,
+                                tnb_bucket_rec *next, int dim, uint32_t stamp)
+{
+    const int n_cand = cnt[C_CAND];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += gridDim.x * blockDim.x)
+        bucket_insert_item(c, cand[c], sig, head, next, dim, stamp);
 }
 
 __global__ void __launch_bounds__(kThreads) k_bucket_insert(const int *__restrict__ cand, const int *__restrict__ cnt,
@@ -941,16 +963,14 @@ struct OffsetEmit {
     __device__ __forceinline__ void operator()(int64_t i, int pos, int) const { off[i] = pos; }
 };
 
-__device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
-                                                         const uint64_t *sig,
-                                                         const unsigned long long *head,
-                                                         const tnb_bucket_rec *next, int dim, uint32_t stamp,
-                                                         uint64_t colmask, const int *pcount,
-                                                         const int *poff, int2 *edges_out, const int *pcache)
+__device__ __forceinline__ void pair_write_item(int a, const int *cand, const uint64_t *sig,
+                                                const unsigned long long *head, const tnb_bucket_rec *next, int dim,
+                                                uint32_t stamp, uint64_t colmask, const int *pcount, const int *poff,
+                                                int2 *edges_out, const int *pcache)
 {
-    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x) {
+    {
         const int c = pcount[a];
-        if (c == 0) continue;
+        if (c == 0) return;
         const int va = cand[a];
         int2 *dst = edges_out + poff[a];
         // ascending partner number = the order unique(dim=0) leaves (subpoly.py:243-244)
@@ -978,6 +998,16 @@ __device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
             for (int i = 0; i < c; ++i) dst[i].x = va;
         }
     }
+}
+__device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
+                                                         const uint64_t *sig,
+                                                         const unsigned long long *head,
+                                                         const tnb_bucket_rec *next, int dim, uint32_t stamp,
+                                                         uint64_t colmask, const int *pcount,
+                                                         const int *poff, int2 *edges_out, const int *pcache)
+{
+    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x)
+        pair_write_item(a, cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache);
 }
 
 __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__ cand, int n_cand,
@@ -1119,11 +1149,9 @@ namespace cg = cooperative_groups;
 // current (C_VPAR / C_EPAR), capacity checks and sticky error bits (C_STICKY).  The host can
 // therefore enqueue all 33 steps back to back and sync ONCE at the end.
 struct StepArgs {
-    int idx, R, do_prune;
+    int R;
     float eps;
     int Vcap, Ecap, dim;
-    uint32_t stamp;
-    uint64_t colmask, futmask;
     int2 *edges[2];
     float *vert[2], *out[2];
     uint64_t *sig[2], *bmask;
@@ -1139,7 +1167,37 @@ struct StepArgs {
     const unsigned char *in[2];     // liveness bytes received from the lower / upper neighbour
     long long *dbg;                 // TNB_PHASE_TRACE: globaltimer stamps after every phase
 };
-#define TNB_PHASE_MARK(k) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) a.dbg[k] = global_ns(); } while (0)
+// what changes from one hyperplane to the next
+struct StepVar {
+    int idx, do_prune;
+    uint32_t stamp;       // bucket generation of this step
+    uint64_t colmask, futmask;
+};
+__host__ __device__ __forceinline__ StepVar step_var(int idx, int R, int do_prune, uint32_t stamp)
+{
+    StepVar v;
+    v.idx = idx;
+    v.do_prune = do_prune;
+    v.stamp = stamp;
+    v.colmask = (1ull << idx) - 1ull;
+    v.futmask = ~v.colmask & (R >= 64 ? ~0ull : ((1ull << R) - 1ull));
+    return v;
+}
+// TNB_PHASE_TRACE: time spent up to each phase mark, accumulated over the steps of one launch
+// (dbg[63] = time of the previous mark; marks 0 and 16 open the front / back half)
+#define TNB_PHASE_MARK(k) do { if (a.dbg && blockIdx.x == 0 && threadIdx.x == 0) { const long long now_ = global_ns(); \
+        if ((k) != 0 && (k) != 16) a.dbg[k] += now_ - a.dbg[63]; a.dbg[63] = now_; } } while (0)
+
+// How the CTAs of a persistent step kernel wait for each other between phases: the whole
+// cooperative grid (one CTA per SM), or ONE thread-block cluster (barrier.cluster: ~0.2 us instead
+// of ~2.5 us, which is what a small complex needs: its phases are a few microseconds each).
+struct GridSync {
+    cg::grid_group g;
+    __device__ __forceinline__ void operator()() { g.sync(); }
+};
+struct ClusterSync {
+    __device__ __forceinline__ void operator()() { cg::this_cluster().sync(); }
+};
 
 struct TagCount {  // vertices on one shared slab plane
     const unsigned char *tag;
@@ -1158,10 +1216,9 @@ struct StageEmit {  // k-th vertex of the plane: remember k, publish its livenes
     }
 };
 
-template <class C>
-__global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_constant__ NetMeta n, const StepArgs a)
+template <class C, int NT, class Sync>
+__device__ __forceinline__ void step_front(const NetMeta &n, const StepArgs &a, const StepVar sv, Sync sync)
 {
-    cg::grid_group grid = cg::this_grid();
     TNB_PHASE_MARK(0);
     int *cnt = a.cnt;
     if (cnt[C_STICKY]) return;  // an earlier step failed: uniform exit, nobody reaches a grid sync
@@ -1171,32 +1228,32 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
     uint64_t *sig = a.sig[pv];
     // the words read above (>= C_V) are not among the transient counters block 0 clears now
     if (blockIdx.x == 0 && threadIdx.x < C_V) cnt[threadIdx.x] = 0;
-    const SplitCount sc{edges, out, n.R, a.idx, a.eps};
-    scan_count_body(E, sc, a.block_sums);
-    grid.sync();
+    const SplitCount sc{edges, out, n.R, sv.idx, a.eps};
+    scan_count_body_t<NT>(E, sc, a.block_sums);
+    sync();
     TNB_PHASE_MARK(1);
-    scan_write_body(E, sc, ListEmit{a.split_list}, a.block_sums, cnt + C_RAW);
-    grid.sync();
+    scan_write_body_t<NT>(E, sc, ListEmit{a.split_list}, a.block_sums, cnt + C_RAW);
+    sync();
     TNB_PHASE_MARK(2);
     // subpoly.py:110-111: the plane crosses no edge -> the step changes nothing (uniform exit; a
     // slab must go on, another slab may have crossed: halo.cuh)
     if (cnt[C_RAW] == 0 && !a.halo) return;
-    body_new_vertices<C>(n, a.idx, a.eps, a.Vcap, a.Ecap, a.split_list, edges, vert, out, sig, a.bmask, cnt, a.tag[pv]);
-    const HitCount hc{out, a.used[cnt[C_APAR]], n.R, a.idx, a.eps};  // old vertices only: independent of the new rows
-    scan_count_body(V, hc, a.block_sums);
-    grid.sync();
+    body_new_vertices<C>(n, sv.idx, a.eps, a.Vcap, a.Ecap, a.split_list, edges, vert, out, sig, a.bmask, cnt, a.tag[pv]);
+    const HitCount hc{out, a.used[cnt[C_APAR]], n.R, sv.idx, a.eps};  // old vertices only: independent of the new rows
+    scan_count_body_t<NT>(V, hc, a.block_sums);
+    sync();
     TNB_PHASE_MARK(3);
     body_finalize_new(n, vert, out, sig, a.bmask, cnt);
     {   // every CTA knows the hit count from the block sums: the new vertices' candidate slots
         // [H, H+S) can be filled in the same phase as the hit list [0, H)
-        __shared__ int s_h[kScanWarps];
+        __shared__ int s_h[NT / 32];
         int acc = 0;
-        for (int b = threadIdx.x; b < (int)gridDim.x; b += kScanThreads) acc += a.block_sums[b];
+        for (int b = threadIdx.x; b < (int)gridDim.x; b += NT) acc += a.block_sums[b];
         acc = warp_sum(acc);
         if ((threadIdx.x & 31) == 0) s_h[threadIdx.x >> 5] = acc;
         __syncthreads();
         int Hn = 0;
-        for (int w = 0; w < kScanWarps; ++w) Hn += s_h[w];
+        for (int w = 0; w < NT / 32; ++w) Hn += s_h[w];
         __syncthreads();
         if (!cnt[C_OVERFLOW]) {
             const int S = cnt[C_SPLIT];
@@ -1211,35 +1268,41 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_con
             }
         }
     }
-    scan_write_body(V, hc, ListEmit{a.cand}, a.block_sums, cnt + C_HIT);
-    grid.sync();
+    scan_write_body_t<NT>(V, hc, ListEmit{a.cand}, a.block_sums, cnt + C_HIT);
+    sync();
     TNB_PHASE_MARK(4);
-    if (a.do_prune && !cnt[C_OVERFLOW]) {  // the back half marks the vertices that keep an edge in the idle half of the liveness array
+    if (sv.do_prune && !cnt[C_OVERFLOW]) {  // the back half marks the vertices that keep an edge in the idle half of the liveness array
         int *used = a.used[cnt[C_APAR] ^ 1];
         const int Vn = V + cnt[C_SPLIT];
         for (int v = blockIdx.x * blockDim.x + threadIdx.x; v < Vn; v += gridDim.x * blockDim.x) used[v] = 0;
     }
-    body_bucket_insert(a.cand, cnt, sig, a.head, a.next, a.dim, a.stamp);
-    grid.sync();
+    body_bucket_insert(a.cand, cnt, sig, a.head, a.next, a.dim, sv.stamp);
+    sync();
     TNB_PHASE_MARK(5);
     const int n_cand = cnt[C_CAND];
     {   // partner search on this CTA's slice of the candidates (8 lanes each), then the slice's sum
-        __shared__ int s_grp[kScanThreads / 8];
+        __shared__ int s_grp[NT / 8];
         int64_t begin, end;
         scan_slice(n_cand, begin, end);
-        pair_count_groups((int)begin, (int)end, a.cand, sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount, a.pcache, s_grp);
+        pair_count_groups((int)begin, (int)end, a.cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.pcache, s_grp);
         __syncthreads();
     }
-    scan_count_body(n_cand, ArrayCount{a.pcount}, a.block_sums);
-    grid.sync();
+    scan_count_body_t<NT>(n_cand, ArrayCount{a.pcount}, a.block_sums);
+    sync();
     TNB_PHASE_MARK(6);
-    scan_write_body(n_cand, ArrayCount{a.pcount}, OffsetEmit{a.poff}, a.block_sums, cnt + C_PAIRS);
+    scan_write_body_t<NT>(n_cand, ArrayCount{a.pcount}, OffsetEmit{a.poff}, a.block_sums, cnt + C_PAIRS);
     TNB_PHASE_MARK(7);
 }
 
-__global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
+template <class C>
+__global__ void __launch_bounds__(kScanThreads, 2) k_step_front(const __grid_constant__ NetMeta n, const StepArgs a, const StepVar sv)
 {
-    cg::grid_group grid = cg::this_grid();
+    step_front<C, kScanThreads>(n, a, sv, GridSync{cg::this_grid()});
+}
+
+template <int NT, class Sync>
+__device__ __forceinline__ void step_back(const StepArgs &a, const StepVar sv, Sync sync)
+{
     TNB_PHASE_MARK(16);
     int *cnt = a.cnt;
     // all decisions are uniform over the grid (same device words read by everybody before any write)
@@ -1263,14 +1326,14 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
             return;
         }
         if (P > 0)
-            body_pair_write(a.cand, n_cand, sig, a.head, a.next, a.dim, a.stamp, a.colmask, a.pcount, a.poff, edges + E0 + S, a.pcache);
-        if (!a.do_prune) {  // the output neuron (subpoly.py:253): sizes only
+            body_pair_write(a.cand, n_cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.poff, edges + E0 + S, a.pcache);
+        if (!sv.do_prune) {  // the output neuron (subpoly.py:253): sizes only
             if (a.halo) {   // no liveness to exchange, only the status word
                 if (blockIdx.x == 0 && threadIdx.x == 0) a.stage_count[0] = a.stage_count[1] = 0;
                 return;
             }
             for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) alive[V0 + k] = 1;
-            grid.sync();
+            sync();
             TNB_PHASE_MARK(17);
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 cnt[C_V] = Vn;
@@ -1279,23 +1342,23 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
             }
             return;
         }
-        grid.sync();
+        sync();
         TNB_PHASE_MARK(18);
-        const KeepCount kc{edges, sig, a.futmask};
-        scan_count_body(En, kc, a.block_sums);
-        grid.sync();
+        const KeepCount kc{edges, sig, sv.futmask};
+        scan_count_body_t<NT>(En, kc, a.block_sums);
+        sync();
         TNB_PHASE_MARK(19);
-        scan_write_body(En, kc, KeepEmit{edges, edges_dst, used}, a.block_sums, kept);
-        grid.sync();
+        scan_write_body_t<NT>(En, kc, KeepEmit{edges, edges_dst, used}, a.block_sums, kept);
+        sync();
         TNB_PHASE_MARK(20);
         if (a.halo) {  // ordered lists of the two shared planes' vertices and their liveness
             for (int side = 0; side < 2; ++side) {
                 const TagCount tc{a.tag[pv], 1 << side};
-                scan_count_body(Vn, tc, a.block_sums);
-                grid.sync();
+                scan_count_body_t<NT>(Vn, tc, a.block_sums);
+                sync();
                 TNB_PHASE_MARK(21);
-                scan_write_body(Vn, tc, StageEmit{a.hslot, a.stage[side], used, a.stage_cap}, a.block_sums, a.stage_count + side);
-                grid.sync();
+                scan_write_body_t<NT>(Vn, tc, StageEmit{a.hslot, a.stage[side], used, a.stage_cap}, a.block_sums, a.stage_count + side);
+                sync();
                 TNB_PHASE_MARK(22);
             }
             return;  // k_halo_send / k_halo_recv run between the two launches
@@ -1309,9 +1372,9 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
             for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x)
                 for (uint64_t m = a.bmask[k]; m; m &= m - 1) out[((int64_t)V0 + k) * a.R + __ffsll((long long)m) - 1] = 0.0f;
         }
-        if (!a.do_prune) {
+        if (!sv.do_prune) {
             for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) alive[V0 + k] = 1;
-            grid.sync();  // everybody has read the counter block
+            sync();  // everybody has read the counter block
             if (blockIdx.x == 0 && threadIdx.x == 0) {
                 cnt[C_V] = Vn;
                 cnt[C_E] = (int)En;
@@ -1329,7 +1392,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
             used[v] = u;
             if (!u && t) tag[v] = 0;
         }
-        grid.sync();  // everybody has read the counter block (the parked edge count among it)
+        sync();  // everybody has read the counter block (the parked edge count among it)
         TNB_PHASE_MARK(23);
     }
     // Commit: the freshly marked half of the liveness array and the compacted half of the edge
@@ -1343,6 +1406,175 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a)
         a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8 + (unsigned long long)En * (8 + 2 * 48) +
                       (unsigned long long)Vn * 8;
     }
+}
+
+__global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a, const StepVar sv)
+{
+    step_back<kScanThreads>(a, sv, GridSync{cg::this_grid()});
+}
+
+// ---- persistent step loop ---------------------------------------------------------------------------
+// One hyperplane, start to finish, inside a kernel that stays resident over all hyperplanes of
+// the extraction.  Compared with the front/back pair above, the phases are arranged so that every
+// CTA keeps working on what it produced itself: the CTA that finds a crossed edge also makes its
+// new vertex, finalises it, files it into the cell buckets; the CTA that counts a candidate's
+// partners also writes its connecting edges.  Offsets and totals come from the per-CTA block
+// sums (every CTA adds them up itself), never from a word another CTA publishes, so a compaction
+// costs ONE barrier: 7 barriers per hyperplane that crosses something, 1 for one that does not
+// (subpoly.py:110-111), and nothing returns to the host in between.
+//   returns 0 = done, 2 = nothing to do, 1 = work arrays too small (uniform over the CTAs)
+template <class C, int NT, class Sync>
+__device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, const StepVar sv, int parity, Sync sync)
+{
+    int *cnt = a.cnt;
+    const int E = cnt[C_E], V = cnt[C_V], pv = cnt[C_VPAR], pe = cnt[C_EPAR], pa = cnt[C_APAR];
+    int2 *edges = a.edges[pe], *edges_dst = a.edges[pe ^ 1];
+    float *vert = a.vert[pv], *out = a.out[pv];
+    uint64_t *sig = a.sig[pv];
+    unsigned char *tag = a.tag[pv];
+    int *alive = a.used[pa], *used = a.used[pa ^ 1];
+    const int nb = (int)gridDim.x, R = n.R;
+    int *sums_x = a.block_sums + (parity ? nb : 0), *sums_y = a.block_sums + 2 * nb;
+    TNB_PHASE_MARK(0);
+    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_FLAG] = 0;  // last read two barriers ago
+    // P0: edges the plane crosses, per CTA slice
+    const SplitCount sc{edges, out, R, sv.idx, a.eps};
+    scan_count_body_t<NT>(E, sc, sums_x);
+    sync();
+    TNB_PHASE_MARK(1);
+    // P1: split list of this CTA's slice, and straight away the new vertices of exactly those edges
+    int s_base, S;
+    block_sums_reduce<NT>(sums_x, s_base, S);
+    if (S == 0) return 2;  // the plane crosses no edge: the step changes nothing, and published nothing
+    if ((int64_t)V + S > a.Vcap || (int64_t)E + S > a.Ecap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_STICKY] = kStickyCapacity;
+        return 1;
+    }
+    const int s_end = scan_write_from<NT>(E, sc, ListEmit{a.split_list}, s_base);
+    {
+        int any = 0;
+        for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT)
+            any |= new_vertex_item<C>(n, sv.idx, a.eps, k, V, E, a.split_list, edges, vert, out, sig, a.bmask, tag);
+        if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
+    }
+    const HitCount hc{out, alive, R, sv.idx, a.eps};  // old vertices only: independent of the new rows
+    scan_count_body_t<NT>(V, hc, sums_y);
+    sync();
+    TNB_PHASE_MARK(2);
+    // P2: failover override + packed signs of the own new vertices; candidate list (hit old vertices,
+    // then the new ones); the own candidates go into the cell buckets
+    const int flag = cnt[C_FLAG];
+    int h_base, Hn;
+    block_sums_reduce<NT>(sums_y, h_base, Hn);
+    for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) {
+        finalize_item(n, vert, out, sig, a.bmask, flag, V, k);
+        a.cand[Hn + k] = V + k;
+    }
+    const int h_end = scan_write_from<NT>(V, hc, ListEmit{a.cand}, h_base);  // ends in a CTA barrier
+    for (int c = h_base + (int)threadIdx.x; c < h_end; c += NT) bucket_insert_item(c, a.cand[c], sig, a.head, a.next, a.dim, sv.stamp);
+    for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) bucket_insert_item(Hn + k, V + k, sig, a.head, a.next, a.dim, sv.stamp);
+    const int Vn = V + S, n_cand = Hn + S;
+    if (sv.do_prune) {  // P6 marks the vertices that keep an edge in the idle half of the liveness array
+        for (int v = blockIdx.x * NT + threadIdx.x; v < Vn; v += nb * NT) used[v] = 0;
+    } else {
+        for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) alive[V + k] = 1;
+    }
+    sync();
+    TNB_PHASE_MARK(3);
+    // P3: partners of this CTA's slice of the candidates (8 lanes each)
+    int64_t c_begin, c_end;
+    scan_slice(n_cand, c_begin, c_end);
+    {
+        __shared__ int s_grp[NT / 8];
+        pair_count_groups((int)c_begin, (int)c_end, a.cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.pcache, s_grp);
+        __syncthreads();
+    }
+    scan_count_body_t<NT>(n_cand, ArrayCount{a.pcount}, sums_x);
+    sync();
+    TNB_PHASE_MARK(4);
+    // P4: offsets of the slice, then its connecting edges
+    int p_base, P;
+    block_sums_reduce<NT>(sums_x, p_base, P);
+    const int64_t En = (int64_t)E + S + P;
+    if (En > a.Ecap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_STICKY] = kStickyCapacity;
+        return 1;
+    }
+    if (P > 0) {
+        scan_write_from<NT>(n_cand, ArrayCount{a.pcount}, OffsetEmit{a.poff}, p_base);
+        for (int c = (int)c_begin + (int)threadIdx.x; c < (int)c_end; c += NT)
+            pair_write_item(c, a.cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.poff, edges + E + S, a.pcache);
+    }
+    if (!sv.do_prune) {  // the output neuron (subpoly.py:253): sizes only
+        if (blockIdx.x == 0 && threadIdx.x == 0) {
+            cnt[C_V] = Vn;
+            cnt[C_E] = (int)En;
+            a.bytes[0] += 2ull * 16 * E + 2ull * 4 * V + (unsigned long long)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * R + 8 + 16) +
+                          (unsigned long long)n_cand * (24 + 8 + 4 + 24);
+            a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8;
+        }
+        return 0;
+    }
+    sync();
+    TNB_PHASE_MARK(5);
+    // P5 / P6: pruning (subpoly.py:252-277): keep the edges whose ends differ in a future indicator
+    const KeepCount kc{edges, sig, sv.futmask};
+    scan_count_body_t<NT>(En, kc, sums_y);
+    sync();
+    TNB_PHASE_MARK(6);
+    int k_base, kept;
+    block_sums_reduce<NT>(sums_y, k_base, kept);
+    scan_write_from<NT>(En, kc, KeepEmit{edges, edges_dst, used}, k_base);
+    // Commit: the freshly marked half of the liveness array and the compacted half of the edge array
+    // become current; the rows of dead vertices stay where they are (complex.cuh).  The caller's
+    // barrier after the step orders these words before the next step reads them.
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        cnt[C_V] = Vn;
+        cnt[C_E] = kept;
+        cnt[C_EPAR] = pe ^ 1;
+        cnt[C_APAR] = pa ^ 1;
+        a.bytes[0] += 2ull * 16 * E + 2ull * 4 * V + (unsigned long long)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * R + 8 + 16) +
+                      (unsigned long long)n_cand * (24 + 8 + 4 + 24);
+        a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8 + (unsigned long long)En * (8 + 2 * 48) +
+                      (unsigned long long)Vn * 8;
+    }
+    TNB_PHASE_MARK(7);
+    return 0;
+}
+
+constexpr int kClusterThreads = 512;
+constexpr int kMaxStepList = 128;
+struct StepList {
+    int n;
+    uint32_t stamp0;                  // step i uses bucket generation stamp0 + i
+    unsigned char idx[kMaxStepList];  // output column of the hyperplane
+    unsigned char prune[kMaxStepList];
+};
+template <class C, int NT, class Sync>
+__device__ __forceinline__ void steps_loop(const NetMeta &n, const StepArgs &a, const StepList &list, Sync sync)
+{
+    if (a.cnt[C_STICKY]) return;  // an earlier launch failed (nobody writes this word before the first barrier)
+    for (int i = 0; i < list.n; ++i) {
+        const StepVar sv = step_var(list.idx[i], a.R, list.prune[i], list.stamp0 + (uint32_t)i);
+        const int r = step_fused<C, NT>(n, a, sv, i & 1, sync);
+        if (r == 1) return;
+        if (r == 0) sync();  // the next step reads the sizes and buffer parities this one published
+    }
+}
+// ... by the cooperative grid (one CTA per SM): the default
+template <class C>
+__global__ void __launch_bounds__(kScanThreads, 1) k_steps_grid(const __grid_constant__ NetMeta n, const __grid_constant__ StepArgs a,
+                                                                const __grid_constant__ StepList list)
+{
+    steps_loop<C, kScanThreads>(n, a, list, GridSync{cg::this_grid()});
+}
+// ... by ONE thread-block cluster of 16 CTAs: a barrier costs a tenth, but 16 SMs do the work of
+// 148.  Slower for one object; it leaves 132 SMs to other objects' clusters.
+template <class C>
+__global__ void __launch_bounds__(kClusterThreads, 1) k_steps_cluster(const __grid_constant__ NetMeta n, const __grid_constant__ StepArgs a,
+                                                                      const __grid_constant__ StepList list)
+{
+    steps_loop<C, kClusterThreads>(n, a, list, ClusterSync{});
 }
 
 // co-resident grid size of a cooperative kernel: blocks/SM x SMs, capped by the scan tables
@@ -1480,6 +1712,146 @@ int halo_merge_used(tnb_complex *c, int64_t V, int *used, cudaStream_t s)
     return TNB_OK;
 }
 
+static void fill_step_args(const tnb_net *net, tnb_complex *c, float eps, StepArgs &sa)
+{
+    memset(&sa, 0, sizeof(sa));
+    sa.R = net->meta.R; sa.eps = eps;
+    sa.Vcap = (int)c->Vcap; sa.Ecap = (int)c->Ecap; sa.dim = c->cell_dim;
+    for (int k = 0; k < 2; ++k) {
+        sa.edges[k] = c->edges[k].p; sa.vert[k] = c->vert[k].p; sa.out[k] = c->out[k].p; sa.sig[k] = c->sig[k].p;
+        sa.used[k] = c->used[k].p; sa.tag[k] = c->tag[k].p;
+    }
+    sa.bmask = c->bmask.p; sa.split_list = c->split_list.p; sa.cand = c->cand.p; sa.pcount = c->pcount.p;
+    sa.poff = c->poff.p; sa.pcache = c->pcache.p; sa.next = c->next.p; sa.remap = c->remap.p;
+    sa.block_sums = c->block_sums.p; sa.cnt = c->counters.p; sa.head = c->head.p; sa.bytes = c->bytes.p;
+}
+
+static const bool g_phase_trace = std::getenv("TNB_PHASE_TRACE") != nullptr;
+static DevBuf<long long> g_phase_dbg;
+static int phase_trace_begin(StepArgs &sa, cudaStream_t s)
+{
+    if (!g_phase_trace) return TNB_OK;
+    TNB_CUDA(g_phase_dbg.reserve(64));
+    TNB_CUDA(cudaMemsetAsync(g_phase_dbg.p, 0, 64 * sizeof(long long), s));
+    sa.dbg = g_phase_dbg.p;
+    return TNB_OK;
+}
+static int phase_trace_print(const char *what, int idx, cudaStream_t s)
+{
+    if (!g_phase_trace) return TNB_OK;
+    long long h[64];
+    TNB_CUDA(cudaMemcpyAsync(h, g_phase_dbg.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    TNB_CUDA(cudaStreamSynchronize(s));
+    fprintf(stderr, "phase-trace %s %d front:", what, idx);
+    for (int k = 1; k < 16; ++k) if (h[k]) fprintf(stderr, " %d:%.1f", k, h[k] * 1e-3);
+    fprintf(stderr, " | back:");
+    for (int k = 17; k < 32; ++k) if (h[k]) fprintf(stderr, " %d:%.1f", k, h[k] * 1e-3);
+    fprintf(stderr, "\n");
+    return TNB_OK;
+}
+
+// ---- all hyperplanes in one cluster launch ---------------------------------------------------------
+// largest cluster (CTAs) k_steps_cluster can run with on this device: 16 (non-portable), else 8; 0 = none
+template <class K>
+static int cluster_ctas(K kernel)
+{
+    if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    for (int cs : {16, 8}) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(cs);
+        cfg.blockDim = dim3(kClusterThreads);
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, kernel, &cfg) == cudaSuccess && n >= 1) return cs;
+        cudaGetLastError();
+    }
+    return 0;
+}
+static int64_t g_cluster_max_items = std::getenv("TNB_CLUSTER_MAX_ITEMS") ? std::atoll(std::getenv("TNB_CLUSTER_MAX_ITEMS")) : 0;
+
+// How can the hyperplanes of this complex run?  0 = one step at a time (multi-launch kernels with
+// full-size grids: large complexes; the curve path; slab sharding has its own kernels),
+// 1 = persistent cooperative grid, 2 = persistent single cluster (opt-in: tnb_set_cluster_max_items)
+int steps_mode(const tnb_net *net, const tnb_complex *c, bool planar)
+{
+    (void)net;
+    if (!planar || c->halo.enabled || !g_fused_steps || c->E <= 0) return 0;
+    const int64_t items = c->E + c->V;  // may be stale upper bounds: good enough for this choice
+    if (g_cluster_max_items > 0 && items <= g_cluster_max_items) return 2;
+    return items <= kFusedMaxItems ? 1 : 0;
+}
+
+// lh[2*i], lh[2*i+1] = (layer, neuron) of step i, as tnb_subpoly_step takes them.  One launch; the
+// host does not wait: sizes, buffer parity, capacity and error bits stay in the counter block.
+// TNB_ERR_UNSUPPORTED = this device / step list cannot run that way (the caller goes step by step).
+int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh, int n_steps, float eps, int mode, cudaStream_t s)
+{
+    const NetMeta &m = net->meta;
+    const int H = m.H, R = m.R;
+    if (n_steps <= 0) return TNB_OK;
+    if (n_steps > kMaxStepList || R > 256) return TNB_ERR_UNSUPPORTED;
+    static int cs_ref = -1, cs_any = -1, gb_ref = -1, gb_any = -1;
+    if (cs_ref < 0) {
+        cs_ref = cluster_ctas(k_steps_cluster<CfgRef>);
+        cs_any = cluster_ctas(k_steps_cluster<CfgAny>);
+        gb_ref = coop_blocks(k_steps_grid<CfgRef>);
+        gb_any = coop_blocks(k_steps_grid<CfgAny>);
+    }
+    static const int env_blocks = std::getenv("TNB_STEP_BLOCKS") ? std::atoi(std::getenv("TNB_STEP_BLOCKS")) : 0;  // tuning knob
+    // one CTA per SM keeps the grid barrier cheap
+    const int blocks = mode == 2 ? (net->fixed_cfg ? cs_ref : cs_any)
+                                 : std::min(env_blocks > 0 ? env_blocks : kSMs, net->fixed_cfg ? gb_ref : gb_any);
+    if (blocks <= 0 || 3 * blocks > kScanMaxBlocks) return TNB_ERR_UNSUPPORTED;
+    StepList list;
+    memset(&list, 0, sizeof(list));
+    list.n = n_steps;
+    bool prunes = false;
+    for (int i = 0; i < n_steps; ++i) {
+        const int l = lh[2 * i], h = lh[2 * i + 1], idx = l * H + h;
+        if (l < 0 || h < 0 || h > H || idx >= R) { set_error("tnb_subpoly_steps: (l,h) out of range"); return TNB_ERR_INVALID; }
+        list.idx[i] = (unsigned char)idx;
+        list.prune[i] = h < H ? 1 : 0;
+        prunes = prunes || h < H;
+    }
+    if (c->stamp > 0xffffffffu - (uint32_t)n_steps - 1u) {  // the generation stamps of this launch would wrap
+        TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
+        c->stamp = 0;
+    }
+    list.stamp0 = c->stamp + 1;
+    c->stamp += (uint32_t)n_steps;
+    StepArgs sa;
+    fill_step_args(net, c, eps, sa);
+    int rc;
+    if ((rc = phase_trace_begin(sa, s))) return rc;
+    prof_begin(TNB_PROF_NEW_VERTICES, s);
+    if (mode == 2) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(blocks);
+        cfg.blockDim = dim3(kClusterThreads);
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = blocks; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (net->fixed_cfg) TNB_CUDA(cudaLaunchKernelEx(&cfg, k_steps_cluster<CfgRef>, m, sa, list));
+        else TNB_CUDA(cudaLaunchKernelEx(&cfg, k_steps_cluster<CfgAny>, m, sa, list));
+    } else {
+        void *params[] = {(void *)&m, (void *)&sa, (void *)&list};
+        if (net->fixed_cfg) TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_steps_grid<CfgRef>, dim3(blocks), dim3(kScanThreads), params, 0, s));
+        else TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_steps_grid<CfgAny>, dim3(blocks), dim3(kScanThreads), params, 0, s));
+    }
+    count_launch();
+    prof_end(TNB_PROF_NEW_VERTICES, s, 0);
+    c->counts_stale = true;
+    if (prunes) c->maybe_dead = true;
+    return phase_trace_print(mode == 2 ? "cluster steps" : "grid steps", n_steps, s);
+}
+
 // part 0: the whole step; 1: up to and including the send of the slab exchange; 2: from its receive on
 static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps, bool planar, cudaStream_t s, int part = 0)
 {
@@ -1512,7 +1884,15 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     const int front_blocks = std::min(net->fixed_cfg ? front_blocks_ref : front_blocks_any, sm_blocks);
     const bool fused = planar && front_blocks > 0 && back_blocks > 0 && (halo || (g_fused_steps && c->E + c->V <= kFusedMaxItems));
     if (halo && !fused) { set_error("slab-sharded extraction needs the cooperative step kernels"); return TNB_ERR_UNSUPPORTED; }
-    if (fused) {
+    if (!halo) {  // a small complex: the persistent step kernel, with a list of one
+        const int mode = steps_mode(net, c, planar);
+        if (mode) {
+            const int32_t one[2] = {l, h};
+            rc = steps_persistent_impl(net, c, one, 1, eps, mode, s);
+            if (rc != TNB_ERR_UNSUPPORTED) return rc;
+        }
+    }
+    if (fused && halo) {
         if (part != 2) {
             c->stamp += 1;
             if (c->stamp == 0) {
@@ -1521,28 +1901,12 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             }
         }
         StepArgs sa;
-        memset(&sa, 0, sizeof(sa));
-        sa.idx = idx; sa.R = R; sa.do_prune = h < H ? 1 : 0; sa.eps = eps;
-        sa.Vcap = (int)c->Vcap; sa.Ecap = (int)c->Ecap; sa.dim = c->cell_dim; sa.stamp = c->stamp;
-        sa.colmask = colmask;
-        sa.futmask = ~colmask & (R >= 64 ? ~0ull : ((1ull << R) - 1ull));
-        for (int k = 0; k < 2; ++k) {
-            sa.edges[k] = c->edges[k].p; sa.vert[k] = c->vert[k].p; sa.out[k] = c->out[k].p; sa.sig[k] = c->sig[k].p;
-        }
-        sa.bmask = c->bmask.p; sa.split_list = c->split_list.p; sa.cand = c->cand.p; sa.pcount = c->pcount.p;
-        sa.poff = c->poff.p; sa.pcache = c->pcache.p; sa.next = c->next.p; sa.used[0] = c->used[0].p; sa.used[1] = c->used[1].p; sa.remap = c->remap.p;
-        sa.block_sums = c->block_sums.p; sa.cnt = c->counters.p; sa.head = c->head.p; sa.bytes = c->bytes.p;
-        sa.tag[0] = c->tag[0].p; sa.tag[1] = c->tag[1].p;
-        static const bool trace = std::getenv("TNB_PHASE_TRACE") != nullptr;
-        static DevBuf<long long> dbg;
-        if (trace) {
-            TNB_CUDA(dbg.reserve(64));
-            TNB_CUDA(cudaMemsetAsync(dbg.p, 0, 64 * sizeof(long long), s));
-            sa.dbg = dbg.p;
-        }
+        fill_step_args(net, c, eps, sa);
+        const StepVar sv = step_var(idx, R, h < H ? 1 : 0, c->stamp);
+        if ((rc = phase_trace_begin(sa, s))) return rc;
         sa.halo = halo ? 1 : 0;
-        void *fparams[] = {(void *)&m, (void *)&sa};
-        void *bparams[] = {(void *)&sa};
+        void *fparams[] = {(void *)&m, (void *)&sa, (void *)&sv};
+        void *bparams[] = {(void *)&sa, (void *)&sv};
         const dim3 bgrid(std::min(back_blocks, sm_blocks));
         if (halo) {
             sa.has_lower = c->halo.tag_lower; sa.has_upper = c->halo.tag_upper;
@@ -1575,19 +1939,8 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             prof_end(TNB_PROF_PAIRS, s, 0);
         }
         c->counts_stale = true;  // sizes and buffer parity are on the device until the next sync
-        if (sa.do_prune) c->maybe_dead = true;
-        if (trace) {
-            long long h[64];
-            TNB_CUDA(cudaMemcpyAsync(h, dbg.p, sizeof(h), cudaMemcpyDeviceToHost, s));
-            TNB_CUDA(cudaStreamSynchronize(s));
-            fprintf(stderr, "phase-trace idx %d front:", idx);
-            for (int k = 1; k < 16 && h[k]; ++k) fprintf(stderr, " %.1f", (h[k] - h[k - 1]) * 1e-3);
-            fprintf(stderr, " | gap %.1f | back:", h[16] && h[0] ? (h[16] - h[0]) * 1e-3 : 0.0);
-            long long prev = h[16];
-            for (int k = 17; k < 32; ++k) if (h[k]) { fprintf(stderr, " %.1f", (h[k] - prev) * 1e-3); prev = h[k]; }
-            fprintf(stderr, "\n");
-        }
-        return TNB_OK;
+        if (sv.do_prune) c->maybe_dead = true;
+        return phase_trace_print("step", idx, s);
     }
     // multi-launch path: needs the host's view of sizes and buffer parity to be current
     if ((rc = complex_sync_counts(c, s))) return rc;
@@ -1808,6 +2161,13 @@ int tnb_set_capacity_factor(double f)
     return TNB_OK;
 }
 
+int64_t tnb_set_cluster_max_items(int64_t items)
+{
+    const int64_t before = g_cluster_max_items;
+    if (items >= 0) g_cluster_max_items = items;
+    return before;
+}
+
 int tnb_skeleton(const tnb_net *net, int32_t unit, float size, tnb_complex **out, void *stream)
 {
     if (!net || !out) { set_error("tnb_skeleton: null argument"); return TNB_ERR_INVALID; }
@@ -1990,6 +2350,27 @@ int tnb_complex_read(const tnb_complex *c, float *d_vertices, int64_t *d_edges, 
     if (d_edges && c->E) {
         k_edges_to_i64<<<grid_for(c->E, 256), 256, 0, s>>>(c->cedges(), c->E, d_edges);
         TNB_LAUNCH_CHECK();
+    }
+    return TNB_OK;
+}
+
+int tnb_subpoly_steps(const tnb_net *net, tnb_complex *c, const int32_t *lh, int32_t n_steps, float eps, int32_t force,
+                      void *stream)
+{
+    if (!net || !c || (n_steps > 0 && !lh) || n_steps < 0) { set_error("tnb_subpoly_steps: bad argument"); return TNB_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    current_stream() = s;
+    c->stream = s;
+    for (int i = 0; i < n_steps;) {
+        // as soon as the complex is small enough, everything that is left runs as ONE persistent launch
+        const int mode = steps_mode(net, c, force != 0);
+        if (mode) {
+            const int rc = steps_persistent_impl(net, c, lh + 2 * i, n_steps - i, eps, mode, s);
+            if (rc != TNB_ERR_UNSUPPORTED) return rc;
+        }
+        const int rc = step_impl(net, c, lh[2 * i], lh[2 * i + 1], eps, force != 0, s);
+        if (rc) return rc;
+        ++i;
     }
     return TNB_OK;
 }

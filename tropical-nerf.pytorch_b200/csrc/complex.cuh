@@ -93,7 +93,7 @@ namespace tnb {
 int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap);
 int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s);
 int complex_sync_counts(tnb_complex *c, cudaStream_t s);
-int complex_compact(tnb_complex *c, cudaStream_t s);  // drop the rows of dead vertices (order preserving), renumber the edges
+int complex_compact(tnb_complex *c, cudaStream_t s);
 int launch_outputs(const tnb_net *net, const float *d_x, int64_t n, float *d_out, cudaStream_t s);
 int launch_sdf_grad(const tnb_net *net, const float *d_x, int64_t n, float *d_sdf, float *d_grad, cudaStream_t s);
 int launch_region(const tnb_net *net, const float *d_x, const float *d_outputs, int64_t n, float eps,

@@ -860,9 +860,12 @@ int tnb_subpoly(const tnb_net *net, float size, float eps, int32_t force, int32_
         rc = tnb_skeleton(net, unit, size, &c, stream);
         if (rc != TNB_OK) break;
         const int H = net->meta.H, NL = net->meta.NLIN;
-        for (int l = 0; l < NL - 1 && rc == TNB_OK; ++l)
-            for (int h = 0; h < H && rc == TNB_OK; ++h) rc = tnb_subpoly_step(net, c, l, h, eps, force, stream);
-        if (rc == TNB_OK) rc = tnb_subpoly_step(net, c, NL - 2, H, eps, force, stream);  // the output neuron
+        std::vector<int32_t> lh;  // every hidden neuron in layer order, then the output neuron (subpoly.py:58-72)
+        for (int l = 0; l < NL - 1; ++l)
+            for (int h = 0; h < H; ++h) { lh.push_back(l); lh.push_back(h); }
+        lh.push_back(NL - 2);
+        lh.push_back(H);
+        rc = tnb_subpoly_steps(net, c, lh.data(), (int32_t)(lh.size() / 2), eps, force, stream);
         if (rc == TNB_OK) rc = tnb_extract_mesh(net, c, eps, out, stream);
         tnb_complex_destroy(c);
         if (rc != TNB_ERR_CAPACITY) break;

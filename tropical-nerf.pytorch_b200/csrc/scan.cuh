@@ -50,70 +50,151 @@ __device__ __forceinline__ void scan_slice(int64_t n, int64_t &begin, int64_t &e
     if (end > n) end = n;
 }
 
-// The two phases as device functions (blockDim.x == kScanThreads), so that fused cooperative
-// kernels can run them between grid syncs; the __global__ wrappers follow.
-template <class Count>
-__device__ __forceinline__ void scan_count_body(int64_t n, Count count, int *block_sums)
+// The two phases as device functions, so that fused persistent kernels can run them between
+// grid / cluster syncs; NT = threads per CTA (blockDim.x).  The __global__ wrappers follow.
+template <int NT, class Count>
+__device__ __forceinline__ void scan_count_body_t(int64_t n, Count count, int *block_sums)
 {
+    constexpr int NW = NT / 32;
     int64_t begin, end;
     scan_slice(n, begin, end);
     int acc = 0;
-    for (int64_t i = begin + threadIdx.x; i < end; i += kScanThreads) acc += count(i);
+    for (int64_t i = begin + threadIdx.x; i < end; i += NT) acc += count(i);
     acc = warp_sum(acc);
-    __shared__ int s[kScanWarps];
+    __shared__ int s[NW];
     if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int t = 0;
-        for (int w = 0; w < kScanWarps; ++w) t += s[w];
-        block_sums[blockIdx.x] = t;
+    if (threadIdx.x < 32) {
+        int t = (int)threadIdx.x < NW ? s[threadIdx.x] : 0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
     }
     __syncthreads();  // s[] may be reused by the caller's next phase
 }
 
-template <class Count, class Emit>
-__device__ __forceinline__ void scan_write_body(int64_t n, Count count, Emit emit, const int *block_sums, int *total)
+template <int NT, class Count, class Emit>
+__device__ __forceinline__ void scan_write_body_t(int64_t n, Count count, Emit emit, const int *block_sums, int *total)
 {
-    __shared__ int s_warp[kScanWarps];
-    __shared__ int s_base;
+    constexpr int NW = NT / 32;
+    __shared__ int s_warp[NW];
+    __shared__ int s_excl[32];
+    __shared__ int s_base, s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     // base offset of this block = sum of the sums before it; block 0 also publishes the total
     {
         int acc = 0;
         const int upto = (blockIdx.x == 0) ? (int)gridDim.x : (int)blockIdx.x;
-        for (int b = threadIdx.x; b < upto; b += kScanThreads) acc += block_sums[b];
+        for (int b = threadIdx.x; b < upto; b += NT) acc += block_sums[b];
         acc = warp_sum(acc);
-        if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = acc;
+        if (lane == 0) s_warp[warp] = acc;
         __syncthreads();
-        if (threadIdx.x == 0) {
-            int t = 0;
-            for (int w = 0; w < kScanWarps; ++w) t += s_warp[w];
-            if (blockIdx.x == 0) { if (total) *total = t; s_base = 0; }
-            else s_base = t;
+        if (threadIdx.x < 32) {
+            int t = lane < NW ? s_warp[lane] : 0;
+            t = warp_sum(t);
+            if (threadIdx.x == 0) {
+                if (blockIdx.x == 0) { if (total) *total = t; s_base = 0; }
+                else s_base = t;
+            }
         }
         __syncthreads();
     }
     int64_t begin, end;
     scan_slice(n, begin, end);
     int running = s_base;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int64_t tile = begin; tile < end; tile += kScanThreads) {
+    for (int64_t tile = begin; tile < end; tile += NT) {
         const int64_t i = tile + threadIdx.x;
         const int c = (i < end) ? count(i) : 0;
         const int incl = warp_inclusive_scan(c);
-        __syncthreads();  // s_warp reuse
+        __syncthreads();  // s_warp / s_excl reuse
         if (lane == 31) s_warp[warp] = incl;
         __syncthreads();
-        int warp_off = 0, tile_total = 0;
-#pragma unroll
-        for (int w = 0; w < kScanWarps; ++w) {
-            const int t = s_warp[w];
-            if (w < warp) warp_off += t;
-            tile_total += t;
+        if (warp == 0) {  // scan of the warp totals
+            const int t = lane < NW ? s_warp[lane] : 0;
+            const int ti = warp_inclusive_scan(t);
+            s_excl[lane] = ti - t;
+            if (lane == 31) s_tile = ti;
         }
-        if (c) emit(i, running + warp_off + incl - c, c);
-        running += tile_total;
+        __syncthreads();
+        if (c) emit(i, running + s_excl[warp] + incl - c, c);
+        running += s_tile;
     }
     __syncthreads();
+}
+
+// Pieces for kernels that keep going after a compaction: every CTA derives its own base offset
+// AND the grand total from the block sums (no second pass over a published total), and the write
+// pass returns where the CTA's items went, so that the CTA can process exactly what it emitted.
+template <int NT>
+__device__ __forceinline__ void block_sums_reduce(const int *block_sums, int &base, int &total)
+{
+    constexpr int NW = NT / 32;
+    __shared__ int s_b[NW], s_t[NW];
+    __shared__ int s_out[2];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int before = 0, all = 0;
+    for (int b = threadIdx.x; b < (int)gridDim.x; b += NT) {
+        const int v = block_sums[b];
+        all += v;
+        if (b < (int)blockIdx.x) before += v;
+    }
+    before = warp_sum(before);
+    all = warp_sum(all);
+    if (lane == 0) { s_b[warp] = before; s_t[warp] = all; }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int x = lane < NW ? s_b[lane] : 0, y = lane < NW ? s_t[lane] : 0;
+        x = warp_sum(x);
+        y = warp_sum(y);
+        if (lane == 0) { s_out[0] = x; s_out[1] = y; }
+    }
+    __syncthreads();
+    base = s_out[0];
+    total = s_out[1];
+    __syncthreads();  // s_out may be rewritten by the next call
+}
+
+// write pass of this CTA's slice starting at position `base`; returns the position after its last item
+template <int NT, class Count, class Emit>
+__device__ __forceinline__ int scan_write_from(int64_t n, Count count, Emit emit, int base)
+{
+    constexpr int NW = NT / 32;
+    __shared__ int s_warp[NW];
+    __shared__ int s_excl[32];
+    __shared__ int s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int64_t begin, end;
+    scan_slice(n, begin, end);
+    int running = base;
+    for (int64_t tile = begin; tile < end; tile += NT) {
+        const int64_t i = tile + threadIdx.x;
+        const int c = (i < end) ? count(i) : 0;
+        const int incl = warp_inclusive_scan(c);
+        __syncthreads();  // s_warp / s_excl reuse
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int t = lane < NW ? s_warp[lane] : 0;
+            const int ti = warp_inclusive_scan(t);
+            s_excl[lane] = ti - t;
+            if (lane == 31) s_tile = ti;
+        }
+        __syncthreads();
+        if (c) emit(i, running + s_excl[warp] + incl - c, c);
+        running += s_tile;
+    }
+    __syncthreads();
+    return running;
+}
+
+template <class Count>
+__device__ __forceinline__ void scan_count_body(int64_t n, Count count, int *block_sums)
+{
+    scan_count_body_t<kScanThreads>(n, count, block_sums);
+}
+template <class Count, class Emit>
+__device__ __forceinline__ void scan_write_body(int64_t n, Count count, Emit emit, const int *block_sums, int *total)
+{
+    scan_write_body_t<kScanThreads>(n, count, emit, block_sums, total);
 }
 
 // n_dev (optional): the item count lives in device memory (a previous kernel produced it);

@@ -62,6 +62,8 @@ SIGNATURES = {
     "tnb_complex_num_edges": (_I64, [_P]),
     "tnb_complex_read": (ctypes.c_int, [_P, _P, _P, _P, _P]),
     "tnb_subpoly_step": (ctypes.c_int, [_P, _P, _I32, _I32, _F, _I32, _P]),
+    "tnb_subpoly_steps": (ctypes.c_int, [_P, _P, _P, _I32, _F, _I32, _P]),
+    "tnb_set_cluster_max_items": (_I64, [_I64]),
     "tnb_extract_mesh": (ctypes.c_int, [_P, _P, _F, ctypes.POINTER(_P), _P]),
     "tnb_mesh_destroy": (None, [_P]),
     "tnb_mesh_num_vertices": (_I64, [_P]),
@@ -359,6 +361,13 @@ class NativeComplex:
     def step(self, l, h, eps=1e-4, force=True):
         check(lib().tnb_subpoly_step(self.net.handle, self.handle, int(l), int(h), float(eps),
                                      int(bool(force)), _stream()))
+        return self
+
+    def steps(self, lh, eps=1e-4, force=True):
+        """All hyperplanes `lh` = [(l, h), ...] in one call (tnb_subpoly_steps)."""
+        arr = (ctypes.c_int32 * (2 * len(lh)))(*[int(x) for pair in lh for x in pair])
+        check(lib().tnb_subpoly_steps(self.net.handle, self.handle, arr, len(lh), float(eps),
+                                      int(bool(force)), _stream()))
         return self
 
     def extract_mesh(self, eps=1e-4):
