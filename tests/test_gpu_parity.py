@@ -377,3 +377,27 @@ def test_whole_path_same_mesh_with_and_without_cluster_launch():
         lib().tnb_set_cluster_max_items(before)
     for x, y in zip(m0, m1):
         assert np.array_equal(x, y)
+
+
+def test_steps_with_an_eps_other_than_the_networks():
+    """The no-op shortcut (crossing mask from the packed signs) only holds when the step's eps is the
+    eps the signs were packed with; with another eps every step looks at the edges again."""
+    from oracle import subpoly_ref as R
+    g = load_golden("tiny_sphere_h8")
+    P = oracle_net(g)
+    N = native_net(P)
+    steps = _all_steps(P)[:9]
+    eps = 3e-4
+    c = N.skeleton(128)
+    c.steps(steps, eps=eps)
+    v, e, o = [t.cpu().numpy() for t in c.read()]
+    d = N.skeleton(128)
+    for l, h in steps:
+        d.step(l, h, eps=eps)
+    v2, e2, o2 = [t.cpu().numpy() for t in d.read()]
+    vo, eo = R.skeleton(P)
+    oo = P.outputs(vo)
+    for l, h in steps:
+        vo, eo, oo = R.subpoly_step(P, vo, eo, oo, l, h, eps)
+    assert np.array_equal(e, eo) and np.array_equal(v, vo) and np.array_equal(o, oo)
+    assert np.array_equal(e2, eo) and np.array_equal(v2, vo) and np.array_equal(o2, oo)

@@ -36,7 +36,7 @@ constexpr int kCachedPartners = 12;  // the partner-count pass keeps this many p
 //   C_STICKY = error bits that survive steps (sync-free fused path)
 //   C_KEPT = edges kept by pruning, parked until the slab exchange decides whether the step counts
 //   C_APAR = which half of the liveness array is current.  C_V counts vertex SLOTS (dead rows included)
-enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_NUM = 16 };
+enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_CROSS = 16 /* 64-bit crossing mask */, C_NUM = 32 };
 enum { kErrNoPlane = 1, kErrGradientDescent = 2 };
 enum { kStickyCapacity = 1 };
 
@@ -130,6 +130,17 @@ int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
 }
 
 __global__ void k_set_counts(int *__restrict__ cnt, int V, int E, int vpar, int epar, int apar);
+__global__ void k_cross_mask(const int2 *__restrict__ edges, int64_t E, const uint64_t *__restrict__ sig, int *__restrict__ cnt);
+// which hyperplanes cross an edge of a fresh complex (its packed signs must be in place)
+static int initial_cross_mask(tnb_complex *c, cudaStream_t s)
+{
+    if (c->E > 0) {
+        k_cross_mask<<<grid_for(c->E, 256), 256, 0, s>>>(c->cedges(), c->E, c->csig(), c->counters.p);
+        TNB_LAUNCH_CHECK();
+    }
+    c->cross_stale = true;
+    return TNB_OK;
+}
 
 static int read_counters(tnb_complex *c, cudaStream_t s)
 {
@@ -456,6 +467,7 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
         TNB_LAUNCH_CHECK();
         rc = eval_vertices(net, c, 0, V, s);
         if (rc) return rc;
+        if ((rc = initial_cross_mask(c, s))) return rc;
     }
     return TNB_OK;
 }
@@ -1022,6 +1034,64 @@ __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__
 }
 
 // ---- pruning -------------------------------------------------------------------------------------
+// hyperplanes that separate the two ends of an edge (beyond eps on both sides), from the packed signs
+__device__ __forceinline__ uint64_t edge_cross_bits(const uint64_t *sig, int2 ed)
+{
+    const uint64_t pa = sig[3 * (int64_t)ed.x], na = sig[3 * (int64_t)ed.x + 1];
+    const uint64_t pb = sig[3 * (int64_t)ed.y], nb = sig[3 * (int64_t)ed.y + 1];
+    return (pa & nb) | (na & pb);
+}
+__device__ __forceinline__ void cross_publish(uint64_t m, int *cnt)
+{
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) m |= __shfl_xor_sync(0xffffffffu, m, d);
+    if ((threadIdx.x & 31) == 0 && m) atomicOr((unsigned long long *)(cnt + C_CROSS), (unsigned long long)m);
+}
+// crossing mask of a fresh complex (skeleton / caller arrays)
+__global__ void k_cross_mask(const int2 *__restrict__ edges, int64_t E, const uint64_t *__restrict__ sig, int *__restrict__ cnt)
+{
+    uint64_t m = 0;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) m |= edge_cross_bits(sig, edges[e]);
+    cross_publish(m, cnt);
+}
+// The count pass of the pruning compaction (KeepCount below) that also ORs the crossing bits of the
+// edges.  A pruned edge has equal signs in every later column, so the OR over all edges equals the OR
+// over the kept ones in the columns that matter.
+template <int NT>
+__device__ __forceinline__ void keep_count_cross(int64_t n, const int2 *edges, const uint64_t *sig, uint64_t futmask, int *block_sums,
+                                                 int *cnt)
+{
+    constexpr int NW = NT / 32;
+    int64_t begin, end;
+    scan_slice(n, begin, end);
+    int acc = 0;
+    uint64_t m = 0;
+    for (int64_t e = begin + threadIdx.x; e < end; e += NT) {
+        const int2 ed = edges[e];
+        const uint64_t pa = sig[3 * (int64_t)ed.x], na = sig[3 * (int64_t)ed.x + 1];
+        const uint64_t pb = sig[3 * (int64_t)ed.y], nb = sig[3 * (int64_t)ed.y + 1];
+        acc += (((pa ^ pb) | (na ^ nb)) & futmask) ? 1 : 0;
+        m |= (pa & nb) | (na & pb);
+    }
+    cross_publish(m, cnt);
+    acc = warp_sum(acc);
+    __shared__ int s[NW];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int t = (int)threadIdx.x < NW ? s[threadIdx.x] : 0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
+    }
+    __syncthreads();
+}
+__global__ void __launch_bounds__(kScanThreads) k_keep_count_cross(int64_t n, const int *__restrict__ n_dev, const int2 *__restrict__ edges,
+                                                                   const uint64_t *__restrict__ sig, uint64_t futmask,
+                                                                   int *__restrict__ block_sums, int *__restrict__ cnt)
+{
+    if (n_dev) n = *n_dev;
+    keep_count_cross<kScanThreads>(n, edges, sig, futmask, block_sums, cnt);
+}
 struct KeepCount {  // subpoly.py:262-264: keep an edge iff its ends differ in a future indicator
     const int2 *edges;
     const uint64_t *sig;
@@ -1160,6 +1230,7 @@ struct StepArgs {
     unsigned long long *head, *bytes;  // bytes[0/1]: algorithmic bytes of the front / back halves
     unsigned char *tag[2];
     // slab sharding (halo.cuh): the back half runs in two launches around the exchange
+    int use_cross;                  // the packed signs were made with this step's eps: the crossing mask decides no-op steps
     int halo, part;                 // part 0: whole back half, 1: up to the exchange, 2: after it
     int has_lower, has_upper;
     int *hslot, *stage_count, stage_cap;
@@ -1435,6 +1506,10 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     int *alive = a.used[pa], *used = a.used[pa ^ 1];
     const int nb = (int)gridDim.x, R = n.R;
     int *sums_x = a.block_sums + (parity ? nb : 0), *sums_y = a.block_sums + 2 * nb;
+    // Nothing crosses this plane (the last pruning pass looked): subpoly.py:110-111 without touching an
+    // edge.  The mask was published before the barrier that ended the step which wrote it.
+    unsigned long long *cross = (unsigned long long *)(cnt + C_CROSS);
+    if (a.use_cross && !((*cross >> sv.idx) & 1ull)) return 2;
     TNB_PHASE_MARK(0);
     if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_FLAG] = 0;  // last read two barriers ago
     // P0: edges the plane crosses, per CTA slice
@@ -1464,6 +1539,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     // P2: failover override + packed signs of the own new vertices; candidate list (hit old vertices,
     // then the new ones); the own candidates go into the cell buckets
     const int flag = cnt[C_FLAG];
+    if (blockIdx.x == 0 && threadIdx.x == 0) *cross = sv.do_prune ? 0ull : ~0ull;  // everybody read it before the first barrier; P5 rebuilds it
     int h_base, Hn;
     block_sums_reduce<NT>(sums_y, h_base, Hn);
     for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) {
@@ -1519,7 +1595,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     TNB_PHASE_MARK(5);
     // P5 / P6: pruning (subpoly.py:252-277): keep the edges whose ends differ in a future indicator
     const KeepCount kc{edges, sig, sv.futmask};
-    scan_count_body_t<NT>(En, kc, sums_y);
+    keep_count_cross<NT>(En, edges, sig, sv.futmask, sums_y, cnt);
     sync();
     TNB_PHASE_MARK(6);
     int k_base, kept;
@@ -1593,7 +1669,7 @@ static bool g_fused_steps = std::getenv("TNB_NO_FUSED_STEPS") == nullptr;  // A/
 // Refresh the host's view of the complex size (one small D2H + sync).
 int complex_sync_counts(tnb_complex *c, cudaStream_t s)
 {
-    if (!c->counts_stale) return TNB_OK;
+    if (!c->counts_stale && !c->cross_stale) return TNB_OK;
     int rc = read_counters(c, s);
     if (rc) return rc;
     c->V = c->h_counters[C_V];
@@ -1601,6 +1677,8 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
     c->vcur = c->h_counters[C_VPAR];
     c->ecur = c->h_counters[C_EPAR];
     c->acur = c->h_counters[C_APAR];
+    memcpy(&c->cross, c->h_counters + C_CROSS, sizeof(uint64_t));
+    c->cross_stale = false;
     c->counts_stale = false;
     if (c->bytes.p) {  // algorithmic bytes the fused kernels accumulated on the device
         unsigned long long hb[2] = {0, 0};
@@ -1716,6 +1794,7 @@ static void fill_step_args(const tnb_net *net, tnb_complex *c, float eps, StepAr
 {
     memset(&sa, 0, sizeof(sa));
     sa.R = net->meta.R; sa.eps = eps;
+    sa.use_cross = (eps == net->meta.eps && net->meta.R <= 64) ? 1 : 0;
     sa.Vcap = (int)c->Vcap; sa.Ecap = (int)c->Ecap; sa.dim = c->cell_dim;
     for (int k = 0; k < 2; ++k) {
         sa.edges[k] = c->edges[k].p; sa.vert[k] = c->vert[k].p; sa.out[k] = c->out[k].p; sa.sig[k] = c->sig[k].p;
@@ -1848,6 +1927,7 @@ int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh,
     count_launch();
     prof_end(TNB_PROF_NEW_VERTICES, s, 0);
     c->counts_stale = true;
+    c->cross_stale = true;
     if (prunes) c->maybe_dead = true;
     return phase_trace_print(mode == 2 ? "cluster steps" : "grid steps", n_steps, s);
 }
@@ -1946,6 +2026,8 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     if ((rc = complex_sync_counts(c, s))) return rc;
     if (c->E == 0) return TNB_OK;
     // dead rows cost a little in every per-vertex pass: squeeze them out once they fill half the arrays
+    // the pruning pass of the last step that changed the complex saw no edge across this plane
+    if (eps == m.eps && idx < 64 && !((c->cross >> idx) & 1ull)) return TNB_OK;
     if (c->maybe_dead && (size_t)c->V * 2 > c->Vcap && (rc = complex_compact(c, s))) return rc;
     cnt = c->counters.p;
 
@@ -2057,7 +2139,15 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         TNB_CUDA(cudaMemsetAsync(used, 0, (size_t)c->V * sizeof(int), s));
         KeepCount kc{c->cedges(), c->csig(), futmask};
         int2 *dst = c->edges[c->ecur ^ 1].p;
-        if ((rc = compact(c->E, kc, KeepEmit{c->cedges(), dst, used}, c->block_sums.p, cnt + C_E, s))) return rc;
+        {   // the compaction of scan.cuh's compact(), its count pass also collecting the crossing mask
+            const int64_t blocks = std::min<int64_t>((c->E + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
+            TNB_CUDA(cudaMemsetAsync(cnt + C_CROSS, 0, sizeof(uint64_t), s));
+            k_keep_count_cross<<<(unsigned)blocks, kScanThreads, 0, s>>>(c->E, nullptr, c->cedges(), c->csig(), futmask, c->block_sums.p, cnt);
+            TNB_LAUNCH_CHECK();
+            k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(c->E, nullptr, kc, KeepEmit{c->cedges(), dst, used}, c->block_sums.p, cnt + C_E);
+            TNB_LAUNCH_CHECK();
+            c->cross_stale = true;
+        }
         c->ecur ^= 1;
         c->acur ^= 1;
         k_set_counts<<<1, 1, 0, s>>>(cnt, (int)c->V, -1, c->vcur, c->ecur, c->acur);  // the fused kernels read sizes and parity on the device
@@ -2066,6 +2156,8 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         c->counts_stale = true;  // c->E is an upper bound until the next sync
     } else {
         TNB_CUDA(cudaMemsetAsync(c->calive() + V0, 1, (size_t)S * sizeof(int), s));  // the new vertices are alive
+        TNB_CUDA(cudaMemsetAsync(cnt + C_CROSS, 0xff, sizeof(uint64_t), s));          // no pruning pass: crossings unknown
+        c->cross = ~0ull;
         k_set_counts<<<1, 1, 0, s>>>(cnt, (int)c->V, (int)c->E, c->vcur, c->ecur, c->acur);
         TNB_LAUNCH_CHECK();
     }
@@ -2145,7 +2237,8 @@ static int from_arrays_impl(const tnb_net *net, const float *d_vertices, int64_t
     c->E = E;
     k_set_counts<<<1, 1, 0, s>>>(c->counters.p, (int)V, (int)E, c->vcur, c->ecur, c->acur);
     TNB_LAUNCH_CHECK();
-    return eval_vertices(net, c, 0, V, s);
+    if ((rc = eval_vertices(net, c, 0, V, s))) return rc;
+    return initial_cross_mask(c, s);
 }
 
 }  // namespace tnb

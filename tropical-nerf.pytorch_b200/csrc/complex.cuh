@@ -49,6 +49,11 @@ struct tnb_complex {
     int64_t V = 0, E = 0;
     size_t Vcap = 0, Ecap = 0;
     int vcur = 0, ecur = 0, acur = 0;
+    // bit j set = some edge of the current complex has ends on opposite sides of hyperplane j (from the
+    // packed signs, OR-ed over the edges by the pruning pass): a clear bit means step j is a no-op
+    // (subpoly.py:110-111) and is skipped without looking at the edges again
+    uint64_t cross = ~0ull;
+    bool cross_stale = false;       // the device holds a newer mask than `cross`
     bool maybe_dead = false;        // a prune ran since the last compaction: rows of dead vertices may exist
     tnb::DevBuf<float> vert[2], out[2];
     tnb::DevBuf<uint64_t> sig[2];
