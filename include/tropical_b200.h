@@ -221,9 +221,10 @@ void tnb_launch_count_reset(void);
  * events on the launching stream.  Classes: 0 = marks-grid sweep (sdf + gradient),
  * 1 = vertex network rows (outputs + packed signs), 2 = new-vertex subdivision kernel,
  * 3 = connecting-edge search, 4 = face rows, 5 = dense sign sweep.
- * On small complexes the planar step runs as two fused cooperative kernels: class 2 then
- * times the front half (split scan + new vertices + hit scan + buckets + partner count) and
- * class 3 the back half (connecting-edge write + pruning compactions).
+ * On small complexes all hyperplanes run inside ONE persistent cooperative kernel (class 6).
+ * A slab-sharded complex runs each step as two cooperative kernels around the exchange: class 2
+ * then times the front half (split scan + new vertices + hit scan + buckets + partner count) and
+ * class 3 the back half (connecting-edge write + pruning compaction).
  * tnb_profile_read synchronises the recorded events and returns the summed milliseconds,
  * the launch count, the units (vertices / points / edges / candidates) processed and the
  * ALGORITHMIC bytes of those launches (compulsory HBM traffic). */
@@ -233,7 +234,8 @@ void tnb_launch_count_reset(void);
 #define TNB_PROF_PAIRS 3
 #define TNB_PROF_FACE_ROWS 4
 #define TNB_PROF_SIGN_SWEEP 5
-#define TNB_PROF_CLASSES 6
+#define TNB_PROF_STEPS 6       /* persistent step kernel: every hyperplane of a small complex in one launch */
+#define TNB_PROF_CLASSES 7
 int tnb_profile_enable(int on);
 int tnb_profile_read(int cls, double *ms, int64_t *launches, int64_t *units, int64_t *bytes);
 void tnb_profile_reset(void);

@@ -1685,8 +1685,12 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
         TNB_CUDA(cudaMemcpyAsync(hb, c->bytes.p, sizeof(hb), cudaMemcpyDeviceToHost, s));
         TNB_CUDA(cudaMemsetAsync(c->bytes.p, 0, sizeof(hb), s));
         TNB_CUDA(cudaStreamSynchronize(s));
-        prof_add(TNB_PROF_NEW_VERTICES, 0, (int64_t)hb[0]);
-        prof_add(TNB_PROF_PAIRS, 0, (int64_t)hb[1]);
+        if (c->halo.enabled) {
+            prof_add(TNB_PROF_NEW_VERTICES, 0, (int64_t)hb[0]);
+            prof_add(TNB_PROF_PAIRS, 0, (int64_t)hb[1]);
+        } else {
+            prof_add(TNB_PROF_STEPS, 0, (int64_t)(hb[0] + hb[1]));
+        }
     }
     if (c->h_counters[C_STICKY] & kStickyCapacity) {
         set_error("work buffers too small for this complex (capacity factor " + std::to_string(g_capacity_factor) + ")");
@@ -1906,7 +1910,7 @@ int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh,
     fill_step_args(net, c, eps, sa);
     int rc;
     if ((rc = phase_trace_begin(sa, s))) return rc;
-    prof_begin(TNB_PROF_NEW_VERTICES, s);
+    prof_begin(TNB_PROF_STEPS, s);
     if (mode == 2) {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(blocks);
@@ -1925,7 +1929,7 @@ int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh,
         else TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_steps_grid<CfgAny>, dim3(blocks), dim3(kScanThreads), params, 0, s));
     }
     count_launch();
-    prof_end(TNB_PROF_NEW_VERTICES, s, 0);
+    prof_end(TNB_PROF_STEPS, s, 0);
     c->counts_stale = true;
     c->cross_stale = true;
     if (prunes) c->maybe_dead = true;

@@ -134,7 +134,7 @@ def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
-PROFILE_CLASSES = ["sweep", "vertex_rows", "step_front", "step_back", "face_rows", "sign_sweep"]
+PROFILE_CLASSES = ["sweep", "vertex_rows", "step_front", "step_back", "face_rows", "sign_sweep", "steps_persistent"]
 
 
 def profile_enable(on=True):
