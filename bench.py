@@ -480,6 +480,40 @@ def run_ours(args):
                  "note": "output larger than L2 (16 B/point); the kernel is fp32-issue bound"}
         del buf
 
+    # ---- several objects in flight on ONE GPU (outside the timed region; N=1 only) ---------
+    # K host threads, one CUDA stream each; the hyperplanes of every object run inside ONE
+    # thread-block cluster (16 SMs), so up to 8 objects' step loops are resident side by side.
+    concurrent = None
+    if world == 1 and not slab and planar and args.concurrent > 1:
+        import threading
+        K, M = args.concurrent, 12
+        before = _native.lib().tnb_set_cluster_max_items(200000)   # complexes up to 200 k items take the cluster form
+        streams = [torch.cuda.Stream() for _ in range(K)]
+        gate = threading.Barrier(K + 1)
+
+        def work(i):
+            with torch.cuda.stream(streams[i]):
+                step()
+                streams[i].synchronize()
+                gate.wait()
+                for _ in range(M):
+                    step()
+                streams[i].synchronize()
+
+        th = [threading.Thread(target=work, args=(i,)) for i in range(K)]
+        for x in th:
+            x.start()
+        gate.wait()
+        tc = time.perf_counter()
+        for x in th:
+            x.join()
+        dtc = time.perf_counter() - tc
+        _native.lib().tnb_set_cluster_max_items(before)
+        concurrent = {"objects_in_flight": K, "objects_per_s": K * M / dtc, "vertices_per_s": K * M * sizes["V"] / dtc,
+                      "vs_one_at_a_time": (K * M * sizes["V"] / dtc) / value,
+                      "note": "K host threads x 1 stream; small complexes run their hyperplanes in one 16-CTA cluster each "
+                              "(k_steps_cluster); bounded by the host's CUDA API call rate (~100 calls per extraction)"}
+
     # ---- CPU baseline (bounded sample on the box's host cores) ----------------------------
     cpu = None
     if world == 1 and not args.no_cpu:
@@ -499,7 +533,7 @@ def run_ours(args):
            "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": 1e3 * float(t.item()) / args.steps},
-           "roofline": roofline, "cpu_baseline": cpu, "eval_sweep": sweep}
+           "roofline": roofline, "cpu_baseline": cpu, "eval_sweep": sweep, "concurrent": concurrent}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -518,6 +552,7 @@ def main():
                     help="N>1: object = every rank extracts its own object (weak scaling, default); "
                          "slab = ONE object cut into marks-grid slabs, one per GPU (strong scaling)")
     ap.add_argument("--ref-cores", type=int, default=0, help="--impl reference: host cores to use (0 = all)")
+    ap.add_argument("--concurrent", type=int, default=8, help="extra leg: objects in flight on one GPU (0/1 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the evaluation-sweep throughput leg")
     ap.add_argument("--sweep-n", type=int, default=512, help="lattice size per axis of the evaluation sweep")
