@@ -199,38 +199,40 @@ struct SkelEdgeCount {
     const float *dist;
     const unsigned *max_grad;
     float k_len;  // (sqrt(3)*2) * max mark spacing  (tropical.py:125-126)
-    __device__ __forceinline__ bool locate(int64_t t, int &hi, int &lo) const
+    mutable int hint = 0;  // segment of the thread's previous slot: successive slots of a thread rarely change segment
+    // segment of slot t (last one with first <= t)
+    __device__ __forceinline__ int seg_of(int64_t t) const
     {
-        int a = 0, b = n_segs - 1;
-        while (a < b) {  // last segment with first <= t
-            int mid = (a + b + 1) >> 1;
-            if (segs[mid].first <= t) a = mid; else b = mid - 1;
-        }
-        const ChunkSeg sg = segs[a];
-        int64_t r = t - sg.first;
-        int dims[3] = {sg.n[0], sg.n[1], sg.n[2]};
-        dims[sg.axis] -= 1;
-        const int k = (int)(r % dims[2]), j = (int)((r / dims[2]) % dims[1]), i = (int)(r / ((int64_t)dims[2] * dims[1]));
-        int p[3] = {sg.s[0] + i, sg.s[1] + j, sg.s[2] + k};
-        lo = (p[0] * M + p[1]) * M + p[2];
-        p[sg.axis] += 1;
-        hi = (p[0] * M + p[1]) * M + p[2];
-        return true;
-    }
-    __device__ __forceinline__ int chunk_of(int64_t t) const
-    {
-        int a = 0, b = n_segs - 1;
+        int a = hint;
+        if (segs[a].first <= t && (a + 1 == n_segs || t < segs[a + 1].first)) return a;
+        a = 0;
+        int b = n_segs - 1;
         while (a < b) {
             int mid = (a + b + 1) >> 1;
             if (segs[mid].first <= t) a = mid; else b = mid - 1;
         }
-        return segs[a].chunk;
+        hint = a;
+        return a;
+    }
+    // the two grid vertices of slot t; returns the chunk (32-bit index arithmetic: a segment has < 2^31 slots)
+    __device__ __forceinline__ int locate(int64_t t, int &hi, int &lo) const
+    {
+        const ChunkSeg sg = segs[seg_of(t)];
+        const unsigned r = (unsigned)(t - sg.first);
+        unsigned dims[3] = {(unsigned)sg.n[0], (unsigned)sg.n[1], (unsigned)sg.n[2]};
+        dims[sg.axis] -= 1;
+        const unsigned q = r / dims[2], k = r - q * dims[2], i = q / dims[1], j = q - i * dims[1];
+        int p[3] = {sg.s[0] + (int)i, sg.s[1] + (int)j, sg.s[2] + (int)k};
+        lo = (p[0] * M + p[1]) * M + p[2];
+        p[sg.axis] += 1;
+        hi = (p[0] * M + p[1]) * M + p[2];
+        return sg.chunk;
     }
     __device__ __forceinline__ int operator()(int64_t t) const
     {
         int hi, lo;
-        locate(t, hi, lo);
-        const float eps = k_len * __uint_as_float(max_grad[chunk_of(t)]);
+        const int chunk = locate(t, hi, lo);
+        const float eps = k_len * __uint_as_float(max_grad[chunk]);
         return (dist[hi] <= eps && dist[lo] <= eps) ? 1 : 0;
     }
 };
@@ -1011,6 +1013,21 @@ __device__ __forceinline__ void pair_write_item(int a, const int *cand, const ui
         }
     }
 }
+// connecting edges of the candidates [begin, end) by the calling CTA (NT threads), one thread per
+// candidate.  (Measured alternative: 8-lane / 32-lane groups walking the cells of one candidate side
+// by side and rank-sorting its list: 2.4x SLOWER on the large model, 348 vs 145 us per launch: the
+// coincident-vertex clusters of the reference's chunk-overlap duplicates make long lists the common
+// case there, and one list per thread keeps far more dependent-load chains in flight.)
+template <int NT>
+__device__ __forceinline__ void pair_write_range(int begin, int end, const int *cand, const uint64_t *sig,
+                                                 const unsigned long long *head, const tnb_bucket_rec *next, int dim,
+                                                 uint32_t stamp, uint64_t colmask, const int *pcount, const int *poff,
+                                                 int2 *edges_out, const int *pcache)
+{
+    for (int a = begin + (int)threadIdx.x; a < end; a += NT)
+        pair_write_item(a, cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache);
+}
+template <int NT>
 __device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
                                                          const uint64_t *sig,
                                                          const unsigned long long *head,
@@ -1018,8 +1035,8 @@ __device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
                                                          uint64_t colmask, const int *pcount,
                                                          const int *poff, int2 *edges_out, const int *pcache)
 {
-    for (int a = blockIdx.x * blockDim.x + threadIdx.x; a < n_cand; a += gridDim.x * blockDim.x)
-        pair_write_item(a, cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache);
+    for (int base = blockIdx.x * NT; base < n_cand; base += gridDim.x * NT)
+        pair_write_range<NT>(base, min(base + NT, n_cand), cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache);
 }
 
 __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__ cand, int n_cand,
@@ -1030,7 +1047,7 @@ __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__
                                                          const int *__restrict__ poff, int2 *__restrict__ edges_out,
                                                          const int *__restrict__ pcache)
 {
-    body_pair_write(cand, n_cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache);
+    body_pair_write<kThreads>(cand, n_cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache);
 }
 
 // ---- pruning -------------------------------------------------------------------------------------
@@ -1397,7 +1414,7 @@ __device__ __forceinline__ void step_back(const StepArgs &a, const StepVar sv, S
             return;
         }
         if (P > 0)
-            body_pair_write(a.cand, n_cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.poff, edges + E0 + S, a.pcache);
+            body_pair_write<NT>(a.cand, n_cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.poff, edges + E0 + S, a.pcache);
         if (!sv.do_prune) {  // the output neuron (subpoly.py:253): sizes only
             if (a.halo) {   // no liveness to exchange, only the status word
                 if (blockIdx.x == 0 && threadIdx.x == 0) a.stage_count[0] = a.stage_count[1] = 0;
@@ -1578,8 +1595,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     }
     if (P > 0) {
         scan_write_from<NT>(n_cand, ArrayCount{a.pcount}, OffsetEmit{a.poff}, p_base);
-        for (int c = (int)c_begin + (int)threadIdx.x; c < (int)c_end; c += NT)
-            pair_write_item(c, a.cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.poff, edges + E + S, a.pcache);
+        pair_write_range<NT>((int)c_begin, (int)c_end, a.cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.poff, edges + E + S, a.pcache);
     }
     if (!sv.do_prune) {  // the output neuron (subpoly.py:253): sizes only
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -2029,10 +2045,10 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     // multi-launch path: needs the host's view of sizes and buffer parity to be current
     if ((rc = complex_sync_counts(c, s))) return rc;
     if (c->E == 0) return TNB_OK;
-    // dead rows cost a little in every per-vertex pass: squeeze them out once they fill half the arrays
+    // dead rows cost a little in every per-vertex pass: squeeze them out once the arrays are three quarters full
     // the pruning pass of the last step that changed the complex saw no edge across this plane
     if (eps == m.eps && idx < 64 && !((c->cross >> idx) & 1ull)) return TNB_OK;
-    if (c->maybe_dead && (size_t)c->V * 2 > c->Vcap && (rc = complex_compact(c, s))) return rc;
+    if (c->maybe_dead && (size_t)c->V * 4 > c->Vcap * 3 && (rc = complex_compact(c, s))) return rc;
     cnt = c->counters.p;
 
     for (int attempt = 0;; ++attempt) {
