@@ -64,7 +64,7 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
     TNB_CUDA(c->pcache.reserve(Vcap * kCachedPartners));
     TNB_CUDA(c->next.reserve(Vcap * 8));
     TNB_CUDA(c->remap.reserve(Vcap));
-    TNB_CUDA(c->block_sums.reserve(kScanMaxBlocks));
+    TNB_CUDA(c->block_sums.reserve(3 * kScanMaxBlocks));  // the persistent step kernels keep three sets of block sums
     TNB_CUDA(c->counters.reserve(C_NUM));
     TNB_CUDA(c->bytes.reserve(2));
     TNB_CUDA(cudaMemsetAsync(c->bytes.p, 0, 2 * sizeof(unsigned long long), current_stream()));
@@ -1660,6 +1660,14 @@ __global__ void __launch_bounds__(kScanThreads, 1) k_steps_grid(const __grid_con
 {
     steps_loop<C, kScanThreads>(n, a, list, GridSync{cg::this_grid()});
 }
+// ... by two CTAs per SM (<= 128 registers): twice the threads in flight for a complex whose phases are
+// throughput bound, at the price of a slightly dearer barrier
+template <class C>
+__global__ void __launch_bounds__(kScanThreads, 2) k_steps_grid2(const __grid_constant__ NetMeta n, const __grid_constant__ StepArgs a,
+                                                                 const __grid_constant__ StepList list)
+{
+    steps_loop<C, kScanThreads>(n, a, list, GridSync{cg::this_grid()});
+}
 // ... by ONE thread-block cluster of 16 CTAs: a barrier costs a tenth, but 16 SMs do the work of
 // 148.  Slower for one object; it leaves 132 SMs to other objects' clusters.
 template <class C>
@@ -1679,7 +1687,7 @@ static int coop_blocks(K kernel)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kScanThreads, 0) != cudaSuccess || per_sm < 1) return 0;
     return std::min(per_sm * sms, kScanMaxBlocks);
 }
-constexpr int64_t kFusedMaxItems = 400000;
+static const int64_t kFusedMaxItems = std::getenv("TNB_FUSED_MAX_ITEMS") ? std::atoll(std::getenv("TNB_FUSED_MAX_ITEMS")) : 700000;  // larger complexes: multi-launch path (measured: the large model's 2.3 M items take 6.2 ms in the persistent kernel, 3.7 ms as separate full-size launches)
 static bool g_fused_steps = std::getenv("TNB_NO_FUSED_STEPS") == nullptr;  // A/B switch for profiling
 
 // Refresh the host's view of the complex size (one small D2H + sync).
@@ -1893,18 +1901,23 @@ int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh,
     const int H = m.H, R = m.R;
     if (n_steps <= 0) return TNB_OK;
     if (n_steps > kMaxStepList || R > 256) return TNB_ERR_UNSUPPORTED;
-    static int cs_ref = -1, cs_any = -1, gb_ref = -1, gb_any = -1;
+    static int cs_ref = -1, cs_any = -1, gb_ref = -1, gb_any = -1, g2_ref = -1, g2_any = -1;
     if (cs_ref < 0) {
         cs_ref = cluster_ctas(k_steps_cluster<CfgRef>);
         cs_any = cluster_ctas(k_steps_cluster<CfgAny>);
         gb_ref = coop_blocks(k_steps_grid<CfgRef>);
         gb_any = coop_blocks(k_steps_grid<CfgAny>);
+        g2_ref = coop_blocks(k_steps_grid2<CfgRef>);
+        g2_any = coop_blocks(k_steps_grid2<CfgAny>);
     }
+    static const int64_t wide_from = std::getenv("TNB_WIDE_FROM_ITEMS") ? std::atoll(std::getenv("TNB_WIDE_FROM_ITEMS")) : 150000;  // medium model: steps 0.68 -> 0.58 ms with two CTAs per SM
+    const bool wide = mode == 1 && c->E + c->V > wide_from && (net->fixed_cfg ? g2_ref : g2_any) >= 2 * kSMs;
     static const int env_blocks = std::getenv("TNB_STEP_BLOCKS") ? std::atoi(std::getenv("TNB_STEP_BLOCKS")) : 0;  // tuning knob
     // one CTA per SM keeps the grid barrier cheap
     const int blocks = mode == 2 ? (net->fixed_cfg ? cs_ref : cs_any)
+                       : wide    ? 2 * kSMs
                                  : std::min(env_blocks > 0 ? env_blocks : kSMs, net->fixed_cfg ? gb_ref : gb_any);
-    if (blocks <= 0 || 3 * blocks > kScanMaxBlocks) return TNB_ERR_UNSUPPORTED;
+    if (blocks <= 0 || blocks > kScanMaxBlocks) return TNB_ERR_UNSUPPORTED;
     StepList list;
     memset(&list, 0, sizeof(list));
     list.n = n_steps;
@@ -1941,8 +1954,9 @@ int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh,
         else TNB_CUDA(cudaLaunchKernelEx(&cfg, k_steps_cluster<CfgAny>, m, sa, list));
     } else {
         void *params[] = {(void *)&m, (void *)&sa, (void *)&list};
-        if (net->fixed_cfg) TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_steps_grid<CfgRef>, dim3(blocks), dim3(kScanThreads), params, 0, s));
-        else TNB_CUDA(cudaLaunchCooperativeKernel((void *)k_steps_grid<CfgAny>, dim3(blocks), dim3(kScanThreads), params, 0, s));
+        const void *kern = wide ? (net->fixed_cfg ? (const void *)k_steps_grid2<CfgRef> : (const void *)k_steps_grid2<CfgAny>)
+                                : (net->fixed_cfg ? (const void *)k_steps_grid<CfgRef> : (const void *)k_steps_grid<CfgAny>);
+        TNB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kScanThreads), params, 0, s));
     }
     count_launch();
     prof_end(TNB_PROF_STEPS, s, 0);
