@@ -459,26 +459,31 @@ def run_ours(args):
     # ---- evaluation-sweep throughput (BASELINE configs[4]), outside the timed region -----
     sweep = None
     if not args.no_sweep:
-        n3 = args.sweep_n
-        buf = torch.empty((n3 ** 3, 2), dtype=torch.int64, device="cuda")
-        for _ in range(2):
-            net.sweep_signs((-1, -1, -1), (1, 1, 1), (n3, n3, n3), out=buf)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        reps = 5
-        torch.cuda.synchronize()
-        a.record()
-        for _ in range(reps):
-            net.sweep_signs((-1, -1, -1), (1, 1, 1), (n3, n3, n3), out=buf)
-        b.record()
-        torch.cuda.synchronize()
-        ms_sw = a.elapsed_time(b) / reps
-        pts = n3 ** 3
-        sweep = {"lattice": f"{n3}^3", "points_per_s": pts / (ms_sw * 1e-3), "ms": ms_sw,
-                 "algorithmic_bytes_per_point": 16, "achieved_gbs": pts * 16 / (ms_sw * 1e-3) / 1e9,
-                 "hbm_frac": pts * 16 / (ms_sw * 1e-3) / 1e9 / peak,
-                 "approx_fp32_tflops": pts * 2 * (4 * 8 * 5 + 8 * 16 + 16 * 16 + 16 * 2) / (ms_sw * 1e-3) / 1e12,
-                 "note": "output larger than L2 (16 B/point); the kernel is fp32-issue bound"}
-        del buf
+        sweep = {"algorithmic_bytes_per_point": 16,
+                 "note": "batched trilinear network eval + packed sign vectors over a dense lattice; output larger than L2 "
+                         "(16 B/point); the kernel is fp32-issue bound", "lattices": []}
+        for n3 in ([args.sweep_n] if args.sweep_n > 0 else [256, 512, 1024]):
+            buf = torch.empty((n3 ** 3, 2), dtype=torch.int64, device="cuda")
+            for _ in range(2):
+                net.sweep_signs((-1, -1, -1), (1, 1, 1), (n3, n3, n3), out=buf)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            torch.cuda.synchronize()
+            a.record()
+            for _ in range(reps):
+                net.sweep_signs((-1, -1, -1), (1, 1, 1), (n3, n3, n3), out=buf)
+            b.record()
+            torch.cuda.synchronize()
+            ms_sw = a.elapsed_time(b) / reps
+            pts = n3 ** 3
+            one = {"lattice": f"{n3}^3", "points_per_s": pts / (ms_sw * 1e-3), "ms": ms_sw,
+                   "achieved_gbs": pts * 16 / (ms_sw * 1e-3) / 1e9, "hbm_frac": pts * 16 / (ms_sw * 1e-3) / 1e9 / peak,
+                   "approx_fp32_tflops": pts * 2 * (4 * 8 * 5 + 8 * 16 + 16 * 16 + 16 * 2) / (ms_sw * 1e-3) / 1e12}
+            sweep["lattices"].append(one)
+            if n3 == 512 or len(sweep["lattices"]) == 1:
+                sweep.update(one)
+            del buf
+            torch.cuda.empty_cache()
 
     # ---- several objects in flight on ONE GPU (outside the timed region; N=1 only) ---------
     # K host threads, one CUDA stream each; the hyperplanes of every object run inside ONE
@@ -555,7 +560,7 @@ def main():
     ap.add_argument("--concurrent", type=int, default=8, help="extra leg: objects in flight on one GPU (0/1 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-sweep", action="store_true", help="skip the evaluation-sweep throughput leg")
-    ap.add_argument("--sweep-n", type=int, default=512, help="lattice size per axis of the evaluation sweep")
+    ap.add_argument("--sweep-n", type=int, default=0, help="lattice size per axis of the evaluation sweep (0 = 256, 512 and 1024)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
