@@ -38,7 +38,7 @@ constexpr int kCachedPartners = 12;  // the partner-count pass keeps this many p
 //   C_APAR = which half of the liveness array is current.  C_V counts vertex SLOTS (dead rows included)
 enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_CROSS = 16 /* 64-bit crossing mask */, C_NUM = 32 };
 enum { kErrNoPlane = 1, kErrGradientDescent = 2 };
-enum { kStickyCapacity = 1 };
+enum { kStickyCapacity = 1, kStickyNoPlane = 32, kStickyGradientDescent = 64 };  // 2..16: halo.cuh
 
 // ---- allocation ---------------------------------------------------------------------------
 int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
@@ -619,22 +619,14 @@ __global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant
 // ping-pong vertex arrays), no rewiring yet.  sflag bit0 = edge is not axis aligned (c),
 // bit1 = no admissible intersection (gg).
 template <class C>
-__global__ void __launch_bounds__(kThreads) k_new_vertices_curve(const __grid_constant__ NetMeta n, int idx, float eps,
-                                                                 int Vcap, int Ecap, const int *__restrict__ split_list,
-                                                                 const int2 *__restrict__ edges,
-                                                                 const float *__restrict__ vert, const float *__restrict__ out,
-                                                                 const uint64_t *__restrict__ sig, float *__restrict__ tvert,
-                                                                 float *__restrict__ tout, uint64_t *__restrict__ bmask,
-                                                                 int *__restrict__ sflag, int *__restrict__ cnt)
+__device__ __forceinline__ int curve_candidate_item(const NetMeta &n, int idx, float eps, int k, const int *split_list,
+                                                    const int2 *edges, const float *vert, const float *out,
+                                                    const uint64_t *sig, float *tvert, float *tout, uint64_t *bmask,
+                                                    int *sflag, int *cnt)
 {
     const int R = n.R;
-    const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
-    if ((int64_t)V + S > Vcap || (int64_t)E + S > Ecap) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_OVERFLOW] = 1;
-        return;
-    }
     int any = 0;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
+    {
         const int e = split_list[k];
         const int2 ed = edges[e];
         float e0[3], e1[3];
@@ -692,25 +684,47 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices_curve(const __grid_co
             if (fabsf(row[col]) > eps) any = 1;
         }
     }
+    return any;
+}
+
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_new_vertices_curve(const __grid_constant__ NetMeta n, int idx, float eps,
+                                                                 int Vcap, int Ecap, const int *__restrict__ split_list,
+                                                                 const int2 *__restrict__ edges,
+                                                                 const float *__restrict__ vert, const float *__restrict__ out,
+                                                                 const uint64_t *__restrict__ sig, float *__restrict__ tvert,
+                                                                 float *__restrict__ tout, uint64_t *__restrict__ bmask,
+                                                                 int *__restrict__ sflag, int *__restrict__ cnt)
+{
+    const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
+    if ((int64_t)V + S > Vcap || (int64_t)E + S > Ecap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_OVERFLOW] = 1;
+        return;
+    }
+    int any = 0;
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x)
+        any |= curve_candidate_item<C>(n, idx, eps, k, split_list, edges, vert, out, sig, tvert, tout, bmask, sflag, cnt);
     if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
 }
 
 // Pass 2: failover override on the temp rows, then strict_check's keep decision
 // (subpoly_debug.py:234-271): on the plane within eps, and not a curved edge without a root.
+__device__ __forceinline__ void strict_keep_item(int R, int idx, float eps, float *tout, const uint64_t *bmask, int *sflag, int flag, int k)
+{
+    float *row = tout + (int64_t)k * R;
+    if (flag)
+        for (uint64_t m = bmask[k]; m; m &= m - 1) row[__ffsll((long long)m) - 1] = 0.0f;
+    const int f = sflag[k];
+    const bool keep = fabsf(row[idx]) < eps && !((f & 1) && (f & 2));
+    sflag[k] = keep ? 1 : 0;
+}
 __global__ void __launch_bounds__(kThreads) k_strict_keep(int R, int idx, float eps, float *__restrict__ tout,
                                                           const uint64_t *__restrict__ bmask, int *__restrict__ sflag,
                                                           const int *__restrict__ cnt)
 {
     if (cnt[C_OVERFLOW]) return;
     const int flag = cnt[C_FLAG], S = cnt[C_RAW];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) {
-        float *row = tout + (int64_t)k * R;
-        if (flag)
-            for (uint64_t m = bmask[k]; m; m &= m - 1) row[__ffsll((long long)m) - 1] = 0.0f;
-        const int f = sflag[k];
-        const bool keep = fabsf(row[idx]) < eps && !((f & 1) && (f & 2));
-        sflag[k] = keep ? 1 : 0;
-    }
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) strict_keep_item(R, idx, eps, tout, bmask, sflag, flag, k);
 }
 
 struct KeepFlagCount {
@@ -1511,7 +1525,10 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a,
 // costs ONE barrier: 7 barriers per hyperplane that crosses something, 1 for one that does not
 // (subpoly.py:110-111), and nothing returns to the host in between.
 //   returns 0 = done, 2 = nothing to do, 1 = work arrays too small (uniform over the CTAs)
-template <class C, int NT, class Sync>
+//   kCurve: the curve-approximation path (force=False).  The candidates of a CTA's crossed edges go to
+//   temporary rows (the idle half of the vertex arrays); strict_check's keep decision needs the
+//   failover flag of ALL candidates and the survivors need their ordered rank: two more barriers.
+template <class C, int NT, bool kCurve, class Sync>
 __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, const StepVar sv, int parity, Sync sync)
 {
     int *cnt = a.cnt;
@@ -1528,7 +1545,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     unsigned long long *cross = (unsigned long long *)(cnt + C_CROSS);
     if (a.use_cross && !((*cross >> sv.idx) & 1ull)) return 2;
     TNB_PHASE_MARK(0);
-    if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_FLAG] = 0;  // last read two barriers ago
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cnt[C_FLAG] = 0; cnt[C_ERR] = 0; }  // last read two barriers ago
     // P0: edges the plane crosses, per CTA slice
     const SplitCount sc{edges, out, R, sv.idx, a.eps};
     scan_count_body_t<NT>(E, sc, sums_x);
@@ -1542,25 +1559,55 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
         if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_STICKY] = kStickyCapacity;
         return 1;
     }
-    const int s_end = scan_write_from<NT>(E, sc, ListEmit{a.split_list}, s_base);
+    int s_end = scan_write_from<NT>(E, sc, ListEmit{a.split_list}, s_base);
+    float *tvert = a.vert[pv ^ 1], *tout = a.out[pv ^ 1];  // curve path: temporary rows of the candidates
+    int *sflag = a.pcount;                                 // free until P3
     {
         int any = 0;
-        for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT)
-            any |= new_vertex_item<C>(n, sv.idx, a.eps, k, V, E, a.split_list, edges, vert, out, sig, a.bmask, tag);
+        for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) {
+            if constexpr (kCurve)
+                any |= curve_candidate_item<C>(n, sv.idx, a.eps, k, a.split_list, edges, vert, out, sig, tvert, tout, a.bmask, sflag, cnt);
+            else
+                any |= new_vertex_item<C>(n, sv.idx, a.eps, k, V, E, a.split_list, edges, vert, out, sig, a.bmask, tag);
+        }
         if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
     }
     const HitCount hc{out, alive, R, sv.idx, a.eps};  // old vertices only: independent of the new rows
     scan_count_body_t<NT>(V, hc, sums_y);
     sync();
     TNB_PHASE_MARK(2);
+    const int flag = cnt[C_FLAG];
+    const int S_raw = S;
+    if constexpr (kCurve) {
+        // P1b: an intersection the path cannot place ends the extraction (uniform: C_ERR was last
+        // written before the barrier); else strict_check (subpoly_debug.py:234-271) on the own candidates
+        const int err = cnt[C_ERR];
+        if (err) {
+            if (blockIdx.x == 0 && threadIdx.x == 0)
+                atomicOr(cnt + C_STICKY, ((err & kErrNoPlane) ? kStickyNoPlane : 0) | ((err & kErrGradientDescent) ? kStickyGradientDescent : 0));
+            return 1;
+        }
+        for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) strict_keep_item(R, sv.idx, a.eps, tout, a.bmask, sflag, flag, k);
+        __syncthreads();
+        scan_count_range<NT>(s_base, s_end, FlagCount{sflag}, sums_x);  // everybody finished reading sums_x before the barrier above
+        sync();
+        TNB_PHASE_MARK(8);
+        // P1c: the survivors move to their final slots V + rank, in crossed-edge order; edges are rewired
+        int r_base;
+        block_sums_reduce<NT>(sums_x, r_base, S);
+        const CurveCommitEmit ce{nullptr, a.split_list, edges, tvert, tout, vert, out, sig, n.marks, cnt, R, n.n_marks, n.eps,
+                                 n.pre_scale, n.pre_2s, n.pre_inv, n.pre_pow2, tag};
+        const int r_end = scan_write_range<NT>(s_base, s_end, FlagCount{sflag}, ce, r_base);
+        s_base = r_base;  // from here on: the CTA's own NEW VERTICES are the ranks [s_base, s_end)
+        s_end = r_end;
+    }
     // P2: failover override + packed signs of the own new vertices; candidate list (hit old vertices,
     // then the new ones); the own candidates go into the cell buckets
-    const int flag = cnt[C_FLAG];
     if (blockIdx.x == 0 && threadIdx.x == 0) *cross = sv.do_prune ? 0ull : ~0ull;  // everybody read it before the first barrier; P5 rebuilds it
     int h_base, Hn;
     block_sums_reduce<NT>(sums_y, h_base, Hn);
     for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) {
-        finalize_item(n, vert, out, sig, a.bmask, flag, V, k);
+        if constexpr (!kCurve) finalize_item(n, vert, out, sig, a.bmask, flag, V, k);
         a.cand[Hn + k] = V + k;
     }
     const int h_end = scan_write_from<NT>(V, hc, ListEmit{a.cand}, h_base);  // ends in a CTA barrier
@@ -1601,7 +1648,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
         if (blockIdx.x == 0 && threadIdx.x == 0) {
             cnt[C_V] = Vn;
             cnt[C_E] = (int)En;
-            a.bytes[0] += 2ull * 16 * E + 2ull * 4 * V + (unsigned long long)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * R + 8 + 16) +
+            a.bytes[0] += 2ull * 16 * E + 2ull * 4 * V + (unsigned long long)S_raw * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * R + 8 + 16) +
                           (unsigned long long)n_cand * (24 + 8 + 4 + 24);
             a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8;
         }
@@ -1625,7 +1672,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
         cnt[C_E] = kept;
         cnt[C_EPAR] = pe ^ 1;
         cnt[C_APAR] = pa ^ 1;
-        a.bytes[0] += 2ull * 16 * E + 2ull * 4 * V + (unsigned long long)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * R + 8 + 16) +
+        a.bytes[0] += 2ull * 16 * E + 2ull * 4 * V + (unsigned long long)S_raw * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * R + 8 + 16) +
                       (unsigned long long)n_cand * (24 + 8 + 4 + 24);
         a.bytes[1] += (unsigned long long)n_cand * 28 + (unsigned long long)P * 8 + (unsigned long long)En * (8 + 2 * 48) +
                       (unsigned long long)Vn * 8;
@@ -1642,13 +1689,13 @@ struct StepList {
     unsigned char idx[kMaxStepList];  // output column of the hyperplane
     unsigned char prune[kMaxStepList];
 };
-template <class C, int NT, class Sync>
+template <class C, int NT, bool kCurve, class Sync>
 __device__ __forceinline__ void steps_loop(const NetMeta &n, const StepArgs &a, const StepList &list, Sync sync)
 {
     if (a.cnt[C_STICKY]) return;  // an earlier launch failed (nobody writes this word before the first barrier)
     for (int i = 0; i < list.n; ++i) {
         const StepVar sv = step_var(list.idx[i], a.R, list.prune[i], list.stamp0 + (uint32_t)i);
-        const int r = step_fused<C, NT>(n, a, sv, i & 1, sync);
+        const int r = step_fused<C, NT, kCurve>(n, a, sv, i & 1, sync);
         if (r == 1) return;
         if (r == 0) sync();  // the next step reads the sizes and buffer parities this one published
     }
@@ -1658,7 +1705,14 @@ template <class C>
 __global__ void __launch_bounds__(kScanThreads, 1) k_steps_grid(const __grid_constant__ NetMeta n, const __grid_constant__ StepArgs a,
                                                                 const __grid_constant__ StepList list)
 {
-    steps_loop<C, kScanThreads>(n, a, list, GridSync{cg::this_grid()});
+    steps_loop<C, kScanThreads, false>(n, a, list, GridSync{cg::this_grid()});
+}
+// ... the curve-approximation path (force=False) the same way
+template <class C>
+__global__ void __launch_bounds__(kScanThreads, 1) k_steps_grid_curve(const __grid_constant__ NetMeta n, const __grid_constant__ StepArgs a,
+                                                                      const __grid_constant__ StepList list)
+{
+    steps_loop<C, kScanThreads, true>(n, a, list, GridSync{cg::this_grid()});
 }
 // ... by two CTAs per SM (<= 128 registers): twice the threads in flight for a complex whose phases are
 // throughput bound, at the price of a slightly dearer barrier
@@ -1666,7 +1720,7 @@ template <class C>
 __global__ void __launch_bounds__(kScanThreads, 2) k_steps_grid2(const __grid_constant__ NetMeta n, const __grid_constant__ StepArgs a,
                                                                  const __grid_constant__ StepList list)
 {
-    steps_loop<C, kScanThreads>(n, a, list, GridSync{cg::this_grid()});
+    steps_loop<C, kScanThreads, false>(n, a, list, GridSync{cg::this_grid()});
 }
 // ... by ONE thread-block cluster of 16 CTAs: a barrier costs a tenth, but 16 SMs do the work of
 // 148.  Slower for one object; it leaves 132 SMs to other objects' clusters.
@@ -1674,7 +1728,7 @@ template <class C>
 __global__ void __launch_bounds__(kClusterThreads, 1) k_steps_cluster(const __grid_constant__ NetMeta n, const __grid_constant__ StepArgs a,
                                                                       const __grid_constant__ StepList list)
 {
-    steps_loop<C, kClusterThreads>(n, a, list, ClusterSync{});
+    steps_loop<C, kClusterThreads, false>(n, a, list, ClusterSync{});
 }
 
 // co-resident grid size of a cooperative kernel: blocks/SM x SMs, capped by the scan tables
@@ -1719,6 +1773,14 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
     if (c->h_counters[C_STICKY] & kStickyCapacity) {
         set_error("work buffers too small for this complex (capacity factor " + std::to_string(g_capacity_factor) + ")");
         return TNB_ERR_CAPACITY;
+    }
+    if (c->h_counters[C_STICKY] & kStickyNoPlane) {
+        set_error("curve path: a non-axis-aligned edge lies on no earlier plane (the reference exits here, subpoly.py:140-148)");
+        return TNB_ERR_INVALID;
+    }
+    if (c->h_counters[C_STICKY] & kStickyGradientDescent) {
+        set_error("curve path: an intersection needs the gradient-descent repair of subpoly_debug.py:121-165, which is not built");
+        return TNB_ERR_UNSUPPORTED;
     }
     if (c->h_counters[C_STICKY] & kStickyHaloPayload) {
         set_error("slab exchange: a shared plane holds more vertices than the mailbox payload");
@@ -1878,6 +1940,7 @@ static int cluster_ctas(K kernel)
     }
     return 0;
 }
+static bool g_fused_curve = std::getenv("TNB_NO_FUSED_CURVE") == nullptr;  // A/B switch: curve path step by step
 static int64_t g_cluster_max_items = std::getenv("TNB_CLUSTER_MAX_ITEMS") ? std::atoll(std::getenv("TNB_CLUSTER_MAX_ITEMS")) : 0;
 
 // How can the hyperplanes of this complex run?  0 = one step at a time (multi-launch kernels with
@@ -1886,23 +1949,27 @@ static int64_t g_cluster_max_items = std::getenv("TNB_CLUSTER_MAX_ITEMS") ? std:
 int steps_mode(const tnb_net *net, const tnb_complex *c, bool planar)
 {
     (void)net;
-    if (!planar || c->halo.enabled || !g_fused_steps || c->E <= 0) return 0;
+    if (c->halo.enabled || !g_fused_steps || c->E <= 0) return 0;
+    if (!planar && !g_fused_curve) return 0;
     const int64_t items = c->E + c->V;  // may be stale upper bounds: good enough for this choice
-    if (g_cluster_max_items > 0 && items <= g_cluster_max_items) return 2;
+    if (planar && g_cluster_max_items > 0 && items <= g_cluster_max_items) return 2;
     return items <= kFusedMaxItems ? 1 : 0;
 }
 
 // lh[2*i], lh[2*i+1] = (layer, neuron) of step i, as tnb_subpoly_step takes them.  One launch; the
 // host does not wait: sizes, buffer parity, capacity and error bits stay in the counter block.
 // TNB_ERR_UNSUPPORTED = this device / step list cannot run that way (the caller goes step by step).
-int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh, int n_steps, float eps, int mode, cudaStream_t s)
+int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh, int n_steps, float eps, int mode, bool planar, cudaStream_t s)
 {
+    if (!planar && mode != 1) return TNB_ERR_UNSUPPORTED;
     const NetMeta &m = net->meta;
     const int H = m.H, R = m.R;
     if (n_steps <= 0) return TNB_OK;
     if (n_steps > kMaxStepList || R > 256) return TNB_ERR_UNSUPPORTED;
-    static int cs_ref = -1, cs_any = -1, gb_ref = -1, gb_any = -1, g2_ref = -1, g2_any = -1;
+    static int cs_ref = -1, cs_any = -1, gb_ref = -1, gb_any = -1, g2_ref = -1, g2_any = -1, gc_ref = -1, gc_any = -1;
     if (cs_ref < 0) {
+        gc_ref = coop_blocks(k_steps_grid_curve<CfgRef>);
+        gc_any = coop_blocks(k_steps_grid_curve<CfgAny>);
         cs_ref = cluster_ctas(k_steps_cluster<CfgRef>);
         cs_any = cluster_ctas(k_steps_cluster<CfgAny>);
         gb_ref = coop_blocks(k_steps_grid<CfgRef>);
@@ -1911,11 +1978,12 @@ int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh,
         g2_any = coop_blocks(k_steps_grid2<CfgAny>);
     }
     static const int64_t wide_from = std::getenv("TNB_WIDE_FROM_ITEMS") ? std::atoll(std::getenv("TNB_WIDE_FROM_ITEMS")) : 150000;  // medium model: steps 0.68 -> 0.58 ms with two CTAs per SM
-    const bool wide = mode == 1 && c->E + c->V > wide_from && (net->fixed_cfg ? g2_ref : g2_any) >= 2 * kSMs;
+    const bool wide = planar && mode == 1 && c->E + c->V > wide_from && (net->fixed_cfg ? g2_ref : g2_any) >= 2 * kSMs;
     static const int env_blocks = std::getenv("TNB_STEP_BLOCKS") ? std::atoi(std::getenv("TNB_STEP_BLOCKS")) : 0;  // tuning knob
     // one CTA per SM keeps the grid barrier cheap
     const int blocks = mode == 2 ? (net->fixed_cfg ? cs_ref : cs_any)
                        : wide    ? 2 * kSMs
+                       : !planar ? std::min(env_blocks > 0 ? env_blocks : kSMs, net->fixed_cfg ? gc_ref : gc_any)
                                  : std::min(env_blocks > 0 ? env_blocks : kSMs, net->fixed_cfg ? gb_ref : gb_any);
     if (blocks <= 0 || blocks > kScanMaxBlocks) return TNB_ERR_UNSUPPORTED;
     StepList list;
@@ -1954,7 +2022,8 @@ int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh,
         else TNB_CUDA(cudaLaunchKernelEx(&cfg, k_steps_cluster<CfgAny>, m, sa, list));
     } else {
         void *params[] = {(void *)&m, (void *)&sa, (void *)&list};
-        const void *kern = wide ? (net->fixed_cfg ? (const void *)k_steps_grid2<CfgRef> : (const void *)k_steps_grid2<CfgAny>)
+        const void *kern = !planar ? (net->fixed_cfg ? (const void *)k_steps_grid_curve<CfgRef> : (const void *)k_steps_grid_curve<CfgAny>)
+                           : wide  ? (net->fixed_cfg ? (const void *)k_steps_grid2<CfgRef> : (const void *)k_steps_grid2<CfgAny>)
                                 : (net->fixed_cfg ? (const void *)k_steps_grid<CfgRef> : (const void *)k_steps_grid<CfgAny>);
         TNB_CUDA(cudaLaunchCooperativeKernel(kern, dim3(blocks), dim3(kScanThreads), params, 0, s));
     }
@@ -2002,7 +2071,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         const int mode = steps_mode(net, c, planar);
         if (mode) {
             const int32_t one[2] = {l, h};
-            rc = steps_persistent_impl(net, c, one, 1, eps, mode, s);
+            rc = steps_persistent_impl(net, c, one, 1, eps, mode, planar, s);
             if (rc != TNB_ERR_UNSUPPORTED) return rc;
         }
     }
@@ -2492,7 +2561,7 @@ int tnb_subpoly_steps(const tnb_net *net, tnb_complex *c, const int32_t *lh, int
         // as soon as the complex is small enough, everything that is left runs as ONE persistent launch
         const int mode = steps_mode(net, c, force != 0);
         if (mode) {
-            const int rc = steps_persistent_impl(net, c, lh + 2 * i, n_steps - i, eps, mode, s);
+            const int rc = steps_persistent_impl(net, c, lh + 2 * i, n_steps - i, eps, mode, force != 0, s);
             if (rc != TNB_ERR_UNSUPPORTED) return rc;
         }
         const int rc = step_impl(net, c, lh[2 * i], lh[2 * i + 1], eps, force != 0, s);

@@ -186,6 +186,55 @@ __device__ __forceinline__ int scan_write_from(int64_t n, Count count, Emit emit
     return running;
 }
 
+// The same two passes over a range [begin, end) the CTA owns for another reason than scan_slice
+// (e.g. the items it emitted itself in an earlier phase: ranges of consecutive CTAs are consecutive).
+template <int NT, class Count>
+__device__ __forceinline__ void scan_count_range(int64_t begin, int64_t end, Count count, int *block_sums)
+{
+    constexpr int NW = NT / 32;
+    int acc = 0;
+    for (int64_t i = begin + threadIdx.x; i < end; i += NT) acc += count(i);
+    acc = warp_sum(acc);
+    __shared__ int s[NW];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        int t = (int)threadIdx.x < NW ? s[threadIdx.x] : 0;
+        t = warp_sum(t);
+        if (threadIdx.x == 0) block_sums[blockIdx.x] = t;
+    }
+    __syncthreads();
+}
+template <int NT, class Count, class Emit>
+__device__ __forceinline__ int scan_write_range(int64_t begin, int64_t end, Count count, Emit emit, int base)
+{
+    constexpr int NW = NT / 32;
+    __shared__ int s_warp[NW];
+    __shared__ int s_excl[32];
+    __shared__ int s_tile;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int running = base;
+    for (int64_t tile = begin; tile < end; tile += NT) {
+        const int64_t i = tile + threadIdx.x;
+        const int c = (i < end) ? count(i) : 0;
+        const int incl = warp_inclusive_scan(c);
+        __syncthreads();  // s_warp / s_excl reuse
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const int t = lane < NW ? s_warp[lane] : 0;
+            const int ti = warp_inclusive_scan(t);
+            s_excl[lane] = ti - t;
+            if (lane == 31) s_tile = ti;
+        }
+        __syncthreads();
+        if (c) emit(i, running + s_excl[warp] + incl - c, c);
+        running += s_tile;
+    }
+    __syncthreads();
+    return running;
+}
+
 template <class Count>
 __device__ __forceinline__ void scan_count_body(int64_t n, Count count, int *block_sums)
 {
