@@ -206,6 +206,36 @@ int tnb_mesh_read_tags(const tnb_mesh *m, uint8_t *d_tags, void *stream);
  * from the other side can differ. */
 int64_t tnb_mesh_near_plane(const tnb_mesh *m);
 
+/* ---- hash-grid encoding under autograd (the training loop) -------------------------
+ * What the reference gets from tiny-cuda-nn through tcnn.Encoding when autograd is on
+ * (tropical.py:32-47; stanford/train.py:180-201: L1 + eikonal loss, i.e. the input gradient is
+ * differentiated once more).  d_table is the CALLER's parameter storage (`enc.module.params`,
+ * [sum(level sizes) * 2] floats on the device); gradients w.r.t. the table are ACCUMULATED
+ * into d_dtable (same layout; zero it first when that is wanted).  d_x [n,3] grid coordinates. */
+typedef struct tnb_grid_desc {
+    int32_t n_levels;         /* L                  */
+    int32_t log2_hashmap;     /* T                  */
+    int32_t base_resolution;  /* N_min              */
+    double per_level_scale;   /* b (tropical.py:31) */
+} tnb_grid_desc;
+/* floats in the table of this layout (-1: bad description) */
+int64_t tnb_grid_train_table_len(const tnb_grid_desc *desc);
+/* d_enc [n, 2L] = encoding(x) */
+int tnb_grid_train_forward(const tnb_grid_desc *desc, const float *d_table, const float *d_x,
+                           int64_t n, float *d_enc, void *stream);
+/* given d_denc = dLoss/d enc [n,2L]: d_dtable += dLoss/d table, d_dx [n,3] = dLoss/d x
+ * (either may be NULL) */
+int tnb_grid_train_backward(const tnb_grid_desc *desc, const float *d_table, const float *d_x,
+                            int64_t n, const float *d_denc, float *d_dtable, float *d_dx,
+                            void *stream);
+/* backward of the map (table, x, denc) -> dx above, given d_ddx = dLoss/d(dx) [n,3]:
+ * d_dtable += dLoss/d table, d_ddenc [n,2L] = dLoss/d denc, d_dx2 [n,3] = dLoss/d x
+ * (any may be NULL) */
+int tnb_grid_train_backward_backward(const tnb_grid_desc *desc, const float *d_table,
+                                     const float *d_x, int64_t n, const float *d_denc,
+                                     const float *d_ddx, float *d_dtable, float *d_ddenc,
+                                     float *d_dx2, void *stream);
+
 /* ---- knobs / introspection ------------------------------------------------------ */
 /* work-buffer growth factor for the complex (default 4.0) */
 int tnb_set_capacity_factor(double f);

@@ -6,6 +6,7 @@ for p in (ROOT, os.path.join(ROOT, "tropical-nerf.pytorch_b200"), HERE):
     sys.path.insert(0, p)
 import bench
 name = sys.argv[1] if len(sys.argv) > 1 else "large_sphere"
+force = not (len(sys.argv) > 2 and sys.argv[2] == "curve")  # second argument "curve": force=False
 w = bench.load_workload(name)
 net = bench.make_native(w)
 def ev(): return torch.cuda.Event(enable_timing=True)
@@ -14,7 +15,7 @@ for rep in range(4):
     t0 = time.perf_counter()
     e[0].record(); c = net.skeleton(128); e[1].record()
     lh = [(l, h) for l in range(net.num_layers - 1) for h in range(net.num_hidden)] + [(net.num_layers - 2, net.num_hidden)]
-    c.steps(lh); e[2].record()
+    c.steps(lh, force=force); e[2].record()
     m = c.extract_mesh(); e[3].record()
     torch.cuda.synchronize()
     t1 = time.perf_counter()
@@ -24,5 +25,5 @@ c = net.skeleton(128)
 print("skeleton V,E", c.num_vertices, c.num_edges)
 for l in range(net.num_layers - 1):
     for h in range(net.num_hidden):
-        a = ev(); b = ev(); a.record(); c.step(l, h); b.record(); torch.cuda.synchronize()
+        a = ev(); b = ev(); a.record(); c.step(l, h, force=force); b.record(); torch.cuda.synchronize()
         print("step", l, h, "%.3f ms" % a.elapsed_time(b), c.num_vertices, c.num_edges)

@@ -618,59 +618,63 @@ __global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant
 // Pass 1: candidate new vertex of every crossed edge into TEMP slots (the idle half of the
 // ping-pong vertex arrays), no rewiring yet.  sflag bit0 = edge is not axis aligned (c),
 // bit1 = no admissible intersection (gg).
+// Warp-cooperative (curve.cuh): every lane of the warp calls it, `active` says whether the lane has
+// a crossed edge k of its own.
 template <class C>
-__device__ __forceinline__ int curve_candidate_item(const NetMeta &n, int idx, float eps, int k, const int *split_list,
+__device__ __forceinline__ int curve_candidate_item(const NetMeta &n, int idx, float eps, bool active, int k, const int *split_list,
                                                     const int2 *edges, const float *vert, const float *out,
                                                     const uint64_t *sig, float *tvert, float *tout, uint64_t *bmask,
                                                     int *sflag, int *cnt)
 {
     const int R = n.R;
-    int any = 0;
-    {
+    float e0[3] = {0.0f, 0.0f, 0.0f}, e1[3] = {0.0f, 0.0f, 0.0f}, x[3] = {0.0f, 0.0f, 0.0f};
+    uint64_t common = 0;
+    int flags = 0, plane = 0;
+    bool curved = false;
+    if (active) {
         const int e = split_list[k];
         const int2 ed = edges[e];
-        float e0[3], e1[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) { e0[d] = vert[3 * (int64_t)ed.x + d]; e1[d] = vert[3 * (int64_t)ed.y + d]; }
         const float d0 = __fdiv_rn(out[(int64_t)ed.x * R + idx], eps), d1 = __fdiv_rn(out[(int64_t)ed.y * R + idx], eps);
         const float w = __fdiv_rn(fabsf(d0), fabsf(d1 - d0));
         const float omw = 1.0f - w;
-        float x[3];
 #pragma unroll
         for (int d = 0; d < 3; ++d) x[d] = e0[d] * omw + e1[d] * w;
         const uint64_t za = ~(sig[3 * (int64_t)ed.x] | sig[3 * (int64_t)ed.x + 1]);
         const uint64_t zb = ~(sig[3 * (int64_t)ed.y] | sig[3 * (int64_t)ed.y + 1]);
-        const uint64_t common = za & zb & ((1ull << idx) - 1ull);
-        int flags = 0;
+        common = za & zb & ((1ull << idx) - 1ull);
         int moved = 0;
 #pragma unroll
         for (int d = 0; d < 3; ++d) moved += fabsf(e1[d] - e0[d]) > eps ? 1 : 0;
         if (moved > 1) {  // bi-/tri-linear edge (subpoly.py:122)
             flags = 1;
-            if (!common) {
-                atomicOr(cnt + C_ERR, kErrNoPlane);  // the reference exits here (subpoly.py:140-148)
+            if (!common) atomicOr(cnt + C_ERR, kErrNoPlane);  // the reference exits here (subpoly.py:140-148)
+            else { curved = true; plane = 63 - __clzll((long long)common); }  // nonzero_last
+        }
+    }
+    float p8[8], q8[8], ints[3] = {0.0f, 0.0f, 0.0f};
+    warp_group8_columns<C>(n, curved, e0, e1, n.eps, plane, idx, p8, q8);
+    warp_curve_intersection(curved, p8, q8, ints);
+    int any = 0;
+    if (active) {
+        if (curved) {
+            bool gg = false;
+#pragma unroll
+            for (int d = 0; d < 3; ++d) gg = gg || ints[d] < 0.0f || ints[d] > 1.0f;
+            if (gg) {
+                flags |= 2;
             } else {
-                const int plane = 63 - __clzll((long long)common);  // nonzero_last
-                float p8[8], q8[8], ints[3];
-                group8_columns<C>(n, e0, e1, n.eps, plane, idx, p8, q8);
-                curve_intersection(p8, q8, ints);
-                bool gg = false;
+                float xg[3];
 #pragma unroll
-                for (int d = 0; d < 3; ++d) gg = gg || ints[d] < 0.0f || ints[d] > 1.0f;
-                if (gg) {
-                    flags |= 2;
-                } else {
-                    float xg[3];
-#pragma unroll
-                    for (int d = 0; d < 3; ++d) xg[d] = e0[d] * (1.0f - ints[d]) + e1[d] * ints[d];
-                    float *row = tout + (int64_t)k * R;
-                    outputs_row<C>(n, xg, row);
-                    if (fabsf(row[plane]) > eps || fabsf(row[idx]) > eps)
-                        atomicOr(cnt + C_ERR, kErrGradientDescent);  // subpoly_debug.py:121-165 not built
-                }
-#pragma unroll
-                for (int d = 0; d < 3; ++d) x[d] = e0[d] + ints[d] * (e1[d] - e0[d]);  // subpoly.py:183
+                for (int d = 0; d < 3; ++d) xg[d] = e0[d] * (1.0f - ints[d]) + e1[d] * ints[d];
+                float *row = tout + (int64_t)k * R;
+                outputs_row<C>(n, xg, row);
+                if (fabsf(row[plane]) > eps || fabsf(row[idx]) > eps)
+                    atomicOr(cnt + C_ERR, kErrGradientDescent);  // subpoly_debug.py:121-165 not built
             }
+#pragma unroll
+            for (int d = 0; d < 3; ++d) x[d] = e0[d] + ints[d] * (e1[d] - e0[d]);  // subpoly.py:183
         }
 #pragma unroll
         for (int d = 0; d < 3; ++d) tvert[3 * (int64_t)k + d] = x[d];
@@ -702,8 +706,9 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices_curve(const __grid_co
         return;
     }
     int any = 0;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x)
-        any |= curve_candidate_item<C>(n, idx, eps, k, split_list, edges, vert, out, sig, tvert, tout, bmask, sflag, cnt);
+    const int lane = threadIdx.x & 31;
+    for (int k0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); k0 < S; k0 += gridDim.x * blockDim.x)  // warp-uniform trip count
+        any |= curve_candidate_item<C>(n, idx, eps, k0 + lane < S, k0 + lane, split_list, edges, vert, out, sig, tvert, tout, bmask, sflag, cnt);
     if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
 }
 
@@ -1562,12 +1567,29 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     int s_end = scan_write_from<NT>(E, sc, ListEmit{a.split_list}, s_base);
     float *tvert = a.vert[pv ^ 1], *tout = a.out[pv ^ 1];  // curve path: temporary rows of the candidates
     int *sflag = a.pcount;                                 // free until P3
+    if constexpr (kCurve) {
+        // The crossed edges cluster in a few CTAs' slices, and a curved candidate is a warp's work, not a
+        // thread's (curve.cuh): once the whole split list is in place the candidates are shared out evenly.
+        // From here on the CTA owns the crossed edges [s_base, s_end) of that share.
+        sync();
+        TNB_PHASE_MARK(9);
+        const int per = (S + nb - 1) / nb;
+        s_base = min(S, (int)blockIdx.x * per);
+        s_end = min(S, s_base + per);
+    }
     {
         int any = 0;
-        for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) {
-            if constexpr (kCurve)
-                any |= curve_candidate_item<C>(n, sv.idx, a.eps, k, a.split_list, edges, vert, out, sig, tvert, tout, a.bmask, sflag, cnt);
-            else
+        if constexpr (kCurve) {
+            // the CTA's j-th candidate goes to warp j % NW, lane (j / NW) % 32: the warps share the curved
+            // edges, which a warp works through one after the other (curve.cuh)
+            constexpr int NW = NT / 32;
+            const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+            for (int j0 = 0; s_base + j0 < s_end; j0 += NT) {
+                const int k = s_base + j0 + lane * NW + warp;
+                any |= curve_candidate_item<C>(n, sv.idx, a.eps, k < s_end, k, a.split_list, edges, vert, out, sig, tvert, tout, a.bmask, sflag, cnt);
+            }
+        } else {
+            for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT)
                 any |= new_vertex_item<C>(n, sv.idx, a.eps, k, V, E, a.split_list, edges, vert, out, sig, a.bmask, tag);
         }
         if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
@@ -1604,15 +1626,19 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     // P2: failover override + packed signs of the own new vertices; candidate list (hit old vertices,
     // then the new ones); the own candidates go into the cell buckets
     if (blockIdx.x == 0 && threadIdx.x == 0) *cross = sv.do_prune ? 0ull : ~0ull;  // everybody read it before the first barrier; P5 rebuilds it
+    TNB_PHASE_MARK(10);
     int h_base, Hn;
     block_sums_reduce<NT>(sums_y, h_base, Hn);
     for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) {
         if constexpr (!kCurve) finalize_item(n, vert, out, sig, a.bmask, flag, V, k);
         a.cand[Hn + k] = V + k;
     }
+    TNB_PHASE_MARK(11);
     const int h_end = scan_write_from<NT>(V, hc, ListEmit{a.cand}, h_base);  // ends in a CTA barrier
+    TNB_PHASE_MARK(12);
     for (int c = h_base + (int)threadIdx.x; c < h_end; c += NT) bucket_insert_item(c, a.cand[c], sig, a.head, a.next, a.dim, sv.stamp);
     for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) bucket_insert_item(Hn + k, V + k, sig, a.head, a.next, a.dim, sv.stamp);
+    TNB_PHASE_MARK(13);
     const int Vn = V + S, n_cand = Hn + S;
     if (sv.do_prune) {  // P6 marks the vertices that keep an edge in the idle half of the liveness array
         for (int v = blockIdx.x * NT + threadIdx.x; v < Vn; v += nb * NT) used[v] = 0;

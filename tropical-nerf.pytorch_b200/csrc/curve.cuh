@@ -7,141 +7,253 @@
 
 namespace tnb {
 
+// All helpers here are WARP-COOPERATIVE: every lane of the warp calls them (full mask), each
+// lane brings its own candidate edge (or none), and the warp works through the candidates that
+// need the curve treatment together.  A candidate costs one network evaluation and at most 32
+// rounds of polynomial samples in lock-step instead of 8 evaluations and 1024 dependent samples
+// in one thread, which is what a persistent step kernel with a few candidates per CTA needs.
+// Per corner / per sample the operations and their order are those of oracle/trinet_ref.c, so
+// the results are bit-identical to the one-thread formulation.
+constexpr unsigned kFullWarp = 0xffffffffu;
+
+__device__ __forceinline__ double shfl_double(double v, int src)
+{
+    int lo = __double2loint(v), hi = __double2hiint(v);
+    lo = __shfl_sync(kFullWarp, lo, src);
+    hi = __shfl_sync(kFullWarp, hi, src);
+    return __hiloint2double(hi, lo);
+}
+
 // Values of output columns colA and colB at the 8 corners of the box spanned by edge (e0,e1)
 // (corner index 4*iz + 2*iy + ix, coordinate from endpoint 0 or 1 per axis, geometry.py:350-372),
 // evaluated "within a common linear space": a hidden neuron stays linear iff it is > eps at the
 // first or the last corner, else it is multiplied by 0.
+// Four candidates at a time, 8 lanes (one corner each) per candidate.
 template <class C>
-__device__ void group8_columns(const NetMeta &n, const float e0[3], const float e1[3], float eps, int colA,
-                               int colB, float pA[8], float pB[8])
+__device__ void warp_group8_columns(const NetMeta &n, bool need, const float e0[3], const float e1[3], float eps, int colA,
+                                    int colB, float pA[8], float pB[8])
 {
-    float act[8][C::kMaxW], pre[8][C::kMaxH];
+    const int lane = threadIdx.x & 31, grp = lane >> 3, corner = lane & 7;
     const int L = C::L(n), H = C::H(n), NL = C::NLIN(n), R = n.R;
-    for (int k = 0; k < 8; ++k) {
-        const float x[3] = {(k & 1) ? e1[0] : e0[0], (k & 2) ? e1[1] : e0[1], (k & 4) ? e1[2] : e0[2]};
+    unsigned todo = __ballot_sync(kFullWarp, need);
+    while (todo) {
+        // the grp-th pending candidate is this lane group's job (-1: none left for the group)
+        int src = -1;
+        {
+            unsigned t = todo;
+            for (int g = 0; g < 4; ++g) {
+                const int s = t ? __ffs(t) - 1 : -1;
+                if (g == grp) src = s;
+                if (t) t &= t - 1;
+            }
+            todo = t;
+        }
+        const int from = src < 0 ? lane : src;
+        float x[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) {
+            const float a = __shfl_sync(kFullWarp, e0[d], from), b = __shfl_sync(kFullWarp, e1[d], from);
+            x[d] = ((corner >> d) & 1) ? b : a;
+        }
+        const int cA = __shfl_sync(kFullWarp, colA, from), cB = __shfl_sync(kFullWarp, colB, from);
+        float act[C::kMaxW], pre[C::kMaxH];
+        float myA = 0.0f, myB = 0.0f;
         float xp[3];
         preprocess(n, x, xp);
         for (int l = 0; l < L; ++l) {
             uint32_t cell[3];
             float frac[3];
             const float2 f = encode_level(n, l, xp, cell, frac);
-            act[k][2 * l] = f.x;
-            act[k][2 * l + 1] = f.y;
+            act[2 * l] = f.x;
+            act[2 * l + 1] = f.y;
         }
-    }
-    int base = 0;
-    for (int i = 0; i < NL; ++i) {
-        const int ni = C::nin(n, i), no = C::nout(n, i);
-        for (int k = 0; k < 8; ++k)
-            for (int j = 0; j < no; ++j) {
-                float acc = C::w(n, base + no * ni + j);
-                for (int c = 0; c < ni; ++c) acc = __fmaf_rn(act[k][c], C::w(n, base + j * ni + c), acc);
-                pre[k][j] = acc;
+        int base = 0;
+        for (int i = 0; i < NL; ++i) {
+            const int ni = C::nin(n, i), no = C::nout(n, i);
+#pragma unroll(C::kUnroll)
+            for (int j = 0; j < C::kMaxH; ++j) {
+                if (j < no) {
+                    float acc = C::w(n, base + no * ni + j);
+#pragma unroll(C::kUnroll)
+                    for (int c = 0; c < C::kMaxW; ++c)
+                        if (c < ni) acc = __fmaf_rn(act[c], C::w(n, base + j * ni + c), acc);
+                    pre[j] = acc;
+                }
             }
-        if (i != NL - 1) {
-            for (int j = 0; j < no; ++j) {
-                const int col = i * H + j;
-                if (col == colA)
-                    for (int k = 0; k < 8; ++k) pA[k] = pre[k][j];
-                if (col == colB)
-                    for (int k = 0; k < 8; ++k) pB[k] = pre[k][j];
-                const float m = (pre[0][j] > eps || pre[7][j] > eps) ? 1.0f : 0.0f;
-                for (int k = 0; k < 8; ++k) act[k][j] = pre[k][j] * m;
+            if (i != NL - 1) {
+#pragma unroll(C::kUnroll)
+                for (int j = 0; j < C::kMaxH; ++j) {
+                    if (j < no) {
+                        const int col = i * H + j;
+                        if (col == cA) myA = pre[j];
+                        if (col == cB) myB = pre[j];
+                        const float first = __shfl_sync(kFullWarp, pre[j], grp * 8), last = __shfl_sync(kFullWarp, pre[j], grp * 8 + 7);
+                        const float m = (first > eps || last > eps) ? 1.0f : 0.0f;
+                        act[j] = pre[j] * m;
+                    }
+                }
+            } else {
+                const float v = pre[1] - pre[0];
+                if (cA == R - 1) myA = v;
+                if (cB == R - 1) myB = v;
             }
-        } else {
-            for (int k = 0; k < 8; ++k) {
-                const float v = pre[k][1] - pre[k][0];
-                if (colA == R - 1) pA[k] = v;
-                if (colB == R - 1) pB[k] = v;
-            }
+            base += no * ni + no;
         }
-        base += no * ni + no;
+        // hand the 8 corner values to the lane that owns the candidate
+        int my_grp = -1;
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int s = __shfl_sync(kFullWarp, src, g * 8);
+            if (s == lane) my_grp = g;
+        }
+        const int take = my_grp < 0 ? 0 : my_grp * 8;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const float a = __shfl_sync(kFullWarp, myA, take + k), b = __shfl_sync(kFullWarp, myB, take + k);
+            if (my_grp >= 0) { pA[k] = a; pB[k] = b; }
+        }
     }
 }
 
-__device__ __forceinline__ double poly_eval(const double *c, int deg, double t)
+// c[0] t^4 + ... + c[4] by Horner's rule, one rounded operation at a time.  A polynomial of lower degree
+// is passed with leading zeros: 0 * t + c = c exactly, so the value equals the shorter Horner chain's.
+__device__ __forceinline__ double poly4_eval(const double c[5], double t)
 {
     double v = c[0];
-    for (int i = 1; i <= deg; ++i) v = v * t + c[i];
+#pragma unroll
+    for (int i = 1; i <= 4; ++i) v = v * t + c[i];
     return v;
 }
 
-// smallest real root in [0,1] (the one the reference's eigenvalue filter keeps), or -1
-__device__ double smallest_root01(const double *c, int deg)
+// smallest real root in [0,1] (the one the reference's eigenvalue filter keeps), or -1: first sign
+// change among the samples k/1024 (k = 1..1024), then 60 bisections.  The warp samples 128 consecutive
+// points per round, 4 per lane (independent Horner chains); the first hit of the first round that has
+// one is exactly the sequential scan's hit.  c = the polynomial padded to degree 4 (see poly4_eval),
+// readable on every lane.
+__device__ double warp_smallest_root01(bool need, const double c[5])
 {
-    const int N = 1024;
-    double t0 = 0.0, f0 = poly_eval(c, deg, 0.0);
-    if (f0 == 0.0) return 0.0;
-    for (int k = 1; k <= N; ++k) {
-        const double t1 = (double)k / (double)N, f1 = poly_eval(c, deg, t1);
-        if (f1 == 0.0) return t1;
-        if ((f0 < 0.0) != (f1 < 0.0)) {
-            double lo = t0, hi = t1, flo = f0;
-            for (int it = 0; it < 60; ++it) {
-                const double mid = 0.5 * (lo + hi), fm = poly_eval(c, deg, mid);
-                if (fm == 0.0) return mid;
-                if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else hi = mid;
+    const int lane = threadIdx.x & 31;
+    double result = -1.0;
+    unsigned todo = __ballot_sync(kFullWarp, need);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        double cc[5];
+#pragma unroll
+        for (int i = 0; i < 5; ++i) cc[i] = shfl_double(c[i], src);
+        double r = -1.0;
+        const double f_at_0 = poly4_eval(cc, 0.0);
+        if (f_at_0 == 0.0) {
+            r = 0.0;
+        } else {
+            double carry = f_at_0;  // the sample before this round's first
+            for (int j = 0; j < 8; ++j) {
+                const int k1 = j * 128 + lane * 4 + 1;  // this lane's samples: k1 .. k1+3
+                double f[5];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) f[q + 1] = poly4_eval(cc, (double)(k1 + q) * 0.0009765625);  // k / 1024, exact
+                f[0] = shfl_double(f[4], lane == 0 ? 0 : lane - 1);
+                if (lane == 0) f[0] = carry;
+                int first = -1;  // first of the lane's samples that ends the scan
+#pragma unroll
+                for (int q = 3; q >= 0; --q)
+                    if (f[q + 1] == 0.0 || ((f[q] < 0.0) != (f[q + 1] < 0.0))) first = q;
+                const unsigned hb = __ballot_sync(kFullWarp, first >= 0);
+                if (hb) {
+                    const int hl = __ffs(hb) - 1;
+                    double rr = 0.0;
+                    if (lane == hl) {
+                        double f0 = f[0], f1 = f[1];
+#pragma unroll
+                        for (int q = 1; q < 4; ++q)
+                            if (first == q) { f0 = f[q]; f1 = f[q + 1]; }
+                        const int k = k1 + first;
+                        const double t1 = (double)k * 0.0009765625;
+                        if (f1 == 0.0) {
+                            rr = t1;
+                        } else {
+                            double lo = (double)(k - 1) * 0.0009765625, hi = t1, flo = f0;
+                            for (int it = 0; it < 60; ++it) {
+                                const double mid = 0.5 * (lo + hi), fm = poly4_eval(cc, mid);
+                                if (fm == 0.0) { lo = hi = mid; break; }
+                                if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else hi = mid;
+                            }
+                            rr = 0.5 * (lo + hi);
+                        }
+                    }
+                    r = shfl_double(rr, hl);
+                    break;
+                }
+                carry = shfl_double(f[4], 31);
             }
-            return 0.5 * (lo + hi);
         }
-        t0 = t1;
-        f0 = f1;
+        if (lane == src) result = r;
     }
-    return -1.0;
+    return result;
 }
 
-// p, q: the two planes' values at the 8 corners.  out = (x, y, z) trilinear coordinates.
-__device__ void curve_intersection(const float *p, const float *q, float out[3])
+// p, q: the two planes' values at the 8 corners (valid where need).  out = (x, y, z) trilinear
+// coordinates.  geometry.intersection_of_two_planes (geometry.py:24-138) for one edge per lane.
+__device__ void warp_curve_intersection(bool need, const float *p, const float *q, float out[3])
 {
-    const int T_[3][4] = {{0, 1, 4, 5}, {0, 1, 2, 3}, {0, 4, 2, 6}};
-    const int U_[3][4] = {{2, 3, 6, 7}, {4, 5, 6, 7}, {1, 5, 3, 7}};
-    for (int pl = 0; pl < 3; ++pl) {
-        bool same = true;
-        for (int k = 0; k < 4; ++k) same = same && p[T_[pl][k]] == p[U_[pl][k]] && q[T_[pl][k]] == q[U_[pl][k]];
-        if (same) { out[0] = out[1] = out[2] = -1.0f; return; }  // bilinear cases: geometry.py:108
-    }
     const int r[4] = {0, 1, 4, 5}, s[4] = {2, 3, 6, 7};
-    double a[3], b[3], c[3], d[3];
-    a[0] = q[r[0]]; a[1] = (double)(q[r[1]] + q[r[2]]); a[2] = q[r[3]];
-    b[0] = p[s[0]]; b[1] = (double)(p[s[1]] + p[s[2]]); b[2] = p[s[3]];
-    c[0] = q[s[0]]; c[1] = (double)(q[s[1]] + q[s[2]]); c[2] = q[s[3]];
-    d[0] = p[r[0]]; d[1] = (double)(p[r[1]] + p[r[2]]); d[2] = p[r[3]];
-    double A[3][3], B[3][3], TA[3][3];
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) A[i][j] = a[i] * b[j] - c[i] * d[j];
-    const double T[3][3] = {{1, -2, 1}, {-1, 1, 0}, {1, 0, 0}};
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            double v = 0.0;
-            for (int k = 0; k < 3; ++k) v += T[k][i] * A[k][j];
-            TA[i][j] = v;
+    double co[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    int lead = 0;
+    bool bilinear = false, want_root = false;
+    if (need) {
+        const int T_[3][4] = {{0, 1, 4, 5}, {0, 1, 2, 3}, {0, 4, 2, 6}};
+        const int U_[3][4] = {{2, 3, 6, 7}, {4, 5, 6, 7}, {1, 5, 3, 7}};
+        for (int pl = 0; pl < 3; ++pl) {
+            bool same = true;
+            for (int k = 0; k < 4; ++k) same = same && p[T_[pl][k]] == p[U_[pl][k]] && q[T_[pl][k]] == q[U_[pl][k]];
+            bilinear = bilinear || same;  // bilinear cases: geometry.py:108
         }
-    for (int i = 0; i < 3; ++i)
-        for (int j = 0; j < 3; ++j) {
-            double v = 0.0;
-            for (int k = 0; k < 3; ++k) v += TA[i][k] * T[k][j];
-            B[i][j] = v;
-        }
-    double co[5] = {B[0][0], B[1][0] + B[0][1], B[2][0] + B[1][1] + B[0][2], B[1][2] + B[2][1], B[2][2]};
-    float x = -1.0f;
-    {
-        float cf[5];
-        for (int i = 0; i < 5; ++i) {
-            cf[i] = (float)co[i];
-            if (fabsf(cf[i]) < 1e-9f) { cf[i] = 0.0f; co[i] = 0.0; }
-        }
-        int lead = 0;
-        while (lead < 4 && !(fabsf(cf[lead]) > 1e-9f)) ++lead;
-        if (lead < 4) {
-            float mean = 0.0f;
-            for (int i = lead; i < 5; ++i) mean += fabsf(cf[i]);
-            mean = __fdiv_rn(mean, (float)(5 - lead));
-            if (mean > 1e-9f) {
-                const double rt = smallest_root01(co + lead, 4 - lead);
-                if (rt >= 0.0) x = (float)rt;
+        if (!bilinear) {
+            double a[3], b[3], c[3], d[3];
+            a[0] = q[r[0]]; a[1] = (double)(q[r[1]] + q[r[2]]); a[2] = q[r[3]];
+            b[0] = p[s[0]]; b[1] = (double)(p[s[1]] + p[s[2]]); b[2] = p[s[3]];
+            c[0] = q[s[0]]; c[1] = (double)(q[s[1]] + q[s[2]]); c[2] = q[s[3]];
+            d[0] = p[r[0]]; d[1] = (double)(p[r[1]] + p[r[2]]); d[2] = p[r[3]];
+            double A[3][3], B[3][3], TA[3][3];
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) A[i][j] = a[i] * b[j] - c[i] * d[j];
+            const double T[3][3] = {{1, -2, 1}, {-1, 1, 0}, {1, 0, 0}};
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    double v = 0.0;
+                    for (int k = 0; k < 3; ++k) v += T[k][i] * A[k][j];
+                    TA[i][j] = v;
+                }
+            for (int i = 0; i < 3; ++i)
+                for (int j = 0; j < 3; ++j) {
+                    double v = 0.0;
+                    for (int k = 0; k < 3; ++k) v += TA[i][k] * T[k][j];
+                    B[i][j] = v;
+                }
+            co[0] = B[0][0]; co[1] = B[1][0] + B[0][1]; co[2] = B[2][0] + B[1][1] + B[0][2]; co[3] = B[1][2] + B[2][1]; co[4] = B[2][2];
+            float cf[5];
+            for (int i = 0; i < 5; ++i) {
+                cf[i] = (float)co[i];
+                if (fabsf(cf[i]) < 1e-9f) { cf[i] = 0.0f; co[i] = 0.0; }
+            }
+            while (lead < 4 && !(fabsf(cf[lead]) > 1e-9f)) ++lead;
+            if (lead < 4) {
+                float mean = 0.0f;
+                for (int i = lead; i < 5; ++i) mean += fabsf(cf[i]);
+                mean = __fdiv_rn(mean, (float)(5 - lead));
+                want_root = mean > 1e-9f;
             }
         }
     }
+    // the polynomial the scan sees starts at the leading coefficient: the skipped ones count as zero
+    double cs[5];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) cs[i] = i < lead ? 0.0 : co[i];
+    const double rt = warp_smallest_root01(want_root, cs);
+    if (!need) return;
+    if (bilinear) { out[0] = out[1] = out[2] = -1.0f; return; }
+    float x = -1.0f;
+    if (want_root && rt >= 0.0) x = (float)rt;
     const float w0 = (1.0f - x) * (1.0f - x), w1 = x * (1.0f - x), w3 = x * x;
     const float AX = ((q[r[0]] * w0 + q[r[1]] * w1) + q[r[2]] * w1) + q[r[3]] * w3;
     const float BX = ((q[s[0]] * w0 + q[s[1]] * w1) + q[s[2]] * w1) + q[s[3]] * w3;

@@ -35,6 +35,11 @@ class NetDesc(ctypes.Structure):
                 ("marks", ctypes.c_void_p), ("n_marks", ctypes.c_int32)]
 
 
+class GridDesc(ctypes.Structure):
+    _fields_ = [("n_levels", ctypes.c_int32), ("log2_hashmap", ctypes.c_int32),
+                ("base_resolution", ctypes.c_int32), ("per_level_scale", ctypes.c_double)]
+
+
 _lib = None
 
 _P = ctypes.c_void_p
@@ -93,6 +98,10 @@ SIGNATURES = {
     "tnb_extract_mesh_finish": (ctypes.c_int, [_P, _P, _P, _P]),
     "tnb_mesh_read_tags": (ctypes.c_int, [_P, _P, _P]),
     "tnb_mesh_near_plane": (_I64, [_P]),
+    "tnb_grid_train_table_len": (_I64, [_P]),
+    "tnb_grid_train_forward": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P]),
+    "tnb_grid_train_backward": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P]),
+    "tnb_grid_train_backward_backward": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "tnb_launch_count": (_I64, []),
     "tnb_launch_count_reset": (None, []),
     "tnb_profile_enable": (ctypes.c_int, [ctypes.c_int]),

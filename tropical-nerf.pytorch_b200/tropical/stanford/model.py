@@ -14,7 +14,8 @@ class Net(nn.Module):
     and methods as the reference.  Under torch.no_grad() (the extraction path, which is
     @torch.no_grad in the reference too) forward/sdf/region/normal run in the fused sm_100a
     kernels and input gradients are computed analytically on the device; with autograd enabled
-    (the training loop) forward/sdf are ordinary differentiable torch."""
+    (the training loop) the encoding runs in the sm_100a training kernels (twice differentiable) and
+    the three nn.Linear layers in torch."""
 
     def __init__(self, num_layers: int = 3, num_hidden: int = 16, levels: int = 4,
                  r_min: int = 2, r_max: int = 32, T: int = 19, eps: float = 1e-4):
@@ -64,9 +65,9 @@ class Net(nn.Module):
         return out
 
     def _forward_autograd(self, x, gather=False):
-        """model.py:52-76 in differentiable torch ops (training)."""
+        """model.py:52-76 under autograd (training): device encoding kernels + nn.Linear."""
         inputs = []
-        h = self.enc.module.forward_autograd(self.preprocess(x)).float()
+        h = self.enc.module.forward_train(self.preprocess(x))
         last = len(self.fc) - 1
         for i, fc in enumerate(self.fc):
             h = fc(h)

@@ -4,6 +4,7 @@
 forward runs the fused sm_100a gather kernel (`tnb_grid_encode`).  Parameter names match
 the reference (`enc.module.params`), so its released state_dicts load unchanged.
 """
+import ctypes
 from typing import Any, Tuple
 
 import numpy as np
@@ -16,16 +17,84 @@ from . import _native
 __all__ = ["HashEncoding", "TropicalHashGrid", "Tropical", "low_precision"]
 
 
+class _GridEncode(torch.autograd.Function):
+    """enc = encoding(x; table) on the device (`tnb_grid_train_forward`), differentiable twice:
+    its backward is itself an autograd Function, because the reference's training loss
+    differentiates d sdf / d x once more (eikonal term, stanford/train.py:194-197)."""
+
+    @staticmethod
+    def forward(ctx, x, params, desc):
+        xc = x.detach().contiguous().float()
+        n = xc.shape[0]
+        enc = torch.empty(n, 2 * desc.n_levels, device=xc.device, dtype=torch.float32)
+        with torch.cuda.device(xc.device):
+            _native.check(_native.lib().tnb_grid_train_forward(
+                ctypes.byref(desc), _native._ptr(params.detach()), _native._ptr(xc), n, _native._ptr(enc), _native._stream()))
+        ctx.save_for_backward(x, params)  # the inputs themselves: the backward is differentiable w.r.t. both
+        ctx.desc = desc
+        return enc
+
+    @staticmethod
+    def backward(ctx, denc):
+        x, params = ctx.saved_tensors
+        dx, dparams = _GridEncodeBackward.apply(denc, x, params, ctx.desc, ctx.needs_input_grad[0], ctx.needs_input_grad[1])
+        return dx, dparams, None
+
+
+class _GridEncodeBackward(torch.autograd.Function):
+    """(denc, x, table) -> (dLoss/dx, dLoss/dtable) (`tnb_grid_train_backward`); its own backward
+    (`tnb_grid_train_backward_backward`) differentiates the dx output w.r.t. denc, x and the table.
+    The table-gradient output is first order only."""
+
+    @staticmethod
+    def forward(ctx, denc, x, params, desc, want_dx, want_dparams):
+        dc = denc.detach().contiguous().float()
+        xc = x.detach().contiguous().float()
+        n = xc.shape[0]
+        dx = torch.empty(n, 3, device=xc.device, dtype=torch.float32) if want_dx else None
+        dparams = torch.zeros_like(params) if want_dparams else None
+        with torch.cuda.device(xc.device):
+            _native.check(_native.lib().tnb_grid_train_backward(
+                ctypes.byref(desc), _native._ptr(params.detach()), _native._ptr(xc), n, _native._ptr(dc),
+                _native._ptr(dparams), _native._ptr(dx), _native._stream()))
+        ctx.save_for_backward(denc, x, params)
+        ctx.desc = desc
+        ctx.set_materialize_grads(False)
+        return dx, dparams
+
+    @staticmethod
+    def backward(ctx, ddx, ddparams):
+        if ddparams is not None:
+            raise _native.NativeError("the table gradient of the hash-grid encoding is first order only")
+        if ddx is None:
+            return None, None, None, None, None, None
+        denc, x, params = ctx.saved_tensors
+        denc, x = denc.detach().contiguous().float(), x.detach().contiguous().float()
+        n = x.shape[0]
+        need = ctx.needs_input_grad
+        ddx = ddx.detach().contiguous().float()
+        g_denc = torch.empty_like(denc) if need[0] else None
+        g_x = torch.empty(n, 3, device=x.device, dtype=torch.float32) if need[1] else None
+        g_params = torch.zeros_like(params) if need[2] else None
+        with torch.cuda.device(x.device):
+            _native.check(_native.lib().tnb_grid_train_backward_backward(
+                ctypes.byref(ctx.desc), _native._ptr(params.detach()), _native._ptr(x), n, _native._ptr(denc), _native._ptr(ddx),
+                _native._ptr(g_params), _native._ptr(g_denc), _native._ptr(g_x), _native._stream()))
+        return g_denc, g_x, g_params, None, None, None
+
+
 class HashEncoding(Module):
     """Multiresolution hash encoding with tiny-cuda-nn's parameter layout
     (`tcnn.Encoding(D, {"otype": "Grid", "type": "Hash", ...}, dtype=torch.float)`,
     tropical.py:32-40).
 
-    Two evaluation routes.  Under `torch.no_grad()` (the whole extraction path) the fused
-    sm_100a kernel runs (`tnb_grid_encode`).  When autograd needs the result (the training loop
-    of stanford/train.py, including its double-backward eikonal term) the same interpolation is
-    expressed in differentiable torch ops on whatever device the parameters live on; training
-    is not on the extraction hot path."""
+    Under `torch.no_grad()` (the whole extraction path) the fused sm_100a kernel runs
+    (`tnb_grid_encode`).  When autograd needs the result (the training loop of stanford/train.py,
+    including its double-backward eikonal term) the sm_100a training kernels run
+    (`tnb_grid_train_forward/_backward/_backward_backward`, csrc/grid_train.cu) straight on the
+    parameter storage; there is no CPU route: parameters that are not on a CUDA device raise.
+    `forward_autograd` is the same interpolation in plain torch ops: the restatement the kernels
+    are tested against (and what bench.py's workload generator mirrors), not a product path."""
 
     def __init__(self, n_input_dims, n_levels, n_features_per_level, log2_hashmap_size,
                  base_resolution, per_level_scale, seed=1337):
@@ -86,9 +155,19 @@ class HashEncoding(Module):
             off += size
         return torch.cat(outs, dim=-1)
 
+    def grid_desc(self):
+        return _native.GridDesc(self.n_levels, self.log2_hashmap_size, self.base_resolution, self.per_level_scale)
+
+    def forward_train(self, x: Tensor) -> Tensor:
+        """The encoding under autograd, on the device (twice differentiable in x and the table)."""
+        if not (self.params.is_cuda and x.is_cuda):
+            raise _native.NativeError("the hash-grid encoding trains on a CUDA device only (no CPU route); "
+                                      "move the network and the batch to cuda")
+        return _GridEncode.apply(x, self.params, self.grid_desc())
+
     def forward(self, x: Tensor) -> Tensor:
         if torch.is_grad_enabled() and (x.requires_grad or self.params.requires_grad):
-            return self.forward_autograd(x)
+            return self.forward_train(x)
         return self._owner._native_for_encoding().encode(x)
 
 
