@@ -139,17 +139,39 @@ __device__ __forceinline__ void preprocess(const NetMeta &n, const float x[3], f
     for (int d = 0; d < 3; ++d) xp[d] = div_2s(n, x[d] + n.pre_scale);
 }
 
+// Out-of-line pieces of corner_indices: a dense cell whose corners wrap around the table (points
+// outside the grid only) and levels whose table size is not a power of two.  Kept out of the
+// callers on purpose: the evaluation kernels are fully unrolled straight-line code of several
+// thousand instructions, and their issue rate is bounded by instruction fetch (ncu: stall
+// no_instruction is the largest stall of k_sweep_chunk), so every inlined copy of a path that in-grid
+// points never take costs time.
+static __device__ __noinline__ void dense_corners_wrapped(uint32_t size, uint32_t res, uint32_t res2, uint32_t base, uint32_t idx[8])
+{
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) {
+        uint32_t i = base + (c & 1) + ((c >> 1) & 1) * res + ((c >> 2) & 1) * res2;
+        if (i >= size) i %= size;
+        idx[c] = i;
+    }
+}
+static __device__ __noinline__ void generic_corners(uint32_t size, uint32_t res, uint32_t cx, uint32_t cy, uint32_t cz, uint32_t idx[8])
+{
+#pragma unroll 1
+    for (int c = 0; c < 8; ++c) idx[c] = grid_index(size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1));
+}
+
 // the 8 corner indices of cell (cx,cy,cz): corner bit d set = +1 along axis d
 __device__ __forceinline__ void corner_indices(const LevelMeta &lv, uint32_t cx, uint32_t cy, uint32_t cz,
                                                uint32_t idx[8])
 {
     if (lv.mode == kLevelDense) {
         const uint32_t base = cx + cy * lv.res + cz * lv.res2;
+        const uint32_t top = base + 1u + lv.res + lv.res2;  // the largest of the 8 (size <= 2^31: no overflow when base < size)
+        if (base < lv.size && top < lv.size) {  // every point inside the grid: no corner wraps
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            uint32_t i = base + (c & 1) + ((c >> 1) & 1) * lv.res + ((c >> 2) & 1) * lv.res2;
-            if (i >= lv.size) i %= lv.size;  // only for points outside the grid
-            idx[c] = i;
+            for (int c = 0; c < 8; ++c) idx[c] = base + (c & 1) + ((c >> 1) & 1) * lv.res + ((c >> 2) & 1) * lv.res2;
+        } else {
+            dense_corners_wrapped(lv.size, lv.res, lv.res2, base, idx);
         }
     } else if (lv.mode == kLevelHashPow2) {
         const uint32_t hx[2] = {cx, cx + 1u};
@@ -159,9 +181,7 @@ __device__ __forceinline__ void corner_indices(const LevelMeta &lv, uint32_t cx,
 #pragma unroll
         for (int c = 0; c < 8; ++c) idx[c] = (hx[c & 1] ^ hy[(c >> 1) & 1] ^ hz[(c >> 2) & 1]) & mask;
     } else {
-#pragma unroll
-        for (int c = 0; c < 8; ++c)
-            idx[c] = grid_index(lv.size, lv.res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1));
+        generic_corners(lv.size, lv.res, cx, cy, cz, idx);
     }
 }
 

@@ -577,7 +577,7 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant
 
 // apply the failover override when any new vertex violated it, then bit-pack the region
 // indicator of the new vertices
-__device__ __forceinline__ void finalize_item(const NetMeta &n, const float *vert, float *out, uint64_t *sig,
+__device__ __forceinline__ void finalize_item(const NetMeta &n, const float *marks, const float *vert, float *out, uint64_t *sig,
                                               const uint64_t *bmask, int flag, int V, int k)
 {
     const int R = n.R;
@@ -592,7 +592,7 @@ __device__ __forceinline__ void finalize_item(const NetMeta &n, const float *ver
         pack_signs(row, R, n.eps, pos, neg);
         sig[3 * v] = pos;
         sig[3 * v + 1] = neg;
-        sig[3 * v + 2] = pack_grid(n, n.marks, xp, n.eps);
+        sig[3 * v + 2] = pack_grid(n, marks, xp, n.eps);
     }
 }
 __device__ __forceinline__ void body_finalize_new(const NetMeta &n,
@@ -602,7 +602,7 @@ __device__ __forceinline__ void body_finalize_new(const NetMeta &n,
 {
     if (cnt[C_OVERFLOW]) return;
     const int flag = cnt[C_FLAG], S = cnt[C_SPLIT], V = cnt[C_V];
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) finalize_item(n, vert, out, sig, bmask, flag, V, k);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) finalize_item(n, n.marks, vert, out, sig, bmask, flag, V, k);
 }
 
 __global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant__ NetMeta n,
@@ -764,10 +764,17 @@ struct CurveCommitEmit {
         }
         float *row = out + nv * R;
         uint64_t pos = 0, neg = 0;
-        for (int c = 0; c < R; ++c) {
-            const float v = tout[k * R + c];
-            row[c] = v;
-            if (!(fabsf(v) <= eps)) { if (v > 0.0f) pos |= 1ull << c; else neg |= 1ull << c; }
+        for (int c0 = 0; c0 < R; c0 += 16) {  // 16 loads in flight (see pack_signs)
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = c0 + i < R ? tout[k * R + c0 + i] : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                if (c0 + i < R) {
+                    row[c0 + i] = v[i];
+                    if (!(fabsf(v[i]) <= eps)) { if (v[i] > 0.0f) pos |= 1ull << (c0 + i); else neg |= 1ull << (c0 + i); }
+                }
+            }
         }
         uint64_t g = 0;
         for (int d = 0; d < 3; ++d) {
@@ -792,7 +799,12 @@ struct HitCount {
     const int *alive;  // rows of pruned vertices stay in place (complex.cuh): they are not part of the complex
     int R, idx;
     float eps;
-    __device__ __forceinline__ int operator()(int64_t v) const { return (alive[v] && fabsf(out[v * R + idx]) < eps) ? 1 : 0; }  // subpoly.py:233
+    __device__ __forceinline__ int operator()(int64_t v) const
+    {
+        const int al = alive[v];
+        const float o = out[v * R + idx];  // both loads in flight (a dead vertex's row is still there)
+        return (al && fabsf(o) < eps) ? 1 : 0;  // subpoly.py:233
+    }
 };
 
 // candidates = hit old vertices (already in cand[0..H)), then the new ones; publishes the
@@ -834,23 +846,30 @@ __device__ __forceinline__ int64_t cell_id(int cx, int cy, int cz, int dim)
 __device__ __forceinline__ void bucket_insert_item(int c, int v, const uint64_t *sig, unsigned long long *head,
                                                    tnb_bucket_rec *next, int dim, uint32_t stamp)
 {
-    {
-        tnb_bucket_rec r;
-        r.v = v;
-        r.pos = sig[3 * (int64_t)v];
-        r.neg = sig[3 * (int64_t)v + 1];
-        r.grd = sig[3 * (int64_t)v + 2];
-        const CellBox b = cell_box(r.grd);
-        int slot = 0;
-        for (int cx = b.lo[0]; cx <= b.hi[0]; ++cx)
-            for (int cy = b.lo[1]; cy <= b.hi[1]; ++cy)
-                for (int cz = b.lo[2]; cz <= b.hi[2]; ++cz, ++slot) {
-                    const int rec = c * 8 + slot;
-                    const unsigned long long mine = ((unsigned long long)stamp << 32) | (unsigned)rec;
-                    const unsigned long long old = atomicExch(head + cell_id(cx, cy, cz, dim), mine);
-                    r.next = ((uint32_t)(old >> 32) == stamp) ? (int)(uint32_t)old : -1;
-                    next[rec] = r;
-                }
+    tnb_bucket_rec r;
+    r.v = v;
+    r.pos = sig[3 * (int64_t)v];
+    r.neg = sig[3 * (int64_t)v + 1];
+    r.grd = sig[3 * (int64_t)v + 2];
+    const CellBox b = cell_box(r.grd);
+    // a vertex lies in 1, 2, 4 or 8 cells (one or two per axis).  All exchanges are issued before the
+    // first record is written: their round trips overlap instead of adding up.  Record c*8 + slot,
+    // slot = the cell's (dx,dy,dz) bits; which slot a cell gets does not matter.
+    unsigned long long old[8];
+#pragma unroll
+    for (int slot = 0; slot < 8; ++slot) {
+        const int cx = b.lo[0] + (slot >> 2), cy = b.lo[1] + ((slot >> 1) & 1), cz = b.lo[2] + (slot & 1);
+        const bool in = cx <= b.hi[0] && cy <= b.hi[1] && cz <= b.hi[2];
+        const unsigned long long mine = ((unsigned long long)stamp << 32) | (unsigned)(c * 8 + slot);
+        old[slot] = in ? atomicExch(head + cell_id(cx, cy, cz, dim), mine) : 0ull;
+    }
+#pragma unroll
+    for (int slot = 0; slot < 8; ++slot) {
+        const int cx = b.lo[0] + (slot >> 2), cy = b.lo[1] + ((slot >> 1) & 1), cz = b.lo[2] + (slot & 1);
+        if (cx <= b.hi[0] && cy <= b.hi[1] && cz <= b.hi[2]) {
+            r.next = ((uint32_t)(old[slot] >> 32) == stamp) ? (int)(uint32_t)old[slot] : -1;
+            next[c * 8 + slot] = r;
+        }
     }
 }
 __device__ __forceinline__ void body_bucket_insert(const int *cand, const int *cnt,
@@ -1534,7 +1553,7 @@ __global__ void __launch_bounds__(kScanThreads, 2) k_step_back(const StepArgs a,
 //   temporary rows (the idle half of the vertex arrays); strict_check's keep decision needs the
 //   failover flag of ALL candidates and the survivors need their ordered rank: two more barriers.
 template <class C, int NT, bool kCurve, class Sync>
-__device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, const StepVar sv, int parity, Sync sync)
+__device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, const StepVar sv, int parity, const float *marks, Sync sync)
 {
     int *cnt = a.cnt;
     const int E = cnt[C_E], V = cnt[C_V], pv = cnt[C_VPAR], pe = cnt[C_EPAR], pa = cnt[C_APAR];
@@ -1617,7 +1636,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
         // P1c: the survivors move to their final slots V + rank, in crossed-edge order; edges are rewired
         int r_base;
         block_sums_reduce<NT>(sums_x, r_base, S);
-        const CurveCommitEmit ce{nullptr, a.split_list, edges, tvert, tout, vert, out, sig, n.marks, cnt, R, n.n_marks, n.eps,
+        const CurveCommitEmit ce{nullptr, a.split_list, edges, tvert, tout, vert, out, sig, marks, cnt, R, n.n_marks, n.eps,
                                  n.pre_scale, n.pre_2s, n.pre_inv, n.pre_pow2, tag};
         const int r_end = scan_write_range<NT>(s_base, s_end, FlagCount{sflag}, ce, r_base);
         s_base = r_base;  // from here on: the CTA's own NEW VERTICES are the ranks [s_base, s_end)
@@ -1630,7 +1649,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     int h_base, Hn;
     block_sums_reduce<NT>(sums_y, h_base, Hn);
     for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT) {
-        if constexpr (!kCurve) finalize_item(n, vert, out, sig, a.bmask, flag, V, k);
+        if constexpr (!kCurve) finalize_item(n, marks, vert, out, sig, a.bmask, flag, V, k);
         a.cand[Hn + k] = V + k;
     }
     TNB_PHASE_MARK(11);
@@ -1708,6 +1727,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
 }
 
 constexpr int kClusterThreads = 512;
+constexpr int kMarksInSmem = 1312;  // every marks grid the dense cell-head array admits (<= 1288 per axis)
 constexpr int kMaxStepList = 128;
 struct StepList {
     int n;
@@ -1719,9 +1739,18 @@ template <class C, int NT, bool kCurve, class Sync>
 __device__ __forceinline__ void steps_loop(const NetMeta &n, const StepArgs &a, const StepList &list, Sync sync)
 {
     if (a.cnt[C_STICKY]) return;  // an earlier launch failed (nobody writes this word before the first barrier)
+    // The marks stay in shared memory for the whole launch: a grid barrier's fence leaves L1 cold, so the
+    // three binary searches of a new vertex's grid word were 24 dependent L2 round trips (~6 us per step).
+    __shared__ float s_marks[kMarksInSmem];
+    const float *marks = n.marks;
+    if (n.n_marks <= kMarksInSmem) {
+        for (int i = threadIdx.x; i < n.n_marks; i += NT) s_marks[i] = n.marks[i];
+        __syncthreads();
+        marks = s_marks;
+    }
     for (int i = 0; i < list.n; ++i) {
         const StepVar sv = step_var(list.idx[i], a.R, list.prune[i], list.stamp0 + (uint32_t)i);
-        const int r = step_fused<C, NT, kCurve>(n, a, sv, i & 1, sync);
+        const int r = step_fused<C, NT, kCurve>(n, a, sv, i & 1, marks, sync);
         if (r == 1) return;
         if (r == 0) sync();  // the next step reads the sizes and buffer parities this one published
     }

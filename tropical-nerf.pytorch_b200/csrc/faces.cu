@@ -119,7 +119,14 @@ struct SurfVertEmit {
         remap[v] = pos;
         ntag[pos] = tag[v];
         for (int d = 0; d < 3; ++d) nvert[3 * (int64_t)pos + d] = vert[3 * v + d];
-        for (int c = 0; c < R; ++c) nout[(int64_t)pos * R + c] = out[v * R + c];
+        for (int c0 = 0; c0 < R; c0 += 16) {  // 16 loads in flight, then their stores
+            float t[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) t[i] = c0 + i < R ? out[v * R + c0 + i] : 0.0f;
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (c0 + i < R) nout[(int64_t)pos * R + c0 + i] = t[i];
+        }
     }
 };
 __global__ void k_remap_edges2(int2 *__restrict__ edges, int64_t E, const int *__restrict__ remap)

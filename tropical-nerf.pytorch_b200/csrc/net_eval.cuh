@@ -272,10 +272,17 @@ __device__ __forceinline__ void pack_signs(const float *__restrict__ row, int R,
 {
     pos = 0;
     neg = 0;
-    for (int c = 0; c < R; ++c) {
-        float v = row[c];
-        if (!(fabsf(v) <= eps)) {
-            if (v > 0.0f) pos |= 1ull << c; else neg |= 1ull << c;
+    // 16 loads in flight at a time: the row usually sits in L2 (written before a grid barrier, or by
+    // another kernel), and one load per loop trip made this 33 dependent round trips
+    for (int c0 = 0; c0 < R; c0 += 16) {
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = c0 + i < R ? row[c0 + i] : 0.0f;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            if (c0 + i < R && !(fabsf(v[i]) <= eps)) {
+                if (v[i] > 0.0f) pos |= 1ull << (c0 + i); else neg |= 1ull << (c0 + i);
+            }
         }
     }
 }
