@@ -139,39 +139,17 @@ __device__ __forceinline__ void preprocess(const NetMeta &n, const float x[3], f
     for (int d = 0; d < 3; ++d) xp[d] = div_2s(n, x[d] + n.pre_scale);
 }
 
-// Out-of-line pieces of corner_indices: a dense cell whose corners wrap around the table (points
-// outside the grid only) and levels whose table size is not a power of two.  Kept out of the
-// callers on purpose: the evaluation kernels are fully unrolled straight-line code of several
-// thousand instructions, and their issue rate is bounded by instruction fetch (ncu: stall
-// no_instruction is the largest stall of k_sweep_chunk), so every inlined copy of a path that in-grid
-// points never take costs time.
-static __device__ __noinline__ void dense_corners_wrapped(uint32_t size, uint32_t res, uint32_t res2, uint32_t base, uint32_t idx[8])
-{
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) {
-        uint32_t i = base + (c & 1) + ((c >> 1) & 1) * res + ((c >> 2) & 1) * res2;
-        if (i >= size) i %= size;
-        idx[c] = i;
-    }
-}
-static __device__ __noinline__ void generic_corners(uint32_t size, uint32_t res, uint32_t cx, uint32_t cy, uint32_t cz, uint32_t idx[8])
-{
-#pragma unroll 1
-    for (int c = 0; c < 8; ++c) idx[c] = grid_index(size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1));
-}
-
 // the 8 corner indices of cell (cx,cy,cz): corner bit d set = +1 along axis d
 __device__ __forceinline__ void corner_indices(const LevelMeta &lv, uint32_t cx, uint32_t cy, uint32_t cz,
                                                uint32_t idx[8])
 {
     if (lv.mode == kLevelDense) {
         const uint32_t base = cx + cy * lv.res + cz * lv.res2;
-        const uint32_t top = base + 1u + lv.res + lv.res2;  // the largest of the 8 (size <= 2^31: no overflow when base < size)
-        if (base < lv.size && top < lv.size) {  // every point inside the grid: no corner wraps
 #pragma unroll
-            for (int c = 0; c < 8; ++c) idx[c] = base + (c & 1) + ((c >> 1) & 1) * lv.res + ((c >> 2) & 1) * lv.res2;
-        } else {
-            dense_corners_wrapped(lv.size, lv.res, lv.res2, base, idx);
+        for (int c = 0; c < 8; ++c) {
+            uint32_t i = base + (c & 1) + ((c >> 1) & 1) * lv.res + ((c >> 2) & 1) * lv.res2;
+            if (i >= lv.size) i %= lv.size;  // only for points outside the grid
+            idx[c] = i;
         }
     } else if (lv.mode == kLevelHashPow2) {
         const uint32_t hx[2] = {cx, cx + 1u};
@@ -181,8 +159,65 @@ __device__ __forceinline__ void corner_indices(const LevelMeta &lv, uint32_t cx,
 #pragma unroll
         for (int c = 0; c < 8; ++c) idx[c] = (hx[c & 1] ^ hy[(c >> 1) & 1] ^ hz[(c >> 2) & 1]) & mask;
     } else {
-        generic_corners(lv.size, lv.res, cx, cy, cz, idx);
+#pragma unroll
+        for (int c = 0; c < 8; ++c)
+            idx[c] = grid_index(lv.size, lv.res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1));
     }
+}
+
+// The same 8 indices for the cells every in-grid point lies in, without the wrap checks: a dense
+// cell whose largest corner index is below the table size, or a hashed level with a power-of-two
+// table.  false = this cell needs the general routine (a point outside the grid, or a table size
+// that is not a power of two): the callers then take their out-of-line slow path.  The split exists
+// for code size: the evaluation kernels are fully unrolled straight-line code of several thousand
+// instructions whose issue rate is bounded by instruction fetch (ncu: stall no_instruction is the
+// largest stall of k_sweep_chunk), so inlined copies of paths that in-grid points never take cost time.
+__device__ __forceinline__ bool corner_indices_fast(const LevelMeta &lv, uint32_t cx, uint32_t cy, uint32_t cz,
+                                                    uint32_t idx[8])
+{
+    if (lv.mode == kLevelDense) {
+        const uint32_t base = cx + cy * lv.res + cz * lv.res2;
+        const uint32_t top = base + 1u + lv.res + lv.res2;  // the largest of the 8 (size <= 2^31: no overflow when base < size)
+        if (!(base < lv.size && top < lv.size)) return false;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) idx[c] = base + (c & 1) + ((c >> 1) & 1) * lv.res + ((c >> 2) & 1) * lv.res2;
+        return true;
+    }
+    if (lv.mode == kLevelHashPow2) {
+        const uint32_t hx[2] = {cx, cx + 1u};
+        const uint32_t hy[2] = {cy * 2654435761u, (cy + 1u) * 2654435761u};
+        const uint32_t hz[2] = {cz * 805459861u, (cz + 1u) * 805459861u};
+        const uint32_t mask = lv.size - 1u;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) idx[c] = (hx[c & 1] ^ hy[(c >> 1) & 1] ^ hz[(c >> 2) & 1]) & mask;
+        return true;
+    }
+    return false;
+}
+
+// trilinear interpolation of the 8 corner rows (tiny-cuda-nn kernel_grid, linear interpolation)
+__device__ __forceinline__ float2 interpolate8(const float2 v[8], const float frac[3])
+{
+    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int corner = 0; corner < 8; ++corner) {
+        float w = 1.0f;
+#pragma unroll
+        for (int d = 0; d < 3; ++d) w = w * ((corner >> d) & 1 ? frac[d] : 1.0f - frac[d]);
+        acc.x = __fmaf_rn(w, v[corner].x, acc.x);
+        acc.y = __fmaf_rn(w, v[corner].y, acc.y);
+    }
+    return acc;
+}
+// a level through the general index routine, out of line (same arithmetic as the fast path)
+static __device__ __noinline__ float2 encode_level_general(const float2 *tab, uint32_t size, uint32_t res, uint32_t cx, uint32_t cy,
+                                                           uint32_t cz, float f0, float f1, float f2)
+{
+    const float frac[3] = {f0, f1, f2};
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + grid_index(size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1)));
+    return interpolate8(v, frac);
 }
 
 // Level l of the hash encoding at xp.  Returns the two features; optionally the cell
@@ -199,50 +234,64 @@ __device__ __forceinline__ float2 encode_level(const NetMeta &n, int l, const fl
         frac[d] = pos - fl;
     }
     const float2 *tab = n.table + lv.off;
-    float2 v[8];
     uint32_t idx[8];
-    corner_indices(lv, cell[0], cell[1], cell[2], idx);
+    if (!corner_indices_fast(lv, cell[0], cell[1], cell[2], idx))
+        return encode_level_general(tab, lv.size, lv.res, cell[0], cell[1], cell[2], frac[0], frac[1], frac[2]);
+    float2 v[8];
 #pragma unroll
     for (int corner = 0; corner < 8; ++corner) v[corner] = __ldg(tab + idx[corner]);
-    float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int corner = 0; corner < 8; ++corner) {
-        float w = 1.0f;
-#pragma unroll
-        for (int d = 0; d < 3; ++d) w = w * ((corner >> d) & 1 ? frac[d] : 1.0f - frac[d]);
-        acc.x = __fmaf_rn(w, v[corner].x, acc.x);
-        acc.y = __fmaf_rn(w, v[corner].y, acc.y);
-    }
-    return acc;
+    return interpolate8(v, frac);
 }
 
-// d(level features)/d xp[d]  (tiny-cuda-nn kernel_grid_backward_input, linear interp.)
-__device__ __forceinline__ float2 encode_level_dx(const NetMeta &n, int l, int d,
-                                                  const uint32_t cell[3], const float frac[3])
+// (ix, iy, iz) of the flat lattice index i = ix + nx * (iy + ny * iz) along a grid-stride loop: split
+// once per thread, then advanced by carries.  (Three 64-bit divisions per point were ~15 % of the
+// instructions of the sweep kernels.)
+struct LatticeStride {  // split of the grid stride, made on the host
+    int sx, sy, sz;
+};
+inline LatticeStride lattice_stride(int64_t stride, int nx, int ny)
 {
-    const LevelMeta lv = n.lvl[l];
-    const float2 *tab = n.table + lv.off;
-    float2 acc = make_float2(0.0f, 0.0f);
-#pragma unroll
-    for (int idx = 0; idx < 4; ++idx) {
-        float w = lv.scale;
-        uint32_t c[3];
-#pragma unroll
-        for (int nd = 0; nd < 2; ++nd) {
-            int dim = nd >= d ? nd + 1 : nd;
-            int bit = (idx >> nd) & 1;
-            w = w * (bit ? frac[dim] : 1.0f - frac[dim]);
-            c[dim] = cell[dim] + bit;
-        }
-        c[d] = cell[d];
-        float2 vl = __ldg(tab + grid_index(lv.size, lv.res, c[0], c[1], c[2]));
-        c[d] = cell[d] + 1u;
-        float2 vr = __ldg(tab + grid_index(lv.size, lv.res, c[0], c[1], c[2]));
-        acc.x = __fmaf_rn(w, vr.x - vl.x, acc.x);
-        acc.y = __fmaf_rn(w, vr.y - vl.y, acc.y);
-    }
-    return acc;
+    const int64_t plane = (int64_t)nx * ny;
+    LatticeStride s;
+    s.sz = (int)(stride / plane);
+    const int64_t r = stride - (int64_t)s.sz * plane;
+    s.sy = (int)(r / nx);
+    s.sx = (int)(r - (int64_t)s.sy * nx);
+    return s;
 }
+#ifdef __CUDACC__
+struct Lattice3 {
+    int ix, iy, iz;      // current point
+    int sx, sy, sz;      // the stride, split the same way
+    int nx, ny;
+    __device__ __forceinline__ Lattice3(int64_t first, LatticeStride st, int nx_, int ny_) : sx(st.sx), sy(st.sy), sz(st.sz), nx(nx_), ny(ny_)
+    {
+        if (first < 0x7fffffff) {  // every launch in practice: 32-bit divisions
+            const unsigned f = (unsigned)first, plane = (unsigned)nx_ * (unsigned)ny_;
+            iz = (int)(f / plane);
+            const unsigned r = f - (unsigned)iz * plane;
+            iy = (int)(r / (unsigned)nx_);
+            ix = (int)(r - (unsigned)iy * (unsigned)nx_);
+        } else {
+            const int64_t plane = (int64_t)nx_ * ny_;
+            iz = (int)(first / plane);
+            const int r = (int)(first - (int64_t)iz * plane);
+            iy = r / nx_;
+            ix = r - iy * nx_;
+        }
+    }
+    __device__ __forceinline__ void advance()
+    {
+        ix += sx;
+        const int cx = ix >= nx ? 1 : 0;
+        ix -= cx ? nx : 0;
+        iy += sy + cx;
+        const int cy = iy >= ny ? 1 : 0;
+        iy -= cy ? ny : 0;
+        iz += sz + cy;
+    }
+};
+#endif
 
 // torch.searchsorted(marks, v, right=False)
 __device__ __forceinline__ int lower_bound(const float *__restrict__ marks, int m, float v)

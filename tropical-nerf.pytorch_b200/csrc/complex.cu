@@ -162,15 +162,17 @@ constexpr int kMaxSegs = 3 * 512;
 // |tanh(sdf)| and |grad| of every marks-grid vertex of one chunk; per-chunk max |grad|
 template <class C>
 __global__ void __launch_bounds__(kThreads, 4) k_sweep_chunk(const __grid_constant__ NetMeta n, int M, int sx, int sy,
-                                                          int sz, int nx, int ny, int nz,
+                                                          int sz, int nx, int ny, int nz, LatticeStride ls,
                                                           float *__restrict__ dist, unsigned *__restrict__ max_grad)
 {
     const int64_t count = (int64_t)nx * ny * nz;
     float local = 0.0f;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    Lattice3 at(first < count ? first : 0, ls, nx, ny);
+    for (int64_t t = first; t < count; t += stride, at.advance()) {
         // x is the lane axis: the hash table is x-fastest, so a warp's gathers touch
         // consecutive entries (the |sdf| store is the only strided access)
-        const int i = (int)(t % nx), j = (int)((t / nx) % ny), k = (int)(t / ((int64_t)nx * ny));
+        const int i = at.ix, j = at.iy, k = at.iz;
         const int gi = sx + i, gj = sy + j, gk = sz + k;
         // preprocess_inverse(marks[...]) (tropical.py:186, model.py:81-82)
         float x[3] = {n.marks[gi] * n.pre_2s - n.pre_scale, n.marks[gj] * n.pre_2s - n.pre_scale,
@@ -374,11 +376,12 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
                 nn[0] = hi - lo + 1;
                 const int64_t count = (int64_t)nn[0] * nn[1] * nn[2];
                 unsigned g = grid_for(count, kThreads);
+                const LatticeStride ls = lattice_stride((int64_t)g * kThreads, nn[0], nn[1]);
                 prof_begin(TNB_PROF_SWEEP, s);
                 if (net->fixed_cfg)
-                    k_sweep_chunk<CfgRef><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist0, sw->max_grad.p + chunk);
+                    k_sweep_chunk<CfgRef><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], ls, dist0, sw->max_grad.p + chunk);
                 else
-                    k_sweep_chunk<CfgAny><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], dist0, sw->max_grad.p + chunk);
+                    k_sweep_chunk<CfgAny><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], ls, dist0, sw->max_grad.p + chunk);
                 TNB_LAUNCH_CHECK();
                 prof_end(TNB_PROF_SWEEP, s, count, count * 4 + (int64_t)net->table.cap * 8);
                 for (int axis = 0; axis < 3; ++axis) {

@@ -141,6 +141,39 @@ __device__ __forceinline__ void forward_masks(const NetMeta &n, const float xp[3
 // (tiny-cuda-nn kernel_grid_backward_input: for axis d, sum over the 4 corner pairs that
 // differ in d of scale * prod(other weights) * (right - left)).  Accumulates
 // g0 * d f0 + g1 * d f1 into acc[d] in the oracle's order.
+// sum over the 4 corner pairs that differ in axis d of scale * prod(other weights) * (right - left)
+__device__ __forceinline__ float2 level_dx(const float2 v[8], const float frac[3], float scale, int d)
+{
+    float2 dl = make_float2(0.0f, 0.0f);
+#pragma unroll
+    for (int idx = 0; idx < 4; ++idx) {
+        float w = scale;
+        int corner = 0;
+#pragma unroll
+        for (int nd = 0; nd < 2; ++nd) {
+            const int dim = nd >= d ? nd + 1 : nd;
+            const int bit = (idx >> nd) & 1;
+            w = w * (bit ? frac[dim] : 1.0f - frac[dim]);
+            corner |= bit << dim;
+        }
+        const float2 vl = v[corner], vr = v[corner | (1 << d)];
+        dl.x = __fmaf_rn(w, vr.x - vl.x, dl.x);
+        dl.y = __fmaf_rn(w, vr.y - vl.y, dl.y);
+    }
+    return dl;
+}
+// one axis of a level through the general index routine, out of line (see corner_indices_fast)
+static __device__ __noinline__ float2 level_dx_general(const float2 *tab, uint32_t size, uint32_t res, float scale, int d, uint32_t cx,
+                                                       uint32_t cy, uint32_t cz, float f0, float f1, float f2)
+{
+    const float frac[3] = {f0, f1, f2};
+    float2 v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = __ldg(tab + grid_index(size, res, cx + (c & 1), cy + ((c >> 1) & 1), cz + ((c >> 2) & 1)));
+    if (d == 0) return level_dx(v, frac, scale, 0);
+    if (d == 1) return level_dx(v, frac, scale, 1);
+    return level_dx(v, frac, scale, 2);
+}
 __device__ __forceinline__ void encode_level_grad(const NetMeta &n, int l, const float xp[3], float g0, float g1,
                                                   float acc[3])
 {
@@ -155,29 +188,23 @@ __device__ __forceinline__ void encode_level_grad(const NetMeta &n, int l, const
         frac[d] = pos - fl;
     }
     const float2 *tab = n.table + lv.off;
-    float2 v[8];
     uint32_t cidx[8];
-    corner_indices(lv, cell[0], cell[1], cell[2], cidx);
+    if (!corner_indices_fast(lv, cell[0], cell[1], cell[2], cidx)) {
+#pragma unroll 1
+        for (int d = 0; d < 3; ++d) {
+            const float2 dl = level_dx_general(tab, lv.size, lv.res, lv.scale, d, cell[0], cell[1], cell[2], frac[0], frac[1], frac[2]);
+            const float a = __fmaf_rn(g0, dl.x, d == 0 ? acc[0] : d == 1 ? acc[1] : acc[2]);
+            const float b = __fmaf_rn(g1, dl.y, a);
+            if (d == 0) acc[0] = b; else if (d == 1) acc[1] = b; else acc[2] = b;
+        }
+        return;
+    }
+    float2 v[8];
 #pragma unroll
     for (int corner = 0; corner < 8; ++corner) v[corner] = __ldg(tab + cidx[corner]);
 #pragma unroll
     for (int d = 0; d < 3; ++d) {
-        float2 dl = make_float2(0.0f, 0.0f);
-#pragma unroll
-        for (int idx = 0; idx < 4; ++idx) {
-            float w = lv.scale;
-            int corner = 0;
-#pragma unroll
-            for (int nd = 0; nd < 2; ++nd) {
-                const int dim = nd >= d ? nd + 1 : nd;
-                const int bit = (idx >> nd) & 1;
-                w = w * (bit ? frac[dim] : 1.0f - frac[dim]);
-                corner |= bit << dim;
-            }
-            const float2 vl = v[corner], vr = v[corner | (1 << d)];
-            dl.x = __fmaf_rn(w, vr.x - vl.x, dl.x);
-            dl.y = __fmaf_rn(w, vr.y - vl.y, dl.y);
-        }
+        const float2 dl = level_dx(v, frac, lv.scale, d);
         acc[d] = __fmaf_rn(g0, dl.x, acc[d]);
         acc[d] = __fmaf_rn(g1, dl.y, acc[d]);
     }

@@ -180,16 +180,16 @@ __global__ void __launch_bounds__(kThreads) k_region(const __grid_constant__ Net
 // Dense lattice sweep: evaluate + bit-pack, nothing but 16 B per point leaves the SM.
 template <class C>
 __global__ void __launch_bounds__(kThreads, 4) k_sweep_signs(const __grid_constant__ NetMeta n, float3 lo,
-                                                          float3 step, int nx, int ny, int nz,
+                                                          float3 step, int nx, int ny, int nz, LatticeStride ls,
                                                           float eps, ulonglong2 *__restrict__ packed)
 {
     const int64_t count = (int64_t)nx * ny * nz;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count;
-         i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
+    if (first >= count) return;
+    Lattice3 at(first, ls, nx, ny);
+    for (int64_t i = first; i < count; i += stride, at.advance()) {
         // x is the lane axis (table is x-fastest); the output index stays z-fastest
-        int ix = (int)(i % nx);
-        int iy = (int)((i / nx) % ny);
-        int iz = (int)(i / ((int64_t)nx * ny));
+        const int ix = at.ix, iy = at.iy, iz = at.iz;
         float p[3] = {__fmaf_rn((float)ix, step.x, lo.x), __fmaf_rn((float)iy, step.y, lo.y),
                       __fmaf_rn((float)iz, step.z, lo.z)};
         float xp[3];
@@ -446,11 +446,12 @@ int tnb_sweep_signs(const tnb_net *net, const float lo[3], const float hi[3], co
     int64_t count = (int64_t)nn[0] * nn[1] * nn[2];
     cudaStream_t s = (cudaStream_t)stream;
     unsigned g = grid_for(count, kThreads, kSMs * 32);
+    const LatticeStride ls = lattice_stride((int64_t)g * kThreads, nn[0], nn[1]);
     prof_begin(TNB_PROF_SIGN_SWEEP, s);
     if (net->fixed_cfg)
-        k_sweep_signs<CfgRef><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], eps, (ulonglong2 *)d_packed);
+        k_sweep_signs<CfgRef><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], ls, eps, (ulonglong2 *)d_packed);
     else
-        k_sweep_signs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], eps, (ulonglong2 *)d_packed);
+        k_sweep_signs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], ls, eps, (ulonglong2 *)d_packed);
     TNB_LAUNCH_CHECK();
     prof_end(TNB_PROF_SIGN_SWEEP, s, count, count * 16);
     return TNB_OK;
