@@ -165,10 +165,10 @@ __device__ __forceinline__ void corner_indices(const LevelMeta &lv, uint32_t cx,
     }
 }
 
-// The same 8 indices for the cells every in-grid point lies in, without the wrap checks: a dense
-// cell whose largest corner index is below the table size, or a hashed level with a power-of-two
-// table.  false = this cell needs the general routine (a point outside the grid, or a table size
-// that is not a power of two): the callers then take their out-of-line slow path.  The split exists
+// The same 8 indices for the cells every in-grid point lies in, without modulo: a dense cell (corners
+// below the table size, or wrapping around it once), or a hashed level with a power-of-two table.
+// false = this cell needs the general routine (a point far outside the grid, or a table size that is
+// not a power of two): the callers then take their out-of-line slow path.  The split exists
 // for code size: the evaluation kernels are fully unrolled straight-line code of several thousand
 // instructions whose issue rate is bounded by instruction fetch (ncu: stall no_instruction is the
 // largest stall of k_sweep_chunk), so inlined copies of paths that in-grid points never take cost time.
@@ -177,10 +177,20 @@ __device__ __forceinline__ bool corner_indices_fast(const LevelMeta &lv, uint32_
 {
     if (lv.mode == kLevelDense) {
         const uint32_t base = cx + cy * lv.res + cz * lv.res2;
-        const uint32_t top = base + 1u + lv.res + lv.res2;  // the largest of the 8 (size <= 2^31: no overflow when base < size)
-        if (!(base < lv.size && top < lv.size)) return false;
+        if (!(base < lv.size)) return false;
+        const uint32_t top = base + 1u + lv.res + lv.res2;  // the largest of the 8 (size <= 2^31: no overflow)
+        if (top < lv.size) {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) idx[c] = base + (c & 1) + ((c >> 1) & 1) * lv.res + ((c >> 2) & 1) * lv.res2;
+            for (int c = 0; c < 8; ++c) idx[c] = base + (c & 1) + ((c >> 1) & 1) * lv.res + ((c >> 2) & 1) * lv.res2;
+        } else {
+            // the last layer of cells of a level (up to half of the grid at the coarsest one): the upper
+            // corners wrap around the table once (1 + res + res^2 <= res^3 <= size), so i % size = i - size
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const uint32_t i = base + (c & 1) + ((c >> 1) & 1) * lv.res + ((c >> 2) & 1) * lv.res2;
+                idx[c] = i >= lv.size ? i - lv.size : i;
+            }
+        }
         return true;
     }
     if (lv.mode == kLevelHashPow2) {

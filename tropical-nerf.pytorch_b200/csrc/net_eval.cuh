@@ -293,12 +293,34 @@ __device__ __forceinline__ void outputs_row(const NetMeta &n, const float x[3], 
     row[(NL - 1) * H] = o[1] - o[0];
 }
 
+// sign of one output with tolerance eps >= 0 (model.py:97-98) into bit c of pos / neg:
+//   pos <=> |v| > eps and v > 0 <=> v > eps;   neg <=> not(|v| <= eps) and not(v > 0) <=> not(v >= -eps)
+// (the second form keeps a NaN on the negative side, like the reference's comparison chain).  One
+// compare and one predicated OR on a 32-bit half each: as nested ifs on 64-bit words this compiled
+// to a BSSY / BRA / BSYNC triple per neuron (a tenth of the instructions of the dense sign sweep).
+struct SignWords {
+    uint32_t plo = 0, phi = 0, nlo = 0, nhi = 0;
+    __device__ __forceinline__ void add(float v, float eps, int c)
+    {
+        const uint32_t bit = 1u << (c & 31);
+        const bool p = v > eps, q = !(v >= -eps);
+        if (c < 32) {
+            if (p) plo |= bit;
+            if (q) nlo |= bit;
+        } else {
+            if (p) phi |= bit;
+            if (q) nhi |= bit;
+        }
+    }
+    __device__ __forceinline__ uint64_t pos() const { return ((uint64_t)phi << 32) | plo; }
+    __device__ __forceinline__ uint64_t neg() const { return ((uint64_t)nhi << 32) | nlo; }
+};
+
 // sign bits of a row of outputs (model.py:97-98)
 __device__ __forceinline__ void pack_signs(const float *__restrict__ row, int R, float eps,
                                            uint64_t &pos, uint64_t &neg)
 {
-    pos = 0;
-    neg = 0;
+    SignWords w;
     // 16 loads in flight at a time: the row usually sits in L2 (written before a grid barrier, or by
     // another kernel), and one load per loop trip made this 33 dependent round trips
     for (int c0 = 0; c0 < R; c0 += 16) {
@@ -306,12 +328,11 @@ __device__ __forceinline__ void pack_signs(const float *__restrict__ row, int R,
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = c0 + i < R ? row[c0 + i] : 0.0f;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-            if (c0 + i < R && !(fabsf(v[i]) <= eps)) {
-                if (v[i] > 0.0f) pos |= 1ull << (c0 + i); else neg |= 1ull << (c0 + i);
-            }
-        }
+        for (int i = 0; i < 16; ++i)
+            if (c0 + i < R) w.add(v[i], eps, c0 + i);
     }
+    pos = w.pos();
+    neg = w.neg();
 }
 
 }  // namespace tnb

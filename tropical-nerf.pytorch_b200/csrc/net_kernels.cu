@@ -197,25 +197,17 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_signs(const __grid_consta
         float pre[(C::kMaxLin - 1) * C::kMaxH];
         float o[2];
         forward<C>(n, xp, pre, o);
-        uint64_t pos = 0, neg = 0;
+        SignWords w;
         const int H = C::H(n), NL = C::NLIN(n);
 #pragma unroll(C::kUnroll)
         for (int l = 0; l < C::kMaxLin - 1; ++l)
             if (l < NL - 1) {
 #pragma unroll(C::kUnroll)
                 for (int j = 0; j < C::kMaxH; ++j)
-                    if (j < H) {
-                        float v = pre[l * C::kMaxH + j];
-                        if (!(fabsf(v) <= eps)) {
-                            if (v > 0.0f) pos |= 1ull << (l * H + j); else neg |= 1ull << (l * H + j);
-                        }
-                    }
+                    if (j < H) w.add(pre[l * C::kMaxH + j], eps, l * H + j);
             }
-        float v = o[1] - o[0];
-        if (!(fabsf(v) <= eps)) {
-            if (v > 0.0f) pos |= 1ull << ((NL - 1) * H); else neg |= 1ull << ((NL - 1) * H);
-        }
-        packed[i] = make_ulonglong2(pos, neg);  // x fastest: coalesced 16 B stores
+        w.add(o[1] - o[0], eps, (NL - 1) * H);
+        packed[i] = make_ulonglong2(w.pos(), w.neg());  // x fastest: coalesced 16 B stores
     }
 }
 
