@@ -432,7 +432,10 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
     SkelEdgeCount q{d_segs.p, (int)segs.size(), M, dist0, sw->max_grad.p, sw->k_len};
     {
         int64_t blocks = std::min<int64_t>((slots + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
-        k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, nullptr, q, block_sums.p);
+        // one bit per slot: the write pass does not decode and test the ~93 % of the slots that fail again
+        DevBuf<uint32_t> slot_mask;
+        TNB_CUDA(slot_mask.reserve((size_t)((slots + 31) / 32 + kScanMaxBlocks)));
+        k_scan_count_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, q, block_sums.p, slot_mask.p);
         TNB_LAUNCH_CHECK();
         std::vector<int> h(blocks);
         TNB_CUDA(cudaMemcpyAsync(h.data(), block_sums.p, blocks * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -444,7 +447,7 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
         DevBuf<int2> raw;
         TNB_CUDA(raw.reserve((size_t)E));
         SkelEdgeEmit emit{q, raw.p, used.p - base};
-        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, nullptr, q, emit, block_sums.p, total.p);
+        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, nullptr, MaskCount{slot_mask.p}, emit, block_sums.p, total.p);
         TNB_LAUNCH_CHECK();
         // vertex pass: count, size, then place
         FlagCount fc{used.p};

@@ -256,6 +256,38 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, const in
     scan_count_body(n, count, block_sums);
 }
 
+// Count pass that also leaves one bit per item (bit i & 31 of mask[i >> 5]): when count(i) is
+// expensive and few items pass, the write pass reads the bit (MaskCount) instead of evaluating
+// count(i) again.  Slices are warp aligned, so a warp's ballot is exactly one mask word.
+template <class Count>
+__global__ void __launch_bounds__(kScanThreads) k_scan_count_mask(int64_t n, Count count, int *__restrict__ block_sums,
+                                                                  uint32_t *__restrict__ mask)
+{
+    constexpr int NW = kScanThreads / 32;
+    int64_t begin, end;
+    scan_slice(n, begin, end);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int acc = 0;
+    for (int64_t i0 = begin + warp * 32; i0 < end; i0 += kScanThreads) {
+        const int64_t i = i0 + lane;
+        const int c = (i < end && count(i)) ? 1 : 0;
+        const uint32_t word = __ballot_sync(0xffffffffu, c);
+        if (lane == 0) { mask[i0 >> 5] = word; acc += __popc(word); }
+    }
+    __shared__ int s[NW];
+    if (lane == 0) s[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < NW; ++w) t += s[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+struct MaskCount {
+    const uint32_t *mask;
+    __device__ __forceinline__ int operator()(int64_t i) const { return (int)((mask[i >> 5] >> (i & 31)) & 1u); }
+};
+
 template <class Count, class Emit>
 __global__ void __launch_bounds__(kScanThreads) k_scan_write(int64_t n, const int *__restrict__ n_dev, Count count,
                                                              Emit emit, const int *__restrict__ block_sums,
