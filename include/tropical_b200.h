@@ -125,9 +125,10 @@ int tnb_subpoly_step(const tnb_net *net, tnb_complex *c, int32_t l, int32_t h, f
                      int32_t force, void *stream);
 
 /* The loop over hyperplanes of subpoly() (subpoly.py:58-72) in one call: lh[2*i], lh[2*i+1] =
- * (l, h) of step i.  Same result as n_steps calls of tnb_subpoly_step; a small complex on the
- * planar path runs all of them in ONE launch of one thread-block cluster (no host round trip
- * and no grid-wide barrier between steps). */
+ * (l, h) of step i.  Same result as n_steps calls of tnb_subpoly_step; a small complex (planar
+ * or curve-approximation path) runs all of them in ONE persistent cooperative launch, with no
+ * host round trip between steps (optionally, planar path, inside one thread-block cluster:
+ * tnb_set_cluster_max_items). */
 int tnb_subpoly_steps(const tnb_net *net, tnb_complex *c, const int32_t *lh, int32_t n_steps, float eps,
                       int32_t force, void *stream);
 

@@ -27,8 +27,9 @@ namespace tnb {
 
 double g_capacity_factor = 4.0;
 constexpr int kThreads = 128;
-constexpr int kCachedPartners = 12;  // the partner-count pass keeps this many partners per candidate: the write
-                                    // pass of a short list (nearly all of them) does not walk the buckets again
+constexpr int kCachedPartners = 32;  // the partner-count pass keeps this many partners per candidate: the write
+                                    // pass of such a list does not walk the buckets again
+constexpr int kNetworkPartners = 12; // lists up to this size (nearly all of them) are sorted in registers
 // device counters: [0, C_V) are cleared at the start of every step, C_V / C_E hold the complex size
 //   C_RAW = edges the plane crosses, C_SPLIT = edges actually split (== C_RAW on the planar path,
 //   fewer after strict_check on the curve path)
@@ -1032,18 +1033,23 @@ __device__ __forceinline__ void pair_write_item(int a, const int *cand, const ui
         const int va = cand[a];
         int2 *dst = edges_out + poff[a];
         // ascending partner number = the order unique(dim=0) leaves (subpoly.py:243-244)
-        if (c <= kCachedPartners) {  // the count pass left the whole list behind
-            int list[kCachedPartners];
+        if (c <= kNetworkPartners) {  // the count pass left the whole list behind
+            int list[kNetworkPartners];
 #pragma unroll
-            for (int i = 0; i < kCachedPartners; ++i) list[i] = i < c ? pcache[(int64_t)a * kCachedPartners + i] : 0x7fffffff;
+            for (int i = 0; i < kNetworkPartners; ++i) list[i] = i < c ? pcache[(int64_t)a * kCachedPartners + i] : 0x7fffffff;
 #pragma unroll
-            for (int i = 1; i < kCachedPartners; ++i)
+            for (int i = 1; i < kNetworkPartners; ++i)
 #pragma unroll
-                for (int j = kCachedPartners - 1; j >= i; --j)
+                for (int j = kNetworkPartners - 1; j >= i; --j)
                     if (list[j - 1] > list[j]) { const int t = list[j]; list[j] = list[j - 1]; list[j - 1] = t; }
 #pragma unroll
-            for (int i = 0; i < kCachedPartners; ++i)
+            for (int i = 0; i < kNetworkPartners; ++i)
                 if (i < c) dst[i] = make_int2(va, list[i]);
+        } else if (c <= kCachedPartners) {  // still no second walk: sort the cached list
+            int list[kCachedPartners];
+            for (int i = 0; i < c; ++i) list[i] = pcache[(int64_t)a * kCachedPartners + i];
+            thread_sort(list, c);
+            for (int i = 0; i < c; ++i) dst[i] = make_int2(va, list[i]);
         } else if (c <= kLocalPartners) {
             int list[kLocalPartners];
             find_partners(a, cand, sig, head, next, dim, stamp, colmask, list, kLocalPartners, 1);

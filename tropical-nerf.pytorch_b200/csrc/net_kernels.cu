@@ -431,6 +431,7 @@ int tnb_sweep_signs(const tnb_net *net, const float lo[3], const float hi[3], co
 {
     if (!net || !lo || !hi || !nn || !d_packed) { set_error("tnb_sweep_signs: null argument"); return TNB_ERR_INVALID; }
     if (nn[0] < 1 || nn[1] < 1 || nn[2] < 1) { set_error("tnb_sweep_signs: empty lattice"); return TNB_ERR_INVALID; }
+    if ((int64_t)nn[0] * nn[1] >= 0x7fffffff) { set_error("tnb_sweep_signs: a lattice plane of 2^31 points or more"); return TNB_ERR_UNSUPPORTED; }
     float3 l = make_float3(lo[0], lo[1], lo[2]);
     float3 st = make_float3(nn[0] > 1 ? (hi[0] - lo[0]) / (float)(nn[0] - 1) : 0.0f,
                             nn[1] > 1 ? (hi[1] - lo[1]) / (float)(nn[1] - 1) : 0.0f,
