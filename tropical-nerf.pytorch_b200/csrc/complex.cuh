@@ -66,7 +66,7 @@ struct tnb_complex {
     tnb::DevBuf<int> cand;          // [Vcap]   candidate vertex numbers (hits, then new)
     tnb::DevBuf<int> pcount;        // [Vcap]   partners per candidate
     tnb::DevBuf<int> poff;          // [Vcap]   exclusive scan of pcount
-    tnb::DevBuf<int> pcache;        // [6*Vcap] first partners of each candidate, left by the count pass
+    tnb::DevBuf<int> pcache;        // [32*Vcap] first partners of each candidate, left by the count pass
     tnb::DevBuf<tnb_bucket_rec> next;  // [8*Vcap] bucket chains
     tnb::DevBuf<unsigned long long> head;  // [n_cells] (stamp << 32 | record)
     tnb::DevBuf<int> used[2];       // [Vcap]   vertex referenced by a kept edge; used[acur] = liveness of the current complex
