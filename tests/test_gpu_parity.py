@@ -260,11 +260,13 @@ def test_mirror_api_matches_native():
     assert np.array_equal(vertices.cpu().numpy(), vo) and np.array_equal(tri, to) and np.array_equal(faces, fo)
 
 
-@pytest.mark.parametrize("unit", [17, 25])
+@pytest.mark.parametrize("unit", [9, 17, 25])
 def test_chunked_skeleton_reproduces_the_overlap_duplicates(unit):
     """TropicalHashGrid.skeleton walks the marks grid in chunks of `unit` vertices that overlap by
     one plane (tropical.py:176-181): per-chunk thresholds, and grid edges on a chunk-boundary plane
-    come out twice.  Small chunks exercise that path (the large model hits it with unit=128)."""
+    come out twice.  Small chunks exercise that path (the large model hits it with unit=128).
+    unit=9 leaves clusters of 40 coincident vertices: partner lists longer than the cache, i.e. the
+    warp-per-list write pass (pair_write_long) inside the persistent step kernel."""
     from oracle import subpoly_ref as R
     g = load_golden("small_sphere")
     P = oracle_net(g)

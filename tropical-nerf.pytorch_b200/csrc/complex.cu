@@ -37,7 +37,8 @@ constexpr int kNetworkPartners = 12; // lists up to this size (nearly all of the
 //   C_STICKY = error bits that survive steps (sync-free fused path)
 //   C_KEPT = edges kept by pruning, parked until the slab exchange decides whether the step counts
 //   C_APAR = which half of the liveness array is current.  C_V counts vertex SLOTS (dead rows included)
-enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_CROSS = 16 /* 64-bit crossing mask */, C_NUM = 32 };
+//   C_LONG = candidates whose partner list is longer than the cache (their connecting edges are a warp's job)
+enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_LONG = 15, C_CROSS = 16 /* 64-bit crossing mask */, C_NUM = 32 };
 enum { kErrNoPlane = 1, kErrGradientDescent = 2 };
 enum { kStickyCapacity = 1, kStickyNoPlane = 32, kStickyGradientDescent = 64 };  // 2..16: halo.cuh
 
@@ -968,7 +969,8 @@ __device__ __forceinline__ int find_partners(int a, const int *cand, const uint6
 // count in pcount[a] and the first kCachedPartners partners (unsorted) in pcache.
 __device__ __forceinline__ void pair_count_groups(int begin, int end, const int *cand, const uint64_t *sig,
                                                   const unsigned long long *head, const tnb_bucket_rec *next, int dim,
-                                                  uint32_t stamp, uint64_t colmask, int *pcount, int *pcache, int *s_cnt)
+                                                  uint32_t stamp, uint64_t colmask, int *pcount, int *pcache, int *s_cnt,
+                                                  int *long_list = nullptr, int *long_cnt = nullptr)
 {
     const int g = threadIdx.x & 7, grp = threadIdx.x >> 3, per_pass = blockDim.x >> 3;
     for (int base = begin; base < end; base += per_pass) {
@@ -987,7 +989,10 @@ __device__ __forceinline__ void pair_count_groups(int begin, int end, const int 
             }
         }
         __syncwarp();
-        if (g == 0 && a < end) pcount[a] = s_cnt[grp];
+        if (g == 0 && a < end) {
+            pcount[a] = s_cnt[grp];
+            if (long_list && s_cnt[grp] > kCachedPartners) long_list[atomicAdd(long_cnt, 1)] = a;  // any order: each list has its own range
+        }
         __syncwarp();
     }
 }
@@ -996,21 +1001,23 @@ __device__ __forceinline__ void body_pair_count(const int *cand, int *cnt,
                                                          const uint64_t *sig,
                                                          const unsigned long long *head,
                                                          const tnb_bucket_rec *next, int dim, uint32_t stamp,
-                                                         uint64_t colmask, int *pcount, int *pcache)
+                                                         uint64_t colmask, int *pcount, int *pcache, int *long_list)
 {
     __shared__ int s_cnt[kThreads / 8];
     const int n_cand = cnt[C_CAND], per_block = blockDim.x >> 3;
     for (int base = blockIdx.x * per_block; base < n_cand; base += gridDim.x * per_block)
-        pair_count_groups(base, min(base + per_block, n_cand), cand, sig, head, next, dim, stamp, colmask, pcount, pcache, s_cnt);
+        pair_count_groups(base, min(base + per_block, n_cand), cand, sig, head, next, dim, stamp, colmask, pcount, pcache, s_cnt,
+                          long_list, cnt + C_LONG);
 }
 
 __global__ void __launch_bounds__(kThreads) k_pair_count(const int *__restrict__ cand, int *__restrict__ cnt,
                                                          const uint64_t *__restrict__ sig,
                                                          const unsigned long long *__restrict__ head,
                                                          const tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp,
-                                                         uint64_t colmask, int *__restrict__ pcount, int *__restrict__ pcache)
+                                                         uint64_t colmask, int *__restrict__ pcount, int *__restrict__ pcache,
+                                                         int *__restrict__ long_list)
 {
-    body_pair_count(cand, cnt, sig, head, next, dim, stamp, colmask, pcount, pcache);
+    body_pair_count(cand, cnt, sig, head, next, dim, stamp, colmask, pcount, pcache, long_list);
 }
 
 struct ArrayCount {
@@ -1025,11 +1032,12 @@ struct OffsetEmit {
 __device__ __forceinline__ void pair_write_item(int a, const int *cand, const uint64_t *sig,
                                                 const unsigned long long *head, const tnb_bucket_rec *next, int dim,
                                                 uint32_t stamp, uint64_t colmask, const int *pcount, const int *poff,
-                                                int2 *edges_out, const int *pcache)
+                                                int2 *edges_out, const int *pcache, bool defer_long = false)
 {
     {
         const int c = pcount[a];
         if (c == 0) return;
+        if (defer_long && c > kCachedPartners) return;  // pair_write_long: a warp per long list
         const int va = cand[a];
         int2 *dst = edges_out + poff[a];
         // ascending partner number = the order unique(dim=0) leaves (subpoly.py:243-244)
@@ -1072,10 +1080,90 @@ template <int NT>
 __device__ __forceinline__ void pair_write_range(int begin, int end, const int *cand, const uint64_t *sig,
                                                  const unsigned long long *head, const tnb_bucket_rec *next, int dim,
                                                  uint32_t stamp, uint64_t colmask, const int *pcount, const int *poff,
-                                                 int2 *edges_out, const int *pcache)
+                                                 int2 *edges_out, const int *pcache, bool defer_long = false)
 {
     for (int a = begin + (int)threadIdx.x; a < end; a += NT)
-        pair_write_item(a, cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache);
+        pair_write_item(a, cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache, defer_long);
+}
+
+// Connecting edges of ONE candidate with a long partner list, by a warp.  The long lists are the
+// clusters of coincident vertices the reference's chunk-overlap duplicates leave behind (rows of up to
+// 250 vertices in the large model): with one thread per candidate the write pass lasted as long as
+// its longest list (a single wave of threads, 145 us for the large sphere).  Eight lanes walk one cell
+// of the candidate's box each and append to the list's own output range, then the warp sorts the keys
+// (bitonic, in shared memory, up to kLongSortMax) and writes (va, key) pairs in ascending order.
+constexpr int kLongSortMax = 1024;
+constexpr int kSortWarps = 8;
+__device__ __forceinline__ void pair_write_long_warp(int a, const int *cand, const uint64_t *sig, const unsigned long long *head,
+                                                     const tnb_bucket_rec *next, int dim, uint32_t stamp, uint64_t colmask,
+                                                     const int *pcount, const int *poff, int2 *edges_out, int *keys_smem, int *s_pos)
+{
+    const int lane = threadIdx.x & 31;
+    const int c = pcount[a];
+    const int va = cand[a];
+    int2 *dst = edges_out + poff[a];
+    if (lane == 0) *s_pos = 0;
+    __syncwarp();
+    const bool in_smem = c <= kLongSortMax;
+    {
+        const PartnerQuery q = partner_query(va, sig);
+        const int nx = q.ba.hi[0] - q.ba.lo[0] + 1, ny = q.ba.hi[1] - q.ba.lo[1] + 1, nz = q.ba.hi[2] - q.ba.lo[2] + 1;
+        if (lane < nx * ny * nz) {
+            const int cz = q.ba.lo[2] + lane % nz, cy = q.ba.lo[1] + (lane / nz) % ny, cx = q.ba.lo[0] + lane / (nz * ny);
+            walk_cell(q, cx, cy, cz, head, next, dim, stamp, colmask, [&](int vb) {
+                const int pos = atomicAdd(s_pos, 1);
+                if (in_smem) keys_smem[pos] = vb; else dst[pos].y = vb;
+            });
+        }
+    }
+    __syncwarp();
+    if (in_smem) {
+        int n = 32;
+        while (n < c) n <<= 1;
+        for (int i = c + lane; i < n; i += 32) keys_smem[i] = 0x7fffffff;
+        __syncwarp();
+        for (int k = 2; k <= n; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = lane; i < n; i += 32) {
+                    const int p = i ^ j;
+                    if (p > i) {
+                        const int x = keys_smem[i], y = keys_smem[p];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { keys_smem[i] = y; keys_smem[p] = x; }
+                    }
+                }
+                __syncwarp();
+            }
+        for (int i = lane; i < c; i += 32) dst[i] = make_int2(va, keys_smem[i]);
+    } else {  // longer than the shared buffer (never seen): one lane sorts in place in HBM
+        if (lane == 0) {
+            thread_sort(&dst[0].y, c, 2);
+            for (int i = 0; i < c; ++i) dst[i].x = va;
+        }
+    }
+    __syncwarp();
+}
+// all long lists, by the warps of the calling grid (the first kSortWarps warps of every CTA)
+__device__ __forceinline__ void pair_write_long(const int *long_list, int n_long, const int *cand, const uint64_t *sig,
+                                                const unsigned long long *head, const tnb_bucket_rec *next, int dim, uint32_t stamp,
+                                                uint64_t colmask, const int *pcount, const int *poff, int2 *edges_out)
+{
+    __shared__ int s_keys[kSortWarps][kLongSortMax];
+    __shared__ int s_pos[kSortWarps];
+    const int warp = threadIdx.x >> 5;
+    if (warp >= kSortWarps) return;
+    const int warps_per_cta = min((int)(blockDim.x >> 5), kSortWarps);
+    for (int li = blockIdx.x * warps_per_cta + warp; li < n_long; li += gridDim.x * warps_per_cta)
+        pair_write_long_warp(long_list[li], cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, s_keys[warp], s_pos + warp);
+}
+__global__ void __launch_bounds__(kSortWarps * 32) k_pair_write_long(const int *__restrict__ long_list, const int *__restrict__ cnt,
+                                                                     const int *__restrict__ cand, const uint64_t *__restrict__ sig,
+                                                                     const unsigned long long *__restrict__ head,
+                                                                     const tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp,
+                                                                     uint64_t colmask, const int *__restrict__ pcount,
+                                                                     const int *__restrict__ poff, int2 *__restrict__ edges_out)
+{
+    pair_write_long(long_list, cnt[C_LONG], cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out);
 }
 template <int NT>
 __device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
@@ -1083,10 +1171,10 @@ __device__ __forceinline__ void body_pair_write(const int *cand, int n_cand,
                                                          const unsigned long long *head,
                                                          const tnb_bucket_rec *next, int dim, uint32_t stamp,
                                                          uint64_t colmask, const int *pcount,
-                                                         const int *poff, int2 *edges_out, const int *pcache)
+                                                         const int *poff, int2 *edges_out, const int *pcache, bool defer_long = false)
 {
     for (int base = blockIdx.x * NT; base < n_cand; base += gridDim.x * NT)
-        pair_write_range<NT>(base, min(base + NT, n_cand), cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache);
+        pair_write_range<NT>(base, min(base + NT, n_cand), cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache, defer_long);
 }
 
 __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__ cand, int n_cand,
@@ -1095,9 +1183,9 @@ __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__
                                                          const tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp,
                                                          uint64_t colmask, const int *__restrict__ pcount,
                                                          const int *__restrict__ poff, int2 *__restrict__ edges_out,
-                                                         const int *__restrict__ pcache)
+                                                         const int *__restrict__ pcache, int defer_long)
 {
-    body_pair_write<kThreads>(cand, n_cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache);
+    body_pair_write<kThreads>(cand, n_cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache, defer_long != 0);
 }
 
 // ---- pruning -------------------------------------------------------------------------------------
@@ -1272,6 +1360,7 @@ __global__ void k_set_parity(int *__restrict__ cnt, int vpar, int epar, int apar
 __global__ void k_clear_step_counters(int *__restrict__ cnt)
 {
     if (threadIdx.x < C_V) cnt[threadIdx.x] = 0;
+    if (threadIdx.x == 0) cnt[C_LONG] = 0;
 }
 
 
@@ -1581,7 +1670,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     unsigned long long *cross = (unsigned long long *)(cnt + C_CROSS);
     if (a.use_cross && !((*cross >> sv.idx) & 1ull)) return 2;
     TNB_PHASE_MARK(0);
-    if (blockIdx.x == 0 && threadIdx.x == 0) { cnt[C_FLAG] = 0; cnt[C_ERR] = 0; }  // last read two barriers ago
+    if (blockIdx.x == 0 && threadIdx.x == 0) { cnt[C_FLAG] = 0; cnt[C_ERR] = 0; cnt[C_LONG] = 0; }  // last read at least one barrier ago
     // P0: edges the plane crosses, per CTA slice
     const SplitCount sc{edges, out, R, sv.idx, a.eps};
     scan_count_body_t<NT>(E, sc, sums_x);
@@ -1683,7 +1772,8 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     scan_slice(n_cand, c_begin, c_end);
     {
         __shared__ int s_grp[NT / 8];
-        pair_count_groups((int)c_begin, (int)c_end, a.cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.pcache, s_grp);
+        pair_count_groups((int)c_begin, (int)c_end, a.cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.pcache, s_grp,
+                          a.remap, cnt + C_LONG);  // remap is idle during the steps: the list of long partner lists
         __syncthreads();
     }
     scan_count_body_t<NT>(n_cand, ArrayCount{a.pcount}, sums_x);
@@ -1699,7 +1789,13 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     }
     if (P > 0) {
         scan_write_from<NT>(n_cand, ArrayCount{a.pcount}, OffsetEmit{a.poff}, p_base);
-        pair_write_range<NT>((int)c_begin, (int)c_end, a.cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.poff, edges + E + S, a.pcache);
+        pair_write_range<NT>((int)c_begin, (int)c_end, a.cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.poff, edges + E + S, a.pcache, true);
+        const int n_long = cnt[C_LONG];  // complete since the barrier before this phase
+        if (n_long > 0) {
+            // the offsets of ALL candidates must be in place before a warp takes somebody else's list
+            sync();
+            pair_write_long(a.remap, n_long, a.cand, sig, a.head, a.next, a.dim, sv.stamp, sv.colmask, a.pcount, a.poff, edges + E + S);
+        }
     }
     if (!sv.do_prune) {  // the output neuron (subpoly.py:253): sizes only
         if (blockIdx.x == 0 && threadIdx.x == 0) {
@@ -2007,6 +2103,7 @@ static int cluster_ctas(K kernel)
     }
     return 0;
 }
+static bool g_long_lists = std::getenv("TNB_NO_LONG_LISTS") == nullptr;  // A/B switch: long partner lists by warps
 static bool g_fused_curve = std::getenv("TNB_NO_FUSED_CURVE") == nullptr;  // A/B switch: curve path step by step
 static int64_t g_cluster_max_items = std::getenv("TNB_CLUSTER_MAX_ITEMS") ? std::atoll(std::getenv("TNB_CLUSTER_MAX_ITEMS")) : 0;
 
@@ -2256,7 +2353,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
             k_bucket_insert<<<g, kThreads, 0, s>>>(c->cand.p, cnt, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp);
             TNB_LAUNCH_CHECK();
             prof_begin(TNB_PROF_PAIRS, s);
-            k_pair_count<<<grid_for(cand_ub * 8, kThreads), kThreads, 0, s>>>(c->cand.p, cnt, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->pcache.p);
+            k_pair_count<<<grid_for(cand_ub * 8, kThreads), kThreads, 0, s>>>(c->cand.p, cnt, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->pcache.p, g_long_lists ? c->remap.p : nullptr);
             TNB_LAUNCH_CHECK();
             prof_end(TNB_PROF_PAIRS, s, 0);
         }
@@ -2294,8 +2391,14 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     cnt = c->counters.p;
     if (P > 0) {
         prof_begin(TNB_PROF_PAIRS, s);
-        k_pair_write<<<grid_for(n_cand, kThreads), kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S, c->pcache.p);
+        k_pair_write<<<grid_for(n_cand, kThreads), kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S, c->pcache.p, g_long_lists ? 1 : 0);
         TNB_LAUNCH_CHECK();
+        const int n_long = c->h_counters[C_LONG];
+        if (g_long_lists && n_long > 0) {
+            k_pair_write_long<<<(unsigned)std::min<int64_t>((n_long + kSortWarps - 1) / kSortWarps, kSMs * 4), kSortWarps * 32, 0, s>>>(
+                c->remap.p, cnt, c->cand.p, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S);
+            TNB_LAUNCH_CHECK();
+        }
         prof_end(TNB_PROF_PAIRS, s, n_cand, (int64_t)n_cand * 28 + (int64_t)P * 8);
     }
     c->V = V0 + S;
