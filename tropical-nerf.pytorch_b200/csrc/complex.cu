@@ -449,7 +449,7 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
         DevBuf<int2> raw;
         TNB_CUDA(raw.reserve((size_t)E));
         SkelEdgeEmit emit{q, raw.p, used.p - base};
-        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, nullptr, MaskCount{slot_mask.p}, emit, block_sums.p, total.p);
+        k_scan_write_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, slot_mask.p, emit, block_sums.p, total.p);
         TNB_LAUNCH_CHECK();
         // vertex pass: count, size, then place
         FlagCount fc{used.p};
