@@ -198,7 +198,9 @@ __global__ void k_face_bucket_insert(int64_t V, const uint64_t *__restrict__ sig
 }
 
 // One warp per surface vertex a; lane q builds the row of a's q-th adjacent region.
-// mode 0: rows_per_vertex[a] = number of distinct rows a leads (>= 3 vertices), max width.
+// mode 0: rows_per_vertex[a] = bit mask of the regions (lanes) whose row a leads and keeps (distinct rows of
+//         >= 3 vertices; their count is the popcount), max width.  mode 1 walks the buckets again only for
+//         those lanes: a row has one leader, so nearly all (vertex, region) pairs have nothing to do there.
 // mode 1: write those rows, lexicographically ranked, at row_off[a].
 // Row storage: `stride` 64-bit keys ((zero count << 32) | vertex) per lane, in dynamic shared
 // memory when `scratch` is null, else in HBM (one slice per thread).  A row longer than
@@ -237,9 +239,11 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
         const int ka = __popcll(za) + gz;
         int cnt = 0;
         bool lead = false;
+        const unsigned todo = mode == 1 ? (unsigned)rows_per_vertex[a] : 0xffffffffu;
+        if (todo == 0) continue;  // warp uniform
         if (ka > kMaxZeros) {
             if (lane == 0) atomicOr(counters + F_ERR_ZEROS, 1);
-        } else if (lane < (1 << ka)) {
+        } else if (lane < (1 << ka) && ((todo >> lane) & 1u)) {
             // region q: bit t of q decides the side of a's t-th zero column (grid axes first)
             int cell[3];
             int t = 0;
@@ -297,7 +301,7 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
             }
         const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
         if (mode == 0) {
-            if (lane == 0) rows_per_vertex[a] = __popc(keep_mask);
+            if (lane == 0) rows_per_vertex[a] = (int)keep_mask;
             int wmax = keep ? cnt : 0;
 #pragma unroll
             for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
@@ -320,6 +324,10 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
 struct ArrayCount {
     const int *v;
     __device__ __forceinline__ int operator()(int64_t i) const { return v[i]; }
+};
+struct PopcCount {
+    const int *v;
+    __device__ __forceinline__ int operator()(int64_t i) const { return __popc((unsigned)v[i]); }
 };
 struct OffsetEmit {
     int *off;
@@ -661,7 +669,7 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
                                                                        counters.p, cell_lo, cell_hi);
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_FACE_ROWS, s, Vs, Vs * 28);
-        if ((rc = compact(Vs, ArrayCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
+        if ((rc = compact(Vs, PopcCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
         if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
         if (h[F_ERR_ZEROS]) { set_error("a surface vertex lies on more than 5 planes: more than 32 adjacent regions"); return TNB_ERR_UNSUPPORTED; }
         if (!h[F_ERR_ROW]) break;
