@@ -82,3 +82,17 @@ def test_train_entry_point_cli_matches_the_reference():
     assert (a.dataset, a.seed, a.model_size, a.eval, a.force, a.cache) == ("bunny", 1, "large", True, True, True)
     a = train.parse(["-f", "-c"])   # both switches are store_false in the reference (train.py:44-51)
     assert a.force is False and a.cache is False and a.dataset == "dragon" and a.seed == 45
+
+
+def test_training_grid_description_matches_the_parameter_layout():
+    """tnb_grid_desc (include/tropical_b200.h) as HashEncoding fills it: the library derives the same
+    table length as the tiny-cuda-nn layout the parameters were allocated with (no device needed)."""
+    import ctypes
+    from tropical import _native
+    from tropical.stanford.model import Net
+    for r_min, r_max, T in ((2, 32, 19), (4, 64, 19), (8, 128, 19), (8, 128, 21)):
+        net = Net(num_layers=3, num_hidden=16, levels=4, r_min=r_min, r_max=r_max, T=T)
+        d = net.enc.module.grid_desc()
+        assert _native.lib().tnb_grid_train_table_len(ctypes.byref(d)) == net.enc.module.params.numel()
+    bad = _native.GridDesc(0, 19, 2, 2.0)
+    assert _native.lib().tnb_grid_train_table_len(ctypes.byref(bad)) == -1
