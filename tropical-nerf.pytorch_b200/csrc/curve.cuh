@@ -9,7 +9,7 @@ namespace tnb {
 
 // All helpers here are WARP-COOPERATIVE: every lane of the warp calls them (full mask), each
 // lane brings its own candidate edge (or none), and the warp works through the candidates that
-// need the curve treatment together.  A candidate costs one network evaluation and at most 32
+// need the curve treatment together.  A candidate costs one network evaluation and at most 8
 // rounds of polynomial samples in lock-step instead of 8 evaluations and 1024 dependent samples
 // in one thread, which is what a persistent step kernel with a few candidates per CTA needs.
 // Per corner / per sample the operations and their order are those of oracle/trinet_ref.c, so
