@@ -265,36 +265,45 @@ def cpu_extract_seconds(P, planar=True):
 
 
 def _reference_worker(job):
-    """One host core: `steps` full extractions of the workload with the oracle port."""
-    name, planar, steps, warm = job
+    """One host core: its share of the run's full extractions with the oracle port."""
+    name, planar, n_mine, warm = job
     os.environ.setdefault("OMP_NUM_THREADS", "1")
     w = load_workload(name)
     P = oracle_params(w)
-    for _ in range(warm):
-        cpu_extract_seconds(P, planar)
+    if warm:   # page in numpy / the C checker with a small extraction (untimed)
+        cpu_extract_seconds(oracle_params(load_workload("small_sphere")), planar)
     t0 = time.perf_counter()
-    nv = 0
-    for _ in range(steps):
-        _, nv, _ = cpu_extract_seconds(P, planar)
-    return time.perf_counter() - t0, nv
+    nv = nt = 0
+    for _ in range(n_mine):
+        _, nv, nt = cpu_extract_seconds(P, planar)
+    return time.perf_counter() - t0, nv, nt
+
+
+def shared_config(w, planar, nv, nt):
+    """`config` of the JSON line: identical in both arms (the mesh sizes are bit-exact parity facts)."""
+    return {"workload": w["describe"] + ("" if planar else " [curve-approximation path]"),
+            "path": "planar" if planar else "curve", "marks_grid": int(len(w["marks"])),
+            "mesh_vertices": int(nv), "mesh_triangles": int(nt)}
 
 
 def run_reference(args):
-    """The reference's algorithm on the box's host cores.  The path shards by object, so every
-    core extracts its own copy of the object (the same decomposition our arm uses over GPUs):
-    value = vertices of all cores' extractions / wall time of the slowest core."""
+    """The reference's algorithm on the box's host cores (oracle port; the reference itself is Python
+    over tiny-cuda-nn and cannot run on the GPU box).  The path shards by object: the run's K full
+    extractions are dealt out over the worker processes, one per core, and
+    value = vertices of all K extractions / wall time of the slowest worker."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     w = load_workload(args.workload)   # (builds the cached fit once, before the workers look for it)
     planar = args.path == "planar"
-    cores = max(1, min(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1),
-                       args.ref_cores if args.ref_cores > 0 else
-                       # bounded so that the workers' working sets (numpy temporaries of [sum 2^k, 36] int64 region
-                       # matrices: gigabytes each for the large model) cannot exhaust the box's memory
-                       {"small": 32, "medium": 16, "large": 8}.get(args.workload.split("_")[0], 8)))
-    jobs = [(args.workload, planar, args.steps, min(args.warmup, 1))] * cores
+    avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    # bounded so that the workers' working sets (numpy temporaries of [sum 2^k, 36] int64 region matrices:
+    # gigabytes each for the large model) cannot exhaust the box's memory
+    cap = args.ref_cores if args.ref_cores > 0 else {"small": 32, "medium": 16, "large": 8}.get(args.workload.split("_")[0], 8)
+    cores = max(1, min(avail, cap, args.steps))
+    share = [args.steps // cores + (1 if i < args.steps % cores else 0) for i in range(cores)]
+    jobs = [(args.workload, planar, n, 1 if args.warmup > 0 else 0) for n in share]
     t0 = time.perf_counter()
     if cores == 1:
         res = [_reference_worker(jobs[0])]
@@ -303,17 +312,16 @@ def run_reference(args):
             res = pool.map(_reference_worker, jobs)
     wall = time.perf_counter() - t0
     slowest = max(r[0] for r in res)
-    nv = res[0][1]
-    value = nv * args.steps * cores / slowest
+    nv, nt = res[0][1], res[0][2]
+    value = nv * args.steps / slowest
     cpu = {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-           "sample": f"{args.steps} full extraction(s) of the same network per core on {cores} core(s) with the numpy+C oracle "
-                     f"port, one process per core (the reference is Python over tiny-cuda-nn and cannot run on the GPU box)",
-           "wall_s": wall}
+           "sample": f"{args.steps} full extraction(s) of the same network dealt out over {cores} worker process(es), one per host "
+                     f"core ({max(share)} each at most), numpy+C oracle port; warm-up = one small-model extraction per worker",
+           "wall_s": wall, "seconds_per_extraction_one_core": slowest / max(share)}
     print(json.dumps({"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
                       "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * slowest / args.steps,
                       "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                      "data": "synthetic", "config": {"workload": w["describe"] + ("" if planar else " [curve-approximation path]"), "mesh_vertices": nv,
-                                                        "objects_per_step": cores},
+                      "data": "synthetic", "config": shared_config(w, planar, nv, nt),
                       "cpu_baseline": cpu,
                       "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
@@ -529,12 +537,12 @@ def run_ours(args):
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
            "scaling": "strong" if slab else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": w["describe"] + ("" if planar else " [curve-approximation path]"), "mesh_vertices": sizes["V"], "mesh_triangles": sizes["T"],
-                      "polygons": sizes["P"], "objects_per_step": objects, "l2": "flushed (512 MiB write) between timed steps",
-                      "extraction_s": ms_total / args.steps * 1e-3,
-                      "sharding": ("one object cut into %d marks-grid slabs, one per GPU; per-step exchange through peer mailboxes, "
-                                   "all-gather + merge inside the timed region" % world) if slab else "one object per GPU",
-                      "slab_stats": slab_stats},
+           "config": shared_config(w, planar, sizes["V"], sizes["T"]),
+           "run": {"polygons": sizes["P"], "objects_per_step": objects, "l2": "flushed (512 MiB write) between timed steps",
+                   "extraction_s": ms_total / args.steps * 1e-3,
+                   "sharding": ("one object cut into %d marks-grid slabs, one per GPU; per-step exchange through peer mailboxes, "
+                                "all-gather + merge inside the timed region" % world) if slab else "one object per GPU",
+                   "slab_stats": slab_stats},
            "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": 1e3 * float(t.item()) / args.steps},
@@ -550,7 +558,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="small_sphere")
+    ap.add_argument("--workload", default="large_sphere",
+                    help="large_sphere (default: the configuration BASELINE.json quotes its target on), medium_sphere, "
+                         "small_sphere, small_torus, medium_torus, large_torus, <size>_random")
     ap.add_argument("--path", default="planar", choices=["planar", "curve"],
                     help="planar = the reference's -f default (force=True); curve = curve approximation")
     ap.add_argument("--shard", default="object", choices=["object", "slab"],

@@ -111,6 +111,8 @@ int tnb_skeleton(const tnb_net *net, int32_t unit, float size, tnb_complex **out
 int tnb_complex_from_arrays(const tnb_net *net, const float *d_vertices, int64_t V,
                             const int64_t *d_edges, int64_t E, tnb_complex **out, void *stream);
 void tnb_complex_destroy(tnb_complex *c);
+/* -1: the complex carries a device-side error (capacity, curve path, slab exchange); the same
+ * TNB_ERR_* code is returned by every later call on it and tnb_last_error() says why */
 int64_t tnb_complex_num_vertices(const tnb_complex *c);
 int64_t tnb_complex_num_edges(const tnb_complex *c);
 /* copy out to device buffers (any may be NULL): vertices [V,3] f32, edges [E,2] i64,

@@ -1,0 +1,119 @@
+"""GPU parity at the sizes BASELINE.json quotes its metric on: the medium and large models, at
+full size, through the C ABI, against the CPU oracle (bit-exact: every array) and -- for the
+medium torus, BASELINE configs[2] -- against the fixture the UNMODIFIED reference produced
+(tests/golden/make_golden_medium.py).  The fitted medium/large sphere networks are bench.py's
+workloads (fitted once per box, cached); the oracle needs ~10 s (medium) / ~75 s (large)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import load_golden, native_net, oracle_net
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _bench():
+    if ROOT not in sys.path:
+        sys.path.insert(0, ROOT)
+    import bench
+    return bench
+
+
+def _medium_torus():
+    g = load_golden("medium_torus")
+    g["net_table"] = g["net_table"].astype(np.float32)   # stored as fp16: the network IS those values
+    return g
+
+
+@pytest.mark.parametrize("name", ["medium_sphere", "large_sphere"])
+def test_fitted_sphere_full_size_bit_exact(name):
+    """bench.py's headline workloads: device mesh == oracle mesh, every array, at full size
+    (large: 201^3 marks grid, ~122 k vertices / ~300 k triangles)."""
+    from oracle import subpoly_ref as R
+    bench = _bench()
+    w = bench.load_workload(name)
+    N = bench.make_native(w)
+    mesh = N.subpoly()
+    v, e, tri, f, p = [a.cpu().numpy() for a in mesh.read()]
+    faces, vo, to, inter = R.subpoly(bench.oracle_params(w), return_intermediate=True)
+    assert v.shape[0] > (100000 if name.startswith("large") else 10000)
+    assert np.array_equal(v, vo)
+    assert np.array_equal(e, inter["surface_edges"])
+    assert np.array_equal(tri, to)
+    assert np.array_equal(f, faces)
+    # the same extraction twice gives the same arrays (no order left to atomics)
+    v2, e2, tri2, _, _ = [a.cpu().numpy() for a in N.subpoly().read()]
+    assert np.array_equal(v, v2) and np.array_equal(e, e2) and np.array_equal(tri, tri2)
+
+
+def test_medium_torus_planar_matches_oracle_and_reference():
+    from oracle import subpoly_ref as R
+    g = _medium_torus()
+    P = oracle_net(g)
+    N = native_net(P)
+    H = P.num_hidden
+    steps = [(l, h) for l in range(P.num_layers - 1) for h in range(H)] + [(P.num_layers - 2, H)]
+    c = N.skeleton(128)
+    for i, (l, h) in enumerate(steps):
+        c.step(l, h)
+        assert (c.num_vertices, c.num_edges) == tuple(g["planar_step_sizes"][i]), (l, h)
+    _, e, _ = c.read()
+    assert np.array_equal(e.cpu().numpy(), g["planar_complex_edges"].astype(np.int64))
+    mesh = N.subpoly()
+    v, _, tri, f, _ = [a.cpu().numpy() for a in mesh.read()]
+    faces, vo, to = R.subpoly(P)
+    assert np.array_equal(v, vo) and np.array_equal(tri, to) and np.array_equal(f, faces)
+    assert v.shape == g["planar_surface_vertices"].shape
+    assert np.abs(v - g["planar_surface_vertices"]).max() <= 1e-5
+    assert tri.shape[0] == g["planar_triangles"].shape[0]
+
+
+def test_medium_torus_curve_path_matches_oracle_and_reference():
+    """BASELINE configs[2]: medium model, analytic torus, curve-approximation path (force=False)."""
+    from scipy.spatial import cKDTree
+    from oracle import subpoly_ref as R
+    g = _medium_torus()
+    P = oracle_net(g)
+    N = native_net(P)
+    H = P.num_hidden
+    steps = [(l, h) for l in range(P.num_layers - 1) for h in range(H)] + [(P.num_layers - 2, H)]
+    c = N.skeleton(128)
+    c.steps(steps, force=False)
+    _, e, _ = c.read()
+    # the complex after all 33 hyperplanes: the reference's own edge array, bit for bit
+    assert (c.num_vertices, c.num_edges) == tuple(g["curve_step_sizes"][-1])
+    assert np.array_equal(e.cpu().numpy(), g["curve_complex_edges"].astype(np.int64))
+    mesh = N.subpoly(force=False)
+    v, _, tri, f, _ = [a.cpu().numpy() for a in mesh.read()]
+    faces, vo, to = R.subpoly(P, force=False)
+    assert np.array_equal(v, vo) and np.array_equal(tri, to) and np.array_equal(f, faces)
+    ref_v = g["curve_surface_vertices"]
+    assert v.shape == ref_v.shape
+    d1, _ = cKDTree(ref_v).query(v)
+    d2, _ = cKDTree(v).query(ref_v)
+    assert d1.max() <= 1e-5 and d2.max() <= 1e-5          # BASELINE: max nearest-vertex error
+    assert (d1.mean() + d2.mean()) / 2 <= 1e-6            # BASELINE: Chamfer distance
+    assert 0 <= g["curve_triangles"].shape[0] - tri.shape[0] <= 4   # faces the reference emits twice (test_whole_path_mesh)
+
+
+def test_latched_capacity_error_is_reported_by_every_call():
+    """a sticky device error must not be swallowed by the first size query."""
+    from tropical import _native
+    N = native_net(oracle_net(load_golden("small_sphere")))
+    _native.check(_native.lib().tnb_set_capacity_factor(1.0))
+    try:
+        c = N.skeleton(128)     # arrays exactly as large as the skeleton: the first crossing step overflows
+    finally:
+        _native.check(_native.lib().tnb_set_capacity_factor(4.0))
+    H = N.num_hidden
+    c.steps([(l, h) for l in range(N.num_layers - 1) for h in range(H)])
+    for _ in range(2):
+        with pytest.raises(_native.NativeError, match="CAPACITY"):
+            c.num_vertices
+        with pytest.raises(_native.NativeError, match="CAPACITY"):
+            c.read()
+        with pytest.raises(_native.NativeError, match="CAPACITY"):
+            c.extract_mesh()

@@ -461,7 +461,8 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
         TNB_CUDA(cudaStreamSynchronize(s));
         int64_t V = 0;
         for (int v : hv) V += v;
-        size_t Vcap = (size_t)(V * g_capacity_factor) + 4096, Ecap = (size_t)(E * g_capacity_factor) + 4096;
+        // the additive head-room scales with the factor too: a retry with twice the factor doubles a tiny complex's room as well
+        size_t Vcap = (size_t)(std::max<int64_t>(V, 4096) * g_capacity_factor), Ecap = (size_t)(std::max<int64_t>(E, 4096) * g_capacity_factor);
         int rc = complex_alloc(c, net, Vcap, Ecap);
         if (rc) return rc;
         SkelVertEmit vemit{nullptr, net->meta.marks, net->meta.pre_2s, net->meta.pre_scale, M, remap.p, c->cvert(),
@@ -1910,6 +1911,7 @@ static bool g_fused_steps = std::getenv("TNB_NO_FUSED_STEPS") == nullptr;  // A/
 // Refresh the host's view of the complex size (one small D2H + sync).
 int complex_sync_counts(tnb_complex *c, cudaStream_t s)
 {
+    if (c->sticky_rc) { set_error(c->sticky_msg); return c->sticky_rc; }
     if (!c->counts_stale && !c->cross_stale) return TNB_OK;
     int rc = read_counters(c, s);
     if (rc) return rc;
@@ -1933,34 +1935,25 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
             prof_add(TNB_PROF_STEPS, 0, (int64_t)(hb[0] + hb[1]));
         }
     }
-    if (c->h_counters[C_STICKY] & kStickyCapacity) {
-        set_error("work buffers too small for this complex (capacity factor " + std::to_string(g_capacity_factor) + ")");
-        return TNB_ERR_CAPACITY;
-    }
-    if (c->h_counters[C_STICKY] & kStickyNoPlane) {
-        set_error("curve path: a non-axis-aligned edge lies on no earlier plane (the reference exits here, subpoly.py:140-148)");
-        return TNB_ERR_INVALID;
-    }
-    if (c->h_counters[C_STICKY] & kStickyGradientDescent) {
-        set_error("curve path: an intersection needs the gradient-descent repair of subpoly_debug.py:121-165, which is not built");
-        return TNB_ERR_UNSUPPORTED;
-    }
-    if (c->h_counters[C_STICKY] & kStickyHaloPayload) {
-        set_error("slab exchange: a shared plane holds more vertices than the mailbox payload");
-        return TNB_ERR_CAPACITY;
-    }
-    if (c->h_counters[C_STICKY] & kStickyHaloTimeout) {
-        set_error("slab exchange: a peer did not answer within the timeout");
-        return TNB_ERR_CUDA;
-    }
-    if (c->h_counters[C_STICKY] & kStickyHaloMismatch) {
-        set_error("slab exchange: the two sides of a shared plane disagree on its vertex count");
-        return TNB_ERR_INVALID;
-    }
-    if (c->h_counters[C_STICKY] & kStickyHaloPeer) {
-        set_error("slab exchange: another slab reported an error");
-        return TNB_ERR_CAPACITY;
-    }
+    // A sticky device error freezes the complex at the failing step (the step kernels exit early once
+    // a bit is set): latch it, so that EVERY later call on this complex reports it, not only this one.
+    const int sticky = c->h_counters[C_STICKY];
+    auto latch = [&](int rc, const std::string &msg) {
+        c->sticky_rc = rc;
+        c->sticky_msg = msg;
+        set_error(msg);
+        return rc;
+    };
+    if (sticky & kStickyCapacity)
+        return latch(TNB_ERR_CAPACITY, "work buffers too small for this complex (capacity factor " + std::to_string(g_capacity_factor) + ")");
+    if (sticky & kStickyNoPlane)
+        return latch(TNB_ERR_INVALID, "curve path: a non-axis-aligned edge lies on no earlier plane (the reference exits here, subpoly.py:140-148)");
+    if (sticky & kStickyGradientDescent)
+        return latch(TNB_ERR_UNSUPPORTED, "curve path: an intersection needs the gradient-descent repair of subpoly_debug.py:121-165, which is not built");
+    if (sticky & kStickyHaloPayload) return latch(TNB_ERR_CAPACITY, "slab exchange: a shared plane holds more vertices than the mailbox payload");
+    if (sticky & kStickyHaloTimeout) return latch(TNB_ERR_CUDA, "slab exchange: a peer did not answer within the timeout");
+    if (sticky & kStickyHaloMismatch) return latch(TNB_ERR_INVALID, "slab exchange: the two sides of a shared plane disagree on its vertex count");
+    if (sticky & kStickyHaloPeer) return latch(TNB_ERR_CAPACITY, "slab exchange: another slab reported an error");
     return TNB_OK;
 }
 
@@ -2499,7 +2492,7 @@ static int from_arrays_impl(const tnb_net *net, const float *d_vertices, int64_t
 {
     tnb_complex *c = new tnb_complex();
     *out = c;
-    int rc = complex_alloc(c, net, (size_t)(V * g_capacity_factor) + 4096, (size_t)(E * g_capacity_factor) + 4096);
+    int rc = complex_alloc(c, net, (size_t)(std::max<int64_t>(V, 4096) * g_capacity_factor), (size_t)(std::max<int64_t>(E, 4096) * g_capacity_factor));
     if (rc) return rc;
     if (V > 0) TNB_CUDA(cudaMemcpyAsync(c->cvert(), d_vertices, (size_t)V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (E > 0) {
@@ -2694,13 +2687,13 @@ int64_t tnb_complex_num_vertices(const tnb_complex *c)
 {
     if (!c) return 0;
     current_stream() = c->stream;
-    complex_compact(const_cast<tnb_complex *>(c), c->stream);
+    if (complex_compact(const_cast<tnb_complex *>(c), c->stream) != TNB_OK) return -1;  // tnb_last_error() says why
     return c->V;
 }
 int64_t tnb_complex_num_edges(const tnb_complex *c)
 {
     if (!c) return 0;
-    complex_sync_counts(const_cast<tnb_complex *>(c), c->stream);
+    if (complex_sync_counts(const_cast<tnb_complex *>(c), c->stream) != TNB_OK) return -1;
     return c->E;
 }
 

@@ -76,6 +76,8 @@ struct tnb_complex {
     tnb::DevBuf<unsigned long long> bytes;  // [2] algorithmic bytes accumulated by the fused kernels
     int *h_counters = nullptr;      // pinned mirror (per thread, not owned)
     bool counts_stale = false;      // V/E are upper bounds; exact sizes are in counters[C_V], [C_E]
+    int sticky_rc = 0;              // latched device error (capacity, curve path, slab exchange): every later call returns it
+    std::string sticky_msg;
     cudaStream_t stream = nullptr;  // stream of the last call
     uint32_t stamp = 0;             // bucket generation
     int64_t n_cells = 0;

@@ -353,11 +353,19 @@ class NativeComplex:
 
     @property
     def num_vertices(self):
-        return int(lib().tnb_complex_num_vertices(self.handle))
+        return self._size(lib().tnb_complex_num_vertices(self.handle))
 
     @property
     def num_edges(self):
-        return int(lib().tnb_complex_num_edges(self.handle))
+        return self._size(lib().tnb_complex_num_edges(self.handle))
+
+    @staticmethod
+    def _size(n):
+        if n < 0:   # the complex carries a latched device-side error
+            msg = lib().tnb_last_error().decode("utf-8", "replace")
+            code = "TNB_ERR_CAPACITY" if "too small" in msg or "payload" in msg else "TNB_ERR"
+            raise NativeError(f"{code}: {msg}")
+        return int(n)
 
     def read(self, vertices=True, edges=True, outputs=True):
         V, E, R = self.num_vertices, self.num_edges, self.net.n_outputs
