@@ -264,12 +264,15 @@ def cpu_extract_seconds(P, planar=True):
     return time.perf_counter() - t, vertices.shape[0], tri.shape[0]
 
 
+_REF_WORKLOAD = None   # set in the parent before the worker pool forks: the children must not build it again
+
+
 def _reference_worker(job):
-    """One host core: its share of the run's full extractions with the oracle port."""
-    name, planar, n_mine, warm = job
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
-    w = load_workload(name)
-    P = oracle_params(w)
+    """One host core: its share of the run's full extractions with the oracle port.  Touches numpy and
+    the C checker only -- the parent imported torch (workload generation) and a forked child must not
+    enter torch's thread pools."""
+    planar, n_mine, warm = job
+    P = oracle_params(_REF_WORKLOAD)
     if warm:   # page in numpy / the C checker with a small extraction (untimed)
         cpu_extract_seconds(oracle_params(load_workload("small_sphere")), planar)
     t0 = time.perf_counter()
@@ -295,7 +298,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    w = load_workload(args.workload)   # (builds the cached fit once, before the workers look for it)
+    global _REF_WORKLOAD
+    w = _REF_WORKLOAD = load_workload(args.workload)
     planar = args.path == "planar"
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     # bounded so that the workers' working sets (numpy temporaries of [sum 2^k, 36] int64 region matrices:
@@ -303,7 +307,7 @@ def run_reference(args):
     cap = args.ref_cores if args.ref_cores > 0 else {"small": 32, "medium": 16, "large": 8}.get(args.workload.split("_")[0], 8)
     cores = max(1, min(avail, cap, args.steps))
     share = [args.steps // cores + (1 if i < args.steps % cores else 0) for i in range(cores)]
-    jobs = [(args.workload, planar, n, 1 if args.warmup > 0 else 0) for n in share]
+    jobs = [(planar, n, 1 if args.warmup > 0 else 0) for n in share]
     t0 = time.perf_counter()
     if cores == 1:
         res = [_reference_worker(jobs[0])]

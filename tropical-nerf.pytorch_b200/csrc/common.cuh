@@ -205,7 +205,10 @@ __device__ __forceinline__ bool corner_indices_fast(const LevelMeta &lv, uint32_
     return false;
 }
 
-// trilinear interpolation of the 8 corner rows (tiny-cuda-nn kernel_grid, linear interpolation)
+// trilinear interpolation of the 8 corner rows (tiny-cuda-nn kernel_grid, linear interpolation).
+// The two features of a row advance together in ONE packed FFMA2 (Blackwell fma.rn.f32x2: two
+// independent IEEE binary32 FMAs per issue slot, the weight broadcast to both halves), so each half
+// is exactly the __fmaf_rn of the scalar definition in oracle/trinet_ref.c.
 __device__ __forceinline__ float2 interpolate8(const float2 v[8], const float frac[3])
 {
     float2 acc = make_float2(0.0f, 0.0f);
@@ -214,8 +217,7 @@ __device__ __forceinline__ float2 interpolate8(const float2 v[8], const float fr
         float w = 1.0f;
 #pragma unroll
         for (int d = 0; d < 3; ++d) w = w * ((corner >> d) & 1 ? frac[d] : 1.0f - frac[d]);
-        acc.x = __fmaf_rn(w, v[corner].x, acc.x);
-        acc.y = __fmaf_rn(w, v[corner].y, acc.y);
+        acc = __ffma2_rn(make_float2(w, w), v[corner], acc);
     }
     return acc;
 }

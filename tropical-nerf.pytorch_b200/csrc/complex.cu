@@ -15,6 +15,7 @@
 #include <cooperative_groups.h>
 
 #include "complex.cuh"
+#include "cells.cuh"
 #include "curve.cuh"
 #include "halo.cuh"
 #include "net_eval.cuh"
@@ -38,7 +39,7 @@ constexpr int kNetworkPartners = 12; // lists up to this size (nearly all of the
 //   C_KEPT = edges kept by pruning, parked until the slab exchange decides whether the step counts
 //   C_APAR = which half of the liveness array is current.  C_V counts vertex SLOTS (dead rows included)
 //   C_LONG = candidates whose partner list is longer than the cache (their connecting edges are a warp's job)
-enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_LONG = 15, C_CROSS = 16 /* 64-bit crossing mask */, C_NUM = 32 };
+enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_LONG = 15, C_CROSS = 16 /* 64-bit crossing mask */, C_RECS = 18 /* records in the contiguous cell segments */, C_NUM = 32 };
 enum { kErrNoPlane = 1, kErrGradientDescent = 2 };
 enum { kStickyCapacity = 1, kStickyNoPlane = 32, kStickyGradientDescent = 64 };  // 2..16: halo.cuh
 
@@ -65,6 +66,8 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
     TNB_CUDA(c->poff.reserve(Vcap));
     TNB_CUDA(c->pcache.reserve(Vcap * kCachedPartners));
     TNB_CUDA(c->next.reserve(Vcap * 8));
+    TNB_CUDA(c->cslot.reserve(Vcap * 8));
+    TNB_CUDA(c->scan_mask.reserve((std::max(Vcap, Ecap) + 31) / 32 + kScanMaxBlocks + 64));
     TNB_CUDA(c->remap.reserve(Vcap));
     TNB_CUDA(c->block_sums.reserve(3 * kScanMaxBlocks));  // the persistent step kernels keep three sets of block sums
     TNB_CUDA(c->counters.reserve(C_NUM));
@@ -104,6 +107,10 @@ static int grow(DevBuf<T> &b, size_t new_elems, size_t keep_elems, cudaStream_t 
 // make room for Vneed vertices / Eneed edges, keeping the current contents
 int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
 {
+    if (Vneed > c->Vcap || Eneed > c->Ecap) {
+        int rc = grow(c->scan_mask, (std::max(std::max(Vneed, (size_t)(c->Vcap * 2)), std::max(Eneed, (size_t)(c->Ecap * 2))) + 31) / 32 + kScanMaxBlocks + 64, 0, s);
+        if (rc) return rc;
+    }
     if (Vneed > c->Vcap) {
         size_t nc = std::max(Vneed, (size_t)(c->Vcap * 2));
         int rc;
@@ -116,7 +123,7 @@ int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
             if ((rc = grow(c->used[k], nc, (k == c->acur) ? (size_t)c->V : 0, s))) return rc;
         }
         if ((rc = grow(c->cand, nc, 0, s)) || (rc = grow(c->pcount, nc, 0, s)) || (rc = grow(c->poff, nc, 0, s)) || (rc = grow(c->pcache, nc * kCachedPartners, 0, s)) ||
-            (rc = grow(c->next, nc * 8, 0, s)) || (rc = grow(c->remap, nc, 0, s)))
+            (rc = grow(c->next, nc * 8, 0, s)) || (rc = grow(c->cslot, nc * 8, 0, s)) || (rc = grow(c->remap, nc, 0, s)))
             return rc;
         c->Vcap = nc;
     }
@@ -171,18 +178,38 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_chunk(const __grid_consta
     float local = 0.0f;
     const int64_t first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     Lattice3 at(first < count ? first : 0, ls, nx, ny);
-    for (int64_t t = first; t < count; t += stride, at.advance()) {
-        // x is the lane axis: the hash table is x-fastest, so a warp's gathers touch
-        // consecutive entries (the |sdf| store is the only strided access)
-        const int i = at.ix, j = at.iy, k = at.iz;
-        const int gi = sx + i, gj = sy + j, gk = sz + k;
-        // preprocess_inverse(marks[...]) (tropical.py:186, model.py:81-82)
-        float x[3] = {n.marks[gi] * n.pre_2s - n.pre_scale, n.marks[gj] * n.pre_2s - n.pre_scale,
-                      n.marks[gk] * n.pre_2s - n.pre_scale};
-        float g[3];
-        const float sdf = sdf_grad<C>(n, x, g, true);
-        dist[((int64_t)gi * M + gj) * M + gk] = fabsf(sdf);
-        local = fmaxf(local, grad_norm(g));
+    if constexpr (C::kFixed) {
+        // two grid vertices per trip (t and t + stride): both networks in packed FFMA2s (net_eval.cuh)
+        for (int64_t t = first; t < count; t += 2 * stride) {
+            const bool two = t + stride < count;
+            const int gi0 = sx + at.ix, gj0 = sy + at.iy, gk0 = sz + at.iz;
+            at.advance();
+            const int gi1 = two ? sx + at.ix : gi0, gj1 = two ? sy + at.iy : gj0, gk1 = two ? sz + at.iz : gk0;
+            at.advance();
+            // preprocess_inverse(marks[...]) (tropical.py:186, model.py:81-82)
+            float x0[3] = {n.marks[gi0] * n.pre_2s - n.pre_scale, n.marks[gj0] * n.pre_2s - n.pre_scale, n.marks[gk0] * n.pre_2s - n.pre_scale};
+            float x1[3] = {n.marks[gi1] * n.pre_2s - n.pre_scale, n.marks[gj1] * n.pre_2s - n.pre_scale, n.marks[gk1] * n.pre_2s - n.pre_scale};
+            float sdf[2], g[2][3];
+            sdf_grad_pair<C>(n, x0, x1, sdf, g);
+            dist[((int64_t)gi0 * M + gj0) * M + gk0] = fabsf(sdf[0]);
+            local = fmaxf(local, grad_norm(g[0]));
+            if (two) {
+                dist[((int64_t)gi1 * M + gj1) * M + gk1] = fabsf(sdf[1]);
+                local = fmaxf(local, grad_norm(g[1]));
+            }
+        }
+    } else {
+        for (int64_t t = first; t < count; t += stride, at.advance()) {
+            // x is the lane axis: the hash table is x-fastest, so a warp's gathers touch
+            // consecutive entries (the |sdf| store is the only strided access)
+            const int gi = sx + at.ix, gj = sy + at.iy, gk = sz + at.iz;
+            float x[3] = {n.marks[gi] * n.pre_2s - n.pre_scale, n.marks[gj] * n.pre_2s - n.pre_scale,
+                          n.marks[gk] * n.pre_2s - n.pre_scale};
+            float g[3];
+            const float sdf = sdf_grad<C>(n, x, g, true);
+            dist[((int64_t)gi * M + gj) * M + gk] = fabsf(sdf);
+            local = fmaxf(local, grad_norm(g));
+        }
     }
     // block max (non-negative floats order like their bit patterns)
     unsigned v = __float_as_uint(local);
@@ -518,9 +545,11 @@ struct ListEmit {
 // new vertex of every split edge: position (subpoly.py:113-117, :180), network row, the
 // failover mask of subpoly_debug.py:37-43, edge rewiring (subpoly.py:210-215)
 // k-th split edge of the step -> vertex V + k; returns whether the failover override fires
-template <class C>
+// kPack: also bit-pack the new vertex's region indicator right away, as if the failover override will not
+// fire (it almost never does; when it does, k_finalize_new redoes the packing from the overridden row)
+template <class C, bool kPack = false>
 __device__ __forceinline__ int new_vertex_item(const NetMeta &n, int idx, float eps, int k, int V, int E, const int *split_list,
-                                               int2 *edges, float *vert, float *out, const uint64_t *sig, uint64_t *bmask,
+                                               int2 *edges, float *vert, float *out, uint64_t *sig, uint64_t *bmask,
                                                unsigned char *tag)
 {
     const int R = n.R;
@@ -538,14 +567,24 @@ __device__ __forceinline__ int new_vertex_item(const NetMeta &n, int idx, float 
 #pragma unroll
         for (int d = 0; d < 3; ++d) vert[3 * nv + d] = x[d];
         float *row = out + nv * R;
-        outputs_row<C>(n, x, row);
         const uint64_t za = ~(sig[3 * (int64_t)ed.x] | sig[3 * (int64_t)ed.x + 1]);
         const uint64_t zb = ~(sig[3 * (int64_t)ed.y] | sig[3 * (int64_t)ed.y + 1]);
         const uint64_t bm = (za & zb & ((1ull << idx) - 1ull)) | (1ull << idx);
         bmask[k] = bm;
-        for (uint64_t m = bm; m; m &= m - 1) {
-            const int col = __ffsll((long long)m) - 1;
-            if (fabsf(row[col]) > eps) any = 1;
+        if constexpr (kPack) {
+            uint64_t pos, neg, big;  // big: |value| > eps (the step's eps), for the failover test below
+            float xp[3];
+            outputs_row_packed<C>(n, x, row, n.eps, eps, xp, pos, neg, big);
+            if (big & bm) any = 1;
+            sig[3 * nv] = pos;
+            sig[3 * nv + 1] = neg;
+            sig[3 * nv + 2] = pack_grid(n, n.marks, xp, n.eps);
+        } else {
+            outputs_row<C>(n, x, row);
+            for (uint64_t m = bm; m; m &= m - 1) {
+                const int col = __ffsll((long long)m) - 1;
+                if (fabsf(row[col]) > eps) any = 1;
+            }
         }
         tag[nv] = tag[ed.x] & tag[ed.y];         // on a shared slab plane iff both parents are
         edges[e].y = (int)nv;                    // left part keeps the first endpoint
@@ -554,11 +593,11 @@ __device__ __forceinline__ int new_vertex_item(const NetMeta &n, int idx, float 
     return any;
 }
 
-template <class C>
+template <class C, bool kPack = false>
 __device__ __forceinline__ void body_new_vertices(const NetMeta &n, int idx, float eps,
                                                            int Vcap, int Ecap, const int *split_list,
                                                            int2 *edges, float *vert,
-                                                           float *out, const uint64_t *sig,
+                                                           float *out, uint64_t *sig,
                                                            uint64_t *bmask, int *cnt, unsigned char *tag)
 {
     const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
@@ -569,19 +608,20 @@ __device__ __forceinline__ void body_new_vertices(const NetMeta &n, int idx, flo
     if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_SPLIT] = S;  // planar path: every crossed edge is split
     int any = 0;
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x)
-        any |= new_vertex_item<C>(n, idx, eps, k, V, E, split_list, edges, vert, out, sig, bmask, tag);
+        any |= new_vertex_item<C, kPack>(n, idx, eps, k, V, E, split_list, edges, vert, out, sig, bmask, tag);
     if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
 }
 
+// (sig is read at the old vertices and written at the new ones: no __restrict__)
 template <class C>
 __global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant__ NetMeta n, int idx, float eps,
                                                            int Vcap, int Ecap, const int *__restrict__ split_list,
                                                            int2 *__restrict__ edges, float *__restrict__ vert,
-                                                           float *__restrict__ out, const uint64_t *__restrict__ sig,
+                                                           float *__restrict__ out, uint64_t *sig,
                                                            uint64_t *__restrict__ bmask, int *__restrict__ cnt,
                                                            unsigned char *__restrict__ tag)
 {
-    body_new_vertices<C>(n, idx, eps, Vcap, Ecap, split_list, edges, vert, out, sig, bmask, cnt, tag);
+    body_new_vertices<C, true>(n, idx, eps, Vcap, Ecap, split_list, edges, vert, out, sig, bmask, cnt, tag);
 }
 
 // apply the failover override when any new vertex violated it, then bit-pack the region
@@ -614,11 +654,14 @@ __device__ __forceinline__ void body_finalize_new(const NetMeta &n,
     for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x) finalize_item(n, n.marks, vert, out, sig, bmask, flag, V, k);
 }
 
+// multi-launch path: k_new_vertices packed the region indicators already; only a step whose failover
+// override fired (subpoly_debug.py:41-49) has rows to zero and indicators to pack again
 __global__ void __launch_bounds__(kThreads) k_finalize_new(const __grid_constant__ NetMeta n,
                                                            const float *__restrict__ vert, float *__restrict__ out,
                                                            uint64_t *__restrict__ sig, const uint64_t *__restrict__ bmask,
                                                            const int *__restrict__ cnt)
 {
+    if (!cnt[C_FLAG]) return;
     body_finalize_new(n, vert, out, sig, bmask, cnt);
 }
 
@@ -831,27 +874,8 @@ __global__ void k_fill_new_cands(int *__restrict__ cand, int *__restrict__ cnt)
     body_fill_new_cands(cand, cnt);
 }
 
-// ---- cell buckets ------------------------------------------------------------------------------
-// A candidate lies in the cells [lo_d, hi_d] per axis: hi = offset, lo = offset - 1 when it
-// sits on the grid plane (mask 0) -- the (m-1)//2 + offset expansion of subpoly.py:332.
-struct CellBox {
-    int lo[3], hi[3];
-};
-__device__ __forceinline__ CellBox cell_box(uint64_t g)
-{
-    CellBox b;
-#pragma unroll
-    for (int d = 0; d < 3; ++d) {
-        b.hi[d] = grid_off(g, d);
-        b.lo[d] = b.hi[d] - (grid_mask(g, d) ? 0 : 1);
-    }
-    return b;
-}
-__device__ __forceinline__ int64_t cell_id(int cx, int cy, int cz, int dim)
-{
-    return ((int64_t)(cx + 2) * dim + (cy + 2)) * dim + (cz + 2);
-}
-
+// ---- cell buckets (linked-list form: the persistent step kernels of small complexes) ---------------
+// (CellBox / cell_box / cell_id: cells.cuh)
 __device__ __forceinline__ void bucket_insert_item(int c, int v, const uint64_t *sig, unsigned long long *head,
                                                    tnb_bucket_rec *next, int dim, uint32_t stamp)
 {
@@ -918,6 +942,25 @@ __device__ __forceinline__ PartnerQuery partner_query(int va, const uint64_t *si
     q.ba = cell_box(q.ga);
     return q;
 }
+// is the candidate of record r a partner of q, found in cell (cx,cy,cz)?  (each pair is accepted in
+// exactly one cell: the smallest common one)
+__device__ __forceinline__ bool partner_test(const PartnerQuery &q, const tnb_bucket_rec &r, int cx, int cy, int cz, uint64_t colmask)
+{
+    if (r.v <= q.va) return false;
+    const uint64_t pb = r.pos, nb = r.neg, gb = r.grd;
+    if (((q.pa & nb) | (q.na & pb)) & colmask) return false;  // opposite signs: no common region
+    const CellBox bb = cell_box(gb);
+    const int cur[3] = {cx, cy, cz};
+    bool ok = true;
+    int shared = __popcll(q.za & ~(pb | nb) & colmask);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int lo = max(q.ba.lo[d], bb.lo[d]), hi = min(q.ba.hi[d], bb.hi[d]);
+        if (lo > hi || cur[d] != lo) ok = false;  // not a common cell / not the canonical one
+        if (!grid_mask(q.ga, d) && !grid_mask(gb, d) && q.ba.hi[d] == bb.hi[d]) ++shared;
+    }
+    return ok && shared >= 1;
+}
 // walks the bucket of ONE cell; hit(vb) is called for every partner found there
 template <class Hit>
 __device__ __forceinline__ void walk_cell(const PartnerQuery &q, int cx, int cy, int cz, const unsigned long long *head,
@@ -925,25 +968,10 @@ __device__ __forceinline__ void walk_cell(const PartnerQuery &q, int cx, int cy,
 {
     const unsigned long long h = head[cell_id(cx, cy, cz, dim)];
     if ((uint32_t)(h >> 32) != stamp) return;
-    const int cur[3] = {cx, cy, cz};
     for (int rec = (int)(uint32_t)h; rec >= 0;) {
         const tnb_bucket_rec r = next[rec];
         rec = r.next;
-        const int vb = r.v;
-        if (vb <= q.va) continue;
-        const uint64_t pb = r.pos, nb = r.neg, gb = r.grd;
-        if (((q.pa & nb) | (q.na & pb)) & colmask) continue;  // opposite signs: no common region
-        const CellBox bb = cell_box(gb);
-        bool ok = true;
-        int shared = __popcll(q.za & ~(pb | nb) & colmask);
-#pragma unroll
-        for (int d = 0; d < 3; ++d) {
-            const int lo = max(q.ba.lo[d], bb.lo[d]), hi = min(q.ba.hi[d], bb.hi[d]);
-            if (lo > hi || cur[d] != lo) ok = false;  // not a common cell / not the canonical one
-            if (!grid_mask(q.ga, d) && !grid_mask(gb, d) && q.ba.hi[d] == bb.hi[d]) ++shared;
-        }
-        if (!ok || shared < 1) continue;
-        hit(vb);
+        if (partner_test(q, r, cx, cy, cz, colmask)) hit(r.v);
     }
 }
 // One thread, all cells of the candidate's box.  Returns the count; when `list` is non-null the
@@ -1189,6 +1217,174 @@ __global__ void __launch_bounds__(kThreads) k_pair_write(const int *__restrict__
     body_pair_write<kThreads>(cand, n_cand, sig, head, next, dim, stamp, colmask, pcount, poff, edges_out, pcache, defer_long != 0);
 }
 
+// ---- connecting edges over contiguous cell segments (cells.cuh): large complexes ----------------------
+// Every candidate is filed ONCE, in the lowest cell of its box.  One WARP per candidate a: the boxes of a
+// and b overlap iff b's lowest cell lies in [a.lo - 1, a.hi] per axis, i.e. in one of up to 27 cells
+// around a.  Their segments are laid end to end; lane l tests records l, l+32, ... of that
+// concatenation, four independent 32-byte loads in flight per lane, hits compacted with ballots.  The
+// first kCachedPartners partners go to shared memory; a list that fits is sorted right here (bitonic over
+// the lanes) and the write pass is a flat copy.  Longer lists (the coincident-vertex clusters the
+// reference's chunk-overlap duplicates leave: one cluster is now streamed once per member, not once per
+// cell of its box) are filed in long_list for k_pair_write_long_seg.
+__device__ __forceinline__ bool partner_test_once(const PartnerQuery &q, const tnb_bucket_rec &r, uint64_t colmask)
+{
+    if (r.v <= q.va) return false;
+    const uint64_t pb = r.pos, nb = r.neg, gb = r.grd;
+    if (((q.pa & nb) | (q.na & pb)) & colmask) return false;  // opposite signs: no common region
+    const CellBox bb = cell_box(gb);
+    bool ok = true;
+    int shared = __popcll(q.za & ~(pb | nb) & colmask);
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        if (max(q.ba.lo[d], bb.lo[d]) > min(q.ba.hi[d], bb.hi[d])) ok = false;  // no common cell
+        if (!grid_mask(q.ga, d) && !grid_mask(gb, d) && q.ba.hi[d] == bb.hi[d]) ++shared;
+    }
+    return ok && shared >= 1;
+}
+// Streams the neighbourhood of q with the calling warp; emit(hit, vb) is called by ALL lanes once per
+// round of 32 records (hit = this lane's record is a partner).  s_incl / s_base: 32 ints each, per warp.
+template <class Emit>
+__device__ __forceinline__ void stream_partners(const PartnerQuery &q, const int2 *__restrict__ cells,
+                                                const tnb_bucket_rec *__restrict__ recs, int dim, uint64_t colmask,
+                                                int *s_incl, int *s_base, Emit emit)
+{
+    const int lane = threadIdx.x & 31;
+    const int ny = q.ba.hi[1] - q.ba.lo[1] + 2, nz = q.ba.hi[2] - q.ba.lo[2] + 2;
+    const int ncell = (q.ba.hi[0] - q.ba.lo[0] + 2) * ny * nz;
+    int cnt = 0, base = 0;
+    if (lane < ncell) {
+        const int cz = q.ba.lo[2] - 1 + lane % nz, cy = q.ba.lo[1] - 1 + (lane / nz) % ny, cx = q.ba.lo[0] - 1 + lane / (nz * ny);
+        if (cx >= -2 && cy >= -2 && cz >= -2) {  // no vertex has a lowest cell below -2 (offsets start at -1)
+            const int2 cb = cells[cell_id(cx, cy, cz, dim)];
+            cnt = cb.x; base = cb.y;
+        }
+    }
+    const int incl = warp_inclusive_scan(cnt);
+    const int total = __shfl_sync(0xffffffffu, incl, 31);
+    __syncwarp();
+    s_incl[lane] = incl;
+    s_base[lane] = base - (incl - cnt);  // record i of the concatenation, if it falls into this cell, is recs[s_base + i]
+    __syncwarp();
+    for (int i0 = 0; i0 < total; i0 += 128) {
+        tnb_bucket_rec r[4];
+        bool have[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int i = i0 + 32 * u + lane;
+            have[u] = i < total;
+            if (have[u]) {
+                int k = 0;  // first cell whose inclusive prefix exceeds i
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1)
+                    if (s_incl[k + step - 1] <= i) k += step;
+                r[u] = recs[s_base[k] + i];
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            if (i0 + 32 * u >= total) break;  // warp uniform
+            emit(have[u] && partner_test_once(q, r[u], colmask), have[u] ? r[u].v : 0);
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_pair_count_seg(const int *__restrict__ cand, int *__restrict__ cnt,
+                                                        const uint64_t *__restrict__ sig, const int2 *__restrict__ cells,
+                                                        const tnb_bucket_rec *__restrict__ recs, int dim, uint64_t colmask,
+                                                        int *__restrict__ pcount, int *__restrict__ pcache, int *__restrict__ long_list)
+{
+    __shared__ int s_keys[8][kCachedPartners], s_incl[8][32], s_base[8][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_cand = cnt[C_CAND], warps = gridDim.x * (blockDim.x >> 5);
+    for (int a = blockIdx.x * (blockDim.x >> 5) + warp; a < n_cand; a += warps) {
+        const PartnerQuery q = partner_query(cand[a], sig);
+        int found = 0;
+        stream_partners(q, cells, recs, dim, colmask, s_incl[warp], s_base[warp], [&](bool hit, int vb) {
+            const unsigned ball = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int pos = found + __popc(ball & ((1u << lane) - 1u));
+                if (pos < kCachedPartners) s_keys[warp][pos] = vb;
+            }
+            found += __popc(ball);
+        });
+        __syncwarp();
+        if (found > 0 && found <= kCachedPartners) {
+            // ascending partner number = the order unique(dim=0) leaves (subpoly.py:243-244)
+            const int key = warp_sort_asc(lane < found ? s_keys[warp][lane] : 0x7fffffff);
+            if (lane < found) pcache[(int64_t)a * kCachedPartners + lane] = key;
+        }
+        if (lane == 0) {
+            pcount[a] = found;
+            if (found > kCachedPartners) long_list[atomicAdd(cnt + C_LONG, 1)] = a;  // any order: each list has its own range
+        }
+        __syncwarp();
+    }
+}
+// connecting edges of the lists that fit the cache: a flat copy, one thread per (candidate, entry)
+__global__ void __launch_bounds__(256) k_pair_copy(const int *__restrict__ cand, const int *__restrict__ cnt, const int *__restrict__ pcount,
+                                                   const int *__restrict__ poff, const int *__restrict__ pcache, int2 *__restrict__ edges_out)
+{
+    const int64_t n = (int64_t)cnt[C_CAND] * kCachedPartners;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int a = (int)(t / kCachedPartners), i = (int)(t % kCachedPartners);
+        const int c = pcount[a];
+        if (i < c && c <= kCachedPartners) edges_out[poff[a] + i] = make_int2(cand[a], pcache[t]);
+    }
+}
+// a warp per long list: stream the neighbourhood again, keys into shared memory, bitonic sort, write
+__global__ void __launch_bounds__(kSortWarps * 32) k_pair_write_long_seg(const int *__restrict__ long_list, const int *__restrict__ cnt,
+                                                                         const int *__restrict__ cand, const uint64_t *__restrict__ sig,
+                                                                         const int2 *__restrict__ cells, const tnb_bucket_rec *__restrict__ recs,
+                                                                         int dim, uint64_t colmask, const int *__restrict__ pcount,
+                                                                         const int *__restrict__ poff, int2 *__restrict__ edges_out)
+{
+    __shared__ int s_keys[kSortWarps][kLongSortMax];
+    __shared__ int s_incl[kSortWarps][32], s_base[kSortWarps][32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_long = cnt[C_LONG];
+    for (int li = blockIdx.x * kSortWarps + warp; li < n_long; li += gridDim.x * kSortWarps) {
+        const int a = long_list[li], c = pcount[a], va = cand[a];
+        int2 *dst = edges_out + poff[a];
+        int *keys = s_keys[warp];
+        const bool in_smem = c <= kLongSortMax;
+        const PartnerQuery q = partner_query(va, sig);
+        int found = 0;
+        stream_partners(q, cells, recs, dim, colmask, s_incl[warp], s_base[warp], [&](bool hit, int vb) {
+            const unsigned ball = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                const int pos = found + __popc(ball & ((1u << lane) - 1u));
+                if (in_smem) keys[pos] = vb; else dst[pos].y = vb;
+            }
+            found += __popc(ball);
+        });
+        __syncwarp();
+        if (in_smem) {
+            int n = 32;
+            while (n < c) n <<= 1;
+            for (int i = c + lane; i < n; i += 32) keys[i] = 0x7fffffff;
+            __syncwarp();
+            for (int k = 2; k <= n; k <<= 1)
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = lane; i < n; i += 32) {
+                        const int p = i ^ j;
+                        if (p > i) {
+                            const int x = keys[i], y = keys[p];
+                            const bool up = (i & k) == 0;
+                            if ((x > y) == up) { keys[i] = y; keys[p] = x; }
+                        }
+                    }
+                    __syncwarp();
+                }
+            for (int i = lane; i < c; i += 32) dst[i] = make_int2(va, keys[i]);
+        } else {  // longer than the shared buffer (never seen): one lane sorts in place in HBM
+            if (lane == 0) {
+                thread_sort(&dst[0].y, c, 2);
+                for (int i = 0; i < c; ++i) dst[i].x = va;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // ---- pruning -------------------------------------------------------------------------------------
 // hyperplanes that separate the two ends of an edge (beyond eps on both sides), from the packed signs
 __device__ __forceinline__ uint64_t edge_cross_bits(const uint64_t *sig, int2 ed)
@@ -1361,7 +1557,7 @@ __global__ void k_set_parity(int *__restrict__ cnt, int vpar, int epar, int apar
 __global__ void k_clear_step_counters(int *__restrict__ cnt)
 {
     if (threadIdx.x < C_V) cnt[threadIdx.x] = 0;
-    if (threadIdx.x == 0) cnt[C_LONG] = 0;
+    if (threadIdx.x == 0) { cnt[C_LONG] = 0; cnt[C_RECS] = 0; }
 }
 
 
@@ -2154,6 +2350,11 @@ int steps_persistent_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh,
         list.prune[i] = h < H ? 1 : 0;
         prunes = prunes || h < H;
     }
+    if (c->bucket_mode == 2) {  // counts of an abandoned multi-launch step
+        TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
+        c->stamp = 0;
+    }
+    c->bucket_mode = 1;
     if (c->stamp > 0xffffffffu - (uint32_t)n_steps - 1u) {  // the generation stamps of this launch would wrap
         TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
         c->stamp = 0;
@@ -2234,6 +2435,11 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     }
     if (fused && halo) {
         if (part != 2) {
+            if (c->bucket_mode == 2) {
+                TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
+                c->stamp = 0;
+            }
+            c->bucket_mode = 1;
             c->stamp += 1;
             if (c->stamp == 0) {
                 TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
@@ -2297,7 +2503,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         TNB_LAUNCH_CHECK();
         // 1. edges the hyperplane crosses
         SplitCount sc{c->cedges(), c->cout_(), R, idx, eps};
-        if ((rc = compact(c->E, sc, ListEmit{c->split_list.p}, c->block_sums.p, cnt + C_RAW, s, cnt + C_E))) return rc;
+        if ((rc = compact_masked(c->E, sc, ListEmit{c->split_list.p}, c->block_sums.p, c->scan_mask.p, cnt + C_RAW, s, cnt + C_E))) return rc;
         if (attempt == 0) {  // most hyperplanes of a fitted network cross nothing: learn it now (subpoly.py:110-111)
             if ((rc = read_counters(c, s))) return rc;
             if (c->h_counters[C_RAW] == 0) return TNB_OK;
@@ -2332,24 +2538,21 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         }
         // 3. candidates for connecting edges: old vertices on the plane, then the new ones
         HitCount hc{c->cout_(), c->calive(), R, idx, eps};
-        if ((rc = compact(c->V, hc, ListEmit{c->cand.p}, c->block_sums.p, cnt + C_HIT, s, cnt + C_V))) return rc;
+        if ((rc = compact_masked(c->V, hc, ListEmit{c->cand.p}, c->block_sums.p, c->scan_mask.p, cnt + C_HIT, s, cnt + C_V))) return rc;
         const int64_t cand_ub = std::min<int64_t>(c->V + c->E, (int64_t)c->Vcap);
         k_fill_new_cands<<<grid_for(c->E, 256), 256, 0, s>>>(c->cand.p, cnt);
         TNB_LAUNCH_CHECK();
-        c->stamp += 1;
-        if (c->stamp == 0) {  // generation wrapped: clear the heads once
+        // contiguous cell segments (cells.cuh): the cell grid is all-zero between uses
+        if (c->bucket_mode != 0) {  // the linked-list form left its generation stamps there, or a failed step its counts
             TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
-            c->stamp = 1;
+            c->stamp = 0;
         }
-        {
-            unsigned g = grid_for(cand_ub, kThreads);
-            k_bucket_insert<<<g, kThreads, 0, s>>>(c->cand.p, cnt, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp);
-            TNB_LAUNCH_CHECK();
-            prof_begin(TNB_PROF_PAIRS, s);
-            k_pair_count<<<grid_for(cand_ub * 8, kThreads), kThreads, 0, s>>>(c->cand.p, cnt, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->pcache.p, g_long_lists ? c->remap.p : nullptr);
-            TNB_LAUNCH_CHECK();
-            prof_end(TNB_PROF_PAIRS, s, 0);
-        }
+        c->bucket_mode = 2;
+        if ((rc = cells_build(1, c->cand.p, cnt + C_CAND, cand_ub, c->csig(), (int2 *)c->head.p, c->cslot.p, c->next.p, cnt + C_RECS, c->cell_dim, s))) return rc;
+        prof_begin(TNB_PROF_PAIRS, s);
+        k_pair_count_seg<<<kSMs * 8, 256, 0, s>>>(c->cand.p, cnt, c->csig(), (const int2 *)c->head.p, c->next.p, c->cell_dim, colmask, c->pcount.p, c->pcache.p, c->remap.p);
+        TNB_LAUNCH_CHECK();
+        prof_end(TNB_PROF_PAIRS, s, 0);
         if ((rc = compact(cand_ub, ArrayCount{c->pcount.p}, OffsetEmit{c->poff.p}, c->block_sums.p, cnt + C_PAIRS, s, cnt + C_CAND))) return rc;
       }
         // ---- the one host sync of the step ----
@@ -2384,16 +2587,18 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     cnt = c->counters.p;
     if (P > 0) {
         prof_begin(TNB_PROF_PAIRS, s);
-        k_pair_write<<<grid_for(n_cand, kThreads), kThreads, 0, s>>>(c->cand.p, n_cand, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S, c->pcache.p, g_long_lists ? 1 : 0);
+        k_pair_copy<<<grid_for((int64_t)n_cand * kCachedPartners, 256), 256, 0, s>>>(c->cand.p, cnt, c->pcount.p, c->poff.p, c->pcache.p, c->cedges() + E0 + S);
         TNB_LAUNCH_CHECK();
         const int n_long = c->h_counters[C_LONG];
-        if (g_long_lists && n_long > 0) {
-            k_pair_write_long<<<(unsigned)std::min<int64_t>((n_long + kSortWarps - 1) / kSortWarps, kSMs * 4), kSortWarps * 32, 0, s>>>(
-                c->remap.p, cnt, c->cand.p, c->csig(), c->head.p, c->next.p, c->cell_dim, c->stamp, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S);
+        if (n_long > 0) {
+            k_pair_write_long_seg<<<(unsigned)std::min<int64_t>((n_long + kSortWarps - 1) / kSortWarps, kSMs * 4), kSortWarps * 32, 0, s>>>(
+                c->remap.p, cnt, c->cand.p, c->csig(), (const int2 *)c->head.p, c->next.p, c->cell_dim, colmask, c->pcount.p, c->poff.p, c->cedges() + E0 + S);
             TNB_LAUNCH_CHECK();
         }
         prof_end(TNB_PROF_PAIRS, s, n_cand, (int64_t)n_cand * 28 + (int64_t)P * 8);
     }
+    if ((rc = cells_clear(1, nullptr, n_cand, (int2 *)c->head.p, c->cslot.p, s))) return rc;
+    c->bucket_mode = 0;
     c->V = V0 + S;
     c->E = (int64_t)E0 + S + P;
 

@@ -68,10 +68,13 @@ struct tnb_complex {
     tnb::DevBuf<int> poff;          // [Vcap]   exclusive scan of pcount
     tnb::DevBuf<int> pcache;        // [32*Vcap] first partners of each candidate, left by the count pass
     tnb::DevBuf<tnb_bucket_rec> next;  // [8*Vcap] bucket chains
-    tnb::DevBuf<unsigned long long> head;  // [n_cells] (stamp << 32 | record)
+    tnb::DevBuf<unsigned long long> head;  // [n_cells] (stamp << 32 | record); the contiguous form (cells.cuh) reads it as int2 {count, base}
+    tnb::DevBuf<int2> cslot;        // [8*Vcap] contiguous form: {cell, index in the cell's segment} of every (candidate, cell)
+    int bucket_mode = 0;            // what `head` holds: 0 all-zero, 1 generation stamps (linked lists), 2 counts of a step in flight
     tnb::DevBuf<int> used[2];       // [Vcap]   vertex referenced by a kept edge; used[acur] = liveness of the current complex
     tnb::DevBuf<int> remap;         // [Vcap]
     tnb::DevBuf<int> block_sums;    // [kScanMaxBlocks]
+    tnb::DevBuf<uint32_t> scan_mask;  // one bit per edge / vertex: masked compactions (scan.cuh)
     tnb::DevBuf<int> counters;      // [16] device counters
     tnb::DevBuf<unsigned long long> bytes;  // [2] algorithmic bytes accumulated by the fused kernels
     int *h_counters = nullptr;      // pinned mirror (per thread, not owned)

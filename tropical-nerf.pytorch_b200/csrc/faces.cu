@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "complex.cuh"
+#include "cells.cuh"
 #include "net_eval.cuh"
 #include "scan.cuh"
 #include "sort.cuh"
@@ -40,10 +41,10 @@ namespace tnb {
 
 constexpr int kThreads = 128;
 constexpr int kMaxRow = 8192;      // hard limit of vertices per face row (sizes the HBM row scratch)
-constexpr int kSmemRowStride = 64;  // rows up to this length are built in shared memory (64 KB per CTA)
+constexpr int kSmemRowStride = 16;  // rows up to this length are built in shared memory (16 KB per CTA: a dozen CTAs per SM)
 constexpr int kMaxZeros = 5;  // 2^5 regions = one per lane
 constexpr int kSortLocal = 32;  // face rows up to this length are angle-sorted in registers / local memory
-enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_NUM = 16 };
+enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_RECS, F_NLONG, F_NUM = 16 };
 
 // ---- surface skeleton -----------------------------------------------------------------------------
 __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
@@ -174,29 +175,6 @@ __device__ __forceinline__ int zero_count(uint64_t pos, uint64_t neg, uint64_t g
     return __popcll(~(pos | neg) & colmask) + (3 - grid_mask(g, 0) - grid_mask(g, 1) - grid_mask(g, 2));
 }
 
-__global__ void k_face_bucket_insert(int64_t V, const uint64_t *__restrict__ sig, unsigned long long *__restrict__ head,
-                                     tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp)
-{
-    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
-        tnb_bucket_rec r;
-        r.v = (int)v;
-        r.pos = sig[3 * v];
-        r.neg = sig[3 * v + 1];
-        r.grd = sig[3 * v + 2];
-        const Box b = box_of(r.grd);
-        int slot = 0;
-        for (int cx = b.lo[0]; cx <= b.hi[0]; ++cx)
-            for (int cy = b.lo[1]; cy <= b.hi[1]; ++cy)
-                for (int cz = b.lo[2]; cz <= b.hi[2]; ++cz, ++slot) {
-                    const int rec = (int)v * 8 + slot;
-                    const unsigned long long mine = ((unsigned long long)stamp << 32) | (unsigned)rec;
-                    const unsigned long long old = atomicExch(head + cell_of(cx, cy, cz, dim), mine);
-                    r.next = ((uint32_t)(old >> 32) == stamp) ? (int)(uint32_t)old : -1;
-                    next[rec] = r;
-                }
-    }
-}
-
 // One warp per surface vertex a; lane q builds the row of a's q-th adjacent region.
 // mode 0: rows_per_vertex[a] = bit mask of the regions (lanes) whose row a leads and keeps (distinct rows of
 //         >= 3 vertices; their count is the popcount), max width.  mode 1 walks the buckets again only for
@@ -216,15 +194,22 @@ __device__ __forceinline__ int row_compare(const unsigned long long *x, int nx, 
 }
 
 __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint64_t *__restrict__ sig,
-                                                          const unsigned long long *__restrict__ head,
-                                                          const tnb_bucket_rec *__restrict__ next, int dim, uint32_t stamp,
+                                                          const int2 *__restrict__ cells,
+                                                          const tnb_bucket_rec *__restrict__ recs, int dim,
                                                           uint64_t colmask, int mode, int stride,
                                                           unsigned long long *__restrict__ scratch,
                                                           int *__restrict__ rows_per_vertex,
                                                           const int *__restrict__ row_off, int *__restrict__ rows,
                                                           int *__restrict__ row_cnt, int W, int *__restrict__ counters,
-                                                          int cell_lo, int cell_hi)
+                                                          int cell_lo, int cell_hi, const int *__restrict__ list, int n_list,
+                                                          unsigned char *__restrict__ is_long, int *__restrict__ long_list)
 {
+    // Two passes share this kernel.  The FAST pass (list == nullptr) takes every vertex, builds rows of up to
+    // `stride` (= kSmemRowStride) keys per lane in shared memory -- small enough for a dozen CTAs per SM: the
+    // kernel is a chain of dependent L2 round trips per vertex, so what it needs is warps in flight -- and files
+    // a vertex one of whose rows is longer (the coincident-vertex clusters of the reference's chunk-overlap
+    // duplicates: rows of hundreds of vertices) in long_list.  The LONG pass (list != nullptr) takes those
+    // vertices only, rows in an HBM scratch of the longest row seen.
     extern __shared__ unsigned long long s_rows[];  // [kThreads][stride] unless scratch is used
     __shared__ int s_cnt[kThreads];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -232,7 +217,10 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                                        : s_rows + (size_t)warp * 32 * stride;
     unsigned long long *mine = base + (size_t)lane * stride;
     int *wcnt = s_cnt + warp * 32;
-    for (int64_t a = (int64_t)blockIdx.x * (kThreads / 32) + warp; a < V; a += (int64_t)gridDim.x * (kThreads / 32)) {
+    const int64_t n_items = list ? n_list : V;
+    for (int64_t item = (int64_t)blockIdx.x * (kThreads / 32) + warp; item < n_items; item += (int64_t)gridDim.x * (kThreads / 32)) {
+        const int64_t a = list ? list[item] : item;
+        if (!list && mode == 1 && is_long[a]) continue;  // the long pass writes this vertex's rows
         const uint64_t pa = sig[3 * a], na = sig[3 * a + 1], ga = sig[3 * a + 2];
         const uint64_t za = ~(pa | na) & colmask;
         const int gz = 3 - grid_mask(ga, 0) - grid_mask(ga, 1) - grid_mask(ga, 2);
@@ -259,35 +247,52 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
             const bool mine_cell = cell[0] >= cell_lo && cell[0] <= cell_hi;
             // collect the region's vertices ordered by (zero count, vertex number): the row
             // order r_idx_as_tensor builds from regions_to_vertices' group-by-zero-count output
-            const unsigned long long h = head[cell_of(cell[0], cell[1], cell[2], dim)];
+            const int2 seg = cells[cell_of(cell[0], cell[1], cell[2], dim)];  // {records, first record} of the region's cell
             const unsigned long long my_key = ((unsigned long long)ka << 32) | (unsigned)a;
             bool led_by_other = false;
-            if (mine_cell && (uint32_t)(h >> 32) == stamp) {
-                for (int rec = (int)(uint32_t)h; rec >= 0;) {
-                    const tnb_bucket_rec r = next[rec];
-                    rec = r.next;
-                    const int b = r.v;
-                    const uint64_t pb = r.pos, nb = r.neg, gb = r.grd;
-                    if ((pb & ~pat & colmask) || (nb & pat)) continue;  // a nonzero sign disagrees
-                    const Box bb = box_of(gb);
-                    bool in = true;
+            if (mine_cell) {
+                // the cell's segment is contiguous (cells.cuh): four independent 32-byte loads in flight per lane
+                for (int i0 = 0; i0 < seg.x && !led_by_other; i0 += 4) {
+                    tnb_bucket_rec r4[4];
 #pragma unroll
-                    for (int d = 0; d < 3; ++d) in = in && cell[d] >= bb.lo[d] && cell[d] <= bb.hi[d];
-                    if (!in) continue;
-                    const unsigned long long key = ((unsigned long long)zero_count(pb, nb, gb, colmask) << 32) | (unsigned)b;
-                    if (key < my_key) { led_by_other = true; break; }  // that vertex emits this row, not a
-                    if (cnt < stride) mine[cnt] = key;
-                    ++cnt;
+                    for (int k = 0; k < 4; ++k)
+                        if (i0 + k < seg.x) r4[k] = recs[seg.y + i0 + k];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (i0 + k >= seg.x || led_by_other) continue;
+                        const int b = r4[k].v;
+                        const uint64_t pb = r4[k].pos, nb = r4[k].neg, gb = r4[k].grd;
+                        if ((pb & ~pat & colmask) || (nb & pat)) continue;  // a nonzero sign disagrees
+                        const Box bb = box_of(gb);
+                        bool in = true;
+#pragma unroll
+                        for (int d = 0; d < 3; ++d) in = in && cell[d] >= bb.lo[d] && cell[d] <= bb.hi[d];
+                        if (!in) continue;
+                        const unsigned long long key = ((unsigned long long)zero_count(pb, nb, gb, colmask) << 32) | (unsigned)b;
+                        if (key < my_key) { led_by_other = true; continue; }  // that vertex emits this row, not a
+                        if (cnt < stride) mine[cnt] = key;
+                        ++cnt;
+                    }
                 }
             }
             if (led_by_other) cnt = 0;
             if (cnt <= stride) thread_sort(mine, cnt);
-            if (cnt > stride) {
-                atomicOr(counters + F_ERR_ROW, 1);
-                atomicMax(counters + F_MAXCNT, cnt);
-                cnt = 0;
-            }
             lead = cnt >= 3;  // every surviving row starts with a itself
+        }
+        {   // a row that does not fit: the whole vertex goes to the long pass (warp uniform)
+            const bool over = cnt > stride;
+            if (over) atomicMax(counters + F_MAXCNT, cnt);
+            if (__any_sync(0xffffffffu, over)) {
+                if (lane == 0) {
+                    if (list) atomicOr(counters + F_ERR_ROW, 1);  // the long pass is sized to the longest row: cannot happen
+                    else if (mode == 0) {
+                        is_long[a] = 1;
+                        rows_per_vertex[a] = 0;
+                        long_list[atomicAdd(counters + F_NLONG, 1)] = (int)a;
+                    }
+                }
+                continue;
+            }
         }
         wcnt[lane] = cnt;
         __syncwarp();
@@ -627,65 +632,59 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     DevBuf<uint64_t> sig;
     DevBuf<tnb_bucket_rec> next;
     DevBuf<int> rows_per_vertex, row_off;
-    DevBuf<unsigned long long> head;
+    DevBuf<unsigned long long> head;   // read as int2 {records, first record} per cell (cells.cuh)
+    DevBuf<int2> cslot;
     TNB_CUDA(sig.reserve((size_t)Vs * 3));
     TNB_CUDA(next.reserve((size_t)Vs * 8));
+    TNB_CUDA(cslot.reserve((size_t)Vs * 8));
     TNB_CUDA(rows_per_vertex.reserve((size_t)Vs));
     TNB_CUDA(row_off.reserve((size_t)Vs));
     const int dim = nm.n_marks + 2;
     const int64_t n_cells = (int64_t)dim * dim * dim;
     TNB_CUDA(head.reserve((size_t)n_cells));
     TNB_CUDA(cudaMemsetAsync(head.p, 0, (size_t)n_cells * sizeof(unsigned long long), s));
-    const uint32_t stamp = 1;
     const uint64_t colmask = (1ull << (R - 1)) - 1ull;  // m_rgn[:, :-1], subpoly.py:611
     k_surface_sig<<<grid_for(Vs, kThreads), kThreads, 0, s>>>(nm, m->vert.p, m->out.p, Vs, eps, sig.p);
     TNB_LAUNCH_CHECK();
-    k_face_bucket_insert<<<grid_for(Vs, 256), 256, 0, s>>>(Vs, sig.p, head.p, next.p, dim, stamp);
-    TNB_LAUNCH_CHECK();
-    unsigned gw = grid_for(Vs, kThreads / 32);
-    int stride = kSmemRowStride;
+    TNB_CUDA(cudaMemsetAsync(counters.p + F_RECS, 0, sizeof(int), s));
+    if ((rc = cells_build(8, nullptr, nullptr, Vs, sig.p, (int2 *)head.p, cslot.p, next.p, counters.p + F_RECS, dim, s))) return rc;
+    const unsigned gw = grid_for(Vs, kThreads / 32);
+    const size_t rows_smem = (size_t)kThreads * kSmemRowStride * sizeof(unsigned long long);
     DevBuf<unsigned long long> scratch;
-    size_t rows_smem = (size_t)kThreads * stride * sizeof(unsigned long long);
-    // the previous extraction of this network (or of one on the same marks grid) needed rows in
-    // HBM: start there (saves the failed pass)
-    static int hint_marks = 0, hint_stride = 0;
-    const int hint = std::max(net->face_row_hint, hint_marks == nm.n_marks ? hint_stride : 0);
-    if (hint > kSmemRowStride) {
-        stride = hint;
-        gw = std::min<unsigned>(gw, kSMs * 4);
-        TNB_CUDA(scratch.reserve((size_t)gw * kThreads * stride));
-    }
-    {
-        static bool attr_set = false;
-        if (!attr_set) {
-            TNB_CUDA(cudaFuncSetAttribute(k_region_rows, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rows_smem));
-            attr_set = true;
-        }
-    }
-    for (int attempt = 0;; ++attempt) {
-        prof_begin(TNB_PROF_FACE_ROWS, s);
-        k_region_rows<<<gw, kThreads, scratch.p ? 0 : rows_smem, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 0, stride,
-                                                                       scratch.p, rows_per_vertex.p, nullptr, nullptr, nullptr, 0,
-                                                                       counters.p, cell_lo, cell_hi);
-        TNB_LAUNCH_CHECK();
-        prof_end(TNB_PROF_FACE_ROWS, s, Vs, Vs * 28);
-        if ((rc = compact(Vs, PopcCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
-        if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
-        if (h[F_ERR_ZEROS]) { set_error("a surface vertex lies on more than 5 planes: more than 32 adjacent regions"); return TNB_ERR_UNSUPPORTED; }
-        if (!h[F_ERR_ROW]) break;
-        // a face row did not fit: retry with rows in HBM, sized to the longest row seen
-        if (attempt > 1 || h[F_MAXCNT] > kMaxRow) {
+    DevBuf<unsigned char> is_long;
+    DevBuf<int> long_list;
+    TNB_CUDA(is_long.reserve((size_t)Vs));
+    TNB_CUDA(long_list.reserve((size_t)Vs));
+    TNB_CUDA(cudaMemsetAsync(is_long.p, 0, (size_t)Vs, s));
+    // fast pass: every vertex, rows in shared memory
+    prof_begin(TNB_PROF_FACE_ROWS, s);
+    k_region_rows<<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, next.p, dim, colmask, 0, kSmemRowStride, nullptr,
+                                                  rows_per_vertex.p, nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi,
+                                                  nullptr, 0, is_long.p, long_list.p);
+    TNB_LAUNCH_CHECK();
+    prof_end(TNB_PROF_FACE_ROWS, s, Vs, Vs * 28);
+    if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
+    if (h[F_ERR_ZEROS]) { set_error("a surface vertex lies on more than 5 planes: more than 32 adjacent regions"); return TNB_ERR_UNSUPPORTED; }
+    const int n_long = h[F_NLONG];
+    int stride = 0;
+    unsigned gl = 0;
+    if (n_long > 0) {  // long pass: the vertices with a row that did not fit, rows in HBM, sized to the longest row seen
+        if (h[F_MAXCNT] > kMaxRow) {
             set_error("a face has more than " + std::to_string(kMaxRow) + " vertices (" + std::to_string(h[F_MAXCNT]) + ")");
             return TNB_ERR_UNSUPPORTED;
         }
-        stride = (h[F_MAXCNT] + 7) / 8 * 8;  // exactly the longest row: the retry cannot overflow
-        net->face_row_hint = stride;
-        hint_marks = nm.n_marks;
-        hint_stride = stride;
-        gw = std::min<unsigned>(gw, kSMs * 4);
-        TNB_CUDA(scratch.reserve((size_t)gw * kThreads * stride));
-        TNB_CUDA(cudaMemsetAsync(counters.p + F_ROWS, 0, (F_NUM - F_ROWS) * sizeof(int), s));
+        stride = (h[F_MAXCNT] + 7) / 8 * 8;
+        gl = std::min<unsigned>(grid_for(n_long, kThreads / 32), kSMs * 4);
+        TNB_CUDA(scratch.reserve((size_t)gl * kThreads * stride));
+        prof_begin(TNB_PROF_FACE_ROWS, s);
+        k_region_rows<<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, next.p, dim, colmask, 0, stride, scratch.p, rows_per_vertex.p,
+                                              nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr);
+        TNB_LAUNCH_CHECK();
+        prof_end(TNB_PROF_FACE_ROWS, s, n_long, (int64_t)n_long * 28);
     }
+    if ((rc = compact(Vs, PopcCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
+    if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
+    if (h[F_ERR_ROW]) { set_error("face rows: a row outgrew the scratch sized for it"); return TNB_ERR_CAPACITY; }
     const int64_t P = h[F_ROWS];
     const int W = h[F_WIDTH];
     m->P = P;
@@ -693,9 +692,17 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     if (P == 0) return TNB_OK;
     TNB_CUDA(m->poly.reserve((size_t)P * W));
     TNB_CUDA(m->pcnt.reserve((size_t)P));
-    k_region_rows<<<gw, kThreads, scratch.p ? 0 : rows_smem, s>>>(Vs, sig.p, head.p, next.p, dim, stamp, colmask, 1, stride, scratch.p,
-                                                                   rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi);
+    prof_begin(TNB_PROF_FACE_ROWS, s);
+    k_region_rows<<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, next.p, dim, colmask, 1, kSmemRowStride, nullptr,
+                                                  rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi,
+                                                  nullptr, 0, is_long.p, nullptr);
     TNB_LAUNCH_CHECK();
+    if (n_long > 0) {
+        k_region_rows<<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, next.p, dim, colmask, 1, stride, scratch.p, rows_per_vertex.p,
+                                              row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr);
+        TNB_LAUNCH_CHECK();
+    }
+    prof_end(TNB_PROF_FACE_ROWS, s, 0, 0);
     {
         unsigned g = grid_for(P, kThreads);
         DevBuf<unsigned long long> score_scratch;  // one segment per long row (their total was counted with the rows)

@@ -157,8 +157,8 @@ __device__ __forceinline__ float2 level_dx(const float2 v[8], const float frac[3
             corner |= bit << dim;
         }
         const float2 vl = v[corner], vr = v[corner | (1 << d)];
-        dl.x = __fmaf_rn(w, vr.x - vl.x, dl.x);
-        dl.y = __fmaf_rn(w, vr.y - vl.y, dl.y);
+        // both features at once: packed subtract (a + (-b) IS a - b in IEEE arithmetic) and packed FMA
+        dl = __ffma2_rn(make_float2(w, w), __fadd2_rn(vr, make_float2(-vl.x, -vl.y)), dl);
     }
     return dl;
 }
@@ -207,6 +207,165 @@ __device__ __forceinline__ void encode_level_grad(const NetMeta &n, int l, const
         const float2 dl = level_dx(v, frac, lv.scale, d);
         acc[d] = __fmaf_rn(g0, dl.x, acc[d]);
         acc[d] = __fmaf_rn(g1, dl.y, acc[d]);
+    }
+}
+
+// ---- two points per thread (the lattice sweeps) ---------------------------------------------------
+// Blackwell's packed FFMA2 (fma.rn.f32x2) does two independent IEEE binary32 FMAs per issue slot, and it
+// takes a SCALAR second operand that is broadcast to both halves.  With two lattice points per thread,
+// a pair = (value at point 0, value at point 1), and the MLP weight -- a uniform-register / constant
+// operand -- as the broadcast scalar, every FMA of the network advances both points at once, each half
+// bit-identical to the __fmaf_rn chain of the one-point code (and of oracle/trinet_ref.c).  The sweeps
+// are fp32-issue bound: this halves their dominant instruction class.
+template <class C>
+__device__ __forceinline__ void encode_pair(const NetMeta &n, const float xp0[3], const float xp1[3], float2 act[C::kMaxW])
+{
+#pragma unroll(C::kUnroll)
+    for (int l = 0; l < C::kMaxL; ++l) {
+        if (l < C::L(n)) {
+            uint32_t cell[3];
+            float frac[3];
+            const float2 f0 = encode_level(n, l, xp0, cell, frac);
+            const float2 f1 = encode_level(n, l, xp1, cell, frac);
+            act[2 * l] = make_float2(f0.x, f1.x);
+            act[2 * l + 1] = make_float2(f0.y, f1.y);
+        }
+    }
+}
+// one nn.Linear for both points: nxt[j] = b_j + sum_c act[c] * W[j][c], c ascending (the oracle's order)
+template <class C>
+__device__ __forceinline__ void layer_pair(const NetMeta &n, int base, int ni, int no, const float2 act[C::kMaxW], float2 nxt[C::kMaxH])
+{
+#pragma unroll(C::kUnroll)
+    for (int j = 0; j < C::kMaxH; ++j) {
+        if (j < no) {
+            const float b = C::w(n, base + no * ni + j);
+            float2 acc = make_float2(b, b);
+#pragma unroll(C::kUnroll)
+            for (int c = 0; c < C::kMaxW; ++c)
+                if (c < ni) {
+                    const float w = C::w(n, base + j * ni + c);
+                    acc = __ffma2_rn(act[c], make_float2(w, w), acc);
+                }
+            nxt[j] = acc;
+        }
+    }
+}
+// forward<C> for two points: pre[(i*maxH)+j] = pre-activation j of hidden layer i, o[k] = last layer
+template <class C>
+__device__ __forceinline__ void forward_pair(const NetMeta &n, const float xp0[3], const float xp1[3], float2 *__restrict__ pre, float2 o[2])
+{
+    float2 act[C::kMaxW];
+    encode_pair<C>(n, xp0, xp1, act);
+    int base = 0;
+#pragma unroll(C::kUnroll)
+    for (int i = 0; i < C::kMaxLin; ++i) {
+        if (i < C::NLIN(n)) {
+            const int ni = C::nin(n, i), no = C::nout(n, i);
+            float2 nxt[C::kMaxH];
+            layer_pair<C>(n, base, ni, no, act, nxt);
+            if (i == C::NLIN(n) - 1) {
+                o[0] = nxt[0];
+                o[1] = nxt[1];
+            } else {
+#pragma unroll(C::kUnroll)
+                for (int j = 0; j < C::kMaxH; ++j)
+                    if (j < no) {
+                        pre[i * C::kMaxH + j] = nxt[j];
+                        act[j] = make_float2(nxt[j].x > 0.0f ? nxt[j].x : 0.0f, nxt[j].y > 0.0f ? nxt[j].y : 0.0f);
+                    }
+            }
+            base += no * ni + no;
+        }
+    }
+}
+// sdf_grad<C> for two points: t[k] = tanh(o1 - o0), grad[k][3] = d t / d x of point k
+template <class C>
+__device__ __forceinline__ void sdf_grad_pair(const NetMeta &n, const float x0[3], const float x1[3], float t[2], float grad[2][3])
+{
+    float xp0[3], xp1[3];
+    preprocess(n, x0, xp0);
+    preprocess(n, x1, xp1);
+    uint64_t mask0[C::kMaxLin], mask1[C::kMaxLin];
+    float2 o[2];
+    {
+        float2 act[C::kMaxW];
+        encode_pair<C>(n, xp0, xp1, act);
+        int base = 0;
+#pragma unroll(C::kUnroll)
+        for (int i = 0; i < C::kMaxLin; ++i) {
+            if (i < C::NLIN(n)) {
+                const int ni = C::nin(n, i), no = C::nout(n, i);
+                float2 nxt[C::kMaxH];
+                layer_pair<C>(n, base, ni, no, act, nxt);
+                if (i == C::NLIN(n) - 1) {
+                    o[0] = nxt[0];
+                    o[1] = nxt[1];
+                } else {
+                    uint64_t m0 = 0, m1 = 0;
+#pragma unroll(C::kUnroll)
+                    for (int j = 0; j < C::kMaxH; ++j)
+                        if (j < no) {
+                            const bool on0 = nxt[j].x > 0.0f, on1 = nxt[j].y > 0.0f;
+                            m0 |= (uint64_t)on0 << j;
+                            m1 |= (uint64_t)on1 << j;
+                            act[j] = make_float2(on0 ? nxt[j].x : 0.0f, on1 ? nxt[j].y : 0.0f);
+                        }
+                    mask0[i] = m0;
+                    mask1[i] = m1;
+                }
+                base += no * ni + no;
+            }
+        }
+    }
+    t[0] = det_tanhf(o[1].x - o[0].x);
+    t[1] = det_tanhf(o[1].y - o[0].y);
+    const float gs0 = 1.0f - t[0] * t[0], gs1 = 1.0f - t[1] * t[1];
+    float2 g_out[C::kMaxW], g_in[C::kMaxW];
+    g_out[0] = make_float2(-gs0, -gs1);
+    g_out[1] = make_float2(gs0, gs1);
+    int base[C::kMaxLin];
+    {
+        int b = 0;
+#pragma unroll(C::kUnroll)
+        for (int i = 0; i < C::kMaxLin; ++i)
+            if (i < C::NLIN(n)) { base[i] = b; b += C::nout(n, i) * C::nin(n, i) + C::nout(n, i); }
+    }
+#pragma unroll(C::kUnroll)
+    for (int k = C::kMaxLin - 1; k >= 0; --k) {
+        if (k < C::NLIN(n)) {
+            const int ni = C::nin(n, k), no = C::nout(n, k);
+#pragma unroll(C::kUnroll)
+            for (int c = 0; c < C::kMaxW; ++c) {
+                if (c < ni) {
+                    float2 acc = make_float2(0.0f, 0.0f);
+#pragma unroll(C::kUnroll)
+                    for (int j = 0; j < C::kMaxH; ++j)
+                        if (j < no) {
+                            const float w = C::w(n, base[k] + j * ni + c);
+                            acc = __ffma2_rn(make_float2(w, w), g_out[j], acc);
+                        }
+                    g_in[c] = acc;
+                }
+            }
+            if (k > 0) {
+#pragma unroll(C::kUnroll)
+                for (int c = 0; c < C::kMaxH; ++c)
+                    if (c < ni) g_out[c] = make_float2(((mask0[k - 1] >> c) & 1) ? g_in[c].x : 0.0f, ((mask1[k - 1] >> c) & 1) ? g_in[c].y : 0.0f);
+            }
+        }
+    }
+    float acc0[3] = {0.0f, 0.0f, 0.0f}, acc1[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll(C::kUnroll)
+    for (int l = 0; l < C::kMaxL; ++l)
+        if (l < C::L(n)) {
+            encode_level_grad(n, l, xp0, g_in[2 * l].x, g_in[2 * l + 1].x, acc0);
+            encode_level_grad(n, l, xp1, g_in[2 * l].y, g_in[2 * l + 1].y, acc1);
+        }
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        grad[0][d] = div_2s(n, acc0[d]);
+        grad[1][d] = div_2s(n, acc1[d]);
     }
 }
 
@@ -315,6 +474,44 @@ struct SignWords {
     __device__ __forceinline__ uint64_t pos() const { return ((uint64_t)phi << 32) | plo; }
     __device__ __forceinline__ uint64_t neg() const { return ((uint64_t)nhi << 32) | nlo; }
 };
+
+// outputs_row + the packed signs of the row straight from the registers (tolerance eps_sign), the grid
+// coordinates, and `big`: bit c set <=> |row[c]| > eps_big
+template <class C>
+__device__ __forceinline__ void outputs_row_packed(const NetMeta &n, const float x[3], float *__restrict__ row, float eps_sign,
+                                                   float eps_big, float xp[3], uint64_t &pos, uint64_t &neg, uint64_t &big)
+{
+    preprocess(n, x, xp);
+    float pre[(C::kMaxLin - 1) * C::kMaxH];
+    float o[2];
+    forward<C>(n, xp, pre, o);
+    const int H = C::H(n), NL = C::NLIN(n);
+    SignWords w;
+    uint32_t blo = 0, bhi = 0;
+#pragma unroll(C::kUnroll)
+    for (int i = 0; i < C::kMaxLin - 1; ++i)
+        if (i < NL - 1) {
+#pragma unroll(C::kUnroll)
+            for (int j = 0; j < C::kMaxH; ++j)
+                if (j < H) {
+                    const float v = pre[i * C::kMaxH + j];
+                    const int c = i * H + j;
+                    row[c] = v;
+                    w.add(v, eps_sign, c);
+                    if (fabsf(v) > eps_big) { if (c < 32) blo |= 1u << (c & 31); else bhi |= 1u << (c & 31); }
+                }
+        }
+    {
+        const float v = o[1] - o[0];
+        const int c = (NL - 1) * H;
+        row[c] = v;
+        w.add(v, eps_sign, c);
+        if (fabsf(v) > eps_big) { if (c < 32) blo |= 1u << (c & 31); else bhi |= 1u << (c & 31); }
+    }
+    pos = w.pos();
+    neg = w.neg();
+    big = ((uint64_t)bhi << 32) | blo;
+}
 
 // sign bits of a row of outputs (model.py:97-98)
 __device__ __forceinline__ void pack_signs(const float *__restrict__ row, int R, float eps,

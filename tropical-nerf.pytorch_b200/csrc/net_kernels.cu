@@ -187,6 +187,40 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_signs(const __grid_consta
     const int64_t first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
     if (first >= count) return;
     Lattice3 at(first, ls, nx, ny);
+    if constexpr (C::kFixed) {
+        // two lattice points per trip (i and i + stride): the MLP of both in packed FFMA2s (net_eval.cuh)
+        for (int64_t i = first; i < count; i += 2 * stride) {
+            const bool two = i + stride < count;
+            float p0[3] = {__fmaf_rn((float)at.ix, step.x, lo.x), __fmaf_rn((float)at.iy, step.y, lo.y), __fmaf_rn((float)at.iz, step.z, lo.z)};
+            at.advance();
+            float p1[3] = {p0[0], p0[1], p0[2]};  // no second point: the first one twice, not stored
+            if (two) { p1[0] = __fmaf_rn((float)at.ix, step.x, lo.x); p1[1] = __fmaf_rn((float)at.iy, step.y, lo.y); p1[2] = __fmaf_rn((float)at.iz, step.z, lo.z); }
+            at.advance();
+            float xp0[3], xp1[3];
+            preprocess(n, p0, xp0);
+            preprocess(n, p1, xp1);
+            float2 pre[(C::kMaxLin - 1) * C::kMaxH];
+            float2 o[2];
+            forward_pair<C>(n, xp0, xp1, pre, o);
+            SignWords w0, w1;
+            const int H = C::H(n), NL = C::NLIN(n);
+#pragma unroll(C::kUnroll)
+            for (int l = 0; l < C::kMaxLin - 1; ++l)
+                if (l < NL - 1) {
+#pragma unroll(C::kUnroll)
+                    for (int j = 0; j < C::kMaxH; ++j)
+                        if (j < H) {
+                            w0.add(pre[l * C::kMaxH + j].x, eps, l * H + j);
+                            w1.add(pre[l * C::kMaxH + j].y, eps, l * H + j);
+                        }
+                }
+            w0.add(o[1].x - o[0].x, eps, (NL - 1) * H);
+            w1.add(o[1].y - o[0].y, eps, (NL - 1) * H);
+            packed[i] = make_ulonglong2(w0.pos(), w0.neg());  // x fastest: coalesced 16 B stores
+            if (two) packed[i + stride] = make_ulonglong2(w1.pos(), w1.neg());
+        }
+        return;
+    }
     for (int64_t i = first; i < count; i += stride, at.advance()) {
         // x is the lane axis (table is x-fastest); the output index stays z-fastest
         const int ix = at.ix, iy = at.iy, iz = at.iz;

@@ -261,9 +261,10 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, const in
 // count(i) again.  Slices are warp aligned, so a warp's ballot is exactly one mask word.
 template <class Count>
 __global__ void __launch_bounds__(kScanThreads) k_scan_count_mask(int64_t n, Count count, int *__restrict__ block_sums,
-                                                                  uint32_t *__restrict__ mask)
+                                                                  uint32_t *__restrict__ mask, const int *__restrict__ n_dev = nullptr)
 {
     constexpr int NW = kScanThreads / 32;
+    if (n_dev) n = *n_dev;
     int64_t begin, end;
     scan_slice(n, begin, end);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -289,9 +290,11 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count_mask(int64_t n, Cou
 // Same slices, same order: emit(i, position, 1) for every set bit, ascending i.
 template <class Emit>
 __global__ void __launch_bounds__(kScanThreads) k_scan_write_mask(int64_t n, const uint32_t *__restrict__ mask, Emit emit,
-                                                                  const int *__restrict__ block_sums, int *__restrict__ total)
+                                                                  const int *__restrict__ block_sums, int *__restrict__ total,
+                                                                  const int *__restrict__ n_dev = nullptr)
 {
     constexpr int NT = kScanThreads, NW = NT / 32;
+    if (n_dev) n = *n_dev;
     __shared__ int s_warp[NW];
     __shared__ int s_excl[32];
     __shared__ int s_base, s_tile;
@@ -370,6 +373,29 @@ inline int compact(int64_t n, Count count, Emit emit, int *block_sums, int *d_to
     k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, n_dev, count, block_sums);
     TNB_LAUNCH_CHECK();
     k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, n_dev, count, emit, block_sums, d_total);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+
+
+// The same compaction through a bit mask: the count pass evaluates count(i) ONCE and leaves one bit per
+// item, the write pass takes 32 items per thread from the bits.  For sparse selections whose test is a
+// gather (edges crossed by a plane, vertices hit by it: a few percent pass) the second evaluation and
+// the per-256-item barriers of the generic write pass were most of the cost.
+// `mask` must hold (n + 31) / 32 + kScanMaxBlocks words.
+template <class Count, class Emit>
+inline int compact_masked(int64_t n, Count count, Emit emit, int *block_sums, uint32_t *mask, int *d_total, cudaStream_t s,
+                          const int *n_dev = nullptr)
+{
+    if (n <= 0) {
+        TNB_CUDA(cudaMemsetAsync(d_total, 0, sizeof(int), s));
+        return TNB_OK;
+    }
+    int64_t blocks = (n + kScanThreads - 1) / kScanThreads;
+    if (blocks > kScanMaxBlocks) blocks = kScanMaxBlocks;
+    k_scan_count_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, count, block_sums, mask, n_dev);
+    TNB_LAUNCH_CHECK();
+    k_scan_write_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, mask, emit, block_sums, d_total, n_dev);
     TNB_LAUNCH_CHECK();
     return TNB_OK;
 }
