@@ -353,37 +353,116 @@ void trinet_outputs_group8(const trinet_t *n, const float *x, int64_t groups, fl
     }
 }
 
-/* Smallest real root in [0,1] of c[0] t^deg + ... + c[deg] (deg <= 4), or -1.
- * The reference takes the eigenvalues of the companion matrix (geometry.py:271-299) and keeps
- * the LAST admissible one in LAPACK's order, which for these matrices is the smallest root
- * (checked empirically, tests/test_oracle_vs_reference.py).  Defined here as: scan 1024 equal
- * sub-intervals of [0,1] left to right in double precision, take the first sign change (or
- * exact zero) and bisect it 60 times. */
+/* Which root of c[0] t^deg + ... + c[deg] (deg <= 4) does the reference take?
+ * It forms the companion matrix, calls torch.linalg.eigvals (LAPACK sgeev) and keeps the LAST
+ * eigenvalue, in LAPACK's output order, that is real (|imag| <= 1e-9) and lies in [0,1]
+ * (geometry.py:271-299, nonzero_last at :296).  For a quadratic with both roots in [0,1] that order
+ * is fixed by slanv2's standardisation of the 2x2 block: ascending whenever the root sum is positive,
+ * so the reference takes the LARGER root (187 of the 189 multi-root intersections of the medium-torus
+ * fixture are quadratics, every one of them ascending: tests/golden/investigate_roots.py).  For
+ * cubics and quartics with several admissible roots the order depends on the rounding history of the
+ * float32 QR iteration (the two quartic cases of that run went one each way): implementation defined.
+ * DEFINED here, and followed by the device (csrc/curve.cuh), as: the LARGEST real root in [0,1],
+ * in double precision:
+ *   deg 1: -c1/c0;
+ *   deg 2: discriminant D = b*b - 4ac (D < 0: none); q = -(b + sign(b) sqrt(D))/2; roots q/a and c/q;
+ *   deg 3, 4: the critical points of p in (0,1) (roots of p', found the same way one degree down)
+ *            cut [0,1] into intervals on which p is monotone; from the right, the first interval
+ *            whose end values differ in sign (or whose right end is an exact zero) holds the root:
+ *            64 bisection steps.
+ * Unlike a fixed-step sign scan this finds both members of a close root pair. */
 static double poly_eval(const double *c, int deg, double t)
 {
     double v = c[0];
     for (int i = 1; i <= deg; ++i) v = v * t + c[i];
     return v;
 }
-static double smallest_root01(const double *c, int deg)
+static double bisect_root(const double *c, int deg, double lo, double hi, double flo)
 {
-    const int N = 1024;
-    double t0 = 0.0, f0 = poly_eval(c, deg, 0.0);
-    if (f0 == 0.0) return 0.0;
-    for (int k = 1; k <= N; ++k) {
-        const double t1 = (double)k / (double)N, f1 = poly_eval(c, deg, t1);
-        if (f1 == 0.0) return t1;
-        if ((f0 < 0.0) != (f1 < 0.0)) {
-            double lo = t0, hi = t1, flo = f0;
-            for (int it = 0; it < 60; ++it) {
-                const double mid = 0.5 * (lo + hi), fm = poly_eval(c, deg, mid);
-                if (fm == 0.0) return mid;
-                if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else hi = mid;
-            }
-            return 0.5 * (lo + hi);
-        }
-        t0 = t1;
-        f0 = f1;
+    for (int it = 0; it < 64; ++it) {
+        const double mid = 0.5 * (lo + hi), fm = poly_eval(c, deg, mid);
+        if (fm == 0.0) return mid;
+        if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else hi = mid;
+    }
+    return 0.5 * (lo + hi);
+}
+/* all real roots of a quadratic a t^2 + b t + c (a != 0) in ascending order; returns their number */
+static int quadratic_roots(double a, double b, double c, double *r)
+{
+    const double D = b * b - 4.0 * a * c;
+    if (D < 0.0) return 0;
+    const double sq = sqrt(D);
+    const double q = -0.5 * (b + (b < 0.0 ? -sq : sq));
+    double r0 = q / a, r1 = (q != 0.0) ? c / q : r0;
+    if (r0 > r1) { const double t = r0; r0 = r1; r1 = t; }
+    r[0] = r0;
+    r[1] = r1;
+    return 2;
+}
+/* interior points of (0,1), ascending, where a polynomial of degree deg (<= 3, leading coefficient
+ * possibly zero) changes sign or touches zero: the cut points for the next degree up */
+static int roots_inside01(const double *c, int deg, double *r)
+{
+    while (deg > 0 && c[0] == 0.0) { ++c; --deg; }
+    int n = 0;
+    if (deg <= 0) return 0;
+    if (deg == 1) {
+        const double t = -c[1] / c[0];
+        if (t > 0.0 && t < 1.0) r[n++] = t;
+        return n;
+    }
+    if (deg == 2) {
+        double q[2];
+        const int k = quadratic_roots(c[0], c[1], c[2], q);
+        for (int i = 0; i < k; ++i)
+            if (q[i] > 0.0 && q[i] < 1.0 && (n == 0 || q[i] > r[n - 1])) r[n++] = q[i];
+        return n;
+    }
+    /* deg == 3: monotone pieces between the critical points */
+    double d[3] = {3.0 * c[0], 2.0 * c[1], c[2]}, cut[4];
+    int nc = 0;
+    cut[nc++] = 0.0;
+    {
+        double q[2];
+        const int k = quadratic_roots(d[0], d[1], d[2], q);
+        for (int i = 0; i < k; ++i)
+            if (q[i] > 0.0 && q[i] < 1.0 && q[i] > cut[nc - 1]) cut[nc++] = q[i];
+    }
+    cut[nc++] = 1.0;
+    for (int i = 0; i + 1 < nc; ++i) {
+        const double lo = cut[i], hi = cut[i + 1], flo = poly_eval(c, 3, lo), fhi = poly_eval(c, 3, hi);
+        double t = -1.0;
+        if (flo == 0.0) t = lo;
+        else if (fhi != 0.0 && (flo < 0.0) != (fhi < 0.0)) t = bisect_root(c, 3, lo, hi, flo);
+        if (t > 0.0 && t < 1.0 && (n == 0 || t > r[n - 1])) r[n++] = t;
+    }
+    return n;
+}
+static double last_root01(const double *c, int deg)
+{
+    if (deg == 1) {
+        const double t = -c[1] / c[0];
+        return (t >= 0.0 && t <= 1.0) ? t : -1.0;
+    }
+    if (deg == 2) {
+        double q[2];
+        const int k = quadratic_roots(c[0], c[1], c[2], q);
+        for (int i = k - 1; i >= 0; --i)
+            if (q[i] >= 0.0 && q[i] <= 1.0) return q[i];
+        return -1.0;
+    }
+    /* deg 3 or 4: cut [0,1] at the critical points, look at the pieces from the right */
+    double d[4], cut[5];
+    for (int i = 0; i < deg; ++i) d[i] = (double)(deg - i) * c[i];
+    int nc = 0;
+    cut[nc++] = 0.0;
+    nc += roots_inside01(d, deg - 1, cut + nc);
+    cut[nc++] = 1.0;
+    for (int i = nc - 2; i >= 0; --i) {
+        const double lo = cut[i], hi = cut[i + 1], flo = poly_eval(c, deg, lo), fhi = poly_eval(c, deg, hi);
+        if (fhi == 0.0) return hi;
+        if (flo != 0.0 && (flo < 0.0) != (fhi < 0.0)) return bisect_root(c, deg, lo, hi, flo);
+        if (i == 0 && flo == 0.0) return lo;
     }
     return -1.0;
 }
@@ -437,7 +516,7 @@ void curve_intersection(const float *p, const float *q, float *out)
             for (int i = lead; i < 5; ++i) mean += fabsf(cf[i]);
             mean /= (float)(5 - lead);
             if (mean > 1e-9f) {
-                const double rt = smallest_root01(co + lead, 4 - lead);
+                const double rt = last_root01(co + lead, 4 - lead);
                 if (rt >= 0.0) x = (float)rt;
             }
         }

