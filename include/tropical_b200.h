@@ -130,7 +130,9 @@ int tnb_subpoly_step(const tnb_net *net, tnb_complex *c, int32_t l, int32_t h, f
  * (l, h) of step i.  Same result as n_steps calls of tnb_subpoly_step; a small complex (planar
  * or curve-approximation path) runs all of them in ONE persistent cooperative launch, with no
  * host round trip between steps (optionally, planar path, inside one thread-block cluster:
- * tnb_set_cluster_max_items). */
+ * tnb_set_cluster_max_items); a large complex (planar path) runs them as a device-driven stream
+ * of launches: the device picks the next hyperplane that crosses an edge, the host never waits
+ * (tnb_set_fused_max_items). */
 int tnb_subpoly_steps(const tnb_net *net, tnb_complex *c, const int32_t *lh, int32_t n_steps, float eps,
                       int32_t force, void *stream);
 
@@ -246,6 +248,11 @@ int tnb_set_capacity_factor(double f);
  * vertices + edges as one thread-block-cluster launch (default 200000, env
  * TNB_CLUSTER_MAX_ITEMS; 0 = never).  Returns the previous value; items < 0 only queries. */
 int64_t tnb_set_cluster_max_items(int64_t items);
+/* tnb_subpoly_steps / tnb_subpoly run the hyperplanes of a complex with at most `items` vertices + edges
+ * inside the persistent step kernel (default 700000, env TNB_FUSED_MAX_ITEMS); a larger complex runs them
+ * as a device-driven stream of full-size launches (no host synchronisation between hyperplanes, planar
+ * path).  0 = always the stream.  Returns the previous value; items < 0 only queries. */
+int64_t tnb_set_fused_max_items(int64_t items);
 /* number of CUDA kernels this library launched on the calling thread since the last
  * reset (bench.py's gpu_launches) */
 int64_t tnb_launch_count(void);

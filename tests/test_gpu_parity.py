@@ -403,3 +403,74 @@ def test_steps_with_an_eps_other_than_the_networks():
         vo, eo, oo = R.subpoly_step(P, vo, eo, oo, l, h, eps)
     assert np.array_equal(e, eo) and np.array_equal(v, vo) and np.array_equal(o, oo)
     assert np.array_equal(e2, eo) and np.array_equal(v2, vo) and np.array_equal(o2, oo)
+
+
+@pytest.mark.parametrize("case", CASES)
+def test_device_driven_step_stream_equals_single_steps(case):
+    """The launch stream of LARGE complexes (tnb_subpoly_steps without the persistent kernel: the device picks
+    the next crossing hyperplane, the host never synchronises), forced onto the small fixtures: the same
+    complex as separate tnb_subpoly_step calls and as the oracle, for the whole list, for prefixes, and when
+    the stream hands the rest of the list to the persistent kernel half-way."""
+    from oracle import subpoly_ref as R
+    from tropical._native import lib
+    g = load_golden(case)
+    P = oracle_net(g)
+    N = native_net(P)
+    steps = _all_steps(P)
+    before = lib().tnb_set_fused_max_items(-1)
+    try:
+        a = N.skeleton(128)
+        for l, h in steps:
+            a.step(l, h)
+        va, ea, oa = [t.cpu().numpy() for t in a.read()]
+        lib().tnb_set_fused_max_items(0)            # never the persistent kernel
+        b = N.skeleton(128)
+        b.steps(steps)
+        vb, eb, ob = [t.cpu().numpy() for t in b.read()]
+        assert np.array_equal(ea, eb) and np.array_equal(va, vb) and np.array_equal(oa, ob)
+        m_stream = [x.cpu().numpy() for x in N.subpoly().read()]
+        p7 = N.skeleton(128)
+        p7.steps(steps[:7])
+        v7, e7, o7 = [t.cpu().numpy() for t in p7.read()]
+        # hand-over: the stream starts (the skeleton is larger than the limit) and the persistent kernel finishes
+        e0 = N.skeleton(128).num_edges
+        lib().tnb_set_fused_max_items(int(e0))
+        h = N.skeleton(128)
+        h.steps(steps)
+        vh, eh, oh = [t.cpu().numpy() for t in h.read()]
+        assert np.array_equal(ea, eh) and np.array_equal(va, vh) and np.array_equal(oa, oh)
+    finally:
+        lib().tnb_set_fused_max_items(before)
+    m_default = [x.cpu().numpy() for x in N.subpoly().read()]
+    for x, y in zip(m_stream, m_default):
+        assert np.array_equal(x, y)
+    vo, eo = R.skeleton(P)
+    oo = P.outputs(vo)
+    for l, h in steps[:7]:
+        vo, eo, oo = R.subpoly_step(P, vo, eo, oo, l, h, 1e-4)
+    assert np.array_equal(e7, eo) and np.array_equal(v7, vo) and np.array_equal(o7, oo)
+
+
+def test_device_driven_step_stream_reports_capacity():
+    """Work arrays do not grow inside the stream: an overflow is latched and tnb_subpoly repeats the extraction
+    with more head-room (same mesh in the end)."""
+    from tropical import _native
+    from tropical._native import lib
+    g = load_golden("small_sphere")
+    N = native_net(oracle_net(g))
+    want = [x.cpu().numpy() for x in N.subpoly().read()]
+    before = lib().tnb_set_fused_max_items(0)
+    try:
+        _native.check(lib().tnb_set_capacity_factor(1.0))
+        try:
+            c = N.skeleton(128)
+            got = [x.cpu().numpy() for x in N.subpoly().read()]   # retries inside tnb_subpoly
+        finally:
+            _native.check(lib().tnb_set_capacity_factor(4.0))
+        c.steps(_all_steps(oracle_net(g)))
+        with pytest.raises(_native.NativeError, match="CAPACITY"):
+            c.num_vertices
+    finally:
+        lib().tnb_set_fused_max_items(before)
+    for x, y in zip(got, want):
+        assert np.array_equal(x, y)

@@ -39,11 +39,17 @@ constexpr int kNetworkPartners = 12; // lists up to this size (nearly all of the
 //   C_KEPT = edges kept by pruning, parked until the slab exchange decides whether the step counts
 //   C_APAR = which half of the liveness array is current.  C_V counts vertex SLOTS (dead rows included)
 //   C_LONG = candidates whose partner list is longer than the cache (their connecting edges are a warp's job)
-enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_LONG = 15, C_CROSS = 16 /* 64-bit crossing mask */, C_RECS = 18 /* records in the contiguous cell segments */, C_NUM = 32 };
+enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_LONG = 15, C_CROSS = 16 /* 64-bit crossing mask */, C_RECS = 18 /* records in the contiguous cell segments */,
+       C_STEP = 19 /* device-driven step stream: next position in the step list */, C_IDX = 20 /* its current hyperplane column, -1 = none */, C_PRUNE = 21, C_NUM = 32 };
 enum { kErrNoPlane = 1, kErrGradientDescent = 2 };
 enum { kStickyCapacity = 1, kStickyNoPlane = 32, kStickyGradientDescent = 64 };  // 2..16: halo.cuh
 
 // ---- allocation ---------------------------------------------------------------------------
+// one bit per edge and, behind them, one bit per vertex (the split and the hit compaction of a step can run
+// side by side); a compaction over n items needs (n + 31) / 32 + kScanMaxBlocks words (warp-aligned slices)
+static size_t scan_mask_vertex_offset(size_t Ecap) { return (Ecap + 31) / 32 + kScanMaxBlocks + 64; }
+static size_t scan_mask_words(size_t Vcap, size_t Ecap) { return scan_mask_vertex_offset(Ecap) + (Vcap + 31) / 32 + kScanMaxBlocks + 64; }
+
 int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
 {
     c->R = net->meta.R;
@@ -67,12 +73,12 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
     TNB_CUDA(c->pcache.reserve(Vcap * kCachedPartners));
     TNB_CUDA(c->next.reserve(Vcap * 8));
     TNB_CUDA(c->cslot.reserve(Vcap * 8));
-    TNB_CUDA(c->scan_mask.reserve((std::max(Vcap, Ecap) + 31) / 32 + kScanMaxBlocks + 64));
+    TNB_CUDA(c->scan_mask.reserve(scan_mask_words(Vcap, Ecap)));
     TNB_CUDA(c->remap.reserve(Vcap));
     TNB_CUDA(c->block_sums.reserve(3 * kScanMaxBlocks));  // the persistent step kernels keep three sets of block sums
     TNB_CUDA(c->counters.reserve(C_NUM));
-    TNB_CUDA(c->bytes.reserve(2));
-    TNB_CUDA(cudaMemsetAsync(c->bytes.p, 0, 2 * sizeof(unsigned long long), current_stream()));
+    TNB_CUDA(c->bytes.reserve(4));
+    TNB_CUDA(cudaMemsetAsync(c->bytes.p, 0, 4 * sizeof(unsigned long long), current_stream()));
     TNB_CUDA(cudaMemsetAsync(c->counters.p, 0, C_NUM * sizeof(int), current_stream()));
     {   // one pinned mirror per thread, reused by every complex
         static thread_local int *pinned = nullptr;
@@ -108,7 +114,7 @@ static int grow(DevBuf<T> &b, size_t new_elems, size_t keep_elems, cudaStream_t 
 int complex_reserve(tnb_complex *c, size_t Vneed, size_t Eneed, cudaStream_t s)
 {
     if (Vneed > c->Vcap || Eneed > c->Ecap) {
-        int rc = grow(c->scan_mask, (std::max(std::max(Vneed, (size_t)(c->Vcap * 2)), std::max(Eneed, (size_t)(c->Ecap * 2))) + 31) / 32 + kScanMaxBlocks + 64, 0, s);
+        int rc = grow(c->scan_mask, scan_mask_words(std::max(Vneed, (size_t)(c->Vcap * 2)), std::max(Eneed, (size_t)(c->Ecap * 2))), 0, s);
         if (rc) return rc;
     }
     if (Vneed > c->Vcap) {
@@ -314,6 +320,18 @@ __global__ void k_remap_edges(int2 *__restrict__ edges, int64_t E, const int *__
     }
 }
 
+// A warp's 32 rows are consecutive in `out` (32 * R floats): each lane builds its row in shared memory (stride R
+// floats: R = 33 is odd, no bank conflicts), then the warp writes the block with coalesced stores.  One thread
+// per 132-byte row cost 32 sectors per store instruction (k_vertex_outputs 0.28 TB/s, k_new_vertices lg_throttle
+// 6.7 warps per issue in profiles/r2_ncu_summary.txt).
+__device__ __forceinline__ void warp_store_rows(float *__restrict__ out, int64_t first_row, int rows, int R, const float *tile)
+{
+    const int lane = threadIdx.x & 31;
+    float *dst = out + first_row * R;
+    const int n = rows * R;
+    for (int e = lane; e < n; e += 32) dst[e] = tile[e];
+}
+
 // outputs row + packed signs of vertices [first, first+count)
 template <class C>
 __global__ void __launch_bounds__(kThreads) k_vertex_outputs(const __grid_constant__ NetMeta n,
@@ -321,18 +339,22 @@ __global__ void __launch_bounds__(kThreads) k_vertex_outputs(const __grid_consta
                                                              int64_t count, float *__restrict__ out,
                                                              uint64_t *__restrict__ sig)
 {
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < count; t += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t v = first + t;
-        float x[3] = {vert[3 * v], vert[3 * v + 1], vert[3 * v + 2]};
-        float *row = out + v * n.R;
-        outputs_row<C>(n, x, row);
-        float xp[3];
-        preprocess(n, x, xp);
-        uint64_t pos, neg;
-        pack_signs(row, n.R, n.eps, pos, neg);
-        sig[3 * v] = pos;
-        sig[3 * v + 1] = neg;
-        sig[3 * v + 2] = pack_grid(n, n.marks, xp, n.eps);
+    extern __shared__ float s_tile[];  // [kThreads][R]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, R = n.R;
+    float *wtile = s_tile + (size_t)warp * 32 * R, *row = wtile + lane * R;
+    for (int64_t t0 = blockIdx.x * (int64_t)blockDim.x + warp * 32; t0 < count; t0 += (int64_t)gridDim.x * blockDim.x) {  // warp uniform
+        const int64_t t = t0 + lane, v = first + t;
+        if (t < count) {
+            float x[3] = {vert[3 * v], vert[3 * v + 1], vert[3 * v + 2]}, xp[3];
+            uint64_t pos, neg, big;
+            outputs_row_packed<C>(n, x, row, n.eps, n.eps, xp, pos, neg, big);
+            sig[3 * v] = pos;
+            sig[3 * v + 1] = neg;
+            sig[3 * v + 2] = pack_grid(n, n.marks, xp, n.eps);
+        }
+        __syncwarp();
+        warp_store_rows(out, first + t0, (int)min((int64_t)32, count - t0), R, wtile);
+        __syncwarp();
     }
 }
 
@@ -341,8 +363,9 @@ static int eval_vertices(const tnb_net *net, tnb_complex *c, int64_t first, int6
     if (count <= 0) return TNB_OK;
     unsigned g = grid_for(count, kThreads);
     prof_begin(TNB_PROF_VERTEX_ROWS, s);
-    if (net->fixed_cfg) k_vertex_outputs<CfgRef><<<g, kThreads, 0, s>>>(net->meta, c->cvert(), first, count, c->cout_(), c->csig());
-    else k_vertex_outputs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, c->cvert(), first, count, c->cout_(), c->csig());
+    const size_t tile = (size_t)kThreads * net->meta.R * sizeof(float);
+    if (net->fixed_cfg) k_vertex_outputs<CfgRef><<<g, kThreads, tile, s>>>(net->meta, c->cvert(), first, count, c->cout_(), c->csig());
+    else k_vertex_outputs<CfgAny><<<g, kThreads, tile, s>>>(net->meta, c->cvert(), first, count, c->cout_(), c->csig());
     TNB_LAUNCH_CHECK();
     prof_end(TNB_PROF_VERTEX_ROWS, s, count, count * (12 + 4 * net->meta.R + 24) + (int64_t)net->table.cap * 8);
     return TNB_OK;
@@ -550,7 +573,7 @@ struct ListEmit {
 template <class C, bool kPack = false>
 __device__ __forceinline__ int new_vertex_item(const NetMeta &n, int idx, float eps, int k, int V, int E, const int *split_list,
                                                int2 *edges, float *vert, float *out, uint64_t *sig, uint64_t *bmask,
-                                               unsigned char *tag)
+                                               unsigned char *tag, float *row_dst = nullptr)
 {
     const int R = n.R;
     int any = 0;
@@ -566,7 +589,7 @@ __device__ __forceinline__ int new_vertex_item(const NetMeta &n, int idx, float 
         const int64_t nv = (int64_t)V + k;
 #pragma unroll
         for (int d = 0; d < 3; ++d) vert[3 * nv + d] = x[d];
-        float *row = out + nv * R;
+        float *row = row_dst ? row_dst : out + nv * R;  // row_dst: the caller stores the warp's rows together
         const uint64_t za = ~(sig[3 * (int64_t)ed.x] | sig[3 * (int64_t)ed.x + 1]);
         const uint64_t zb = ~(sig[3 * (int64_t)ed.y] | sig[3 * (int64_t)ed.y + 1]);
         const uint64_t bm = (za & zb & ((1ull << idx) - 1ull)) | (1ull << idx);
@@ -598,7 +621,7 @@ __device__ __forceinline__ void body_new_vertices(const NetMeta &n, int idx, flo
                                                            int Vcap, int Ecap, const int *split_list,
                                                            int2 *edges, float *vert,
                                                            float *out, uint64_t *sig,
-                                                           uint64_t *bmask, int *cnt, unsigned char *tag)
+                                                           uint64_t *bmask, int *cnt, unsigned char *tag, float *tile = nullptr)
 {
     const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
     if ((int64_t)V + S > Vcap || (int64_t)E + S > Ecap) {  // host grows the arrays and re-runs
@@ -607,8 +630,20 @@ __device__ __forceinline__ void body_new_vertices(const NetMeta &n, int idx, flo
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) cnt[C_SPLIT] = S;  // planar path: every crossed edge is split
     int any = 0;
-    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x)
-        any |= new_vertex_item<C, kPack>(n, idx, eps, k, V, E, split_list, edges, vert, out, sig, bmask, tag);
+    if (tile) {  // [blockDim.x][R] floats of shared memory: the rows of a warp leave together (warp_store_rows)
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, R = n.R;
+        float *wtile = tile + (size_t)warp * 32 * R;
+        for (int k0 = blockIdx.x * blockDim.x + warp * 32; k0 < S; k0 += gridDim.x * blockDim.x) {  // warp uniform
+            const int k = k0 + lane;
+            if (k < S) any |= new_vertex_item<C, kPack>(n, idx, eps, k, V, E, split_list, edges, vert, out, sig, bmask, tag, wtile + lane * R);
+            __syncwarp();
+            warp_store_rows(out, (int64_t)V + k0, min(32, S - k0), R, wtile);
+            __syncwarp();
+        }
+    } else {
+        for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < S; k += gridDim.x * blockDim.x)
+            any |= new_vertex_item<C, kPack>(n, idx, eps, k, V, E, split_list, edges, vert, out, sig, bmask, tag);
+    }
     if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
 }
 
@@ -621,7 +656,8 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices(const __grid_constant
                                                            uint64_t *__restrict__ bmask, int *__restrict__ cnt,
                                                            unsigned char *__restrict__ tag)
 {
-    body_new_vertices<C, true>(n, idx, eps, Vcap, Ecap, split_list, edges, vert, out, sig, bmask, cnt, tag);
+    extern __shared__ float s_tile[];  // [kThreads][R]
+    body_new_vertices<C, true>(n, idx, eps, Vcap, Ecap, split_list, edges, vert, out, sig, bmask, cnt, tag, s_tile);
 }
 
 // apply the failover override when any new vertex violated it, then bit-pack the region
@@ -1290,8 +1326,14 @@ __device__ __forceinline__ void stream_partners(const PartnerQuery &q, const int
 __global__ void __launch_bounds__(256) k_pair_count_seg(const int *__restrict__ cand, int *__restrict__ cnt,
                                                         const uint64_t *__restrict__ sig, const int2 *__restrict__ cells,
                                                         const tnb_bucket_rec *__restrict__ recs, int dim, uint64_t colmask,
-                                                        int *__restrict__ pcount, int *__restrict__ pcache, int *__restrict__ long_list)
+                                                        int *__restrict__ pcount, int *__restrict__ pcache, int *__restrict__ long_list,
+                                                        const int *__restrict__ idx_dev = nullptr)
 {
+    if (idx_dev) {  // device-driven step stream: the hyperplane of this step is chosen on the device
+        const int idx = *idx_dev;
+        if (idx < 0) return;
+        colmask = (1ull << idx) - 1ull;
+    }
     __shared__ int s_keys[8][kCachedPartners], s_incl[8][32], s_base[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n_cand = cnt[C_CAND], warps = gridDim.x * (blockDim.x >> 5);
@@ -1331,16 +1373,15 @@ __global__ void __launch_bounds__(256) k_pair_copy(const int *__restrict__ cand,
     }
 }
 // a warp per long list: stream the neighbourhood again, keys into shared memory, bitonic sort, write
-__global__ void __launch_bounds__(kSortWarps * 32) k_pair_write_long_seg(const int *__restrict__ long_list, const int *__restrict__ cnt,
-                                                                         const int *__restrict__ cand, const uint64_t *__restrict__ sig,
-                                                                         const int2 *__restrict__ cells, const tnb_bucket_rec *__restrict__ recs,
-                                                                         int dim, uint64_t colmask, const int *__restrict__ pcount,
-                                                                         const int *__restrict__ poff, int2 *__restrict__ edges_out)
+__device__ __forceinline__ void pair_write_long_seg_body(const int *__restrict__ long_list, int n_long, const int *__restrict__ cand,
+                                                         const uint64_t *__restrict__ sig, const int2 *__restrict__ cells,
+                                                         const tnb_bucket_rec *__restrict__ recs, int dim, uint64_t colmask,
+                                                         const int *__restrict__ pcount, const int *__restrict__ poff,
+                                                         int2 *__restrict__ edges_out)
 {
     __shared__ int s_keys[kSortWarps][kLongSortMax];
     __shared__ int s_incl[kSortWarps][32], s_base[kSortWarps][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_long = cnt[C_LONG];
     for (int li = blockIdx.x * kSortWarps + warp; li < n_long; li += gridDim.x * kSortWarps) {
         const int a = long_list[li], c = pcount[a], va = cand[a];
         int2 *dst = edges_out + poff[a];
@@ -1383,6 +1424,14 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_pair_write_long_seg(const i
         }
         __syncwarp();
     }
+}
+__global__ void __launch_bounds__(kSortWarps * 32) k_pair_write_long_seg(const int *__restrict__ long_list, const int *__restrict__ cnt,
+                                                                         const int *__restrict__ cand, const uint64_t *__restrict__ sig,
+                                                                         const int2 *__restrict__ cells, const tnb_bucket_rec *__restrict__ recs,
+                                                                         int dim, uint64_t colmask, const int *__restrict__ pcount,
+                                                                         const int *__restrict__ poff, int2 *__restrict__ edges_out)
+{
+    pair_write_long_seg_body(long_list, cnt[C_LONG], cand, sig, cells, recs, dim, colmask, pcount, poff, edges_out);
 }
 
 // ---- pruning -------------------------------------------------------------------------------------
@@ -1580,8 +1629,10 @@ struct StepArgs {
     uint64_t *sig[2], *bmask;
     int *split_list, *cand, *pcount, *poff, *used[2], *remap, *block_sums, *cnt, *pcache;
     tnb_bucket_rec *next;
-    unsigned long long *head, *bytes;  // bytes[0/1]: algorithmic bytes of the front / back halves
+    unsigned long long *head, *bytes;  // bytes[0/1]: algorithmic bytes of the front / back halves, [2/3]: their units
     unsigned char *tag[2];
+    int2 *cslot;                    // contiguous cell segments (cells.cuh): slot of every candidate
+    uint32_t *mask_e, *mask_v;      // one bit per edge / per vertex (masked compactions)
     // slab sharding (halo.cuh): the back half runs in two launches around the exchange
     int use_cross;                  // the packed signs were made with this step's eps: the crossing mask decides no-op steps
     int halo, part;                 // part 0: whole back half, 1: up to the exchange, 2: after it
@@ -2101,7 +2152,7 @@ static int coop_blocks(K kernel)
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kScanThreads, 0) != cudaSuccess || per_sm < 1) return 0;
     return std::min(per_sm * sms, kScanMaxBlocks);
 }
-static const int64_t kFusedMaxItems = std::getenv("TNB_FUSED_MAX_ITEMS") ? std::atoll(std::getenv("TNB_FUSED_MAX_ITEMS")) : 700000;  // larger complexes: multi-launch path (measured: the large model's 2.3 M items take 6.2 ms in the persistent kernel, 3.7 ms as separate full-size launches)
+static int64_t g_fused_max_items = std::getenv("TNB_FUSED_MAX_ITEMS") ? std::atoll(std::getenv("TNB_FUSED_MAX_ITEMS")) : 700000;  // larger complexes: multi-launch path (measured: the large model's 2.3 M items take 6.2 ms in the persistent kernel, 3.7 ms as separate full-size launches)
 static bool g_fused_steps = std::getenv("TNB_NO_FUSED_STEPS") == nullptr;  // A/B switch for profiling
 
 // Refresh the host's view of the complex size (one small D2H + sync).
@@ -2120,13 +2171,14 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
     c->cross_stale = false;
     c->counts_stale = false;
     if (c->bytes.p) {  // algorithmic bytes the fused kernels accumulated on the device
-        unsigned long long hb[2] = {0, 0};
+        unsigned long long hb[4] = {0, 0, 0, 0};
         TNB_CUDA(cudaMemcpyAsync(hb, c->bytes.p, sizeof(hb), cudaMemcpyDeviceToHost, s));
         TNB_CUDA(cudaMemsetAsync(c->bytes.p, 0, sizeof(hb), s));
         TNB_CUDA(cudaStreamSynchronize(s));
-        if (c->halo.enabled) {
-            prof_add(TNB_PROF_NEW_VERTICES, 0, (int64_t)hb[0]);
-            prof_add(TNB_PROF_PAIRS, 0, (int64_t)hb[1]);
+        if (c->halo.enabled || c->bytes_by_half) {
+            prof_add(TNB_PROF_NEW_VERTICES, (int64_t)hb[2], (int64_t)hb[0]);
+            prof_add(TNB_PROF_PAIRS, (int64_t)hb[3], (int64_t)hb[1]);
+            c->bytes_by_half = false;
         } else {
             prof_add(TNB_PROF_STEPS, 0, (int64_t)(hb[0] + hb[1]));
         }
@@ -2245,6 +2297,7 @@ static void fill_step_args(const tnb_net *net, tnb_complex *c, float eps, StepAr
     sa.bmask = c->bmask.p; sa.split_list = c->split_list.p; sa.cand = c->cand.p; sa.pcount = c->pcount.p;
     sa.poff = c->poff.p; sa.pcache = c->pcache.p; sa.next = c->next.p; sa.remap = c->remap.p;
     sa.block_sums = c->block_sums.p; sa.cnt = c->counters.p; sa.head = c->head.p; sa.bytes = c->bytes.p;
+    sa.cslot = c->cslot.p; sa.mask_e = c->scan_mask.p; sa.mask_v = c->scan_mask.p + scan_mask_vertex_offset(c->Ecap);
 }
 
 static const bool g_phase_trace = std::getenv("TNB_PHASE_TRACE") != nullptr;
@@ -2306,7 +2359,7 @@ int steps_mode(const tnb_net *net, const tnb_complex *c, bool planar)
     if (!planar && !g_fused_curve) return 0;
     const int64_t items = c->E + c->V;  // may be stale upper bounds: good enough for this choice
     if (planar && g_cluster_max_items > 0 && items <= g_cluster_max_items) return 2;
-    return items <= kFusedMaxItems ? 1 : 0;
+    return items <= g_fused_max_items ? 1 : 0;
 }
 
 // lh[2*i], lh[2*i+1] = (layer, neuron) of step i, as tnb_subpoly_step takes them.  One launch; the
@@ -2423,7 +2476,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     static const int env_blocks = std::getenv("TNB_STEP_BLOCKS") ? std::atoi(std::getenv("TNB_STEP_BLOCKS")) : 0;  // tuning knob
     const int sm_blocks = std::min(env_blocks > 0 ? env_blocks : kSMs, std::min(front_blocks_ref, back_blocks));
     const int front_blocks = std::min(net->fixed_cfg ? front_blocks_ref : front_blocks_any, sm_blocks);
-    const bool fused = planar && front_blocks > 0 && back_blocks > 0 && (halo || (g_fused_steps && c->E + c->V <= kFusedMaxItems));
+    const bool fused = planar && front_blocks > 0 && back_blocks > 0 && (halo || (g_fused_steps && c->E + c->V <= g_fused_max_items));
     if (halo && !fused) { set_error("slab-sharded extraction needs the cooperative step kernels"); return TNB_ERR_UNSUPPORTED; }
     if (!halo) {  // a small complex: the persistent step kernel, with a list of one
         const int mode = steps_mode(net, c, planar);
@@ -2527,10 +2580,11 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         } else {
             unsigned g = grid_for(c->E, kThreads);
             prof_begin(TNB_PROF_NEW_VERTICES, s);
+            const size_t row_tile = (size_t)kThreads * R * sizeof(float);
             if (net->fixed_cfg)
-                k_new_vertices<CfgRef><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt, c->tag[c->vcur].p);
+                k_new_vertices<CfgRef><<<g, kThreads, row_tile, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt, c->tag[c->vcur].p);
             else
-                k_new_vertices<CfgAny><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt, c->tag[c->vcur].p);
+                k_new_vertices<CfgAny><<<g, kThreads, row_tile, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt, c->tag[c->vcur].p);
             TNB_LAUNCH_CHECK();
             prof_end(TNB_PROF_NEW_VERTICES, s, 0);
             k_finalize_new<<<g, kThreads, 0, s>>>(m, c->cvert(), c->cout_(), c->csig(), c->bmask.p, cnt);
@@ -2635,6 +2689,338 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
     return TNB_OK;
 }
 
+// ================================================================================================
+// Device-driven step stream: the hyperplanes of a LARGE complex (planar path)
+// ================================================================================================
+// A large complex keeps full-size grids per phase (a persistent 148-CTA grid is too thin for millions of
+// edges), but nothing a phase needs comes from the host any more: the hyperplane of the step (C_IDX), every
+// size, which half of the ping-pong arrays is current and the capacity checks live in the counter block,
+// and the step list itself is a kernel parameter.  One SEQUENCE of 16 launches runs one hyperplane that
+// crosses something; its last kernel (k_sd_finish) commits the step, picks the next hyperplane whose bit
+// is set in the crossing mask (the 25 of 33 planes of a fitted network that cross nothing cost nothing) and
+// reports through mapped pinned memory.  The host enqueues one sequence ahead of the one it has a report
+// for, so the stream never drains and the host never synchronises: before, every crossing hyperplane cost
+// three cudaStreamSynchronize round trips (crossing mask, crossed-edge count, sizing of the edge array).
+// Work arrays do not grow on this path: an overflow raises the sticky capacity bit and tnb_subpoly
+// repeats the extraction with twice the head-room, exactly as for the persistent kernels.
+struct PreMeta {  // what finalising a new vertex needs of NetMeta (5 KB as a kernel parameter: not for a housekeeping kernel)
+    int R, n_marks, pre_pow2;
+    float eps, pre_scale, pre_2s, pre_inv;
+    const float *marks;
+};
+static PreMeta pre_meta(const NetMeta &m)
+{
+    PreMeta p;
+    p.R = m.R; p.n_marks = m.n_marks; p.pre_pow2 = m.pre_pow2;
+    p.eps = m.eps; p.pre_scale = m.pre_scale; p.pre_2s = m.pre_2s; p.pre_inv = m.pre_inv;
+    p.marks = m.marks;
+    return p;
+}
+// finalize_item without NetMeta (same operations)
+__device__ __forceinline__ void finalize_item_slim(const PreMeta &n, const float *vert, float *out, uint64_t *sig, const uint64_t *bmask, int V, int k)
+{
+    const int64_t v = (int64_t)V + k;
+    float *row = out + v * n.R;
+    for (uint64_t m = bmask[k]; m; m &= m - 1) row[__ffsll((long long)m) - 1] = 0.0f;
+    uint64_t pos, neg;
+    pack_signs(row, n.R, n.eps, pos, neg);
+    uint64_t g = 0;
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const float t = vert[3 * v + d] + n.pre_scale;
+        const float xp = n.pre_pow2 ? t * n.pre_inv : __fdiv_rn(t, n.pre_2s);
+        const int off = lower_bound(n.marks, n.n_marks, xp + n.eps) - 1;
+        const float mk = n.marks[off < 0 ? off + n.n_marks : off];
+        g |= (uint64_t)(uint32_t)(off + 1) << (20 * d);
+        g |= (fabsf(mk - xp) > n.eps ? 1ull : 0ull) << (60 + d);
+    }
+    sig[3 * v] = pos;
+    sig[3 * v + 1] = neg;
+    sig[3 * v + 2] = g;
+}
+
+// is there a step to run, and may it go on?  (uniform over the grid: these words are written by single-CTA kernels
+// of earlier launches only)
+__device__ __forceinline__ bool sd_active(const int *cnt) { return cnt[C_IDX] >= 0 && !cnt[C_STICKY]; }
+// ... after the new vertices: did the plane cross something, and did everything fit?
+__device__ __forceinline__ bool sd_crossed(const int *cnt) { return sd_active(cnt) && cnt[C_RAW] > 0 && !cnt[C_OVERFLOW]; }
+// ... after the connecting-edge count: room for the edges?
+__device__ __forceinline__ bool sd_fits(const StepArgs &a) { return (int64_t)a.cnt[C_E] + a.cnt[C_SPLIT] + a.cnt[C_PAIRS] <= a.Ecap; }
+
+// split compaction over the edges (first half of the grid) and hit compaction over the vertices (second half)
+__global__ void __launch_bounds__(kScanThreads) k_sd_count(const __grid_constant__ StepArgs a)
+{
+    const int *cnt = a.cnt;
+    if (!sd_active(cnt)) return;
+    const int idx = cnt[C_IDX], nb = (int)gridDim.x >> 1, pv = cnt[C_VPAR];
+    if ((int)blockIdx.x < nb)
+        scan_count_mask_part(cnt[C_E], SplitCount{a.edges[cnt[C_EPAR]], a.out[pv], a.R, idx, a.eps}, a.block_sums, a.mask_e, (int)blockIdx.x, nb);
+    else
+        scan_count_mask_part(cnt[C_V], HitCount{a.out[pv], a.used[cnt[C_APAR]], a.R, idx, a.eps}, a.block_sums + nb, a.mask_v, (int)blockIdx.x - nb, nb);
+}
+__global__ void __launch_bounds__(kScanThreads) k_sd_write(const __grid_constant__ StepArgs a)
+{
+    int *cnt = a.cnt;
+    if (!sd_active(cnt)) return;
+    const int nb = (int)gridDim.x >> 1;
+    if ((int)blockIdx.x < nb) scan_write_mask_part(cnt[C_E], a.mask_e, ListEmit{a.split_list}, a.block_sums, cnt + C_RAW, (int)blockIdx.x, nb);
+    else scan_write_mask_part(cnt[C_V], a.mask_v, ListEmit{a.cand}, a.block_sums + nb, cnt + C_HIT, (int)blockIdx.x - nb, nb);
+}
+template <class C>
+__global__ void __launch_bounds__(kThreads) k_sd_new_vertices(const __grid_constant__ NetMeta n, const __grid_constant__ StepArgs a)
+{
+    int *cnt = a.cnt;
+    if (!sd_active(cnt) || cnt[C_RAW] == 0) return;
+    const int pv = cnt[C_VPAR];
+    extern __shared__ float s_tile[];  // [kThreads][R]
+    body_new_vertices<C, true>(n, cnt[C_IDX], a.eps, a.Vcap, a.Ecap, a.split_list, a.edges[cnt[C_EPAR]], a.vert[pv], a.out[pv], a.sig[pv], a.bmask, cnt, a.tag[pv], s_tile);
+}
+// candidate list (hit old vertices, then the new ones), the failover override when it fired, liveness array of the
+// pruning pass cleared, crossing mask reset (k_sd_keep_count rebuilds it)
+__global__ void __launch_bounds__(256) k_sd_cands(const __grid_constant__ StepArgs a, const PreMeta pm)
+{
+    int *cnt = a.cnt;
+    if (!sd_crossed(cnt)) return;
+    const int Hn = cnt[C_HIT], S = cnt[C_SPLIT], V = cnt[C_V], flag = cnt[C_FLAG], prune = cnt[C_PRUNE], pv = cnt[C_VPAR], pa = cnt[C_APAR];
+    const int t0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    for (int k = t0; k < S; k += stride) {
+        a.cand[Hn + k] = V + k;
+        if (flag) finalize_item_slim(pm, a.vert[pv], a.out[pv], a.sig[pv], a.bmask, V, k);
+        if (!prune) a.used[pa][V + k] = 1;  // the output neuron (subpoly.py:253): the new vertices simply join
+    }
+    if (prune) {
+        int *used = a.used[pa ^ 1];
+        for (int v = t0; v < V + S; v += stride) used[v] = 0;
+    }
+    if (t0 == 0) {
+        cnt[C_CAND] = Hn + S;
+        *(unsigned long long *)(cnt + C_CROSS) = prune ? 0ull : ~0ull;
+    }
+}
+__global__ void __launch_bounds__(256) k_sd_pair_copy(const __grid_constant__ StepArgs a)
+{
+    const int *cnt = a.cnt;
+    if (!sd_crossed(cnt) || !sd_fits(a) || cnt[C_PAIRS] == 0) return;
+    int2 *edges_out = a.edges[cnt[C_EPAR]] + cnt[C_E] + cnt[C_SPLIT];
+    const int64_t n = (int64_t)cnt[C_CAND] * kCachedPartners;
+    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(t / kCachedPartners), i = (int)(t % kCachedPartners);
+        const int pc = a.pcount[c];
+        if (i < pc && pc <= kCachedPartners) edges_out[a.poff[c] + i] = make_int2(a.cand[c], a.pcache[t]);
+    }
+}
+__global__ void __launch_bounds__(kSortWarps * 32) k_sd_pair_long(const __grid_constant__ StepArgs a)
+{
+    const int *cnt = a.cnt;
+    if (!sd_crossed(cnt) || !sd_fits(a) || cnt[C_LONG] == 0) return;
+    pair_write_long_seg_body(a.remap, cnt[C_LONG], a.cand, a.sig[cnt[C_VPAR]], (const int2 *)a.head, a.next, a.dim, (1ull << cnt[C_IDX]) - 1ull,
+                             a.pcount, a.poff, a.edges[cnt[C_EPAR]] + cnt[C_E] + cnt[C_SPLIT]);
+}
+__device__ __forceinline__ uint64_t sd_futmask(int idx, int R) { return ~((1ull << idx) - 1ull) & (R >= 64 ? ~0ull : ((1ull << R) - 1ull)); }
+__global__ void __launch_bounds__(kScanThreads) k_sd_keep_count(const __grid_constant__ StepArgs a)
+{
+    int *cnt = a.cnt;
+    if (!sd_crossed(cnt) || !sd_fits(a) || !cnt[C_PRUNE]) return;
+    const int64_t En = (int64_t)cnt[C_E] + cnt[C_SPLIT] + cnt[C_PAIRS];
+    keep_count_cross<kScanThreads>(En, a.edges[cnt[C_EPAR]], a.sig[cnt[C_VPAR]], sd_futmask(cnt[C_IDX], a.R), a.block_sums, cnt);
+}
+__global__ void __launch_bounds__(kScanThreads) k_sd_keep_write(const __grid_constant__ StepArgs a)
+{
+    int *cnt = a.cnt;
+    if (!sd_crossed(cnt) || !sd_fits(a) || !cnt[C_PRUNE]) return;
+    const int64_t En = (int64_t)cnt[C_E] + cnt[C_SPLIT] + cnt[C_PAIRS];
+    const int pe = cnt[C_EPAR];
+    const int2 *edges = a.edges[pe];
+    scan_write_body(En, KeepCount{edges, a.sig[cnt[C_VPAR]], sd_futmask(cnt[C_IDX], a.R)}, KeepEmit{edges, a.edges[pe ^ 1], a.used[cnt[C_APAR] ^ 1]},
+                    a.block_sums, cnt + C_KEPT);
+}
+// Commits the step that just ran (first = 0), chooses the next hyperplane and reports to the host.
+//   slot = report + 8 * (seq % kReportSlots): slot[1..5] = {another step follows, vertex slots, edges, position of the
+//   chosen step in the list, sticky bits}, then slot[0] = seq (the host waits for that word).  A ring, because the
+//   device may be one report ahead of the one the host is reading.
+constexpr int kReportSlots = 4;
+__global__ void k_sd_finish(const __grid_constant__ StepArgs a, const __grid_constant__ StepList list, int first, int seq, volatile int *report)
+{
+    if (threadIdx.x != 0) return;
+    report += 8 * (seq & (kReportSlots - 1));
+    int *cnt = a.cnt;
+    if (!first && sd_active(cnt)) {
+        if (cnt[C_OVERFLOW]) cnt[C_STICKY] = kStickyCapacity;
+        else if (cnt[C_RAW] > 0) {
+            const int E0 = cnt[C_E], S = cnt[C_SPLIT], P = cnt[C_PAIRS], V0 = cnt[C_V], n_cand = cnt[C_CAND];
+            const int64_t En = (int64_t)E0 + S + P;
+            if (En > a.Ecap) cnt[C_STICKY] = kStickyCapacity;
+            else {
+                cnt[C_V] = V0 + S;
+                unsigned long long back = (unsigned long long)n_cand * 28 + (unsigned long long)P * 8;
+                if (cnt[C_PRUNE]) {
+                    cnt[C_E] = cnt[C_KEPT];
+                    cnt[C_EPAR] ^= 1;
+                    cnt[C_APAR] ^= 1;
+                    back += (unsigned long long)En * (8 + 2 * 48) + (unsigned long long)(V0 + S) * 8;
+                } else {
+                    cnt[C_E] = (int)En;
+                }
+                a.bytes[0] += 2ull * 16 * E0 + 2ull * 4 * V0 + (unsigned long long)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * a.R + 8 + 16) +
+                              (unsigned long long)n_cand * (24 + 8 + 4 + 24);
+                a.bytes[1] += back;
+                a.bytes[2] += (unsigned long long)S;
+                a.bytes[3] += (unsigned long long)n_cand;
+            }
+        }
+    }
+    // the next hyperplane that crosses an edge (subpoly.py:110-111 for the others, decided from the crossing mask the
+    // last pruning pass left: a clear bit means the float test fails for every edge)
+    int i = first ? 0 : cnt[C_STEP];
+    const unsigned long long cross = *(unsigned long long *)(cnt + C_CROSS);
+    if (cnt[C_STICKY]) i = list.n;
+    while (i < list.n && !((cross >> list.idx[i]) & 1ull)) ++i;
+    const int more = i < list.n ? 1 : 0;
+    cnt[C_IDX] = more ? (int)list.idx[i] : -1;
+    cnt[C_PRUNE] = more ? (int)list.prune[i] : 0;
+    cnt[C_STEP] = more ? i + 1 : list.n;
+    for (int k = 0; k < C_V; ++k) cnt[k] = 0;
+    cnt[C_LONG] = 0;
+    cnt[C_RECS] = 0;
+    report[1] = more;
+    report[2] = cnt[C_V];
+    report[3] = cnt[C_E];
+    report[4] = i;
+    report[5] = cnt[C_STICKY];
+    __threadfence_system();
+    report[0] = seq;
+}
+
+static bool g_stream_steps = std::getenv("TNB_NO_STREAM_STEPS") == nullptr;  // A/B switch: one hyperplane at a time with host syncs
+
+// can the hyperplanes of this complex run as a device-driven stream?
+static bool stream_ok(const tnb_net *net, const tnb_complex *c, float eps, bool planar)
+{
+    return g_stream_steps && planar && !c->halo.enabled && c->E > 0 && eps == net->meta.eps && net->meta.R <= 64;
+}
+
+// Runs the steps lh[0 .. n_steps) (or, when the complex becomes small enough for the persistent kernel, a prefix
+// of them) and returns how many list entries are done in *consumed.  The host does not wait for the last sequence.
+static int steps_stream_impl(const tnb_net *net, tnb_complex *c, const int32_t *lh, int n_steps, float eps, cudaStream_t s, int *consumed)
+{
+    const NetMeta &m = net->meta;
+    const int H = m.H, R = m.R;
+    *consumed = 0;
+    if (n_steps <= 0) return TNB_OK;
+    if (n_steps > kMaxStepList) n_steps = kMaxStepList;  // the caller comes back for the rest
+    StepList list;
+    memset(&list, 0, sizeof(list));
+    list.n = n_steps;
+    for (int i = 0; i < n_steps; ++i) {
+        const int l = lh[2 * i], h = lh[2 * i + 1], idx = l * H + h;
+        if (l < 0 || h < 0 || h > H || idx >= R) { set_error("tnb_subpoly_steps: (l,h) out of range"); return TNB_ERR_INVALID; }
+        list.idx[i] = (unsigned char)idx;
+        list.prune[i] = h < H ? 1 : 0;
+    }
+    // mapped pinned report block, one per host thread; sequence numbers never repeat, so a late write of an
+    // earlier call cannot be mistaken for a report of this one
+    static thread_local int *report = nullptr, *report_dev = nullptr;
+    static thread_local int seq_base = 0;
+    if (!report) {
+        TNB_CUDA(cudaHostAlloc((void **)&report, kReportSlots * 8 * sizeof(int), cudaHostAllocMapped));
+        TNB_CUDA(cudaHostGetDevicePointer((void **)&report_dev, report, 0));
+        memset(report, 0, kReportSlots * 8 * sizeof(int));
+    }
+    volatile int *rep = report;  // set by wait_for to the slot of the report it waited for
+    if (c->bucket_mode != 0) {  // the cell grid must be all-zero for the contiguous segments (cells.cuh)
+        TNB_CUDA(cudaMemsetAsync(c->head.p, 0, (size_t)c->n_cells * sizeof(unsigned long long), s));
+        c->stamp = 0;
+        c->bucket_mode = 0;
+    }
+    StepArgs sa;
+    fill_step_args(net, c, eps, sa);
+    const PreMeta pm = pre_meta(m);
+    const size_t row_tile = (size_t)kThreads * R * sizeof(float);
+    const int64_t cand_ub = (int64_t)c->Vcap;
+    const unsigned nb2 = 2 * kScanMaxBlocks;
+    auto wait_for = [&](int seq) -> int {
+        rep = report + 8 * (seq & (kReportSlots - 1));
+        for (long spins = 0; rep[0] - seq < 0; ++spins) {
+            if ((spins & 0xfffff) == 0xfffff) {  // now and then: did the stream die?
+                cudaError_t e = cudaStreamQuery(s);
+                if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "device-driven step stream", __FILE__, __LINE__);
+                if (e == cudaSuccess && rep[0] - seq < 0) { set_error("device-driven step stream: the stream drained without a report"); return TNB_ERR_CUDA; }
+            }
+        }
+        return TNB_OK;
+    };
+    auto enqueue_sequence = [&](int seq) -> int {
+        int rc;
+        k_sd_count<<<nb2, kScanThreads, 0, s>>>(sa);
+        TNB_LAUNCH_CHECK();
+        k_sd_write<<<nb2, kScanThreads, 0, s>>>(sa);
+        TNB_LAUNCH_CHECK();
+        prof_begin(TNB_PROF_NEW_VERTICES, s);
+        if (net->fixed_cfg) k_sd_new_vertices<CfgRef><<<kSMs * 8, kThreads, row_tile, s>>>(m, sa);
+        else k_sd_new_vertices<CfgAny><<<kSMs * 8, kThreads, row_tile, s>>>(m, sa);
+        TNB_LAUNCH_CHECK();
+        prof_end(TNB_PROF_NEW_VERTICES, s, 0);
+        k_sd_cands<<<kSMs * 8, 256, 0, s>>>(sa, pm);
+        TNB_LAUNCH_CHECK();
+        if ((rc = cells_build(1, sa.cand, sa.cnt + C_CAND, cand_ub, sa.sig[c->vcur], (int2 *)sa.head, sa.cslot, sa.next, sa.cnt + C_RECS, sa.dim, s))) return rc;
+        prof_begin(TNB_PROF_PAIRS, s);
+        k_pair_count_seg<<<kSMs * 8, 256, 0, s>>>(sa.cand, sa.cnt, sa.sig[c->vcur], (const int2 *)sa.head, sa.next, sa.dim, 0ull, sa.pcount, sa.pcache, sa.remap, sa.cnt + C_IDX);
+        TNB_LAUNCH_CHECK();
+        prof_end(TNB_PROF_PAIRS, s, 0);
+        if ((rc = compact(cand_ub, ArrayCount{sa.pcount}, OffsetEmit{sa.poff}, sa.block_sums, sa.cnt + C_PAIRS, s, sa.cnt + C_CAND))) return rc;
+        prof_begin(TNB_PROF_PAIRS, s);
+        k_sd_pair_copy<<<kSMs * 16, 256, 0, s>>>(sa);
+        TNB_LAUNCH_CHECK();
+        k_sd_pair_long<<<kSMs * 2, kSortWarps * 32, 0, s>>>(sa);
+        TNB_LAUNCH_CHECK();
+        prof_end(TNB_PROF_PAIRS, s, 0);
+        if ((rc = cells_clear(1, sa.cnt + C_CAND, cand_ub, (int2 *)sa.head, sa.cslot, s))) return rc;
+        k_sd_keep_count<<<kScanMaxBlocks, kScanThreads, 0, s>>>(sa);
+        TNB_LAUNCH_CHECK();
+        k_sd_keep_write<<<kScanMaxBlocks, kScanThreads, 0, s>>>(sa);
+        TNB_LAUNCH_CHECK();
+        k_sd_finish<<<1, 32, 0, s>>>(sa, list, 0, seq, report_dev);
+        TNB_LAUNCH_CHECK();
+        return TNB_OK;
+    };
+    c->bytes_by_half = true;
+    c->counts_stale = true;
+    c->cross_stale = true;
+    c->maybe_dead = true;
+    int rc;
+    // Reports: seq0 = the initial choice; sequence k (k = 0, 1, ...) ends with report seq0 + 1 + k, which holds the
+    // sizes after it and the choice for sequence k + 1.  Sequence numbers are reserved up front.
+    const int seq0 = seq_base + 1;
+    seq_base += n_steps + 2;
+    k_sd_finish<<<1, 32, 0, s>>>(sa, list, 1, seq0, report_dev);
+    TNB_LAUNCH_CHECK();
+    if ((rc = enqueue_sequence(seq0 + 1))) return rc;   // run-ahead: enqueued before its own choice is known
+    int enq = 1;
+    *consumed = n_steps;
+    for (;;) {
+        // the report that precedes the sequence enqueued last: is that sequence a real step, and of which list entry?
+        if ((rc = wait_for(seq0 + enq - 1))) return rc;
+        const int more = rep[1], pos = rep[4];
+        const int64_t items = (int64_t)rep[2] + rep[3];   // sizes BEFORE that sequence
+        if (rep[5]) return TNB_OK;           // sticky error: what is in flight does nothing; complex_sync_counts reports it
+        if (!more) return TNB_OK;            // the sequence in flight finds no step: every plane left crosses nothing
+        if (pos + 1 >= n_steps) return TNB_OK;   // it runs the last list entry: nothing can follow
+        if (g_fused_steps && items <= g_fused_max_items) {
+            // small enough for the persistent kernel by now: let the sequence in flight finish; its report says where
+            // the list goes on
+            if ((rc = wait_for(seq0 + enq))) return rc;
+            if (!rep[5] && rep[1]) {
+                *consumed = rep[4];
+                c->V = rep[2];
+                c->E = rep[3];
+            }
+            return TNB_OK;
+        }
+        if ((rc = enqueue_sequence(seq0 + 1 + enq))) return rc;
+        ++enq;
+    }
+}
+
 // Drop the rows of dead vertices (order preserving) and renumber the edges: what the reference
 // does after every hyperplane (subpoly.py:268-277), done here once, when the complex is read.
 int complex_compact(tnb_complex *c, cudaStream_t s)
@@ -2723,6 +3109,13 @@ int tnb_set_capacity_factor(double f)
     if (!(f >= 1.0)) { set_error("capacity factor must be >= 1"); return TNB_ERR_INVALID; }
     g_capacity_factor = f;
     return TNB_OK;
+}
+
+int64_t tnb_set_fused_max_items(int64_t items)
+{
+    const int64_t before = g_fused_max_items;
+    if (items >= 0) g_fused_max_items = items;
+    return before;
 }
 
 int64_t tnb_set_cluster_max_items(int64_t items)
@@ -2931,6 +3324,12 @@ int tnb_subpoly_steps(const tnb_net *net, tnb_complex *c, const int32_t *lh, int
         if (mode) {
             const int rc = steps_persistent_impl(net, c, lh + 2 * i, n_steps - i, eps, mode, force != 0, s);
             if (rc != TNB_ERR_UNSUPPORTED) return rc;
+        }
+        if (stream_ok(net, c, eps, force != 0)) {   // a large complex: device-driven stream of launches, no host syncs
+            int consumed = 0;
+            const int rc = steps_stream_impl(net, c, lh + 2 * i, n_steps - i, eps, s, &consumed);
+            if (rc) return rc;
+            if (consumed > 0) { i += consumed; continue; }
         }
         const int rc = step_impl(net, c, lh[2 * i], lh[2 * i + 1], eps, force != 0, s);
         if (rc) return rc;

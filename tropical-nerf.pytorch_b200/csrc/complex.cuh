@@ -55,6 +55,7 @@ struct tnb_complex {
     uint64_t cross = ~0ull;
     bool cross_stale = false;       // the device holds a newer mask than `cross`
     bool maybe_dead = false;        // a prune ran since the last compaction: rows of dead vertices may exist
+    bool bytes_by_half = false;     // `bytes` was filled by the device-driven step stream: front half -> new vertices, back half -> pairs
     tnb::DevBuf<float> vert[2], out[2];
     tnb::DevBuf<uint64_t> sig[2];
     tnb::DevBuf<int2> edges[2];
@@ -76,7 +77,7 @@ struct tnb_complex {
     tnb::DevBuf<int> block_sums;    // [kScanMaxBlocks]
     tnb::DevBuf<uint32_t> scan_mask;  // one bit per edge / vertex: masked compactions (scan.cuh)
     tnb::DevBuf<int> counters;      // [16] device counters
-    tnb::DevBuf<unsigned long long> bytes;  // [2] algorithmic bytes accumulated by the fused kernels
+    tnb::DevBuf<unsigned long long> bytes;  // [4] algorithmic bytes (front / back half of a step) and units accumulated by the fused kernels
     int *h_counters = nullptr;      // pinned mirror (per thread, not owned)
     bool counts_stale = false;      // V/E are upper bounds; exact sizes are in counters[C_V], [C_E]
     int sticky_rc = 0;              // latched device error (capacity, curve path, slab exchange): every later call returns it

@@ -50,6 +50,17 @@ __device__ __forceinline__ void scan_slice(int64_t n, int64_t &begin, int64_t &e
     if (end > n) end = n;
 }
 
+// the same for block `bid` of `nb` (kernels that run two compactions side by side in one grid)
+__device__ __forceinline__ void scan_slice_part(int64_t n, int bid, int nb, int64_t &begin, int64_t &end)
+{
+    int64_t per = (n + nb - 1) / nb;
+    per = (per + 31) / 32 * 32;
+    begin = per * bid;
+    end = begin + per;
+    if (begin > n) begin = n;
+    if (end > n) end = n;
+}
+
 // The two phases as device functions, so that fused persistent kernels can run them between
 // grid / cluster syncs; NT = threads per CTA (blockDim.x).  The __global__ wrappers follow.
 template <int NT, class Count>
@@ -260,13 +271,12 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, const in
 // expensive and few items pass, the write pass reads the bit (MaskCount) instead of evaluating
 // count(i) again.  Slices are warp aligned, so a warp's ballot is exactly one mask word.
 template <class Count>
-__global__ void __launch_bounds__(kScanThreads) k_scan_count_mask(int64_t n, Count count, int *__restrict__ block_sums,
-                                                                  uint32_t *__restrict__ mask, const int *__restrict__ n_dev = nullptr)
+__device__ __forceinline__ void scan_count_mask_part(int64_t n, Count count, int *__restrict__ block_sums, uint32_t *__restrict__ mask,
+                                                     int bid, int nb)
 {
     constexpr int NW = kScanThreads / 32;
-    if (n_dev) n = *n_dev;
     int64_t begin, end;
-    scan_slice(n, begin, end);
+    scan_slice_part(n, bid, nb, begin, end);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int acc = 0;
     for (int64_t i0 = begin + warp * 32; i0 < end; i0 += kScanThreads) {
@@ -281,27 +291,32 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_count_mask(int64_t n, Cou
     if (threadIdx.x == 0) {
         int t = 0;
         for (int w = 0; w < NW; ++w) t += s[w];
-        block_sums[blockIdx.x] = t;
+        block_sums[bid] = t;
     }
+}
+template <class Count>
+__global__ void __launch_bounds__(kScanThreads) k_scan_count_mask(int64_t n, Count count, int *__restrict__ block_sums,
+                                                                  uint32_t *__restrict__ mask, const int *__restrict__ n_dev = nullptr)
+{
+    if (n_dev) n = *n_dev;
+    scan_count_mask_part(n, count, block_sums, mask, (int)blockIdx.x, (int)gridDim.x);
 }
 // Write pass over the bits k_scan_count_mask left: one 32-bit word (32 items) per thread and tile instead
 // of one item, so a tile is 8 192 items (the generic pass spends its time in the three CTA barriers of
 // each 256-item tile when nearly all items fail: 152 us for the 24 M skeleton slots of the large model).
 // Same slices, same order: emit(i, position, 1) for every set bit, ascending i.
 template <class Emit>
-__global__ void __launch_bounds__(kScanThreads) k_scan_write_mask(int64_t n, const uint32_t *__restrict__ mask, Emit emit,
-                                                                  const int *__restrict__ block_sums, int *__restrict__ total,
-                                                                  const int *__restrict__ n_dev = nullptr)
+__device__ __forceinline__ void scan_write_mask_part(int64_t n, const uint32_t *__restrict__ mask, Emit emit,
+                                                     const int *__restrict__ block_sums, int *__restrict__ total, int bid, int nb)
 {
     constexpr int NT = kScanThreads, NW = NT / 32;
-    if (n_dev) n = *n_dev;
     __shared__ int s_warp[NW];
     __shared__ int s_excl[32];
     __shared__ int s_base, s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     {
         int acc = 0;
-        const int upto = (blockIdx.x == 0) ? (int)gridDim.x : (int)blockIdx.x;
+        const int upto = (bid == 0) ? nb : bid;
         for (int b = threadIdx.x; b < upto; b += NT) acc += block_sums[b];
         acc = warp_sum(acc);
         if (lane == 0) s_warp[warp] = acc;
@@ -310,14 +325,14 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_write_mask(int64_t n, con
             int t = lane < NW ? s_warp[lane] : 0;
             t = warp_sum(t);
             if (threadIdx.x == 0) {
-                if (blockIdx.x == 0) { if (total) *total = t; s_base = 0; }
+                if (bid == 0) { if (total) *total = t; s_base = 0; }
                 else s_base = t;
             }
         }
         __syncthreads();
     }
     int64_t begin, end;
-    scan_slice(n, begin, end);
+    scan_slice_part(n, bid, nb, begin, end);
     const int64_t wb = begin >> 5, we = begin < end ? (end + 31) >> 5 : wb;  // slices are warp aligned: a word belongs to one CTA
     int running = s_base;
     for (int64_t tile = wb; tile < we; tile += NT) {
@@ -343,6 +358,14 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_write_mask(int64_t n, con
         }
         running += s_tile;
     }
+}
+template <class Emit>
+__global__ void __launch_bounds__(kScanThreads) k_scan_write_mask(int64_t n, const uint32_t *__restrict__ mask, Emit emit,
+                                                                  const int *__restrict__ block_sums, int *__restrict__ total,
+                                                                  const int *__restrict__ n_dev = nullptr)
+{
+    if (n_dev) n = *n_dev;
+    scan_write_mask_part(n, mask, emit, block_sums, total, (int)blockIdx.x, (int)gridDim.x);
 }
 struct MaskCount {
     const uint32_t *mask;

@@ -69,6 +69,7 @@ SIGNATURES = {
     "tnb_subpoly_step": (ctypes.c_int, [_P, _P, _I32, _I32, _F, _I32, _P]),
     "tnb_subpoly_steps": (ctypes.c_int, [_P, _P, _P, _I32, _F, _I32, _P]),
     "tnb_set_cluster_max_items": (_I64, [_I64]),
+    "tnb_set_fused_max_items": (_I64, [_I64]),
     "tnb_extract_mesh": (ctypes.c_int, [_P, _P, _F, ctypes.POINTER(_P), _P]),
     "tnb_mesh_destroy": (None, [_P]),
     "tnb_mesh_num_vertices": (_I64, [_P]),
