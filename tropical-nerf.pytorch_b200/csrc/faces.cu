@@ -44,7 +44,7 @@ constexpr int kMaxRow = 8192;      // hard limit of vertices per face row (sizes
 constexpr int kSmemRowStride = 16;  // rows up to this length are built in shared memory (16 KB per CTA: a dozen CTAs per SM)
 constexpr int kMaxZeros = 5;  // 2^5 regions = one per lane
 constexpr int kSortLocal = 32;  // face rows up to this length are angle-sorted in registers / local memory
-enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_RECS, F_NLONG, F_NUM = 16 };
+enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_RECS, F_NLONG, F_NHUGE, F_ERR_CELL, F_NLONGROWS, F_NUM = 16 };
 
 // ---- surface skeleton -----------------------------------------------------------------------------
 __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
@@ -175,6 +175,144 @@ __device__ __forceinline__ int zero_count(uint64_t pos, uint64_t neg, uint64_t g
     return __popcll(~(pos | neg) & colmask) + (3 - grid_mask(g, 0) - grid_mask(g, 1) - grid_mask(g, 2));
 }
 
+// ---- cell segments sorted by (zero count, vertex) ------------------------------------------------------
+// A face row is the list of a region's vertices ordered by (zero count, vertex number) and is emitted by its
+// first member.  With the records of every cell in THAT order (the key does not depend on the region), a lane
+// that is not the leader of its row knows after the first compatible record -- before, a member of one of the
+// reference's coincident-vertex clusters (hundreds of vertices in one cell) streamed the whole cluster to
+// learn that some other member leads -- and the leader's row arrives sorted.  One warp per touched cell:
+// up to 32 records in registers (bitonic over the lanes), up to kCellSortSmem in shared memory, longer
+// segments by a CTA each (k_cell_sort_huge).  Records are rebuilt from the vertex number (cells.cuh files the
+// vertex's packed signs with it), so only 64-bit keys are sorted.
+constexpr int kCellSortSmem = 1024;
+constexpr int kCellSortHuge = 8192;
+__device__ __forceinline__ tnb_bucket_rec rec_of_vertex(int v, const uint64_t *__restrict__ sig)
+{
+    tnb_bucket_rec r;
+    r.next = v;
+    r.v = v;
+    r.pos = sig[3 * (int64_t)v];
+    r.neg = sig[3 * (int64_t)v + 1];
+    r.grd = sig[3 * (int64_t)v + 2];
+    return r;
+}
+__global__ void __launch_bounds__(kThreads) k_cell_sort(int64_t n_slots, const int2 *__restrict__ slots, const int2 *__restrict__ cells,
+                                                        const tnb_bucket_rec *__restrict__ recs, tnb_bucket_rec *__restrict__ sorted,
+                                                        const uint64_t *__restrict__ sig, uint64_t colmask, int *__restrict__ huge_list,
+                                                        int *__restrict__ counters)
+{
+    __shared__ unsigned long long s_keys[kThreads / 32][kCellSortSmem];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    unsigned long long *keys = s_keys[warp];
+    for (int64_t t0 = ((int64_t)blockIdx.x * (kThreads / 32) + warp) * 32; t0 < n_slots; t0 += (int64_t)gridDim.x * kThreads) {  // warp uniform
+        const int64_t t = t0 + lane;
+        int2 sl = make_int2(-1, 0);
+        if (t < n_slots) sl = slots[t];
+        unsigned todo = __ballot_sync(0xffffffffu, sl.x >= 0 && sl.y == 0);  // the li == 0 entry stands for its cell
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const int cell = __shfl_sync(0xffffffffu, sl.x, src);
+            const int2 seg = cells[cell];  // {records, first record}
+            if (seg.x <= 32) {
+                tnb_bucket_rec r = {0, 0, 0ull, 0ull, 0ull};
+                unsigned long long key = ~0ull;
+                if (lane < seg.x) {
+                    r = recs[seg.y + lane];
+                    key = ((unsigned long long)zero_count(r.pos, r.neg, r.grd, colmask) << 32) | (unsigned)r.v;
+                }
+                int from = lane;
+                if (seg.x > 1) {  // bitonic network over the lanes; the source lane travels with the key
+#pragma unroll
+                    for (int k = 2; k <= 32; k <<= 1)
+#pragma unroll
+                        for (int j = k >> 1; j > 0; j >>= 1) {
+                            const unsigned long long ok = __shfl_xor_sync(0xffffffffu, key, j);
+                            const int of = __shfl_xor_sync(0xffffffffu, from, j);
+                            const bool up = (lane & k) == 0 || k == 32, lower = (lane & j) == 0;
+                            const bool take_min = lower == up;
+                            if (take_min ? ok < key : ok > key) { key = ok; from = of; }
+                        }
+                }
+                // lane p holds the p-th key and where its record sits
+                tnb_bucket_rec o;
+                o.next = __shfl_sync(0xffffffffu, r.next, from);
+                o.v = __shfl_sync(0xffffffffu, r.v, from);
+                o.pos = __shfl_sync(0xffffffffu, r.pos, from);
+                o.neg = __shfl_sync(0xffffffffu, r.neg, from);
+                o.grd = __shfl_sync(0xffffffffu, r.grd, from);
+                if (lane < seg.x) sorted[seg.y + lane] = o;
+            } else if (seg.x <= kCellSortSmem) {
+                int n = 64;
+                while (n < seg.x) n <<= 1;
+                for (int i = lane; i < n; i += 32) {
+                    unsigned long long key = ~0ull;
+                    if (i < seg.x) {
+                        const tnb_bucket_rec r = recs[seg.y + i];
+                        key = ((unsigned long long)zero_count(r.pos, r.neg, r.grd, colmask) << 32) | (unsigned)r.v;
+                    }
+                    keys[i] = key;
+                }
+                __syncwarp();
+                for (int k = 2; k <= n; k <<= 1)
+                    for (int j = k >> 1; j > 0; j >>= 1) {
+                        for (int i = lane; i < n; i += 32) {
+                            const int p = i ^ j;
+                            if (p > i) {
+                                const unsigned long long x = keys[i], y = keys[p];
+                                const bool up = (i & k) == 0;
+                                if ((x > y) == up) { keys[i] = y; keys[p] = x; }
+                            }
+                        }
+                        __syncwarp();
+                    }
+                for (int i = lane; i < seg.x; i += 32) sorted[seg.y + i] = rec_of_vertex((int)(uint32_t)keys[i], sig);
+                __syncwarp();
+            } else if (lane == 0) {
+                if (seg.x > kCellSortHuge) atomicOr(counters + F_ERR_CELL, 1);
+                else huge_list[atomicAdd(counters + F_NHUGE, 1)] = cell;
+            }
+        }
+    }
+}
+// segments of more than kCellSortSmem records: a CTA each, keys in dynamic shared memory (never seen for a sphere;
+// the large torus has cells with > 1000 coincident vertices)
+__global__ void __launch_bounds__(256) k_cell_sort_huge(const int *__restrict__ huge_list, const int *__restrict__ counters,
+                                                        const int2 *__restrict__ cells, const tnb_bucket_rec *__restrict__ recs,
+                                                        tnb_bucket_rec *__restrict__ sorted, const uint64_t *__restrict__ sig, uint64_t colmask)
+{
+    extern __shared__ unsigned long long s_huge[];  // [kCellSortHuge]
+    const int n_huge = counters[F_NHUGE];
+    for (int h = blockIdx.x; h < n_huge; h += gridDim.x) {
+        const int2 seg = cells[huge_list[h]];
+        int n = kCellSortSmem;
+        while (n < seg.x) n <<= 1;
+        for (int i = threadIdx.x; i < n; i += blockDim.x) {
+            unsigned long long key = ~0ull;
+            if (i < seg.x) {
+                const tnb_bucket_rec r = recs[seg.y + i];
+                key = ((unsigned long long)zero_count(r.pos, r.neg, r.grd, colmask) << 32) | (unsigned)r.v;
+            }
+            s_huge[i] = key;
+        }
+        __syncthreads();
+        for (int k = 2; k <= n; k <<= 1)
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                for (int i = threadIdx.x; i < n; i += blockDim.x) {
+                    const int p = i ^ j;
+                    if (p > i) {
+                        const unsigned long long x = s_huge[i], y = s_huge[p];
+                        const bool up = (i & k) == 0;
+                        if ((x > y) == up) { s_huge[i] = y; s_huge[p] = x; }
+                    }
+                }
+                __syncthreads();
+            }
+        for (int i = threadIdx.x; i < seg.x; i += blockDim.x) sorted[seg.y + i] = rec_of_vertex((int)(uint32_t)s_huge[i], sig);
+        __syncthreads();
+    }
+}
+
 // One warp per surface vertex a; lane q builds the row of a's q-th adjacent region.
 // mode 0: rows_per_vertex[a] = bit mask of the regions (lanes) whose row a leads and keeps (distinct rows of
 //         >= 3 vertices; their count is the popcount), max width.  mode 1 walks the buckets again only for
@@ -248,10 +386,11 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
             // collect the region's vertices ordered by (zero count, vertex number): the row
             // order r_idx_as_tensor builds from regions_to_vertices' group-by-zero-count output
             const int2 seg = cells[cell_of(cell[0], cell[1], cell[2], dim)];  // {records, first record} of the region's cell
-            const unsigned long long my_key = ((unsigned long long)ka << 32) | (unsigned)a;
             bool led_by_other = false;
             if (mine_cell) {
-                // the cell's segment is contiguous (cells.cuh): four independent 32-byte loads in flight per lane
+                // the cell's segment is contiguous and sorted by key (k_cell_sort): four independent 32-byte loads in
+                // flight per lane; the FIRST member of the row leads it, so a lane whose first compatible record is
+                // not a itself is done, and the leader's row arrives in row order
                 for (int i0 = 0; i0 < seg.x && !led_by_other; i0 += 4) {
                     tnb_bucket_rec r4[4];
 #pragma unroll
@@ -268,15 +407,13 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
 #pragma unroll
                         for (int d = 0; d < 3; ++d) in = in && cell[d] >= bb.lo[d] && cell[d] <= bb.hi[d];
                         if (!in) continue;
-                        const unsigned long long key = ((unsigned long long)zero_count(pb, nb, gb, colmask) << 32) | (unsigned)b;
-                        if (key < my_key) { led_by_other = true; continue; }  // that vertex emits this row, not a
-                        if (cnt < stride) mine[cnt] = key;
+                        if (cnt == 0 && b != (int)a) { led_by_other = true; continue; }  // that vertex emits this row, not a
+                        if (cnt < stride) mine[cnt] = ((unsigned long long)zero_count(pb, nb, gb, colmask) << 32) | (unsigned)b;
                         ++cnt;
                     }
                 }
             }
             if (led_by_other) cnt = 0;
-            if (cnt <= stride) thread_sort(mine, cnt);
             lead = cnt >= 3;  // every surviving row starts with a itself
         }
         {   // a row that does not fit: the whole vertex goes to the long pass (warp uniform)
@@ -357,10 +494,14 @@ __global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ 
                                                         const float *__restrict__ vert, int *__restrict__ rows,
                                                         const int *__restrict__ row_cnt,
                                                         unsigned long long *__restrict__ key_scratch,
-                                                        int *__restrict__ counters)
+                                                        int *__restrict__ counters, int *__restrict__ long_rows)
 {
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
         const int cnt = row_cnt[p];
+        if (cnt > kSortLocal && long_rows) {  // a warp's job (k_sort_rows_long): one thread sorting hundreds of keys held the whole launch up
+            long_rows[atomicAdd(counters + F_NLONGROWS, 1)] = (int)p;
+            continue;
+        }
         int *row = rows + p * W;
         float sx = 0.0f, sy = 0.0f, sz = 0.0f;
         bool origin = false;
@@ -414,6 +555,121 @@ __global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ 
             for (int j = 0; j < cnt; ++j) keys[j] = (unsigned)row[(uint32_t)keys[j]];
             for (int j = 0; j < cnt; ++j) row[j] = (int)(uint32_t)keys[j];
         }
+    }
+}
+
+// The rows of more than kSortLocal vertices (the coincident-vertex clusters of the reference's chunk-overlap
+// duplicates: hundreds of vertices), one WARP each: positions gathered into shared memory by all lanes, the
+// centre summed left to right by one lane (the order the oracle defines), the normal at the centre, scores by
+// all lanes, 64-bit keys (descending score, then original position: stable) sorted by a bitonic network in
+// shared memory.  Same operations per element as k_sort_rows, so the order is bit-identical.
+constexpr int kLongRowSmem = 1024;
+constexpr int kLongRowWarps = 2;
+template <class C>
+__global__ void __launch_bounds__(kLongRowWarps * 32) k_sort_rows_long(const __grid_constant__ NetMeta n, int W, const float *__restrict__ vert,
+                                                                       int *__restrict__ rows, const int *__restrict__ row_cnt,
+                                                                       const int *__restrict__ long_rows,
+                                                                       unsigned long long *__restrict__ key_scratch, int *__restrict__ counters)
+{
+    __shared__ float s_pos[kLongRowWarps][3][kLongRowSmem];
+    __shared__ unsigned long long s_keys[kLongRowWarps][kLongRowSmem];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n_long = counters[F_NLONGROWS];
+    float *px = s_pos[warp][0], *py = s_pos[warp][1], *pz = s_pos[warp][2];
+    unsigned long long *keys = s_keys[warp];
+    for (int li = blockIdx.x * kLongRowWarps + warp; li < n_long; li += gridDim.x * kLongRowWarps) {
+        const int64_t p = long_rows[li];
+        const int cnt = row_cnt[p];
+        int *row = rows + p * W;
+        if (cnt > kLongRowSmem) {  // longer than the shared buffers: one lane, keys in the HBM scratch (as k_sort_rows did)
+            if (lane == 0) {
+                float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+                bool origin = false;
+                for (int j = 0; j < cnt; ++j) {
+                    const float *q = vert + 3 * (int64_t)row[j];
+                    sx = sx + q[0];
+                    sy = sy + q[1];
+                    sz = sz + q[2];
+                    const float n2 = (q[0] * q[0] + q[1] * q[1]) + q[2] * q[2];
+                    if (!(__fsqrt_rn(n2) > 0.0f)) origin = true;
+                }
+                if (origin) atomicOr(counters + F_ERR_ORIGIN, 1);
+                const float k = (float)cnt;
+                float mean[3] = {__fdiv_rn(sx, k), __fdiv_rn(sy, k), __fdiv_rn(sz, k)};
+                float nrm[3];
+                sdf_grad<C>(n, mean, nrm, true);
+                const float *q0 = vert + 3 * (int64_t)row[0];
+                const float a[3] = {q0[0] - mean[0], q0[1] - mean[1], q0[2] - mean[2]};
+                const float an = fmaxf(__fsqrt_rn((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]), 1e-8f);
+                const float ua[3] = {__fdiv_rn(a[0], an), __fdiv_rn(a[1], an), __fdiv_rn(a[2], an)};
+                unsigned long long *ks = key_scratch + atomicAdd(counters + F_LONG_CURSOR, cnt);
+                for (int j = 0; j < cnt; ++j) {
+                    const float *q = vert + 3 * (int64_t)row[j];
+                    const float u[3] = {q[0] - mean[0], q[1] - mean[1], q[2] - mean[2]};
+                    const uint32_t b = __float_as_uint(angle_score(a, ua, u, nrm));
+                    const uint32_t asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);  // orders like the float
+                    ks[j] = ((unsigned long long)(0xFFFFFFFFu - asc) << 32) | (unsigned)j;
+                }
+                thread_sort(ks, cnt);
+                for (int j = 0; j < cnt; ++j) ks[j] = (unsigned)row[(uint32_t)ks[j]];
+                for (int j = 0; j < cnt; ++j) row[j] = (int)(uint32_t)ks[j];
+            }
+            __syncwarp();
+            continue;
+        }
+        bool origin = false;
+        for (int j = lane; j < cnt; j += 32) {
+            const float *q = vert + 3 * (int64_t)row[j];
+            const float x = q[0], y = q[1], z = q[2];
+            px[j] = x; py[j] = y; pz[j] = z;
+            const float n2 = (x * x + y * y) + z * z;
+            if (!(__fsqrt_rn(n2) > 0.0f)) origin = true;
+        }
+        if (__any_sync(0xffffffffu, origin) && lane == 0) atomicOr(counters + F_ERR_ORIGIN, 1);  // geometry.py:496 would drop this vertex
+        __syncwarp();
+        float sx = 0.0f, sy = 0.0f, sz = 0.0f;
+        if (lane == 0)
+            for (int j = 0; j < cnt; ++j) { sx = sx + px[j]; sy = sy + py[j]; sz = sz + pz[j]; }
+        sx = __shfl_sync(0xffffffffu, sx, 0);
+        sy = __shfl_sync(0xffffffffu, sy, 0);
+        sz = __shfl_sync(0xffffffffu, sz, 0);
+        const float k = (float)cnt;
+        float mean[3] = {__fdiv_rn(sx, k), __fdiv_rn(sy, k), __fdiv_rn(sz, k)};
+        float nrm[3];
+        sdf_grad<C>(n, mean, nrm, true);  // every lane the same point: the same value
+        const float a[3] = {px[0] - mean[0], py[0] - mean[1], pz[0] - mean[2]};
+        const float an = fmaxf(__fsqrt_rn((a[0] * a[0] + a[1] * a[1]) + a[2] * a[2]), 1e-8f);
+        const float ua[3] = {__fdiv_rn(a[0], an), __fdiv_rn(a[1], an), __fdiv_rn(a[2], an)};
+        int m = 64;
+        while (m < cnt) m <<= 1;
+        for (int j = lane; j < m; j += 32) {
+            unsigned long long key = ~0ull;
+            if (j < cnt) {
+                const float u[3] = {px[j] - mean[0], py[j] - mean[1], pz[j] - mean[2]};
+                const uint32_t b = __float_as_uint(angle_score(a, ua, u, nrm));
+                const uint32_t asc = (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+                key = ((unsigned long long)(0xFFFFFFFFu - asc) << 32) | (unsigned)j;
+            }
+            keys[j] = key;
+        }
+        __syncwarp();
+        for (int kk = 2; kk <= m; kk <<= 1)
+            for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+                for (int i = lane; i < m; i += 32) {
+                    const int q = i ^ jj;
+                    if (q > i) {
+                        const unsigned long long x = keys[i], y = keys[q];
+                        const bool up = (i & kk) == 0;
+                        if ((x > y) == up) { keys[i] = y; keys[q] = x; }
+                    }
+                }
+                __syncwarp();
+            }
+        int *ids = reinterpret_cast<int *>(px);  // the positions are not needed any more
+        for (int j = lane; j < cnt; j += 32) ids[j] = row[(uint32_t)keys[j]];
+        __syncwarp();
+        for (int j = lane; j < cnt; j += 32) row[j] = ids[j];
+        __syncwarp();
     }
 }
 
@@ -648,6 +904,21 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     TNB_LAUNCH_CHECK();
     TNB_CUDA(cudaMemsetAsync(counters.p + F_RECS, 0, sizeof(int), s));
     if ((rc = cells_build(8, nullptr, nullptr, Vs, sig.p, (int2 *)head.p, cslot.p, next.p, counters.p + F_RECS, dim, s))) return rc;
+    DevBuf<tnb_bucket_rec> sorted;    // the same segments, every one ordered by (zero count, vertex)
+    DevBuf<int> huge_list;
+    TNB_CUDA(sorted.reserve((size_t)Vs * 8));
+    TNB_CUDA(huge_list.reserve((size_t)std::max<int64_t>(Vs * 8 / kCellSortSmem, 1) + 1));
+    k_cell_sort<<<grid_for(Vs * 8, kThreads), kThreads, 0, s>>>(Vs * 8, cslot.p, (const int2 *)head.p, next.p, sorted.p, sig.p, colmask, huge_list.p, counters.p);
+    TNB_LAUNCH_CHECK();
+    {
+        static bool attr_set = false;
+        if (!attr_set) {
+            TNB_CUDA(cudaFuncSetAttribute(k_cell_sort_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, kCellSortHuge * (int)sizeof(unsigned long long)));
+            attr_set = true;
+        }
+        k_cell_sort_huge<<<kSMs, 256, kCellSortHuge * sizeof(unsigned long long), s>>>(huge_list.p, counters.p, (const int2 *)head.p, next.p, sorted.p, sig.p, colmask);
+        TNB_LAUNCH_CHECK();
+    }
     const unsigned gw = grid_for(Vs, kThreads / 32);
     const size_t rows_smem = (size_t)kThreads * kSmemRowStride * sizeof(unsigned long long);
     DevBuf<unsigned long long> scratch;
@@ -658,13 +929,14 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     TNB_CUDA(cudaMemsetAsync(is_long.p, 0, (size_t)Vs, s));
     // fast pass: every vertex, rows in shared memory
     prof_begin(TNB_PROF_FACE_ROWS, s);
-    k_region_rows<<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, next.p, dim, colmask, 0, kSmemRowStride, nullptr,
+    k_region_rows<<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
                                                   rows_per_vertex.p, nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi,
                                                   nullptr, 0, is_long.p, long_list.p);
     TNB_LAUNCH_CHECK();
     prof_end(TNB_PROF_FACE_ROWS, s, Vs, Vs * 28);
     if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
     if (h[F_ERR_ZEROS]) { set_error("a surface vertex lies on more than 5 planes: more than 32 adjacent regions"); return TNB_ERR_UNSUPPORTED; }
+    if (h[F_ERR_CELL]) { set_error("a marks-grid cell holds more than " + std::to_string(kCellSortHuge) + " surface vertices"); return TNB_ERR_UNSUPPORTED; }
     const int n_long = h[F_NLONG];
     int stride = 0;
     unsigned gl = 0;
@@ -677,7 +949,7 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         gl = std::min<unsigned>(grid_for(n_long, kThreads / 32), kSMs * 4);
         TNB_CUDA(scratch.reserve((size_t)gl * kThreads * stride));
         prof_begin(TNB_PROF_FACE_ROWS, s);
-        k_region_rows<<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, next.p, dim, colmask, 0, stride, scratch.p, rows_per_vertex.p,
+        k_region_rows<<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, stride, scratch.p, rows_per_vertex.p,
                                               nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr);
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_FACE_ROWS, s, n_long, (int64_t)n_long * 28);
@@ -693,12 +965,12 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     TNB_CUDA(m->poly.reserve((size_t)P * W));
     TNB_CUDA(m->pcnt.reserve((size_t)P));
     prof_begin(TNB_PROF_FACE_ROWS, s);
-    k_region_rows<<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, next.p, dim, colmask, 1, kSmemRowStride, nullptr,
+    k_region_rows<<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
                                                   rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi,
                                                   nullptr, 0, is_long.p, nullptr);
     TNB_LAUNCH_CHECK();
     if (n_long > 0) {
-        k_region_rows<<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, next.p, dim, colmask, 1, stride, scratch.p, rows_per_vertex.p,
+        k_region_rows<<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, stride, scratch.p, rows_per_vertex.p,
                                               row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr);
         TNB_LAUNCH_CHECK();
     }
@@ -707,9 +979,17 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         unsigned g = grid_for(P, kThreads);
         DevBuf<unsigned long long> score_scratch;  // one segment per long row (their total was counted with the rows)
         if (W > kSortLocal) TNB_CUDA(score_scratch.reserve((size_t)std::max(h[F_LONG_TOTAL], 1)));
-        if (net->fixed_cfg) k_sort_rows<CfgRef><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p);
-        else k_sort_rows<CfgAny><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p);
+        DevBuf<int> long_rows;
+        TNB_CUDA(long_rows.reserve((size_t)std::max(h[F_LONG_TOTAL] / (kSortLocal + 1) + 1, 1)));  // every long row counted more than kSortLocal keys
+        if (net->fixed_cfg) k_sort_rows<CfgRef><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p, long_rows.p);
+        else k_sort_rows<CfgAny><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p, long_rows.p);
         TNB_LAUNCH_CHECK();
+        if (W > kSortLocal) {
+            const unsigned gl2 = (unsigned)std::min<int64_t>(h[F_LONG_TOTAL] / (kSortLocal + 1) / kLongRowWarps + 1, kSMs * 8);
+            if (net->fixed_cfg) k_sort_rows_long<CfgRef><<<gl2, kLongRowWarps * 32, 0, s>>>(nm, W, m->vert.p, m->poly.p, m->pcnt.p, long_rows.p, score_scratch.p, counters.p);
+            else k_sort_rows_long<CfgAny><<<gl2, kLongRowWarps * 32, 0, s>>>(nm, W, m->vert.p, m->poly.p, m->pcnt.p, long_rows.p, score_scratch.p, counters.p);
+            TNB_LAUNCH_CHECK();
+        }
     }
     // fan triangles, ordered by fan step then by row
     if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
