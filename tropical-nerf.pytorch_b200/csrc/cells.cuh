@@ -156,16 +156,19 @@ inline int cells_clear(int K, const int *n_dev, int64_t n, int2 *cells, const in
     return TNB_OK;
 }
 
-// ascending sort of one key per lane (bitonic network over the warp's 32 lanes, register shuffles)
-__device__ __forceinline__ int warp_sort_asc(int key)
+// ascending sort of one key per lane (bitonic network over the lanes, register shuffles).  Only the first `count`
+// lanes hold keys (the others pass INT_MAX): the network stops at the first power of two >= count -- most
+// partner lists have one to four entries, for which the full 15-stage network was most of the kernel's
+// shuffle traffic.
+__device__ __forceinline__ int warp_sort_asc(int key, int count = 32)
 {
     const int lane = threadIdx.x & 31;
-#pragma unroll
-    for (int k = 2; k <= 32; k <<= 1)
-#pragma unroll
+    int n = 2;
+    while (n < count) n <<= 1;  // warp uniform
+    for (int k = 2; k <= n; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
             const int o = __shfl_xor_sync(0xffffffffu, key, j);
-            const bool up = (lane & k) == 0 || k == 32, lower = (lane & j) == 0;
+            const bool up = (lane & k) == 0 || k == n, lower = (lane & j) == 0;
             key = (lower == up) ? min(key, o) : max(key, o);
         }
     return key;

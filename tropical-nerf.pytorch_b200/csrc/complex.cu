@@ -1336,9 +1336,18 @@ __global__ void __launch_bounds__(256) k_pair_count_seg(const int *__restrict__ 
     }
     __shared__ int s_keys[8][kCachedPartners], s_incl[8][32], s_base[8][32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int n_cand = cnt[C_CAND], warps = gridDim.x * (blockDim.x >> 5);
-    for (int a = blockIdx.x * (blockDim.x >> 5) + warp; a < n_cand; a += warps) {
-        const PartnerQuery q = partner_query(cand[a], sig);
+    // The candidates are taken in RECORD order (K = 1: every candidate has exactly one record, and records of one cell
+    // and of neighbouring cells are neighbours in memory): the record already holds the candidate's number and packed
+    // signs, so the chain candidate -> vertex -> signature (two dependent loads, the top stall of this kernel) is one
+    // load, and consecutive warps read the same cell headers and records.
+    const int n_recs = cnt[C_RECS], warps = gridDim.x * (blockDim.x >> 5);
+    for (int ri = blockIdx.x * (blockDim.x >> 5) + warp; ri < n_recs; ri += warps) {
+        const tnb_bucket_rec me = recs[ri];
+        const int a = me.next;  // the item number (cells.cuh)
+        PartnerQuery q;
+        q.va = me.v; q.pa = me.pos; q.na = me.neg; q.ga = me.grd;
+        q.za = ~(q.pa | q.na);
+        q.ba = cell_box(q.ga);
         int found = 0;
         stream_partners(q, cells, recs, dim, colmask, s_incl[warp], s_base[warp], [&](bool hit, int vb) {
             const unsigned ball = __ballot_sync(0xffffffffu, hit);
@@ -1351,7 +1360,7 @@ __global__ void __launch_bounds__(256) k_pair_count_seg(const int *__restrict__ 
         __syncwarp();
         if (found > 0 && found <= kCachedPartners) {
             // ascending partner number = the order unique(dim=0) leaves (subpoly.py:243-244)
-            const int key = warp_sort_asc(lane < found ? s_keys[warp][lane] : 0x7fffffff);
+            const int key = warp_sort_asc(lane < found ? s_keys[warp][lane] : 0x7fffffff, found);
             if (lane < found) pcache[(int64_t)a * kCachedPartners + lane] = key;
         }
         if (lane == 0) {

@@ -44,7 +44,7 @@ constexpr int kMaxRow = 8192;      // hard limit of vertices per face row (sizes
 constexpr int kSmemRowStride = 16;  // rows up to this length are built in shared memory (16 KB per CTA: a dozen CTAs per SM)
 constexpr int kMaxZeros = 5;  // 2^5 regions = one per lane
 constexpr int kSortLocal = 32;  // face rows up to this length are angle-sorted in registers / local memory
-enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_RECS, F_NLONG, F_NHUGE, F_ERR_CELL, F_NLONGROWS, F_NUM = 16 };
+enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_RECS, F_NLONG, F_NHUGE, F_ERR_CELL, F_NLONGROWS, F_NUM = 24 };
 
 // ---- surface skeleton -----------------------------------------------------------------------------
 __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
