@@ -241,6 +241,31 @@ int tnb_grid_train_backward_backward(const tnb_grid_desc *desc, const float *d_t
                                      const float *d_ddx, float *d_dtable, float *d_ddenc,
                                      float *d_dx2, void *stream);
 
+/* ---- stage-level pieces of the curve-approximation path ------------------------------ */
+/* Net.forward(x, gather=True, group=8) (tropical/stanford/model.py:52-76, the masking of :65-70):
+ * d_x holds groups of 8 points (the corners of an edge's box, geometry.corner_points); inside a
+ * group a hidden neuron stays linear iff it is > eps at the first or the last point, else it is
+ * multiplied by 0.  d_out [groups*8][R] = the gathered pre-activation rows (last column o1 - o0),
+ * d_raw [groups*8][2] = the last layer's output (may be NULL). */
+int tnb_net_outputs_group8(const tnb_net *net, const float *d_x, int64_t groups, float eps,
+                           float *d_out, float *d_raw, void *stream);
+/* geometry.intersection_of_two_planes(p, q, plane="xz") (tropical/geometry.py:24-138) with
+ * batched_polynomial_roots / _batched_polynomial_roots (:259-300): d_p, d_q [count][8] corner
+ * values of the two planes, d_out [count][3] trilinear coordinates (-1 where the reference
+ * leaves "no root"; bilinear configurations -1 as with the reference's failover off). */
+int tnb_curve_intersections(const float *d_p, const float *d_q, int64_t count, float *d_out,
+                            void *stream);
+/* The ordering of geometry.sort_polygon_vertices_batch(v, n, idx) (tropical/geometry.py:483-516):
+ * d_v [B][M][3] padded face rows (norm 0 = padding), d_normals [B][3]; d_order [B][M] = the
+ * permutation that sorts every row by angle around its centre (stable, descending score),
+ * d_valid_sorted [B][M] = the padding mask in that order. */
+int tnb_polygon_order(const float *d_v, const float *d_normals, int64_t B, int32_t M, int32_t base,
+                      int64_t *d_order, uint8_t *d_valid_sorted, void *stream);
+/* extract_skeleton's third return value (tropical/subpoly.py:556-581): for every mesh vertex its
+ * row in the vertex arrays of the complex the mesh was extracted from (for a complex built by
+ * tnb_complex_from_arrays: the caller's numbering). */
+int tnb_mesh_read_vertex_index(const tnb_mesh *m, int64_t *d_index, void *stream);
+
 /* ---- knobs / introspection ------------------------------------------------------ */
 /* work-buffer growth factor for the complex (default 4.0) */
 int tnb_set_capacity_factor(double f);

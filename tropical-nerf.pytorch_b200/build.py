@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT_DIR, "libtropical_b200.so")
-SOURCES = ["net_kernels.cu", "complex.cu", "faces.cu", "grid_train.cu"]
+SOURCES = ["net_kernels.cu", "complex.cu", "faces.cu", "grid_train.cu", "compat.cu"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

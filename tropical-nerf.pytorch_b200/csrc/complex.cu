@@ -501,10 +501,13 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
         SkelEdgeEmit emit{q, raw.p, used.p - base};
         k_scan_write_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, slot_mask.p, emit, block_sums.p, total.p);
         TNB_LAUNCH_CHECK();
-        // vertex pass: count, size, then place
+        // vertex pass: count, size, then place (one bit per grid vertex: ~90 % of them are on no kept edge, and the
+        // generic write pass spent its time in the CTA barriers of their tiles)
         FlagCount fc{used.p};
         int64_t vblocks = std::min<int64_t>((MS + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
-        k_scan_count<<<(unsigned)vblocks, kScanThreads, 0, s>>>(MS, nullptr, fc, block_sums.p);
+        DevBuf<uint32_t> vmask;
+        TNB_CUDA(vmask.reserve((size_t)((MS + 31) / 32 + kScanMaxBlocks + 64)));
+        k_scan_count_mask<<<(unsigned)vblocks, kScanThreads, 0, s>>>(MS, fc, block_sums.p, vmask.p);
         TNB_LAUNCH_CHECK();
         std::vector<int> hv(vblocks);
         TNB_CUDA(cudaMemcpyAsync(hv.data(), block_sums.p, vblocks * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -517,7 +520,7 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
         if (rc) return rc;
         SkelVertEmit vemit{nullptr, net->meta.marks, net->meta.pre_2s, net->meta.pre_scale, M, remap.p, c->cvert(),
                            c->tag[c->vcur].p, sw->x_lo, sw->tag_lower ? sw->x_lo : -1, sw->tag_upper ? sw->x_hi : -1};
-        k_scan_write<<<(unsigned)vblocks, kScanThreads, 0, s>>>(MS, nullptr, fc, vemit, block_sums.p, total.p + 1);
+        k_scan_write_mask<<<(unsigned)vblocks, kScanThreads, 0, s>>>(MS, vmask.p, vemit, block_sums.p, total.p + 1);
         TNB_LAUNCH_CHECK();
         TNB_CUDA(cudaMemcpyAsync(c->cedges(), raw.p, (size_t)E * sizeof(int2), cudaMemcpyDeviceToDevice, s));
         k_remap_edges<<<grid_for(E, 256), 256, 0, s>>>(c->cedges(), E, remap.p - base);
@@ -1303,9 +1306,12 @@ __device__ __forceinline__ void stream_partners(const PartnerQuery &q, const int
     __syncwarp();
     for (int i0 = 0; i0 < total; i0 += 128) {
         tnb_bucket_rec r[4];
-        bool have[4];
+        bool have[4] = {false, false, false, false};
+        // nearly every neighbourhood holds fewer than 32 records: the unrolled slots past the end are skipped as a
+        // warp (uniform test), not predicated off (they were 3/4 of the instructions this kernel issued)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
+            if (i0 + 32 * u >= total) break;  // warp uniform
             const int i = i0 + 32 * u + lane;
             have[u] = i < total;
             if (have[u]) {

@@ -30,7 +30,7 @@ __device__ __forceinline__ double shfl_double(double v, int src)
 // first or the last corner, else it is multiplied by 0.
 // Four candidates at a time, 8 lanes (one corner each) per candidate.
 template <class C>
-__device__ void warp_group8_columns(const NetMeta &n, bool need, const float e0[3], const float e1[3], float eps, int colA,
+static __device__ void warp_group8_columns(const NetMeta &n, bool need, const float e0[3], const float e1[3], float eps, int colA,
                                     int colB, float pA[8], float pB[8])
 {
     const int lane = threadIdx.x & 31, grp = lane >> 3, corner = lane & 7;
@@ -152,7 +152,7 @@ __device__ __forceinline__ int quadratic_roots(double a, double b, double c, dou
     return 2;
 }
 // interior points of (0,1), ascending, where a polynomial of degree <= 3 has a root: the cut points one degree up
-__device__ __noinline__ int roots_inside01(const double *c, int deg, double *r)
+static __device__ __noinline__ int roots_inside01(const double *c, int deg, double *r)
 {
     while (deg > 0 && c[0] == 0.0) { ++c; --deg; }
     int n = 0;
@@ -189,7 +189,7 @@ __device__ __noinline__ int roots_inside01(const double *c, int deg, double *r)
     return n;
 }
 // largest real root in [0,1] of c[0] t^deg + ... + c[deg] (1 <= deg <= 4, c[0] != 0), or -1
-__device__ __noinline__ double last_root01(const double *c, int deg)
+static __device__ __noinline__ double last_root01(const double *c, int deg)
 {
     if (deg == 1) {
         const double t = -c[1] / c[0];
@@ -219,7 +219,7 @@ __device__ __noinline__ double last_root01(const double *c, int deg)
 
 // p, q: the two planes' values at the 8 corners (valid where need).  out = (x, y, z) trilinear
 // coordinates.  geometry.intersection_of_two_planes (geometry.py:24-138) for one edge per lane.
-__device__ void warp_curve_intersection(bool need, const float *p, const float *q, float out[3])
+static __device__ void warp_curve_intersection(bool need, const float *p, const float *q, float out[3])
 {
     const int r[4] = {0, 1, 4, 5}, s[4] = {2, 3, 6, 7};
     double co[5] = {0.0, 0.0, 0.0, 0.0, 0.0};

@@ -29,6 +29,7 @@ struct tnb_mesh {
     tnb::DevBuf<int> pcnt;     // [P]
     tnb::DevBuf<int> tri;      // [T][3]
     tnb::DevBuf<unsigned char> tag;  // [V] slab sharding: bit0 / bit1 = on the plane shared with the lower / upper neighbour
+    tnb::DevBuf<int> vidx;     // [V] number of the vertex in the complex (extract_skeleton's v_idx, subpoly.py:575)
     // between tnb_extract_mesh_begin and _finish (the slab exchange of vertex liveness sits in between)
     tnb::DevBuf<int> surf, used, counters;
     tnb::DevBuf<int2> tmp_edges;
@@ -108,28 +109,34 @@ struct FlagCount {
     const int *flag;
     __device__ __forceinline__ int operator()(int64_t i) const { return flag[i] ? 1 : 0; }
 };
-struct SurfVertEmit {
-    const float *vert, *out;
-    float *nvert, *nout;
+struct SurfVertEmit {  // new number of every surface vertex; its rows follow in k_gather_rows
     int *remap;
-    int R;
     const unsigned char *tag;
     unsigned char *ntag;
+    int *vidx;
     __device__ __forceinline__ void operator()(int64_t v, int pos, int) const
     {
         remap[v] = pos;
+        vidx[pos] = (int)v;
         ntag[pos] = tag[v];
-        for (int d = 0; d < 3; ++d) nvert[3 * (int64_t)pos + d] = vert[3 * v + d];
-        for (int c0 = 0; c0 < R; c0 += 16) {  // 16 loads in flight, then their stores
-            float t[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) t[i] = c0 + i < R ? out[v * R + c0 + i] : 0.0f;
-#pragma unroll
-            for (int i = 0; i < 16; ++i)
-                if (c0 + i < R) nout[(int64_t)pos * R + c0 + i] = t[i];
-        }
     }
 };
+// position and output row of every surface vertex, flattened over (vertex, column): a warp reads and writes
+// consecutive floats of the 33-float rows (one thread per row made every store instruction touch 32 sectors)
+__global__ void __launch_bounds__(256) k_gather_rows(int64_t Vs, int R, const int *__restrict__ vidx, const float *__restrict__ vert,
+                                                     const float *__restrict__ out, float *__restrict__ nvert, float *__restrict__ nout)
+{
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    const int64_t total = Vs * R;
+    for (int64_t i = t0; i < total; i += stride) {
+        const int64_t pos = i / R;
+        nout[i] = out[(int64_t)vidx[pos] * R + (i - pos * R)];
+    }
+    for (int64_t i = t0; i < Vs * 3; i += stride) {
+        const int64_t pos = i / 3;
+        nvert[i] = vert[(int64_t)vidx[pos] * 3 + (i - pos * 3)];
+    }
+}
 __global__ void k_remap_edges2(int2 *__restrict__ edges, int64_t E, const int *__restrict__ remap)
 {
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
@@ -208,12 +215,35 @@ __global__ void __launch_bounds__(kThreads) k_cell_sort(int64_t n_slots, const i
         const int64_t t = t0 + lane;
         int2 sl = make_int2(-1, 0);
         if (t < n_slots) sl = slots[t];
-        unsigned todo = __ballot_sync(0xffffffffu, sl.x >= 0 && sl.y == 0);  // the li == 0 entry stands for its cell
+        // the li == 0 entry stands for its cell.  Nearly all cells hold one to four vertices: such a cell is its own
+        // lane's job (four independent loads, a sorting network in registers); the warp works together only through
+        // the larger ones
+        const bool rep = sl.x >= 0 && sl.y == 0;
+        int2 myseg = make_int2(0, 0);
+        if (rep) myseg = cells[sl.x];
+        if (rep && myseg.x <= 4) {
+            tnb_bucket_rec r[4] = {};
+            unsigned long long key[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < myseg.x) r[i] = recs[myseg.y + i];
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                key[i] = i < myseg.x ? (((unsigned long long)zero_count(r[i].pos, r[i].neg, r[i].grd, colmask) << 32) | (unsigned)r[i].v) : ~0ull;
+#define TNB_CSWAP(a_, b_) do { if (key[a_] > key[b_]) { const unsigned long long tk = key[a_]; key[a_] = key[b_]; key[b_] = tk; \
+                                                         const tnb_bucket_rec tr = r[a_]; r[a_] = r[b_]; r[b_] = tr; } } while (0)
+            TNB_CSWAP(0, 1); TNB_CSWAP(2, 3); TNB_CSWAP(0, 2); TNB_CSWAP(1, 3); TNB_CSWAP(1, 2);
+#undef TNB_CSWAP
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < myseg.x) sorted[myseg.y + i] = r[i];
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, rep && myseg.x > 4);
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
             const int cell = __shfl_sync(0xffffffffu, sl.x, src);
-            const int2 seg = cells[cell];  // {records, first record}
+            const int2 seg = make_int2(__shfl_sync(0xffffffffu, myseg.x, src), __shfl_sync(0xffffffffu, myseg.y, src));  // {records, first record}
             if (seg.x <= 32) {
                 tnb_bucket_rec r = {0, 0, 0ull, 0ull, 0ull};
                 unsigned long long key = ~0ull;
@@ -709,34 +739,62 @@ __global__ void __launch_bounds__(kFanThreads) k_fan_hist(const int *__restrict_
     }
 }
 
-// off[b][i] = base[i] + sum_{b' < b} G[b'][i];  total triangle count -> *total
-__global__ void __launch_bounds__(1024) k_fan_scan(const int *__restrict__ G, int blocks, int W, int *__restrict__ off,
-                                                   int *__restrict__ total)
+// off[b][i] = sum_{b' < b} G[b'][i] (one CTA per fan step i: a column of G), col_total[i] = the column's sum
+__global__ void __launch_bounds__(kFanThreads) k_fan_cols(const int *__restrict__ G, int blocks, int W, int *__restrict__ off,
+                                                          int *__restrict__ col_total)
 {
-    __shared__ int s_col[kMaxRow + 1];
-    for (int i = threadIdx.x; i < W - 2; i += blockDim.x) {
-        int col = 0;
-        for (int b = 0; b < blocks; ++b) col += G[(int64_t)b * W + i];
-        s_col[i] = col;
-    }
+    __shared__ int s_w[kFanThreads / 32];
+    const int i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int per = (blocks + kFanThreads - 1) / kFanThreads, b0 = threadIdx.x * per, b1 = min(b0 + per, blocks);
+    int mine = 0;
+    for (int b = b0; b < b1; ++b) mine += G[(int64_t)b * W + i];
+    const int incl = warp_inclusive_scan(mine);
+    if (lane == 31) s_w[warp] = incl;
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int run = 0;
-        for (int j = 0; j < W - 2; ++j) { const int t = s_col[j]; s_col[j] = run; run += t; }
-        *total = run;
+    int before = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < kFanThreads / 32; ++w) {
+        const int t = s_w[w];
+        if (w < warp) before += t;
+        all += t;
     }
+    int run = before + incl - mine;
+    for (int b = b0; b < b1; ++b) {
+        off[(int64_t)b * W + i] = run;
+        run += G[(int64_t)b * W + i];
+    }
+    if (threadIdx.x == 0) col_total[i] = all;
+}
+// base[i] = triangles of the fan steps before i; total triangle count -> *total
+__global__ void __launch_bounds__(1024) k_fan_base(const int *__restrict__ col_total, int n, int *__restrict__ base, int *__restrict__ total)
+{
+    __shared__ int s_w[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
     __syncthreads();
-    for (int i = threadIdx.x; i < W - 2; i += blockDim.x) {
-        int run = s_col[i];
-        for (int b = 0; b < blocks; ++b) {
-            off[(int64_t)b * W + i] = run;
-            run += G[(int64_t)b * W + i];
+    for (int i0 = 0; i0 < n; i0 += 1024) {
+        const int i = i0 + threadIdx.x;
+        const int v = i < n ? col_total[i] : 0;
+        const int incl = warp_inclusive_scan(v);
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        int before = s_carry, all = 0;
+        for (int w = 0; w < 32; ++w) {
+            const int t = s_w[w];
+            if (w < warp) before += t;
+            all += t;
         }
+        if (i < n) base[i] = before + incl - v;
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry += all;
+        __syncthreads();
     }
+    if (threadIdx.x == 0) *total = s_carry;
 }
 
 __global__ void __launch_bounds__(kFanThreads) k_fan_write(const int *__restrict__ rows, const int *__restrict__ row_cnt,
-                                                           int64_t P, int W, const int *__restrict__ off,
+                                                           int64_t P, int W, const int *__restrict__ off, const int *__restrict__ base,
                                                            int *__restrict__ tri)
 {
     extern __shared__ int s_run[];  // [W] triangles already emitted by this block per step
@@ -773,7 +831,7 @@ __global__ void __launch_bounds__(kFanThreads) k_fan_write(const int *__restrict
                 ttot += t;
             }
             if (pred) {
-                const int64_t pos = (int64_t)boff[i] + s_run[i] + woff + __popc(ball & ((1u << lane) - 1u));
+                const int64_t pos = (int64_t)base[i] + boff[i] + s_run[i] + woff + __popc(ball & ((1u << lane) - 1u));
                 tri[3 * pos] = row[0];
                 tri[3 * pos + 1] = row[i + 1];
                 tri[3 * pos + 2] = row[i + 2];
@@ -854,10 +912,12 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     m->near_plane = h[F_NEAR];
     if (h[F_SURF] < 3 && !halo) return TNB_OK;  // subpoly.py:568-569
     const int64_t Es = h[F_EDGES];
-    // vertex compaction: count first to size the mesh
+    // vertex compaction: count first to size the mesh (one bit per vertex slot: the write pass takes 32 slots per thread)
     {
         int64_t blocks = std::min<int64_t>((V + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
-        k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, nullptr, FlagCount{used.p}, block_sums.p);
+        DevBuf<uint32_t> vmask;
+        TNB_CUDA(vmask.reserve((size_t)((V + 31) / 32 + kScanMaxBlocks + 64)));
+        k_scan_count_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, FlagCount{used.p}, block_sums.p, vmask.p);
         TNB_LAUNCH_CHECK();
         std::vector<int> hb(blocks);
         if ((rc = read_small(block_sums.p, hb.data(), (int)blocks, s))) return rc;
@@ -869,9 +929,14 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         TNB_CUDA(m->out.reserve((size_t)std::max<int64_t>(Vs, 1) * R));
         TNB_CUDA(m->tag.reserve((size_t)std::max<int64_t>(Vs, 1)));
         TNB_CUDA(m->edges.reserve((size_t)std::max<int64_t>(Es, 1)));
-        SurfVertEmit ve{c->cvert(), c->cout_(), m->vert.p, m->out.p, remap.p, R, c->tag[c->vcur].p, m->tag.p};
-        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, nullptr, FlagCount{used.p}, ve, block_sums.p, counters.p + F_VERTS);
+        TNB_CUDA(m->vidx.reserve((size_t)std::max<int64_t>(Vs, 1)));
+        SurfVertEmit ve{remap.p, c->tag[c->vcur].p, m->tag.p, m->vidx.p};
+        k_scan_write_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, vmask.p, ve, block_sums.p, counters.p + F_VERTS);
         TNB_LAUNCH_CHECK();
+        if (Vs > 0) {
+            k_gather_rows<<<grid_for(Vs * R, 256), 256, 0, s>>>(Vs, R, m->vidx.p, c->cvert(), c->cout_(), m->vert.p, m->out.p);
+            TNB_LAUNCH_CHECK();
+        }
     }
     if (Es > 0) {
         TNB_CUDA(cudaMemcpyAsync(m->edges.p, tmp_edges.p, (size_t)Es * sizeof(int2), cudaMemcpyDeviceToDevice, s));
@@ -999,19 +1064,23 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     }
     if (W >= 3) {
         const int fblocks = (int)std::min<int64_t>((P + kFanThreads - 1) / kFanThreads, kSMs * 4);
-        DevBuf<int> G, off;
+        DevBuf<int> G, off, col_total, base;
         TNB_CUDA(G.reserve((size_t)fblocks * W));
         TNB_CUDA(off.reserve((size_t)fblocks * W));
+        TNB_CUDA(col_total.reserve((size_t)W));
+        TNB_CUDA(base.reserve((size_t)W));
         k_fan_hist<<<fblocks, kFanThreads, (W + 1) * sizeof(int), s>>>(m->pcnt.p, P, W, G.p);
         TNB_LAUNCH_CHECK();
-        k_fan_scan<<<1, 1024, 0, s>>>(G.p, fblocks, W, off.p, counters.p + F_VERTS);
+        k_fan_cols<<<W - 2, kFanThreads, 0, s>>>(G.p, fblocks, W, off.p, col_total.p);
+        TNB_LAUNCH_CHECK();
+        k_fan_base<<<1, 1024, 0, s>>>(col_total.p, W - 2, base.p, counters.p + F_VERTS);
         TNB_LAUNCH_CHECK();
         if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
         const int64_t T = h[F_VERTS];
         m->T = T;
         TNB_CUDA(m->tri.reserve((size_t)std::max<int64_t>(T, 1) * 3));
         if (T > 0) {
-            k_fan_write<<<fblocks, kFanThreads, W * sizeof(int), s>>>(m->poly.p, m->pcnt.p, P, W, off.p, m->tri.p);
+            k_fan_write<<<fblocks, kFanThreads, W * sizeof(int), s>>>(m->poly.p, m->pcnt.p, P, W, off.p, base.p, m->tri.p);
             TNB_LAUNCH_CHECK();
         }
     }
@@ -1083,6 +1152,16 @@ int tnb_mesh_read_tags(const tnb_mesh *m, uint8_t *d_tags, void *stream)
 {
     if (!m || !d_tags) { set_error("tnb_mesh_read_tags: null argument"); return TNB_ERR_INVALID; }
     if (m->V) TNB_CUDA(cudaMemcpyAsync(d_tags, m->tag.p, (size_t)m->V, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TNB_OK;
+}
+
+int tnb_mesh_read_vertex_index(const tnb_mesh *m, int64_t *d_index, void *stream)
+{
+    if (!m || !d_index) { set_error("tnb_mesh_read_vertex_index: null argument"); return TNB_ERR_INVALID; }
+    if (m->V) {
+        k_i32_to_i64<<<grid_for(m->V, 256), 256, 0, (cudaStream_t)stream>>>(m->vidx.p, m->V, d_index);
+        TNB_LAUNCH_CHECK();
+    }
     return TNB_OK;
 }
 

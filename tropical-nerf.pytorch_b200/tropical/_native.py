@@ -98,6 +98,10 @@ SIGNATURES = {
     "tnb_extract_mesh_begin": (ctypes.c_int, [_P, _P, _F, ctypes.POINTER(_P), _P]),
     "tnb_extract_mesh_finish": (ctypes.c_int, [_P, _P, _P, _P]),
     "tnb_mesh_read_tags": (ctypes.c_int, [_P, _P, _P]),
+    "tnb_mesh_read_vertex_index": (ctypes.c_int, [_P, _P, _P]),
+    "tnb_net_outputs_group8": (ctypes.c_int, [_P, _P, _I64, _F, _P, _P, _P]),
+    "tnb_curve_intersections": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
+    "tnb_polygon_order": (ctypes.c_int, [_P, _P, _I64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P]),
     "tnb_mesh_near_plane": (_I64, [_P]),
     "tnb_grid_train_table_len": (_I64, [_P]),
     "tnb_grid_train_forward": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P]),
@@ -166,6 +170,27 @@ def profile_read():
     return out
 
 
+def curve_intersections(p, q):
+    """geometry.intersection_of_two_planes on [E, 8] corner values -> [E, 3] (device tensors)."""
+    require_cuda()
+    p, q = p.contiguous().float(), q.contiguous().float()
+    out = torch.empty((p.shape[0], 3), dtype=torch.float32, device=p.device)
+    check(lib().tnb_curve_intersections(_ptr(p), _ptr(q), p.shape[0], _ptr(out), _stream()))
+    return out
+
+
+def polygon_order(v, normals, base=0):
+    """Ordering of geometry.sort_polygon_vertices_batch: v [B, M, 3], normals [B, 3] -> (order [B, M] int64,
+    valid mask in that order [B, M] bool)."""
+    require_cuda()
+    v, normals = v.contiguous().float(), normals.contiguous().float()
+    B, M = v.shape[0], v.shape[1]
+    order = torch.empty((B, M), dtype=torch.int64, device=v.device)
+    valid = torch.empty((B, M), dtype=torch.uint8, device=v.device)
+    check(lib().tnb_polygon_order(_ptr(v), _ptr(normals), B, M, int(base), _ptr(order), _ptr(valid), _stream()))
+    return order, valid.bool()
+
+
 def require_cuda():
     if not torch.cuda.is_available() or lib().tnb_device_count() == 0:
         raise NativeError("no CUDA device: the mesh-extraction path has no CPU fallback")
@@ -220,6 +245,18 @@ class NativeNet:
         out = torch.empty((n, self.n_outputs), dtype=torch.float32, device=x.device)
         check(lib().tnb_net_outputs(self.handle, _ptr(x), n, _ptr(out), _stream()))
         return out
+
+    def outputs_group8(self, x, eps=None):
+        """Net.forward(x, gather=True, group=8) (model.py:52-76): x [8 G, 3] -> (rows [8 G, R], raw [8 G, 2])."""
+        x = x.contiguous().float()
+        n = x.shape[0]
+        if n % 8:
+            raise NativeError("group=8 needs a multiple of 8 points")
+        out = torch.empty((n, self.n_outputs), dtype=torch.float32, device=x.device)
+        raw = torch.empty((n, 2), dtype=torch.float32, device=x.device)
+        check(lib().tnb_net_outputs_group8(self.handle, _ptr(x), n // 8, float(self.eps if eps is None else eps),
+                                           _ptr(out), _ptr(raw), _stream()))
+        return out, raw
 
     def sdf_grad(self, x, want_grad=True):
         x = x.contiguous().float()
@@ -442,6 +479,13 @@ class NativeMesh:
         p = torch.empty((s["P"], s["W"]), dtype=torch.int64, device=dev)
         check(lib().tnb_mesh_read(self.handle, _ptr(v), _ptr(e), _ptr(t), _ptr(f), _ptr(p), _stream()))
         return v, e, t, f, p
+
+    def read_vertex_index(self):
+        """int64 per mesh vertex: its row in the complex the mesh came from (extract_skeleton's v_idx)."""
+        t = torch.empty(self.sizes()["V"], dtype=torch.int64, device="cuda")
+        if t.numel():
+            check(lib().tnb_mesh_read_vertex_index(self.handle, _ptr(t), _stream()))
+        return t
 
     @property
     def near_plane(self):

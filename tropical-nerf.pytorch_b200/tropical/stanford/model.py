@@ -34,7 +34,8 @@ class Net(nn.Module):
     # ---- device copy of the network ------------------------------------------------------
     def native(self) -> "_native.NativeNet":
         """The tnb_net for the current parameters (rebuilt when any parameter changed)."""
-        key = tuple((p._version, p.data_ptr()) for p in self.parameters())
+        key = tuple((p._version, p.data_ptr()) for p in self.parameters()) + (float(self.eps), float(self.scale),
+                                                                                  self.enc.marks.data_ptr(), self.enc.marks._version)
         if self._native_cache is None or self._native_cache[0] != key:
             mlp = np.concatenate([np.concatenate([fc.weight.detach().cpu().numpy().reshape(-1),
                                                   fc.bias.detach().cpu().numpy().reshape(-1)])
@@ -49,22 +50,24 @@ class Net(nn.Module):
     def forward(self, x, gather: bool = False, group: int = 1):
         """model.py:52-76.  gather=True returns (output, [hidden pre-activations..., o1-o0])."""
         if torch.is_grad_enabled() and (x.requires_grad or self.fc[0].weight.requires_grad):
-            return self._forward_autograd(x, gather)
-        if group != 1:
-            raise _native.NativeError("group != 1 (model.py:65-70) is evaluated inside the device "
-                                      "kernels of the curve-approximation path; it has no host entry")
+            return self._forward_autograd(x, gather, group)
         nat = self.native()
-        rows = nat.outputs(x)
         H = self.num_hidden
+        if group == 1:
+            rows, out = nat.outputs(x), None
+        elif group == 8:  # "infer within a common linear space" (model.py:65-70): the corners of an edge's box
+            rows, out = nat.outputs_group8(x)
+        else:
+            raise _native.NativeError("Net.forward: group must be 1 or 8 on the device (the path uses 8: subpoly.py:125)")
         inputs = [rows[:, i * H:(i + 1) * H] for i in range(self.num_layers - 1)] + [rows[:, -1:]]
-        # the last linear layer on the last hidden activation gives the 2-vector output
-        h = F.relu(inputs[-2])
-        out = F.linear(h, self.fc[-1].weight, self.fc[-1].bias)
+        if out is None:
+            # the last linear layer on the last hidden activation gives the 2-vector output
+            out = F.linear(F.relu(inputs[-2]), self.fc[-1].weight, self.fc[-1].bias)
         if gather:
             return out, inputs
         return out
 
-    def _forward_autograd(self, x, gather=False):
+    def _forward_autograd(self, x, gather=False, group=1):
         """model.py:52-76 under autograd (training): device encoding kernels + nn.Linear."""
         inputs = []
         h = self.enc.module.forward_train(self.preprocess(x))
@@ -73,7 +76,11 @@ class Net(nn.Module):
             h = fc(h)
             if i != last:
                 inputs.append(h)
-                h = F.relu(h)
+                if group == 1:
+                    h = F.relu(h)
+                else:  # infer within a common linear space (model.py:65-70)
+                    m = (h[::group] > self.eps) | (h[group - 1::group] > self.eps)
+                    h = h * m.repeat(1, group).view(*h.shape)
             else:
                 inputs.append(h[:, 1:] - h[:, :1])
         return (h, inputs) if gather else h

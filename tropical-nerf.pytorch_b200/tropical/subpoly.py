@@ -1,9 +1,18 @@
 """Subdivision-of-polygons mesh extraction (reference: tropical/subpoly.py), CUDA-backed.
 
 `subpoly(net, d, size, eps, force)` keeps the reference's signature and return values
-(faces, vertices, faces_with_indices); the work is one `tnb_subpoly` call.  The stage-level
-functions (`subpoly_`, `extract_skeleton`, `extract_faces`, `edge_vertices`, ...) are kept
-for callers that drive the stages themselves and map onto the stage-level C ABI.
+(faces, vertices, faces_with_indices); the work is one `tnb_subpoly` call.  For callers that
+drive the stages themselves: `subpoly_` (one hyperplane), `extract_skeleton`, `extract_faces`,
+`get_hypercube` map onto the stage-level C ABI.  The reference's internal grouping helpers
+(`regions_to_vertices`, `r_idx_as_tensor`, `edge_vertices`, `mean_points_with_valid`,
+`tensor_to_triangle_faces`: subpoly.py:281-535, :669-728) have no device counterpart of their
+own: the kernels group by marks-grid cell instead of expanding and sorting region rows
+(csrc/complex.cu, csrc/faces.cu), so those names are not provided.
+
+Difference to the reference's return value, on purpose: `subpoly()`'s first value is the triangle
+positions [T, 3, 3] of the de-duplicated faces (== vertices[faces_with_indices]); the reference
+returns the fan of sort_polygon_vertices_batch over rows that may repeat a face
+(its own TODO, subpoly.py:645).  `mesh.read()[4]` holds the sorted polygon rows.
 """
 from typing import List, Tuple
 
@@ -56,6 +65,31 @@ def subpoly_(vertices, edges, net, l, h, eps, outputs_=None, pruning=True, stric
     state.cx.step(l, h, eps, force)
     v, e, _ = state.cx.read(outputs=False)
     return v, e, state
+
+
+def extract_skeleton(vertices, edges, net, eps, outputs=None):
+    """Vertices and edges of the complex that lie on the zero level set (subpoly.py:556-581):
+    (vertices, edges, v_idx) with v_idx = the numbers of the kept vertices in the input.  `outputs`
+    (the cached rows the reference threads through) is recomputed on the device."""
+    cx = net.native().complex_from_arrays(vertices, edges)
+    mesh = cx.extract_mesh(eps)
+    if mesh.sizes()["V"] == 0:
+        return torch.Tensor([]).to(edges), torch.Tensor([]).to(edges), None
+    v, e, _, _, _ = mesh.read()
+    return v, e, mesh.read_vertex_index()
+
+
+def extract_faces(vertices: Tensor, edges: Tensor, net: Module, outputs: Tensor = None, eps: float = None):
+    """Faces of a surface skeleton (subpoly.py:584-652): (faces [T, 3, 3] numpy positions,
+    faces_with_indices [T, 3] numpy vertex numbers).  `vertices` / `edges` are what extract_skeleton
+    returned (every vertex on the surface and on an edge), so the numbering is kept."""
+    if 0 == vertices.shape[0]:
+        return [], []
+    mesh = net.native().complex_from_arrays(vertices, edges).extract_mesh(net.eps if eps is None else eps)
+    if mesh.sizes()["V"] != vertices.shape[0]:
+        raise _native.NativeError("extract_faces expects the output of extract_skeleton (vertices off the surface or on no edge)")
+    _, _, tri, faces, _ = mesh.read()
+    return faces.cpu().numpy(), tri.cpu().numpy()
 
 
 def extract_mesh(state: _ComplexState, net, eps=1e-4):
