@@ -357,6 +357,7 @@ def run_ours(args):
 
     planar = args.path == "planar"
     slab = args.shard == "slab" and world > 1
+    sweep_sharded = args.shard == "sweep" and world > 1
     if slab and not planar:
         raise SystemExit("--shard slab supports the planar path only")
 
@@ -377,6 +378,9 @@ def run_ours(args):
     def step(n=None):
         if slab:
             return SlabMesh(n or net)
+        if sweep_sharded:   # ONE object: the skeleton sweep dealt to the ranks by grid planes, the rest on every rank
+            from tropical import parallel
+            return parallel.subpoly_sweep_sharded(n or net, size=1.2, eps=w["eps"], force=planar)
         return (n or net).subpoly(size=1.2, eps=w["eps"], force=planar)
 
     sampler = ClockSampler(local)
@@ -410,7 +414,7 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
-    objects = 1 if slab else world   # slab mode: ONE object over all ranks (strong scaling)
+    objects = 1 if (slab or sweep_sharded) else world   # slab / sweep mode: ONE object over all ranks (strong scaling)
     value = sizes["V"] * objects * args.steps / (ms_total * 1e-3)
 
     # ---- end to end through the C ABI with host buffers --------------------------------
@@ -438,6 +442,52 @@ def run_ours(args):
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = sizes["V"] * objects * args.steps / float(t.item())
+
+    # ---- strong scaling of ONE object over the N GPUs (outside the timed region; every rank takes part) ------
+    strong = None
+    if world > 1 and not slab and not sweep_sharded and args.strong != "none":
+        from tropical import parallel
+        strong = {"note": "ONE object over all ranks (the headline above is one object per rank); ms = max over ranks, CUDA events, "
+                          "L2 flushed between steps; mesh compared with this rank's single-GPU mesh"}
+        ref_sizes = sizes
+
+        def timed(fn, reps):
+            for _ in range(3):
+                m = fn()
+            got = m.sizes() if hasattr(m, "sizes") else None
+            barrier()
+            evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for a, b in evs:
+                flush.fill_(1)
+                a.record()
+                m = fn()
+                b.record()
+                del m
+            barrier()
+            tt = torch.tensor([sum(a.elapsed_time(b) for a, b in evs) / reps], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            return float(tt.item()), got
+
+        if "sweep" in args.strong:
+            ms_sw, got = timed(lambda: parallel.subpoly_sweep_sharded(net, size=1.2, eps=w["eps"], force=planar), args.steps)
+            strong["sweep_sharded"] = {"ms_per_extraction": ms_sw, "vertices_per_s": sizes["V"] / (ms_sw * 1e-3),
+                                       "speedup_vs_one_gpu": (ms_total / args.steps) / ms_sw,
+                                       "mesh_equals_single_gpu": bool(got and got["V"] == ref_sizes["V"] and got["T"] == ref_sizes["T"]),
+                                       "what": "skeleton sweep dealt to the ranks by planes of the marks grid; one NCCL all-gather of the |sdf| "
+                                               "planes + one MAX all-reduce of the per-chunk gradient maxima; subdivision and faces on every rank: "
+                                               "bit-identical to the single-GPU mesh by construction"}
+        if "slab" in args.strong and planar:
+            try:
+                ms_sl, _ = timed(lambda: SlabMesh(net), max(2, args.steps // 2))
+                sm = SlabMesh(net)
+                strong["slab_sharded"] = {"ms_per_extraction": ms_sl, "speedup_vs_one_gpu": (ms_total / args.steps) / ms_sl,
+                                          "merged_vertices": sm.sizes()["V"], "merged_triangles": sm.sizes()["T"],
+                                          "single_gpu_vertices": ref_sizes["V"], "single_gpu_triangles": ref_sizes["T"],
+                                          "near_plane": sm.stats.get("near_plane"),
+                                          "what": "cell slabs along the first axis, per-hyperplane liveness exchange through peer mailboxes (NVLink), "
+                                                  "all-gather + merge; exact iff near_plane == 0"}
+            except Exception as e:  # noqa: BLE001  (a failed optional leg must not take the headline down)
+                strong["slab_sharded"] = {"error": str(e)[:300]}
 
     if rank != 0:
         if dist is not None:
@@ -578,17 +628,19 @@ def run_ours(args):
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-           "scaling": "strong" if slab else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "scaling": "strong" if (slab or sweep_sharded) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": shared_config(w, planar, sizes["V"], sizes["T"]),
            "run": {"polygons": sizes["P"], "objects_per_step": objects, "l2": "flushed (512 MiB write) between timed steps",
                    "extraction_s": ms_total / args.steps * 1e-3,
                    "sharding": ("one object cut into %d marks-grid slabs, one per GPU; per-step exchange through peer mailboxes, "
-                                "all-gather + merge inside the timed region" % world) if slab else "one object per GPU",
+                                "all-gather + merge inside the timed region" % world) if slab else
+                               ("one object; skeleton sweep dealt to %d GPUs by grid planes (all-gather inside the timed region), the rest on every rank" % world)
+                               if sweep_sharded else "one object per GPU",
                    "slab_stats": slab_stats},
            "clocks": clocks, "gpu_launches": launches,
            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                    "ms_per_step": 1e3 * float(t.item()) / args.steps},
-           "roofline": roofline, "cpu_baseline": cpu, "eval_sweep": sweep, "concurrent": concurrent}
+           "roofline": roofline, "cpu_baseline": cpu, "eval_sweep": sweep, "concurrent": concurrent, "strong_scaling": strong}
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
@@ -605,9 +657,12 @@ def main():
                          "small_sphere, small_torus, medium_torus, large_torus, <size>_random")
     ap.add_argument("--path", default="planar", choices=["planar", "curve"],
                     help="planar = the reference's -f default (force=True); curve = curve approximation")
-    ap.add_argument("--shard", default="object", choices=["object", "slab"],
+    ap.add_argument("--shard", default="object", choices=["object", "slab", "sweep"],
                     help="N>1: object = every rank extracts its own object (weak scaling, default); "
-                         "slab = ONE object cut into marks-grid slabs, one per GPU (strong scaling)")
+                         "slab = ONE object cut into marks-grid slabs, one per GPU (strong scaling); "
+                         "sweep = ONE object, its skeleton sweep dealt to the GPUs by grid planes (strong scaling, exact)")
+    ap.add_argument("--strong", default="sweep", help="N>1, --shard object: extra strong-scaling legs of ONE object, outside the timed region: "
+                                                      "'sweep' (default), 'sweep,slab', or 'none'")
     ap.add_argument("--ref-cores", type=int, default=0, help="--impl reference: host cores to use (0 = all)")
     ap.add_argument("--concurrent", type=int, default=8, help="extra leg: objects in flight on one GPU (0/1 = skip)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")

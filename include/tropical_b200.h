@@ -176,6 +176,16 @@ int tnb_mesh_read_host(const tnb_mesh *m, float *h_vertices, int64_t *h_triangle
  * (tropical.py:189-197), so the caller reduces max_grad (MAX over ranks) in between. */
 int tnb_skeleton_sweep(const tnb_net *net, int32_t unit, int32_t x_lo, int32_t x_hi,
                        int32_t shared_lower, int32_t shared_upper, tnb_sweep **out, void *stream);
+/* Plane sharding of the sweep only (exact by construction: the marks-grid planes are split over the GPUs,
+ * every rank evaluates |sdf| and the per-chunk max |grad| of its planes, the planes travel by ONE all-gather
+ * and the maxima by one MAX all-reduce, then every rank holds the sweep of the whole grid):
+ * tnb_skeleton_sweep_alloc = the layout of the whole grid's sweep with nothing evaluated;
+ * tnb_sweep_read_dist copies a sweep's planes out ([planes][M][M] floats, plane x_lo first),
+ * tnb_sweep_write_dist copies the planes [x_lo, x_hi] in. */
+int tnb_skeleton_sweep_alloc(const tnb_net *net, int32_t unit, tnb_sweep **out, void *stream);
+int64_t tnb_sweep_num_planes(const tnb_sweep *sw);
+int tnb_sweep_read_dist(const tnb_sweep *sw, float *d_out, void *stream);
+int tnb_sweep_write_dist(tnb_sweep *sw, const float *d_in, int32_t x_lo, int32_t x_hi, void *stream);
 void tnb_sweep_destroy(tnb_sweep *sw);
 int32_t tnb_sweep_num_chunks(const tnb_sweep *sw);
 int tnb_sweep_read_max_grad(const tnb_sweep *sw, float *d_out, void *stream);   /* [n_chunks] */

@@ -29,9 +29,15 @@ def main():
         assert np.array_equal(canonical_vertices(v.cpu().numpy()), canonical_vertices(v1.cpu().numpy())), "vertices differ"
         assert np.array_equal(canonical_triangles(v.cpu().numpy(), t.cpu().numpy()),
                               canonical_triangles(v1.cpu().numpy(), t1.cpu().numpy())), "triangles differ"
+    # plane-sharded sweep (exact by construction): every array of the mesh equals the single-GPU one, on every rank
+    want = [a.cpu().numpy() for a in N.subpoly(size=1.2, eps=1e-4, force=True).read()]
+    for rep in range(2):
+        got = [a.cpu().numpy() for a in parallel.subpoly_sweep_sharded(N).read()]
+        for x, y in zip(got, want):
+            assert np.array_equal(x, y), "plane-sharded sweep: mesh differs from the single-GPU mesh"
     dist.barrier()
     if dist.get_rank() == 0:
-        print(f"slab_dist_check ok: {case} world {dist.get_world_size()} {stats}")
+        print(f"slab_dist_check ok: {case} world {dist.get_world_size()} {stats}; sweep-sharded mesh identical")
     dist.destroy_process_group()
 
 

@@ -65,8 +65,7 @@ def test_intersection_of_two_planes_bit_exact():
     want = curve_intersections(p, q)
     got = gm.intersection_of_two_planes(torch.from_numpy(p).cuda(), torch.from_numpy(q).cuda()).cpu().numpy()
     assert np.array_equal(got, want, equal_nan=True)
-    adm = ((want >= 0) & (want <= 1)).all(1)
-    assert adm.sum() > 20 and (want[:, 0] == -1).sum() > 100   # both branches are exercised
+    assert (want[:, 0] >= 0).sum() > 100 and (want[:, 0] == -1).sum() > 100   # roots found / none (degenerate boxes among them)
 
 
 def test_sort_polygon_vertices_batch_matches_the_oracle_order():

@@ -100,3 +100,28 @@ def test_two_ranks_equal_single():
     out = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     assert "slab_dist_check ok" in out.stdout
+
+
+@pytest.mark.parametrize("case,parts", [("small_sphere", 3), ("small_torus", 5)])
+def test_sweep_assembled_from_plane_ranges_equals_the_whole_sweep(case, parts):
+    """The plane-sharded sweep of parallel.subpoly_sweep_sharded on ONE device: the planes of the first axis are
+    evaluated range by range (as the ranks would), |sdf| planes and per-chunk gradient maxima assembled into an
+    empty whole-grid sweep: the same complex, and the same mesh, as tnb_skeleton + steps + extract."""
+    from tropical.parallel import _hyperplanes, plane_ranges
+    N = native_net(oracle_net(load_golden(case)))
+    want_c = [t.cpu().numpy() for t in N.skeleton(128).read()]
+    whole = N.skeleton_sweep_alloc(128)
+    mg = None
+    for a, b in plane_ranges(N.n_marks, parts):
+        sw = N.skeleton_sweep(a, b, False, False, 128)
+        whole.write_dist(sw.read_dist(), a, b)
+        mg = sw.max_grad() if mg is None else torch.maximum(mg, sw.max_grad())
+    whole.set_max_grad(mg)
+    c = whole.finish()
+    for x, y in zip([t.cpu().numpy() for t in c.read()], want_c):
+        assert np.array_equal(x, y)
+    c.steps(_hyperplanes(N))
+    got = [t.cpu().numpy() for t in c.extract_mesh().read()]
+    want = [t.cpu().numpy() for t in N.subpoly().read()]
+    for x, y in zip(got, want):
+        assert np.array_equal(x, y)

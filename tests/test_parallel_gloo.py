@@ -54,3 +54,18 @@ def test_shard_is_a_partition():
             parts = [shard(n, w, r) for r in range(w)]
             assert sorted(sum(parts, [])) == list(range(n))
             assert max(map(len, parts)) - min(map(len, parts)) <= 1
+
+
+def test_plane_ranges_deal_every_plane_once():
+    from tropical.parallel import plane_ranges, slab_planes
+    for m in (9, 49, 98, 201):
+        for w in (1, 2, 3, 4, 8):
+            r = plane_ranges(m, w)
+            planes = [x for a, b in r for x in range(a, b + 1)]
+            assert planes == list(range(m))                      # a partition, in rank order
+            sizes = [b - a + 1 for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+            s = slab_planes(m, w)                                # cell slabs: neighbours share one plane
+            assert s[0][0] == 0 and s[-1][1] == m - 1 and all(s[i][1] == s[i + 1][0] for i in range(w - 1))
+    with pytest.raises(ValueError):
+        plane_ranges(4, 5)

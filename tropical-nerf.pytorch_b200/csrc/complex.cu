@@ -389,8 +389,10 @@ struct tnb_sweep {
 
 namespace tnb {
 
+// launch = false: only the layout (segments, buffers); |sdf| and max |grad| are written by the caller
+// (tnb_sweep_write_dist / tnb_sweep_write_max_grad: a sweep whose planes were evaluated on several GPUs)
 static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag_lower, bool tag_upper, tnb_sweep *sw,
-                      cudaStream_t s)
+                      cudaStream_t s, bool launch = true)
 {
     const int M = net->meta.n_marks;
     if (unit < 2) { set_error("tnb_skeleton: unit must be >= 2"); return TNB_ERR_INVALID; }
@@ -427,15 +429,17 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
                 st[0] = lo;
                 nn[0] = hi - lo + 1;
                 const int64_t count = (int64_t)nn[0] * nn[1] * nn[2];
-                unsigned g = grid_for(count, kThreads);
-                const LatticeStride ls = lattice_stride((int64_t)g * kThreads, nn[0], nn[1]);
-                prof_begin(TNB_PROF_SWEEP, s);
-                if (net->fixed_cfg)
-                    k_sweep_chunk<CfgRef><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], ls, dist0, sw->max_grad.p + chunk);
-                else
-                    k_sweep_chunk<CfgAny><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], ls, dist0, sw->max_grad.p + chunk);
-                TNB_LAUNCH_CHECK();
-                prof_end(TNB_PROF_SWEEP, s, count, count * 4 + (int64_t)net->table.cap * 8);
+                if (launch) {
+                    unsigned g = grid_for(count, kThreads);
+                    const LatticeStride ls = lattice_stride((int64_t)g * kThreads, nn[0], nn[1]);
+                    prof_begin(TNB_PROF_SWEEP, s);
+                    if (net->fixed_cfg)
+                        k_sweep_chunk<CfgRef><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], ls, dist0, sw->max_grad.p + chunk);
+                    else
+                        k_sweep_chunk<CfgAny><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], ls, dist0, sw->max_grad.p + chunk);
+                    TNB_LAUNCH_CHECK();
+                    prof_end(TNB_PROF_SWEEP, s, count, count * 4 + (int64_t)net->table.cap * 8);
+                }
                 for (int axis = 0; axis < 3; ++axis) {
                     int dims[3] = {nn[0], nn[1], nn[2]};
                     dims[axis] -= 1;
@@ -1306,12 +1310,9 @@ __device__ __forceinline__ void stream_partners(const PartnerQuery &q, const int
     __syncwarp();
     for (int i0 = 0; i0 < total; i0 += 128) {
         tnb_bucket_rec r[4];
-        bool have[4] = {false, false, false, false};
-        // nearly every neighbourhood holds fewer than 32 records: the unrolled slots past the end are skipped as a
-        // warp (uniform test), not predicated off (they were 3/4 of the instructions this kernel issued)
+        bool have[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            if (i0 + 32 * u >= total) break;  // warp uniform
             const int i = i0 + 32 * u + lane;
             have[u] = i < total;
             if (have[u]) {
@@ -1322,6 +1323,8 @@ __device__ __forceinline__ void stream_partners(const PartnerQuery &q, const int
                 r[u] = recs[s_base[k] + i];
             }
         }
+        // (measured: leaving the unrolled slots past `total` as a warp -- uniform breaks in both loops -- made the
+        // kernel 20 % SLOWER, 71 -> 87 us per launch: the slots' loads no longer issue back to back)
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             if (i0 + 32 * u >= total) break;  // warp uniform
@@ -3182,6 +3185,34 @@ int tnb_skeleton_sweep(const tnb_net *net, int32_t unit, int32_t x_lo, int32_t x
     int rc = sweep_impl(net, unit, x_lo, x_hi, shared_lower != 0, shared_upper != 0, sw, s);
     if (rc != TNB_OK) { delete sw; return rc; }
     *out = sw;
+    return TNB_OK;
+}
+int tnb_skeleton_sweep_alloc(const tnb_net *net, int32_t unit, tnb_sweep **out, void *stream)
+{
+    if (!net || !out) { set_error("tnb_skeleton_sweep_alloc: null argument"); return TNB_ERR_INVALID; }
+    *out = nullptr;
+    cudaStream_t s = (cudaStream_t)stream;
+    current_stream() = s;
+    tnb_sweep *sw = new tnb_sweep();
+    int rc = sweep_impl(net, unit, 0, net->meta.n_marks - 1, false, false, sw, s, false);
+    if (rc != TNB_OK) { delete sw; return rc; }
+    *out = sw;
+    return TNB_OK;
+}
+int64_t tnb_sweep_num_planes(const tnb_sweep *sw) { return sw ? sw->x_hi - sw->x_lo + 1 : 0; }
+int tnb_sweep_read_dist(const tnb_sweep *sw, float *d_out, void *stream)
+{
+    if (!sw || !d_out) { set_error("tnb_sweep_read_dist: null argument"); return TNB_ERR_INVALID; }
+    const size_t n = (size_t)(sw->x_hi - sw->x_lo + 1) * sw->M * sw->M;
+    TNB_CUDA(cudaMemcpyAsync(d_out, sw->dist.p, n * sizeof(float), cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return TNB_OK;
+}
+int tnb_sweep_write_dist(tnb_sweep *sw, const float *d_in, int32_t x_lo, int32_t x_hi, void *stream)
+{
+    if (!sw || !d_in || x_lo < sw->x_lo || x_hi > sw->x_hi || x_lo > x_hi) { set_error("tnb_sweep_write_dist: bad argument"); return TNB_ERR_INVALID; }
+    const size_t plane = (size_t)sw->M * sw->M;
+    TNB_CUDA(cudaMemcpyAsync(sw->dist.p + (size_t)(x_lo - sw->x_lo) * plane, d_in, (size_t)(x_hi - x_lo + 1) * plane * sizeof(float),
+                             cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
     return TNB_OK;
 }
 void tnb_sweep_destroy(tnb_sweep *sw) { delete sw; }

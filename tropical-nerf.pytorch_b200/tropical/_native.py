@@ -83,6 +83,10 @@ SIGNATURES = {
     "tnb_set_capacity_factor": (ctypes.c_int, [ctypes.c_double]),
     "tnb_skeleton_sweep": (ctypes.c_int, [_P, _I32, _I32, _I32, _I32, _I32, ctypes.POINTER(_P), _P]),
     "tnb_sweep_destroy": (None, [_P]),
+    "tnb_skeleton_sweep_alloc": (ctypes.c_int, [_P, _I32, ctypes.POINTER(_P), _P]),
+    "tnb_sweep_num_planes": (_I64, [_P]),
+    "tnb_sweep_read_dist": (ctypes.c_int, [_P, _P, _P]),
+    "tnb_sweep_write_dist": (ctypes.c_int, [_P, _P, _I32, _I32, _P]),
     "tnb_sweep_num_chunks": (_I32, [_P]),
     "tnb_sweep_read_max_grad": (ctypes.c_int, [_P, _P, _P]),
     "tnb_sweep_write_max_grad": (ctypes.c_int, [_P, _P, _P]),
@@ -307,6 +311,12 @@ class NativeNet:
                                             edges.shape[0], ctypes.byref(h), _stream()))
         return NativeComplex(self, h)
 
+    def skeleton_sweep_alloc(self, unit=128):
+        """The whole grid's sweep with nothing evaluated (filled by write_dist / set_max_grad)."""
+        h = ctypes.c_void_p()
+        check(lib().tnb_skeleton_sweep_alloc(self.handle, int(unit), ctypes.byref(h), _stream()))
+        return NativeSweep(self, h)
+
     def skeleton_sweep(self, x_lo, x_hi, shared_lower, shared_upper, unit=128):
         """First half of the skeleton of the slab of marks-grid planes [x_lo, x_hi]."""
         h = ctypes.c_void_p()
@@ -343,6 +353,19 @@ class NativeSweep:
         t = t.contiguous().float()
         assert t.numel() == self.n_chunks
         check(lib().tnb_sweep_write_max_grad(self.handle, _ptr(t), _stream()))
+
+    def read_dist(self, out=None):
+        """|sdf| of the sweep's planes: [planes * M * M] floats, first plane first."""
+        n = int(lib().tnb_sweep_num_planes(self.handle)) * self.net.n_marks ** 2
+        if out is None:
+            out = torch.empty(n, dtype=torch.float32, device="cuda")
+        assert out.numel() >= n and out.is_contiguous()
+        check(lib().tnb_sweep_read_dist(self.handle, _ptr(out), _stream()))
+        return out
+
+    def write_dist(self, t, x_lo, x_hi):
+        assert t.is_contiguous() and t.numel() >= (x_hi - x_lo + 1) * self.net.n_marks ** 2
+        check(lib().tnb_sweep_write_dist(self.handle, _ptr(t), int(x_lo), int(x_hi), _stream()))
 
     def finish(self):
         h = ctypes.c_void_p()

@@ -313,3 +313,48 @@ def subpoly_sharded(net, size: float = 1.2, eps: float = 1e-4, unit: int = 128, 
     stats["slab_vertices"] = [int(x.shape[0]) for x in vs]
     stats["near_plane"] = sum_int(meshes[0].near_plane)
     return v, t, stats
+
+
+# ==================================================================================================
+# Plane sharding of the skeleton sweep (exact): the dense part of the path over the GPUs, the rest replicated
+# ==================================================================================================
+# The sweep over the marks grid (|sdf| and |grad| at every grid vertex: the one phase whose cost is the grid's
+# VOLUME, a fifth of a large extraction) is split by planes of the first axis.  Every rank evaluates its planes,
+# one all-gather moves the |sdf| planes and one MAX all-reduce the per-chunk gradient maxima (the reference's
+# threshold is per chunk, tropical.py:189-197); from there on every rank holds the sweep of the whole grid and
+# runs the subdivision and the faces itself, so the mesh is the single-GPU mesh bit for bit, on every rank,
+# whatever the cut.  (Slab sharding of the whole path, above, cuts the subdivision too, but is exact only when no
+# vertex falls within eps of a shared plane.)
+def plane_ranges(n_marks: int, world_size: int) -> List[tuple]:
+    """[(x_lo, x_hi)] per rank: disjoint, contiguous, near-equal plane ranges of the first grid axis."""
+    if world_size < 1 or world_size > n_marks:
+        raise ValueError(f"cannot deal {n_marks} planes to {world_size} ranks")
+    bounds = [(r * n_marks) // world_size for r in range(world_size + 1)]
+    return [(bounds[r], bounds[r + 1] - 1) for r in range(world_size)]
+
+
+def subpoly_sweep_sharded(net, size: float = 1.2, eps: float = 1e-4, unit: int = 128, force: bool = True, group=None):
+    """One object, the skeleton sweep sharded over the ranks of `group` by grid planes.  Every rank calls this with
+    the same network and gets the whole mesh (a NativeMesh), identical to net.subpoly(...)."""
+    if world() == 1:
+        return net.subpoly(size=size, eps=eps, force=force, unit=unit)
+    w, me = dist.get_world_size(group), dist.get_rank(group)
+    M = net.n_marks
+    ranges = plane_ranges(M, w)
+    lo, hi = ranges[me]
+    sw = net.skeleton_sweep(lo, hi, False, False, unit)
+    per = max(b - a + 1 for a, b in ranges) * M * M          # equal-sized all-gather slots (NCCL all_gather_into_tensor)
+    full = torch.empty(w * per, dtype=torch.float32, device="cuda")
+    sw.read_dist(full[me * per:(me + 1) * per])
+    dist.all_gather_into_tensor(full, full[me * per:(me + 1) * per].clone(), group=group)
+    mg = sw.max_grad()
+    dist.all_reduce(mg, op=dist.ReduceOp.MAX, group=group)
+    whole = net.skeleton_sweep_alloc(unit)
+    for r, (a, b) in enumerate(ranges):
+        whole.write_dist(full[r * per:], a, b)
+    whole.set_max_grad(mg)
+    c = whole.finish()
+    if c.num_edges == 0:   # empty skeleton: the hypercube route (subpoly.py:51-52)
+        return net.subpoly(size=size, eps=eps, force=force, unit=unit)
+    c.steps(_hyperplanes(net), eps, force)
+    return c.extract_mesh(eps)
