@@ -110,6 +110,11 @@ int tnb_skeleton(const tnb_net *net, int32_t unit, float size, tnb_complex **out
  * [E,2] i64.  Outputs are evaluated. */
 int tnb_complex_from_arrays(const tnb_net *net, const float *d_vertices, int64_t V,
                             const int64_t *d_edges, int64_t E, tnb_complex **out, void *stream);
+/* The `outputs_` argument the reference threads through subpoly_ / extract_skeleton / extract_faces
+ * (tropical/subpoly.py:92-95, :556-560, :607): replace the complex's evaluated network rows by the
+ * caller's [V][R] rows (they may carry the exact zeros of the failover override,
+ * subpoly_debug.py:41-49); the packed sign vectors are rebuilt from them. */
+int tnb_complex_write_outputs(const tnb_net *net, tnb_complex *c, const float *d_outputs, void *stream);
 void tnb_complex_destroy(tnb_complex *c);
 /* -1: the complex carries a device-side error (capacity, curve path, slab exchange); the same
  * TNB_ERR_* code is returned by every later call on it and tnb_last_error() says why */

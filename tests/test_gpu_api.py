@@ -96,10 +96,10 @@ def test_extract_skeleton_and_extract_faces_stage_functions():
     c = N.skeleton(128)
     c.steps([(l, h) for l in range(P.num_layers - 1) for h in range(H)] + [(P.num_layers - 2, H)])
     v, e, o = c.read()
-    sv, se, v_idx = sp.extract_skeleton(v, e, net, 1e-4)
+    sv, se, v_idx = sp.extract_skeleton(v, e, net, 1e-4, outputs=o)
     vo, eo, idx_o = R.extract_skeleton(P, v.cpu().numpy(), e.cpu().numpy(), o.cpu().numpy(), 1e-4)
     assert np.array_equal(sv.cpu().numpy(), vo) and np.array_equal(se.cpu().numpy(), eo)
     assert np.array_equal(v_idx.cpu().numpy(), idx_o)
-    faces, tri = sp.extract_faces(sv, se, net, eps=1e-4)
+    faces, tri = sp.extract_faces(sv, se, net, outputs=o[v_idx], eps=1e-4)
     want = [a.cpu().numpy() for a in N.subpoly().read()]
     assert np.array_equal(tri, want[2]) and np.array_equal(faces, want[3])

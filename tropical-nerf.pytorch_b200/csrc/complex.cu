@@ -171,6 +171,9 @@ struct ChunkSeg {  // one (chunk, axis) block of candidate grid edges, in the re
     int64_t first;  // first slot number
     int s[3], n[3]; // chunk start / size per axis
     int axis, chunk;
+    int64_t row_first;  // first ROW of the block: a row = the slots that differ in the last coordinate only
+    int64_t bit_word;   // first word of the chunk piece's "close to the surface" bits ([n0][n1][w32] words)
+    int w32;            // words per bit row
 };
 constexpr int kMaxSegs = 3 * 512;
 
@@ -287,6 +290,107 @@ struct SkelEdgeEmit {
     }
 };
 
+// ---- the same selection row by row ---------------------------------------------------------------------
+// A candidate edge is kept iff both its grid vertices are within the chunk's threshold of the surface
+// (tropical.py:113-138).  Per SLOT that is a decode (two divisions) and two scattered loads for 24 M slots of
+// which 7 % pass.  Per ROW (the slots of a block that differ in the last coordinate only, up to `unit` of them)
+// it is a few word operations: k_skel_bits leaves one bit per (chunk piece, grid vertex) -- "close enough" under
+// that chunk's threshold, coalesced along the last axis --, and a row's kept slots are  bits(row) & bits(row
+// shifted by one vertex along the block's axis).  The ordered compaction then runs over ~0.4 M rows, each
+// emitting its edges in ascending last coordinate: the reference's order (chunk, axis, i, j, k).
+constexpr int kMaxRowWords = 32;  // unit <= 1024
+__global__ void __launch_bounds__(256) k_skel_bits(const ChunkSeg *__restrict__ segs, int n_segs, int M, const float *__restrict__ dist,
+                                                   const unsigned *__restrict__ max_grad, float k_len, uint32_t *__restrict__ bits)
+{
+    // one warp per bit word; blockIdx.y = segment (only a piece's first block writes its bits)
+    const ChunkSeg sg = segs[blockIdx.y];
+    if (blockIdx.y > 0 && segs[blockIdx.y - 1].bit_word == sg.bit_word) return;  // same chunk piece as the block before
+    const float eps = k_len * __uint_as_float(max_grad[sg.chunk]);
+    const int lane = threadIdx.x & 31;
+    const int64_t n_words = (int64_t)sg.n[0] * sg.n[1] * sg.w32;
+    for (int64_t w = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); w < n_words; w += (int64_t)gridDim.x * (blockDim.x >> 5)) {
+        const int kw = (int)(w % sg.w32);
+        const int64_t row = w / sg.w32;
+        const int j = (int)(row % sg.n[1]), i = (int)(row / sg.n[1]), k = kw * 32 + lane;
+        bool ok = false;
+        if (k < sg.n[2]) ok = dist[((int64_t)(sg.s[0] + i) * M + (sg.s[1] + j)) * M + sg.s[2] + k] <= eps;
+        const uint32_t word = __ballot_sync(0xffffffffu, ok);
+        if (lane == 0) bits[sg.bit_word + w] = word;
+    }
+}
+struct SkelRows {
+    const ChunkSeg *segs;
+    int n_segs, M;
+    const uint32_t *bits;
+    mutable int hint = 0;
+    __device__ __forceinline__ int seg_of(int64_t r) const
+    {
+        int a = hint;
+        if (segs[a].row_first <= r && (a + 1 == n_segs || r < segs[a + 1].row_first)) return a;
+        a = 0;
+        int b = n_segs - 1;
+        while (a < b) {
+            const int mid = (a + b + 1) >> 1;
+            if (segs[mid].row_first <= r) a = mid; else b = mid - 1;
+        }
+        hint = a;
+        return a;
+    }
+    // kept slots of row r as bit words (bit k of word w = slot k + 32 w of the row); returns the number of words
+    __device__ __forceinline__ int row_words(int64_t r, uint32_t *out, int &lo0, int &step) const
+    {
+        const ChunkSeg sg = segs[seg_of(r)];
+        int dims1 = sg.n[1] - (sg.axis == 1 ? 1 : 0);
+        const int rr = (int)(r - sg.row_first), i = rr / dims1, j = rr - i * dims1;
+        const uint32_t *a = bits + sg.bit_word + ((int64_t)i * sg.n[1] + j) * sg.w32;
+        const int len = sg.n[2] - (sg.axis == 2 ? 1 : 0);  // slots of the row
+        if (sg.axis == 2) {
+            for (int w = 0; w < sg.w32; ++w) {
+                const uint32_t x = a[w], nx = w + 1 < sg.w32 ? a[w + 1] : 0u;
+                out[w] = x & ((x >> 1) | (nx << 31));
+            }
+        } else {
+            const uint32_t *b = a + (sg.axis == 0 ? (int64_t)sg.n[1] * sg.w32 : sg.w32);
+            for (int w = 0; w < sg.w32; ++w) out[w] = a[w] & b[w];
+        }
+        if (len & 31) out[len >> 5] &= (1u << (len & 31)) - 1u;  // slots past the end of the row
+        for (int w = (len + 31) >> 5; w < sg.w32; ++w) out[w] = 0u;
+        lo0 = ((sg.s[0] + i) * M + (sg.s[1] + j)) * M + sg.s[2];
+        step = sg.axis == 0 ? M * M : (sg.axis == 1 ? M : 1);
+        return sg.w32;
+    }
+};
+struct SkelRowCount {
+    SkelRows q;
+    __device__ __forceinline__ int operator()(int64_t r) const
+    {
+        uint32_t w[kMaxRowWords];
+        int lo0, step;
+        const int n = q.row_words(r, w, lo0, step);
+        int c = 0;
+        for (int i = 0; i < n; ++i) c += __popc(w[i]);
+        return c;
+    }
+};
+struct SkelRowEmit {
+    SkelRows q;
+    int2 *edges;
+    int *used;
+    __device__ __forceinline__ void operator()(int64_t r, int pos, int) const
+    {
+        uint32_t w[kMaxRowWords];
+        int lo0, step;
+        const int n = q.row_words(r, w, lo0, step);
+        for (int i = 0; i < n; ++i)
+            for (uint32_t m = w[i]; m; m &= m - 1) {
+                const int lo = lo0 + 32 * i + __ffs(m) - 1, hi = lo + step;
+                edges[pos++] = make_int2(hi, lo);  // (indices[1:], indices[:-1]) column order, tropical.py:130
+                used[hi] = 1;
+                used[lo] = 1;
+            }
+    }
+};
+
 struct FlagCount {
     const int *flag;
     __device__ __forceinline__ int operator()(int64_t i) const { return flag[i] ? 1 : 0; }
@@ -381,7 +485,7 @@ struct tnb_sweep {
     int x_lo = 0, x_hi = 0;  // planes of the slab along the first axis (the whole grid: 0, M-1)
     bool tag_lower = false, tag_upper = false;
     float k_len = 0.0f;
-    int64_t slots = 0;
+    int64_t slots = 0, rows = 0, bit_words = 0;
     std::vector<tnb::ChunkSeg> segs;
     tnb::DevBuf<float> dist;         // [(x_hi-x_lo+1) * M * M], plane x_lo first
     tnb::DevBuf<unsigned> max_grad;  // [n_chunks] bit patterns of non-negative floats
@@ -414,7 +518,7 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
     TNB_CUDA(sw->max_grad.reserve((size_t)sw->n_chunks));
     TNB_CUDA(cudaMemsetAsync(sw->max_grad.p, 0, (size_t)sw->n_chunks * sizeof(unsigned), s));
     float *dist0 = sw->dist.p - (int64_t)x_lo * M * M;  // indexed by the global vertex number
-    int64_t slots = 0;
+    int64_t slots = 0, rows = 0, words = 0;
     int chunk = 0;
     for (int a = 0; a < nc; ++a)
         for (int b = 0; b < nc; ++b)
@@ -440,6 +544,7 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
                     TNB_LAUNCH_CHECK();
                     prof_end(TNB_PROF_SWEEP, s, count, count * 4 + (int64_t)net->table.cap * 8);
                 }
+                const int w32 = (nn[2] + 31) / 32;
                 for (int axis = 0; axis < 3; ++axis) {
                     int dims[3] = {nn[0], nn[1], nn[2]};
                     dims[axis] -= 1;
@@ -450,11 +555,18 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
                     for (int d = 0; d < 3; ++d) { sg.s[d] = st[d]; sg.n[d] = nn[d]; }
                     sg.axis = axis;
                     sg.chunk = chunk;
+                    sg.row_first = rows;
+                    sg.bit_word = words;
+                    sg.w32 = w32;
                     sw->segs.push_back(sg);
                     slots += cnt;
+                    rows += (int64_t)dims[0] * dims[1];
                 }
+                words += (int64_t)nn[0] * nn[1] * w32;
             }
     sw->slots = slots;
+    sw->rows = rows;
+    sw->bit_words = words;
     return TNB_OK;
 }
 
@@ -484,14 +596,17 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
     TNB_CUDA(total.reserve(2));
     TNB_CUDA(cudaMemsetAsync(used.p, 0, (size_t)MS * sizeof(int), s));
 
-    // pass 1: count surviving edges so the complex can be sized
-    SkelEdgeCount q{d_segs.p, (int)segs.size(), M, dist0, sw->max_grad.p, sw->k_len};
+    // pass 1: count surviving edges so the complex can be sized (row by row, see k_skel_bits)
+    if (sw->unit > 32 * kMaxRowWords) { set_error("tnb_skeleton: unit above " + std::to_string(32 * kMaxRowWords)); return TNB_ERR_UNSUPPORTED; }
     {
-        int64_t blocks = std::min<int64_t>((slots + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
-        // one bit per slot: the write pass does not decode and test the ~93 % of the slots that fail again
-        DevBuf<uint32_t> slot_mask;
-        TNB_CUDA(slot_mask.reserve((size_t)((slots + 31) / 32 + kScanMaxBlocks)));
-        k_scan_count_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, q, block_sums.p, slot_mask.p);
+        DevBuf<uint32_t> bits;
+        TNB_CUDA(bits.reserve((size_t)sw->bit_words + 1));
+        k_skel_bits<<<dim3(kSMs * 2, (unsigned)segs.size()), 256, 0, s>>>(d_segs.p, (int)segs.size(), M, dist0, sw->max_grad.p, sw->k_len, bits.p);
+        TNB_LAUNCH_CHECK();
+        const SkelRows rows_q{d_segs.p, (int)segs.size(), M, bits.p};
+        const int64_t n_rows = sw->rows;
+        int64_t blocks = std::min<int64_t>((n_rows + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
+        k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(n_rows, nullptr, SkelRowCount{rows_q}, block_sums.p);
         TNB_LAUNCH_CHECK();
         std::vector<int> h(blocks);
         TNB_CUDA(cudaMemcpyAsync(h.data(), block_sums.p, blocks * sizeof(int), cudaMemcpyDeviceToHost, s));
@@ -502,8 +617,7 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
         // vertices are bounded by 2E; real sizing happens after the vertex pass
         DevBuf<int2> raw;
         TNB_CUDA(raw.reserve((size_t)E));
-        SkelEdgeEmit emit{q, raw.p, used.p - base};
-        k_scan_write_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(slots, slot_mask.p, emit, block_sums.p, total.p);
+        k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(n_rows, nullptr, SkelRowCount{rows_q}, SkelRowEmit{rows_q, raw.p, used.p - base}, block_sums.p, total.p);
         TNB_LAUNCH_CHECK();
         // vertex pass: count, size, then place (one bit per grid vertex: ~90 % of them are on no kept edge, and the
         // generic write pass spent its time in the CTA barriers of their tiles)
@@ -2820,11 +2934,15 @@ __global__ void __launch_bounds__(256) k_sd_pair_copy(const __grid_constant__ St
     const int *cnt = a.cnt;
     if (!sd_crossed(cnt) || !sd_fits(a) || cnt[C_PAIRS] == 0) return;
     int2 *edges_out = a.edges[cnt[C_EPAR]] + cnt[C_E] + cnt[C_SPLIT];
-    const int64_t n = (int64_t)cnt[C_CAND] * kCachedPartners;
-    for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(t / kCachedPartners), i = (int)(t % kCachedPartners);
+    // one thread per candidate: nearly every list has one to four entries (a thread per (candidate, slot) left
+    // 30 of 32 threads with nothing to copy)
+    const int n_cand = cnt[C_CAND];
+    for (int c = blockIdx.x * blockDim.x + threadIdx.x; c < n_cand; c += gridDim.x * blockDim.x) {
         const int pc = a.pcount[c];
-        if (i < pc && pc <= kCachedPartners) edges_out[a.poff[c] + i] = make_int2(a.cand[c], a.pcache[t]);
+        if (pc == 0 || pc > kCachedPartners) continue;
+        const int va = a.cand[c], off = a.poff[c];
+        const int *src = a.pcache + (int64_t)c * kCachedPartners;
+        for (int i = 0; i < pc; ++i) edges_out[off + i] = make_int2(va, src[i]);
     }
 }
 __global__ void __launch_bounds__(kSortWarps * 32) k_sd_pair_long(const __grid_constant__ StepArgs a)
@@ -2849,8 +2967,8 @@ __global__ void __launch_bounds__(kScanThreads) k_sd_keep_write(const __grid_con
     const int64_t En = (int64_t)cnt[C_E] + cnt[C_SPLIT] + cnt[C_PAIRS];
     const int pe = cnt[C_EPAR];
     const int2 *edges = a.edges[pe];
-    scan_write_body(En, KeepCount{edges, a.sig[cnt[C_VPAR]], sd_futmask(cnt[C_IDX], a.R)}, KeepEmit{edges, a.edges[pe ^ 1], a.used[cnt[C_APAR] ^ 1]},
-                    a.block_sums, cnt + C_KEPT);
+    scan_write_body4_t<kScanThreads>(En, KeepCount{edges, a.sig[cnt[C_VPAR]], sd_futmask(cnt[C_IDX], a.R)},
+                                     KeepEmit{edges, a.edges[pe ^ 1], a.used[cnt[C_APAR] ^ 1]}, a.block_sums, cnt + C_KEPT);
 }
 // Commits the step that just ran (first = 0), chooses the next hyperplane and reports to the host.
 //   slot = report + 8 * (seq % kReportSlots): slot[1..5] = {another step follows, vertex slots, edges, position of the
@@ -3324,6 +3442,33 @@ int tnb_complex_from_arrays(const tnb_net *net, const float *d_vertices, int64_t
     c->stream = (cudaStream_t)stream;
     *out = c;
     return TNB_OK;
+}
+
+// the caller's cached rows (subpoly.py:92-95: `outputs_` may carry the zeros the failover override wrote) replace the
+// evaluated ones; the packed signs follow them
+static __global__ void k_pack_rows(const float *__restrict__ out, int64_t V, int R, float eps, uint64_t *__restrict__ sig)
+{
+    for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
+        uint64_t pos, neg;
+        pack_signs(out + v * R, R, eps, pos, neg);
+        sig[3 * v] = pos;
+        sig[3 * v + 1] = neg;
+    }
+}
+int tnb_complex_write_outputs(const tnb_net *net, tnb_complex *c, const float *d_outputs, void *stream)
+{
+    if (!net || !c || !d_outputs) { set_error("tnb_complex_write_outputs: null argument"); return TNB_ERR_INVALID; }
+    cudaStream_t s = (cudaStream_t)stream;
+    current_stream() = s;
+    c->stream = s;
+    int rc = complex_compact(c, s);   // the rows are the caller's: one per vertex of the complex as tnb_complex_read returns it
+    if (rc) return rc;
+    if (c->V == 0) return TNB_OK;
+    TNB_CUDA(cudaMemcpyAsync(c->cout_(), d_outputs, (size_t)c->V * c->R * sizeof(float), cudaMemcpyDeviceToDevice, s));
+    k_pack_rows<<<grid_for(c->V, 256), 256, 0, s>>>(c->cout_(), c->V, c->R, net->meta.eps, c->csig());
+    TNB_LAUNCH_CHECK();
+    TNB_CUDA(cudaMemsetAsync(c->counters.p + C_CROSS, 0, sizeof(uint64_t), s));
+    return initial_cross_mask(c, s);
 }
 
 void tnb_complex_destroy(tnb_complex *c) { delete c; }

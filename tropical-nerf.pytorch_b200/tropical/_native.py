@@ -103,6 +103,7 @@ SIGNATURES = {
     "tnb_extract_mesh_finish": (ctypes.c_int, [_P, _P, _P, _P]),
     "tnb_mesh_read_tags": (ctypes.c_int, [_P, _P, _P]),
     "tnb_mesh_read_vertex_index": (ctypes.c_int, [_P, _P, _P]),
+    "tnb_complex_write_outputs": (ctypes.c_int, [_P, _P, _P, _P]),
     "tnb_net_outputs_group8": (ctypes.c_int, [_P, _P, _I64, _F, _P, _P, _P]),
     "tnb_curve_intersections": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "tnb_polygon_order": (ctypes.c_int, [_P, _P, _I64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P]),
@@ -303,13 +304,19 @@ class NativeNet:
         check(lib().tnb_skeleton(self.handle, int(unit), float(size), ctypes.byref(h), _stream()))
         return NativeComplex(self, h)
 
-    def complex_from_arrays(self, vertices, edges):
+    def complex_from_arrays(self, vertices, edges, outputs=None):
+        """Complex from caller arrays; `outputs` [V, R] = cached network rows that replace the evaluated ones."""
         vertices = vertices.contiguous().float()
         edges = edges.contiguous().long()
         h = ctypes.c_void_p()
         check(lib().tnb_complex_from_arrays(self.handle, _ptr(vertices), vertices.shape[0], _ptr(edges),
                                             edges.shape[0], ctypes.byref(h), _stream()))
-        return NativeComplex(self, h)
+        c = NativeComplex(self, h)
+        if outputs is not None and vertices.shape[0]:
+            outputs = outputs.contiguous().float()
+            assert outputs.shape == (vertices.shape[0], self.n_outputs)
+            check(lib().tnb_complex_write_outputs(self.handle, c.handle, _ptr(outputs), _stream()))
+        return c
 
     def skeleton_sweep_alloc(self, unit=128):
         """The whole grid's sweep with nothing evaluated (filled by write_dist / set_max_grad)."""
@@ -521,13 +528,21 @@ class NativeMesh:
             check(lib().tnb_mesh_read_tags(self.handle, _ptr(t), _stream()))
         return t
 
-    def read_host(self, polygons=True):
+    def read_host(self, polygons=True, out=None):
         """numpy arrays through tnb_mesh_read_host (host buffers): vertices, triangles,
-        faces (what the reference's subpoly() returns) and, optionally, the polygon rows."""
+        faces (what the reference's subpoly() returns) and, optionally, the polygon rows.
+        `out` = {"v": float32 buffer, "t": int64 buffer, "f": float32 buffer} of flat host arrays at least as
+        large (e.g. views of pinned memory, reused from call to call): the results are views into them."""
         s = self.sizes()
-        v = np.empty((s["V"], 3), np.float32)
-        t = np.empty((s["T"], 3), np.int64)
-        f = np.empty((s["T"], 3, 3), np.float32)
+        if out is not None:
+            v = out["v"][:s["V"] * 3].reshape(s["V"], 3)
+            t = out["t"][:s["T"] * 3].reshape(s["T"], 3)
+            f = out["f"][:s["T"] * 9].reshape(s["T"], 3, 3)
+            assert v.dtype == np.float32 and t.dtype == np.int64 and f.dtype == np.float32
+        else:
+            v = np.empty((s["V"], 3), np.float32)
+            t = np.empty((s["T"], 3), np.int64)
+            f = np.empty((s["T"], 3, 3), np.float32)
         p = np.empty((s["P"], s["W"]), np.int64) if polygons else None
         check(lib().tnb_mesh_read_host(self.handle, v.ctypes.data, t.ctypes.data, f.ctypes.data,
                                        p.ctypes.data if polygons else None))

@@ -69,9 +69,10 @@ def subpoly_(vertices, edges, net, l, h, eps, outputs_=None, pruning=True, stric
 
 def extract_skeleton(vertices, edges, net, eps, outputs=None):
     """Vertices and edges of the complex that lie on the zero level set (subpoly.py:556-581):
-    (vertices, edges, v_idx) with v_idx = the numbers of the kept vertices in the input.  `outputs`
-    (the cached rows the reference threads through) is recomputed on the device."""
-    cx = net.native().complex_from_arrays(vertices, edges)
+    (vertices, edges, v_idx) with v_idx = the numbers of the kept vertices in the input.  `outputs` =
+    the cached network rows [V, R] of the vertices (they carry the zeros of the failover override);
+    evaluated on the device when None."""
+    cx = net.native().complex_from_arrays(vertices, edges, outputs)
     mesh = cx.extract_mesh(eps)
     if mesh.sizes()["V"] == 0:
         return torch.Tensor([]).to(edges), torch.Tensor([]).to(edges), None
@@ -85,7 +86,7 @@ def extract_faces(vertices: Tensor, edges: Tensor, net: Module, outputs: Tensor 
     returned (every vertex on the surface and on an edge), so the numbering is kept."""
     if 0 == vertices.shape[0]:
         return [], []
-    mesh = net.native().complex_from_arrays(vertices, edges).extract_mesh(net.eps if eps is None else eps)
+    mesh = net.native().complex_from_arrays(vertices, edges, outputs).extract_mesh(net.eps if eps is None else eps)
     if mesh.sizes()["V"] != vertices.shape[0]:
         raise _native.NativeError("extract_faces expects the output of extract_skeleton (vertices off the surface or on no edge)")
     _, _, tri, faces, _ = mesh.read()
