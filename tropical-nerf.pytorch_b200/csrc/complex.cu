@@ -177,16 +177,37 @@ struct ChunkSeg {  // one (chunk, axis) block of candidate grid edges, in the re
 };
 constexpr int kMaxSegs = 3 * 512;
 
-// |tanh(sdf)| and |grad| of every marks-grid vertex of one chunk; per-chunk max |grad|
+// |tanh(sdf)| and |grad| of every marks-grid vertex of every chunk piece, per-chunk max |grad|: ONE launch.
+// A CTA belongs to one piece (cta_first = its first CTA); the pieces get CTAs in proportion to their vertices,
+// four trips of two vertices per thread, so that the hardware back-fills CTAs across pieces.  As one launch
+// per chunk (8 for the 201^3 grid) every launch ended in its own tail: the 74^3 corner chunk ran at 5.9 G
+// vertices/s against 15.7 for the 128^3 one (profiles/r2_ncu_launches_large_sphere.txt).
+struct SweepPiece {
+    int s[3], n[3];   // first grid vertex / vertices per axis
+    int chunk;        // whose max |grad| this piece feeds
+    int cta_first, ctas;
+    LatticeStride ls; // split of the piece's thread stride (ctas * kThreads)
+};
 template <class C>
-__global__ void __launch_bounds__(kThreads, 4) k_sweep_chunk(const __grid_constant__ NetMeta n, int M, int sx, int sy,
-                                                          int sz, int nx, int ny, int nz, LatticeStride ls,
-                                                          float *__restrict__ dist, unsigned *__restrict__ max_grad)
+__global__ void __launch_bounds__(kThreads, 4) k_sweep_pieces(const __grid_constant__ NetMeta n, int M, const SweepPiece *__restrict__ pieces,
+                                                           int n_pieces, float *__restrict__ dist, unsigned *__restrict__ max_grad)
 {
+    __shared__ SweepPiece s_piece;
+    if (threadIdx.x == 0) {
+        int a = 0, b = n_pieces - 1;  // last piece whose first CTA is <= blockIdx.x
+        while (a < b) {
+            const int mid = (a + b + 1) >> 1;
+            if (pieces[mid].cta_first <= (int)blockIdx.x) a = mid; else b = mid - 1;
+        }
+        s_piece = pieces[a];
+    }
+    __syncthreads();
+    const SweepPiece pc = s_piece;
+    const int sx = pc.s[0], sy = pc.s[1], sz = pc.s[2], nx = pc.n[0], ny = pc.n[1], nz = pc.n[2];
     const int64_t count = (int64_t)nx * ny * nz;
     float local = 0.0f;
-    const int64_t first = blockIdx.x * (int64_t)blockDim.x + threadIdx.x, stride = (int64_t)gridDim.x * blockDim.x;
-    Lattice3 at(first < count ? first : 0, ls, nx, ny);
+    const int64_t first = ((int64_t)blockIdx.x - pc.cta_first) * blockDim.x + threadIdx.x, stride = (int64_t)pc.ctas * blockDim.x;
+    Lattice3 at(first < count ? first : 0, pc.ls, nx, ny);
     if constexpr (C::kFixed) {
         // two grid vertices per trip (t and t + stride): both networks in packed FFMA2s (net_eval.cuh)
         for (int64_t t = first; t < count; t += 2 * stride) {
@@ -229,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_chunk(const __grid_consta
     __syncthreads();
     if (threadIdx.x == 0) {
         for (int w = 1; w < kThreads / 32; ++w) v = max(v, s[w]);
-        atomicMax(max_grad, v);
+        atomicMax(max_grad + pc.chunk, v);
     }
 }
 
@@ -487,6 +508,8 @@ struct tnb_sweep {
     float k_len = 0.0f;
     int64_t slots = 0, rows = 0, bit_words = 0;
     std::vector<tnb::ChunkSeg> segs;
+    std::vector<tnb::SweepPiece> pieces;   // host copy (source of the async upload)
+    tnb::DevBuf<tnb::SweepPiece> d_pieces;
     tnb::DevBuf<float> dist;         // [(x_hi-x_lo+1) * M * M], plane x_lo first
     tnb::DevBuf<unsigned> max_grad;  // [n_chunks] bit patterns of non-negative floats
 };
@@ -518,8 +541,8 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
     TNB_CUDA(sw->max_grad.reserve((size_t)sw->n_chunks));
     TNB_CUDA(cudaMemsetAsync(sw->max_grad.p, 0, (size_t)sw->n_chunks * sizeof(unsigned), s));
     float *dist0 = sw->dist.p - (int64_t)x_lo * M * M;  // indexed by the global vertex number
-    int64_t slots = 0, rows = 0, words = 0;
-    int chunk = 0;
+    int64_t slots = 0, rows = 0, words = 0, total_vertices = 0;
+    int chunk = 0, total_ctas = 0;
     for (int a = 0; a < nc; ++a)
         for (int b = 0; b < nc; ++b)
             for (int cc = 0; cc < nc; ++cc, ++chunk) {
@@ -533,16 +556,17 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
                 st[0] = lo;
                 nn[0] = hi - lo + 1;
                 const int64_t count = (int64_t)nn[0] * nn[1] * nn[2];
-                if (launch) {
-                    unsigned g = grid_for(count, kThreads);
-                    const LatticeStride ls = lattice_stride((int64_t)g * kThreads, nn[0], nn[1]);
-                    prof_begin(TNB_PROF_SWEEP, s);
-                    if (net->fixed_cfg)
-                        k_sweep_chunk<CfgRef><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], ls, dist0, sw->max_grad.p + chunk);
-                    else
-                        k_sweep_chunk<CfgAny><<<g, kThreads, 0, s>>>(net->meta, M, st[0], st[1], st[2], nn[0], nn[1], nn[2], ls, dist0, sw->max_grad.p + chunk);
-                    TNB_LAUNCH_CHECK();
-                    prof_end(TNB_PROF_SWEEP, s, count, count * 4 + (int64_t)net->table.cap * 8);
+                {
+                    SweepPiece pc;
+                    for (int d = 0; d < 3; ++d) { pc.s[d] = st[d]; pc.n[d] = nn[d]; }
+                    pc.chunk = chunk;
+                    pc.cta_first = total_ctas;
+                    // four trips of two vertices per thread (one vertex per trip for other network shapes)
+                    pc.ctas = (int)std::max<int64_t>(1, (count + kThreads * 8 - 1) / (kThreads * 8));
+                    pc.ls = lattice_stride((int64_t)pc.ctas * kThreads, nn[0], nn[1]);
+                    total_ctas += pc.ctas;
+                    total_vertices += count;
+                    sw->pieces.push_back(pc);
                 }
                 const int w32 = (nn[2] + 31) / 32;
                 for (int axis = 0; axis < 3; ++axis) {
@@ -567,6 +591,17 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
     sw->slots = slots;
     sw->rows = rows;
     sw->bit_words = words;
+    if (launch && !sw->pieces.empty()) {
+        TNB_CUDA(sw->d_pieces.reserve(sw->pieces.size()));
+        TNB_CUDA(cudaMemcpyAsync(sw->d_pieces.p, sw->pieces.data(), sw->pieces.size() * sizeof(SweepPiece), cudaMemcpyHostToDevice, s));
+        prof_begin(TNB_PROF_SWEEP, s);
+        if (net->fixed_cfg)
+            k_sweep_pieces<CfgRef><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p);
+        else
+            k_sweep_pieces<CfgAny><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p);
+        TNB_LAUNCH_CHECK();
+        prof_end(TNB_PROF_SWEEP, s, total_vertices, total_vertices * 4 + (int64_t)net->table.cap * 8);
+    }
     return TNB_OK;
 }
 
@@ -2967,8 +3002,9 @@ __global__ void __launch_bounds__(kScanThreads) k_sd_keep_write(const __grid_con
     const int64_t En = (int64_t)cnt[C_E] + cnt[C_SPLIT] + cnt[C_PAIRS];
     const int pe = cnt[C_EPAR];
     const int2 *edges = a.edges[pe];
-    scan_write_body4_t<kScanThreads>(En, KeepCount{edges, a.sig[cnt[C_VPAR]], sd_futmask(cnt[C_IDX], a.R)},
-                                     KeepEmit{edges, a.edges[pe ^ 1], a.used[cnt[C_APAR] ^ 1]}, a.block_sums, cnt + C_KEPT);
+    // (four items per thread, scan_write_body4_t, measured SLOWER here: 19.3 -> 23.7 us per launch)
+    scan_write_body(En, KeepCount{edges, a.sig[cnt[C_VPAR]], sd_futmask(cnt[C_IDX], a.R)}, KeepEmit{edges, a.edges[pe ^ 1], a.used[cnt[C_APAR] ^ 1]},
+                    a.block_sums, cnt + C_KEPT);
 }
 // Commits the step that just ran (first = 0), chooses the next hyperplane and reports to the host.
 //   slot = report + 8 * (seq % kReportSlots): slot[1..5] = {another step follows, vertex slots, edges, position of the
