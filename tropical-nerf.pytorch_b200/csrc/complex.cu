@@ -190,7 +190,7 @@ struct SweepPiece {
 };
 template <class C>
 __global__ void __launch_bounds__(kThreads, 4) k_sweep_pieces(const __grid_constant__ NetMeta n, int M, const SweepPiece *__restrict__ pieces,
-                                                           int n_pieces, float *__restrict__ dist, unsigned *__restrict__ max_grad)
+                                                           int n_pieces, float *__restrict__ dist, unsigned *__restrict__ max_grad, int sync_trips)
 {
     __shared__ SweepPiece s_piece;
     if (threadIdx.x == 0) {
@@ -209,20 +209,28 @@ __global__ void __launch_bounds__(kThreads, 4) k_sweep_pieces(const __grid_const
     const int64_t first = ((int64_t)blockIdx.x - pc.cta_first) * blockDim.x + threadIdx.x, stride = (int64_t)pc.ctas * blockDim.x;
     Lattice3 at(first < count ? first : 0, pc.ls, nx, ny);
     if constexpr (C::kFixed) {
-        // two grid vertices per trip (t and t + stride): both networks in packed FFMA2s (net_eval.cuh)
-        for (int64_t t = first; t < count; t += 2 * stride) {
-            const bool two = t + stride < count;
-            const int gi0 = sx + at.ix, gj0 = sy + at.iy, gk0 = sz + at.iz;
-            at.advance();
+        // two grid vertices per trip (t and t + stride): both networks in packed FFMA2s (net_eval.cuh).  The trip count
+        // is the CTA's (a thread past the end evaluates its last valid vertex again and stores nothing), so that the
+        // warps of a CTA can start every trip together (sync_trips): ~100 KB of straight-line code per trip and 16 warps
+        // per SM at 16 different places of it made instruction fetch the top stall of this kernel.
+        const int64_t cta_first = ((int64_t)blockIdx.x - pc.cta_first) * blockDim.x;
+        for (int64_t tb = cta_first; tb < count; tb += 2 * stride) {
+            if (sync_trips) __syncthreads();
+            const int64_t t = tb + threadIdx.x;
+            const bool one = t < count, two = t + stride < count;
+            const int gi0 = one ? sx + at.ix : sx, gj0 = one ? sy + at.iy : sy, gk0 = one ? sz + at.iz : sz;  // past the end: the piece's first vertex, not stored
+            if (one) at.advance();
             const int gi1 = two ? sx + at.ix : gi0, gj1 = two ? sy + at.iy : gj0, gk1 = two ? sz + at.iz : gk0;
-            at.advance();
+            if (two) at.advance();
             // preprocess_inverse(marks[...]) (tropical.py:186, model.py:81-82)
             float x0[3] = {n.marks[gi0] * n.pre_2s - n.pre_scale, n.marks[gj0] * n.pre_2s - n.pre_scale, n.marks[gk0] * n.pre_2s - n.pre_scale};
             float x1[3] = {n.marks[gi1] * n.pre_2s - n.pre_scale, n.marks[gj1] * n.pre_2s - n.pre_scale, n.marks[gk1] * n.pre_2s - n.pre_scale};
             float sdf[2], g[2][3];
             sdf_grad_pair<C>(n, x0, x1, sdf, g);
-            dist[((int64_t)gi0 * M + gj0) * M + gk0] = fabsf(sdf[0]);
-            local = fmaxf(local, grad_norm(g[0]));
+            if (one) {
+                dist[((int64_t)gi0 * M + gj0) * M + gk0] = fabsf(sdf[0]);
+                local = fmaxf(local, grad_norm(g[0]));
+            }
             if (two) {
                 dist[((int64_t)gi1 * M + gj1) * M + gk1] = fabsf(sdf[1]);
                 local = fmaxf(local, grad_norm(g[1]));
@@ -518,6 +526,7 @@ namespace tnb {
 
 // launch = false: only the layout (segments, buffers); |sdf| and max |grad| are written by the caller
 // (tnb_sweep_write_dist / tnb_sweep_write_max_grad: a sweep whose planes were evaluated on several GPUs)
+static const int g_sweep_sync = std::getenv("TNB_SWEEP_SYNC") ? std::atoi(std::getenv("TNB_SWEEP_SYNC")) : 1;  // A/B switch (see k_sweep_pieces)
 static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag_lower, bool tag_upper, tnb_sweep *sw,
                       cudaStream_t s, bool launch = true)
 {
@@ -596,9 +605,9 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
         TNB_CUDA(cudaMemcpyAsync(sw->d_pieces.p, sw->pieces.data(), sw->pieces.size() * sizeof(SweepPiece), cudaMemcpyHostToDevice, s));
         prof_begin(TNB_PROF_SWEEP, s);
         if (net->fixed_cfg)
-            k_sweep_pieces<CfgRef><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p);
+            k_sweep_pieces<CfgRef><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, g_sweep_sync);
         else
-            k_sweep_pieces<CfgAny><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p);
+            k_sweep_pieces<CfgAny><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, 0);
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_SWEEP, s, total_vertices, total_vertices * 4 + (int64_t)net->table.cap * 8);
     }
