@@ -2923,6 +2923,39 @@ __device__ __forceinline__ bool sd_crossed(const int *cnt) { return sd_active(cn
 // ... after the connecting-edge count: room for the edges?
 __device__ __forceinline__ bool sd_fits(const StepArgs &a) { return (int64_t)a.cnt[C_E] + a.cnt[C_SPLIT] + a.cnt[C_PAIRS] <= a.Ecap; }
 
+// The split and hit tests from the PACKED signs (the stream only runs with the eps the signs were packed with):
+//   crossed  <=>  d0 * d1 < 0, |d0| > eps, |d1| > eps  <=>  one end's positive bit and the other end's negative bit
+//   (v > eps and w < -eps: the product is below -eps^2, no underflow to -0), subpoly.py:104-105;
+//   hit      <=>  |v| < eps: only a vertex with neither bit set (|v| <= eps) can pass, and only for those is the
+//   float read (the boundary case |v| == eps is decided by the float, as in subpoly.py:233).
+// The sign words of the whole complex are 17 MB and stay in L2 across the kernels of a step; the 132-byte rows the
+// float tests gathered from are 92 MB (ncu: 115-177 MB of DRAM reads per launch of this kernel before).
+struct SplitCountSig {
+    const int2 *edges;
+    const uint64_t *sig;
+    int idx;
+    __device__ __forceinline__ int operator()(int64_t e) const
+    {
+        const int2 ed = edges[e];
+        const uint64_t pa = sig[3 * (int64_t)ed.x], na = sig[3 * (int64_t)ed.x + 1];
+        const uint64_t pb = sig[3 * (int64_t)ed.y], nb = sig[3 * (int64_t)ed.y + 1];
+        return (int)((((pa & nb) | (na & pb)) >> idx) & 1ull);
+    }
+};
+struct HitCountSig {
+    const float *out;
+    const uint64_t *sig;
+    const int *alive;
+    int R, idx;
+    float eps;
+    __device__ __forceinline__ int operator()(int64_t v) const
+    {
+        const int al = alive[v];
+        const uint64_t nz = sig[3 * v] | sig[3 * v + 1];
+        if (!al || ((nz >> idx) & 1ull)) return 0;
+        return fabsf(out[v * R + idx]) < eps ? 1 : 0;
+    }
+};
 // split compaction over the edges (first half of the grid) and hit compaction over the vertices (second half)
 __global__ void __launch_bounds__(kScanThreads) k_sd_count(const __grid_constant__ StepArgs a)
 {
@@ -2930,9 +2963,10 @@ __global__ void __launch_bounds__(kScanThreads) k_sd_count(const __grid_constant
     if (!sd_active(cnt)) return;
     const int idx = cnt[C_IDX], nb = (int)gridDim.x >> 1, pv = cnt[C_VPAR];
     if ((int)blockIdx.x < nb)
-        scan_count_mask_part(cnt[C_E], SplitCount{a.edges[cnt[C_EPAR]], a.out[pv], a.R, idx, a.eps}, a.block_sums, a.mask_e, (int)blockIdx.x, nb);
+        scan_count_mask_part(cnt[C_E], SplitCountSig{a.edges[cnt[C_EPAR]], a.sig[pv], idx}, a.block_sums, a.mask_e, (int)blockIdx.x, nb);
     else
-        scan_count_mask_part(cnt[C_V], HitCount{a.out[pv], a.used[cnt[C_APAR]], a.R, idx, a.eps}, a.block_sums + nb, a.mask_v, (int)blockIdx.x - nb, nb);
+        scan_count_mask_part(cnt[C_V], HitCountSig{a.out[pv], a.sig[pv], a.used[cnt[C_APAR]], a.R, idx, a.eps}, a.block_sums + nb, a.mask_v,
+                             (int)blockIdx.x - nb, nb);
 }
 __global__ void __launch_bounds__(kScanThreads) k_sd_write(const __grid_constant__ StepArgs a)
 {
@@ -3033,18 +3067,19 @@ __global__ void k_sd_finish(const __grid_constant__ StepArgs a, const __grid_con
             if (En > a.Ecap) cnt[C_STICKY] = kStickyCapacity;
             else {
                 cnt[C_V] = V0 + S;
-                unsigned long long back = (unsigned long long)n_cand * 28 + (unsigned long long)P * 8;
                 if (cnt[C_PRUNE]) {
                     cnt[C_E] = cnt[C_KEPT];
                     cnt[C_EPAR] ^= 1;
                     cnt[C_APAR] ^= 1;
-                    back += (unsigned long long)En * (8 + 2 * 48) + (unsigned long long)(V0 + S) * 8;
                 } else {
                     cnt[C_E] = (int)En;
                 }
-                a.bytes[0] += 2ull * 16 * E0 + 2ull * 4 * V0 + (unsigned long long)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * a.R + 8 + 16) +
-                              (unsigned long long)n_cand * (24 + 8 + 4 + 24);
-                a.bytes[1] += back;
+                // compulsory bytes of the two TIMED kernel classes only (the scans and the pruning pass around them are
+                // not inside the event pairs): a new vertex reads its edge, both ends' position / value / signs and
+                // writes position, row, signs and two edges; a candidate reads its record and the records around it
+                // (counted once: 32 B) and writes its count, offset and pairs
+                a.bytes[0] += (unsigned long long)S * (8 + 4 + 2 * (12 + 4 + 16) + 12 + 4 * a.R + 24 + 16);
+                a.bytes[1] += (unsigned long long)n_cand * (32 + 32 + 8) + (unsigned long long)P * 8;
                 a.bytes[2] += (unsigned long long)S;
                 a.bytes[3] += (unsigned long long)n_cand;
             }
@@ -3077,7 +3112,8 @@ static bool g_stream_steps = std::getenv("TNB_NO_STREAM_STEPS") == nullptr;  // 
 // can the hyperplanes of this complex run as a device-driven stream?
 static bool stream_ok(const tnb_net *net, const tnb_complex *c, float eps, bool planar)
 {
-    return g_stream_steps && planar && !c->halo.enabled && c->E > 0 && eps == net->meta.eps && net->meta.R <= 64;
+    // eps >= 1e-15: the packed-sign form of the split test needs eps^2 to be a normal float (no underflow of d0 * d1)
+    return g_stream_steps && planar && !c->halo.enabled && c->E > 0 && eps == net->meta.eps && eps >= 1e-15f && net->meta.R <= 64;
 }
 
 // Runs the steps lh[0 .. n_steps) (or, when the complex becomes small enough for the persistent kernel, a prefix
