@@ -264,22 +264,23 @@ def cpu_extract_seconds(P, planar=True):
     return time.perf_counter() - t, vertices.shape[0], tri.shape[0]
 
 
-_REF_WORKLOAD = None   # set in the parent before the worker pool forks: the children must not build it again
+_WL_KEYS = ("levels", "n_feat", "log2_T", "n_min", "per_level_scale", "num_layers", "num_hidden", "table", "mlp", "marks", "eps", "scale")
 
 
-def _reference_worker(job):
-    """One host core: its share of the run's full extractions with the oracle port.  Touches numpy and
-    the C checker only -- the parent imported torch (workload generation) and a forked child must not
-    enter torch's thread pools."""
-    planar, n_mine, warm = job
-    P = oracle_params(_REF_WORKLOAD)
+def reference_worker_main(path, planar, n_mine, warm):
+    """`bench.py --ref-worker ...`: one host core's share of the run's full extractions with the oracle port, in a
+    process of its own that imports numpy and the C checker only (no torch, no CUDA: the parent fitted the workload
+    on the GPU, and a forked copy of that process hung in the OpenMP / CUDA state it inherited)."""
+    g = np.load(path)
+    w = {k: (g[k] if g[k].ndim else g[k].item()) for k in _WL_KEYS}
+    P = oracle_params(w)
     if warm:   # page in numpy / the C checker with a small extraction (untimed)
         cpu_extract_seconds(oracle_params(load_workload("small_sphere")), planar)
     t0 = time.perf_counter()
     nv = nt = 0
     for _ in range(n_mine):
         _, nv, nt = cpu_extract_seconds(P, planar)
-    return time.perf_counter() - t0, nv, nt
+    print(json.dumps({"seconds": time.perf_counter() - t0, "nv": int(nv), "nt": int(nt)}), flush=True)
 
 
 def shared_config(w, planar, nv, nt):
@@ -298,8 +299,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    global _REF_WORKLOAD
-    w = _REF_WORKLOAD = load_workload(args.workload)
+    import tempfile
+    w = load_workload(args.workload)
     planar = args.path == "planar"
     avail = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     # bounded so that the workers' working sets (numpy temporaries of [sum 2^k, 36] int64 region matrices:
@@ -307,13 +308,22 @@ def run_reference(args):
     cap = args.ref_cores if args.ref_cores > 0 else {"small": 32, "medium": 16, "large": 8}.get(args.workload.split("_")[0], 8)
     cores = max(1, min(avail, cap, args.steps))
     share = [args.steps // cores + (1 if i < args.steps % cores else 0) for i in range(cores)]
-    jobs = [(planar, n, 1 if args.warmup > 0 else 0) for n in share]
+    fd, path = tempfile.mkstemp(suffix=".npz", prefix="tnb_ref_workload_")
+    os.close(fd)
+    np.savez(path, **{k: np.asarray(w[k]) for k in _WL_KEYS})
+    env = dict(os.environ, OMP_NUM_THREADS="1", OPENBLAS_NUM_THREADS="1", MKL_NUM_THREADS="1", CUDA_VISIBLE_DEVICES="")
     t0 = time.perf_counter()
-    if cores == 1:
-        res = [_reference_worker(jobs[0])]
-    else:
-        with mp.get_context("fork").Pool(cores) as pool:
-            res = pool.map(_reference_worker, jobs)
+    procs = [subprocess.Popen([sys.executable, os.path.abspath(__file__), "--ref-worker", path, str(int(planar)), str(n),
+                               str(1 if args.warmup > 0 else 0)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env)
+             for n in share]
+    res = []
+    for pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise SystemExit("reference worker failed: " + err[-2000:])
+        r = json.loads(out.strip().splitlines()[-1])
+        res.append((r["seconds"], r["nv"], r["nt"]))
+    os.unlink(path)
     wall = time.perf_counter() - t0
     slowest = max(r[0] for r in res)
     nv, nt = res[0][1], res[0][2]
@@ -659,6 +669,8 @@ def run_ours(args):
 
 
 def main():
+    if len(sys.argv) >= 6 and sys.argv[1] == "--ref-worker":
+        return reference_worker_main(sys.argv[2], sys.argv[3] == "1", int(sys.argv[4]), sys.argv[5] == "1")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
