@@ -10,6 +10,7 @@
 #include <cstdlib>
 #include <cstdio>
 #include <cstring>
+#include <thread>
 #include <vector>
 
 #include <cooperative_groups.h>
@@ -3158,6 +3159,10 @@ static int steps_stream_impl(const tnb_net *net, tnb_complex *c, const int32_t *
     auto wait_for = [&](int seq) -> int {
         rep = report + 8 * (seq & (kReportSlots - 1));
         for (long spins = 0; rep[0] - seq < 0; ++spins) {
+#if defined(__x86_64__) || defined(__i386__)
+            __builtin_ia32_pause();
+#endif
+            if ((spins & 0x3ff) == 0x3ff) std::this_thread::yield();  // several extractions in flight on one box share its cores
             if ((spins & 0xfffff) == 0xfffff) {  // now and then: did the stream die?
                 cudaError_t e = cudaStreamQuery(s);
                 if (e != cudaSuccess && e != cudaErrorNotReady) return cuda_fail(e, "device-driven step stream", __FILE__, __LINE__);
