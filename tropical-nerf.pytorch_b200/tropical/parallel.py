@@ -156,37 +156,65 @@ def merge_slab_meshes(parts: Sequence[tuple]):
     return vertices, triangles, {"shared_vertices": shared, "slabs": len(parts)}
 
 
+def _n_chunks(n_marks: int, unit: int) -> int:
+    """Chunks of the skeleton sweep, as range(0, L, unit - 1) enumerates them per axis (tropical.py:176-181)."""
+    return len(range(0, n_marks, unit - 1)) ** 3
+
+
 def _run_slabs(net, mine, world_size, boxes_of, reduce_max, sum_int, eps, unit, payload, seq0, timeout_ms):
     """Skeleton, hyperplane steps and face extraction of the slabs `mine` (rank numbers) on the
     current device and stream.  Several slabs per process run in lock step: every slab posts its
-    messages before any slab waits for them."""
+    messages before any slab waits for them.
+
+    The two collectives of the set-up (`reduce_max`, `sum_int`) are reached by EVERY rank exactly once
+    and in this order, whatever fails locally: a rank whose sweep or edge selection raised contributes
+    neutral values and a failure flag (folded into `sum_int` as a large negative number), so that no rank is
+    left alone in a collective.  From the steps on nothing but the mailboxes connects the ranks, and
+    their receive has its own timeout and status word (csrc/halo.cuh).  Returns (meshes, error)."""
+    from . import _native
     planes = slab_planes(net.n_marks, world_size)
-    sweeps = [net.skeleton_sweep(planes[r][0], planes[r][1], r > 0, r < world_size - 1, unit) for r in mine]
-    mg = sweeps[0].max_grad()
-    for sw in sweeps[1:]:
-        mg = torch.maximum(mg, sw.max_grad())
+    err, sweeps, cs = None, [], []
+    try:
+        sweeps = [net.skeleton_sweep(planes[r][0], planes[r][1], r > 0, r < world_size - 1, unit) for r in mine]
+        mg = sweeps[0].max_grad()
+        for sw in sweeps[1:]:
+            mg = torch.maximum(mg, sw.max_grad())
+    except _native.NativeError as e:
+        err, mg = e, torch.zeros(_n_chunks(net.n_marks, unit), dtype=torch.float32, device="cuda")
     mg = reduce_max(mg)
-    cs = []
-    for sw in sweeps:
-        sw.set_max_grad(mg)
-        cs.append(sw.finish())
+    edges = 0
+    if err is None:
+        try:
+            for sw in sweeps:
+                sw.set_max_grad(mg)
+                cs.append(sw.finish())
+            edges = sum(c.num_edges for c in cs)
+        except _native.NativeError as e:
+            err = e
     del sweeps
-    if sum_int(sum(c.num_edges for c in cs)) == 0:
-        return None  # empty skeleton everywhere: the caller takes the hypercube route (subpoly.py:51-52)
-    for r, c in zip(mine, cs):
-        c.set_halo(r, world_size, boxes_of(r), payload, timeout_ms, seq0)
-    for l, h in _hyperplanes(net):
-        if len(cs) == 1:
-            cs[0].step_part(l, h, 0, eps, True)
-        else:
-            for c in cs:
-                c.step_part(l, h, 1, eps, True)
-            for c in cs:
-                c.step_part(l, h, 2, eps, True)
-    meshes = [c.extract_mesh_begin(eps) for c in cs]
-    for c, m in zip(cs, meshes):
-        c.extract_mesh_finish(m)
-    return meshes
+    FAIL = -(1 << 40)
+    total = sum_int(FAIL if err is not None else edges)
+    if total < 0:      # somebody failed during the set-up: every rank leaves here, together
+        return None, (err or _native.NativeError("another rank failed during the set-up of the sharded extraction"))
+    if total == 0:
+        return None, None  # empty skeleton everywhere: the caller takes the hypercube route (subpoly.py:51-52)
+    try:
+        for r, c in zip(mine, cs):
+            c.set_halo(r, world_size, boxes_of(r), payload, timeout_ms, seq0)
+        for l, h in _hyperplanes(net):
+            if len(cs) == 1:
+                cs[0].step_part(l, h, 0, eps, True)
+            else:
+                for c in cs:
+                    c.step_part(l, h, 1, eps, True)
+                for c in cs:
+                    c.step_part(l, h, 2, eps, True)
+        meshes = [c.extract_mesh_begin(eps) for c in cs]
+        for c, m in zip(cs, meshes):
+            c.extract_mesh_finish(m)
+    except _native.NativeError as e:
+        return None, e
+    return meshes, None
 
 
 def _read_part(mesh):
@@ -209,15 +237,14 @@ def subpoly_slabs_local(net, n_slabs: int, size: float = 1.2, eps: float = 1e-4,
     try:
         for attempt in range(4):
             _RUNS += 1
-            try:
-                meshes = _run_slabs(net, list(range(n_slabs)), n_slabs, lambda r: boxes, lambda t: t, lambda x: x,
-                                    eps, unit, payload, (_RUNS * 4096) & 0xFFFFFF, 200)
+            meshes, e = _run_slabs(net, list(range(n_slabs)), n_slabs, lambda r: boxes, lambda t: t, lambda x: x,
+                                   eps, unit, payload, (_RUNS * 4096) & 0xFFFFFF, 200)
+            if e is None:
                 break
-            except _native.NativeError as e:
-                if "TNB_ERR_CAPACITY" not in str(e) or attempt == 3:
-                    raise
-                factor *= 2.0
-                _native.check(_native.lib().tnb_set_capacity_factor(factor))
+            if "TNB_ERR_CAPACITY" not in str(e) or attempt == 3:
+                raise e
+            factor *= 2.0
+            _native.check(_native.lib().tnb_set_capacity_factor(factor))
     finally:
         _native.check(_native.lib().tnb_set_capacity_factor(4.0))
     if meshes is None:
@@ -285,12 +312,15 @@ def subpoly_sharded(net, size: float = 1.2, eps: float = 1e-4, unit: int = 128, 
     try:
         for attempt in range(4):
             _RUNS += 1
-            err, msg, meshes, part = 0, "", None, None
-            try:
-                meshes = _run_slabs(net, [me], w, lambda r: boxes, reduce_max, sum_int, eps, unit, payload,
-                                    (_RUNS * 4096) & 0xFFFFFF, timeout_ms)
-                part = _read_part(meshes[0]) if meshes is not None else None
-            except _native.NativeError as e:
+            err, msg, part = 0, "", None
+            meshes, e = _run_slabs(net, [me], w, lambda r: boxes, reduce_max, sum_int, eps, unit, payload,
+                                   (_RUNS * 4096) & 0xFFFFFF, timeout_ms)
+            if e is None and meshes is not None:
+                try:
+                    part = _read_part(meshes[0])
+                except _native.NativeError as e2:
+                    e = e2
+            if e is not None:
                 err, msg = (1 if "TNB_ERR_CAPACITY" in str(e) else 2), str(e)
             t = torch.tensor([err], dtype=torch.long, device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
