@@ -361,6 +361,12 @@ __device__ __forceinline__ int row_compare(const unsigned long long *x, int nx, 
     return nx == ny ? 0 : (nx < ny ? -1 : 1);  // torch pads with -1, which sorts first
 }
 
+// LPV = lanes per vertex.  A surface vertex of a fitted network lies on two other planes as a rule: four
+// adjacent regions, i.e. four busy lanes of a warp's 32.  LPV = 8 packs four vertices into a warp (those with
+// up to three zero columns: 8 regions); the rare vertices with four or five zero columns take a whole warp
+// (LPV = 32) in a launch of their own, as do the vertices of the long pass.  Everything below is group local:
+// ballots are masked to the group's lanes, skips are per-lane predicates (no warp-wide `continue`).
+template <int LPV>
 __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint64_t *__restrict__ sig,
                                                           const int2 *__restrict__ cells,
                                                           const tnb_bucket_rec *__restrict__ recs, int dim,
@@ -380,37 +386,44 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
     // vertices only, rows in an HBM scratch of the longest row seen.
     extern __shared__ unsigned long long s_rows[];  // [kThreads][stride] unless scratch is used
     __shared__ int s_cnt[kThreads];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int GPW = 32 / LPV;  // vertices (groups) per warp
+    constexpr int kMaxK = LPV == 8 ? 3 : kMaxZeros;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, sub = lane & (LPV - 1), g0 = lane & ~(LPV - 1);
+    const unsigned gmask = LPV == 32 ? 0xffffffffu : (((1u << LPV) - 1u) << g0);
     unsigned long long *base = scratch ? scratch + ((size_t)blockIdx.x * kThreads + warp * 32) * stride
                                        : s_rows + (size_t)warp * 32 * stride;
     unsigned long long *mine = base + (size_t)lane * stride;
     int *wcnt = s_cnt + warp * 32;
     const int64_t n_items = list ? n_list : V;
-    for (int64_t item = (int64_t)blockIdx.x * (kThreads / 32) + warp; item < n_items; item += (int64_t)gridDim.x * (kThreads / 32)) {
-        const int64_t a = list ? list[item] : item;
-        if (!list && mode == 1 && is_long[a]) continue;  // the long pass writes this vertex's rows
+    const int64_t per_pass = (int64_t)gridDim.x * (kThreads / 32) * GPW;
+    for (int64_t item0 = ((int64_t)blockIdx.x * (kThreads / 32) + warp) * GPW; item0 < n_items; item0 += per_pass) {  // warp uniform
+        const int64_t item = item0 + lane / LPV;
+        bool active = item < n_items;
+        const int64_t a = active ? (list ? list[item] : item) : 0;
+        if (active && !list && mode == 1 && is_long[a]) active = false;  // the long pass writes this vertex's rows
         const uint64_t pa = sig[3 * a], na = sig[3 * a + 1], ga = sig[3 * a + 2];
         const uint64_t za = ~(pa | na) & colmask;
         const int gz = 3 - grid_mask(ga, 0) - grid_mask(ga, 1) - grid_mask(ga, 2);
         const int ka = __popcll(za) + gz;
+        // which launch takes this vertex: the packed one those with up to 3 zero columns, the wide one the others
+        if (!list && (LPV == 8 ? ka > 3 : ka <= 3)) active = false;
         int cnt = 0;
         bool lead = false;
-        const unsigned todo = mode == 1 ? (unsigned)rows_per_vertex[a] : 0xffffffffu;
-        if (todo == 0) continue;  // warp uniform
-        if (ka > kMaxZeros) {
-            if (lane == 0) atomicOr(counters + F_ERR_ZEROS, 1);
-        } else if (lane < (1 << ka) && ((todo >> lane) & 1u)) {
+        const unsigned todo = !active ? 0u : (mode == 1 ? (unsigned)rows_per_vertex[a] : 0xffffffffu);
+        if (active && ka > kMaxZeros) {
+            if (sub == 0) atomicOr(counters + F_ERR_ZEROS, 1);
+        } else if (active && ka <= kMaxK && sub < (1 << ka) && ((todo >> sub) & 1u)) {
             // region q: bit t of q decides the side of a's t-th zero column (grid axes first)
             int cell[3];
             int t = 0;
 #pragma unroll
             for (int d = 0; d < 3; ++d) {
                 cell[d] = grid_off(ga, d);
-                if (!grid_mask(ga, d)) { if (!((lane >> t) & 1)) cell[d] -= 1; ++t; }
+                if (!grid_mask(ga, d)) { if (!((sub >> t) & 1)) cell[d] -= 1; ++t; }
             }
             uint64_t pat = pa & colmask;
             for (uint64_t m = za; m; m &= m - 1, ++t)
-                if ((lane >> t) & 1) pat |= m & (~m + 1);
+                if ((sub >> t) & 1) pat |= m & (~m + 1);
             // slab sharding: regions of cells that belong to a neighbour slab are emitted there
             const bool mine_cell = cell[0] >= cell_lo && cell[0] <= cell_hi;
             // collect the region's vertices ordered by (zero count, vertex number): the row
@@ -446,11 +459,11 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
             if (led_by_other) cnt = 0;
             lead = cnt >= 3;  // every surviving row starts with a itself
         }
-        {   // a row that does not fit: the whole vertex goes to the long pass (warp uniform)
+        {   // a row that does not fit: the whole vertex goes to the long pass (group uniform)
             const bool over = cnt > stride;
             if (over) atomicMax(counters + F_MAXCNT, cnt);
-            if (__any_sync(0xffffffffu, over)) {
-                if (lane == 0) {
+            if (__ballot_sync(0xffffffffu, over) & gmask) {
+                if (sub == 0 && active) {
                     if (list) atomicOr(counters + F_ERR_ROW, 1);  // the long pass is sized to the longest row: cannot happen
                     else if (mode == 0) {
                         is_long[a] = 1;
@@ -458,12 +471,14 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                         long_list[atomicAdd(counters + F_NLONG, 1)] = (int)a;
                     }
                 }
-                continue;
+                active = false;
+                lead = false;
+                cnt = 0;
             }
         }
         wcnt[lane] = cnt;
         __syncwarp();
-        const unsigned lead_mask = __ballot_sync(0xffffffffu, lead);
+        const unsigned lead_mask = __ballot_sync(0xffffffffu, lead) & gmask;
         // identical rows collapse onto the lowest lane (torch.unique(dim=0), subpoly.py:620)
         bool keep = lead;
         if (lead)
@@ -471,13 +486,13 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                 const int o = __ffs(mset) - 1;
                 if (row_compare(base + (size_t)o * stride, wcnt[o], mine, cnt) == 0) keep = false;
             }
-        const unsigned keep_mask = __ballot_sync(0xffffffffu, keep);
+        const unsigned keep_mask = __ballot_sync(0xffffffffu, keep) & gmask;
         if (mode == 0) {
-            if (lane == 0) rows_per_vertex[a] = (int)keep_mask;
+            if (sub == 0 && active) rows_per_vertex[a] = (int)(keep_mask >> g0);
             int wmax = keep ? cnt : 0;
 #pragma unroll
-            for (int d = 16; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
-            if (lane == 0 && wmax) atomicMax(counters + F_WIDTH, wmax);
+            for (int d = LPV / 2; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
+            if (sub == 0 && wmax) atomicMax(counters + F_WIDTH, wmax);
             if (keep && cnt > kSortLocal) atomicAdd(counters + F_LONG_TOTAL, cnt);  // sizes k_sort_rows' key scratch
         } else if (keep) {
             int rank = 0;  // lexicographic rank among the rows this vertex leads
@@ -984,7 +999,7 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         k_cell_sort_huge<<<kSMs, 256, kCellSortHuge * sizeof(unsigned long long), s>>>(huge_list.p, counters.p, (const int2 *)head.p, next.p, sorted.p, sig.p, colmask);
         TNB_LAUNCH_CHECK();
     }
-    const unsigned gw = grid_for(Vs, kThreads / 32);
+    const unsigned gw = grid_for(Vs, kThreads / 32), gw8 = grid_for(Vs, kThreads / 8);
     const size_t rows_smem = (size_t)kThreads * kSmemRowStride * sizeof(unsigned long long);
     DevBuf<unsigned long long> scratch;
     DevBuf<unsigned char> is_long;
@@ -994,9 +1009,14 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     TNB_CUDA(cudaMemsetAsync(is_long.p, 0, (size_t)Vs, s));
     // fast pass: every vertex, rows in shared memory
     prof_begin(TNB_PROF_FACE_ROWS, s);
-    k_region_rows<<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
-                                                  rows_per_vertex.p, nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi,
-                                                  nullptr, 0, is_long.p, long_list.p);
+    // four vertices per warp for those with up to three zero columns (nearly all), a warp each for the others
+    k_region_rows<8><<<gw8, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
+                                                      rows_per_vertex.p, nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi,
+                                                      nullptr, 0, is_long.p, long_list.p);
+    TNB_LAUNCH_CHECK();
+    k_region_rows<32><<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
+                                                       rows_per_vertex.p, nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi,
+                                                       nullptr, 0, is_long.p, long_list.p);
     TNB_LAUNCH_CHECK();
     prof_end(TNB_PROF_FACE_ROWS, s, Vs, Vs * 28);
     if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
@@ -1014,8 +1034,8 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         gl = std::min<unsigned>(grid_for(n_long, kThreads / 32), kSMs * 4);
         TNB_CUDA(scratch.reserve((size_t)gl * kThreads * stride));
         prof_begin(TNB_PROF_FACE_ROWS, s);
-        k_region_rows<<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, stride, scratch.p, rows_per_vertex.p,
-                                              nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr);
+        k_region_rows<32><<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, stride, scratch.p, rows_per_vertex.p,
+                                                  nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr);
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_FACE_ROWS, s, n_long, (int64_t)n_long * 28);
     }
@@ -1030,13 +1050,17 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     TNB_CUDA(m->poly.reserve((size_t)P * W));
     TNB_CUDA(m->pcnt.reserve((size_t)P));
     prof_begin(TNB_PROF_FACE_ROWS, s);
-    k_region_rows<<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
-                                                  rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi,
-                                                  nullptr, 0, is_long.p, nullptr);
+    k_region_rows<8><<<gw8, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
+                                                      rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi,
+                                                      nullptr, 0, is_long.p, nullptr);
+    TNB_LAUNCH_CHECK();
+    k_region_rows<32><<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
+                                                       rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi,
+                                                       nullptr, 0, is_long.p, nullptr);
     TNB_LAUNCH_CHECK();
     if (n_long > 0) {
-        k_region_rows<<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, stride, scratch.p, rows_per_vertex.p,
-                                              row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr);
+        k_region_rows<32><<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, stride, scratch.p, rows_per_vertex.p,
+                                                  row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr);
         TNB_LAUNCH_CHECK();
     }
     prof_end(TNB_PROF_FACE_ROWS, s, 0, 0);
