@@ -1467,6 +1467,19 @@ __device__ __forceinline__ void stream_partners(const PartnerQuery &q, const int
     s_incl[lane] = incl;
     s_base[lane] = base - (incl - cnt);  // record i of the concatenation, if it falls into this cell, is recs[s_base + i]
     __syncwarp();
+    if (total <= 32) {  // warp uniform, and nearly every neighbourhood: one record per lane, no slot loop
+        const bool have = lane < total;
+        tnb_bucket_rec r;
+        if (have) {
+            int k = 0;  // first cell whose inclusive prefix exceeds the lane
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1)
+                if (s_incl[k + step - 1] <= lane) k += step;
+            r = recs[s_base[k] + lane];
+        }
+        emit(have && partner_test_once(q, r, colmask), have ? r.v : 0);
+        return;
+    }
     for (int i0 = 0; i0 < total; i0 += 128) {
         tnb_bucket_rec r[4];
         bool have[4];
