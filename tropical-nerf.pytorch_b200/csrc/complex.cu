@@ -189,8 +189,8 @@ struct SweepPiece {
     int cta_first, ctas;
     LatticeStride ls; // split of the piece's thread stride (ctas * kThreads)
 };
-template <class C>
-__global__ void __launch_bounds__(kThreads, 4) k_sweep_pieces(const __grid_constant__ NetMeta n, int M, const SweepPiece *__restrict__ pieces,
+template <class C, int MINB = 4>
+__global__ void __launch_bounds__(kThreads, MINB) k_sweep_pieces(const __grid_constant__ NetMeta n, int M, const SweepPiece *__restrict__ pieces,
                                                            int n_pieces, float *__restrict__ dist, unsigned *__restrict__ max_grad, int sync_trips)
 {
     __shared__ SweepPiece s_piece;
@@ -605,7 +605,12 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
         TNB_CUDA(sw->d_pieces.reserve(sw->pieces.size()));
         TNB_CUDA(cudaMemcpyAsync(sw->d_pieces.p, sw->pieces.data(), sw->pieces.size() * sizeof(SweepPiece), cudaMemcpyHostToDevice, s));
         prof_begin(TNB_PROF_SWEEP, s);
-        if (net->fixed_cfg)
+        static const int minb = std::getenv("TNB_SWEEP_MINB") ? std::atoi(std::getenv("TNB_SWEEP_MINB")) : 4;  // A/B: registers vs warps per SM
+        if (net->fixed_cfg && minb == 3)
+            k_sweep_pieces<CfgRef, 3><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, g_sweep_sync);
+        else if (net->fixed_cfg && minb == 5)
+            k_sweep_pieces<CfgRef, 5><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, g_sweep_sync);
+        else if (net->fixed_cfg)
             k_sweep_pieces<CfgRef><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, g_sweep_sync);
         else
             k_sweep_pieces<CfgAny><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, 0);
@@ -1467,19 +1472,8 @@ __device__ __forceinline__ void stream_partners(const PartnerQuery &q, const int
     s_incl[lane] = incl;
     s_base[lane] = base - (incl - cnt);  // record i of the concatenation, if it falls into this cell, is recs[s_base + i]
     __syncwarp();
-    if (total <= 32) {  // warp uniform, and nearly every neighbourhood: one record per lane, no slot loop
-        const bool have = lane < total;
-        tnb_bucket_rec r;
-        if (have) {
-            int k = 0;  // first cell whose inclusive prefix exceeds the lane
-#pragma unroll
-            for (int step = 16; step > 0; step >>= 1)
-                if (s_incl[k + step - 1] <= lane) k += step;
-            r = recs[s_base[k] + lane];
-        }
-        emit(have && partner_test_once(q, r, colmask), have ? r.v : 0);
-        return;
-    }
+    // (measured: a one-record-per-lane path for total <= 32 -- nearly every neighbourhood -- made the kernel SLOWER,
+    // 70.7 -> 79.0 us per launch, like the uniform breaks below: the predicated four-slot form issues its loads earlier)
     for (int i0 = 0; i0 < total; i0 += 128) {
         tnb_bucket_rec r[4];
         bool have[4];
