@@ -605,13 +605,15 @@ static int sweep_impl(const tnb_net *net, int unit, int x_lo, int x_hi, bool tag
         TNB_CUDA(sw->d_pieces.reserve(sw->pieces.size()));
         TNB_CUDA(cudaMemcpyAsync(sw->d_pieces.p, sw->pieces.data(), sw->pieces.size() * sizeof(SweepPiece), cudaMemcpyHostToDevice, s));
         prof_begin(TNB_PROF_SWEEP, s);
-        static const int minb = std::getenv("TNB_SWEEP_MINB") ? std::atoi(std::getenv("TNB_SWEEP_MINB")) : 4;  // A/B: registers vs warps per SM
-        if (net->fixed_cfg && minb == 3)
-            k_sweep_pieces<CfgRef, 3><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, g_sweep_sync);
+        // registers vs warps per SM, measured (201^3 grid): 3 CTAs/SM = 168 registers, no spills: 0.80 ms; 4 = 128 registers,
+        // 200 B of spills: 0.85 ms; 5 = 96 registers, 304 B: 0.87 ms
+        static const int minb = std::getenv("TNB_SWEEP_MINB") ? std::atoi(std::getenv("TNB_SWEEP_MINB")) : 3;
+        if (net->fixed_cfg && minb == 4)
+            k_sweep_pieces<CfgRef, 4><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, g_sweep_sync);
         else if (net->fixed_cfg && minb == 5)
             k_sweep_pieces<CfgRef, 5><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, g_sweep_sync);
         else if (net->fixed_cfg)
-            k_sweep_pieces<CfgRef><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, g_sweep_sync);
+            k_sweep_pieces<CfgRef, 3><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, g_sweep_sync);
         else
             k_sweep_pieces<CfgAny><<<(unsigned)total_ctas, kThreads, 0, s>>>(net->meta, M, sw->d_pieces.p, (int)sw->pieces.size(), dist0, sw->max_grad.p, 0);
         TNB_LAUNCH_CHECK();

@@ -178,8 +178,8 @@ __global__ void __launch_bounds__(kThreads) k_region(const __grid_constant__ Net
 }
 
 // Dense lattice sweep: evaluate + bit-pack, nothing but 16 B per point leaves the SM.
-template <class C>
-__global__ void __launch_bounds__(kThreads, 4) k_sweep_signs(const __grid_constant__ NetMeta n, float3 lo,
+template <class C, int MINB = 4>
+__global__ void __launch_bounds__(kThreads, MINB) k_sweep_signs(const __grid_constant__ NetMeta n, float3 lo,
                                                           float3 step, int nx, int ny, int nz, LatticeStride ls,
                                                           float eps, ulonglong2 *__restrict__ packed)
 {
@@ -475,7 +475,12 @@ int tnb_sweep_signs(const tnb_net *net, const float lo[3], const float hi[3], co
     unsigned g = grid_for(count, kThreads, kSMs * 32);
     const LatticeStride ls = lattice_stride((int64_t)g * kThreads, nn[0], nn[1]);
     prof_begin(TNB_PROF_SIGN_SWEEP, s);
-    if (net->fixed_cfg)
+    static const int minb = std::getenv("TNB_SIGNS_MINB") ? std::atoi(std::getenv("TNB_SIGNS_MINB")) : 4;  // A/B: registers vs warps per SM
+    if (net->fixed_cfg && minb == 3)
+        k_sweep_signs<CfgRef, 3><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], ls, eps, (ulonglong2 *)d_packed);
+    else if (net->fixed_cfg && minb == 5)
+        k_sweep_signs<CfgRef, 5><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], ls, eps, (ulonglong2 *)d_packed);
+    else if (net->fixed_cfg)
         k_sweep_signs<CfgRef><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], ls, eps, (ulonglong2 *)d_packed);
     else
         k_sweep_signs<CfgAny><<<g, kThreads, 0, s>>>(net->meta, l, st, nn[0], nn[1], nn[2], ls, eps, (ulonglong2 *)d_packed);
