@@ -264,6 +264,11 @@ int tnb_grid_train_backward_backward(const tnb_grid_desc *desc, const float *d_t
  * d_raw [groups*8][2] = the last layer's output (may be NULL). */
 int tnb_net_outputs_group8(const tnb_net *net, const float *d_x, int64_t groups, float eps,
                            float *d_out, float *d_raw, void *stream);
+/* Net.forward(x, gather=True) (tropical/stanford/model.py:52-76): both return values in one pass,
+ * d_raw [n][2] = the last layer's output (o0, o1), d_out [n][R] = the gathered pre-activation rows
+ * (as tnb_net_outputs; may be NULL). */
+int tnb_net_forward(const tnb_net *net, const float *d_x, int64_t n, float *d_out, float *d_raw,
+                    void *stream);
 /* geometry.intersection_of_two_planes(p, q, plane="xz") (tropical/geometry.py:24-138) with
  * batched_polynomial_roots / _batched_polynomial_roots (:259-300): d_p, d_q [count][8] corner
  * values of the two planes, d_out [count][3] trilinear coordinates (-1 where the reference

@@ -51,6 +51,18 @@ def test_corner_points_and_group8_rows_bit_exact():
         N.outputs_group8(got.reshape(-1, 3)[:9])
 
 
+def test_forward_returns_rows_and_raw_output():
+    g = load_golden("small_sphere")
+    P = oracle_net(g)
+    N = native_net(P)
+    x = torch.rand(5000, 3, device="cuda") * 2.4 - 1.2
+    rows, raw = N.forward(x)
+    assert np.array_equal(rows.cpu().numpy(), P.outputs(x.cpu().numpy()))
+    assert np.array_equal((raw[:, 1] - raw[:, 0]).cpu().numpy(), rows[:, -1].cpu().numpy())
+    none, raw2 = N.forward(x, rows=False)
+    assert none is None and torch.equal(raw, raw2)
+
+
 def test_intersection_of_two_planes_bit_exact():
     from oracle.trinet import curve_intersections
     from tropical import geometry as gm

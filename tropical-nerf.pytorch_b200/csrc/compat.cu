@@ -71,6 +71,35 @@ __global__ void __launch_bounds__(kCompatThreads) k_outputs_group8(const __grid_
     }
 }
 
+// Net.forward(x, gather=True) with the last layer's two outputs as well (model.py:52-76 returns both)
+template <class C>
+__global__ void __launch_bounds__(kCompatThreads) k_forward_raw(const __grid_constant__ NetMeta n, const float *__restrict__ x, int64_t count,
+                                                                float *__restrict__ out, float *__restrict__ raw)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        const float p[3] = {x[3 * i], x[3 * i + 1], x[3 * i + 2]};
+        float xp[3];
+        preprocess(n, p, xp);
+        float pre[(C::kMaxLin - 1) * C::kMaxH];
+        float o[2];
+        forward<C>(n, xp, pre, o);
+        const int H = C::H(n), NL = C::NLIN(n);
+        if (out) {
+            float *row = out + i * n.R;
+#pragma unroll(C::kUnroll)
+            for (int l = 0; l < C::kMaxLin - 1; ++l)
+                if (l < NL - 1) {
+#pragma unroll(C::kUnroll)
+                    for (int j = 0; j < C::kMaxH; ++j)
+                        if (j < H) row[l * H + j] = pre[l * C::kMaxH + j];
+                }
+            row[(NL - 1) * H] = o[1] - o[0];
+        }
+        raw[2 * i] = o[0];
+        raw[2 * i + 1] = o[1];
+    }
+}
+
 __global__ void __launch_bounds__(kCompatThreads) k_curve_intersections(const float *__restrict__ p, const float *__restrict__ q, int64_t count,
                                                                         float *__restrict__ out)
 {
@@ -145,6 +174,18 @@ int tnb_net_outputs_group8(const tnb_net *net, const float *d_x, int64_t groups,
     const unsigned g = grid_for(groups * 8, kCompatThreads);
     if (net->fixed_cfg) k_outputs_group8<CfgRef><<<g, kCompatThreads, 0, s>>>(net->meta, d_x, groups, eps, d_out, d_raw);
     else k_outputs_group8<CfgAny><<<g, kCompatThreads, 0, s>>>(net->meta, d_x, groups, eps, d_out, d_raw);
+    TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+
+int tnb_net_forward(const tnb_net *net, const float *d_x, int64_t n, float *d_out, float *d_raw, void *stream)
+{
+    if (!net || n < 0 || (n > 0 && (!d_x || !d_raw))) { set_error("tnb_net_forward: bad argument"); return TNB_ERR_INVALID; }
+    if (n == 0) return TNB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    const unsigned g = grid_for(n, kCompatThreads);
+    if (net->fixed_cfg) k_forward_raw<CfgRef><<<g, kCompatThreads, 0, s>>>(net->meta, d_x, n, d_out, d_raw);
+    else k_forward_raw<CfgAny><<<g, kCompatThreads, 0, s>>>(net->meta, d_x, n, d_out, d_raw);
     TNB_LAUNCH_CHECK();
     return TNB_OK;
 }

@@ -106,6 +106,7 @@ SIGNATURES = {
     "tnb_complex_write_outputs": (ctypes.c_int, [_P, _P, _P, _P]),
     "tnb_net_outputs_group8": (ctypes.c_int, [_P, _P, _I64, _F, _P, _P, _P]),
     "tnb_curve_intersections": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
+    "tnb_net_forward": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P]),
     "tnb_polygon_order": (ctypes.c_int, [_P, _P, _I64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P]),
     "tnb_mesh_near_plane": (_I64, [_P]),
     "tnb_grid_train_table_len": (_I64, [_P]),
@@ -250,6 +251,15 @@ class NativeNet:
         out = torch.empty((n, self.n_outputs), dtype=torch.float32, device=x.device)
         check(lib().tnb_net_outputs(self.handle, _ptr(x), n, _ptr(out), _stream()))
         return out
+
+    def forward(self, x, rows=True):
+        """Net.forward(x, gather=True): (rows [n, R] or None, raw last-layer output [n, 2])."""
+        x = x.contiguous().float()
+        n = x.shape[0]
+        out = torch.empty((n, self.n_outputs), dtype=torch.float32, device=x.device) if rows else None
+        raw = torch.empty((n, 2), dtype=torch.float32, device=x.device)
+        check(lib().tnb_net_forward(self.handle, _ptr(x), n, _ptr(out), _ptr(raw), _stream()))
+        return out, raw
 
     def outputs_group8(self, x, eps=None):
         """Net.forward(x, gather=True, group=8) (model.py:52-76): x [8 G, 3] -> (rows [8 G, R], raw [8 G, 2])."""

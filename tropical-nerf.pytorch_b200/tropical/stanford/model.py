@@ -54,15 +54,14 @@ class Net(nn.Module):
         nat = self.native()
         H = self.num_hidden
         if group == 1:
-            rows, out = nat.outputs(x), None
+            rows, out = nat.forward(x, rows=gather)   # both return values from one fused pass (no torch layer)
+            if not gather:
+                return out
         elif group == 8:  # "infer within a common linear space" (model.py:65-70): the corners of an edge's box
             rows, out = nat.outputs_group8(x)
         else:
             raise _native.NativeError("Net.forward: group must be 1 or 8 on the device (the path uses 8: subpoly.py:125)")
         inputs = [rows[:, i * H:(i + 1) * H] for i in range(self.num_layers - 1)] + [rows[:, -1:]]
-        if out is None:
-            # the last linear layer on the last hidden activation gives the 2-vector output
-            out = F.linear(F.relu(inputs[-2]), self.fc[-1].weight, self.fc[-1].bias)
         if gather:
             return out, inputs
         return out
