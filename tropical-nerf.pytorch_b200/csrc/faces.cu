@@ -25,8 +25,11 @@ struct tnb_mesh {
     tnb::DevBuf<float> vert;   // [V][3]
     tnb::DevBuf<float> out;    // [V][R]
     tnb::DevBuf<int2> edges;   // [E]
-    tnb::DevBuf<int> poly;     // [P][W] angle-sorted rows, -1 padded
+    tnb::DevBuf<int> poly;     // angle-sorted face rows, one after the other (row p = poly[pstart[p] .. + pcnt[p])); padded to
+                               // [P][W] with -1 only when somebody reads the polygons (W = 250 / 1170 for the large sphere / torus)
+    tnb::DevBuf<int> pstart;   // [P] first element of every row
     tnb::DevBuf<int> pcnt;     // [P]
+    int64_t n_elems = 0;
     tnb::DevBuf<int> tri;      // [T][3]
     tnb::DevBuf<unsigned char> tag;  // [V] slab sharding: bit0 / bit1 = on the plane shared with the lower / upper neighbour
     tnb::DevBuf<int> vidx;     // [V] number of the vertex in the complex (extract_skeleton's v_idx, subpoly.py:575)
@@ -45,7 +48,7 @@ constexpr int kMaxRow = 8192;      // hard limit of vertices per face row (sizes
 constexpr int kSmemRowStride = 16;  // rows up to this length are built in shared memory (16 KB per CTA: a dozen CTAs per SM)
 constexpr int kMaxZeros = 5;  // 2^5 regions = one per lane
 constexpr int kSortLocal = 32;  // face rows up to this length are angle-sorted in registers / local memory
-enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_RECS, F_NLONG, F_NHUGE, F_ERR_CELL, F_NLONGROWS, F_NUM = 24 };
+enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_RECS, F_NLONG, F_NHUGE, F_ERR_CELL, F_NLONGROWS, F_ELEMS, F_NUM = 24 };
 
 // ---- surface skeleton -----------------------------------------------------------------------------
 __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
@@ -374,9 +377,11 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                                                           unsigned long long *__restrict__ scratch,
                                                           int *__restrict__ rows_per_vertex,
                                                           const int *__restrict__ row_off, int *__restrict__ rows,
-                                                          int *__restrict__ row_cnt, int W, int *__restrict__ counters,
+                                                          int *__restrict__ row_cnt, int *__restrict__ counters,
                                                           int cell_lo, int cell_hi, const int *__restrict__ list, int n_list,
-                                                          unsigned char *__restrict__ is_long, int *__restrict__ long_list)
+                                                          unsigned char *__restrict__ is_long, int *__restrict__ long_list,
+                                                          int *__restrict__ elems_per_vertex, const int *__restrict__ elem_off,
+                                                          int *__restrict__ row_start)
 {
     // Two passes share this kernel.  The FAST pass (list == nullptr) takes every vertex, builds rows of up to
     // `stride` (= kSmemRowStride) keys per lane in shared memory -- small enough for a dozen CTAs per SM: the
@@ -468,6 +473,7 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                     else if (mode == 0) {
                         is_long[a] = 1;
                         rows_per_vertex[a] = 0;
+                        elems_per_vertex[a] = 0;
                         long_list[atomicAdd(counters + F_NLONG, 1)] = (int)a;
                     }
                 }
@@ -488,20 +494,28 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
             }
         const unsigned keep_mask = __ballot_sync(0xffffffffu, keep) & gmask;
         if (mode == 0) {
-            if (sub == 0 && active) rows_per_vertex[a] = (int)(keep_mask >> g0);
-            int wmax = keep ? cnt : 0;
+            int wmax = keep ? cnt : 0, wsum = wmax;
 #pragma unroll
-            for (int d = LPV / 2; d > 0; d >>= 1) wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
+            for (int d = LPV / 2; d > 0; d >>= 1) {
+                wmax = max(wmax, __shfl_xor_sync(0xffffffffu, wmax, d));
+                wsum += __shfl_xor_sync(0xffffffffu, wsum, d);
+            }
+            if (sub == 0 && active) {
+                rows_per_vertex[a] = (int)(keep_mask >> g0);
+                elems_per_vertex[a] = wsum;   // the rows are stored one after the other: no padding to the longest row
+            }
             if (sub == 0 && wmax) atomicMax(counters + F_WIDTH, wmax);
             if (keep && cnt > kSortLocal) atomicAdd(counters + F_LONG_TOTAL, cnt);  // sizes k_sort_rows' key scratch
         } else if (keep) {
-            int rank = 0;  // lexicographic rank among the rows this vertex leads
+            int rank = 0, before = 0;  // lexicographic rank among the rows this vertex leads, and their elements
             for (unsigned mset = keep_mask & ~(1u << lane); mset; mset &= mset - 1) {
                 const int o = __ffs(mset) - 1;
-                if (row_compare(base + (size_t)o * stride, wcnt[o], mine, cnt) < 0) ++rank;
+                if (row_compare(base + (size_t)o * stride, wcnt[o], mine, cnt) < 0) { ++rank; before += wcnt[o]; }
             }
             const int64_t r = (int64_t)row_off[a] + rank;
-            for (int j = 0; j < W; ++j) rows[r * W + j] = j < cnt ? (int)(uint32_t)mine[j] : -1;
+            const int64_t first = (int64_t)elem_off[a] + before;
+            for (int j = 0; j < cnt; ++j) rows[first + j] = (int)(uint32_t)mine[j];
+            row_start[r] = (int)first;
             row_cnt[r] = cnt;
         }
         __syncwarp();
@@ -535,7 +549,7 @@ __device__ __forceinline__ float angle_score(const float a[3], const float ua[3]
 }
 
 template <class C>
-__global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ NetMeta n, int64_t P, int W,
+__global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ NetMeta n, int64_t P, const int *__restrict__ row_start,
                                                         const float *__restrict__ vert, int *__restrict__ rows,
                                                         const int *__restrict__ row_cnt,
                                                         unsigned long long *__restrict__ key_scratch,
@@ -547,7 +561,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ 
             long_rows[atomicAdd(counters + F_NLONGROWS, 1)] = (int)p;
             continue;
         }
-        int *row = rows + p * W;
+        int *row = rows + row_start[p];
         float sx = 0.0f, sy = 0.0f, sz = 0.0f;
         bool origin = false;
         for (int j = 0; j < cnt; ++j) {
@@ -611,7 +625,8 @@ __global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ 
 constexpr int kLongRowSmem = 1024;
 constexpr int kLongRowWarps = 2;
 template <class C>
-__global__ void __launch_bounds__(kLongRowWarps * 32) k_sort_rows_long(const __grid_constant__ NetMeta n, int W, const float *__restrict__ vert,
+__global__ void __launch_bounds__(kLongRowWarps * 32) k_sort_rows_long(const __grid_constant__ NetMeta n, const int *__restrict__ row_start,
+                                                                       const float *__restrict__ vert,
                                                                        int *__restrict__ rows, const int *__restrict__ row_cnt,
                                                                        const int *__restrict__ long_rows,
                                                                        unsigned long long *__restrict__ key_scratch, int *__restrict__ counters)
@@ -625,7 +640,7 @@ __global__ void __launch_bounds__(kLongRowWarps * 32) k_sort_rows_long(const __g
     for (int li = blockIdx.x * kLongRowWarps + warp; li < n_long; li += gridDim.x * kLongRowWarps) {
         const int64_t p = long_rows[li];
         const int cnt = row_cnt[p];
-        int *row = rows + p * W;
+        int *row = rows + row_start[p];
         if (cnt > kLongRowSmem) {  // longer than the shared buffers: one lane, keys in the HBM scratch (as k_sort_rows did)
             if (lane == 0) {
                 float sx = 0.0f, sy = 0.0f, sz = 0.0f;
@@ -808,7 +823,8 @@ __global__ void __launch_bounds__(1024) k_fan_base(const int *__restrict__ col_t
     if (threadIdx.x == 0) *total = s_carry;
 }
 
-__global__ void __launch_bounds__(kFanThreads) k_fan_write(const int *__restrict__ rows, const int *__restrict__ row_cnt,
+__global__ void __launch_bounds__(kFanThreads) k_fan_write(const int *__restrict__ rows, const int *__restrict__ row_start,
+                                                           const int *__restrict__ row_cnt,
                                                            int64_t P, int W, const int *__restrict__ off, const int *__restrict__ base,
                                                            int *__restrict__ tri)
 {
@@ -832,7 +848,7 @@ __global__ void __launch_bounds__(kFanThreads) k_fan_write(const int *__restrict
         if (lane == 0) atomicMax(&s_max, mx);
         __syncthreads();
         const int tile_max = s_max;
-        const int *row = rows + p * W;
+        const int *row = rows + (p < end ? row_start[p] : 0);
         for (int i = 0; i + 3 <= tile_max; ++i) {
             const bool pred = c >= i + 3;
             const unsigned ball = __ballot_sync(0xffffffffu, pred);
@@ -967,7 +983,7 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     // ---- extract_faces ----
     DevBuf<uint64_t> sig;
     DevBuf<tnb_bucket_rec> next;
-    DevBuf<int> rows_per_vertex, row_off;
+    DevBuf<int> rows_per_vertex, row_off, elems_per_vertex, elem_off;
     DevBuf<unsigned long long> head;   // read as int2 {records, first record} per cell (cells.cuh)
     DevBuf<int2> cslot;
     TNB_CUDA(sig.reserve((size_t)Vs * 3));
@@ -975,6 +991,8 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     TNB_CUDA(cslot.reserve((size_t)Vs * 8));
     TNB_CUDA(rows_per_vertex.reserve((size_t)Vs));
     TNB_CUDA(row_off.reserve((size_t)Vs));
+    TNB_CUDA(elems_per_vertex.reserve((size_t)Vs));
+    TNB_CUDA(elem_off.reserve((size_t)Vs));
     const int dim = nm.n_marks + 2;
     const int64_t n_cells = (int64_t)dim * dim * dim;
     TNB_CUDA(head.reserve((size_t)n_cells));
@@ -1011,12 +1029,12 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     prof_begin(TNB_PROF_FACE_ROWS, s);
     // four vertices per warp for those with up to three zero columns (nearly all), a warp each for the others
     k_region_rows<8><<<gw8, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
-                                                      rows_per_vertex.p, nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi,
-                                                      nullptr, 0, is_long.p, long_list.p);
+                                                      rows_per_vertex.p, nullptr, nullptr, nullptr, counters.p, cell_lo, cell_hi,
+                                                      nullptr, 0, is_long.p, long_list.p, elems_per_vertex.p, nullptr, nullptr);
     TNB_LAUNCH_CHECK();
     k_region_rows<32><<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
-                                                       rows_per_vertex.p, nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi,
-                                                       nullptr, 0, is_long.p, long_list.p);
+                                                       rows_per_vertex.p, nullptr, nullptr, nullptr, counters.p, cell_lo, cell_hi,
+                                                       nullptr, 0, is_long.p, long_list.p, elems_per_vertex.p, nullptr, nullptr);
     TNB_LAUNCH_CHECK();
     prof_end(TNB_PROF_FACE_ROWS, s, Vs, Vs * 28);
     if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
@@ -1035,11 +1053,13 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         TNB_CUDA(scratch.reserve((size_t)gl * kThreads * stride));
         prof_begin(TNB_PROF_FACE_ROWS, s);
         k_region_rows<32><<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, stride, scratch.p, rows_per_vertex.p,
-                                                  nullptr, nullptr, nullptr, 0, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr);
+                                                  nullptr, nullptr, nullptr, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr,
+                                                  elems_per_vertex.p, nullptr, nullptr);
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_FACE_ROWS, s, n_long, (int64_t)n_long * 28);
     }
     if ((rc = compact(Vs, PopcCount{rows_per_vertex.p}, OffsetEmit{row_off.p}, block_sums.p, counters.p + F_ROWS, s))) return rc;
+    if ((rc = compact(Vs, ArrayCount{elems_per_vertex.p}, OffsetEmit{elem_off.p}, block_sums.p, counters.p + F_ELEMS, s))) return rc;
     if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
     if (h[F_ERR_ROW]) { set_error("face rows: a row outgrew the scratch sized for it"); return TNB_ERR_CAPACITY; }
     const int64_t P = h[F_ROWS];
@@ -1047,20 +1067,23 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     m->P = P;
     m->W = W;
     if (P == 0) return TNB_OK;
-    TNB_CUDA(m->poly.reserve((size_t)P * W));
+    m->n_elems = h[F_ELEMS];
+    TNB_CUDA(m->poly.reserve((size_t)std::max<int64_t>(m->n_elems, 1)));
+    TNB_CUDA(m->pstart.reserve((size_t)P));
     TNB_CUDA(m->pcnt.reserve((size_t)P));
     prof_begin(TNB_PROF_FACE_ROWS, s);
     k_region_rows<8><<<gw8, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
-                                                      rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi,
-                                                      nullptr, 0, is_long.p, nullptr);
+                                                      rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, counters.p, cell_lo, cell_hi,
+                                                      nullptr, 0, is_long.p, nullptr, nullptr, elem_off.p, m->pstart.p);
     TNB_LAUNCH_CHECK();
     k_region_rows<32><<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
-                                                       rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi,
-                                                       nullptr, 0, is_long.p, nullptr);
+                                                       rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, counters.p, cell_lo, cell_hi,
+                                                       nullptr, 0, is_long.p, nullptr, nullptr, elem_off.p, m->pstart.p);
     TNB_LAUNCH_CHECK();
     if (n_long > 0) {
         k_region_rows<32><<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, stride, scratch.p, rows_per_vertex.p,
-                                                  row_off.p, m->poly.p, m->pcnt.p, W, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr);
+                                                  row_off.p, m->poly.p, m->pcnt.p, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr,
+                                                  nullptr, elem_off.p, m->pstart.p);
         TNB_LAUNCH_CHECK();
     }
     prof_end(TNB_PROF_FACE_ROWS, s, 0, 0);
@@ -1070,13 +1093,13 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         if (W > kSortLocal) TNB_CUDA(score_scratch.reserve((size_t)std::max(h[F_LONG_TOTAL], 1)));
         DevBuf<int> long_rows;
         TNB_CUDA(long_rows.reserve((size_t)std::max(h[F_LONG_TOTAL] / (kSortLocal + 1) + 1, 1)));  // every long row counted more than kSortLocal keys
-        if (net->fixed_cfg) k_sort_rows<CfgRef><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p, long_rows.p);
-        else k_sort_rows<CfgAny><<<g, kThreads, 0, s>>>(nm, P, W, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p, long_rows.p);
+        if (net->fixed_cfg) k_sort_rows<CfgRef><<<g, kThreads, 0, s>>>(nm, P, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p, long_rows.p);
+        else k_sort_rows<CfgAny><<<g, kThreads, 0, s>>>(nm, P, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p, long_rows.p);
         TNB_LAUNCH_CHECK();
         if (W > kSortLocal) {
             const unsigned gl2 = (unsigned)std::min<int64_t>(h[F_LONG_TOTAL] / (kSortLocal + 1) / kLongRowWarps + 1, kSMs * 8);
-            if (net->fixed_cfg) k_sort_rows_long<CfgRef><<<gl2, kLongRowWarps * 32, 0, s>>>(nm, W, m->vert.p, m->poly.p, m->pcnt.p, long_rows.p, score_scratch.p, counters.p);
-            else k_sort_rows_long<CfgAny><<<gl2, kLongRowWarps * 32, 0, s>>>(nm, W, m->vert.p, m->poly.p, m->pcnt.p, long_rows.p, score_scratch.p, counters.p);
+            if (net->fixed_cfg) k_sort_rows_long<CfgRef><<<gl2, kLongRowWarps * 32, 0, s>>>(nm, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, long_rows.p, score_scratch.p, counters.p);
+            else k_sort_rows_long<CfgAny><<<gl2, kLongRowWarps * 32, 0, s>>>(nm, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, long_rows.p, score_scratch.p, counters.p);
             TNB_LAUNCH_CHECK();
         }
     }
@@ -1104,7 +1127,7 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         m->T = T;
         TNB_CUDA(m->tri.reserve((size_t)std::max<int64_t>(T, 1) * 3));
         if (T > 0) {
-            k_fan_write<<<fblocks, kFanThreads, W * sizeof(int), s>>>(m->poly.p, m->pcnt.p, P, W, off.p, base.p, m->tri.p);
+            k_fan_write<<<fblocks, kFanThreads, W * sizeof(int), s>>>(m->poly.p, m->pstart.p, m->pcnt.p, P, W, off.p, base.p, m->tri.p);
             TNB_LAUNCH_CHECK();
         }
     }
@@ -1121,6 +1144,16 @@ static void extract_release_scratch(tnb_mesh *m)
 __global__ void k_i32_to_i64(const int *__restrict__ src, int64_t n, int64_t *__restrict__ dst)
 {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+// the polygon rows as the reference's padded [P][W] tensor (-1 where blank), int64
+__global__ void k_rows_padded(const int *__restrict__ rows, const int *__restrict__ row_start, const int *__restrict__ row_cnt, int64_t P, int W,
+                              int64_t *__restrict__ dst)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < P * W; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t p = i / W;
+        const int j = (int)(i - p * W);
+        dst[i] = j < row_cnt[p] ? rows[row_start[p] + j] : -1;
+    }
 }
 __global__ void k_tri_positions(const int *__restrict__ tri, int64_t T, const float *__restrict__ vert, float *__restrict__ faces)
 {
@@ -1217,7 +1250,7 @@ int tnb_mesh_read(const tnb_mesh *m, float *d_vertices, int64_t *d_edges, int64_
         TNB_LAUNCH_CHECK();
     }
     if (d_polygons && m->P) {
-        k_i32_to_i64<<<grid_for(m->P * m->W, 256), 256, 0, s>>>(m->poly.p, m->P * m->W, d_polygons);
+        k_rows_padded<<<grid_for(m->P * m->W, 256), 256, 0, s>>>(m->poly.p, m->pstart.p, m->pcnt.p, m->P, (int)m->W, d_polygons);
         TNB_LAUNCH_CHECK();
     }
     return TNB_OK;
@@ -1245,7 +1278,7 @@ int tnb_mesh_read_host(const tnb_mesh *m, float *h_vertices, int64_t *h_triangle
     }
     if (h_polygons && m->P) {
         TNB_CUDA(p64.reserve((size_t)m->P * m->W));
-        k_i32_to_i64<<<grid_for(m->P * m->W, 256), 256>>>(m->poly.p, m->P * m->W, p64.p);
+        k_rows_padded<<<grid_for(m->P * m->W, 256), 256>>>(m->poly.p, m->pstart.p, m->pcnt.p, m->P, (int)m->W, p64.p);
         TNB_LAUNCH_CHECK();
         TNB_CUDA(cudaMemcpy(h_polygons, p64.p, (size_t)m->P * m->W * sizeof(int64_t), cudaMemcpyDeviceToHost));
     }
