@@ -48,7 +48,7 @@ constexpr int kMaxRow = 8192;      // hard limit of vertices per face row (sizes
 constexpr int kSmemRowStride = 16;  // rows up to this length are built in shared memory (16 KB per CTA: a dozen CTAs per SM)
 constexpr int kMaxZeros = 5;  // 2^5 regions = one per lane
 constexpr int kSortLocal = 32;  // face rows up to this length are angle-sorted in registers / local memory
-enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_RECS, F_NLONG, F_NHUGE, F_ERR_CELL, F_NLONGROWS, F_ELEMS, F_NUM = 24 };
+enum { F_SURF = 0, F_EDGES, F_VERTS, F_ROWS, F_WIDTH, F_ERR_ZEROS, F_ERR_ROW, F_ERR_ORIGIN, F_MAXCNT, F_NEAR, F_LONG_TOTAL, F_LONG_CURSOR, F_RECS, F_NLONG, F_NHUGE, F_ERR_CELL, F_NLONGROWS, F_ELEMS, F_NWIDE, F_NUM = 24 };
 
 // ---- surface skeleton -----------------------------------------------------------------------------
 __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
@@ -381,7 +381,7 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                                                           int cell_lo, int cell_hi, const int *__restrict__ list, int n_list,
                                                           unsigned char *__restrict__ is_long, int *__restrict__ long_list,
                                                           int *__restrict__ elems_per_vertex, const int *__restrict__ elem_off,
-                                                          int *__restrict__ row_start)
+                                                          int *__restrict__ row_start, int *__restrict__ wide_list, const int *__restrict__ n_list_dev)
 {
     // Two passes share this kernel.  The FAST pass (list == nullptr) takes every vertex, builds rows of up to
     // `stride` (= kSmemRowStride) keys per lane in shared memory -- small enough for a dozen CTAs per SM: the
@@ -399,19 +399,25 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                                        : s_rows + (size_t)warp * 32 * stride;
     unsigned long long *mine = base + (size_t)lane * stride;
     int *wcnt = s_cnt + warp * 32;
-    const int64_t n_items = list ? n_list : V;
+    // three kinds of launch: every vertex (list == nullptr; the packed one files the vertices with more than three zero
+    // columns in wide_list), the wide list (LPV = 32, rows still in shared memory), the long list (rows in the HBM scratch)
+    const bool long_pass = scratch != nullptr;
+    const int64_t n_items = list ? (n_list_dev ? *n_list_dev : n_list) : V;
     const int64_t per_pass = (int64_t)gridDim.x * (kThreads / 32) * GPW;
     for (int64_t item0 = ((int64_t)blockIdx.x * (kThreads / 32) + warp) * GPW; item0 < n_items; item0 += per_pass) {  // warp uniform
         const int64_t item = item0 + lane / LPV;
         bool active = item < n_items;
         const int64_t a = active ? (list ? list[item] : item) : 0;
-        if (active && !list && mode == 1 && is_long[a]) active = false;  // the long pass writes this vertex's rows
+        if (active && !long_pass && mode == 1 && is_long[a]) active = false;  // the long pass writes this vertex's rows
         const uint64_t pa = sig[3 * a], na = sig[3 * a + 1], ga = sig[3 * a + 2];
         const uint64_t za = ~(pa | na) & colmask;
         const int gz = 3 - grid_mask(ga, 0) - grid_mask(ga, 1) - grid_mask(ga, 2);
         const int ka = __popcll(za) + gz;
         // which launch takes this vertex: the packed one those with up to 3 zero columns, the wide one the others
-        if (!list && (LPV == 8 ? ka > 3 : ka <= 3)) active = false;
+        if (LPV == 8 && active && ka > 3) {
+            if (mode == 0 && sub == 0 && wide_list) wide_list[atomicAdd(counters + F_NWIDE, 1)] = (int)a;
+            active = false;
+        }
         int cnt = 0;
         bool lead = false;
         const unsigned todo = !active ? 0u : (mode == 1 ? (unsigned)rows_per_vertex[a] : 0xffffffffu);
@@ -469,7 +475,7 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
             if (over) atomicMax(counters + F_MAXCNT, cnt);
             if (__ballot_sync(0xffffffffu, over) & gmask) {
                 if (sub == 0 && active) {
-                    if (list) atomicOr(counters + F_ERR_ROW, 1);  // the long pass is sized to the longest row: cannot happen
+                    if (long_pass) atomicOr(counters + F_ERR_ROW, 1);  // the long pass is sized to the longest row: cannot happen
                     else if (mode == 0) {
                         is_long[a] = 1;
                         rows_per_vertex[a] = 0;
@@ -1017,24 +1023,27 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         k_cell_sort_huge<<<kSMs, 256, kCellSortHuge * sizeof(unsigned long long), s>>>(huge_list.p, counters.p, (const int2 *)head.p, next.p, sorted.p, sig.p, colmask);
         TNB_LAUNCH_CHECK();
     }
-    const unsigned gw = grid_for(Vs, kThreads / 32), gw8 = grid_for(Vs, kThreads / 8);
+    const unsigned gw8 = grid_for(Vs, kThreads / 8);
     const size_t rows_smem = (size_t)kThreads * kSmemRowStride * sizeof(unsigned long long);
     DevBuf<unsigned long long> scratch;
     DevBuf<unsigned char> is_long;
-    DevBuf<int> long_list;
+    DevBuf<int> long_list, wide_list;
     TNB_CUDA(is_long.reserve((size_t)Vs));
     TNB_CUDA(long_list.reserve((size_t)Vs));
+    TNB_CUDA(wide_list.reserve((size_t)Vs));
+    const unsigned gwide = kSMs * 4;  // the wide list is short (its length stays on the device): a fixed grid strides over it
     TNB_CUDA(cudaMemsetAsync(is_long.p, 0, (size_t)Vs, s));
     // fast pass: every vertex, rows in shared memory
     prof_begin(TNB_PROF_FACE_ROWS, s);
     // four vertices per warp for those with up to three zero columns (nearly all), a warp each for the others
     k_region_rows<8><<<gw8, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
                                                       rows_per_vertex.p, nullptr, nullptr, nullptr, counters.p, cell_lo, cell_hi,
-                                                      nullptr, 0, is_long.p, long_list.p, elems_per_vertex.p, nullptr, nullptr);
+                                                      nullptr, 0, is_long.p, long_list.p, elems_per_vertex.p, nullptr, nullptr, wide_list.p, nullptr);
     TNB_LAUNCH_CHECK();
-    k_region_rows<32><<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
-                                                       rows_per_vertex.p, nullptr, nullptr, nullptr, counters.p, cell_lo, cell_hi,
-                                                       nullptr, 0, is_long.p, long_list.p, elems_per_vertex.p, nullptr, nullptr);
+    k_region_rows<32><<<gwide, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
+                                                          rows_per_vertex.p, nullptr, nullptr, nullptr, counters.p, cell_lo, cell_hi,
+                                                          wide_list.p, 0, is_long.p, long_list.p, elems_per_vertex.p, nullptr, nullptr, nullptr,
+                                                          counters.p + F_NWIDE);
     TNB_LAUNCH_CHECK();
     prof_end(TNB_PROF_FACE_ROWS, s, Vs, Vs * 28);
     if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
@@ -1054,7 +1063,7 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         prof_begin(TNB_PROF_FACE_ROWS, s);
         k_region_rows<32><<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, stride, scratch.p, rows_per_vertex.p,
                                                   nullptr, nullptr, nullptr, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr,
-                                                  elems_per_vertex.p, nullptr, nullptr);
+                                                  elems_per_vertex.p, nullptr, nullptr, nullptr, nullptr);
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_FACE_ROWS, s, n_long, (int64_t)n_long * 28);
     }
@@ -1074,16 +1083,17 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     prof_begin(TNB_PROF_FACE_ROWS, s);
     k_region_rows<8><<<gw8, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
                                                       rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, counters.p, cell_lo, cell_hi,
-                                                      nullptr, 0, is_long.p, nullptr, nullptr, elem_off.p, m->pstart.p);
+                                                      nullptr, 0, is_long.p, nullptr, nullptr, elem_off.p, m->pstart.p, nullptr, nullptr);
     TNB_LAUNCH_CHECK();
-    k_region_rows<32><<<gw, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
-                                                       rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, counters.p, cell_lo, cell_hi,
-                                                       nullptr, 0, is_long.p, nullptr, nullptr, elem_off.p, m->pstart.p);
+    k_region_rows<32><<<gwide, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
+                                                          rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, counters.p, cell_lo, cell_hi,
+                                                          wide_list.p, 0, is_long.p, nullptr, nullptr, elem_off.p, m->pstart.p, nullptr,
+                                                          counters.p + F_NWIDE);
     TNB_LAUNCH_CHECK();
     if (n_long > 0) {
         k_region_rows<32><<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, stride, scratch.p, rows_per_vertex.p,
                                                   row_off.p, m->poly.p, m->pcnt.p, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr,
-                                                  nullptr, elem_off.p, m->pstart.p);
+                                                  nullptr, elem_off.p, m->pstart.p, nullptr, nullptr);
         TNB_LAUNCH_CHECK();
     }
     prof_end(TNB_PROF_FACE_ROWS, s, 0, 0);
