@@ -51,6 +51,7 @@ static __global__ void __launch_bounds__(256) k_cell_count(const int *__restrict
                                                     const uint64_t *__restrict__ sig, int2 *__restrict__ cells,
                                                     int2 *__restrict__ slots, int dim)
 {
+    pdl_wait();
     if (n_dev) n = *n_dev;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t v = cand ? cand[i] : i;
@@ -73,6 +74,7 @@ static __global__ void __launch_bounds__(256) k_cell_count(const int *__restrict
 static __global__ void __launch_bounds__(256) k_cell_alloc(const int *__restrict__ n_dev, int64_t n, int K, int2 *__restrict__ cells,
                                                     const int2 *__restrict__ slots, int *__restrict__ total)
 {
+    pdl_wait();
     if (n_dev) n = *n_dev;
     __shared__ int s_warp[8];
     __shared__ int s_base;
@@ -103,6 +105,7 @@ static __global__ void __launch_bounds__(256) k_cell_fill(const int *__restrict_
                                                    const uint64_t *__restrict__ sig, const int2 *__restrict__ cells,
                                                    const int2 *__restrict__ slots, tnb_bucket_rec *__restrict__ recs)
 {
+    pdl_wait();
     if (n_dev) n = *n_dev;
     const int64_t n8 = n * K;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n8; t += (int64_t)gridDim.x * blockDim.x) {
@@ -123,6 +126,7 @@ static __global__ void __launch_bounds__(256) k_cell_fill(const int *__restrict_
 static __global__ void __launch_bounds__(256) k_cell_clear(const int *__restrict__ n_dev, int64_t n, int K, int2 *__restrict__ cells,
                                                     const int2 *__restrict__ slots)
 {
+    pdl_wait();
     if (n_dev) n = *n_dev;
     const int64_t n8 = n * K;
     for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n8; t += (int64_t)gridDim.x * blockDim.x) {
@@ -139,19 +143,19 @@ inline int cells_build(int K, const int *cand, const int *n_dev, int64_t n, cons
 {
     if (n <= 0) return TNB_OK;
     const unsigned g1 = grid_for(n, 256), gk = grid_for(n * K, 256);
-    if (K == 8) k_cell_count<8><<<g1, 256, 0, s>>>(cand, n_dev, n, sig, cells, slots, dim);
-    else k_cell_count<1><<<g1, 256, 0, s>>>(cand, n_dev, n, sig, cells, slots, dim);
+    if (K == 8) TNB_CUDA(launch_pdl(k_cell_count<8>, dim3(g1), dim3(256), 0, s, cand, n_dev, n, sig, cells, slots, dim));
+    else TNB_CUDA(launch_pdl(k_cell_count<1>, dim3(g1), dim3(256), 0, s, cand, n_dev, n, sig, cells, slots, dim));
     TNB_LAUNCH_CHECK();
-    k_cell_alloc<<<gk, 256, 0, s>>>(n_dev, n, K, cells, slots, total);
+    TNB_CUDA(launch_pdl(k_cell_alloc, dim3(gk), dim3(256), 0, s, n_dev, n, K, cells, slots, total));
     TNB_LAUNCH_CHECK();
-    k_cell_fill<<<gk, 256, 0, s>>>(cand, n_dev, n, K, sig, cells, slots, recs);
+    TNB_CUDA(launch_pdl(k_cell_fill, dim3(gk), dim3(256), 0, s, cand, n_dev, n, K, sig, cells, slots, recs));
     TNB_LAUNCH_CHECK();
     return TNB_OK;
 }
 inline int cells_clear(int K, const int *n_dev, int64_t n, int2 *cells, const int2 *slots, cudaStream_t s)
 {
     if (n <= 0) return TNB_OK;
-    k_cell_clear<<<grid_for(n * K, 256), 256, 0, s>>>(n_dev, n, K, cells, slots);
+    TNB_CUDA(launch_pdl(k_cell_clear, dim3(grid_for(n * K, 256)), dim3(256), 0, s, n_dev, n, K, cells, slots));
     TNB_LAUNCH_CHECK();
     return TNB_OK;
 }

@@ -73,6 +73,27 @@ void prof_add(int cls, int64_t units, int64_t bytes);  // sizes that are only kn
 
 // ---- device helpers -----------------------------------------------------------------
 #ifdef __CUDACC__
+// Programmatic dependent launch: a kernel launched with launch_pdl() may be scheduled while the kernel before it
+// in the stream drains; it must call pdl_wait() before it reads anything that kernel wrote (griddepcontrol.wait
+// returns at once when the launch carried no programmatic dependency).  The device-driven step stream is 16 short
+// kernels per hyperplane: this hides their launch latency behind the predecessor's tail.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+extern bool g_pdl;   // A/B switch (TNB_NO_PDL)
+template <class... KArgs, class... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = g_pdl ? 1 : 0;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 
 __device__ __forceinline__ float det_expf(float y)
 {

@@ -263,64 +263,7 @@ __global__ void __launch_bounds__(kThreads, MINB) k_sweep_pieces(const __grid_co
     }
 }
 
-struct SkelEdgeCount {
-    const ChunkSeg *segs;
-    int n_segs, M;
-    const float *dist;
-    const unsigned *max_grad;
-    float k_len;  // (sqrt(3)*2) * max mark spacing  (tropical.py:125-126)
-    mutable int hint = 0;  // segment of the thread's previous slot: successive slots of a thread rarely change segment
-    // segment of slot t (last one with first <= t)
-    __device__ __forceinline__ int seg_of(int64_t t) const
-    {
-        int a = hint;
-        if (segs[a].first <= t && (a + 1 == n_segs || t < segs[a + 1].first)) return a;
-        a = 0;
-        int b = n_segs - 1;
-        while (a < b) {
-            int mid = (a + b + 1) >> 1;
-            if (segs[mid].first <= t) a = mid; else b = mid - 1;
-        }
-        hint = a;
-        return a;
-    }
-    // the two grid vertices of slot t; returns the chunk (32-bit index arithmetic: a segment has < 2^31 slots)
-    __device__ __forceinline__ int locate(int64_t t, int &hi, int &lo) const
-    {
-        const ChunkSeg sg = segs[seg_of(t)];
-        const unsigned r = (unsigned)(t - sg.first);
-        unsigned dims[3] = {(unsigned)sg.n[0], (unsigned)sg.n[1], (unsigned)sg.n[2]};
-        dims[sg.axis] -= 1;
-        const unsigned q = r / dims[2], k = r - q * dims[2], i = q / dims[1], j = q - i * dims[1];
-        int p[3] = {sg.s[0] + (int)i, sg.s[1] + (int)j, sg.s[2] + (int)k};
-        lo = (p[0] * M + p[1]) * M + p[2];
-        p[sg.axis] += 1;
-        hi = (p[0] * M + p[1]) * M + p[2];
-        return sg.chunk;
-    }
-    __device__ __forceinline__ int operator()(int64_t t) const
-    {
-        int hi, lo;
-        const int chunk = locate(t, hi, lo);
-        const float eps = k_len * __uint_as_float(max_grad[chunk]);
-        return (dist[hi] <= eps && dist[lo] <= eps) ? 1 : 0;
-    }
-};
-struct SkelEdgeEmit {
-    SkelEdgeCount q;
-    int2 *edges;
-    int *used;
-    __device__ __forceinline__ void operator()(int64_t t, int pos, int) const
-    {
-        int hi, lo;
-        q.locate(t, hi, lo);
-        edges[pos] = make_int2(hi, lo);  // (indices[1:], indices[:-1]) column order, tropical.py:130
-        used[hi] = 1;
-        used[lo] = 1;
-    }
-};
-
-// ---- the same selection row by row ---------------------------------------------------------------------
+// ---- edge selection, row by row -------------------------------------------------------------------------
 // A candidate edge is kept iff both its grid vertices are within the chunk's threshold of the surface
 // (tropical.py:113-138).  Per SLOT that is a decode (two divisions) and two scattered loads for 24 M slots of
 // which 7 % pass.  Per ROW (the slots of a block that differ in the last coordinate only, up to `unit` of them)
@@ -1506,6 +1449,7 @@ __global__ void __launch_bounds__(256) k_pair_count_seg(const int *__restrict__ 
                                                         int *__restrict__ pcount, int *__restrict__ pcache, int *__restrict__ long_list,
                                                         const int *__restrict__ idx_dev = nullptr)
 {
+    pdl_wait();
     if (idx_dev) {  // device-driven step stream: the hyperplane of this step is chosen on the device
         const int idx = *idx_dev;
         if (idx < 0) return;
@@ -2969,6 +2913,7 @@ struct HitCountSig {
 // split compaction over the edges (first half of the grid) and hit compaction over the vertices (second half)
 __global__ void __launch_bounds__(kScanThreads) k_sd_count(const __grid_constant__ StepArgs a)
 {
+    pdl_wait();
     const int *cnt = a.cnt;
     if (!sd_active(cnt)) return;
     const int idx = cnt[C_IDX], nb = (int)gridDim.x >> 1, pv = cnt[C_VPAR];
@@ -2980,6 +2925,7 @@ __global__ void __launch_bounds__(kScanThreads) k_sd_count(const __grid_constant
 }
 __global__ void __launch_bounds__(kScanThreads) k_sd_write(const __grid_constant__ StepArgs a)
 {
+    pdl_wait();
     int *cnt = a.cnt;
     if (!sd_active(cnt)) return;
     const int nb = (int)gridDim.x >> 1;
@@ -2989,6 +2935,7 @@ __global__ void __launch_bounds__(kScanThreads) k_sd_write(const __grid_constant
 template <class C>
 __global__ void __launch_bounds__(kThreads) k_sd_new_vertices(const __grid_constant__ NetMeta n, const __grid_constant__ StepArgs a)
 {
+    pdl_wait();
     int *cnt = a.cnt;
     if (!sd_active(cnt) || cnt[C_RAW] == 0) return;
     const int pv = cnt[C_VPAR];
@@ -2999,6 +2946,7 @@ __global__ void __launch_bounds__(kThreads) k_sd_new_vertices(const __grid_const
 // pruning pass cleared, crossing mask reset (k_sd_keep_count rebuilds it)
 __global__ void __launch_bounds__(256) k_sd_cands(const __grid_constant__ StepArgs a, const PreMeta pm)
 {
+    pdl_wait();
     int *cnt = a.cnt;
     if (!sd_crossed(cnt)) return;
     const int Hn = cnt[C_HIT], S = cnt[C_SPLIT], V = cnt[C_V], flag = cnt[C_FLAG], prune = cnt[C_PRUNE], pv = cnt[C_VPAR], pa = cnt[C_APAR];
@@ -3019,6 +2967,7 @@ __global__ void __launch_bounds__(256) k_sd_cands(const __grid_constant__ StepAr
 }
 __global__ void __launch_bounds__(256) k_sd_pair_copy(const __grid_constant__ StepArgs a)
 {
+    pdl_wait();
     const int *cnt = a.cnt;
     if (!sd_crossed(cnt) || !sd_fits(a) || cnt[C_PAIRS] == 0) return;
     int2 *edges_out = a.edges[cnt[C_EPAR]] + cnt[C_E] + cnt[C_SPLIT];
@@ -3035,6 +2984,7 @@ __global__ void __launch_bounds__(256) k_sd_pair_copy(const __grid_constant__ St
 }
 __global__ void __launch_bounds__(kSortWarps * 32) k_sd_pair_long(const __grid_constant__ StepArgs a)
 {
+    pdl_wait();
     const int *cnt = a.cnt;
     if (!sd_crossed(cnt) || !sd_fits(a) || cnt[C_LONG] == 0) return;
     pair_write_long_seg_body(a.remap, cnt[C_LONG], a.cand, a.sig[cnt[C_VPAR]], (const int2 *)a.head, a.next, a.dim, (1ull << cnt[C_IDX]) - 1ull,
@@ -3043,6 +2993,7 @@ __global__ void __launch_bounds__(kSortWarps * 32) k_sd_pair_long(const __grid_c
 __device__ __forceinline__ uint64_t sd_futmask(int idx, int R) { return ~((1ull << idx) - 1ull) & (R >= 64 ? ~0ull : ((1ull << R) - 1ull)); }
 __global__ void __launch_bounds__(kScanThreads) k_sd_keep_count(const __grid_constant__ StepArgs a)
 {
+    pdl_wait();
     int *cnt = a.cnt;
     if (!sd_crossed(cnt) || !sd_fits(a) || !cnt[C_PRUNE]) return;
     const int64_t En = (int64_t)cnt[C_E] + cnt[C_SPLIT] + cnt[C_PAIRS];
@@ -3050,12 +3001,13 @@ __global__ void __launch_bounds__(kScanThreads) k_sd_keep_count(const __grid_con
 }
 __global__ void __launch_bounds__(kScanThreads) k_sd_keep_write(const __grid_constant__ StepArgs a)
 {
+    pdl_wait();
     int *cnt = a.cnt;
     if (!sd_crossed(cnt) || !sd_fits(a) || !cnt[C_PRUNE]) return;
     const int64_t En = (int64_t)cnt[C_E] + cnt[C_SPLIT] + cnt[C_PAIRS];
     const int pe = cnt[C_EPAR];
     const int2 *edges = a.edges[pe];
-    // (four items per thread, scan_write_body4_t, measured SLOWER here: 19.3 -> 23.7 us per launch)
+    // (four consecutive items per thread and a 1024-item tile measured SLOWER here: 19.3 -> 23.7 us per launch)
     scan_write_body(En, KeepCount{edges, a.sig[cnt[C_VPAR]], sd_futmask(cnt[C_IDX], a.R)}, KeepEmit{edges, a.edges[pe ^ 1], a.used[cnt[C_APAR] ^ 1]},
                     a.block_sums, cnt + C_KEPT);
 }
@@ -3066,6 +3018,7 @@ __global__ void __launch_bounds__(kScanThreads) k_sd_keep_write(const __grid_con
 constexpr int kReportSlots = 4;
 __global__ void k_sd_finish(const __grid_constant__ StepArgs a, const __grid_constant__ StepList list, int first, int seq, volatile int *report)
 {
+    pdl_wait();
     if (threadIdx.x != 0) return;
     report += 8 * (seq & (kReportSlots - 1));
     int *cnt = a.cnt;
@@ -3182,35 +3135,37 @@ static int steps_stream_impl(const tnb_net *net, tnb_complex *c, const int32_t *
     };
     auto enqueue_sequence = [&](int seq) -> int {
         int rc;
-        k_sd_count<<<nb2, kScanThreads, 0, s>>>(sa);
+        // every kernel of the sequence is launched as a programmatic dependent of the one before it (common.cuh)
+        TNB_CUDA(launch_pdl(k_sd_count, dim3(nb2), dim3(kScanThreads), 0, s, sa));
         TNB_LAUNCH_CHECK();
-        k_sd_write<<<nb2, kScanThreads, 0, s>>>(sa);
+        TNB_CUDA(launch_pdl(k_sd_write, dim3(nb2), dim3(kScanThreads), 0, s, sa));
         TNB_LAUNCH_CHECK();
         prof_begin(TNB_PROF_NEW_VERTICES, s);
-        if (net->fixed_cfg) k_sd_new_vertices<CfgRef><<<kSMs * 8, kThreads, row_tile, s>>>(m, sa);
-        else k_sd_new_vertices<CfgAny><<<kSMs * 8, kThreads, row_tile, s>>>(m, sa);
+        if (net->fixed_cfg) TNB_CUDA(launch_pdl(k_sd_new_vertices<CfgRef>, dim3(kSMs * 8), dim3(kThreads), row_tile, s, m, sa));
+        else TNB_CUDA(launch_pdl(k_sd_new_vertices<CfgAny>, dim3(kSMs * 8), dim3(kThreads), row_tile, s, m, sa));
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_NEW_VERTICES, s, 0);
-        k_sd_cands<<<kSMs * 8, 256, 0, s>>>(sa, pm);
+        TNB_CUDA(launch_pdl(k_sd_cands, dim3(kSMs * 8), dim3(256), 0, s, sa, pm));
         TNB_LAUNCH_CHECK();
         if ((rc = cells_build(1, sa.cand, sa.cnt + C_CAND, cand_ub, sa.sig[c->vcur], (int2 *)sa.head, sa.cslot, sa.next, sa.cnt + C_RECS, sa.dim, s))) return rc;
         prof_begin(TNB_PROF_PAIRS, s);
-        k_pair_count_seg<<<kSMs * 8, 256, 0, s>>>(sa.cand, sa.cnt, sa.sig[c->vcur], (const int2 *)sa.head, sa.next, sa.dim, 0ull, sa.pcount, sa.pcache, sa.remap, sa.cnt + C_IDX);
+        TNB_CUDA(launch_pdl(k_pair_count_seg, dim3(kSMs * 8), dim3(256), 0, s, (const int *)sa.cand, sa.cnt, (const uint64_t *)sa.sig[c->vcur], (const int2 *)sa.head,
+                            (const tnb_bucket_rec *)sa.next, sa.dim, (uint64_t)0, sa.pcount, sa.pcache, sa.remap, (const int *)(sa.cnt + C_IDX)));
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_PAIRS, s, 0);
         if ((rc = compact(cand_ub, ArrayCount{sa.pcount}, OffsetEmit{sa.poff}, sa.block_sums, sa.cnt + C_PAIRS, s, sa.cnt + C_CAND))) return rc;
         prof_begin(TNB_PROF_PAIRS, s);
-        k_sd_pair_copy<<<kSMs * 16, 256, 0, s>>>(sa);
+        TNB_CUDA(launch_pdl(k_sd_pair_copy, dim3(kSMs * 16), dim3(256), 0, s, sa));
         TNB_LAUNCH_CHECK();
-        k_sd_pair_long<<<kSMs * 2, kSortWarps * 32, 0, s>>>(sa);
+        TNB_CUDA(launch_pdl(k_sd_pair_long, dim3(kSMs * 2), dim3(kSortWarps * 32), 0, s, sa));
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_PAIRS, s, 0);
         if ((rc = cells_clear(1, sa.cnt + C_CAND, cand_ub, (int2 *)sa.head, sa.cslot, s))) return rc;
-        k_sd_keep_count<<<kScanMaxBlocks, kScanThreads, 0, s>>>(sa);
+        TNB_CUDA(launch_pdl(k_sd_keep_count, dim3(kScanMaxBlocks), dim3(kScanThreads), 0, s, sa));
         TNB_LAUNCH_CHECK();
-        k_sd_keep_write<<<kScanMaxBlocks, kScanThreads, 0, s>>>(sa);
+        TNB_CUDA(launch_pdl(k_sd_keep_write, dim3(kScanMaxBlocks), dim3(kScanThreads), 0, s, sa));
         TNB_LAUNCH_CHECK();
-        k_sd_finish<<<1, 32, 0, s>>>(sa, list, 0, seq, report_dev);
+        TNB_CUDA(launch_pdl(k_sd_finish, dim3(1), dim3(32), 0, s, sa, list, 0, seq, (volatile int *)report_dev));
         TNB_LAUNCH_CHECK();
         return TNB_OK;
     };

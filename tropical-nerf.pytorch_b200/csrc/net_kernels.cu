@@ -1,6 +1,7 @@
 // net_kernels.cu -- network-level entry points of the C ABI: hash-grid encoding, fused
 // trilinear evaluation, SDF + input gradient, region indicators, dense sign sweep.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <utility>
@@ -50,6 +51,7 @@ struct ProfClass {
 };
 static bool g_prof_on = false;
 static ProfClass g_prof[TNB_PROF_CLASSES];
+bool g_pdl = std::getenv("TNB_NO_PDL") == nullptr;
 void prof_begin(int cls, cudaStream_t s)
 {
     if (!g_prof_on) return;

@@ -132,64 +132,6 @@ __device__ __forceinline__ void scan_write_body_t(int64_t n, Count count, Emit e
     __syncthreads();
 }
 
-// The write pass with FOUR consecutive items per thread (a tile is 4 NT items): for dense selections over millions
-// of items (the pruning pass keeps most of 2 M edges) the three CTA barriers per 256-item tile were most of its time.
-template <int NT, class Count, class Emit>
-__device__ __forceinline__ void scan_write_body4_t(int64_t n, Count count, Emit emit, const int *block_sums, int *total)
-{
-    constexpr int NW = NT / 32;
-    __shared__ int s_warp[NW];
-    __shared__ int s_excl[32];
-    __shared__ int s_base, s_tile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    {
-        int acc = 0;
-        const int upto = (blockIdx.x == 0) ? (int)gridDim.x : (int)blockIdx.x;
-        for (int b = threadIdx.x; b < upto; b += NT) acc += block_sums[b];
-        acc = warp_sum(acc);
-        if (lane == 0) s_warp[warp] = acc;
-        __syncthreads();
-        if (threadIdx.x < 32) {
-            int t = lane < NW ? s_warp[lane] : 0;
-            t = warp_sum(t);
-            if (threadIdx.x == 0) {
-                if (blockIdx.x == 0) { if (total) *total = t; s_base = 0; }
-                else s_base = t;
-            }
-        }
-        __syncthreads();
-    }
-    int64_t begin, end;
-    scan_slice(n, begin, end);
-    int running = s_base;
-    for (int64_t tile = begin; tile < end; tile += 4 * NT) {
-        const int64_t i0 = tile + 4 * (int64_t)threadIdx.x;
-        int c[4], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            c[k] = (i0 + k < end) ? count(i0 + k) : 0;
-            sum += c[k];
-        }
-        const int incl = warp_inclusive_scan(sum);
-        __syncthreads();  // s_warp / s_excl reuse
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            const int t = lane < NW ? s_warp[lane] : 0;
-            const int ti = warp_inclusive_scan(t);
-            s_excl[lane] = ti - t;
-            if (lane == 31) s_tile = ti;
-        }
-        __syncthreads();
-        int pos = running + s_excl[warp] + incl - sum;
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-            if (c[k]) { emit(i0 + k, pos, c[k]); pos += c[k]; }
-        running += s_tile;
-    }
-    __syncthreads();
-}
-
 // Pieces for kernels that keep going after a compaction: every CTA derives its own base offset
 // AND the grand total from the block sums (no second pass over a published total), and the write
 // pass returns where the CTA's items went, so that the CTA can process exactly what it emitted.
@@ -321,6 +263,7 @@ template <class Count>
 __global__ void __launch_bounds__(kScanThreads) k_scan_count(int64_t n, const int *__restrict__ n_dev, Count count,
                                                              int *__restrict__ block_sums)
 {
+    pdl_wait();
     if (n_dev) n = *n_dev;
     scan_count_body(n, count, block_sums);
 }
@@ -435,6 +378,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_write(int64_t n, const in
                                                              Emit emit, const int *__restrict__ block_sums,
                                                              int *__restrict__ total)
 {
+    pdl_wait();
     if (n_dev) n = *n_dev;
     scan_write_body(n, count, emit, block_sums, total);
 }
@@ -451,9 +395,9 @@ inline int compact(int64_t n, Count count, Emit emit, int *block_sums, int *d_to
     }
     int64_t blocks = (n + kScanThreads - 1) / kScanThreads;
     if (blocks > kScanMaxBlocks) blocks = kScanMaxBlocks;
-    k_scan_count<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, n_dev, count, block_sums);
+    TNB_CUDA(launch_pdl(k_scan_count<Count>, dim3((unsigned)blocks), dim3(kScanThreads), 0, s, n, n_dev, count, block_sums));
     TNB_LAUNCH_CHECK();
-    k_scan_write<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, n_dev, count, emit, block_sums, d_total);
+    TNB_CUDA(launch_pdl(k_scan_write<Count, Emit>, dim3((unsigned)blocks), dim3(kScanThreads), 0, s, n, n_dev, count, emit, (const int *)block_sums, d_total));
     TNB_LAUNCH_CHECK();
     return TNB_OK;
 }
