@@ -55,6 +55,7 @@ __global__ void k_surface_flags(const __grid_constant__ NetMeta n, const float *
                                 const float *__restrict__ out, const int *__restrict__ alive, int64_t V, float eps,
                                 int *__restrict__ surf, int *__restrict__ counters)
 {
+    pdl_wait();
     int local = 0;
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
         float x[3] = {vert[3 * v], vert[3 * v + 1], vert[3 * v + 2]}, xp[3];
@@ -79,6 +80,7 @@ __global__ void k_count_near_plane(const uint64_t *__restrict__ sig, const unsig
                                    const int *__restrict__ alive, int64_t V, int plane_lo, int plane_hi,
                                    int *__restrict__ counters)
 {
+    pdl_wait();
     int local = 0;
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
         if (!alive[v]) continue;
@@ -129,6 +131,7 @@ struct SurfVertEmit {  // new number of every surface vertex; its rows follow in
 __global__ void __launch_bounds__(256) k_gather_rows(int64_t Vs, int R, const int *__restrict__ vidx, const float *__restrict__ vert,
                                                      const float *__restrict__ out, float *__restrict__ nvert, float *__restrict__ nout)
 {
+    pdl_wait();
     const int64_t stride = (int64_t)gridDim.x * blockDim.x, t0 = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     const int64_t total = Vs * R;
     for (int64_t i = t0; i < total; i += stride) {
@@ -142,6 +145,7 @@ __global__ void __launch_bounds__(256) k_gather_rows(int64_t Vs, int R, const in
 }
 __global__ void k_remap_edges2(int2 *__restrict__ edges, int64_t E, const int *__restrict__ remap)
 {
+    pdl_wait();
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
         int2 ed = edges[e];
         edges[e] = make_int2(remap[ed.x], remap[ed.y]);
@@ -152,6 +156,7 @@ __global__ void k_remap_edges2(int2 *__restrict__ edges, int64_t E, const int *_
 __global__ void k_surface_sig(const __grid_constant__ NetMeta n, const float *__restrict__ vert,
                               const float *__restrict__ out, int64_t V, float eps, uint64_t *__restrict__ sig)
 {
+    pdl_wait();
     for (int64_t v = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; v < V; v += (int64_t)gridDim.x * blockDim.x) {
         float x[3] = {vert[3 * v], vert[3 * v + 1], vert[3 * v + 2]}, xp[3];
         preprocess(n, x, xp);
@@ -211,6 +216,7 @@ __global__ void __launch_bounds__(kThreads) k_cell_sort(int64_t n_slots, const i
                                                         const uint64_t *__restrict__ sig, uint64_t colmask, int *__restrict__ huge_list,
                                                         int *__restrict__ counters)
 {
+    pdl_wait();
     __shared__ unsigned long long s_keys[kThreads / 32][kCellSortSmem];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     unsigned long long *keys = s_keys[warp];
@@ -314,6 +320,7 @@ __global__ void __launch_bounds__(256) k_cell_sort_huge(const int *__restrict__ 
                                                         const int2 *__restrict__ cells, const tnb_bucket_rec *__restrict__ recs,
                                                         tnb_bucket_rec *__restrict__ sorted, const uint64_t *__restrict__ sig, uint64_t colmask)
 {
+    pdl_wait();
     extern __shared__ unsigned long long s_huge[];  // [kCellSortHuge]
     const int n_huge = counters[F_NHUGE];
     for (int h = blockIdx.x; h < n_huge; h += gridDim.x) {
@@ -383,6 +390,7 @@ __global__ void __launch_bounds__(kThreads) k_region_rows(int64_t V, const uint6
                                                           int *__restrict__ elems_per_vertex, const int *__restrict__ elem_off,
                                                           int *__restrict__ row_start, int *__restrict__ wide_list, const int *__restrict__ n_list_dev)
 {
+    pdl_wait();
     // Two passes share this kernel.  The FAST pass (list == nullptr) takes every vertex, builds rows of up to
     // `stride` (= kSmemRowStride) keys per lane in shared memory -- small enough for a dozen CTAs per SM: the
     // kernel is a chain of dependent L2 round trips per vertex, so what it needs is warps in flight -- and files
@@ -561,6 +569,7 @@ __global__ void __launch_bounds__(kThreads) k_sort_rows(const __grid_constant__ 
                                                         unsigned long long *__restrict__ key_scratch,
                                                         int *__restrict__ counters, int *__restrict__ long_rows)
 {
+    pdl_wait();
     for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < P; p += (int64_t)gridDim.x * blockDim.x) {
         const int cnt = row_cnt[p];
         if (cnt > kSortLocal && long_rows) {  // a warp's job (k_sort_rows_long): one thread sorting hundreds of keys held the whole launch up
@@ -637,6 +646,7 @@ __global__ void __launch_bounds__(kLongRowWarps * 32) k_sort_rows_long(const __g
                                                                        const int *__restrict__ long_rows,
                                                                        unsigned long long *__restrict__ key_scratch, int *__restrict__ counters)
 {
+    pdl_wait();
     __shared__ float s_pos[kLongRowWarps][3][kLongRowSmem];
     __shared__ unsigned long long s_keys[kLongRowWarps][kLongRowSmem];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -759,6 +769,7 @@ __device__ __forceinline__ void fan_slice(int64_t P, int64_t &begin, int64_t &en
 __global__ void __launch_bounds__(kFanThreads) k_fan_hist(const int *__restrict__ row_cnt, int64_t P, int W,
                                                           int *__restrict__ G)
 {
+    pdl_wait();
     extern __shared__ int s_hist[];  // [W+1]
     for (int c = threadIdx.x; c <= W; c += kFanThreads) s_hist[c] = 0;
     __syncthreads();
@@ -779,6 +790,7 @@ __global__ void __launch_bounds__(kFanThreads) k_fan_hist(const int *__restrict_
 __global__ void __launch_bounds__(kFanThreads) k_fan_cols(const int *__restrict__ G, int blocks, int W, int *__restrict__ off,
                                                           int *__restrict__ col_total)
 {
+    pdl_wait();
     __shared__ int s_w[kFanThreads / 32];
     const int i = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int per = (blocks + kFanThreads - 1) / kFanThreads, b0 = threadIdx.x * per, b1 = min(b0 + per, blocks);
@@ -804,6 +816,7 @@ __global__ void __launch_bounds__(kFanThreads) k_fan_cols(const int *__restrict_
 // base[i] = triangles of the fan steps before i; total triangle count -> *total
 __global__ void __launch_bounds__(1024) k_fan_base(const int *__restrict__ col_total, int n, int *__restrict__ base, int *__restrict__ total)
 {
+    pdl_wait();
     __shared__ int s_w[32];
     __shared__ int s_carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -834,6 +847,7 @@ __global__ void __launch_bounds__(kFanThreads) k_fan_write(const int *__restrict
                                                            int64_t P, int W, const int *__restrict__ off, const int *__restrict__ base,
                                                            int *__restrict__ tri)
 {
+    pdl_wait();
     extern __shared__ int s_run[];  // [W] triangles already emitted by this block per step
     __shared__ int s_w[kFanThreads / 32];
     __shared__ int s_max;
@@ -907,7 +921,7 @@ static int extract_begin_impl(const tnb_net *net, tnb_complex *c, float eps, tnb
     TNB_CUDA(cudaMemsetAsync(m->used.p, 0, (size_t)std::max<int64_t>(V, 1) * sizeof(int), s));
     TNB_CUDA(m->tmp_edges.reserve((size_t)std::max<int64_t>(E, 1)));
     if (V > 0) {
-        k_surface_flags<<<grid_for(V, 256), 256, 0, s>>>(nm, c->cvert(), c->cout_(), c->calive(), V, eps, m->surf.p, m->counters.p);
+        TNB_CUDA(launch_pdl(k_surface_flags, dim3(grid_for(V, 256)), dim3(256), 0, s, nm, c->cvert(), c->cout_(), c->calive(), V, eps, m->surf.p, m->counters.p));
         TNB_LAUNCH_CHECK();
         DevBuf<int> block_sums;
         TNB_CUDA(block_sums.reserve(kScanMaxBlocks));
@@ -916,8 +930,8 @@ static int extract_begin_impl(const tnb_net *net, tnb_complex *c, float eps, tnb
             return rc;
     }
     if (c->halo.enabled && V > 0) {
-        k_count_near_plane<<<grid_for(V, 256), 256, 0, s>>>(c->csig(), c->tag[c->vcur].p, c->calive(), V, c->halo.tag_lower ? c->halo.x_lo : -7,
-                                                            c->halo.tag_upper ? c->halo.x_hi : -7, m->counters.p);
+        TNB_CUDA(launch_pdl(k_count_near_plane, dim3(grid_for(V, 256)), dim3(256), 0, s, c->csig(), c->tag[c->vcur].p, c->calive(), V, c->halo.tag_lower ? c->halo.x_lo : -7,
+                                                            c->halo.tag_upper ? c->halo.x_hi : -7, m->counters.p));
         TNB_LAUNCH_CHECK();
     }
     if (c->halo.enabled && (rc = halo_publish_used(c, V, m->used.p, s))) return rc;
@@ -954,7 +968,7 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         int64_t blocks = std::min<int64_t>((V + kScanThreads - 1) / kScanThreads, kScanMaxBlocks);
         DevBuf<uint32_t> vmask;
         TNB_CUDA(vmask.reserve((size_t)((V + 31) / 32 + kScanMaxBlocks + 64)));
-        k_scan_count_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, FlagCount{used.p}, block_sums.p, vmask.p);
+        TNB_CUDA(launch_pdl(k_scan_count_mask<FlagCount>, dim3((unsigned)blocks), dim3(kScanThreads), 0, s, V, FlagCount{used.p}, block_sums.p, vmask.p, (const int *)nullptr));
         TNB_LAUNCH_CHECK();
         std::vector<int> hb(blocks);
         if ((rc = read_small(block_sums.p, hb.data(), (int)blocks, s))) return rc;
@@ -968,16 +982,16 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         TNB_CUDA(m->edges.reserve((size_t)std::max<int64_t>(Es, 1)));
         TNB_CUDA(m->vidx.reserve((size_t)std::max<int64_t>(Vs, 1)));
         SurfVertEmit ve{remap.p, c->tag[c->vcur].p, m->tag.p, m->vidx.p};
-        k_scan_write_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(V, vmask.p, ve, block_sums.p, counters.p + F_VERTS);
+        TNB_CUDA(launch_pdl(k_scan_write_mask<SurfVertEmit>, dim3((unsigned)blocks), dim3(kScanThreads), 0, s, V, (const uint32_t *)vmask.p, ve, (const int *)block_sums.p, counters.p + F_VERTS, (const int *)nullptr));
         TNB_LAUNCH_CHECK();
         if (Vs > 0) {
-            k_gather_rows<<<grid_for(Vs * R, 256), 256, 0, s>>>(Vs, R, m->vidx.p, c->cvert(), c->cout_(), m->vert.p, m->out.p);
+            TNB_CUDA(launch_pdl(k_gather_rows, dim3(grid_for(Vs * R, 256)), dim3(256), 0, s, Vs, R, m->vidx.p, c->cvert(), c->cout_(), m->vert.p, m->out.p));
             TNB_LAUNCH_CHECK();
         }
     }
     if (Es > 0) {
         TNB_CUDA(cudaMemcpyAsync(m->edges.p, tmp_edges.p, (size_t)Es * sizeof(int2), cudaMemcpyDeviceToDevice, s));
-        k_remap_edges2<<<grid_for(Es, 256), 256, 0, s>>>(m->edges.p, Es, remap.p);
+        TNB_CUDA(launch_pdl(k_remap_edges2, dim3(grid_for(Es, 256)), dim3(256), 0, s, m->edges.p, Es, remap.p));
         TNB_LAUNCH_CHECK();
     }
     // cells of this slab along the first axis (all of them without slab sharding)
@@ -1004,7 +1018,7 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     TNB_CUDA(head.reserve((size_t)n_cells));
     TNB_CUDA(cudaMemsetAsync(head.p, 0, (size_t)n_cells * sizeof(unsigned long long), s));
     const uint64_t colmask = (1ull << (R - 1)) - 1ull;  // m_rgn[:, :-1], subpoly.py:611
-    k_surface_sig<<<grid_for(Vs, kThreads), kThreads, 0, s>>>(nm, m->vert.p, m->out.p, Vs, eps, sig.p);
+    TNB_CUDA(launch_pdl(k_surface_sig, dim3(grid_for(Vs, kThreads)), dim3(kThreads), 0, s, nm, m->vert.p, m->out.p, Vs, eps, sig.p));
     TNB_LAUNCH_CHECK();
     TNB_CUDA(cudaMemsetAsync(counters.p + F_RECS, 0, sizeof(int), s));
     if ((rc = cells_build(8, nullptr, nullptr, Vs, sig.p, (int2 *)head.p, cslot.p, next.p, counters.p + F_RECS, dim, s))) return rc;
@@ -1012,7 +1026,7 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     DevBuf<int> huge_list;
     TNB_CUDA(sorted.reserve((size_t)Vs * 8));
     TNB_CUDA(huge_list.reserve((size_t)std::max<int64_t>(Vs * 8 / kCellSortSmem, 1) + 1));
-    k_cell_sort<<<grid_for(Vs * 8, kThreads), kThreads, 0, s>>>(Vs * 8, cslot.p, (const int2 *)head.p, next.p, sorted.p, sig.p, colmask, huge_list.p, counters.p);
+    TNB_CUDA(launch_pdl(k_cell_sort, dim3(grid_for(Vs * 8, kThreads)), dim3(kThreads), 0, s, Vs * 8, cslot.p, (const int2 *)head.p, next.p, sorted.p, sig.p, colmask, huge_list.p, counters.p));
     TNB_LAUNCH_CHECK();
     {
         static bool attr_set = false;
@@ -1020,7 +1034,7 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
             TNB_CUDA(cudaFuncSetAttribute(k_cell_sort_huge, cudaFuncAttributeMaxDynamicSharedMemorySize, kCellSortHuge * (int)sizeof(unsigned long long)));
             attr_set = true;
         }
-        k_cell_sort_huge<<<kSMs, 256, kCellSortHuge * sizeof(unsigned long long), s>>>(huge_list.p, counters.p, (const int2 *)head.p, next.p, sorted.p, sig.p, colmask);
+        TNB_CUDA(launch_pdl(k_cell_sort_huge, dim3(kSMs), dim3(256), kCellSortHuge * sizeof(unsigned long long), s, huge_list.p, counters.p, (const int2 *)head.p, next.p, sorted.p, sig.p, colmask));
         TNB_LAUNCH_CHECK();
     }
     const unsigned gw8 = grid_for(Vs, kThreads / 8);
@@ -1036,14 +1050,14 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     // fast pass: every vertex, rows in shared memory
     prof_begin(TNB_PROF_FACE_ROWS, s);
     // four vertices per warp for those with up to three zero columns (nearly all), a warp each for the others
-    k_region_rows<8><<<gw8, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
+    TNB_CUDA(launch_pdl(k_region_rows<8>, dim3(gw8), dim3(kThreads), rows_smem, s, Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
                                                       rows_per_vertex.p, nullptr, nullptr, nullptr, counters.p, cell_lo, cell_hi,
-                                                      nullptr, 0, is_long.p, long_list.p, elems_per_vertex.p, nullptr, nullptr, wide_list.p, nullptr);
+                                                      nullptr, 0, is_long.p, long_list.p, elems_per_vertex.p, nullptr, nullptr, wide_list.p, nullptr));
     TNB_LAUNCH_CHECK();
-    k_region_rows<32><<<gwide, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
+    TNB_CUDA(launch_pdl(k_region_rows<32>, dim3(gwide), dim3(kThreads), rows_smem, s, Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, kSmemRowStride, nullptr,
                                                           rows_per_vertex.p, nullptr, nullptr, nullptr, counters.p, cell_lo, cell_hi,
                                                           wide_list.p, 0, is_long.p, long_list.p, elems_per_vertex.p, nullptr, nullptr, nullptr,
-                                                          counters.p + F_NWIDE);
+                                                          counters.p + F_NWIDE));
     TNB_LAUNCH_CHECK();
     prof_end(TNB_PROF_FACE_ROWS, s, Vs, Vs * 28);
     if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
@@ -1061,9 +1075,9 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         gl = std::min<unsigned>(grid_for(n_long, kThreads / 32), kSMs * 4);
         TNB_CUDA(scratch.reserve((size_t)gl * kThreads * stride));
         prof_begin(TNB_PROF_FACE_ROWS, s);
-        k_region_rows<32><<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, stride, scratch.p, rows_per_vertex.p,
+        TNB_CUDA(launch_pdl(k_region_rows<32>, dim3(gl), dim3(kThreads), 0, s, Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 0, stride, scratch.p, rows_per_vertex.p,
                                                   nullptr, nullptr, nullptr, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr,
-                                                  elems_per_vertex.p, nullptr, nullptr, nullptr, nullptr);
+                                                  elems_per_vertex.p, nullptr, nullptr, nullptr, nullptr));
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_FACE_ROWS, s, n_long, (int64_t)n_long * 28);
     }
@@ -1081,19 +1095,19 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     TNB_CUDA(m->pstart.reserve((size_t)P));
     TNB_CUDA(m->pcnt.reserve((size_t)P));
     prof_begin(TNB_PROF_FACE_ROWS, s);
-    k_region_rows<8><<<gw8, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
+    TNB_CUDA(launch_pdl(k_region_rows<8>, dim3(gw8), dim3(kThreads), rows_smem, s, Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
                                                       rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, counters.p, cell_lo, cell_hi,
-                                                      nullptr, 0, is_long.p, nullptr, nullptr, elem_off.p, m->pstart.p, nullptr, nullptr);
+                                                      nullptr, 0, is_long.p, nullptr, nullptr, elem_off.p, m->pstart.p, nullptr, nullptr));
     TNB_LAUNCH_CHECK();
-    k_region_rows<32><<<gwide, kThreads, rows_smem, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
+    TNB_CUDA(launch_pdl(k_region_rows<32>, dim3(gwide), dim3(kThreads), rows_smem, s, Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, kSmemRowStride, nullptr,
                                                           rows_per_vertex.p, row_off.p, m->poly.p, m->pcnt.p, counters.p, cell_lo, cell_hi,
                                                           wide_list.p, 0, is_long.p, nullptr, nullptr, elem_off.p, m->pstart.p, nullptr,
-                                                          counters.p + F_NWIDE);
+                                                          counters.p + F_NWIDE));
     TNB_LAUNCH_CHECK();
     if (n_long > 0) {
-        k_region_rows<32><<<gl, kThreads, 0, s>>>(Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, stride, scratch.p, rows_per_vertex.p,
+        TNB_CUDA(launch_pdl(k_region_rows<32>, dim3(gl), dim3(kThreads), 0, s, Vs, sig.p, (const int2 *)head.p, sorted.p, dim, colmask, 1, stride, scratch.p, rows_per_vertex.p,
                                                   row_off.p, m->poly.p, m->pcnt.p, counters.p, cell_lo, cell_hi, long_list.p, n_long, is_long.p, nullptr,
-                                                  nullptr, elem_off.p, m->pstart.p, nullptr, nullptr);
+                                                  nullptr, elem_off.p, m->pstart.p, nullptr, nullptr));
         TNB_LAUNCH_CHECK();
     }
     prof_end(TNB_PROF_FACE_ROWS, s, 0, 0);
@@ -1103,13 +1117,13 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         if (W > kSortLocal) TNB_CUDA(score_scratch.reserve((size_t)std::max(h[F_LONG_TOTAL], 1)));
         DevBuf<int> long_rows;
         TNB_CUDA(long_rows.reserve((size_t)std::max(h[F_LONG_TOTAL] / (kSortLocal + 1) + 1, 1)));  // every long row counted more than kSortLocal keys
-        if (net->fixed_cfg) k_sort_rows<CfgRef><<<g, kThreads, 0, s>>>(nm, P, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p, long_rows.p);
-        else k_sort_rows<CfgAny><<<g, kThreads, 0, s>>>(nm, P, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p, long_rows.p);
+        if (net->fixed_cfg) TNB_CUDA(launch_pdl(k_sort_rows<CfgRef>, dim3(g), dim3(kThreads), 0, s, nm, P, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p, long_rows.p));
+        else TNB_CUDA(launch_pdl(k_sort_rows<CfgAny>, dim3(g), dim3(kThreads), 0, s, nm, P, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, score_scratch.p, counters.p, long_rows.p));
         TNB_LAUNCH_CHECK();
         if (W > kSortLocal) {
             const unsigned gl2 = (unsigned)std::min<int64_t>(h[F_LONG_TOTAL] / (kSortLocal + 1) / kLongRowWarps + 1, kSMs * 8);
-            if (net->fixed_cfg) k_sort_rows_long<CfgRef><<<gl2, kLongRowWarps * 32, 0, s>>>(nm, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, long_rows.p, score_scratch.p, counters.p);
-            else k_sort_rows_long<CfgAny><<<gl2, kLongRowWarps * 32, 0, s>>>(nm, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, long_rows.p, score_scratch.p, counters.p);
+            if (net->fixed_cfg) TNB_CUDA(launch_pdl(k_sort_rows_long<CfgRef>, dim3(gl2), dim3(kLongRowWarps * 32), 0, s, nm, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, long_rows.p, score_scratch.p, counters.p));
+            else TNB_CUDA(launch_pdl(k_sort_rows_long<CfgAny>, dim3(gl2), dim3(kLongRowWarps * 32), 0, s, nm, m->pstart.p, m->vert.p, m->poly.p, m->pcnt.p, long_rows.p, score_scratch.p, counters.p));
             TNB_LAUNCH_CHECK();
         }
     }
@@ -1126,18 +1140,18 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
         TNB_CUDA(off.reserve((size_t)fblocks * W));
         TNB_CUDA(col_total.reserve((size_t)W));
         TNB_CUDA(base.reserve((size_t)W));
-        k_fan_hist<<<fblocks, kFanThreads, (W + 1) * sizeof(int), s>>>(m->pcnt.p, P, W, G.p);
+        TNB_CUDA(launch_pdl(k_fan_hist, dim3(fblocks), dim3(kFanThreads), (W + 1) * sizeof(int), s, m->pcnt.p, P, W, G.p));
         TNB_LAUNCH_CHECK();
-        k_fan_cols<<<W - 2, kFanThreads, 0, s>>>(G.p, fblocks, W, off.p, col_total.p);
+        TNB_CUDA(launch_pdl(k_fan_cols, dim3(W - 2), dim3(kFanThreads), 0, s, G.p, fblocks, W, off.p, col_total.p));
         TNB_LAUNCH_CHECK();
-        k_fan_base<<<1, 1024, 0, s>>>(col_total.p, W - 2, base.p, counters.p + F_VERTS);
+        TNB_CUDA(launch_pdl(k_fan_base, dim3(1), dim3(1024), 0, s, col_total.p, W - 2, base.p, counters.p + F_VERTS));
         TNB_LAUNCH_CHECK();
         if ((rc = read_small(counters.p, h, F_NUM, s))) return rc;
         const int64_t T = h[F_VERTS];
         m->T = T;
         TNB_CUDA(m->tri.reserve((size_t)std::max<int64_t>(T, 1) * 3));
         if (T > 0) {
-            k_fan_write<<<fblocks, kFanThreads, W * sizeof(int), s>>>(m->poly.p, m->pstart.p, m->pcnt.p, P, W, off.p, base.p, m->tri.p);
+            TNB_CUDA(launch_pdl(k_fan_write, dim3(fblocks), dim3(kFanThreads), W * sizeof(int), s, m->poly.p, m->pstart.p, m->pcnt.p, P, W, off.p, base.p, m->tri.p));
             TNB_LAUNCH_CHECK();
         }
     }

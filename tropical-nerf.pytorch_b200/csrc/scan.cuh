@@ -299,6 +299,7 @@ template <class Count>
 __global__ void __launch_bounds__(kScanThreads) k_scan_count_mask(int64_t n, Count count, int *__restrict__ block_sums,
                                                                   uint32_t *__restrict__ mask, const int *__restrict__ n_dev = nullptr)
 {
+    pdl_wait();
     if (n_dev) n = *n_dev;
     scan_count_mask_part(n, count, block_sums, mask, (int)blockIdx.x, (int)gridDim.x);
 }
@@ -365,6 +366,7 @@ __global__ void __launch_bounds__(kScanThreads) k_scan_write_mask(int64_t n, con
                                                                   const int *__restrict__ block_sums, int *__restrict__ total,
                                                                   const int *__restrict__ n_dev = nullptr)
 {
+    pdl_wait();
     if (n_dev) n = *n_dev;
     scan_write_mask_part(n, mask, emit, block_sums, total, (int)blockIdx.x, (int)gridDim.x);
 }
@@ -418,9 +420,9 @@ inline int compact_masked(int64_t n, Count count, Emit emit, int *block_sums, ui
     }
     int64_t blocks = (n + kScanThreads - 1) / kScanThreads;
     if (blocks > kScanMaxBlocks) blocks = kScanMaxBlocks;
-    k_scan_count_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, count, block_sums, mask, n_dev);
+    TNB_CUDA(launch_pdl(k_scan_count_mask<Count>, dim3((unsigned)blocks), dim3(kScanThreads), 0, s, n, count, block_sums, mask, n_dev));
     TNB_LAUNCH_CHECK();
-    k_scan_write_mask<<<(unsigned)blocks, kScanThreads, 0, s>>>(n, mask, emit, block_sums, d_total, n_dev);
+    TNB_CUDA(launch_pdl(k_scan_write_mask<Emit>, dim3((unsigned)blocks), dim3(kScanThreads), 0, s, n, (const uint32_t *)mask, emit, (const int *)block_sums, d_total, n_dev));
     TNB_LAUNCH_CHECK();
     return TNB_OK;
 }
