@@ -275,6 +275,17 @@ int tnb_net_forward(const tnb_net *net, const float *d_x, int64_t n, float *d_ou
  * leaves "no root"; bilinear configurations -1 as with the reference's failover off). */
 int tnb_curve_intersections(const float *d_p, const float *d_q, int64_t count, float *d_out,
                             void *stream);
+/* subpoly_debug.deal_with_gradient_descent(c, d_new, e, eps, gg, idx, inds, ints, net)
+ * (tropical/subpoly_debug.py:121-165) for the `count` edges it selects (its mask `gd`): d_edges
+ * [count][2][3] end points, d_ints [count][3] trilinear coordinates (in: the closed form's, out: after the
+ * loop), d_plane [count] output column of the earlier plane each edge lies in (inds[:, 1]), idx the
+ * current hyperplane's column; d_dnew [count][2] = the distances (d0, d1) the reference stores back into
+ * d_new.  All edges take another step of 1e-2 down the gradient of d0^2 + d1^2 while any of them is farther
+ * than eps from one of its planes, at most 500 steps: *bodies = steps taken, *within_eps = 0 if the loop
+ * ran out (the reference then ends the extraction, subpoly.py:172-174).  Synchronises the stream. */
+int tnb_curve_gradient_descent(const tnb_net *net, const float *d_edges, float *d_ints,
+                               const int32_t *d_plane, int32_t idx, float eps, int64_t count,
+                               float *d_dnew, int32_t *bodies, int32_t *within_eps, void *stream);
 /* The ordering of geometry.sort_polygon_vertices_batch(v, n, idx) (tropical/geometry.py:483-516):
  * d_v [B][M][3] padded face rows (norm 0 = padding), d_normals [B][3]; d_order [B][M] = the
  * permutation that sorts every row by angle around its centre (stable, descending score),

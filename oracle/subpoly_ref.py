@@ -8,9 +8,9 @@ bench.py's cpu_baseline / `--impl reference` legs may import this module.
 Reference functions restated (file:line under /root/reference/tropical):
   skeleton()            tropical.py:158-225  (distance pruning mode, :188-197, :113-138)
   subpoly()             subpoly.py:23-86
-  subpoly_()            subpoly.py:90-279    (both branches; the gradient-descent repair of
-                        subpoly_debug.py:121-165 is NOT restated: it raises if it would be needed,
-                        which the reference's own runs never do)
+  subpoly_()            subpoly.py:90-279    (both branches)
+  deal_with_gradient_descent   subpoly_debug.py:121-165 (C: curve_gradient_descent; pinned by
+                        tests/golden/gd_stage.npz, the reference function's own inputs and results)
   strict_check          subpoly_debug.py:234-271
   corner_points / intersection_of_two_planes   geometry.py:350-372, :24-138 (C: curve_intersection)
   check_edges_with_new_vertices (failover)   subpoly_debug.py:33-51
@@ -34,6 +34,10 @@ torch leaves unspecified (sums over a padded face row, 3-vector dot products) ar
 DEFINED here as left-to-right sums, and the CUDA path follows this file.
 """
 import numpy as np
+
+
+class GradientDescentFailed(RuntimeError):
+    """The reference ends the extraction here (subpoly.py:172-174: the check after the repair)."""
 
 F32 = np.float32
 
@@ -214,8 +218,16 @@ def subpoly_step(P, vertices, edges, outputs, l, h, eps, pruning=True, force=Tru
             og = P.outputs(xg)
             d_new = np.stack([og[rows, plane], og[:, idx]], -1)
             gg = ((ints < 0) | (ints > 1)).sum(-1) > 0
-            if (~gg & ((np.abs(d_new) > eps32).sum(-1) > 0)).any():
-                raise NotImplementedError("gradient-descent repair (subpoly_debug.py:121-165) is not restated")
+            gd = ~gg & ((np.abs(d_new) > eps32).sum(-1) > 0)
+            if gd.any():
+                # subpoly_debug.py:121-165; the reference then ends the extraction if a repaired
+                # intersection is still off its planes (subpoly.py:172-174 -> exit())
+                from .trinet import gradient_descent
+                ints = ints.copy()
+                ints[gd], d_new[gd], _ = gradient_descent(P, ec[gd, 0], ec[gd, 1], ints[gd], plane[gd], idx, eps32)
+                if (np.abs(d_new[~gg]) > eps32).any():
+                    raise GradientDescentFailed(f"hyperplane {l}/{h}: {int(gd.sum())} intersection(s) still off their planes "
+                                                "after the gradient-descent repair (the reference ends here, subpoly.py:172-174)")
             v_new[c] = ec[:, 0] + ints * (ec[:, 1] - ec[:, 0])
     m_rgn_all, offset, outputs_new = P.region(v_new)
     m_idx = 3 + idx

@@ -217,3 +217,20 @@ def curve_intersections(p, q):
     lib().curve_intersections(ctypes.c_void_p(p.ctypes.data), ctypes.c_void_p(q.ctypes.data),
                               ctypes.c_int64(p.shape[0]), ctypes.c_void_p(out.ctypes.data))
     return out
+
+
+def gradient_descent(P, e0, e1, ints, plane, idx, eps):
+    """subpoly_debug.deal_with_gradient_descent (:121-165) for the edges that need it.
+    e0, e1, ints: [G,3]; plane: [G] column of the earlier plane each edge lies in.
+    Returns (ints, d_new [G,2], bodies executed)."""
+    e0 = np.ascontiguousarray(e0, np.float32).reshape(-1, 3)
+    e1 = np.ascontiguousarray(e1, np.float32).reshape(-1, 3)
+    x = np.array(ints, np.float32, copy=True).reshape(-1, 3)
+    pl = np.ascontiguousarray(plane, np.int32).reshape(-1)
+    d = np.zeros((x.shape[0], 2), np.float32)
+    fn = lib().curve_gradient_descent
+    fn.restype = ctypes.c_int
+    n = fn(ctypes.byref(P._c), ctypes.c_void_p(e0.ctypes.data), ctypes.c_void_p(e1.ctypes.data),
+           ctypes.c_void_p(x.ctypes.data), ctypes.c_void_p(pl.ctypes.data), ctypes.c_int32(int(idx)),
+           ctypes.c_float(np.float32(eps)), ctypes.c_int64(x.shape[0]), ctypes.c_void_p(d.ctypes.data))
+    return x, d, int(n)

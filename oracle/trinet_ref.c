@@ -15,7 +15,8 @@
  *     (tropical/tropical.py:190-195) and Net.normal (model.py:105-123)
  *   - Net.forward(gather=True, group=8) (model.py:65-70) and
  *     geometry.intersection_of_two_planes / batched_polynomial_roots
- *     (geometry.py:24-138, :259-299) for the curve-approximation path
+ *     (geometry.py:24-138, :259-299) for the curve-approximation path, and its
+ *     gradient-descent repair (subpoly_debug.py:121-165)
  *   - TropicalHashGrid.forward -> tcnn.Encoding (tropical/tropical.py:32-47).
  *     tiny-cuda-nn is a third-party dependency that is NOT in the reference
  *     tree and NOT pinned by its requirements.txt; the multiresolution hash
@@ -277,6 +278,107 @@ void trinet_grad_norm(const float *grad, int64_t count, float *norm)
         s = fmaf(g[2], g[2], s);
         norm[i] = sqrtf(s);
     }
+}
+
+/* ---- gradient-descent repair of the curve path (subpoly_debug.py:121-165) -------------- */
+/* y = dA^2 + dB^2 with dA, dB = columns colA, colB of trinet_outputs at x; grad = dy/dx (world
+ * space), by the reverse sweep autograd takes: the seeds 2*dA, 2*dB enter at their
+ * pre-activations (the last column o1 - o0 seeds the last layer with -s, +s), every layer's
+ * input gradient is the fma chain over its output neurons in ascending order from 0. */
+static void pair_grad(const trinet_t *n, const float *x, int colA, int colB, float *dA, float *dB, float grad[3])
+{
+    const int F = n->n_feat, H = n->n_hidden, R = trinet_n_outputs(n), last = n->n_linear - 1;
+    float xp[3], enc[TN_MAX_LEVELS * 8], pre[TN_MAX_LINEAR][TN_MAX_WIDTH];
+    enc_ctx_t ctx;
+    preprocess(n, x, xp);
+    encode(n, xp, enc, &ctx);
+    mlp_forward(n, enc, pre);
+    const float oA = colA == R - 1 ? pre[last][1] - pre[last][0] : pre[colA / H][colA % H];
+    const float oB = colB == R - 1 ? pre[last][1] - pre[last][0] : pre[colB / H][colB % H];
+    *dA = oA;
+    *dB = oB;
+    const float seed[2] = {2.0f * oA, 2.0f * oB};
+    const int col[2] = {colA, colB};
+    const float *Wp[TN_MAX_LINEAR];
+    const float *p = n->mlp;
+    for (int k = 0; k < n->n_linear; ++k) {
+        Wp[k] = p;
+        p += (size_t)layer_out(n, k) * layer_in(n, k) + layer_out(n, k);
+    }
+    float g_out[TN_MAX_WIDTH], g_in[TN_MAX_WIDTH];
+    for (int j = 0; j < TN_MAX_WIDTH; ++j) g_out[j] = 0.0f;
+    for (int k = last; k >= 0; --k) {
+        const int nin = layer_in(n, k), nout = layer_out(n, k);
+        /* seeds that enter at this layer's pre-activations (A first, then B) */
+        for (int t = 0; t < 2; ++t) {
+            if (col[t] == R - 1) {
+                if (k == last) { g_out[0] = g_out[0] - seed[t]; g_out[1] = g_out[1] + seed[t]; }
+            } else if (col[t] / H == k) {
+                g_out[col[t] % H] = g_out[col[t] % H] + seed[t];
+            }
+        }
+        for (int c = 0; c < nin; ++c) {
+            float acc = 0.0f;
+            for (int j = 0; j < nout; ++j) acc = fmaf(Wp[k][j * nin + c], g_out[j], acc);
+            g_in[c] = acc;
+        }
+        if (k > 0)
+            for (int c = 0; c < nin; ++c) g_out[c] = pre[k - 1][c] > 0.0f ? g_in[c] : 0.0f;
+    }
+    for (int d = 0; d < 3; ++d) {
+        float acc = 0.0f;
+        for (int l = 0; l < n->n_levels; ++l) {
+            float dl[8];
+            encode_dx(n, &ctx, l, d, dl);
+            for (int f = 0; f < F; ++f) acc = fmaf(g_in[l * F + f], dl[f], acc);
+        }
+        grad[d] = acc / (n->pre_scale * 2.0f);
+    }
+}
+
+/* One body of the loop at subpoly_debug.py:144-151 for one edge: x (edge parameters, one per
+ * axis) -> x - 1e-2 * normalize(dy/dx), clamped to [0,1]; d[2] = the two distances at the x the
+ * body STARTED from.  F.normalize divides by max(|g|, 1e-12). */
+static void gd_body(const trinet_t *n, const float e0[3], const float e1[3], int colA, int colB, float x[3], float d[2])
+{
+    float xw[3], g[3], gx[3];
+    for (int k = 0; k < 3; ++k) {
+        const float t = x[k] * (e1[k] - e0[k]);
+        xw[k] = e0[k] + t;
+    }
+    pair_grad(n, xw, colA, colB, &d[0], &d[1], g);
+    for (int k = 0; k < 3; ++k) gx[k] = g[k] * (e1[k] - e0[k]);
+    float s = gx[0] * gx[0];
+    s = fmaf(gx[1], gx[1], s);
+    s = fmaf(gx[2], gx[2], s);
+    float nrm = sqrtf(s);
+    if (!(nrm > 1e-12f)) nrm = 1e-12f;
+    for (int k = 0; k < 3; ++k) {
+        const float q = gx[k] / nrm;
+        float v = x[k] - 0.01f * q;
+        v = v < 0.0f ? 0.0f : v;
+        v = v > 1.0f ? 1.0f : v;
+        x[k] = v;
+    }
+}
+
+/* deal_with_gradient_descent (subpoly_debug.py:121-165) for the `count` edges that need it:
+ * ALL of them take another step while ANY of them is farther than eps from one of its two planes,
+ * at most 500 steps.  x: [count][3] in/out; plane: column of the earlier plane each edge lies in;
+ * d: [count][2] = distances at the x the last body started from.  Returns the number of bodies. */
+int curve_gradient_descent(const trinet_t *n, const float *e0, const float *e1, float *x, const int32_t *plane,
+                           int32_t idx, float eps, int64_t count, float *d)
+{
+    int i = 0, more = 1;
+    while (more && i < 500) {
+        more = 0;
+        for (int64_t r = 0; r < count; ++r) {
+            gd_body(n, e0 + 3 * r, e1 + 3 * r, plane[r], idx, x + 3 * r, d + 2 * r);
+            if (fabsf(d[2 * r]) > eps || fabsf(d[2 * r + 1]) > eps) more = 1;
+        }
+        ++i;
+    }
+    return i;
 }
 
 /* ---- region indicators ------------------------------------------------------------ */

@@ -5,7 +5,9 @@
 //   tnb_net_outputs_group8   Net.forward(x, gather=True, group=8)            model.py:52-76 (:65-70)
 //   tnb_curve_intersections  geometry.intersection_of_two_planes             geometry.py:24-138
 //   tnb_polygon_order        geometry.sort_polygon_vertices_batch's ordering geometry.py:483-516
+//   tnb_curve_gradient_descent  subpoly_debug.deal_with_gradient_descent     subpoly_debug.py:121-165
 #include "curve.cuh"
+#include "repair.cuh"
 #include "net_eval.cuh"
 #include "runtime.cuh"
 #include "sort.cuh"
@@ -196,6 +198,38 @@ int tnb_curve_intersections(const float *d_p, const float *d_q, int64_t count, f
     if (count == 0) return TNB_OK;
     k_curve_intersections<<<grid_for(count, kCompatThreads), kCompatThreads, 0, (cudaStream_t)stream>>>(d_p, d_q, count, d_out);
     TNB_LAUNCH_CHECK();
+    return TNB_OK;
+}
+
+int tnb_curve_gradient_descent(const tnb_net *net, const float *d_edges, float *d_ints, const int32_t *d_plane, int32_t idx, float eps,
+                               int64_t count, float *d_dnew, int32_t *bodies, int32_t *within_eps, void *stream)
+{
+    if (!net || count < 0 || idx < 1 || idx >= net->meta.R || (count > 0 && (!d_edges || !d_ints || !d_plane || !d_dnew))) {
+        set_error("tnb_curve_gradient_descent: bad argument");
+        return TNB_ERR_INVALID;
+    }
+    if (bodies) *bodies = 0;
+    if (within_eps) *within_eps = 1;
+    if (count == 0) return TNB_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    current_stream() = s;
+    DevBuf<int> gd;
+    TNB_CUDA(gd.reserve(kGdHead));
+    k_gd_reset<<<1, 32, 0, s>>>(gd.p);
+    const unsigned g = grid_for(count, 64);
+    if (net->fixed_cfg) {
+        k_gd_stage_note<CfgRef><<<g, 64, 0, s>>>(net->meta, d_edges, d_ints, d_plane, idx, eps, count, gd.p);
+        k_gd_stage_walk<CfgRef><<<g, 64, 0, s>>>(net->meta, d_edges, d_ints, d_plane, idx, count, d_dnew, gd.p);
+    } else {
+        k_gd_stage_note<CfgAny><<<g, 64, 0, s>>>(net->meta, d_edges, d_ints, d_plane, idx, eps, count, gd.p);
+        k_gd_stage_walk<CfgAny><<<g, 64, 0, s>>>(net->meta, d_edges, d_ints, d_plane, idx, count, d_dnew, gd.p);
+    }
+    TNB_LAUNCH_CHECK();
+    int h[4];
+    TNB_CUDA(cudaMemcpyAsync(h, gd.p, sizeof(h), cudaMemcpyDeviceToHost, s));
+    TNB_CUDA(cudaStreamSynchronize(s));
+    if (bodies) *bodies = h[GD_BODIES];
+    if (within_eps) *within_eps = h[GD_OK];
     return TNB_OK;
 }
 

@@ -18,6 +18,7 @@
 #include "complex.cuh"
 #include "cells.cuh"
 #include "curve.cuh"
+#include "repair.cuh"
 #include "halo.cuh"
 #include "net_eval.cuh"
 #include "scan.cuh"
@@ -42,7 +43,7 @@ constexpr int kNetworkPartners = 12; // lists up to this size (nearly all of the
 //   C_LONG = candidates whose partner list is longer than the cache (their connecting edges are a warp's job)
 enum { C_SPLIT = 0, C_FLAG, C_HIT, C_PAIRS, C_CAND, C_OVERFLOW, C_RAW, C_ERR, C_V = 8, C_E = 9, C_VPAR = 10, C_EPAR = 11, C_STICKY = 12, C_KEPT = 13, C_APAR = 14, C_LONG = 15, C_CROSS = 16 /* 64-bit crossing mask */, C_RECS = 18 /* records in the contiguous cell segments */,
        C_STEP = 19 /* device-driven step stream: next position in the step list */, C_IDX = 20 /* its current hyperplane column, -1 = none */, C_PRUNE = 21, C_NUM = 32 };
-enum { kErrNoPlane = 1, kErrGradientDescent = 2 };
+enum { kErrNoPlane = 1, kErrGradientDescent = 2 /* the repair ended off the planes, or too many walks */, kErrRepair = 4 /* walks filed: run the repair */ };
 enum { kStickyCapacity = 1, kStickyNoPlane = 32, kStickyGradientDescent = 64 };  // 2..16: halo.cuh
 
 // ---- allocation ---------------------------------------------------------------------------
@@ -78,6 +79,8 @@ int complex_alloc(tnb_complex *c, const tnb_net *net, size_t Vcap, size_t Ecap)
     TNB_CUDA(c->remap.reserve(Vcap));
     TNB_CUDA(c->block_sums.reserve(3 * kScanMaxBlocks));  // the persistent step kernels keep three sets of block sums
     TNB_CUDA(c->counters.reserve(C_NUM));
+    TNB_CUDA(c->gd.reserve(kGdInts));
+    k_gd_reset<<<1, 32, 0, current_stream()>>>(c->gd.p);
     TNB_CUDA(c->bytes.reserve(4));
     TNB_CUDA(cudaMemsetAsync(c->bytes.p, 0, 4 * sizeof(unsigned long long), current_stream()));
     TNB_CUDA(cudaMemsetAsync(c->counters.p, 0, C_NUM * sizeof(int), current_stream()));
@@ -828,7 +831,7 @@ template <class C>
 __device__ __forceinline__ int curve_candidate_item(const NetMeta &n, int idx, float eps, bool active, int k, const int *split_list,
                                                     const int2 *edges, const float *vert, const float *out,
                                                     const uint64_t *sig, float *tvert, float *tout, uint64_t *bmask,
-                                                    int *sflag, int *cnt)
+                                                    int *sflag, int *cnt, int *gd)
 {
     const int R = n.R;
     float e0[3] = {0.0f, 0.0f, 0.0f}, e1[3] = {0.0f, 0.0f, 0.0f}, x[3] = {0.0f, 0.0f, 0.0f};
@@ -861,6 +864,7 @@ __device__ __forceinline__ int curve_candidate_item(const NetMeta &n, int idx, f
     warp_group8_columns<C>(n, curved, e0, e1, n.eps, plane, idx, p8, q8);
     warp_curve_intersection(curved, p8, q8, ints);
     int any = 0;
+    bool walks = false;
     if (active) {
         if (curved) {
             bool gg = false;
@@ -874,8 +878,18 @@ __device__ __forceinline__ int curve_candidate_item(const NetMeta &n, int idx, f
                 for (int d = 0; d < 3; ++d) xg[d] = e0[d] * (1.0f - ints[d]) + e1[d] * ints[d];
                 float *row = tout + (int64_t)k * R;
                 outputs_row<C>(n, xg, row);
-                if (fabsf(row[plane]) > eps || fabsf(row[idx]) > eps)
-                    atomicOr(cnt + C_ERR, kErrGradientDescent);  // subpoly_debug.py:121-165 not built
+                if (fabsf(row[plane]) > eps || fabsf(row[idx]) > eps) {
+                    // off one of its two planes: a walk of the gradient-descent repair (subpoly_debug.py:121-165, repair.cuh),
+                    // which writes this candidate's vertex and row once the shared step count is known
+                    const int r = atomicAdd(gd + GD_COUNT, 1);
+                    if (r < kGdCap) {
+                        int *w = gd + kGdHead + 5 * r;
+                        w[0] = k; w[1] = plane;
+                        w[2] = __float_as_int(ints[0]); w[3] = __float_as_int(ints[1]); w[4] = __float_as_int(ints[2]);
+                        atomicOr(cnt + C_ERR, kErrRepair);
+                    } else atomicOr(cnt + C_ERR, kErrGradientDescent);
+                    walks = true;
+                }
             }
 #pragma unroll
             for (int d = 0; d < 3; ++d) x[d] = e0[d] + ints[d] * (e1[d] - e0[d]);  // subpoly.py:183
@@ -891,8 +905,81 @@ __device__ __forceinline__ int curve_candidate_item(const NetMeta &n, int idx, f
             const int col = __ffsll((long long)m) - 1;
             if (fabsf(row[col]) > eps) any = 1;
         }
+        if (walks) any = 0;  // decided by the repaired vertex (gd_complex_walk)
     }
     return any;
+}
+
+// The repair's two passes over the walks curve_candidate_item filed (repair.cuh); tid / nthreads = the caller's
+// place among the threads that share the walks.  The second pass leaves the repaired vertex and its network row in
+// the candidate's temp slot and returns the failover flag of subpoly_debug.py:33-51 for them; if the shared loop
+// ended with a walk still off its planes the reference ends the extraction (subpoly.py:172-174): kErrGradientDescent.
+template <class C>
+static __device__ void gd_complex_note(const NetMeta &n, int idx, float eps, const int *split_list, const int2 *edges,
+                                       const float *vert, int *gd, int tid, int nthreads)
+{
+    const int G = min(gd[GD_COUNT], kGdCap);
+    for (int r = tid; r < G; r += nthreads) {
+        const int *w = gd + kGdHead + 5 * r;
+        const int2 ed = edges[split_list[w[0]]];
+        float e0[3], e1[3];
+#pragma unroll
+        for (int d = 0; d < 3; ++d) { e0[d] = vert[3 * (int64_t)ed.x + d]; e1[d] = vert[3 * (int64_t)ed.y + d]; }
+        const float x0[3] = {__int_as_float(w[2]), __int_as_float(w[3]), __int_as_float(w[4])};
+        gd_note_steps<C>(n, e0, e1, w[1], idx, eps, x0, gd + GD_MASK);
+    }
+}
+template <class C>
+static __device__ int gd_complex_walk(const NetMeta &n, int idx, float eps, const int *split_list, const int2 *edges,
+                                      const float *vert, float *tvert, float *tout, const uint64_t *bmask, int *cnt, int *gd,
+                                      int tid, int nthreads)
+{
+    bool ok;
+    const int bodies = gd_bodies(gd + GD_MASK, ok);
+    if (!ok) {
+        if (tid == 0) atomicOr(cnt + C_ERR, kErrGradientDescent);
+        return 0;
+    }
+    const int G = min(gd[GD_COUNT], kGdCap), R = n.R;
+    int any = 0;
+    for (int r = tid; r < G; r += nthreads) {
+        const int *w = gd + kGdHead + 5 * r;
+        const int k = w[0];
+        const int2 ed = edges[split_list[k]];
+        float e0[3], e1[3], d[2];
+#pragma unroll
+        for (int dd = 0; dd < 3; ++dd) { e0[dd] = vert[3 * (int64_t)ed.x + dd]; e1[dd] = vert[3 * (int64_t)ed.y + dd]; }
+        float x[3] = {__int_as_float(w[2]), __int_as_float(w[3]), __int_as_float(w[4])};
+        gd_walk<C>(n, e0, e1, w[1], idx, bodies, x, d);
+        float xv[3];
+#pragma unroll
+        for (int dd = 0; dd < 3; ++dd) xv[dd] = e0[dd] + x[dd] * (e1[dd] - e0[dd]);  // subpoly.py:183
+#pragma unroll
+        for (int dd = 0; dd < 3; ++dd) tvert[3 * (int64_t)k + dd] = xv[dd];
+        float *row = tout + (int64_t)k * R;
+        outputs_row<C>(n, xv, row);
+        for (uint64_t m = bmask[k]; m; m &= m - 1) {
+            const int col = __ffsll((long long)m) - 1;
+            if (fabsf(row[col]) > eps) any = 1;
+        }
+    }
+    return any;
+}
+template <class C>
+__global__ void __launch_bounds__(64) k_gd_note(const __grid_constant__ NetMeta n, int idx, float eps, const int *__restrict__ split_list,
+                                                const int2 *__restrict__ edges, const float *__restrict__ vert, const int *__restrict__ cnt, int *__restrict__ gd)
+{
+    if (!(cnt[C_ERR] & kErrRepair)) return;
+    gd_complex_note<C>(n, idx, eps, split_list, edges, vert, gd, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x);
+}
+template <class C>
+__global__ void __launch_bounds__(64) k_gd_walk(const __grid_constant__ NetMeta n, int idx, float eps, const int *__restrict__ split_list,
+                                                const int2 *__restrict__ edges, const float *__restrict__ vert, float *__restrict__ tvert,
+                                                float *__restrict__ tout, const uint64_t *__restrict__ bmask, int *__restrict__ cnt, int *__restrict__ gd)
+{
+    if (!(cnt[C_ERR] & kErrRepair)) return;
+    if (gd_complex_walk<C>(n, idx, eps, split_list, edges, vert, tvert, tout, bmask, cnt, gd, blockIdx.x * blockDim.x + threadIdx.x, gridDim.x * blockDim.x))
+        atomicOr(cnt + C_FLAG, 1);
 }
 
 template <class C>
@@ -902,7 +989,7 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices_curve(const __grid_co
                                                                  const float *__restrict__ vert, const float *__restrict__ out,
                                                                  const uint64_t *__restrict__ sig, float *__restrict__ tvert,
                                                                  float *__restrict__ tout, uint64_t *__restrict__ bmask,
-                                                                 int *__restrict__ sflag, int *__restrict__ cnt)
+                                                                 int *__restrict__ sflag, int *__restrict__ cnt, int *__restrict__ gd)
 {
     const int S = cnt[C_RAW], V = cnt[C_V], E = cnt[C_E];
     if ((int64_t)V + S > Vcap || (int64_t)E + S > Ecap) {
@@ -912,7 +999,7 @@ __global__ void __launch_bounds__(kThreads) k_new_vertices_curve(const __grid_co
     int any = 0;
     const int lane = threadIdx.x & 31;
     for (int k0 = blockIdx.x * blockDim.x + (threadIdx.x - lane); k0 < S; k0 += gridDim.x * blockDim.x)  // warp-uniform trip count
-        any |= curve_candidate_item<C>(n, idx, eps, k0 + lane < S, k0 + lane, split_list, edges, vert, out, sig, tvert, tout, bmask, sflag, cnt);
+        any |= curve_candidate_item<C>(n, idx, eps, k0 + lane < S, k0 + lane, split_list, edges, vert, out, sig, tvert, tout, bmask, sflag, cnt, gd);
     if (__any_sync(0xffffffffu, any) && (threadIdx.x & 31) == 0) atomicOr(cnt + C_FLAG, 1);
 }
 
@@ -1758,6 +1845,7 @@ struct StepArgs {
     float *vert[2], *out[2];
     uint64_t *sig[2], *bmask;
     int *split_list, *cand, *pcount, *poff, *used[2], *remap, *block_sums, *cnt, *pcache;
+    int *gd;                        // curve path: walks of the gradient-descent repair (repair.cuh)
     tnb_bucket_rec *next;
     unsigned long long *head, *bytes;  // bytes[0/1]: algorithmic bytes of the front / back halves, [2/3]: their units
     unsigned char *tag[2];
@@ -2049,6 +2137,13 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     if (a.use_cross && !((*cross >> sv.idx) & 1ull)) return 2;
     TNB_PHASE_MARK(0);
     if (blockIdx.x == 0 && threadIdx.x == 0) { cnt[C_FLAG] = 0; cnt[C_ERR] = 0; cnt[C_LONG] = 0; }  // last read at least one barrier ago
+    if constexpr (kCurve) {
+        if (blockIdx.x == 0 && threadIdx.x < 32) {  // an earlier hyperplane needed the repair: clear its walks
+            const int had = a.gd[GD_COUNT];
+            __syncwarp();
+            if (had && threadIdx.x < GD_MASK + kGdWords) a.gd[threadIdx.x] = threadIdx.x < GD_MASK ? 0 : -1;
+        }
+    }
     // P0: edges the plane crosses, per CTA slice
     const SplitCount sc{edges, out, R, sv.idx, a.eps};
     scan_count_body_t<NT>(E, sc, sums_x);
@@ -2084,7 +2179,7 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
             const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
             for (int j0 = 0; s_base + j0 < s_end; j0 += NT) {
                 const int k = s_base + j0 + lane * NW + warp;
-                any |= curve_candidate_item<C>(n, sv.idx, a.eps, k < s_end, k, a.split_list, edges, vert, out, sig, tvert, tout, a.bmask, sflag, cnt);
+                any |= curve_candidate_item<C>(n, sv.idx, a.eps, k < s_end, k, a.split_list, edges, vert, out, sig, tvert, tout, a.bmask, sflag, cnt, a.gd);
             }
         } else {
             for (int k = s_base + (int)threadIdx.x; k < s_end; k += NT)
@@ -2096,12 +2191,24 @@ __device__ __forceinline__ int step_fused(const NetMeta &n, const StepArgs &a, c
     scan_count_body_t<NT>(V, hc, sums_y);
     sync();
     TNB_PHASE_MARK(2);
-    const int flag = cnt[C_FLAG];
+    int flag = cnt[C_FLAG];
     const int S_raw = S;
     if constexpr (kCurve) {
         // P1b: an intersection the path cannot place ends the extraction (uniform: C_ERR was last
         // written before the barrier); else strict_check (subpoly_debug.py:234-271) on the own candidates
-        const int err = cnt[C_ERR];
+        int err = cnt[C_ERR];
+        if (err == kErrRepair) {
+            // intersections off their planes walk down the gradient first (subpoly_debug.py:121-165, repair.cuh):
+            // a failover, two more barriers, one thread per walk
+            const int tid = (int)blockIdx.x * NT + (int)threadIdx.x, nthreads = nb * NT;
+            gd_complex_note<C>(n, sv.idx, a.eps, a.split_list, edges, vert, a.gd, tid, nthreads);
+            sync();
+            if (gd_complex_walk<C>(n, sv.idx, a.eps, a.split_list, edges, vert, tvert, tout, a.bmask, cnt, a.gd, tid, nthreads))
+                atomicOr(cnt + C_FLAG, 1);
+            sync();
+            err = cnt[C_ERR] & ~kErrRepair;
+            flag = cnt[C_FLAG];
+        }
         if (err) {
             if (blockIdx.x == 0 && threadIdx.x == 0)
                 atomicOr(cnt + C_STICKY, ((err & kErrNoPlane) ? kStickyNoPlane : 0) | ((err & kErrGradientDescent) ? kStickyGradientDescent : 0));
@@ -2327,7 +2434,7 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
     if (sticky & kStickyNoPlane)
         return latch(TNB_ERR_INVALID, "curve path: a non-axis-aligned edge lies on no earlier plane (the reference exits here, subpoly.py:140-148)");
     if (sticky & kStickyGradientDescent)
-        return latch(TNB_ERR_UNSUPPORTED, "curve path: an intersection needs the gradient-descent repair of subpoly_debug.py:121-165, which is not built");
+        return latch(TNB_ERR_UNSUPPORTED, "curve path: an intersection is still off its planes after the gradient-descent repair (subpoly_debug.py:121-165); the reference ends the extraction here (subpoly.py:172-174)");
     if (sticky & kStickyHaloPayload) return latch(TNB_ERR_CAPACITY, "slab exchange: a shared plane holds more vertices than the mailbox payload");
     if (sticky & kStickyHaloTimeout) return latch(TNB_ERR_CUDA, "slab exchange: a peer did not answer within the timeout");
     if (sticky & kStickyHaloMismatch) return latch(TNB_ERR_INVALID, "slab exchange: the two sides of a shared plane disagree on its vertex count");
@@ -2425,7 +2532,7 @@ static void fill_step_args(const tnb_net *net, tnb_complex *c, float eps, StepAr
         sa.used[k] = c->used[k].p; sa.tag[k] = c->tag[k].p;
     }
     sa.bmask = c->bmask.p; sa.split_list = c->split_list.p; sa.cand = c->cand.p; sa.pcount = c->pcount.p;
-    sa.poff = c->poff.p; sa.pcache = c->pcache.p; sa.next = c->next.p; sa.remap = c->remap.p;
+    sa.poff = c->poff.p; sa.pcache = c->pcache.p; sa.gd = c->gd.p; sa.next = c->next.p; sa.remap = c->remap.p;
     sa.block_sums = c->block_sums.p; sa.cnt = c->counters.p; sa.head = c->head.p; sa.bytes = c->bytes.p;
     sa.cslot = c->cslot.p; sa.mask_e = c->scan_mask.p; sa.mask_v = c->scan_mask.p + scan_mask_vertex_offset(c->Ecap);
 }
@@ -2695,11 +2802,21 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         if (!planar) {
             const int o = c->vcur ^ 1;  // idle half of the ping-pong arrays = temp slots
             unsigned g = grid_for(c->E, kThreads);
+            k_gd_reset<<<1, 32, 0, s>>>(c->gd.p);
             prof_begin(TNB_PROF_NEW_VERTICES, s);
             if (net->fixed_cfg)
-                k_new_vertices_curve<CfgRef><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->bmask.p, c->pcount.p, cnt);
+                k_new_vertices_curve<CfgRef><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->bmask.p, c->pcount.p, cnt, c->gd.p);
             else
-                k_new_vertices_curve<CfgAny><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->bmask.p, c->pcount.p, cnt);
+                k_new_vertices_curve<CfgAny><<<g, kThreads, 0, s>>>(m, idx, eps, (int)c->Vcap, (int)c->Ecap, c->split_list.p, c->cedges(), c->cvert(), c->cout_(), c->csig(), c->vert[o].p, c->out[o].p, c->bmask.p, c->pcount.p, cnt, c->gd.p);
+            TNB_LAUNCH_CHECK();
+            // the gradient-descent repair of the intersections that are off their planes (both return at once if there are none)
+            if (net->fixed_cfg) {
+                k_gd_note<CfgRef><<<kSMs, 64, 0, s>>>(m, idx, eps, c->split_list.p, c->cedges(), c->cvert(), cnt, c->gd.p);
+                k_gd_walk<CfgRef><<<kSMs, 64, 0, s>>>(m, idx, eps, c->split_list.p, c->cedges(), c->cvert(), c->vert[o].p, c->out[o].p, c->bmask.p, cnt, c->gd.p);
+            } else {
+                k_gd_note<CfgAny><<<kSMs, 64, 0, s>>>(m, idx, eps, c->split_list.p, c->cedges(), c->cvert(), cnt, c->gd.p);
+                k_gd_walk<CfgAny><<<kSMs, 64, 0, s>>>(m, idx, eps, c->split_list.p, c->cedges(), c->cvert(), c->vert[o].p, c->out[o].p, c->bmask.p, cnt, c->gd.p);
+            }
             TNB_LAUNCH_CHECK();
             prof_end(TNB_PROF_NEW_VERTICES, s, 0);
             k_strict_keep<<<g, kThreads, 0, s>>>(R, idx, eps, c->out[o].p, c->bmask.p, c->pcount.p, cnt);
@@ -2754,7 +2871,7 @@ static int step_impl(const tnb_net *net, tnb_complex *c, int l, int h, float eps
         return TNB_ERR_INVALID;
     }
     if (c->h_counters[C_ERR] & kErrGradientDescent) {
-        set_error("curve path: an intersection needs the gradient-descent repair of subpoly_debug.py:121-165, which is not built");
+        set_error("curve path: an intersection is still off its planes after the gradient-descent repair (subpoly_debug.py:121-165); the reference ends the extraction here (subpoly.py:172-174)");
         return TNB_ERR_UNSUPPORTED;
     }
     if (c->h_counters[C_RAW] == 0) return TNB_OK;  // subpoly.py:110-111

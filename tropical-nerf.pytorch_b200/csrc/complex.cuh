@@ -77,6 +77,7 @@ struct tnb_complex {
     tnb::DevBuf<int> block_sums;    // [kScanMaxBlocks]
     tnb::DevBuf<uint32_t> scan_mask;  // one bit per edge / vertex: masked compactions (scan.cuh)
     tnb::DevBuf<int> counters;      // [16] device counters
+    tnb::DevBuf<int> gd;            // curve path: walks of the gradient-descent repair (repair.cuh)
     tnb::DevBuf<unsigned long long> bytes;  // [4] algorithmic bytes (front / back half of a step) and units accumulated by the fused kernels
     int *h_counters = nullptr;      // pinned mirror (per thread, not owned)
     bool counts_stale = false;      // V/E are upper bounds; exact sizes are in counters[C_V], [C_E]

@@ -423,6 +423,62 @@ __device__ __forceinline__ float sdf_grad(const NetMeta &n, const float x[3], fl
     return t;
 }
 
+// y = dA^2 + dB^2 with dA, dB = output columns colA, colB at x; grad = dy/dx in world space (what autograd
+// hands the gradient-descent repair of the curve path, subpoly_debug.py:147-149).  Same reverse sweep and
+// operation order as oracle/trinet_ref.c pair_grad: the seeds 2 dA, 2 dB enter at their pre-activations (the
+// last column o1 - o0 seeds the last layer with -s, +s).  A rare path: out of line, arrays in local memory.
+template <class C>
+static __device__ __noinline__ void pair_grad(const NetMeta &n, const float x[3], int colA, int colB, float d[2], float grad[3])
+{
+    float xp[3];
+    preprocess(n, x, xp);
+    float pre[(C::kMaxLin - 1) * C::kMaxH];
+    float o[2];
+    forward<C>(n, xp, pre, o);
+    const int H = C::H(n), R = n.R, last = C::NLIN(n) - 1;
+    const int col[2] = {colA, colB};
+    float seed[2];
+#pragma unroll
+    for (int t = 0; t < 2; ++t) {
+        d[t] = col[t] == R - 1 ? o[1] - o[0] : pre[(col[t] / H) * C::kMaxH + col[t] % H];
+        seed[t] = 2.0f * d[t];
+    }
+    float g_out[C::kMaxW], g_in[C::kMaxW];
+#pragma unroll(C::kUnroll)
+    for (int j = 0; j < C::kMaxW; ++j) g_out[j] = 0.0f;
+    int base[C::kMaxLin];
+    {
+        int b = 0;
+#pragma unroll(C::kUnroll)
+        for (int i = 0; i < C::kMaxLin; ++i)
+            if (i < C::NLIN(n)) { base[i] = b; b += C::nout(n, i) * C::nin(n, i) + C::nout(n, i); }
+    }
+#pragma unroll 1
+    for (int k = last; k >= 0; --k) {
+        const int ni = C::nin(n, k), no = C::nout(n, k);
+#pragma unroll
+        for (int t = 0; t < 2; ++t) {
+            if (col[t] == R - 1) {
+                if (k == last) { g_out[0] = g_out[0] - seed[t]; g_out[1] = g_out[1] + seed[t]; }
+            } else if (col[t] / H == k) {
+                g_out[col[t] % H] = g_out[col[t] % H] + seed[t];
+            }
+        }
+        for (int c = 0; c < ni; ++c) {
+            float acc = 0.0f;
+            for (int j = 0; j < no; ++j) acc = __fmaf_rn(C::w(n, base[k] + j * ni + c), g_out[j], acc);
+            g_in[c] = acc;
+        }
+        if (k > 0)
+            for (int c = 0; c < ni; ++c) g_out[c] = pre[(k - 1) * C::kMaxH + c] > 0.0f ? g_in[c] : 0.0f;
+    }
+    float acc[3] = {0.0f, 0.0f, 0.0f};
+#pragma unroll 1
+    for (int l = 0; l < C::L(n); ++l) encode_level_grad(n, l, xp, g_in[2 * l], g_in[2 * l + 1], acc);
+#pragma unroll
+    for (int dd = 0; dd < 3; ++dd) grad[dd] = div_2s(n, acc[dd]);
+}
+
 __device__ __forceinline__ float grad_norm(const float g[3])
 {
     float s = g[0] * g[0];

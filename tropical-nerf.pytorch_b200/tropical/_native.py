@@ -107,6 +107,7 @@ SIGNATURES = {
     "tnb_net_outputs_group8": (ctypes.c_int, [_P, _P, _I64, _F, _P, _P, _P]),
     "tnb_curve_intersections": (ctypes.c_int, [_P, _P, _I64, _P, _P]),
     "tnb_net_forward": (ctypes.c_int, [_P, _P, _I64, _P, _P, _P]),
+    "tnb_curve_gradient_descent": (ctypes.c_int, [_P, _P, _P, _P, _I32, _F, _I64, _P, ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_int32), _P]),
     "tnb_polygon_order": (ctypes.c_int, [_P, _P, _I64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P]),
     "tnb_mesh_near_plane": (_I64, [_P]),
     "tnb_grid_train_table_len": (_I64, [_P]),
@@ -272,6 +273,19 @@ class NativeNet:
         check(lib().tnb_net_outputs_group8(self.handle, _ptr(x), n // 8, float(self.eps if eps is None else eps),
                                            _ptr(out), _ptr(raw), _stream()))
         return out, raw
+
+    def gradient_descent(self, edges, ints, plane, idx, eps):
+        """subpoly_debug.deal_with_gradient_descent (:121-165) for the edges it selects: edges [G, 2, 3], ints [G, 3],
+        plane [G] -> (ints after the loop, d_new [G, 2], steps taken, True if every edge ended within eps)."""
+        edges = edges.contiguous().float()
+        x = ints.contiguous().float().clone()
+        plane = plane.contiguous().to(torch.int32)
+        G = x.shape[0]
+        d = torch.zeros((G, 2), dtype=torch.float32, device=x.device)
+        bodies, ok = ctypes.c_int32(0), ctypes.c_int32(1)
+        check(lib().tnb_curve_gradient_descent(self.handle, _ptr(edges), _ptr(x), _ptr(plane), int(idx), float(eps), G, _ptr(d),
+                                               ctypes.byref(bodies), ctypes.byref(ok), _stream()))
+        return x, d, bodies.value, bool(ok.value)
 
     def sdf_grad(self, x, want_grad=True):
         x = x.contiguous().float()
