@@ -297,6 +297,17 @@ int tnb_polygon_order(const float *d_v, const float *d_normals, int64_t B, int32
  * tnb_complex_from_arrays: the caller's numbering). */
 int tnb_mesh_read_vertex_index(const tnb_mesh *m, int64_t *d_index, void *stream);
 
+/* subpoly(net, ...) (tropical/subpoly.py:23-86) for `count` networks in ONE call: the reference extracts one
+ * object per process run (train.py:127); a service that extracts many small objects calls this.  nets[count]
+ * in, out[count] meshes (as tnb_subpoly; NULL where an object failed), rcs[count] per-object return codes (may
+ * be NULL).  Up to `in_flight` objects (<= 0: 8) are worked on at the same time by host threads of the library,
+ * each on a stream of its own that is ordered after `stream` at entry; `stream` is ordered after all of them at
+ * return.  Every object takes the single-object path (same kernels, same results); small complexes run their
+ * hyperplanes in one thread-block cluster each, so up to nine step loops are resident side by side.
+ * Returns the first failure's code (its message names the object) or TNB_OK. */
+int tnb_subpoly_batch(const tnb_net *const *nets, int32_t count, float size, float eps, int32_t force,
+                      int32_t unit, int32_t in_flight, tnb_mesh **out, int32_t *rcs, void *stream);
+
 /* ---- knobs / introspection ------------------------------------------------------ */
 /* work-buffer growth factor for the complex (default 4.0) */
 int tnb_set_capacity_factor(double f);
@@ -313,6 +324,9 @@ int64_t tnb_set_fused_max_items(int64_t items);
  * reset (bench.py's gpu_launches) */
 int64_t tnb_launch_count(void);
 void tnb_launch_count_reset(void);
+/* Work buffers released by an extraction are kept by the calling thread for its next extraction on the same
+ * stream (no allocator call in the steady state); this hands them back to the device's memory pool. */
+void tnb_release_cached_blocks(void);
 /* Per-kernel timers: when enabled, the library brackets its heavy kernels with CUDA
  * events on the launching stream.  Classes: 0 = marks-grid sweep (sdf + gradient),
  * 1 = vertex network rows (outputs + packed signs), 2 = new-vertex subdivision kernel,

@@ -29,6 +29,8 @@ tnb_complex::~tnb_complex() {}
 namespace tnb {
 
 double g_capacity_factor = 4.0;
+thread_local double t_capacity_scale = 1.0;  // the capacity retry of tnb_subpoly (per calling thread)
+double capacity_factor() { return g_capacity_factor * t_capacity_scale; }
 constexpr int kThreads = 128;
 constexpr int kCachedPartners = 32;  // the partner-count pass keeps this many partners per candidate: the write
                                     // pass of such a list does not walk the buckets again
@@ -631,7 +633,7 @@ static int skeleton_finish_impl(const tnb_net *net, tnb_sweep *sw, tnb_complex *
         int64_t V = 0;
         for (int v : hv) V += v;
         // the additive head-room scales with the factor too: a retry with twice the factor doubles a tiny complex's room as well
-        size_t Vcap = (size_t)(std::max<int64_t>(V, 4096) * g_capacity_factor), Ecap = (size_t)(std::max<int64_t>(E, 4096) * g_capacity_factor);
+        size_t Vcap = (size_t)(std::max<int64_t>(V, 4096) * capacity_factor()), Ecap = (size_t)(std::max<int64_t>(E, 4096) * capacity_factor());
         int rc = complex_alloc(c, net, Vcap, Ecap);
         if (rc) return rc;
         SkelVertEmit vemit{nullptr, net->meta.marks, net->meta.pre_2s, net->meta.pre_scale, M, remap.p, c->cvert(),
@@ -2430,7 +2432,7 @@ int complex_sync_counts(tnb_complex *c, cudaStream_t s)
         return rc;
     };
     if (sticky & kStickyCapacity)
-        return latch(TNB_ERR_CAPACITY, "work buffers too small for this complex (capacity factor " + std::to_string(g_capacity_factor) + ")");
+        return latch(TNB_ERR_CAPACITY, "work buffers too small for this complex (capacity factor " + std::to_string(capacity_factor()) + ")");
     if (sticky & kStickyNoPlane)
         return latch(TNB_ERR_INVALID, "curve path: a non-axis-aligned edge lies on no earlier plane (the reference exits here, subpoly.py:140-148)");
     if (sticky & kStickyGradientDescent)
@@ -2567,7 +2569,9 @@ template <class K>
 static int cluster_ctas(K kernel)
 {
     if (cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) cudaGetLastError();
+    static const int want = std::getenv("TNB_CLUSTER_CTAS") ? std::atoi(std::getenv("TNB_CLUSTER_CTAS")) : 16;  // 8: twice as many objects side by side
     for (int cs : {16, 8}) {
+        if (cs > want) continue;
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(cs);
         cfg.blockDim = dim3(kClusterThreads);
@@ -2584,6 +2588,7 @@ static int cluster_ctas(K kernel)
 }
 static bool g_long_lists = std::getenv("TNB_NO_LONG_LISTS") == nullptr;  // A/B switch: long partner lists by warps
 static bool g_fused_curve = std::getenv("TNB_NO_FUSED_CURVE") == nullptr;  // A/B switch: curve path step by step
+thread_local int64_t t_cluster_max_items = -1;  // tnb_subpoly_batch: its workers' complexes take the cluster form (>= 0 overrides the global)
 static int64_t g_cluster_max_items = std::getenv("TNB_CLUSTER_MAX_ITEMS") ? std::atoll(std::getenv("TNB_CLUSTER_MAX_ITEMS")) : 0;
 
 // How can the hyperplanes of this complex run?  0 = one step at a time (multi-launch kernels with
@@ -2595,7 +2600,8 @@ int steps_mode(const tnb_net *net, const tnb_complex *c, bool planar)
     if (c->halo.enabled || !g_fused_steps || c->E <= 0) return 0;
     if (!planar && !g_fused_curve) return 0;
     const int64_t items = c->E + c->V;  // may be stale upper bounds: good enough for this choice
-    if (planar && g_cluster_max_items > 0 && items <= g_cluster_max_items) return 2;
+    const int64_t cluster_max = t_cluster_max_items >= 0 ? t_cluster_max_items : g_cluster_max_items;
+    if (planar && cluster_max > 0 && items <= cluster_max) return 2;
     return items <= g_fused_max_items ? 1 : 0;
 }
 
@@ -3386,7 +3392,7 @@ static int from_arrays_impl(const tnb_net *net, const float *d_vertices, int64_t
 {
     tnb_complex *c = new tnb_complex();
     *out = c;
-    int rc = complex_alloc(c, net, (size_t)(std::max<int64_t>(V, 4096) * g_capacity_factor), (size_t)(std::max<int64_t>(E, 4096) * g_capacity_factor));
+    int rc = complex_alloc(c, net, (size_t)(std::max<int64_t>(V, 4096) * capacity_factor()), (size_t)(std::max<int64_t>(E, 4096) * capacity_factor()));
     if (rc) return rc;
     if (V > 0) TNB_CUDA(cudaMemcpyAsync(c->cvert(), d_vertices, (size_t)V * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
     if (E > 0) {

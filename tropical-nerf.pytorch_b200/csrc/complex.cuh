@@ -114,4 +114,7 @@ int launch_region(const tnb_net *net, const float *d_x, const float *d_outputs, 
 int halo_publish_used(tnb_complex *c, int64_t V, const int *used, cudaStream_t s);
 int halo_merge_used(tnb_complex *c, int64_t V, int *used, cudaStream_t s);
 extern double g_capacity_factor;
+extern thread_local double t_capacity_scale;
+double capacity_factor();
+extern thread_local int64_t t_cluster_max_items;  // >= 0: overrides tnb_set_cluster_max_items for the calling thread
 }  // namespace tnb

@@ -12,6 +12,11 @@
 // ranked inside the warp, so the global row order (torch.unique(dim=0) = lexicographic, first
 // element = leader) falls out of one ordered scan over the vertices -- no global sort.
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 
 #include "complex.cuh"
@@ -1313,7 +1318,7 @@ int tnb_subpoly(const tnb_net *net, float size, float eps, int32_t force, int32_
 {
     if (!net || !out) { set_error("tnb_subpoly: null argument"); return TNB_ERR_INVALID; }
     *out = nullptr;
-    const double factor0 = g_capacity_factor;
+    const double scale0 = t_capacity_scale;
     int rc = TNB_OK;
     // The steps run without host syncs; if the device reports that the work arrays were too
     // small (sticky capacity bit), the extraction is simply repeated with twice the head-room.
@@ -1331,10 +1336,145 @@ int tnb_subpoly(const tnb_net *net, float size, float eps, int32_t force, int32_
         if (rc == TNB_OK) rc = tnb_extract_mesh(net, c, eps, out, stream);
         tnb_complex_destroy(c);
         if (rc != TNB_ERR_CAPACITY) break;
-        g_capacity_factor *= 2.0;
+        t_capacity_scale *= 2.0;
     }
-    g_capacity_factor = factor0;
+    t_capacity_scale = scale0;
     return rc;
 }
 
 }  // extern "C"
+
+// ---- many objects in one call ---------------------------------------------------------------------
+// A small extraction is a chain of short kernels with a handful of host decisions in between (sizes of the next
+// arrays): one object cannot fill the GPU, eight can.  The workers below are host threads that live as long as the
+// library, each with a stream of its own; a batch is dealt to them object by object.  Every worker runs the
+// ordinary single-object path (same kernels, same results); complexes small enough for it take the
+// thread-block-cluster form of the persistent step kernel (16 SMs each), so the step loops of the objects in
+// flight are resident side by side.  The caller's stream is a dependency of every worker stream and depends on
+// all of them at the end: to the caller the batch is one stream-ordered operation.
+namespace tnb {
+struct BatchJob {
+    const tnb_net *const *nets = nullptr;
+    tnb_mesh **out = nullptr;
+    int count = 0;
+    float size = 1.2f, eps = 1e-4f;
+    int force = 1, unit = 128;
+    cudaEvent_t ready = nullptr;
+    std::atomic<int> next{0};
+    std::vector<int> rc;
+    std::vector<std::string> err;
+};
+struct BatchPool {
+    std::mutex mu;
+    std::condition_variable cv_work, cv_done;
+    std::vector<std::thread> threads;
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> done_ev;
+    BatchJob *job = nullptr;
+    uint64_t generation = 0;
+    int wanted = 0;     // workers that take part in the current job
+    int running = 0;
+    int device = 0;
+    std::mutex call_mu;  // one batch at a time
+
+    void worker(int w)
+    {
+        cudaSetDevice(device);
+        uint64_t seen = 0;
+        for (;;) {
+            BatchJob *j;
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv_work.wait(lk, [&] { return generation != seen; });
+                seen = generation;
+                if (w >= wanted) continue;
+                j = job;
+            }
+            cudaStream_t s = streams[w];
+            cudaStreamWaitEvent(s, j->ready, 0);
+            t_cluster_max_items = 200000;
+            for (int i = j->next.fetch_add(1); i < j->count; i = j->next.fetch_add(1)) {
+                j->rc[i] = tnb_subpoly(j->nets[i], j->size, j->eps, j->force, j->unit, &j->out[i], (void *)s);
+                if (j->rc[i] != TNB_OK) j->err[i] = tnb_last_error();
+            }
+            t_cluster_max_items = -1;
+            cudaEventRecord(done_ev[w], s);
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (--running == 0) cv_done.notify_all();
+            }
+        }
+    }
+    int ensure(int n)
+    {
+        while ((int)threads.size() < n) {
+            cudaStream_t s;
+            cudaEvent_t e;
+            TNB_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+            TNB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            streams.push_back(s);
+            done_ev.push_back(e);
+            const int w = (int)threads.size();
+            threads.emplace_back([this, w] { worker(w); });
+            threads.back().detach();
+        }
+        return TNB_OK;
+    }
+};
+static BatchPool &batch_pool()
+{
+    static BatchPool *p = new BatchPool;  // never destroyed: its threads wait for work until the process ends
+    return *p;
+}
+}  // namespace tnb
+
+extern "C" int tnb_subpoly_batch(const tnb_net *const *nets, int32_t count, float size, float eps, int32_t force, int32_t unit,
+                                 int32_t in_flight, tnb_mesh **out, int32_t *rcs, void *stream)
+{
+    if (count < 0 || (count > 0 && (!nets || !out))) { set_error("tnb_subpoly_batch: null argument"); return TNB_ERR_INVALID; }
+    for (int i = 0; i < count; ++i) {
+        out[i] = nullptr;
+        if (rcs) rcs[i] = TNB_OK;
+        if (!nets[i]) { set_error("tnb_subpoly_batch: null network"); return TNB_ERR_INVALID; }
+    }
+    if (count == 0) return TNB_OK;
+    if (in_flight <= 0) in_flight = 8;   // 16-SM clusters: nine fit a B200
+    const int workers = std::min<int>(std::min<int>(in_flight, count), 32);
+    cudaStream_t s = (cudaStream_t)stream;
+    BatchPool &bp = batch_pool();
+    std::lock_guard<std::mutex> call(bp.call_mu);
+    int dev = 0;
+    TNB_CUDA(cudaGetDevice(&dev));
+    if (!bp.threads.empty() && dev != bp.device) { set_error("tnb_subpoly_batch: the worker pool belongs to another device"); return TNB_ERR_UNSUPPORTED; }
+    bp.device = dev;
+    int rc = bp.ensure(workers);
+    if (rc != TNB_OK) return rc;
+    BatchJob job;
+    job.nets = nets; job.out = out; job.count = count;
+    job.size = size; job.eps = eps; job.force = force; job.unit = unit;
+    job.rc.assign(count, TNB_OK);
+    job.err.assign(count, std::string());
+    TNB_CUDA(cudaEventCreateWithFlags(&job.ready, cudaEventDisableTiming));
+    TNB_CUDA(cudaEventRecord(job.ready, s));
+    {
+        std::lock_guard<std::mutex> lk(bp.mu);
+        bp.job = &job;
+        bp.wanted = workers;
+        bp.running = workers;
+        ++bp.generation;
+    }
+    bp.cv_work.notify_all();
+    {
+        std::unique_lock<std::mutex> lk(bp.mu);
+        bp.cv_done.wait(lk, [&] { return bp.running == 0; });
+        bp.job = nullptr;
+    }
+    for (int w = 0; w < workers; ++w) cudaStreamWaitEvent(s, bp.done_ev[w], 0);
+    cudaEventDestroy(job.ready);
+    rc = TNB_OK;
+    for (int i = 0; i < count; ++i) {
+        if (rcs) rcs[i] = job.rc[i];
+        if (job.rc[i] != TNB_OK && rc == TNB_OK) { rc = job.rc[i]; set_error("object " + std::to_string(i) + ": " + job.err[i]); }
+    }
+    return rc;
+}

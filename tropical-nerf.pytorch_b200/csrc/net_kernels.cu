@@ -4,6 +4,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <mutex>
+#include <string>
+#include <unordered_map>
 #include <utility>
 #include <vector>
 
@@ -40,6 +42,80 @@ void init_pool_once()
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
     });
+}
+
+// ---- block cache (runtime.cuh) --------------------------------------------------------------------
+static const bool g_block_cache = std::getenv("TNB_NO_BLOCK_CACHE") == nullptr;
+void block_cache_trim();
+static size_t size_class(size_t bytes)
+{
+    if (bytes <= 512) return 512;
+    size_t top = (size_t)1 << (63 - __builtin_clzll((unsigned long long)bytes));  // largest power of two <= bytes
+    const size_t step = top >> 3;
+    return (bytes + step - 1) / step * step;
+}
+struct BlockCache {   // one per process; the lock covers a vector push / pop, never a CUDA call of the steady state
+    struct Key {
+        cudaStream_t s;
+        size_t bytes;
+        bool operator==(const Key &o) const { return s == o.s && bytes == o.bytes; }
+    };
+    struct Hash {
+        size_t operator()(const Key &k) const { return std::hash<const void *>()((const void *)k.s) * 1000003u ^ std::hash<size_t>()(k.bytes); }
+    };
+    std::mutex mu;
+    std::unordered_map<Key, std::vector<void *>, Hash> free_;
+};
+static BlockCache &block_cache()
+{
+    static BlockCache *c = new BlockCache;  // never destroyed: blocks may be released while the process shuts down
+    return *c;
+}
+void *block_acquire(size_t bytes, cudaStream_t s, size_t *got, cudaError_t *err)
+{
+    *err = cudaSuccess;
+    if (!g_block_cache) {
+        void *p = nullptr;
+        *got = bytes;
+        *err = cudaMallocAsync(&p, bytes, s);
+        return *err == cudaSuccess ? p : nullptr;
+    }
+    const size_t cls = size_class(bytes);
+    *got = cls;
+    BlockCache &bc = block_cache();
+    {
+        std::lock_guard<std::mutex> g(bc.mu);
+        auto it = bc.free_.find(BlockCache::Key{s, cls});
+        if (it != bc.free_.end() && !it->second.empty()) {
+            void *p = it->second.back();
+            it->second.pop_back();
+            return p;
+        }
+    }
+    void *p = nullptr;
+    *err = cudaMallocAsync(&p, cls, s);
+    if (*err != cudaSuccess) {   // out of memory with blocks sitting in the cache: give them back and try once more
+        cudaGetLastError();
+        block_cache_trim();
+        *err = cudaMallocAsync(&p, cls, s);
+    }
+    return *err == cudaSuccess ? p : nullptr;
+}
+void block_cache_trim()
+{
+    BlockCache &bc = block_cache();
+    std::lock_guard<std::mutex> g(bc.mu);
+    for (auto &kv : bc.free_) {
+        for (void *q : kv.second) cudaFreeAsync(q, kv.first.s);
+        kv.second.clear();
+    }
+}
+void block_release(void *p, size_t bytes, cudaStream_t s)
+{
+    if (!g_block_cache) { cudaFreeAsync(p, s); return; }
+    BlockCache &bc = block_cache();
+    std::lock_guard<std::mutex> g(bc.mu);
+    bc.free_[BlockCache::Key{s, bytes}].push_back(p);
 }
 
 struct ProfClass {
@@ -299,6 +375,7 @@ int tnb_device_count(void)
 }
 int64_t tnb_launch_count(void) { return g_launches; }
 void tnb_launch_count_reset(void) { g_launches = 0; }
+void tnb_release_cached_blocks(void) { tnb::block_cache_trim(); }
 int tnb_profile_enable(int on) { g_prof_on = on != 0; return TNB_OK; }
 void tnb_profile_reset(void)
 {

@@ -116,6 +116,8 @@ SIGNATURES = {
     "tnb_grid_train_backward_backward": (ctypes.c_int, [_P, _P, _P, _I64, _P, _P, _P, _P, _P, _P]),
     "tnb_launch_count": (_I64, []),
     "tnb_launch_count_reset": (None, []),
+    "tnb_release_cached_blocks": (None, []),
+    "tnb_subpoly_batch": (ctypes.c_int, [ctypes.POINTER(_P), _I32, _F, _F, _I32, _I32, _I32, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_int32), _P]),
     "tnb_profile_enable": (ctypes.c_int, [ctypes.c_int]),
     "tnb_profile_read": (ctypes.c_int, [ctypes.c_int, _P, _P, _P, _P]),
     "tnb_profile_reset": (None, []),
@@ -175,6 +177,19 @@ def profile_read():
         check(lib().tnb_profile_read(i, ctypes.byref(ms), ctypes.byref(n), ctypes.byref(u), ctypes.byref(b)))
         out[name] = (ms.value, n.value, u.value, b.value)
     return out
+
+
+def subpoly_batch(nets, size=1.2, eps=1e-4, force=True, unit=128, in_flight=8):
+    """tnb_subpoly_batch: the whole path for a list of NativeNet in one call -> list of NativeMesh."""
+    require_cuda()
+    n = len(nets)
+    handles = (_P * n)(*[x.handle for x in nets])
+    out = (_P * n)()
+    rcs = (ctypes.c_int32 * n)()
+    rc = lib().tnb_subpoly_batch(handles, n, float(size), float(eps), int(bool(force)), int(unit), int(in_flight), out, rcs, _stream())
+    meshes = [NativeMesh(nets[i], ctypes.c_void_p(out[i])) if out[i] else None for i in range(n)]
+    check(rc)
+    return meshes
 
 
 def curve_intersections(p, q):

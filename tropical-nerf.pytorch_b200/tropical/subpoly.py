@@ -32,8 +32,9 @@ def subpoly(net: Module, d: int, size: float, eps: float = 1e-4, force: bool = F
     Returns (faces, vertices, faces_with_indices): faces [T,3,3] numpy triangle positions,
     vertices [V,3] device tensor, faces_with_indices [T,3] numpy vertex indices.
     force=True is the planar path the reference's entry point uses (train.py:50-51,127);
-    force=False is the curve-approximation path (subpoly.py:120-183 + strict_check); its
-    gradient-descent repair (subpoly_debug.py:121-165) is not built and raises if needed."""
+    force=False is the curve-approximation path (subpoly.py:120-183 + strict_check) with its
+    gradient-descent repair (subpoly_debug.py:121-165); where the repair leaves an intersection off
+    its planes the reference ends the process (subpoly.py:172-174) and this call raises."""
     mesh = net.native().subpoly(size=size, eps=eps, force=force)
     s = mesh.sizes()
     print()
@@ -41,6 +42,18 @@ def subpoly(net: Module, d: int, size: float, eps: float = 1e-4, force: bool = F
     vertices, _, tri, faces, _ = mesh.read()
     out = (faces.cpu().numpy(), vertices, tri.cpu().numpy())
     return out + (mesh,) if return_mesh else out
+
+
+def subpoly_batch(nets, d: int, size: float, eps: float = 1e-4, force: bool = False, in_flight: int = 8):
+    """subpoly() for a list of networks in one call (tnb_subpoly_batch): up to `in_flight` objects are extracted
+    side by side on one GPU.  Not in the reference (it extracts one object per run, train.py:127); every entry of
+    the returned list is what subpoly(net, d, size, eps, force) returns for that network."""
+    meshes = _native.subpoly_batch([n.native() for n in nets], size=size, eps=eps, force=force, in_flight=in_flight)
+    out = []
+    for mesh in meshes:
+        vertices, _, tri, faces, _ = mesh.read()
+        out.append((faces.cpu().numpy(), vertices, tri.cpu().numpy()))
+    return out
 
 
 class _ComplexState:
