@@ -613,8 +613,8 @@ def run_ours(args):
     concurrent = None
     if world == 1 and not slab and planar and args.concurrent > 1:
         K, M = args.concurrent, 12
-        # always the SMALL model (BASELINE configs[1]): objects whose hyperplanes fit one 16-CTA cluster; a large object fills
-        # the GPU by itself (its extraction is a stream of full-size grids) and gains nothing from company
+        # the SMALL model (BASELINE configs[1]): objects whose hyperplanes fit one 16-CTA cluster; the headline workload
+        # itself follows below when it is another one
         ws = w if args.workload.startswith("small") else load_workload("small_sphere")
         net_s = net if ws is w else make_native(ws)
 
@@ -649,6 +649,33 @@ def run_ours(args):
                       "note": "one call, K worker threads x 1 stream inside the library; small complexes run their hyperplanes in one "
                               "16-CTA cluster each (k_steps_cluster); work buffers come from the library's block cache (the stream-ordered "
                               "allocator calls were what serialised the host threads before)"}
+
+        if ws is not w:
+            # the headline workload, 4 in flight: a large extraction is a stream of ~170 launches, many of them far
+            # from filling 148 SMs, so a second and a third object find room next to it
+            Kb, Bb, Mb = 4, 8, 3
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(Bb):
+                step()
+            torch.cuda.synchronize()
+            one_big = Bb / (time.perf_counter() - t1)
+            ms_ = _native.subpoly_batch([net] * Bb, size=1.2, eps=w["eps"], force=True, in_flight=Kb)
+            assert all(m_.sizes()["V"] == sizes["V"] for m_ in ms_)
+            del ms_
+            torch.cuda.synchronize()
+            t1 = time.perf_counter()
+            for _ in range(Mb):
+                ms_ = _native.subpoly_batch([net] * Bb, size=1.2, eps=w["eps"], force=True, in_flight=Kb)
+                del ms_
+            torch.cuda.synchronize()
+            per_s = Bb * Mb / (time.perf_counter() - t1)
+            concurrent["headline_workload"] = {"entry": "tnb_subpoly_batch", "objects_per_call": Bb, "objects_in_flight": Kb,
+                                               "objects_per_s": per_s, "vertices_per_s": per_s * sizes["V"],
+                                               "one_at_a_time_objects_per_s": one_big, "vs_one_at_a_time": per_s / one_big,
+                                               "note": "back to back, no L2 flush between objects (both figures)"}
 
     # ---- CPU baseline (bounded sample on the box's host cores) ----------------------------
     cpu = None
