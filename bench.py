@@ -374,9 +374,9 @@ def run_ours(args):
     class SlabMesh:
         """One object sharded over the ranks by marks-grid slabs and merged (tropical/parallel.py)."""
 
-        def __init__(self, n):
+        def __init__(self, n, phase_ms=False):
             from tropical import parallel
-            self.v, self.t, self.stats = parallel.subpoly_sharded(n, size=1.2, eps=w["eps"])
+            self.v, self.t, self.stats = parallel.subpoly_sharded(n, size=1.2, eps=w["eps"], phase_ms=phase_ms)
 
         def sizes(self):
             return {"V": int(self.v.shape[0]), "T": int(self.t.shape[0]), "P": None}
@@ -501,8 +501,9 @@ def run_ours(args):
         if "slab" in args.strong and planar:
             try:
                 ms_sl, _ = timed(lambda: SlabMesh(net), max(2, args.steps // 2))
-                sm = SlabMesh(net)
+                sm = SlabMesh(net, phase_ms=True)
                 strong["slab_sharded"] = {"ms_per_extraction": ms_sl, "speedup_vs_one_gpu": (ms_total / args.steps) / ms_sl,
+                                          "phase_ms_rank0": sm.stats.get("phase_ms"),
                                           "merged_vertices": sm.sizes()["V"], "merged_triangles": sm.sizes()["T"],
                                           "single_gpu_vertices": ref_sizes["V"], "single_gpu_triangles": ref_sizes["T"],
                                           "near_plane": sm.stats.get("near_plane"),
@@ -535,7 +536,7 @@ def run_ours(args):
     # for the denominator, not a claim that these kernels are bandwidth bound
     bound_notes = {
         "sweep": "fp32 issue / instruction fetch: 1 136 instructions per grid vertex (sdf + input gradient), issue slots 55 % busy, FMA pipe 26 %, "
-                 "stall no_instruction 1.8 warps per issue (100 KB of straight-line code), 128 registers -> 16 warps per SM; HBM traffic is the |sdf| array only",
+                 "stall no_instruction 0.95 warps per issue (113 KB of straight-line code), 168 registers -> 12 warps per SM; HBM traffic is the |sdf| array only",
         "vertex_rows": "fp32 issue + L2 gathers; rows leave through shared memory with coalesced stores",
         "step_front": "new vertices: L2 latency (two dependent gathers per crossed edge, then a network evaluation by 1 thread in ~30)",
         "step_back": "connecting edges: L2 latency (cell header -> segment records, long_scoreboard 4.1 warps per issue) and shuffle traffic of the partner sort",

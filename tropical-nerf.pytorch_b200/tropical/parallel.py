@@ -161,7 +161,7 @@ def _n_chunks(n_marks: int, unit: int) -> int:
     return len(range(0, n_marks, unit - 1)) ** 3
 
 
-def _run_slabs(net, mine, world_size, boxes_of, reduce_max, sum_int, eps, unit, payload, seq0, timeout_ms):
+def _run_slabs(net, mine, world_size, boxes_of, reduce_max, sum_int, eps, unit, payload, seq0, timeout_ms, marks=None):
     """Skeleton, hyperplane steps and face extraction of the slabs `mine` (rank numbers) on the
     current device and stream.  Several slabs per process run in lock step: every slab posts its
     messages before any slab waits for them.
@@ -172,8 +172,16 @@ def _run_slabs(net, mine, world_size, boxes_of, reduce_max, sum_int, eps, unit, 
     left alone in a collective.  From the steps on nothing but the mailboxes connects the ranks, and
     their receive has its own timeout and status word (csrc/halo.cuh).  Returns (meshes, error)."""
     from . import _native
+
+    def mark(name):   # phase boundaries on the current stream (subpoly_sharded(..., phase_ms=True))
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
     planes = slab_planes(net.n_marks, world_size)
     err, sweeps, cs = None, [], []
+    mark("start")
     try:
         sweeps = [net.skeleton_sweep(planes[r][0], planes[r][1], r > 0, r < world_size - 1, unit) for r in mine]
         mg = sweeps[0].max_grad()
@@ -181,7 +189,9 @@ def _run_slabs(net, mine, world_size, boxes_of, reduce_max, sum_int, eps, unit, 
             mg = torch.maximum(mg, sw.max_grad())
     except _native.NativeError as e:
         err, mg = e, torch.zeros(_n_chunks(net.n_marks, unit), dtype=torch.float32, device="cuda")
+    mark("sweep")
     mg = reduce_max(mg)
+    mark("max_grad_all_reduce")
     edges = 0
     if err is None:
         try:
@@ -192,8 +202,10 @@ def _run_slabs(net, mine, world_size, boxes_of, reduce_max, sum_int, eps, unit, 
         except _native.NativeError as e:
             err = e
     del sweeps
+    mark("skeleton_finish")
     FAIL = -(1 << 40)
     total = sum_int(FAIL if err is not None else edges)
+    mark("edge_count_all_reduce")
     if total < 0:      # somebody failed during the set-up: every rank leaves here, together
         return None, (err or _native.NativeError("another rank failed during the set-up of the sharded extraction"))
     if total == 0:
@@ -209,9 +221,11 @@ def _run_slabs(net, mine, world_size, boxes_of, reduce_max, sum_int, eps, unit, 
                     c.step_part(l, h, 1, eps, True)
                 for c in cs:
                     c.step_part(l, h, 2, eps, True)
+        mark("hyperplanes_with_exchanges")
         meshes = [c.extract_mesh_begin(eps) for c in cs]
         for c, m in zip(cs, meshes):
             c.extract_mesh_finish(m)
+        mark("faces")
     except _native.NativeError as e:
         return None, e
     return meshes, None
@@ -287,7 +301,7 @@ def _dist_boxes(payload, group=None):
 
 
 def subpoly_sharded(net, size: float = 1.2, eps: float = 1e-4, unit: int = 128, payload: int = DEFAULT_PAYLOAD,
-                    group=None, gather: bool = True, timeout_ms: int = 2000):
+                    group=None, gather: bool = True, timeout_ms: int = 2000, phase_ms: bool = False):
     """One object sharded over the ranks of `group` by marks-grid slabs (one slab per GPU).  Every
     rank calls this with the same network.  Returns (vertices, triangles, stats): the merged mesh
     on every rank when `gather`, else this rank's slab (vertices, triangles, tags)."""
@@ -313,8 +327,9 @@ def subpoly_sharded(net, size: float = 1.2, eps: float = 1e-4, unit: int = 128, 
         for attempt in range(4):
             _RUNS += 1
             err, msg, part = 0, "", None
+            marks = [] if phase_ms else None
             meshes, e = _run_slabs(net, [me], w, lambda r: boxes, reduce_max, sum_int, eps, unit, payload,
-                                   (_RUNS * 4096) & 0xFFFFFF, timeout_ms)
+                                   (_RUNS * 4096) & 0xFFFFFF, timeout_ms, marks)
             if e is None and meshes is not None:
                 try:
                     part = _read_part(meshes[0])
@@ -338,10 +353,22 @@ def subpoly_sharded(net, size: float = 1.2, eps: float = 1e-4, unit: int = 128, 
         return v, t, {"shared_vertices": 0, "slabs": 1, "hypercube": True}
     if not gather:
         return part[0], part[1], {"tags": part[2], "slabs": w}
+    def mark(name):
+        if marks is not None:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("read_slab_mesh")
     vs, ts, gs = _gather_rows(part[0], group), _gather_rows(part[1], group), _gather_rows(part[2], group)
+    mark("all_gather")
     v, t, stats = merge_slab_meshes(list(zip(vs, ts, gs)))
+    mark("merge")
     stats["slab_vertices"] = [int(x.shape[0]) for x in vs]
     stats["near_plane"] = sum_int(meshes[0].near_plane)
+    if marks is not None:   # this rank's device time from mark to mark (host waits inside a phase count towards it)
+        torch.cuda.synchronize()
+        stats["phase_ms"] = {b[0]: round(a[1].elapsed_time(b[1]), 4) for a, b in zip(marks[:-1], marks[1:])}
     return v, t, stats
 
 
