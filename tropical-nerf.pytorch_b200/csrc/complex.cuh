@@ -115,6 +115,7 @@ int halo_publish_used(tnb_complex *c, int64_t V, const int *used, cudaStream_t s
 int halo_merge_used(tnb_complex *c, int64_t V, int *used, cudaStream_t s);
 extern double g_capacity_factor;
 extern thread_local double t_capacity_scale;
+extern thread_local bool t_no_profile;   // tnb_profile_* timers are skipped on this thread
 double capacity_factor();
 extern thread_local int64_t t_cluster_max_items;  // >= 0: overrides tnb_set_cluster_max_items for the calling thread
 }  // namespace tnb

@@ -1393,6 +1393,7 @@ struct BatchPool {
             cudaStream_t s = streams[w];
             cudaStreamWaitEvent(s, j->ready, 0);
             t_cluster_max_items = 200000;
+            t_no_profile = true;
             for (int i = j->next.fetch_add(1); i < j->count; i = j->next.fetch_add(1)) {
                 j->rc[i] = tnb_subpoly(j->nets[i], j->size, j->eps, j->force, j->unit, &j->out[i], (void *)s);
                 if (j->rc[i] != TNB_OK) j->err[i] = tnb_last_error();

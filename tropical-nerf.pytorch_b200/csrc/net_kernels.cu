@@ -126,11 +126,12 @@ struct ProfClass {
     int64_t launches = 0;
 };
 static bool g_prof_on = false;
+thread_local bool t_no_profile = false;  // the workers of tnb_subpoly_batch: the event timers belong to the calling thread
 static ProfClass g_prof[TNB_PROF_CLASSES];
 bool g_pdl = std::getenv("TNB_NO_PDL") == nullptr;
 void prof_begin(int cls, cudaStream_t s)
 {
-    if (!g_prof_on) return;
+    if (!g_prof_on || t_no_profile) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, s);
@@ -138,13 +139,13 @@ void prof_begin(int cls, cudaStream_t s)
 }
 void prof_add(int cls, int64_t units, int64_t bytes)
 {
-    if (!g_prof_on) return;
+    if (!g_prof_on || t_no_profile) return;
     g_prof[cls].units += units;
     g_prof[cls].bytes += bytes;
 }
 void prof_end(int cls, cudaStream_t s, int64_t units, int64_t bytes)
 {
-    if (!g_prof_on || !g_prof[cls].open) return;
+    if (!g_prof_on || t_no_profile || !g_prof[cls].open) return;
     cudaEvent_t e;
     cudaEventCreate(&e);
     cudaEventRecord(e, s);
