@@ -224,11 +224,31 @@ def test_train_entry_point_runs_end_to_end(tmp_path, monkeypatch):
     """python -m tropical.stanford.train -d sphere -e : fit, extract on the device, write the mesh."""
     from tropical.stanford import train
     monkeypatch.chdir(tmp_path)
-    train.main(["-d", "sphere", "-s", "1", "-c", "-e"])   # the reference's 10 epochs x 50 batches
+    train.main(["-d", "sphere", "-s", "1", "-e"])   # the reference's 10 epochs x 50 batches; without -c the fitted network is saved
     ply = tmp_path / "meshes" / "sphere" / "our_mesh_small_1.ply"
     assert ply.exists()
-    head = ply.read_text().splitlines()[:4]
-    assert head[0] == "ply" and int(head[2].split()[-1]) > 1000   # a real surface came out
+    lines = ply.read_text().splitlines()
+    n_v, n_f = int(lines[2].split()[-1]), int(lines[6].split()[-1])
+    assert lines[0] == "ply" and n_v > 1000   # a real surface came out
+    # ... and it is the mesh the oracle extracts from the network the run saved: same vertices, same triangles
+    import os
+    from oracle import subpoly_ref as R
+    from oracle.trinet import NetParams
+    from tropical.stanford.dataset import StanfordDataset
+    from tropical.stanford.model import Net
+    ckpt = os.path.join(os.path.dirname(train.__file__), "models", "sphere", "sphere_sdf_small_1.pth")
+    try:
+        net = Net(num_layers=3, num_hidden=16, levels=4, r_min=2, r_max=32, T=19)
+        net.load_state_dict(torch.load(ckpt, map_location="cpu"))
+        _, vo, to = R.subpoly(NetParams.from_reference_net(net), force=True)
+    finally:
+        if os.path.exists(ckpt):
+            os.remove(ckpt)   # the next run trains again
+    assert (n_v, n_f) == (vo.shape[0], to.shape[0])
+    body = np.loadtxt(lines[9:9 + n_v], dtype=np.float64)
+    assert np.abs(body * StanfordDataset("sphere").R - vo).max() <= 1e-6     # the .ply is text with 8 significant digits
+    tri = np.loadtxt(lines[9 + n_v:9 + n_v + n_f], dtype=np.int64)[:, 1:]
+    assert np.array_equal(tri, to)
 
 
 def test_mirror_api_matches_native():
