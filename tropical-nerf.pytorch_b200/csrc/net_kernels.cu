@@ -65,6 +65,9 @@ struct BlockCache {   // one per process; the lock covers a vector push / pop, n
     };
     std::mutex mu;
     std::unordered_map<Key, std::vector<void *>, Hash> free_;
+    size_t cached_bytes = 0;   // what sits in free_
+    size_t max_bytes = std::getenv("TNB_BLOCK_CACHE_MAX_GB") ? (size_t)(std::atof(std::getenv("TNB_BLOCK_CACHE_MAX_GB")) * (1ull << 30))
+                                                             : (size_t)64 << 30;   // beyond this a released block goes back to the pool
 };
 static BlockCache &block_cache()
 {
@@ -89,6 +92,7 @@ void *block_acquire(size_t bytes, cudaStream_t s, size_t *got, cudaError_t *err)
         if (it != bc.free_.end() && !it->second.empty()) {
             void *p = it->second.back();
             it->second.pop_back();
+            bc.cached_bytes -= cls;
             return p;
         }
     }
@@ -109,13 +113,21 @@ void block_cache_trim()
         for (void *q : kv.second) cudaFreeAsync(q, kv.first.s);
         kv.second.clear();
     }
+    bc.cached_bytes = 0;
 }
 void block_release(void *p, size_t bytes, cudaStream_t s)
 {
     if (!g_block_cache) { cudaFreeAsync(p, s); return; }
     BlockCache &bc = block_cache();
-    std::lock_guard<std::mutex> g(bc.mu);
-    bc.free_[BlockCache::Key{s, bytes}].push_back(p);
+    {
+        std::lock_guard<std::mutex> g(bc.mu);
+        if (bc.cached_bytes + bytes <= bc.max_bytes) {
+            bc.free_[BlockCache::Key{s, bytes}].push_back(p);
+            bc.cached_bytes += bytes;
+            return;
+        }
+    }
+    cudaFreeAsync(p, s);
 }
 
 struct ProfClass {
