@@ -420,9 +420,16 @@ def run_ours(args):
     prof = _native.profile_read()
     _native.profile_enable(False)
     clocks = sampler.stop() if rank == 0 else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    rank_ms = None
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        # every rank's mean / fastest / slowest step: the headline takes the slowest rank's sum
+        mine = torch.tensor([sum(step_ms) / len(step_ms), min(step_ms), max(step_ms)], dtype=torch.float64, device="cuda")
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        rank_ms = [[round(float(x), 4) for x in r.tolist()] for r in allr]
     ms_total = float(t.item())
     objects = 1 if (slab or sweep_sharded) else world   # slab / sweep mode: ONE object over all ranks (strong scaling)
     value = sizes["V"] * objects * args.steps / (ms_total * 1e-3)
@@ -693,7 +700,7 @@ def run_ours(args):
            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
            "scaling": "strong" if (slab or sweep_sharded) else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
            "config": shared_config(w, planar, sizes["V"], sizes["T"]),
-           "run": {"polygons": sizes["P"], "objects_per_step": objects, "l2": "flushed (512 MiB write) between timed steps",
+           "run": {"polygons": sizes["P"], "objects_per_step": objects, "rank_ms_mean_min_max": rank_ms, "l2": "flushed (512 MiB write) between timed steps",
                    "extraction_s": ms_total / args.steps * 1e-3,
                    "sharding": ("one object cut into %d marks-grid slabs, one per GPU; per-step exchange through peer mailboxes, "
                                 "all-gather + merge inside the timed region" % world) if slab else
