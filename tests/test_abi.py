@@ -48,6 +48,13 @@ def test_no_cpu_fallback():
     import tropical.subpoly as sp
     with pytest.raises(_native.NativeError):
         sp.subpoly(net, 3, 1.2, force=True)
+    with pytest.raises(_native.NativeError):
+        sp.subpoly_batch([net, net], 3, 1.2, force=True)
+    from tropical import subpoly_debug as dbg
+    z = torch.zeros
+    with pytest.raises(_native.NativeError):   # an edge off its planes: the repair has no CPU route either
+        dbg.deal_with_gradient_descent(torch.ones(1, dtype=torch.bool), torch.ones(1, 2), z(1, 2, 3), 1e-4, z(1, dtype=torch.bool), 5,
+                                       z(1, 2, dtype=torch.long), torch.full((1, 3), 0.5), net)
 
 
 def test_net_create_validates_arguments():
