@@ -3280,7 +3280,8 @@ static int steps_stream_impl(const tnb_net *net, tnb_complex *c, const int32_t *
         prof_begin(TNB_PROF_PAIRS, s);
         TNB_CUDA(launch_pdl(k_sd_pair_copy, dim3(kSMs * 16), dim3(256), 0, s, sa));
         TNB_LAUNCH_CHECK();
-        TNB_CUDA(launch_pdl(k_sd_pair_long, dim3(kSMs * 2), dim3(kSortWarps * 32), 0, s, sa));
+        static const int long_ctas = std::getenv("TNB_PAIR_LONG_CTAS") ? std::atoi(std::getenv("TNB_PAIR_LONG_CTAS")) : 2;  // CTAs per SM (A/B)
+        TNB_CUDA(launch_pdl(k_sd_pair_long, dim3(kSMs * long_ctas), dim3(kSortWarps * 32), 0, s, sa));
         TNB_LAUNCH_CHECK();
         prof_end(TNB_PROF_PAIRS, s, 0);
         if ((rc = cells_clear(1, sa.cnt + C_CAND, cand_ub, (int2 *)sa.head, sa.cslot, s))) return rc;

@@ -1050,7 +1050,8 @@ static int extract_finish_impl(const tnb_net *net, tnb_complex *c, tnb_mesh *m, 
     TNB_CUDA(is_long.reserve((size_t)Vs));
     TNB_CUDA(long_list.reserve((size_t)Vs));
     TNB_CUDA(wide_list.reserve((size_t)Vs));
-    const unsigned gwide = kSMs * 4;  // the wide list is short (its length stays on the device): a fixed grid strides over it
+    static const int wide_ctas = std::getenv("TNB_WIDE_ROW_CTAS") ? std::atoi(std::getenv("TNB_WIDE_ROW_CTAS")) : 4;  // CTAs per SM (A/B)
+    const unsigned gwide = kSMs * wide_ctas;  // the wide list is short (its length stays on the device): a fixed grid strides over it
     TNB_CUDA(cudaMemsetAsync(is_long.p, 0, (size_t)Vs, s));
     // fast pass: every vertex, rows in shared memory
     prof_begin(TNB_PROF_FACE_ROWS, s);
