@@ -1591,7 +1591,11 @@ __global__ void __launch_bounds__(256) k_pair_copy(const int *__restrict__ cand,
         if (i < c && c <= kCachedPartners) edges_out[poff[a] + i] = make_int2(cand[a], pcache[t]);
     }
 }
-// a warp per long list: stream the neighbourhood again, keys into shared memory, bitonic sort, write
+// a warp per long list: stream the neighbourhood again, keys into shared memory, bitonic sort, write.  A launch lasts
+// as long as its longest list (there are fewer lists than warps: more CTAs change nothing, profiles/round2_notes.md), and
+// for a list of several hundred keys that is the sort: lists of more than kWarpSortMax keys are sorted by the whole CTA
+// once its warps have gathered theirs (a stage costs n / 256 compare-exchanges per thread instead of n / 32).
+constexpr int kWarpSortMax = 256;
 __device__ __forceinline__ void pair_write_long_seg_body(const int *__restrict__ long_list, int n_long, const int *__restrict__ cand,
                                                          const uint64_t *__restrict__ sig, const int2 *__restrict__ cells,
                                                          const tnb_bucket_rec *__restrict__ recs, int dim, uint64_t colmask,
@@ -1600,31 +1604,69 @@ __device__ __forceinline__ void pair_write_long_seg_body(const int *__restrict__
 {
     __shared__ int s_keys[kSortWarps][kLongSortMax];
     __shared__ int s_incl[kSortWarps][32], s_base[kSortWarps][32];
+    __shared__ int s_cnt[kSortWarps], s_va[kSortWarps], s_off[kSortWarps];  // lists left to the CTA (count 0: none)
+    constexpr int NT = kSortWarps * 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int li = blockIdx.x * kSortWarps + warp; li < n_long; li += gridDim.x * kSortWarps) {
-        const int a = long_list[li], c = pcount[a], va = cand[a];
-        int2 *dst = edges_out + poff[a];
-        int *keys = s_keys[warp];
-        const bool in_smem = c <= kLongSortMax;
-        const PartnerQuery q = partner_query(va, sig);
-        int found = 0;
-        stream_partners(q, cells, recs, dim, colmask, s_incl[warp], s_base[warp], [&](bool hit, int vb) {
-            const unsigned ball = __ballot_sync(0xffffffffu, hit);
-            if (hit) {
-                const int pos = found + __popc(ball & ((1u << lane) - 1u));
-                if (in_smem) keys[pos] = vb; else dst[pos].y = vb;
+    for (int first = blockIdx.x * kSortWarps; first < n_long; first += gridDim.x * kSortWarps) {  // CTA-uniform trips
+        const int li = first + warp;
+        int left = 0;
+        if (li < n_long) {
+            const int a = long_list[li], c = pcount[a], va = cand[a];
+            int2 *dst = edges_out + poff[a];
+            int *keys = s_keys[warp];
+            const bool in_smem = c <= kLongSortMax;
+            const PartnerQuery q = partner_query(va, sig);
+            int found = 0;
+            stream_partners(q, cells, recs, dim, colmask, s_incl[warp], s_base[warp], [&](bool hit, int vb) {
+                const unsigned ball = __ballot_sync(0xffffffffu, hit);
+                if (hit) {
+                    const int pos = found + __popc(ball & ((1u << lane) - 1u));
+                    if (in_smem) keys[pos] = vb; else dst[pos].y = vb;
+                }
+                found += __popc(ball);
+            });
+            __syncwarp();
+            if (in_smem) {
+                int n = 32;
+                while (n < c) n <<= 1;
+                for (int i = c + lane; i < n; i += 32) keys[i] = 0x7fffffff;
+                __syncwarp();
+                if (n <= kWarpSortMax) {
+                    for (int k = 2; k <= n; k <<= 1)
+                        for (int j = k >> 1; j > 0; j >>= 1) {
+                            for (int i = lane; i < n; i += 32) {
+                                const int p = i ^ j;
+                                if (p > i) {
+                                    const int x = keys[i], y = keys[p];
+                                    const bool up = (i & k) == 0;
+                                    if ((x > y) == up) { keys[i] = y; keys[p] = x; }
+                                }
+                            }
+                            __syncwarp();
+                        }
+                    for (int i = lane; i < c; i += 32) dst[i] = make_int2(va, keys[i]);
+                } else {
+                    left = c;
+                    if (lane == 0) { s_va[warp] = va; s_off[warp] = poff[a]; }
+                }
+            } else {  // longer than the shared buffer (never seen): one lane sorts in place in HBM
+                if (lane == 0) {
+                    thread_sort(&dst[0].y, c, 2);
+                    for (int i = 0; i < c; ++i) dst[i].x = va;
+                }
             }
-            found += __popc(ball);
-        });
-        __syncwarp();
-        if (in_smem) {
+        }
+        if (lane == 0) s_cnt[warp] = left;
+        __syncthreads();
+        for (int w = 0; w < kSortWarps; ++w) {
+            const int c = s_cnt[w];
+            if (c == 0) continue;  // CTA uniform
             int n = 32;
             while (n < c) n <<= 1;
-            for (int i = c + lane; i < n; i += 32) keys[i] = 0x7fffffff;
-            __syncwarp();
+            int *keys = s_keys[w];
             for (int k = 2; k <= n; k <<= 1)
                 for (int j = k >> 1; j > 0; j >>= 1) {
-                    for (int i = lane; i < n; i += 32) {
+                    for (int i = threadIdx.x; i < n; i += NT) {
                         const int p = i ^ j;
                         if (p > i) {
                             const int x = keys[i], y = keys[p];
@@ -1632,16 +1674,13 @@ __device__ __forceinline__ void pair_write_long_seg_body(const int *__restrict__
                             if ((x > y) == up) { keys[i] = y; keys[p] = x; }
                         }
                     }
-                    __syncwarp();
+                    __syncthreads();
                 }
-            for (int i = lane; i < c; i += 32) dst[i] = make_int2(va, keys[i]);
-        } else {  // longer than the shared buffer (never seen): one lane sorts in place in HBM
-            if (lane == 0) {
-                thread_sort(&dst[0].y, c, 2);
-                for (int i = 0; i < c; ++i) dst[i].x = va;
-            }
+            int2 *dst = edges_out + s_off[w];
+            const int va = s_va[w];
+            for (int i = threadIdx.x; i < c; i += NT) dst[i] = make_int2(va, keys[i]);
         }
-        __syncwarp();
+        __syncthreads();  // the next trip's gathers overwrite the keys
     }
 }
 __global__ void __launch_bounds__(kSortWarps * 32) k_pair_write_long_seg(const int *__restrict__ long_list, const int *__restrict__ cnt,
