@@ -43,17 +43,20 @@ def build(force=False, verbose=False):
     headers.append(os.path.join(HERE, "..", "include", "tropical_b200.h"))
     headers.append(os.path.abspath(__file__))
     nvcc = _nvcc()
-    objs, rebuilt = [], False
+    objs, jobs = [], []
     for src in SOURCES:
         path = os.path.join(CSRC, src)
         if not os.path.exists(path):
             continue
         obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
         if force or _stale(obj, [path] + headers):
-            cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj]
-            subprocess.check_call(cmd)
-            rebuilt = True
+            jobs.append([nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", path, "-o", obj])
         objs.append(obj)
+    rebuilt = bool(jobs)
+    if jobs:   # the translation units are independent: compile them side by side (complex.cu alone takes minutes)
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=len(jobs)) as pool:
+            list(pool.map(subprocess.check_call, jobs))
     if rebuilt or not os.path.exists(LIB):
         subprocess.check_call([nvcc, "-shared", "-o", LIB] + objs + ["-lcudart"])
     return LIB
