@@ -620,8 +620,8 @@ def run_ours(args):
             torch.cuda.empty_cache()
 
     # ---- several objects in flight on ONE GPU (outside the timed region; N=1 only) ---------
-    # K host threads, one CUDA stream each; the hyperplanes of every object run inside ONE
-    # thread-block cluster (16 SMs), so up to 8 objects' step loops are resident side by side.
+    # One call of tnb_subpoly_batch: K worker threads of the library, one CUDA stream each; the hyperplanes of
+    # every small object run inside ONE thread-block cluster (16 SMs), so their step loops are resident side by side.
     concurrent = None
     if world == 1 and not slab and planar and args.concurrent > 1:
         K, M = args.concurrent, 12
